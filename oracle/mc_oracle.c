@@ -1,0 +1,603 @@
+/*
+ * mc_oracle.c -- CPU restatement of MetaCell's balanced cell-graph + resampled co-clustering path.
+ *
+ * THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load it.  The product path
+ * (metacell_b200 + libmcb200.so) never calls into this file and has no CPU fallback.
+ *
+ * PARITY UNPINNED: the reference (/root/reference, tanaylab/metacell R package) holds no tests,
+ * golden vectors or fixtures for this path, and its arithmetic lives in the external `tgstat`
+ * package (CRAN, unpinned in DESCRIPTION:51, absent from this container).  Every function below
+ * cites the reference R line it restates; where the behaviour is tgstat's and therefore
+ * unobservable here, the choice made is written down ("DECISION").
+ *
+ * All indices are 0-based.  Plain C11 + OpenMP, fp64 where R is fp64.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Philox4x32-10 (Salmon et al., SC'11) -- the counter-based generator both sides use so that
+ * host-supplied seeds give identical draws on CPU and GPU (north_star: "host-supplied RNG seeds").
+ * ---------------------------------------------------------------------------------------- */
+void orc_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr_in[0], c1 = ctr_in[1], c2 = ctr_in[2], c3 = ctr_in[3];
+    uint32_t k0 = key_in[0], k1 = key_in[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+#define ORC_TAG_DOWNSAMP 0x4453u   /* 'DS' */
+#define ORC_TAG_COVER    0x4743u   /* 'GC' */
+#define ORC_STREAM_SEED  1u
+#define ORC_STREAM_PERM  2u
+
+static uint64_t rng_u64(uint64_t seed, uint32_t stream, uint32_t a, uint32_t b)
+{
+    uint32_t ctr[4] = {a, b, stream, ORC_TAG_COVER};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t o[4];
+    orc_philox4x32_10(ctr, key, o);
+    return (uint64_t)o[0] | ((uint64_t)o[1] << 32);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * quickselect helpers
+ * ---------------------------------------------------------------------------------------- */
+static int cmp_u64(const void* a, const void* b)
+{
+    uint64_t x = *(const uint64_t*)a, y = *(const uint64_t*)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/* k-th smallest (0-based) of a[0..n); permutes a. */
+static uint64_t kth_smallest_u64(uint64_t* a, size_t n, size_t k)
+{
+    int64_t lo = 0, hi = (int64_t)n - 1;
+    while (lo < hi) {
+        uint64_t piv = a[lo + (hi - lo) / 2];
+        int64_t i = lo, j = hi;
+        while (i <= j) {
+            while (a[i] < piv) ++i;
+            while (a[j] > piv) --j;
+            if (i <= j) { uint64_t t = a[i]; a[i] = a[j]; a[j] = t; ++i; --j; }
+        }
+        if ((int64_t)k <= j) hi = j;
+        else if ((int64_t)k >= i) lo = i;
+        else break;
+    }
+    return a[k];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A1. Down-sampling depth rule.  R/scmat.r:399-407:
+ *     min(round(quantile(tot, 0.5)), max(750, round(quantile(tot, 0.05))))
+ * quantile = R default type 7; round = R's round-half-even (base R semantics).
+ * ---------------------------------------------------------------------------------------- */
+static double r_quantile7(const double* sorted, int64_t n, double prob)
+{
+    double h = (double)(n - 1) * prob;
+    int64_t lo = (int64_t)floor(h);
+    int64_t hi = lo + 1 < n ? lo + 1 : n - 1;
+    return sorted[lo] + (h - (double)lo) * (sorted[hi] - sorted[lo]);
+}
+static int cmp_f64(const void* a, const void* b)
+{
+    double x = *(const double*)a, y = *(const double*)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+double orc_downsamp_depth(const int64_t* tot, int64_t n)
+{
+    if (n <= 0) return 0.0;
+    double* s = (double*)malloc(sizeof(double) * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) s[i] = (double)tot[i];
+    qsort(s, (size_t)n, sizeof(double), cmp_f64);
+    double q50 = nearbyint(r_quantile7(s, n, 0.5));   /* default rounding mode: half-even */
+    double q05 = nearbyint(r_quantile7(s, n, 0.05));
+    free(s);
+    double m = q05 > 750.0 ? q05 : 750.0;
+    return q50 < m ? q50 : m;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A2. scm_downsamp.  R/utils.r:30-69.
+ *   - cells with colSums < n are dropped (:34, compared against the raw n);
+ *   - each kept cell: sample(rep(1:m, times=v), size=n, replace=F) then tabulate (:36-39),
+ *     i.e. a uniformly random floor(n)-subset of the cell's UMIs, counted per gene.
+ * DECISION (SURVEY App. A2 `philox_keys`): R's Mersenne-Twister stream (re-seeded with the
+ * constant 19 for every chunk, :49-51) is not reproduced.  UMI t of cell c (t = position in
+ * rep(1:m,times=v), CSC storage order) gets key Philox(seed; t>>2, c)[t&3]; the d UMIs with the
+ * smallest (key, t) are kept.  Same distribution as sample(replace=F); order independent.
+ * p: CSC column pointers [ncells+1]; x: counts per stored entry.
+ * out_x: down-sampled count per stored entry (same sparsity pattern, zeros allowed; all zero for
+ *        dropped cells); kept[c] = 1 iff colSum >= n.
+ * ---------------------------------------------------------------------------------------- */
+int orc_downsample(int64_t ncells, const int64_t* p, const uint32_t* x, double n, uint64_t seed,
+                   uint32_t* out_x, uint8_t* kept)
+{
+    if (!(n >= 1.0)) return 1;
+    const int64_t d = (int64_t)floor(n);
+    int err = 0;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t c = 0; c < ncells; ++c) {
+        int64_t tot = 0;
+        for (int64_t e = p[c]; e < p[c + 1]; ++e) tot += x[e];
+        if ((double)tot < n) {
+            kept[c] = 0;
+            for (int64_t e = p[c]; e < p[c + 1]; ++e) out_x[e] = 0;
+            continue;
+        }
+        kept[c] = 1;
+        uint64_t* keys = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)tot);
+        uint64_t* work = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)tot);
+        if (!keys || !work) { err = 2; free(keys); free(work); continue; }
+        uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+        for (int64_t t = 0; t < tot; t += 4) {
+            uint32_t ctr[4] = {(uint32_t)(t >> 2), (uint32_t)c, (uint32_t)((uint64_t)c >> 32), ORC_TAG_DOWNSAMP};
+            uint32_t o[4];
+            orc_philox4x32_10(ctr, key, o);
+            for (int q = 0; q < 4 && t + q < tot; ++q)
+                keys[t + q] = ((uint64_t)o[q] << 32) | (uint64_t)(uint32_t)(t + q);
+        }
+        memcpy(work, keys, sizeof(uint64_t) * (size_t)tot);
+        uint64_t thr = kth_smallest_u64(work, (size_t)tot, (size_t)(d - 1));
+        int64_t t = 0;
+        for (int64_t e = p[c]; e < p[c + 1]; ++e) {
+            uint32_t cnt = 0;
+            for (uint32_t q = 0; q < x[e]; ++q, ++t) cnt += (keys[t] <= thr);
+            out_x[e] = cnt;
+        }
+        free(keys); free(work);
+    }
+    return err;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A3 + A4. gset_get_feat_mat row subset (R/gset.r:192-197) followed by the bknn transform
+ * log2(1 + k_nonz_exp * u) (R/cgraph_knn.r:13-14, k from inst/config/metacell_params.yaml:44),
+ * then per-cell standardisation so that cor(i,j) = sum_g z[g,i] z[g,j]  (what tgs_cor_knn's
+ * Pearson correlation computes, R/utils.r:119).
+ * feat_map[gene] = feature row (0..G-1) or -1.  Z is [ncells][G] row-major fp64.
+ * DECISION (SURVEY App. A4 `degenerate_policy=no_edges`): a cell whose feature vector has zero
+ * variance has NA correlations in R (R/cgraph_knn_mcnorm.r:25); here valid[c]=0, its Z row is 0
+ * and it takes no part in the kNN stage.  Degenerate <=> no non-zero feature entry or ss<1e-20.
+ * ---------------------------------------------------------------------------------------- */
+int orc_features(int64_t ncells, const int64_t* p, const int32_t* ridx, const uint32_t* x,
+                 const int32_t* feat_map, int32_t G, double k_nonz, double* Z, uint8_t* valid)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < ncells; ++c) {
+        double* z = Z + (size_t)c * (size_t)G;
+        for (int32_t g = 0; g < G; ++g) z[g] = 0.0;
+        double sum = 0.0;
+        int64_t nnz = 0;
+        for (int64_t e = p[c]; e < p[c + 1]; ++e) {
+            int32_t f = feat_map[ridx[e]];
+            if (f < 0 || x[e] == 0) continue;
+            double v = log2(1.0 + k_nonz * (double)x[e]);
+            z[f] = v; sum += v; ++nnz;
+        }
+        double mu = sum / (double)G;
+        double ss = 0.0;
+        for (int32_t g = 0; g < G; ++g) { double dlt = z[g] - mu; ss += dlt * dlt; }
+        if (nnz == 0 || ss < 1e-20) {
+            valid[c] = 0;
+            for (int32_t g = 0; g < G; ++g) z[g] = 0.0;
+            continue;
+        }
+        valid[c] = 1;
+        double inv = 1.0 / sqrt(ss);
+        for (int32_t g = 0; g < G; ++g) z[g] = (z[g] - mu) * inv;
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A5. tgs_cor_knn(x, y = x, knn = Kc)  (call site R/utils.r:119; output schema
+ * col1,col2,cor,rank pinned by R/atlas.r:282,477,585; self is rank 1, R/atlas.r:475-476).
+ * Z: [M][G] standardised rows (valid cells only).  For rows [row_begin,row_end) returns the
+ * Kc' = min(Kc, M) columns with the largest correlation, ordered by (cor desc, col asc).
+ * DECISION: the self match is forced to rank 1 with cor = 1 (so duplicates of a cell cannot
+ * displace it); ties between equal correlations go to the lower column index
+ * (`cor_tie = lower_index_first`).  Unused slots (M < Kc) hold col = -1.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct { double c; int32_t j; } cand_t;
+static inline int cand_before(const cand_t* a, const cand_t* b)
+{   /* a ranks ahead of b */
+    return a->c > b->c || (a->c == b->c && a->j < b->j);
+}
+static int cmp_cand(const void* a, const void* b)
+{
+    const cand_t* x = (const cand_t*)a; const cand_t* y = (const cand_t*)b;
+    if (cand_before(x, y)) return -1;
+    if (cand_before(y, x)) return 1;
+    return 0;
+}
+/* partial selection: after return the k best (by cand_before) occupy a[0..k) in any order */
+static void select_best(cand_t* a, int64_t n, int64_t k)
+{
+    int64_t lo = 0, hi = n - 1;
+    if (k >= n) return;
+    while (lo < hi) {
+        cand_t piv = a[lo + (hi - lo) / 2];
+        int64_t i = lo, j = hi;
+        while (i <= j) {
+            while (cand_before(&a[i], &piv)) ++i;
+            while (cand_before(&piv, &a[j])) --j;
+            if (i <= j) { cand_t t = a[i]; a[i] = a[j]; a[j] = t; ++i; --j; }
+        }
+        if (k - 1 <= j) hi = j;
+        else if (k - 1 >= i) lo = i;
+        else break;
+    }
+}
+
+#define ORC_RB 16     /* rows per block   */
+#define ORC_CB 256    /* columns per block */
+int orc_cor_knn(int64_t M, int32_t G, const double* Z, int32_t Kc, int64_t row_begin, int64_t row_end,
+                int32_t* knn_col, double* knn_cor)
+{
+    if (Kc <= 0 || M <= 0) return 1;
+    const int64_t kk = Kc < M ? Kc : M;
+    int err = 0;
+    const int64_t nrb = (row_end - row_begin + ORC_RB - 1) / ORC_RB;
+#pragma omp parallel
+    {
+        double* C  = (double*)malloc(sizeof(double) * ORC_RB * (size_t)M);
+        double* Bt = (double*)malloc(sizeof(double) * (size_t)G * ORC_CB);
+        double* Cb = (double*)malloc(sizeof(double) * ORC_RB * ORC_CB);
+        cand_t* cd = (cand_t*)malloc(sizeof(cand_t) * (size_t)M);
+        if (!C || !Bt || !Cb || !cd) err = 2;
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t rb = 0; rb < nrb; ++rb) {
+            if (err) continue;
+            const int64_t i0 = row_begin + rb * ORC_RB;
+            const int64_t ni = (i0 + ORC_RB <= row_end) ? ORC_RB : row_end - i0;
+            for (int64_t j0 = 0; j0 < M; j0 += ORC_CB) {
+                const int64_t nj = (j0 + ORC_CB <= M) ? ORC_CB : M - j0;
+                for (int64_t j = 0; j < nj; ++j) {
+                    const double* zj = Z + (size_t)(j0 + j) * (size_t)G;
+                    for (int32_t g = 0; g < G; ++g) Bt[(size_t)g * ORC_CB + j] = zj[g];
+                }
+                for (int64_t q = 0; q < ORC_RB * ORC_CB; ++q) Cb[q] = 0.0;
+                for (int32_t g = 0; g < G; ++g) {
+                    const double* b = Bt + (size_t)g * ORC_CB;
+                    for (int64_t i = 0; i < ni; ++i) {
+                        const double a = Z[(size_t)(i0 + i) * (size_t)G + g];
+                        double* ci = Cb + (size_t)i * ORC_CB;
+                        for (int64_t j = 0; j < nj; ++j) ci[j] += a * b[j];
+                    }
+                }
+                for (int64_t i = 0; i < ni; ++i)
+                    memcpy(C + (size_t)i * (size_t)M + j0, Cb + (size_t)i * ORC_CB, sizeof(double) * (size_t)nj);
+            }
+            for (int64_t i = 0; i < ni; ++i) {
+                const int64_t row = i0 + i;
+                const double* ci = C + (size_t)i * (size_t)M;
+                for (int64_t j = 0; j < M; ++j) { cd[j].c = ci[j]; cd[j].j = (int32_t)j; }
+                cd[row].c = 2.0;                       /* self sentinel: always rank 1 */
+                select_best(cd, M, kk);
+                qsort(cd, (size_t)kk, sizeof(cand_t), cmp_cand);
+                int32_t* oc = knn_col + (size_t)(row - row_begin) * (size_t)Kc;
+                double*  ov = knn_cor + (size_t)(row - row_begin) * (size_t)Kc;
+                for (int64_t r = 0; r < kk; ++r) { oc[r] = cd[r].j; ov[r] = (cd[r].j == row) ? 1.0 : cd[r].c; }
+                for (int64_t r = kk; r < Kc; ++r) { oc[r] = -1; ov[r] = 0.0; }
+            }
+        }
+        free(C); free(Bt); free(Cb); free(cd);
+    }
+    return err;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A6. tgs_graph(x_knn, knn = K, k_expand, k_beta)  (call site R/utils.r:120).  The only in-tree
+ * statement of the rule is cormat_to_balanced_knn, R/cgraph_knn_mcnorm.r:48-81:
+ *   keep pair iff  K*K*k_expand - rank(i,j)*rank(j,i) > 0            (:66-68, strict)
+ *   per node keep the k_beta*K incoming edges with the best score      (:70-71)
+ *   per node keep the K outgoing edges with the best score              (:73-74)
+ * weights are rank fractions 1-(place-1)/K as every consumer assumes (R/cgraph_knn.r:46,
+ * R/mc_confusion.r:26).
+ * DECISIONS: s(i,j) = rank(i,j)*rank(j,i), ranks 1-based positions in the Kc
+ * lists (absent => edge dropped); `thresh_strict` (default 1) uses s < K*K*k_expand; ties on s
+ * are broken by the other node's index, ascending (`sym_tie`); self edges dropped unless
+ * keep_self.  In-prune first (per target j: sources ordered by (s, i)), then out-prune (per
+ * source i: targets ordered by (s, j)).
+ * Output: out_deg[i] <= K, out_dst[i][place], out_s[i][place] (place 0-based, sorted).
+ * ---------------------------------------------------------------------------------------- */
+static int32_t rank_in_list(const int32_t* scol, const int32_t* srank, int32_t n, int32_t target)
+{
+    int32_t lo = 0, hi = n;
+    while (lo < hi) { int32_t mid = (lo + hi) >> 1; if (scol[mid] < target) lo = mid + 1; else hi = mid; }
+    return (lo < n && scol[lo] == target) ? srank[lo] : 0;
+}
+int orc_balance(int64_t M, int32_t Kc, const int32_t* knn_col, int32_t K, int32_t k_expand, int32_t k_beta,
+                int thresh_strict, int keep_self, int32_t* out_deg, int32_t* out_dst, int32_t* out_s)
+{
+    const int64_t smax = (int64_t)K * K * k_expand;
+    const int64_t kin = (int64_t)K * k_beta;
+    /* per-row copies sorted by column, carrying the rank */
+    int32_t* scol  = (int32_t*)malloc(sizeof(int32_t) * (size_t)M * Kc);
+    int32_t* srank = (int32_t*)malloc(sizeof(int32_t) * (size_t)M * Kc);
+    int32_t* nrow  = (int32_t*)malloc(sizeof(int32_t) * (size_t)M);
+    uint32_t* sym  = (uint32_t*)calloc((size_t)M * Kc, sizeof(uint32_t));   /* s per (i,rank), 0 = not mutual */
+    uint64_t* thr_in = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)M);
+    if (!scol || !srank || !nrow || !sym || !thr_in) return 2;
+#pragma omp parallel
+    {
+        uint64_t* tmp = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)Kc);
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < M; ++i) {
+            int32_t n = 0;
+            for (int32_t r = 0; r < Kc; ++r) {
+                int32_t j = knn_col[(size_t)i * Kc + r];
+                if (j < 0) continue;
+                tmp[n++] = ((uint64_t)(uint32_t)j << 32) | (uint32_t)(r + 1);
+            }
+            qsort(tmp, (size_t)n, sizeof(uint64_t), cmp_u64);
+            for (int32_t q = 0; q < n; ++q) {
+                scol[(size_t)i * Kc + q]  = (int32_t)(tmp[q] >> 32);
+                srank[(size_t)i * Kc + q] = (int32_t)(tmp[q] & 0xffffffffu);
+            }
+            nrow[i] = n;
+        }
+        /* mutual scores + in-degree threshold */
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t i = 0; i < M; ++i) {
+            int32_t n = 0;
+            for (int32_t r = 0; r < Kc; ++r) {
+                int32_t j = knn_col[(size_t)i * Kc + r];
+                if (j < 0) continue;
+                if (j == i && !keep_self) continue;
+                int32_t rji = (j == i) ? (r + 1) : rank_in_list(scol + (size_t)j * Kc, srank + (size_t)j * Kc, nrow[j], (int32_t)i);
+                if (!rji) continue;
+                int64_t s = (int64_t)(r + 1) * rji;
+                if (thresh_strict ? !(s < smax) : !(s <= smax)) continue;
+                sym[(size_t)i * Kc + r] = (uint32_t)s;
+                tmp[n++] = ((uint64_t)s << 32) | (uint32_t)j;     /* incoming edge j -> i keyed (s, source) */
+            }
+            if (n > kin) {
+                qsort(tmp, (size_t)n, sizeof(uint64_t), cmp_u64);
+                thr_in[i] = tmp[kin - 1];
+            } else thr_in[i] = UINT64_MAX;
+        }
+        /* out-degree prune */
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t i = 0; i < M; ++i) {
+            int32_t n = 0;
+            for (int32_t r = 0; r < Kc; ++r) {
+                uint32_t s = sym[(size_t)i * Kc + r];
+                if (!s) continue;
+                int32_t j = knn_col[(size_t)i * Kc + r];
+                uint64_t inkey = ((uint64_t)s << 32) | (uint32_t)i;        /* edge i -> j seen from target j */
+                if (inkey > thr_in[j]) continue;
+                tmp[n++] = ((uint64_t)s << 32) | (uint32_t)j;
+            }
+            qsort(tmp, (size_t)n, sizeof(uint64_t), cmp_u64);
+            if (n > K) n = K;
+            out_deg[i] = n;
+            for (int32_t q = 0; q < n; ++q) {
+                out_dst[(size_t)i * K + q] = (int32_t)(tmp[q] & 0xffffffffu);
+                out_s[(size_t)i * K + q]   = (int32_t)(tmp[q] >> 32);
+            }
+            for (int32_t q = n; q < K; ++q) { out_dst[(size_t)i * K + q] = -1; out_s[(size_t)i * K + q] = 0; }
+        }
+        free(tmp);
+    }
+    free(scol); free(srank); free(nrow); free(sym); free(thr_in);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A7. One graph cover on a node sample  -- tgs_graph_cover(_resample) (call sites
+ * R/coclust_graph_cov.r:41, R/mc_graphcov.r:27; cluster 0 = outlier R/mc_graphcov.r:28).
+ * tgstat is absent: the algorithm follows the MetaCell paper's Methods (Baran et al. 2019) as
+ * recalled in SURVEY App. A7; every unverifiable point is a DECISION:
+ *   weights: fixed point, wfix = max(1, round(w * 65536)) so that sums are exact integers and
+ *            CPU/GPU agree bit for bit regardless of accumulation order;
+ *   seeding: f(v) = #uncovered sampled out-neighbours; while some uncovered v has f >= min_size:
+ *            draw v with probability f^3 / sum(f^3) over eligible v (node-index order, draw =
+ *            Philox64(seed, iter) mod total), new cluster = v + its uncovered out-neighbours;
+ *   sweeps : visit sampled nodes in a keyed Feistel permutation; score(v,k) =
+ *            w_out(v,k) * w_in(v,k) / size(k)^2 (fp64, correctly rounded ops only); the current
+ *            cluster's score is multiplied by cooling^max(0, sweep - burn_in); move to the argmax
+ *            (ties -> lower cluster id); candidates need w_in>0 and w_out>0; no candidate => stay;
+ *            stop when a sweep moves nothing or after max_sweeps;
+ *   uncovered nodes join clusters through the same sweep rule; never covered => outlier (-1);
+ *   clusters smaller than min_size are kept ("smaller MC may be returned", R/mc_graphcov.r:6).
+ * mc_out[v]: -2 not sampled, -1 outlier, >=0 cluster id.
+ * ---------------------------------------------------------------------------------------- */
+static inline uint32_t feistel_f(uint32_t x, uint32_t k)
+{
+    x ^= k; x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; return x;
+}
+/* bijection on [0, n): balanced 4-round Feistel over 2*hb bits with cycle walking */
+static uint32_t perm_index(uint32_t t, uint32_t n, uint32_t hb, const uint32_t rk[4])
+{
+    const uint32_t mask = (1u << hb) - 1u;
+    uint32_t x = t;
+    do {
+        uint32_t L = x >> hb, R = x & mask;
+        for (int r = 0; r < 4; ++r) { uint32_t nl = R; R = L ^ (feistel_f(R, rk[r]) & mask); L = nl; }
+        x = (L << hb) | R;
+    } while (x >= n);
+    return x;
+}
+static uint32_t half_bits_for(uint32_t n)
+{
+    uint32_t b = 1; while ((1ull << (2 * b)) < (uint64_t)n) ++b; return b;
+}
+
+int orc_graph_cover(int32_t N, const int64_t* optr, const int32_t* odst, const uint32_t* ow,
+                    const int64_t* iptr, const int32_t* isrc, const uint32_t* iw,
+                    int32_t n_s, const int32_t* sample, int32_t min_size, double cooling, int32_t burn_in,
+                    uint64_t seed, int32_t max_sweeps, int32_t* mc, int32_t* n_sweeps_out)
+{
+    int32_t* f = (int32_t*)calloc((size_t)N, sizeof(int32_t));
+    int32_t ncl_cap = n_s / (min_size > 0 ? min_size + 1 : 1) + 2;
+    int32_t* size = (int32_t*)calloc((size_t)ncl_cap, sizeof(int32_t));
+    int64_t* wout = (int64_t*)calloc((size_t)ncl_cap, sizeof(int64_t));
+    int64_t* win  = (int64_t*)calloc((size_t)ncl_cap, sizeof(int64_t));
+    int32_t* touched = (int32_t*)malloc(sizeof(int32_t) * (size_t)ncl_cap * 2);
+    if (!f || !size || !wout || !win || !touched) return 2;
+    for (int32_t v = 0; v < N; ++v) mc[v] = -2;
+    for (int32_t q = 0; q < n_s; ++q) mc[sample[q]] = -1;
+    for (int32_t q = 0; q < n_s; ++q) {
+        int32_t v = sample[q], c = 0;
+        for (int64_t e = optr[v]; e < optr[v + 1]; ++e) c += (mc[odst[e]] == -1);
+        f[v] = c;
+    }
+    int32_t ncl = 0;
+    for (uint32_t iter = 0;; ++iter) {
+        uint64_t total = 0;
+        for (int32_t v = 0; v < N; ++v)
+            if (mc[v] == -1 && f[v] >= min_size && f[v] > 0) total += (uint64_t)f[v] * f[v] * f[v];
+        if (total == 0) break;
+        uint64_t r = rng_u64(seed, ORC_STREAM_SEED, iter, 0) % total;
+        int32_t pick = -1; uint64_t cum = 0;
+        for (int32_t v = 0; v < N; ++v) {
+            if (mc[v] == -1 && f[v] >= min_size && f[v] > 0) {
+                cum += (uint64_t)f[v] * f[v] * f[v];
+                if (cum > r) { pick = v; break; }
+            }
+        }
+        if (ncl >= ncl_cap) return 3;
+        int32_t k = ncl++;
+        /* claim seed + uncovered sampled out-neighbours; every newly covered node lowers the
+           f of its in-neighbours */
+        mc[pick] = k; size[k] = 1;
+        for (int64_t e = iptr[pick]; e < iptr[pick + 1]; ++e) f[isrc[e]]--;
+        for (int64_t e = optr[pick]; e < optr[pick + 1]; ++e) {
+            int32_t u = odst[e];
+            if (mc[u] != -1) continue;
+            mc[u] = k; size[k]++;
+            for (int64_t e2 = iptr[u]; e2 < iptr[u + 1]; ++e2) f[isrc[e2]]--;
+        }
+    }
+    /* sweeps */
+    const uint32_t hb = half_bits_for((uint32_t)n_s);
+    double factor = 1.0;
+    int32_t sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        if (sweep > burn_in) factor = factor * cooling;
+        uint32_t rk[4];
+        for (int r = 0; r < 4; r += 2) {
+            uint64_t w = rng_u64(seed, ORC_STREAM_PERM, (uint32_t)sweep, (uint32_t)(r >> 1));
+            rk[r] = (uint32_t)w; rk[r + 1] = (uint32_t)(w >> 32);
+        }
+        int32_t moved = 0;
+        for (int32_t t = 0; t < n_s; ++t) {
+            int32_t v = sample[perm_index((uint32_t)t, (uint32_t)n_s, hb, rk)];
+            int32_t nt = 0;
+            for (int64_t e = optr[v]; e < optr[v + 1]; ++e) {
+                int32_t k = mc[odst[e]];
+                if (k < 0) continue;
+                if (wout[k] == 0 && win[k] == 0) touched[nt++] = k;
+                wout[k] += ow[e];
+            }
+            for (int64_t e = iptr[v]; e < iptr[v + 1]; ++e) {
+                int32_t k = mc[isrc[e]];
+                if (k < 0) continue;
+                if (wout[k] == 0 && win[k] == 0) touched[nt++] = k;
+                win[k] += iw[e];
+            }
+            int32_t best = -1; double best_score = 0.0;
+            for (int32_t q = 0; q < nt; ++q) {
+                int32_t k = touched[q];
+                if (wout[k] > 0 && win[k] > 0) {
+                    double sz = (double)size[k];
+                    double sc = (double)(wout[k] * win[k]) / (sz * sz);
+                    if (k == mc[v]) sc = sc * factor;
+                    if (best < 0 || sc > best_score || (sc == best_score && k < best)) { best = k; best_score = sc; }
+                }
+            }
+            for (int32_t q = 0; q < nt; ++q) { wout[touched[q]] = 0; win[touched[q]] = 0; }
+            if (best >= 0 && best != mc[v]) {
+                if (mc[v] >= 0) size[mc[v]]--;
+                mc[v] = best; size[best]++; ++moved;
+            }
+        }
+        if (moved == 0) { ++sweep; break; }
+    }
+    if (n_sweeps_out) *n_sweeps_out = sweep;
+    free(f); free(size); free(wout); free(win); free(touched);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * A8. tgs_graph_cover_resample(..., method = "full")  (R/coclust_graph_cov.r:41): n_resamp
+ * covers on host-supplied node samples; cnt[a][b] (a < b) += 1 for every pair placed in the same
+ * cluster, nsamp[a] += 1 for every sampled node (fields co_cluster / samples, R/coclust.r:39-41,
+ * R/coclust_graph_cov.r:55).  DECISION `count_diag` off: consumers drop node1 == node2
+ * (R/mc_from_coclust.r:241).  cnt is a dense [N][N] uint32, upper triangle used.
+ * ---------------------------------------------------------------------------------------- */
+int orc_coclust(int32_t N, const int64_t* optr, const int32_t* odst, const uint32_t* ow,
+                const int64_t* iptr, const int32_t* isrc, const uint32_t* iw,
+                int32_t n_resamp, int32_t n_s, const int32_t* samples, const uint64_t* seeds,
+                int32_t min_size, double cooling, int32_t burn_in, int32_t max_sweeps,
+                uint32_t* cnt, int32_t* nsamp, int32_t* sweeps_out)
+{
+    int err = 0;
+#pragma omp parallel
+    {
+        int32_t* mc = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+        int32_t* order = (int32_t*)malloc(sizeof(int32_t) * (size_t)N);
+        int32_t* start = (int32_t*)malloc(sizeof(int32_t) * ((size_t)N + 2));
+#pragma omp for schedule(dynamic, 1)
+        for (int32_t r = 0; r < n_resamp; ++r) {
+            const int32_t* S = samples + (size_t)r * n_s;
+            int32_t nsw = 0;
+            int rc = orc_graph_cover(N, optr, odst, ow, iptr, isrc, iw, n_s, S, min_size, cooling, burn_in,
+                                     seeds[r], max_sweeps, mc, &nsw);
+            if (rc) { err = rc; continue; }
+            if (sweeps_out) sweeps_out[r] = nsw;
+            int32_t ncl = 0;
+            for (int32_t v = 0; v < N; ++v) if (mc[v] + 1 > ncl) ncl = mc[v] + 1;
+            for (int32_t k = 0; k <= ncl; ++k) start[k] = 0;
+            for (int32_t v = 0; v < N; ++v) if (mc[v] >= 0) start[mc[v] + 1]++;
+            for (int32_t k = 0; k < ncl; ++k) start[k + 1] += start[k];
+            {   /* members in ascending node order per cluster */
+                int32_t* fill = (int32_t*)malloc(sizeof(int32_t) * ((size_t)ncl + 1));
+                for (int32_t k = 0; k < ncl; ++k) fill[k] = start[k];
+                for (int32_t v = 0; v < N; ++v) if (mc[v] >= 0) order[fill[mc[v]]++] = v;
+                free(fill);
+            }
+            for (int32_t k = 0; k < ncl; ++k)
+                for (int32_t a = start[k]; a < start[k + 1]; ++a)
+                    for (int32_t b = a + 1; b < start[k + 1]; ++b) {
+                        uint32_t* ptr = cnt + (size_t)order[a] * N + order[b];
+#pragma omp atomic
+                        *ptr += 1;
+                    }
+            for (int32_t q = 0; q < n_s; ++q) {
+#pragma omp atomic
+                nsamp[S[q]] += 1;
+            }
+        }
+        free(mc); free(order); free(start);
+    }
+    return err;
+}
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
