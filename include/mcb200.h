@@ -1,0 +1,142 @@
+/*
+ * mcb200.h -- C ABI of libmcb200.so: the B200 (sm_100a) implementation of MetaCell's balanced
+ * cell-graph + resampled co-clustering hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int status codes,
+ * no C++ / torch / R types.  The R `.Call` glue in r/ and the Python host mirror in metacell_b200/
+ * bind exactly these symbols.  Citations are to the reference tree (tanaylab/metacell, R package):
+ * the arithmetic these entry points replace lives in tgstat, which metacell reaches through
+ *     R/utils.r:119   tgs_cor_knn(x, y = x, knn = K * k_expand)           -> mcb_cgraph_knn
+ *     R/utils.r:120   tgs_graph(x_knn, knn, k_expand, k_beta)             -> mcb_cgraph_mutual / _prune
+ *     R/utils.r:30-69 scm_downsamp(umis, n)                               -> mcb_csc_downsample
+ *     R/scmat.r:399-407 scm_which_downsamp_n(mat)                         -> mcb_downsamp_depth
+ *     R/gset.r:151-214 gset_get_feat_mat + R/cgraph_knn.r:13-14 log2(1+7u) -> mcb_cgraph_create
+ *     R/cgraph_knn.r:10-25 mcell_add_cgraph_from_mat_bknn                 -> mcb_cgraph_bknn (one shot)
+ *     R/coclust_graph_cov.r:41 tgs_graph_cover_resample(method = "full")  -> mcb_coclust_*
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; mcb_last_error() then holds a
+ *     message (thread local).  No exception or CUDA error crosses this boundary.
+ *   - all indices are 0-based (the R glue adds 1); cell / gene counts are int64 / int32.
+ *   - "host" pointers are ordinary (ideally pinned) memory owned by the caller, never retained.
+ *     "dev" pointers are CUDA device memory on the context's device.
+ *   - handles own their device memory; destroy them with the matching *_destroy / *_free.
+ *   - the library never falls back to the CPU: without a usable sm_100 device every call fails.
+ */
+#ifndef MCB200_H
+#define MCB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mcb_ctx     mcb_ctx;      /* device + stream + memory pool                    */
+typedef struct mcb_csc     mcb_csc;      /* device-resident genes x cells CSC count matrix   */
+typedef struct mcb_cgraph  mcb_cgraph;   /* one balanced-graph build (features .. edges)     */
+typedef struct mcb_coclust mcb_coclust;  /* one resampled co-clustering run                  */
+
+int         mcb_version(void);
+const char* mcb_last_error(void);
+
+/* ---- context ------------------------------------------------------------------------------ */
+int   mcb_ctx_create(int device, mcb_ctx** out);
+void  mcb_ctx_destroy(mcb_ctx* ctx);
+int   mcb_ctx_sync(mcb_ctx* ctx);
+void* mcb_ctx_stream(mcb_ctx* ctx);                   /* cudaStream_t all kernels are launched on */
+/* options: "gemm_impl" 0 = tcgen05 (default) | 1 = SIMT fp32 validation kernel;
+ *          "profile"   1 = record per-stage CUDA-event timings (mcb_ctx_timings);
+ *          "keep_self" 1 = keep self edges in the balanced graph (default 0);
+ *          "thresh_strict" 1 = s < K*K*k_expand (default), 0 = s <= ...                        */
+int   mcb_ctx_set_option(mcb_ctx* ctx, const char* key, int64_t value);
+/* stage timings of the calls since the last mcb_ctx_timings_reset (needs option profile=1).
+ * Writes up to cap entries; *n receives the number available.  names[i] are static strings.  */
+int   mcb_ctx_timings(mcb_ctx* ctx, int cap, const char** names, float* ms, int64_t* launches, int* n);
+int   mcb_ctx_timings_reset(mcb_ctx* ctx);
+
+/* ---- A1: scm_which_downsamp_n (R/scmat.r:399-407); pure host arithmetic ------------------- */
+int mcb_downsamp_depth(const int64_t* col_sums, int64_t ncells, double* depth);
+
+/* ---- CSC matrix (the dgCMatrix slots of tgScMat@mat: @p, @i, @x, @Dim) --------------------- */
+int  mcb_csc_upload(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* p, const int32_t* i,
+                    const double* x, mcb_csc** out);                       /* host -> device      */
+int  mcb_csc_wrap_device(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* dev_p,
+                         const int32_t* dev_i, const uint32_t* dev_x, mcb_csc** out); /* no copy  */
+void mcb_csc_free(mcb_csc* m);
+int  mcb_csc_col_sums(mcb_ctx* ctx, const mcb_csc* m, int64_t* host_tot);  /* colSums(mat@mat)    */
+/* A2: scm_downsamp(umis, n) (R/utils.r:30-69).  Cells with colSum < n are dropped (kept = 0, all
+ * counts 0) unless add_non_dsamp != 0, in which case they keep their raw counts (R/gset.r:179-187).
+ * Every kept cell gets a uniformly random floor(n)-subset of its UMIs (Philox keys).
+ * The result shares @p/@i with the input; only the counts differ.                              */
+int  mcb_csc_downsample(mcb_ctx* ctx, const mcb_csc* m, double n, uint64_t seed, int add_non_dsamp,
+                        mcb_csc** out);
+int  mcb_csc_download(mcb_ctx* ctx, const mcb_csc* m, double* host_x, uint8_t* host_kept);
+
+/* ---- A3..A7: balanced K-nn cell graph ------------------------------------------------------- */
+/* features: rows feat_rows[0..G) of the matrix (gene-set order, R/gset.r:192-197), log2(1+k_nonz*u)
+ * (R/cgraph_knn.r:13-14), per-cell standardisation.  Zero-variance cells are excluded.          */
+int  mcb_cgraph_create(mcb_ctx* ctx, const mcb_csc* m, const int32_t* feat_rows, int32_t G, double k_nonz,
+                       mcb_cgraph** out);
+/* tgs_cor_graph(x = feat, ...) (R/utils.r:115): x is the dense genes x cells matrix the caller
+ * already transformed, column-major as in R (one contiguous vector of G doubles per cell).      */
+int  mcb_cgraph_create_dense(mcb_ctx* ctx, const double* x, int32_t G, int64_t ncells, mcb_cgraph** out);
+void mcb_cgraph_destroy(mcb_cgraph* g);
+int  mcb_cgraph_num_valid(const mcb_cgraph* g, int64_t* M);
+int  mcb_cgraph_valid_cells(mcb_cgraph* g, int32_t* host_cell_of_row /* [M] */);
+int  mcb_cgraph_features(mcb_cgraph* g, float* host_z /* [M][G] */);      /* test / debug export */
+/* A5: tgs_cor_knn(x, y = x, knn = K*k_expand) for the rows owned by `rank` of `nranks`
+ * (contiguous split of the M valid cells).  Self is rank 1 (R/atlas.r:475-476).                */
+int  mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks);
+/* the full [nranks * rows_per_rank][Kc] int32 kNN column buffer on the device; this rank's block
+ * starts at row rank * rows_per_rank.  The host plumbing all-gathers it in place (NCCL).       */
+int  mcb_cgraph_knn_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank, int32_t* Kc);
+int  mcb_cgraph_download_knn(mcb_cgraph* g, int32_t* host_col /* [rows][Kc] */, float* host_cor);
+int  mcb_cgraph_knn_stats(mcb_cgraph* g, int64_t* n_fallback_rows, int64_t* n_candidates, int32_t* cap,
+                          int32_t* n_sample_cols);
+/* A6 step 1: mutual rank products + per-target in-degree cut (K*k_beta) for the owned rows.   */
+int  mcb_cgraph_mutual(mcb_cgraph* g, int32_t k_beta);
+/* the full [nranks * rows_per_rank] uint64 in-degree threshold buffer (all-gathered in place)  */
+int  mcb_cgraph_thr_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank);
+/* A6 steps 2-4: out-degree cut (K) and weights 1 - (place-1)/K for the owned rows.             */
+int  mcb_cgraph_prune(mcb_cgraph* g, int64_t* n_edges);
+/* edges of the owned rows as (mc1, mc2, w) (R/cgraph_knn.r:22), original 0-based cell ids,
+ * ordered by (source, place).                                                                  */
+int  mcb_cgraph_edges(mcb_cgraph* g, int32_t* host_src, int32_t* host_dst, double* host_w);
+/* test hook: dense correlation block C[a_rows][b_rows] of the first rows of Z through one kernel:
+ * impl 0 = tcgen05 3-pass split-TF32, 2 = tcgen05 1-pass TF32, 1 = SIMT fp32.  Call before _mutual. */
+int  mcb_cgraph_debug_cor(mcb_cgraph* g, int impl, int64_t a_rows, int64_t b_rows, float* host_c);
+
+/* one shot, single GPU, host in / host out: what mcell_add_cgraph_from_mat_bknn's body becomes.
+ * dsamp != 0: depth rule + downsample + add back small cells first (R/cgraph_knn.r:12).
+ * Outputs are library-allocated host arrays; release each with mcb_free.                       */
+int  mcb_cgraph_bknn(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* p, const int32_t* i,
+                     const double* x, const int32_t* feat_rows, int32_t G, int32_t K, int32_t k_expand,
+                     int32_t k_beta, double k_nonz, int dsamp, uint64_t seed, int64_t* n_edges,
+                     int32_t** src, int32_t** dst, double** w, int64_t* n_valid_cells);
+void mcb_free(void* host_ptr);
+
+/* ---- A8: tgs_graph_cover_resample(..., method = "full") ------------------------------------ */
+/* Graph = directed weighted edges (0-based).  samples: [n_resamp][n_s] node ids and one uint64
+ * seed per resample, both host-supplied.  Runs the resamples r with r % nranks == rank and
+ * accumulates cnt[a][b] (a < b) and nsamp[a] on the device.                                     */
+int  mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst,
+                     const double* w, int32_t n_resamp, int32_t n_s, const int32_t* samples,
+                     const uint64_t* seeds, int32_t min_mc_size, double cooling, int32_t burn_in,
+                     int32_t max_sweeps, int32_t rank, int32_t nranks, mcb_coclust** out);
+void mcb_coclust_destroy(mcb_coclust* c);
+/* device buffers for the NCCL reduce: uint32 cnt[N][N] (upper triangle) and int32 nsamp[N]     */
+int  mcb_coclust_buffers(mcb_coclust* c, void** dev_cnt, void** dev_nsamp);
+/* per-resample cluster assignment of this rank's resamples (debug / parity): mc[r][v] in
+ * {-2 not sampled, -1 outlier, >= 0 cluster}, and sweeps[r]                                    */
+int  mcb_coclust_assignments(mcb_coclust* c, int32_t* host_mc /* [n_local][N] */, int32_t* host_sweeps,
+                             int32_t* n_local);
+/* co_cluster rows with cnt > 0 (node1 < node2, sorted) + samples[N] (R/coclust.r:39-41)        */
+int  mcb_coclust_extract(mcb_coclust* c, int64_t* n_pairs);
+int  mcb_coclust_pairs(mcb_coclust* c, int32_t* host_node1, int32_t* host_node2, int32_t* host_cnt,
+                       int32_t* host_samples);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCB200_H */

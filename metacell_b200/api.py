@@ -1,0 +1,382 @@
+"""Host-side mirror of the reference's R interface for the bknn-cgraph + co-clustering path.
+
+The reference is an R package; R is not available in this image, so the host layer that R would
+provide is written here in Python with the reference's names, argument meaning and error behaviour
+(`stop("MC-ERR: ...")` -> McbError("MC-ERR: ...")).  The R `.Call` glue a maintainer would add is in
+r/ and INTEGRATION.md.  All arithmetic goes through libmcb200.so (include/mcb200.h); nothing here
+falls back to numpy or the oracle.
+
+Mirrored entry points (reference file:line):
+    scdb_init / scdb_add_* / scdb_*            R/scdb.r:100-131, 292-320, 400-428
+    get_param / set_param                      inst/config/metacell_params.yaml (keys of the path)
+    tgScMat, tgGeneSets, tgCellGraph, tgCoClust  R/scmat.r, R/gset.r, R/cgraph.r:11-42, R/coclust.r:12-48
+    scm_which_downsamp_n                       R/scmat.r:399-407
+    scm_downsamp                               R/utils.r:30-69
+    gset_get_feat_mat                          R/gset.r:151-214
+    tgs_cor_knn / tgs_graph / tgs_cor_graph    tgstat calls at R/utils.r:115-123
+    mcell_add_cgraph_from_mat_bknn             R/cgraph_knn.r:10-25
+    tgs_graph_cover_resample                   tgstat call at R/coclust_graph_cov.r:41
+    mcell_coclust_from_graph_resamp            R/coclust_graph_cov.r:13-58
+"""
+import os
+import pickle
+import sys
+
+import numpy as np
+
+from . import _lib
+from ._lib import McbError
+
+# ------------------------------------------------------------------------------------------------
+# parameters (inst/config/metacell_params.yaml:12,20,41,44,49-51,53-54)
+# ------------------------------------------------------------------------------------------------
+_PARAMS = {
+    "mc_cores": 16,
+    "mc_rseed": 42,
+    "scm_n_downsamp_gstat": None,
+    "scm_k_nonz_exp": 7,
+    "scm_balance_graph_k_alpha": 10,
+    "scm_balance_graph_k_beta": 3,
+    "scm_balance_graph_k_expand": 10,
+    "scm_tgs_clust_cool": 1.05,
+    "scm_tgs_clust_burn_in": 10,
+}
+
+
+def get_param(key):
+    if key not in _PARAMS:
+        raise McbError(f"MC-ERR: unknown parameter {key}")
+    return _PARAMS[key]
+
+
+def set_param(key, value):
+    if key not in _PARAMS:
+        raise McbError(f"MC-ERR: unknown parameter {key}")
+    _PARAMS[key] = value
+
+
+def _message(msg):
+    print(msg, file=sys.stderr)
+
+
+# ------------------------------------------------------------------------------------------------
+# containers
+# ------------------------------------------------------------------------------------------------
+class tgScMat:
+    """Sparse UMI matrix, genes x cells, stored as the dgCMatrix slots (reference R/scmat.r)."""
+
+    def __init__(self, indptr, indices, data, genes=None, cells=None, ngenes=None):
+        self.indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+        self.indices = np.ascontiguousarray(indices, dtype=np.int32)
+        self.data = np.ascontiguousarray(data, dtype=np.float64)
+        self.ncells = self.indptr.size - 1
+        self.ngenes = int(ngenes if ngenes is not None else (len(genes) if genes is not None else self.indices.max() + 1))
+        self.genes = list(genes) if genes is not None else [f"g{i}" for i in range(self.ngenes)]
+        self.cells = list(cells) if cells is not None else [f"c{i}" for i in range(self.ncells)]
+
+
+class tgGeneSets:
+    """Named gene set; `gene_set` maps gene name -> set id, in insertion order (reference R/gset.r)."""
+
+    def __init__(self, gene_set, description=""):
+        self.gene_set = dict(gene_set)
+        self.description = description
+
+
+class tgCellGraph:
+    """Cell similarity graph (reference R/cgraph.r:11-42): `edges` holds mc1, mc2 (integer codes into
+    cell_names, the R factor codes minus one) and w; `nodes` are the cells that carry an edge."""
+
+    def __init__(self, edges, cell_names):
+        for k in ("mc1", "mc2", "w"):
+            if k not in edges:
+                raise McbError("MC-ERR: cell graph edges need columns mc1, mc2, w")
+        self.cell_names = list(cell_names)
+        self.edges = {k: np.asarray(edges[k]) for k in ("mc1", "mc2", "w")}
+        nodes = np.unique(np.concatenate([self.edges["mc1"], self.edges["mc2"]])) if len(self.edges["mc1"]) else np.zeros(0, np.int64)
+        self.nodes = [self.cell_names[i] for i in nodes]
+        if len(self.cell_names) != len(self.nodes):       # R/cgraph.r:36-39
+            _message(f"sim graph is missing {len(self.cell_names) - len(self.nodes)} nodes, out of {len(self.cell_names)}")
+
+
+class tgCoClust:
+    """Co-clustering statistics (reference R/coclust.r:12-48)."""
+
+    def __init__(self, graph_id, coclust, n_samp):
+        if scdb_cgraph(graph_id) is None:
+            raise McbError(f"MC-ERR: graph id {graph_id} is missing when constructing a coclust object")
+        for k in ("node1", "node2", "cnt"):
+            if k not in coclust:
+                raise McbError("MC-ERR: coclust table must have columns node1, node2, cnt")
+        self.graph_id = graph_id
+        self.coclust = {k: np.asarray(coclust[k]) for k in ("node1", "node2", "cnt")}
+        self.n_samp = np.asarray(n_samp)
+
+
+# ------------------------------------------------------------------------------------------------
+# scdb (reference R/scdb.r): in-memory cache + one file per object, "<base>/<type>.<id>.Rda" there,
+# "<base>/<type>.<id>.pkl" here
+# ------------------------------------------------------------------------------------------------
+_SCDB = {"base": None, "cache": {}}
+
+
+def scdb_init(base_dir, force_reinit=False):
+    if not os.path.isdir(base_dir):
+        raise McbError(f"MC-ERR: cannot initialize scdb to non existing directory {base_dir}")
+    if _SCDB["base"] is not None and not force_reinit and _SCDB["base"] != base_dir:
+        raise McbError("MC-ERR: scdb already initialized, use force_reinit to switch directory")
+    _SCDB["base"] = base_dir
+    _SCDB["cache"] = {}
+
+
+def _scdb_fn(objt, oid):
+    return os.path.join(_SCDB["base"], f"{objt}.{oid}.pkl")
+
+
+def _scdb_add(objt, oid, obj):
+    _SCDB["cache"][(objt, oid)] = obj
+    if _SCDB["base"] is not None:
+        with open(_scdb_fn(objt, oid), "wb") as fh:
+            pickle.dump(obj, fh, protocol=4)
+
+
+def _scdb_get(objt, oid):
+    if (objt, oid) in _SCDB["cache"]:
+        return _SCDB["cache"][(objt, oid)]
+    if _SCDB["base"] is not None and os.path.exists(_scdb_fn(objt, oid)):
+        with open(_scdb_fn(objt, oid), "rb") as fh:
+            obj = pickle.load(fh)
+        _SCDB["cache"][(objt, oid)] = obj
+        return obj
+    return None
+
+
+def scdb_add_mat(oid, mat): _scdb_add("mat", oid, mat)
+def scdb_mat(oid): return _scdb_get("mat", oid)
+def scdb_add_gset(oid, gset): _scdb_add("gset", oid, gset)
+def scdb_gset(oid): return _scdb_get("gset", oid)
+def scdb_add_cgraph(oid, cgraph): _scdb_add("cgraph", oid, cgraph)
+def scdb_cgraph(oid): return _scdb_get("cgraph", oid)
+def scdb_add_coclust(oid, coc): _scdb_add("coclust", oid, coc)
+def scdb_coclust(oid): return _scdb_get("coclust", oid)
+
+
+# ------------------------------------------------------------------------------------------------
+# A1 / A2 / A3
+# ------------------------------------------------------------------------------------------------
+def _ctx(ctx=None):
+    return ctx if ctx is not None else _lib.default_context()
+
+
+def _upload(mat, ctx):
+    return _lib.Csc.upload(ctx, mat.ngenes, mat.indptr, mat.indices, mat.data)
+
+
+def scm_which_downsamp_n(mat, ctx=None):
+    """reference R/scmat.r:399-407"""
+    n = get_param("scm_n_downsamp_gstat")
+    if n is not None:
+        return n
+    ctx = _ctx(ctx)
+    csc = _upload(mat, ctx)
+    tot = csc.col_sums()
+    csc.free()
+    return _lib.downsamp_depth(tot)
+
+
+def scm_downsamp(umis, n, ctx=None):
+    """reference R/utils.r:30-69: returns the down-sampled tgScMat holding only the cells with at least
+    n UMIs (column sums == floor(n))."""
+    ctx = _ctx(ctx)
+    csc = _upload(umis, ctx)
+    ds = csc.downsample(float(n), get_param("mc_rseed"), add_non_dsamp=False)
+    x, kept = ds.download()
+    ds.free()
+    csc.free()
+    return _subset_cells(umis, x, np.nonzero(kept)[0])
+
+
+def _subset_cells(mat, data, cols):
+    lens = np.diff(mat.indptr)
+    keep_entry = np.repeat(np.isin(np.arange(mat.ncells), cols), lens) & (data > 0)
+    col_of_entry = np.repeat(np.arange(mat.ncells), lens)[keep_entry]
+    new_lens = np.bincount(col_of_entry, minlength=mat.ncells)[cols]
+    indptr = np.concatenate([[0], np.cumsum(new_lens)])
+    return tgScMat(indptr, mat.indices[keep_entry], data[keep_entry], genes=mat.genes,
+                   cells=[mat.cells[c] for c in cols], ngenes=mat.ngenes)
+
+
+def _feature_rows(gset, mat):
+    """intersect(names(gset@gene_set), rownames(umis)), gene-set order (reference R/gset.r:192-197)"""
+    row_of = {g: i for i, g in enumerate(mat.genes)}
+    rows = [row_of[g] for g in gset.gene_set.keys() if g in row_of]
+    if len(rows) < 2:
+        raise McbError("MC-ERR: less than 2 feature genes of the gene set are present in the matrix")
+    return np.asarray(rows, dtype=np.int32)
+
+
+def gset_get_feat_mat(gset_id, mat_id, downsamp=False, add_non_dsamp=False, downsample_n=None, ctx=None):
+    """reference R/gset.r:151-214; returns the host feature matrix (tgScMat restricted to feature rows)."""
+    gset, mat = scdb_gset(gset_id), scdb_mat(mat_id)
+    if gset is None:
+        raise McbError(f"MC-ERR: non existing gset {gset_id} when trying to get feature matrix")
+    if mat is None:
+        raise McbError(f"MC-ERR: non existing mat {mat_id} when trying to get feature matrix")
+    ctx = _ctx(ctx)
+    data, cols = mat.data, np.arange(mat.ncells)
+    if downsamp:
+        n = downsample_n if downsample_n is not None else scm_which_downsamp_n(mat, ctx)
+        _message(f"will downsample the matrix, N= {n}")
+        csc = _upload(mat, ctx)
+        ds = csc.downsample(float(n), get_param("mc_rseed"), add_non_dsamp=bool(add_non_dsamp))
+        data, kept = ds.download()
+        ds.free()
+        csc.free()
+        if not add_non_dsamp:
+            cols = np.nonzero(kept)[0]
+    sub = _subset_cells(mat, data, cols)
+    rows = _feature_rows(gset, mat)
+    # row subset on the host: a container operation, not path arithmetic
+    pos = np.full(mat.ngenes, -1, dtype=np.int64)
+    pos[rows] = np.arange(rows.size)
+    keep = pos[sub.indices] >= 0
+    col_of_entry = np.repeat(np.arange(sub.ncells), np.diff(sub.indptr))[keep]
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(col_of_entry, minlength=sub.ncells))])
+    return tgScMat(indptr, pos[sub.indices[keep]].astype(np.int32), sub.data[keep],
+                   genes=[mat.genes[r] for r in rows], cells=sub.cells, ngenes=rows.size)
+
+
+# ------------------------------------------------------------------------------------------------
+# A5 / A6: the tgstat trio
+# ------------------------------------------------------------------------------------------------
+def tgs_cor_knn(x, y=None, knn=None, ctx=None):
+    """tgs_cor_knn(x, y = x, knn): x is genes x cells (like the R matrix).  Returns dict col1, col2, cor,
+    rank (schema pinned by reference R/atlas.r:282,477,585); col1/col2 are 0-based cell codes."""
+    if y is not None and y is not x:
+        raise McbError("MC-ERR: tgs_cor_knn with y != x is not on the accelerated path yet (SURVEY 8f rank 4)")
+    ctx = _ctx(ctx)
+    xt = np.ascontiguousarray(np.asarray(x, dtype=np.float64).T)
+    g = _lib.CGraph.from_dense(ctx, xt)
+    try:
+        if g.M < 2:
+            raise McbError("MC-ERR: fewer than 2 cells with non-constant features")
+        g.knn(int(knn), 1)
+        col, cor = g.download_knn()
+        cells = g.valid_cells()
+    finally:
+        g.destroy()
+    kk = min(int(knn), g.M)
+    col1 = np.repeat(cells, kk)
+    col2 = cells[col[:, :kk].reshape(-1)]
+    rank = np.tile(np.arange(1, kk + 1, dtype=np.int32), g.M)
+    return {"col1": col1.astype(np.int32), "col2": col2.astype(np.int32), "cor": cor[:, :kk].reshape(-1).astype(np.float64),
+            "rank": rank}
+
+
+def _graph_from_handle(g, K, k_expand, k_beta):
+    g.knn(int(K), int(k_expand))
+    g.mutual(int(k_beta))
+    g.prune()
+    src, dst, w = g.edges()
+    return {"col1": src.copy(), "col2": dst.copy(), "weight": w.copy()}
+
+
+def tgs_cor_graph(x, knn, k_expand, k_alpha, k_beta, ctx=None):
+    """reference R/utils.r:115-123: tgs_cor_knn(x, x, knn*k_expand) then tgs_graph(...); k_alpha is
+    accepted and ignored exactly as the reference wrapper does.  x: genes x cells dense."""
+    ctx = _ctx(ctx)
+    xt = np.ascontiguousarray(np.asarray(x, dtype=np.float64).T)
+    g = _lib.CGraph.from_dense(ctx, xt)
+    try:
+        return _graph_from_handle(g, knn, k_expand, k_beta)
+    finally:
+        g.destroy()
+
+
+# ------------------------------------------------------------------------------------------------
+# mcell_add_cgraph_from_mat_bknn (reference R/cgraph_knn.r:10-25)
+# ------------------------------------------------------------------------------------------------
+def mcell_add_cgraph_from_mat_bknn(mat_id, gset_id, graph_id, K, dsamp=False, ctx=None):
+    gset, mat = scdb_gset(gset_id), scdb_mat(mat_id)
+    if gset is None:
+        raise McbError(f"MC-ERR: non existing gset {gset_id} when trying to get feature matrix")
+    if mat is None:
+        raise McbError(f"MC-ERR: non existing mat {mat_id} when trying to get feature matrix")
+    ctx = _ctx(ctx)
+    k_nonz_exp = get_param("scm_k_nonz_exp")
+    k_expand = get_param("scm_balance_graph_k_expand")
+    k_beta = get_param("scm_balance_graph_k_beta")
+    rows = _feature_rows(gset, mat)
+    _message(f"will build balanced knn graph on {mat.ncells} cells and {rows.size} genes, this can be a bit heavy for >20,000 cells")
+    csc = _upload(mat, ctx)
+    use = csc
+    if dsamp:       # gset_get_feat_mat(downsamp = dsamp, add_non_dsamp = dsamp), R/cgraph_knn.r:12
+        n = get_param("scm_n_downsamp_gstat")
+        if n is None:
+            n = _lib.downsamp_depth(csc.col_sums())
+        _message(f"will downsample the matrix, N= {n}")
+        use = csc.downsample(float(n), get_param("mc_rseed"), add_non_dsamp=True)
+    g = _lib.CGraph.from_csc(ctx, use, rows, float(k_nonz_exp))
+    try:
+        gr = _graph_from_handle(g, K, k_expand, k_beta)
+    finally:
+        g.destroy()
+        if use is not csc:
+            use.free()
+        csc.free()
+    edges = {"mc1": gr["col1"], "mc2": gr["col2"], "w": gr["weight"]}       # colnames(gr) = c("mc1","mc2","w")
+    cg = tgCellGraph(edges, mat.cells)
+    scdb_add_cgraph(graph_id, cg)
+    return cg
+
+
+# ------------------------------------------------------------------------------------------------
+# A8: co-clustering
+# ------------------------------------------------------------------------------------------------
+def resample_index_sets(ncells, p_resamp, n_resamp, seed):
+    """Host-supplied node samples + per-resample seeds (north_star: 'host-supplied RNG seeds and resample
+    index sets').  Sample size round(p * N); each set strictly ascending."""
+    rng = np.random.default_rng(seed)
+    n_s = int(round(p_resamp * ncells))
+    sets = np.empty((n_resamp, n_s), dtype=np.int32)
+    for r in range(n_resamp):
+        sets[r] = np.sort(rng.choice(ncells, size=n_s, replace=False))
+    seeds = rng.integers(0, 2 ** 63 - 1, size=n_resamp, dtype=np.int64).astype(np.uint64)
+    return sets, seeds
+
+
+def tgs_graph_cover_resample(edges, knn, min_cluster_size, cooling, burn_in, p_resamp, n_resamp, method="full",
+                             n_nodes=None, seed=None, ctx=None, max_sweeps=1000):
+    """tgstat call of reference R/coclust_graph_cov.r:41.  edges: dict col1, col2, weight (0-based codes).
+    Returns dict(co_cluster = dict(node1, node2, cnt), samples = int[N])."""
+    if method != "full":
+        raise McbError("MC-ERR: only method = \"full\" is supported (what metacell calls)")
+    ctx = _ctx(ctx)
+    src, dst, w = edges["col1"], edges["col2"], edges["weight"]
+    N = int(n_nodes if n_nodes is not None else max(int(np.max(src)), int(np.max(dst))) + 1)
+    sets, seeds = resample_index_sets(N, p_resamp, n_resamp, get_param("mc_rseed") if seed is None else seed)
+    cc = _lib.CoClust(ctx, N, src, dst, w, sets, seeds, int(min_cluster_size), float(cooling), int(burn_in), max_sweeps)
+    try:
+        n1, n2, cnt, samples = cc.pairs()
+    finally:
+        cc.destroy()
+    return {"co_cluster": {"node1": n1.copy(), "node2": n2.copy(), "cnt": cnt.copy()}, "samples": samples}
+
+
+def mcell_coclust_from_graph_resamp(coc_id, graph_id, min_mc_size, p_resamp, n_resamp, ctx=None):
+    """reference R/coclust_graph_cov.r:13-58"""
+    cooling = get_param("scm_tgs_clust_cool")
+    burn_in = get_param("scm_tgs_clust_burn_in")
+    graph = scdb_cgraph(graph_id)
+    if graph is None:
+        raise McbError(f"MC-ERR: cell graph id {graph_id} is missing when running add_mc_from_graph")
+    _message("running bootstrap to generate cocluster")
+    edges = {"col1": graph.edges["mc1"], "col2": graph.edges["mc2"], "weight": graph.edges["w"]}
+    ncells = len(graph.cell_names)
+    K = int(round(len(edges["col1"]) / ncells))                           # R/coclust_graph_cov.r:39
+    resamp = tgs_graph_cover_resample(edges, K, min_mc_size, cooling, burn_in, p_resamp, n_resamp, method="full",
+                                      n_nodes=ncells, ctx=ctx)
+    _message("done resampling")
+    coc = tgCoClust(graph_id, resamp["co_cluster"], resamp["samples"])
+    scdb_add_coclust(coc_id, coc)
+    return coc

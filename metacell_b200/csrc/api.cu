@@ -1,0 +1,930 @@
+// api.cu -- the extern "C" surface of include/mcb200.h: handles, orchestration of the CUDA stages,
+// host<->device staging.  No arithmetic of the path happens on the host; host code here only sizes
+// buffers, derives scalar parameters and moves bytes.
+#include "../../include/mcb200.h"
+#include "internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <vector>
+
+using namespace mcb;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+void mcb::set_error(const char* msg) { g_err = msg ? msg : ""; }
+
+#define MCB_API_BEGIN try {
+#define MCB_API_END                                                                            \
+    return 0;                                                                                  \
+    } catch (const mcb::Error& e) { mcb::set_error(e.what()); return e.code; }                 \
+    catch (const std::bad_alloc&) { mcb::set_error("host out of memory"); return 3; }          \
+    catch (const std::exception& e) { mcb::set_error(e.what()); return 4; }                    \
+    catch (...) { mcb::set_error("unknown error"); return 5; }
+
+extern "C" int mcb_version(void) { return 100; }
+extern "C" const char* mcb_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------------------------------------
+// stage timers
+// ---------------------------------------------------------------------------------------------
+mcb::StageTimer::StageTimer(mcb_ctx* c, const char* name, int64_t launches) : ctx(c)
+{
+    if (!c->profile) return;
+    mcb_ctx::Stage s; s.name = name; s.launches = launches;
+    cudaEventCreate(&s.a); cudaEventCreate(&s.b);
+    cudaEventRecord(s.a, c->stream);
+    idx = (int)c->stages.size();
+    c->stages.push_back(s);
+}
+mcb::StageTimer::~StageTimer()
+{
+    if (idx >= 0) cudaEventRecord(ctx->stages[idx].b, ctx->stream);
+}
+static void resolve_timers(mcb_ctx* ctx)
+{
+    for (auto& s : ctx->stages) {
+        cudaEventSynchronize(s.b);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, s.a, s.b);
+        bool found = false;
+        for (auto& a : ctx->agg) if (strcmp(a.name, s.name) == 0) { a.ms += ms; a.launches += s.launches; found = true; break; }
+        if (!found) ctx->agg.push_back({s.name, ms, s.launches});
+        cudaEventDestroy(s.a); cudaEventDestroy(s.b);
+    }
+    ctx->stages.clear();
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" int mcb_ctx_create(int device, mcb_ctx** out)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(out != nullptr, "mcb_ctx_create: null output");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw Error(2, "MC-ERR: no CUDA device available; libmcb200 has no CPU fallback");
+    MCB_CHECK(device >= 0 && device < ndev, "mcb_ctx_create: bad device index");
+    MCB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MCB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        char b[200];
+        snprintf(b, sizeof(b), "MC-ERR: libmcb200 is built for sm_100a (B200); device %d is sm_%d%d", device, prop.major, prop.minor);
+        throw Error(2, b);
+    }
+    mcb_ctx* c = new mcb_ctx();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    MCB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    MCB_CUDA(cudaDeviceGetDefaultMemPool(&c->pool, device));
+    uint64_t thresh = UINT64_MAX;
+    MCB_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    *out = c;
+    MCB_API_END
+}
+extern "C" void mcb_ctx_destroy(mcb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    resolve_timers(ctx);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" int mcb_ctx_sync(mcb_ctx* ctx)
+{
+    MCB_API_BEGIN
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MCB_API_END
+}
+extern "C" void* mcb_ctx_stream(mcb_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int mcb_ctx_set_option(mcb_ctx* ctx, const char* key, int64_t value)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && key, "mcb_ctx_set_option: null argument");
+    if (!strcmp(key, "gemm_impl")) ctx->gemm_impl = (int)value;
+    else if (!strcmp(key, "profile")) ctx->profile = (int)value;
+    else if (!strcmp(key, "keep_self")) ctx->keep_self = (int)value;
+    else if (!strcmp(key, "thresh_strict")) ctx->thresh_strict = (int)value;
+    else throw Error(1, std::string("unknown option: ") + key);
+    MCB_API_END
+}
+extern "C" int mcb_ctx_timings(mcb_ctx* ctx, int cap, const char** names, float* ms, int64_t* launches, int* n)
+{
+    MCB_API_BEGIN
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    resolve_timers(ctx);
+    *n = (int)ctx->agg.size();
+    for (int i = 0; i < *n && i < cap; ++i) { names[i] = ctx->agg[i].name; ms[i] = ctx->agg[i].ms; launches[i] = ctx->agg[i].launches; }
+    MCB_API_END
+}
+extern "C" int mcb_ctx_timings_reset(mcb_ctx* ctx)
+{
+    MCB_API_BEGIN
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    resolve_timers(ctx);
+    ctx->agg.clear();
+    MCB_API_END
+}
+extern "C" void mcb_free(void* p) { free(p); }
+
+// ---------------------------------------------------------------------------------------------
+// A1: scm_which_downsamp_n (reference R/scmat.r:399-407): R quantile type 7 + round-half-even
+// ---------------------------------------------------------------------------------------------
+static double r_quantile7(const std::vector<double>& s, double prob)
+{
+    const int64_t n = (int64_t)s.size();
+    const double h = (double)(n - 1) * prob;
+    const int64_t lo = (int64_t)std::floor(h);
+    const int64_t hi = lo + 1 < n ? lo + 1 : n - 1;
+    return s[lo] + (h - (double)lo) * (s[hi] - s[lo]);
+}
+extern "C" int mcb_downsamp_depth(const int64_t* col_sums, int64_t ncells, double* depth)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(depth != nullptr, "mcb_downsamp_depth: null output");
+    if (ncells <= 0) { *depth = 0.0; return 0; }
+    std::vector<double> s((size_t)ncells);
+    for (int64_t i = 0; i < ncells; ++i) s[i] = (double)col_sums[i];
+    std::sort(s.begin(), s.end());
+    const double q50 = std::nearbyint(r_quantile7(s, 0.5));
+    const double q05 = std::nearbyint(r_quantile7(s, 0.05));
+    const double m = q05 > 750.0 ? q05 : 750.0;
+    *depth = q50 < m ? q50 : m;
+    MCB_API_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// CSC matrix
+// ---------------------------------------------------------------------------------------------
+struct mcb_csc {
+    mcb_ctx* ctx = nullptr;
+    int32_t ngenes = 0;
+    int64_t ncells = 0, nnz = 0;
+    const int64_t* p = nullptr; const int32_t* i = nullptr; const uint32_t* x = nullptr;   // device views
+    DevBuf<int64_t> own_p; DevBuf<int32_t> own_i; DevBuf<uint32_t> own_x; DevBuf<uint8_t> kept;
+};
+
+extern "C" int mcb_csc_upload(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* p, const int32_t* i,
+                              const double* x, mcb_csc** out)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && p && out, "mcb_csc_upload: null argument");
+    MCB_CHECK(ngenes >= 0 && ncells >= 0, "mcb_csc_upload: negative dimension");
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const int64_t nnz = p[ncells];
+    MCB_CHECK(p[0] == 0 && nnz >= 0, "mcb_csc_upload: malformed column pointer");
+    MCB_CHECK(nnz == 0 || (i && x), "mcb_csc_upload: null index/value array");
+    std::unique_ptr<mcb_csc> m(new mcb_csc());
+    m->ctx = ctx; m->ngenes = ngenes; m->ncells = ncells; m->nnz = nnz;
+    StageTimer t(ctx, "h2d_csc");
+    m->own_p.alloc(ctx, (size_t)ncells + 1);
+    m->own_i.alloc(ctx, (size_t)nnz);
+    m->own_x.alloc(ctx, (size_t)nnz);
+    MCB_CUDA(cudaMemcpyAsync(m->own_p.p, p, sizeof(int64_t) * ((size_t)ncells + 1), cudaMemcpyHostToDevice, ctx->stream));
+    if (nnz) {
+        DevBuf<double> xd(ctx, (size_t)nnz);
+        MCB_CUDA(cudaMemcpyAsync(m->own_i.p, i, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+        MCB_CUDA(cudaMemcpyAsync(xd.p, x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
+        launch_convert_x(ctx, xd.p, m->own_x.p, nnz);
+    }
+    m->p = m->own_p.p; m->i = m->own_i.p; m->x = m->own_x.p;
+    *out = m.release();
+    MCB_API_END
+}
+extern "C" int mcb_csc_wrap_device(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* dev_p,
+                                   const int32_t* dev_i, const uint32_t* dev_x, mcb_csc** out)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && dev_p && out, "mcb_csc_wrap_device: null argument");
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<mcb_csc> m(new mcb_csc());
+    m->ctx = ctx; m->ngenes = ngenes; m->ncells = ncells;
+    int64_t nnz = 0;
+    MCB_CUDA(cudaMemcpy(&nnz, dev_p + ncells, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    m->nnz = nnz; m->p = dev_p; m->i = dev_i; m->x = dev_x;
+    *out = m.release();
+    MCB_API_END
+}
+extern "C" void mcb_csc_free(mcb_csc* m) { delete m; }
+
+extern "C" int mcb_csc_col_sums(mcb_ctx* ctx, const mcb_csc* m, int64_t* host_tot)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && m && host_tot, "mcb_csc_col_sums: null argument");
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    DevBuf<int64_t> tot(ctx, (size_t)m->ncells);
+    { StageTimer t(ctx, "col_sums"); launch_col_sums(ctx, m->ncells, m->p, m->x, tot.p); }
+    MCB_CUDA(cudaMemcpyAsync(host_tot, tot.p, sizeof(int64_t) * (size_t)m->ncells, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MCB_API_END
+}
+extern "C" int mcb_csc_downsample(mcb_ctx* ctx, const mcb_csc* m, double n, uint64_t seed, int add_non_dsamp,
+                                  mcb_csc** out)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && m && out, "mcb_csc_downsample: null argument");
+    MCB_CHECK(n >= 1.0, "MC-ERR: downsample depth must be >= 1");
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<mcb_csc> d(new mcb_csc());
+    d->ctx = ctx; d->ngenes = m->ngenes; d->ncells = m->ncells; d->nnz = m->nnz;
+    d->p = m->p; d->i = m->i;                      // shares structure with the input (caller keeps it alive)
+    d->own_x.alloc(ctx, (size_t)m->nnz);
+    d->kept.alloc(ctx, (size_t)m->ncells);
+    { StageTimer t(ctx, "downsample"); launch_downsample(ctx, m->ncells, m->p, m->x, n, seed, add_non_dsamp, d->own_x.p, d->kept.p); }
+    d->x = d->own_x.p;
+    *out = d.release();
+    MCB_API_END
+}
+extern "C" int mcb_csc_download(mcb_ctx* ctx, const mcb_csc* m, double* host_x, uint8_t* host_kept)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && m, "mcb_csc_download: null argument");
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    if (host_x && m->nnz) {
+        DevBuf<double> xd(ctx, (size_t)m->nnz);
+        launch_x_to_double(ctx, m->x, xd.p, m->nnz);
+        MCB_CUDA(cudaMemcpyAsync(host_x, xd.p, sizeof(double) * (size_t)m->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    if (host_kept) {
+        if (m->kept.p) MCB_CUDA(cudaMemcpyAsync(host_kept, m->kept.p, (size_t)m->ncells, cudaMemcpyDeviceToHost, ctx->stream));
+        else memset(host_kept, 1, (size_t)m->ncells);
+    }
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MCB_API_END
+}
+
+// ---------------------------------------------------------------------------------------------
+// balanced K-nn cell graph
+// ---------------------------------------------------------------------------------------------
+namespace mcb {
+void launch_compact_flags(mcb_ctx* ctx, const int32_t* flag, int64_t n, int32_t* list, int32_t* n_out);
+void launch_widen_i32(mcb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n);
+void launch_tc_store3(mcb_ctx* ctx, const float* Zhi, const float* Zlo, int64_t rows_alloc, int64_t a_rows,
+                      int64_t b_rows, int32_t Gpad, float* C, int64_t ldc);
+}
+
+struct mcb_cgraph {
+    mcb_ctx* ctx = nullptr;
+    int64_t ncells = 0; int32_t G = 0, Gpad = 0;
+    int64_t M = 0, Mpad = 0;
+    DevBuf<float> Zhi, Zlo;
+    DevBuf<int32_t> cell_of_row;
+    // knn
+    int32_t K = 0, k_expand = 0, Kc = 0, kc_out = 0, rank = 0, nranks = 1;
+    int64_t rows_per_rank = 0, row0 = 0, rows = 0;
+    DevBuf<int32_t> knn_col; DevBuf<float> knn_cor;
+    int64_t n_fallback = 0, n_candidates = 0; int32_t cap = 0, n_sample = 0;
+    // balance
+    int32_t H = 0, rank_bits = 0, k_beta = 0;
+    DevBuf<uint32_t> sym; DevBuf<uint64_t> thr_in;
+    DevBuf<int32_t> out_deg, out_dst, out_s;
+    int64_t n_edges = 0;
+    DevBuf<int32_t> e_src, e_dst; DevBuf<double> e_w;
+};
+
+extern "C" int mcb_cgraph_create(mcb_ctx* ctx, const mcb_csc* m, const int32_t* feat_rows, int32_t G, double k_nonz,
+                                 mcb_cgraph** out)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && m && feat_rows && out, "mcb_cgraph_create: null argument");
+    MCB_CHECK(G >= 2, "MC-ERR: need at least 2 feature genes");
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    std::vector<int32_t> fmap((size_t)m->ngenes, -1);
+    for (int32_t g = 0; g < G; ++g) {
+        MCB_CHECK(feat_rows[g] >= 0 && feat_rows[g] < m->ngenes, "MC-ERR: feature gene row out of range");
+        MCB_CHECK(fmap[feat_rows[g]] < 0, "MC-ERR: duplicate feature gene row");
+        fmap[feat_rows[g]] = g;
+    }
+    std::unique_ptr<mcb_cgraph> g(new mcb_cgraph());
+    g->ctx = ctx; g->ncells = m->ncells; g->G = G; g->Gpad = (int32_t)round_up(G, 32);
+    DevBuf<int32_t> d_fmap(ctx, fmap.size());
+    MCB_CUDA(cudaMemcpyAsync(d_fmap.p, fmap.data(), fmap.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    DevBuf<double> mu(ctx, (size_t)m->ncells), inv(ctx, (size_t)m->ncells);
+    DevBuf<int32_t> valid(ctx, (size_t)m->ncells), rowpos(ctx, (size_t)m->ncells), total(ctx, 1);
+    {
+        StageTimer t(ctx, "feat_stats", 2);
+        launch_feat_stats(ctx, m->ncells, m->p, m->i, m->x, d_fmap.p, G, k_nonz, mu.p, inv.p, valid.p);
+        launch_exclusive_scan_i32(ctx, valid.p, rowpos.p, m->ncells, total.p);
+    }
+    int32_t M = 0;
+    MCB_CUDA(cudaMemcpyAsync(&M, total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    g->M = M; g->Mpad = round_up(std::max<int64_t>(M, 1), 256);
+    g->Zhi.alloc(ctx, (size_t)g->Mpad * g->Gpad);
+    g->Zlo.alloc(ctx, (size_t)g->Mpad * g->Gpad);
+    g->cell_of_row.alloc(ctx, (size_t)std::max<int64_t>(M, 1));
+    if (g->Mpad > M) {     // zero the padding rows
+        MCB_CUDA(cudaMemsetAsync(g->Zhi.p + (size_t)M * g->Gpad, 0, (size_t)(g->Mpad - M) * g->Gpad * sizeof(float), ctx->stream));
+        MCB_CUDA(cudaMemsetAsync(g->Zlo.p + (size_t)M * g->Gpad, 0, (size_t)(g->Mpad - M) * g->Gpad * sizeof(float), ctx->stream));
+    }
+    {
+        StageTimer t(ctx, "feat_rows");
+        launch_feat_rows(ctx, m->ncells, m->p, m->i, m->x, d_fmap.p, G, g->Gpad, k_nonz, mu.p, inv.p, valid.p, rowpos.p,
+                         g->Zhi.p, g->Zlo.p, g->cell_of_row.p);
+    }
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));     // temporaries die here
+    *out = g.release();
+    MCB_API_END
+}
+// tgs_cor_graph(x = feat, ...) entry (reference R/utils.r:115): x is the dense genes x cells matrix
+// the caller already transformed (column-major, one contiguous vector of G doubles per cell)
+extern "C" int mcb_cgraph_create_dense(mcb_ctx* ctx, const double* x, int32_t G, int64_t ncells, mcb_cgraph** out)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && x && out, "mcb_cgraph_create_dense: null argument");
+    MCB_CHECK(G >= 2 && ncells >= 1, "MC-ERR: need at least 2 feature genes and 1 cell");
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    std::unique_ptr<mcb_cgraph> g(new mcb_cgraph());
+    g->ctx = ctx; g->ncells = ncells; g->G = G; g->Gpad = (int32_t)round_up(G, 32);
+    DevBuf<double> dx(ctx, (size_t)ncells * G);
+    {
+        StageTimer t(ctx, "h2d_dense");
+        MCB_CUDA(cudaMemcpyAsync(dx.p, x, sizeof(double) * (size_t)ncells * G, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    DevBuf<double> mu(ctx, (size_t)ncells), inv(ctx, (size_t)ncells);
+    DevBuf<int32_t> valid(ctx, (size_t)ncells), rowpos(ctx, (size_t)ncells), total(ctx, 1);
+    {
+        StageTimer t(ctx, "feat_stats", 2);
+        launch_dense_stats(ctx, ncells, dx.p, G, mu.p, inv.p, valid.p);
+        launch_exclusive_scan_i32(ctx, valid.p, rowpos.p, ncells, total.p);
+    }
+    int32_t M = 0;
+    MCB_CUDA(cudaMemcpyAsync(&M, total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    g->M = M; g->Mpad = round_up(std::max<int64_t>(M, 1), 256);
+    g->Zhi.alloc(ctx, (size_t)g->Mpad * g->Gpad);
+    g->Zlo.alloc(ctx, (size_t)g->Mpad * g->Gpad);
+    g->cell_of_row.alloc(ctx, (size_t)std::max<int64_t>(M, 1));
+    if (g->Mpad > M) {
+        MCB_CUDA(cudaMemsetAsync(g->Zhi.p + (size_t)M * g->Gpad, 0, (size_t)(g->Mpad - M) * g->Gpad * sizeof(float), ctx->stream));
+        MCB_CUDA(cudaMemsetAsync(g->Zlo.p + (size_t)M * g->Gpad, 0, (size_t)(g->Mpad - M) * g->Gpad * sizeof(float), ctx->stream));
+    }
+    {
+        StageTimer t(ctx, "feat_rows");
+        launch_dense_rows(ctx, ncells, dx.p, G, g->Gpad, mu.p, inv.p, valid.p, rowpos.p, g->Zhi.p, g->Zlo.p, g->cell_of_row.p);
+    }
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = g.release();
+    MCB_API_END
+}
+extern "C" void mcb_cgraph_destroy(mcb_cgraph* g)
+{
+    if (!g) return;
+    cudaSetDevice(g->ctx->device);
+    delete g;
+}
+extern "C" int mcb_cgraph_num_valid(const mcb_cgraph* g, int64_t* M)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && M, "null argument");
+    *M = g->M;
+    MCB_API_END
+}
+extern "C" int mcb_cgraph_valid_cells(mcb_cgraph* g, int32_t* host)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && host, "null argument");
+    MCB_CUDA(cudaSetDevice(g->ctx->device));
+    if (g->M) MCB_CUDA(cudaMemcpyAsync(host, g->cell_of_row.p, sizeof(int32_t) * (size_t)g->M, cudaMemcpyDeviceToHost, g->ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    MCB_API_END
+}
+extern "C" int mcb_cgraph_features(mcb_cgraph* g, float* host_z)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && host_z, "null argument");
+    mcb_ctx* ctx = g->ctx;
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    // z = hi + lo, unpadded [M][G]
+    std::vector<float> hi((size_t)g->M * g->Gpad), lo((size_t)g->M * g->Gpad);
+    if (g->M) {
+        MCB_CUDA(cudaMemcpyAsync(hi.data(), g->Zhi.p, hi.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        MCB_CUDA(cudaMemcpyAsync(lo.data(), g->Zlo.p, lo.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t r = 0; r < g->M; ++r)
+        for (int32_t c = 0; c < g->G; ++c)
+            host_z[r * g->G + c] = hi[(size_t)r * g->Gpad + c] + lo[(size_t)r * g->Gpad + c];
+    MCB_API_END
+}
+
+// threshold rule of the sampling pass: smallest sample rank r whose expected full-row count stays
+// above kc_out with z sigma of margin (hypergeometric variance), plus the matching capacity
+static void sample_rule(int64_t M, int64_t S, int32_t kc_out, int32_t& r_out, int32_t& cap_out)
+{
+    const double z = 4.0;
+    const double fpc = S >= M ? 0.0 : std::sqrt(1.0 - (double)S / (double)M);
+    const double scale = (double)M / (double)S;
+    int32_t r = -1;
+    for (int64_t q = 1; q <= S; ++q) {
+        const double sd = std::sqrt((double)q * (1.0 - (double)q / (double)S)) * fpc;
+        if (((double)q - z * sd) * scale >= (double)kc_out + 2.0) { r = (int32_t)q; break; }
+    }
+    if (r < 0) { r_out = (int32_t)S + 1; cap_out = (int32_t)round_up(M, 64); return; }    // keep everything
+    const double sd = std::sqrt((double)r * (1.0 - (double)r / (double)S)) * fpc;
+    const double upper = ((double)r + z * sd) * scale;
+    int64_t cap = round_up((int64_t)(upper * 1.08) + 64, 64);
+    cap = std::min<int64_t>(cap, round_up(M, 64));
+    r_out = r; cap_out = (int32_t)cap;
+}
+
+extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g, "null argument");
+    MCB_CHECK(K >= 1 && k_expand >= 1, "MC-ERR: K and k_expand must be >= 1");
+    MCB_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+    MCB_CHECK((int64_t)K * k_expand <= 8192, "MC-ERR: K * k_expand above 8192 is not supported");
+    MCB_CHECK(g->M >= 2, "MC-ERR: fewer than 2 cells with non-constant features");
+    mcb_ctx* ctx = g->ctx;
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const int64_t M = g->M;
+    const int32_t Gpad = g->Gpad;
+    g->K = K; g->k_expand = k_expand; g->Kc = K * k_expand; g->kc_out = (int32_t)std::min<int64_t>(g->Kc, M);
+    g->rank = rank; g->nranks = nranks;
+    g->rows_per_rank = ceil_div(M, nranks);
+    g->row0 = std::min<int64_t>(M, (int64_t)rank * g->rows_per_rank);
+    g->rows = std::min<int64_t>(M, g->row0 + g->rows_per_rank) - g->row0;
+    const int64_t rows = g->rows, row0 = g->row0;
+    const int32_t Kc = g->Kc, kc_out = g->kc_out;
+    g->knn_col.alloc(ctx, (size_t)nranks * g->rows_per_rank * Kc);
+    g->knn_cor.alloc(ctx, (size_t)std::max<int64_t>(rows, 1) * Kc);
+    if (rows == 0) { MCB_CUDA(cudaStreamSynchronize(ctx->stream)); return 0; }
+
+    // ---- sampling pass: per-row filter threshold from a random column sample -----------------
+    int64_t S = std::min<int64_t>(32768, round_up(ceil_div(128 * M, kc_out), 256));
+    if (S >= M) S = M;
+    const int64_t Spad = round_up(S, 256);
+    int32_t r_sel = 0, cap = 0;
+    sample_rule(M, S, kc_out, r_sel, cap);
+    MCB_CHECK(cap <= 16384, "MC-ERR: K * k_expand is too large relative to the number of cells for this build");
+    g->cap = cap; g->n_sample = (int32_t)S;
+    std::vector<int32_t> samp((size_t)Spad, -1);
+    {
+        if (S >= M) { for (int64_t q = 0; q < M; ++q) samp[q] = (int32_t)q; }
+        else {   // partial Fisher-Yates with a fixed seed: the sample only steers the filter, not the result
+            std::vector<int32_t> perm((size_t)M);
+            for (int64_t q = 0; q < M; ++q) perm[q] = (int32_t)q;
+            std::mt19937_64 gen(0x6d63623230300aull);
+            for (int64_t q = 0; q < S; ++q) {
+                const int64_t j = q + (int64_t)(gen() % (uint64_t)(M - q));
+                std::swap(perm[q], perm[j]);
+                samp[q] = perm[q];
+            }
+        }
+    }
+    DevBuf<int32_t> d_samp(ctx, (size_t)Spad);
+    MCB_CUDA(cudaMemcpyAsync(d_samp.p, samp.data(), sizeof(int32_t) * (size_t)Spad, cudaMemcpyHostToDevice, ctx->stream));
+    DevBuf<float> Zs(ctx, (size_t)Spad * Gpad);
+    DevBuf<float> thr(ctx, (size_t)rows);
+    {
+        StageTimer t(ctx, "sample_gather");
+        launch_gather_rows(ctx, g->Zhi.p, Gpad, d_samp.p, (int32_t)Spad, Zs.p);
+    }
+    {
+        int64_t chunk = std::max<int64_t>(128, ((int64_t)2 << 30) / (Spad * 4) / 128 * 128);
+        chunk = std::min(chunk, round_up(rows, 128));
+        DevBuf<float> Cs(ctx, (size_t)chunk * Spad);
+        const float eps = 1.0f / 512.0f;      // covers the 1-pass TF32 error of the sampled correlations
+        for (int64_t c0 = 0; c0 < rows; c0 += chunk) {
+            const int64_t nr = std::min(chunk, rows - c0);
+            {
+                StageTimer t(ctx, "cor_sample_gemm");
+                if (ctx->gemm_impl == 0)
+                    launch_tc_store(ctx, g->Zhi.p + (size_t)(row0 + c0) * Gpad, g->Mpad - (row0 + c0), Zs.p, Spad, Gpad,
+                                    Cs.p, Spad, nr, S);
+                else
+                    launch_simt_store(ctx, g->Zhi.p + (size_t)(row0 + c0) * Gpad, nullptr, nr, Zs.p, nullptr, S, Gpad, Cs.p, Spad);
+            }
+            {
+                StageTimer t(ctx, "sample_threshold");
+                launch_sample_threshold(ctx, Cs.p, Spad, nr, (int32_t)S, r_sel, eps, thr.p + c0);
+            }
+        }
+    }
+    // ---- filter pass: full 3-pass contraction, candidates above the row threshold ------------
+    DevBuf<uint64_t> cand(ctx, (size_t)rows * cap);
+    DevBuf<uint32_t> cnt(ctx, (size_t)rows);
+    cnt.zero();
+    {
+        StageTimer t(ctx, "cor_filter_gemm");
+        if (ctx->gemm_impl == 0)
+            launch_tc_filter(ctx, g->Zhi.p, g->Zlo.p, g->Mpad, row0, rows, M, Gpad, thr.p, cand.p, cnt.p, cap);
+        else
+            launch_simt_filter(ctx, g->Zhi.p + (size_t)row0 * Gpad, g->Zlo.p + (size_t)row0 * Gpad, row0, rows, g->Zhi.p,
+                               g->Zlo.p, M, Gpad, thr.p, cand.p, cnt.p, cap);
+    }
+    // ---- ranked lists -------------------------------------------------------------------------
+    DevBuf<int32_t> fail(ctx, (size_t)rows), fail_list(ctx, (size_t)rows), n_fail_d(ctx, 1);
+    int32_t* own_col = g->knn_col.p + (size_t)row0 * Kc;
+    {
+        StageTimer t(ctx, "topk_rows");
+        launch_topk_rows(ctx, cand.p, cnt.p, cap, row0, rows, kc_out, Kc, own_col, g->knn_cor.p, fail.p);
+    }
+    launch_compact_flags(ctx, fail.p, rows, fail_list.p, n_fail_d.p);
+    int32_t n_fail = 0;
+    MCB_CUDA(cudaMemcpyAsync(&n_fail, n_fail_d.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    g->n_fallback = n_fail;
+    if (n_fail > 0) {
+        // rows whose candidate count missed [kc_out-1, cap]: exact fp32 row on the CUDA cores
+        StageTimer t(ctx, "knn_exact_rows");
+        const int32_t B = 64;
+        DevBuf<float> Ah(ctx, (size_t)B * Gpad), Al(ctx, (size_t)B * Gpad), Cf(ctx, (size_t)B * M);
+        DevBuf<int32_t> glist(ctx, (size_t)B);
+        std::vector<int32_t> hl((size_t)n_fail), gl((size_t)B);
+        MCB_CUDA(cudaMemcpyAsync(hl.data(), fail_list.p, sizeof(int32_t) * (size_t)n_fail, cudaMemcpyDeviceToHost, ctx->stream));
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int32_t b0 = 0; b0 < n_fail; b0 += B) {
+            const int32_t nb = std::min(B, n_fail - b0);
+            for (int32_t q = 0; q < nb; ++q) gl[q] = (int32_t)(row0 + hl[b0 + q]);
+            MCB_CUDA(cudaMemcpyAsync(glist.p, gl.data(), sizeof(int32_t) * (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
+            launch_gather_rows(ctx, g->Zhi.p, Gpad, glist.p, nb, Ah.p);
+            launch_gather_rows(ctx, g->Zlo.p, Gpad, glist.p, nb, Al.p);
+            launch_simt_store(ctx, Ah.p, Al.p, nb, g->Zhi.p, g->Zlo.p, M, Gpad, Cf.p, M);
+            launch_topk_big(ctx, Cf.p, M, M, fail_list.p + b0, nb, row0, kc_out, Kc, own_col, g->knn_cor.p);
+            MCB_CUDA(cudaStreamSynchronize(ctx->stream));      // gl is reused
+        }
+    }
+    {   // statistics for DESIGN / bench: how selective the filter was
+        std::vector<uint32_t> hc((size_t)rows);
+        MCB_CUDA(cudaMemcpyAsync(hc.data(), cnt.p, sizeof(uint32_t) * (size_t)rows, cudaMemcpyDeviceToHost, ctx->stream));
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        int64_t tot = 0;
+        for (auto v : hc) tot += v;
+        g->n_candidates = tot;
+    }
+    MCB_API_END
+}
+
+extern "C" int mcb_cgraph_knn_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank, int32_t* Kc)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && g->knn_col.p, "mcb_cgraph_knn_buffer: run mcb_cgraph_knn first");
+    if (dev_ptr) *dev_ptr = g->knn_col.p;
+    if (rows_per_rank) *rows_per_rank = g->rows_per_rank;
+    if (Kc) *Kc = g->Kc;
+    MCB_API_END
+}
+extern "C" int mcb_cgraph_download_knn(mcb_cgraph* g, int32_t* host_col, float* host_cor)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && g->knn_col.p, "mcb_cgraph_download_knn: run mcb_cgraph_knn first");
+    mcb_ctx* ctx = g->ctx;
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)g->rows * g->Kc;
+    if (host_col && n) MCB_CUDA(cudaMemcpyAsync(host_col, g->knn_col.p + (size_t)g->row0 * g->Kc, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_cor && n) MCB_CUDA(cudaMemcpyAsync(host_cor, g->knn_cor.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MCB_API_END
+}
+extern "C" int mcb_cgraph_knn_stats(mcb_cgraph* g, int64_t* n_fallback_rows, int64_t* n_candidates, int32_t* cap,
+                                    int32_t* n_sample_cols)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g, "null argument");
+    if (n_fallback_rows) *n_fallback_rows = g->n_fallback;
+    if (n_candidates) *n_candidates = g->n_candidates;
+    if (cap) *cap = g->cap;
+    if (n_sample_cols) *n_sample_cols = g->n_sample;
+    MCB_API_END
+}
+
+static int ilog2_ceil(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) ++l; return l; }
+
+extern "C" int mcb_cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && g->knn_col.p, "mcb_cgraph_mutual: run mcb_cgraph_knn first");
+    MCB_CHECK(k_beta >= 1, "MC-ERR: k_beta must be >= 1");
+    mcb_ctx* ctx = g->ctx;
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const int64_t M = g->M;
+    const int32_t Kc = g->Kc;
+    g->k_beta = k_beta;
+    g->rank_bits = std::max(1, ilog2_ceil(Kc));
+    int32_t H = 2; while (H < 2 * Kc) H <<= 1;
+    g->H = H;
+    MCB_CHECK(M < ((int64_t)1 << (32 - g->rank_bits)) - 1, "MC-ERR: too many cells for the packed rank table at this K * k_expand");
+    // drop the feature planes: they are not needed after the kNN stage and the table is large
+    g->Zhi.release(); g->Zlo.release();
+    DevBuf<uint32_t> table(ctx, (size_t)M * H);
+    g->sym.alloc(ctx, (size_t)std::max<int64_t>(g->rows, 1) * Kc);
+    g->thr_in.alloc(ctx, (size_t)g->nranks * g->rows_per_rank);
+    {
+        StageTimer t(ctx, "balance_hash");
+        launch_build_hash(ctx, g->knn_col.p, M, Kc, H, g->rank_bits, table.p);
+    }
+    {
+        StageTimer t(ctx, "balance_mutual");
+        launch_mutual(ctx, g->knn_col.p, table.p, g->row0, g->rows, Kc, H, g->rank_bits,
+                      (int64_t)g->K * g->K * g->k_expand, ctx->thresh_strict, ctx->keep_self, g->K * k_beta, g->sym.p, g->thr_in.p);
+    }
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MCB_API_END
+}
+extern "C" int mcb_cgraph_thr_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && g->thr_in.p, "mcb_cgraph_thr_buffer: run mcb_cgraph_mutual first");
+    if (dev_ptr) *dev_ptr = g->thr_in.p;
+    if (rows_per_rank) *rows_per_rank = g->rows_per_rank;
+    MCB_API_END
+}
+extern "C" int mcb_cgraph_prune(mcb_cgraph* g, int64_t* n_edges)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && g->sym.p, "mcb_cgraph_prune: run mcb_cgraph_mutual first");
+    mcb_ctx* ctx = g->ctx;
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const int64_t rows = g->rows;
+    const int32_t K = g->K;
+    const size_t rk = (size_t)std::max<int64_t>(rows, 1) * K;
+    g->out_deg.alloc(ctx, (size_t)std::max<int64_t>(rows, 1));
+    g->out_dst.alloc(ctx, rk);
+    g->out_s.alloc(ctx, rk);
+    {
+        StageTimer t(ctx, "balance_prune");
+        launch_prune(ctx, g->knn_col.p, g->sym.p, g->thr_in.p, g->row0, rows, g->Kc, K, g->out_deg.p, g->out_dst.p, g->out_s.p);
+    }
+    DevBuf<int64_t> deg64(ctx, (size_t)std::max<int64_t>(rows, 1)), offs(ctx, (size_t)std::max<int64_t>(rows, 1)), total(ctx, 1);
+    int64_t ne = 0;
+    if (rows) {
+        StageTimer t(ctx, "edge_scan", 2);
+        launch_widen_i32(ctx, g->out_deg.p, deg64.p, rows);
+        launch_exclusive_scan_i64(ctx, deg64.p, offs.p, rows, total.p);
+        MCB_CUDA(cudaMemcpyAsync(&ne, total.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    g->n_edges = ne;
+    g->e_src.alloc(ctx, (size_t)std::max<int64_t>(ne, 1));
+    g->e_dst.alloc(ctx, (size_t)std::max<int64_t>(ne, 1));
+    g->e_w.alloc(ctx, (size_t)std::max<int64_t>(ne, 1));
+    if (rows) {
+        StageTimer t(ctx, "edge_emit");
+        launch_emit_edges(ctx, g->out_deg.p, g->out_dst.p, offs.p, g->cell_of_row.p, g->row0, rows, K, g->e_src.p, g->e_dst.p, g->e_w.p);
+    }
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_edges) *n_edges = ne;
+    MCB_API_END
+}
+extern "C" int mcb_cgraph_edges(mcb_cgraph* g, int32_t* host_src, int32_t* host_dst, double* host_w)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && g->e_src.p, "mcb_cgraph_edges: run mcb_cgraph_prune first");
+    mcb_ctx* ctx = g->ctx;
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const size_t ne = (size_t)g->n_edges;
+    StageTimer t(ctx, "d2h_edges");
+    if (ne) {
+        if (host_src) MCB_CUDA(cudaMemcpyAsync(host_src, g->e_src.p, ne * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (host_dst) MCB_CUDA(cudaMemcpyAsync(host_dst, g->e_dst.p, ne * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        if (host_w) MCB_CUDA(cudaMemcpyAsync(host_w, g->e_w.p, ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MCB_API_END
+}
+
+// test hook: dense correlation block through the tensor-core (impl 0, 3-pass; impl 2, 1-pass) or
+// SIMT (impl 1) kernel: C[a_rows][b_rows] = Z[0:a_rows] . Z[0:b_rows]^T
+extern "C" int mcb_cgraph_debug_cor(mcb_cgraph* g, int impl, int64_t a_rows, int64_t b_rows, float* host_c)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && g->Zhi.p && host_c, "mcb_cgraph_debug_cor: features not available");
+    MCB_CHECK(a_rows <= g->M && b_rows <= g->M, "mcb_cgraph_debug_cor: block exceeds matrix");
+    mcb_ctx* ctx = g->ctx;
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const int64_t ldc = round_up(b_rows, 4);
+    DevBuf<float> C(ctx, (size_t)a_rows * ldc);
+    C.zero();
+    if (impl == 0) launch_tc_store3(ctx, g->Zhi.p, g->Zlo.p, g->Mpad, a_rows, b_rows, g->Gpad, C.p, ldc);
+    else if (impl == 2) launch_tc_store(ctx, g->Zhi.p, g->Mpad, g->Zhi.p, g->Mpad, g->Gpad, C.p, ldc, a_rows, b_rows);
+    else launch_simt_store(ctx, g->Zhi.p, g->Zlo.p, a_rows, g->Zhi.p, g->Zlo.p, b_rows, g->Gpad, C.p, ldc);
+    std::vector<float> h((size_t)a_rows * ldc);
+    MCB_CUDA(cudaMemcpyAsync(h.data(), C.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t r = 0; r < a_rows; ++r) memcpy(host_c + r * b_rows, h.data() + r * ldc, sizeof(float) * (size_t)b_rows);
+    MCB_API_END
+}
+
+extern "C" int mcb_cgraph_bknn(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* p, const int32_t* i,
+                               const double* x, const int32_t* feat_rows, int32_t G, int32_t K, int32_t k_expand,
+                               int32_t k_beta, double k_nonz, int dsamp, uint64_t seed, int64_t* n_edges,
+                               int32_t** src, int32_t** dst, double** w, int64_t* n_valid_cells)
+{
+    mcb_csc* m = nullptr; mcb_csc* d = nullptr; mcb_cgraph* g = nullptr;
+    int32_t* hs = nullptr; int32_t* hd = nullptr; double* hw = nullptr;
+    int rc = 0;
+    do {
+        if (!n_edges || !src || !dst || !w) { mcb::set_error("mcb_cgraph_bknn: null output"); rc = 1; break; }
+        if ((rc = mcb_csc_upload(ctx, ngenes, ncells, p, i, x, &m))) break;
+        const mcb_csc* use = m;
+        if (dsamp) {
+            std::vector<int64_t> tot((size_t)ncells);
+            if ((rc = mcb_csc_col_sums(ctx, m, tot.data()))) break;
+            double depth = 0.0;
+            if ((rc = mcb_downsamp_depth(tot.data(), ncells, &depth))) break;
+            if ((rc = mcb_csc_downsample(ctx, m, depth, seed, /*add_non_dsamp=*/1, &d))) break;
+            use = d;
+        }
+        if ((rc = mcb_cgraph_create(ctx, use, feat_rows, G, k_nonz, &g))) break;
+        if ((rc = mcb_cgraph_knn(g, K, k_expand, 0, 1))) break;
+        if ((rc = mcb_cgraph_mutual(g, k_beta))) break;
+        int64_t ne = 0;
+        if ((rc = mcb_cgraph_prune(g, &ne))) break;
+        hs = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
+        hd = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
+        hw = (double*)malloc(sizeof(double) * (size_t)std::max<int64_t>(ne, 1));
+        if (!hs || !hd || !hw) { mcb::set_error("host out of memory"); rc = 3; break; }
+        if ((rc = mcb_cgraph_edges(g, hs, hd, hw))) break;
+        *n_edges = ne; *src = hs; *dst = hd; *w = hw;
+        if (n_valid_cells) *n_valid_cells = g->M;
+        hs = nullptr; hd = nullptr; hw = nullptr;
+    } while (0);
+    free(hs); free(hd); free(hw);
+    mcb_cgraph_destroy(g);
+    mcb_csc_free(d);
+    mcb_csc_free(m);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// resampled co-clustering
+// ---------------------------------------------------------------------------------------------
+struct mcb_coclust {
+    mcb_ctx* ctx = nullptr;
+    int32_t N = 0, n_local = 0, ncl_cap = 0;
+    DevBuf<uint32_t> cnt; DevBuf<int32_t> nsamp;
+    DevBuf<int32_t> mc, sweeps;
+    int64_t n_pairs = -1;
+    DevBuf<int32_t> p1, p2, pc;
+};
+
+extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst,
+                               const double* w, int32_t n_resamp, int32_t n_s, const int32_t* samples,
+                               const uint64_t* seeds, int32_t min_mc_size, double cooling, int32_t burn_in,
+                               int32_t max_sweeps, int32_t rank, int32_t nranks, mcb_coclust** out)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && out, "mcb_coclust_run: null argument");
+    MCB_CHECK(N >= 1 && n_edges >= 0 && n_resamp >= 0 && n_s >= 1 && n_s <= N, "MC-ERR: bad co-clustering dimensions");
+    MCB_CHECK(n_edges == 0 || (src && dst && w), "mcb_coclust_run: null edge arrays");
+    MCB_CHECK(n_resamp == 0 || (samples && seeds), "mcb_coclust_run: null sample arrays");
+    MCB_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+    MCB_CHECK((int64_t)N * N < ((int64_t)1 << 36), "MC-ERR: method=\"full\" needs an N x N counter matrix; N is too large");
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    // CSR (out and in) with 16-bit fixed-point weights: host-side counting sort of the R edge table
+    std::vector<int64_t> optr((size_t)N + 1, 0), iptr((size_t)N + 1, 0);
+    for (int64_t e = 0; e < n_edges; ++e) {
+        MCB_CHECK(src[e] >= 0 && src[e] < N && dst[e] >= 0 && dst[e] < N, "MC-ERR: edge endpoint out of range");
+        optr[(size_t)src[e] + 1]++; iptr[(size_t)dst[e] + 1]++;
+    }
+    for (int32_t v = 0; v < N; ++v) { optr[v + 1] += optr[v]; iptr[v + 1] += iptr[v]; }
+    std::vector<int32_t> odst((size_t)n_edges), isrc((size_t)n_edges);
+    std::vector<uint32_t> ow((size_t)n_edges), iw((size_t)n_edges);
+    {
+        std::vector<int64_t> oc(optr.begin(), optr.end() - 1), ic(iptr.begin(), iptr.end() - 1);
+        for (int64_t e = 0; e < n_edges; ++e) {
+            const double wf = std::nearbyint(w[e] * 65536.0);
+            const uint32_t wi = wf < 1.0 ? 1u : (uint32_t)wf;
+            const int64_t po = oc[src[e]]++, pi = ic[dst[e]]++;
+            odst[po] = dst[e]; ow[po] = wi;
+            isrc[pi] = src[e]; iw[pi] = wi;
+        }
+    }
+    for (int32_t r = 0; r < n_resamp; ++r) {
+        const int32_t* S = samples + (size_t)r * n_s;
+        for (int32_t q = 0; q < n_s; ++q) {
+            MCB_CHECK(S[q] >= 0 && S[q] < N, "MC-ERR: sampled node out of range");
+            MCB_CHECK(q == 0 || S[q] > S[q - 1], "MC-ERR: each resample index set must be strictly ascending");
+        }
+    }
+    std::vector<int32_t> ids;
+    for (int32_t r = rank; r < n_resamp; r += nranks) ids.push_back(r);
+    std::unique_ptr<mcb_coclust> c(new mcb_coclust());
+    c->ctx = ctx; c->N = N; c->n_local = (int32_t)ids.size();
+    c->ncl_cap = n_s / (min_mc_size > 0 ? min_mc_size + 1 : 1) + 2;
+    const int32_t nl = c->n_local;
+
+    DevBuf<int64_t> d_optr(ctx, optr.size()), d_iptr(ctx, iptr.size());
+    DevBuf<int32_t> d_odst(ctx, odst.size()), d_isrc(ctx, isrc.size());
+    DevBuf<uint32_t> d_ow(ctx, ow.size()), d_iw(ctx, iw.size());
+    DevBuf<int32_t> d_samples(ctx, (size_t)n_resamp * n_s), d_ids(ctx, (size_t)std::max(nl, 1));
+    DevBuf<uint64_t> d_seeds(ctx, (size_t)std::max(n_resamp, 1));
+    {
+        StageTimer t(ctx, "h2d_graph");
+        MCB_CUDA(cudaMemcpyAsync(d_optr.p, optr.data(), optr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        MCB_CUDA(cudaMemcpyAsync(d_iptr.p, iptr.data(), iptr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (n_edges) {
+            MCB_CUDA(cudaMemcpyAsync(d_odst.p, odst.data(), odst.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            MCB_CUDA(cudaMemcpyAsync(d_isrc.p, isrc.data(), isrc.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            MCB_CUDA(cudaMemcpyAsync(d_ow.p, ow.data(), ow.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            MCB_CUDA(cudaMemcpyAsync(d_iw.p, iw.data(), iw.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (n_resamp) {
+            MCB_CUDA(cudaMemcpyAsync(d_samples.p, samples, (size_t)n_resamp * n_s * 4, cudaMemcpyHostToDevice, ctx->stream));
+            MCB_CUDA(cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n_resamp * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (nl) MCB_CUDA(cudaMemcpyAsync(d_ids.p, ids.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    c->cnt.alloc(ctx, (size_t)N * N); c->cnt.zero();
+    c->nsamp.alloc(ctx, (size_t)N); c->nsamp.zero();
+    c->mc.alloc(ctx, (size_t)std::max(nl, 1) * N);
+    c->sweeps.alloc(ctx, (size_t)std::max(nl, 1));
+    DevBuf<int32_t> f_ws(ctx, (size_t)std::max(nl, 1) * N), status(ctx, (size_t)std::max(nl, 1));
+    DevBuf<int32_t> ws_order(ctx, (size_t)std::max(nl, 1) * N), ws_start(ctx, (size_t)std::max(nl, 1) * (c->ncl_cap + 1));
+    CoverGraph cg{N, d_optr.p, d_odst.p, d_ow.p, d_iptr.p, d_isrc.p, d_iw.p};
+    {
+        StageTimer t(ctx, "graph_cover");
+        launch_graph_cover(ctx, cg, nl, d_ids.p, n_s, d_samples.p, d_seeds.p, min_mc_size, cooling, burn_in, max_sweeps,
+                           c->ncl_cap, c->mc.p, f_ws.p, c->sweeps.p, status.p);
+    }
+    {
+        StageTimer t(ctx, "cooccur");
+        launch_cooccur(ctx, N, nl, c->mc.p, c->ncl_cap, c->cnt.p, c->nsamp.p, ws_order.p, ws_start.p);
+    }
+    std::vector<int32_t> hst((size_t)std::max(nl, 1), 0);
+    if (nl) MCB_CUDA(cudaMemcpyAsync(hst.data(), status.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int32_t q = 0; q < nl; ++q) MCB_CHECK(hst[q] == 0, "MC-ERR: graph cover ran out of cluster slots");
+    *out = c.release();
+    MCB_API_END
+}
+extern "C" void mcb_coclust_destroy(mcb_coclust* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->ctx->device);
+    delete c;
+}
+extern "C" int mcb_coclust_buffers(mcb_coclust* c, void** dev_cnt, void** dev_nsamp)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(c, "null argument");
+    if (dev_cnt) *dev_cnt = c->cnt.p;
+    if (dev_nsamp) *dev_nsamp = c->nsamp.p;
+    MCB_API_END
+}
+extern "C" int mcb_coclust_assignments(mcb_coclust* c, int32_t* host_mc, int32_t* host_sweeps, int32_t* n_local)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(c, "null argument");
+    mcb_ctx* ctx = c->ctx;
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    if (n_local) *n_local = c->n_local;
+    if (host_mc && c->n_local) MCB_CUDA(cudaMemcpyAsync(host_mc, c->mc.p, (size_t)c->n_local * c->N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_sweeps && c->n_local) MCB_CUDA(cudaMemcpyAsync(host_sweeps, c->sweeps.p, (size_t)c->n_local * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MCB_API_END
+}
+extern "C" int mcb_coclust_extract(mcb_coclust* c, int64_t* n_pairs)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(c && n_pairs, "null argument");
+    mcb_ctx* ctx = c->ctx;
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const int32_t N = c->N;
+    DevBuf<int64_t> rc(ctx, (size_t)N), offs(ctx, (size_t)N), total(ctx, 1);
+    {
+        StageTimer t(ctx, "coclust_extract", 3);
+        launch_count_pairs(ctx, N, c->cnt.p, rc.p);
+        launch_exclusive_scan_i64(ctx, rc.p, offs.p, N, total.p);
+        int64_t np = 0;
+        MCB_CUDA(cudaMemcpyAsync(&np, total.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        c->n_pairs = np;
+        c->p1.alloc(ctx, (size_t)std::max<int64_t>(np, 1));
+        c->p2.alloc(ctx, (size_t)std::max<int64_t>(np, 1));
+        c->pc.alloc(ctx, (size_t)std::max<int64_t>(np, 1));
+        launch_extract_pairs(ctx, N, c->cnt.p, offs.p, c->p1.p, c->p2.p, c->pc.p);
+    }
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_pairs = c->n_pairs;
+    MCB_API_END
+}
+extern "C" int mcb_coclust_pairs(mcb_coclust* c, int32_t* h1, int32_t* h2, int32_t* hc, int32_t* host_samples)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(c && c->n_pairs >= 0, "mcb_coclust_pairs: run mcb_coclust_extract first");
+    mcb_ctx* ctx = c->ctx;
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const size_t np = (size_t)c->n_pairs;
+    if (np) {
+        if (h1) MCB_CUDA(cudaMemcpyAsync(h1, c->p1.p, np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (h2) MCB_CUDA(cudaMemcpyAsync(h2, c->p2.p, np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (hc) MCB_CUDA(cudaMemcpyAsync(hc, c->pc.p, np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (host_samples) MCB_CUDA(cudaMemcpyAsync(host_samples, c->nsamp.p, (size_t)c->N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MCB_API_END
+}

@@ -1,0 +1,235 @@
+// balance.cu -- tgs_graph(x_knn, knn = K, k_expand, k_beta): rank-product balancing of the kNN lists
+// (reference call site R/utils.r:120).  The rule is the one cormat_to_balanced_knn states in R
+// (R/cgraph_knn_mcnorm.r:48-81):
+//     keep pair iff  K*K*k_expand - rank(i,j)*rank(j,i) > 0                (:66-68)
+//     per node keep the k_beta*K incoming edges with the best score        (:70-71)
+//     per node keep the K outgoing edges with the best score               (:73-74)
+// and the weights are the rank fractions 1 - (place-1)/K every consumer assumes
+// (R/cgraph_knn.r:46, R/mc_confusion.r:26).  Tie-breaks follow oracle/mc_oracle.c orc_balance:
+// ties on s = rank(i,j)*rank(j,i) go to the lower node index; self edges dropped unless keep_self.
+//
+// Data layout: the reverse rank rank(j,i) is found through a per-row open-addressing hash table
+// (H = 2^k >= 2*Kc slots of u32 = (column << rank_bits) | rank0) instead of a binary search or a
+// global sort, so the join costs ~1.5 random 32-byte sectors per edge.  All kernels are one CTA per
+// row with the row's keys sorted in shared memory; HBM-bound integer work.
+#include "internal.h"
+
+namespace mcb {
+
+constexpr int BAL_THREADS = 256;
+constexpr uint32_t HASH_EMPTY = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t hash_slot(uint32_t key, int log2H) { return (key * 2654435761u) >> (32 - log2H); }
+
+__global__ void __launch_bounds__(BAL_THREADS)
+build_hash_kernel(const int32_t* __restrict__ knn_col, int64_t M, int32_t Kc, int32_t H, int32_t log2H,
+                  int32_t rank_bits, uint32_t* __restrict__ table)
+{
+    extern __shared__ uint32_t stab[];      // [H]
+    for (int64_t row = blockIdx.x; row < M; row += gridDim.x) {
+        for (int q = threadIdx.x; q < H; q += BAL_THREADS) stab[q] = HASH_EMPTY;
+        __syncthreads();
+        const int32_t* kc = knn_col + row * (int64_t)Kc;
+        for (int r = threadIdx.x; r < Kc; r += BAL_THREADS) {
+            const int32_t j = kc[r];
+            if (j < 0) continue;
+            const uint32_t val = ((uint32_t)j << rank_bits) | (uint32_t)r;
+            uint32_t slot = hash_slot((uint32_t)j, log2H);
+            while (atomicCAS(&stab[slot], HASH_EMPTY, val) != HASH_EMPTY) slot = (slot + 1) & (uint32_t)(H - 1);
+        }
+        __syncthreads();
+        uint32_t* out = table + row * (int64_t)H;
+        for (int q = threadIdx.x; q < H; q += BAL_THREADS) out[q] = stab[q];
+        __syncthreads();
+    }
+}
+
+// 1-based rank of `target` in row j's list, 0 if absent
+__device__ __forceinline__ uint32_t hash_lookup(const uint32_t* __restrict__ tab, int32_t H, int32_t log2H,
+                                                int32_t rank_bits, uint32_t target)
+{
+    uint32_t slot = hash_slot(target, log2H);
+    const uint32_t rmask = (1u << rank_bits) - 1u;
+    for (int probe = 0; probe < H; ++probe) {
+        const uint32_t v = __ldg(tab + slot);
+        if (v == HASH_EMPTY) return 0u;
+        if ((v >> rank_bits) == target) return (v & rmask) + 1u;
+        slot = (slot + 1) & (uint32_t)(H - 1);
+    }
+    return 0u;
+}
+
+// mutual scores s(i, r) and the in-degree threshold of every owned row
+__global__ void __launch_bounds__(BAL_THREADS)
+mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ table, int64_t row0, int64_t rows,
+              int32_t Kc, int32_t H, int32_t log2H, int32_t rank_bits, long long smax, int strict, int keep_self,
+              int32_t kin, uint32_t* __restrict__ sym, uint64_t* __restrict__ thr_in)
+{
+    extern __shared__ uint64_t sk[];        // [pow2(Kc)]
+    int np2 = 2; while (np2 < Kc) np2 <<= 1;
+    for (int64_t lrow = blockIdx.x; lrow < rows; lrow += gridDim.x) {
+        const int64_t i = row0 + lrow;
+        const int32_t* kc = knn_col + i * (int64_t)Kc;
+        uint32_t* so = sym + lrow * (int64_t)Kc;
+        for (int r = threadIdx.x; r < np2; r += BAL_THREADS) {
+            uint64_t key = ~0ull;
+            if (r < Kc) {
+                const int32_t j = kc[r];
+                uint32_t sv = 0;
+                if (j >= 0 && (j != (int32_t)i || keep_self)) {
+                    const uint32_t rji = (j == (int32_t)i) ? (uint32_t)(r + 1)
+                                                           : hash_lookup(table + (int64_t)j * H, H, log2H, rank_bits, (uint32_t)i);
+                    if (rji) {
+                        const long long s = (long long)(r + 1) * (long long)rji;
+                        if (strict ? (s < smax) : (s <= smax)) { sv = (uint32_t)s; key = ((uint64_t)s << 32) | (uint32_t)j; }
+                    }
+                }
+                so[r] = sv;
+            }
+            sk[r] = key;
+        }
+        __syncthreads();
+        bitonic_sort_u64<BAL_THREADS>(sk, np2);
+        if (threadIdx.x == 0)
+            thr_in[i] = (kin >= 1 && kin < np2 && sk[kin] != ~0ull) ? sk[kin - 1] : ~0ull;
+        __syncthreads();
+    }
+}
+
+// out-degree prune: survivors of the target's in-degree cut, best K by (s, target)
+__global__ void __launch_bounds__(BAL_THREADS)
+prune_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ sym, const uint64_t* __restrict__ thr_in,
+             int64_t row0, int64_t rows, int32_t Kc, int32_t K, int32_t* __restrict__ out_deg,
+             int32_t* __restrict__ out_dst, int32_t* __restrict__ out_s)
+{
+    extern __shared__ uint64_t sk[];
+    __shared__ int s_n;
+    int np2 = 2; while (np2 < Kc) np2 <<= 1;
+    for (int64_t lrow = blockIdx.x; lrow < rows; lrow += gridDim.x) {
+        const int64_t i = row0 + lrow;
+        const int32_t* kc = knn_col + i * (int64_t)Kc;
+        const uint32_t* so = sym + lrow * (int64_t)Kc;
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        int local = 0;
+        for (int r = threadIdx.x; r < np2; r += BAL_THREADS) {
+            uint64_t key = ~0ull;
+            if (r < Kc) {
+                const uint32_t s = so[r];
+                if (s) {
+                    const int32_t j = kc[r];
+                    const uint64_t inkey = ((uint64_t)s << 32) | (uint32_t)i;   // edge i -> j seen from target j
+                    if (inkey <= thr_in[j]) { key = ((uint64_t)s << 32) | (uint32_t)j; ++local; }
+                }
+            }
+            sk[r] = key;
+        }
+        if (local) atomicAdd(&s_n, local);
+        __syncthreads();
+        bitonic_sort_u64<BAL_THREADS>(sk, np2);
+        const int n = s_n < K ? s_n : K;
+        if (threadIdx.x == 0) out_deg[lrow] = n;
+        for (int q = threadIdx.x; q < K; q += BAL_THREADS) {
+            const bool ok = q < n;
+            out_dst[lrow * (int64_t)K + q] = ok ? (int32_t)(uint32_t)sk[q] : -1;
+            out_s[lrow * (int64_t)K + q] = ok ? (int32_t)(sk[q] >> 32) : 0;
+        }
+        __syncthreads();
+    }
+}
+
+// (mc1, mc2, w) rows of the tgCellGraph edge table (reference R/cgraph_knn.r:22), original cell ids
+__global__ void emit_edges_kernel(const int32_t* __restrict__ out_deg, const int32_t* __restrict__ out_dst,
+                                  const int64_t* __restrict__ offs, const int32_t* __restrict__ cell_of_row,
+                                  int64_t row0, int64_t rows, int32_t K, int32_t* __restrict__ src,
+                                  int32_t* __restrict__ dst, double* __restrict__ w)
+{
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < rows * K;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t lrow = idx / K;
+        const int q = (int)(idx % K);
+        if (q >= out_deg[lrow]) continue;
+        const int64_t e = offs[lrow] + q;
+        src[e] = cell_of_row[row0 + lrow];
+        dst[e] = cell_of_row[out_dst[lrow * (int64_t)K + q]];
+        w[e] = 1.0 - (double)q / (double)K;
+    }
+}
+
+__global__ void widen_i32_kernel(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = in[i];
+}
+
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+template <typename F>
+static void ensure_smem(F* kernel, size_t smem, size_t& configured)
+{
+    MCB_CHECK(smem <= 200 * 1024, "balance: K*k_expand too large for shared memory");
+    if (smem > configured) {
+        MCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+}
+
+void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t Kc, int32_t H, int32_t rank_bits,
+                       uint32_t* table)
+{
+    if (M == 0) return;
+    static size_t configured = 0;
+    const size_t smem = (size_t)H * sizeof(uint32_t);
+    ensure_smem(build_hash_kernel, smem, configured);
+    int grid = (int)std::min<int64_t>(M, (int64_t)ctx->num_sms * 8);
+    build_hash_kernel<<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, M, Kc, H, ilog2(H), rank_bits, table);
+    MCB_LAUNCH_CHECK();
+}
+
+void launch_mutual(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* table, int64_t row0, int64_t rows,
+                   int32_t Kc, int32_t H, int32_t rank_bits, int64_t smax, int strict, int keep_self, int32_t kin,
+                   uint32_t* sym, uint64_t* thr_in)
+{
+    if (rows == 0) return;
+    int np2 = 2; while (np2 < Kc) np2 <<= 1;
+    static size_t configured = 0;
+    const size_t smem = (size_t)np2 * sizeof(uint64_t);
+    ensure_smem(mutual_kernel, smem, configured);
+    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
+    mutual_kernel<<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, table, row0, rows, Kc, H, ilog2(H), rank_bits,
+                                                             (long long)smax, strict, keep_self, kin, sym, thr_in);
+    MCB_LAUNCH_CHECK();
+}
+
+void launch_prune(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* sym, const uint64_t* thr_in, int64_t row0,
+                  int64_t rows, int32_t Kc, int32_t K, int32_t* out_deg, int32_t* out_dst, int32_t* out_s)
+{
+    if (rows == 0) return;
+    int np2 = 2; while (np2 < Kc) np2 <<= 1;
+    static size_t configured = 0;
+    const size_t smem = (size_t)np2 * sizeof(uint64_t);
+    ensure_smem(prune_kernel, smem, configured);
+    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
+    prune_kernel<<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, sym, thr_in, row0, rows, Kc, K, out_deg, out_dst, out_s);
+    MCB_LAUNCH_CHECK();
+}
+
+void launch_widen_i32(mcb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n)
+{
+    if (n == 0) return;
+    int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->num_sms * 8);
+    widen_i32_kernel<<<grid, 256, 0, ctx->stream>>>(in, out, n);
+    MCB_LAUNCH_CHECK();
+}
+
+void launch_emit_edges(mcb_ctx* ctx, const int32_t* out_deg, const int32_t* out_dst, const int64_t* offs,
+                       const int32_t* cell_of_row, int64_t row0, int64_t rows, int32_t K, int32_t* src, int32_t* dst,
+                       double* w)
+{
+    if (rows == 0) return;
+    int grid = (int)std::min<int64_t>(ceil_div(rows * K, 256), (int64_t)ctx->num_sms * 16);
+    emit_edges_kernel<<<grid, 256, 0, ctx->stream>>>(out_deg, out_dst, offs, cell_of_row, row0, rows, K, src, dst, w);
+    MCB_LAUNCH_CHECK();
+}
+
+}  // namespace mcb

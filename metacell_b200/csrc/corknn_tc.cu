@@ -1,0 +1,328 @@
+// corknn_tc.cu -- the cell x cell Pearson correlation of tgs_cor_knn (reference call site
+// R/utils.r:119) as a tcgen05 / TMEM GEMM fed by TMA, with the per-row selection fused into the
+// epilogue so the N x N matrix never touches HBM.
+//
+//   C[i][j] = sum_g Z[i][g] * Z[j][g]          Z = standardised log-feature rows (features.cu)
+//
+// Precision: 3-pass split-TF32.  Z is stored as two TF32-exact planes (Zhi + Zlo); per k-block the
+// kernel issues  hi*hi, hi*lo, lo*hi  into the same FP32 TMEM accumulator, which keeps the result
+// within ~1e-6 of fp32 (DESIGN.md "Precision").  NPASS = 1 (hi*hi only) is used by the threshold
+// sampling pass where 1e-3 accuracy is enough.
+//
+// Kernel shape (persistent, warp specialised, one CTA per SM, cta_group::1):
+//   warp 0      TMA producer : cp.async.bulk.tensor 2D tiles, 128-byte swizzle, NSTAGE-deep ring
+//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=256, K=8)
+//                              into one of two 256-column TMEM accumulators; owns TMEM alloc/dealloc
+//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32, then either
+//                                STORE  : write the fp32 tile (sample block of the threshold pass), or
+//                                FILTER : keep (i, j, c) with c >= thr[i], j != i -> append to the
+//                                         row's candidate buffer (global atomics; ~1.5% of elements)
+//   Double-buffered TMEM lets the epilogue of tile t overlap the MMAs of tile t+1.
+// Tile order: groups of GROUP_M row tiles sweep the column tiles together so the A panel of the
+// group (GROUP_M x 1 MB) stays L2 resident and each B tile is fetched from HBM once per group.
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace mcb {
+
+using namespace ptx;
+
+constexpr int BM = 128;            // rows of C per tile (TMEM lanes)
+constexpr int BN = 256;            // columns of C per tile (TMEM columns per accumulator)
+constexpr int BK = 32;             // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int UMMA_K = 8;          // tf32
+constexpr int GROUP_M = 16;
+constexpr int TC_THREADS = 192;    // 6 warps
+constexpr uint32_t TMEM_COLS = 512;
+
+template <int NPASS> struct TcCfg {
+    static constexpr int A_PLANES = NPASS == 3 ? 2 : 1;
+    static constexpr int A_BYTES = BM * BK * 4;                      // 16 KB per plane
+    static constexpr int B_BYTES = BN * BK * 4;                      // 32 KB per plane
+    static constexpr int STAGE_BYTES = A_PLANES * (A_BYTES + B_BYTES);
+    static constexpr int NSTAGE = NPASS == 3 ? 2 : 4;
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct TcParams {
+    int64_t a_row0;      // first row of A (global row index of local row 0), used for the self test
+    int64_t a_rows;      // valid local rows
+    int64_t b_rows;      // valid columns
+    int32_t num_kb;      // Gpad / BK
+    int32_t m_tiles, n_tiles;
+    // STORE
+    float* C; int64_t ldc;
+    // FILTER
+    const float* thr; uint64_t* cand; uint32_t* cnt; int32_t cap;
+};
+
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& m_blk, int& n_blk)
+{
+    const int per_group = GROUP_M * n_tiles;
+    const int group = tile / per_group;
+    const int within = tile - group * per_group;
+    const int gm0 = group * GROUP_M;
+    const int gmc = min(GROUP_M, m_tiles - gm0);
+    m_blk = gm0 + within % gmc;
+    n_blk = within / gmc;
+}
+
+template <int NPASS, int MODE>   // MODE 0 = STORE, 1 = FILTER
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+              const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
+              const TcParams prm)
+{
+    using Cfg = TcCfg<NPASS>;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128-byte swizzle atoms
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                       // [NSTAGE]
+    uint64_t* empty_bar = bars + Cfg::NSTAGE;        // [NSTAGE]
+    uint64_t* tfull_bar = bars + 2 * Cfg::NSTAGE;    // [2]
+    uint64_t* tempty_bar = bars + 2 * Cfg::NSTAGE + 2;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::NSTAGE + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = prm.m_tiles * prm.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_a_hi); prefetch_tensormap(&map_b_hi);
+        if (NPASS == 3) { prefetch_tensormap(&map_a_lo); prefetch_tensormap(&map_b_lo); }
+        for (int s = 0; s < Cfg::NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int m_blk, n_blk;
+                tile_coords(tile, prm.m_tiles, prm.n_tiles, m_blk, n_blk);
+                const int32_t m0 = (int32_t)(prm.a_row0 + (int64_t)m_blk * BM);
+                const int32_t n0 = n_blk * BN;
+                for (int kb = 0; kb < prm.num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(st, &map_a_hi, &full_bar[stage], kb * BK, m0);
+                    tma_load_2d(st + Cfg::A_PLANES * Cfg::A_BYTES, &map_b_hi, &full_bar[stage], kb * BK, n0);
+                    if (NPASS == 3) {
+                        tma_load_2d(st + Cfg::A_BYTES, &map_a_lo, &full_bar[stage], kb * BK, m0);
+                        tma_load_2d(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &map_b_lo, &full_bar[stage], kb * BK, n0);
+                    }
+                    if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < prm.num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t a_hi = make_sw128_kmajor_desc(st);
+                    const uint64_t b_hi = make_sw128_kmajor_desc(st + Cfg::A_PLANES * Cfg::A_BYTES);
+                    const uint64_t a_lo = make_sw128_kmajor_desc(st + Cfg::A_BYTES);
+                    const uint64_t b_lo = make_sw128_kmajor_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);     // 32 bytes per k step
+                        mma_tf32_ss(d_tmem, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (NPASS == 3) {
+                            mma_tf32_ss(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
+                            mma_tf32_ss(d_tmem, a_lo + koff, b_hi + koff, idesc, 1u);
+                        }
+                    }
+                    tc_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
+                    if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(&tfull_bar[acc]);                // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===== epilogue warps 2..5 : TMEM lanes (warp % 4) * 32 .. + 31 =====
+        const int quarter = warp & 3;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            int m_blk, n_blk;
+            tile_coords(tile, prm.m_tiles, prm.n_tiles, m_blk, n_blk);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            const int64_t lrow = (int64_t)m_blk * BM + quarter * 32 + lane;       // local row
+            const bool row_ok = lrow < prm.a_rows;
+            const int64_t n0 = (int64_t)n_blk * BN;
+            float t = 0.f;
+            if (MODE == 1) t = row_ok ? prm.thr[lrow] : __int_as_float(0x7f800000);
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
+                tmem_ld_wait();
+                const int64_t col0 = n0 + c * 32;
+                if (MODE == 0) {
+                    if (row_ok && col0 < prm.b_rows) {
+                        float* dst = prm.C + lrow * prm.ldc + col0;
+                        if (col0 + 32 <= prm.b_rows) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                reinterpret_cast<float4*>(dst)[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                                __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q)
+                                if (col0 + q < prm.b_rows) dst[q] = __uint_as_float(v[q]);
+                        }
+                    }
+                } else {
+                    const int64_t self = prm.a_row0 + lrow;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) {
+                        const float cv = __uint_as_float(v[q]);
+                        if (cv >= t) {
+                            const int64_t col = col0 + q;
+                            if (col < prm.b_rows && col != self) {
+                                const uint32_t pos = atomicAdd(&prm.cnt[lrow], 1u);
+                                if (pos < (uint32_t)prm.cap) prm.cand[lrow * (int64_t)prm.cap + pos] = cand_key(cv, (uint32_t)col);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc<TMEM_COLS>(tmem_base); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+void tc_init()
+{
+    if (g_encode) return;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MCB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    MCB_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+// 2D fp32 tensor [rows][Gpad] row-major; box = BK columns x box_rows rows; 128-byte swizzle
+static CUtensorMap make_map(const float* base, int64_t rows, int32_t Gpad, int box_rows)
+{
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)Gpad, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)Gpad * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[160];
+        snprintf(b, sizeof(b), "cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld Gpad=%d)", (int)r, (long long)rows, Gpad);
+        throw Error(2, b);
+    }
+    return m;
+}
+
+template <int NPASS, int MODE>
+static void launch_tc(mcb_ctx* ctx, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
+                      const CUtensorMap& bl, const TcParams& prm)
+{
+    using Cfg = TcCfg<NPASS>;
+    static bool configured = false;
+    if (!configured) {
+        MCB_CUDA(cudaFuncSetAttribute(tc_cor_kernel<NPASS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int total = prm.m_tiles * prm.n_tiles;
+    const int grid = std::min(total, ctx->num_sms);
+    tc_cor_kernel<NPASS, MODE><<<grid, TC_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(ah, al, bh, bl, prm);
+    MCB_LAUNCH_CHECK();
+}
+
+void launch_tc_store(mcb_ctx* ctx, const float* Ahi, int64_t a_rows_alloc, const float* Bhi, int64_t b_rows_alloc,
+                     int32_t Gpad, float* C, int64_t ldc, int64_t a_rows, int64_t b_rows)
+{
+    if (a_rows == 0 || b_rows == 0) return;
+    tc_init();
+    MCB_CHECK(Gpad % BK == 0, "Gpad must be a multiple of 32");
+    const CUtensorMap ah = make_map(Ahi, a_rows_alloc, Gpad, BM);
+    const CUtensorMap bh = make_map(Bhi, b_rows_alloc, Gpad, BN);
+    TcParams prm{};
+    prm.a_row0 = 0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK;
+    prm.m_tiles = (int32_t)ceil_div(a_rows, BM); prm.n_tiles = (int32_t)ceil_div(b_rows, BN);
+    prm.C = C; prm.ldc = ldc;
+    launch_tc<1, 0>(ctx, ah, ah, bh, bh, prm);
+}
+
+void launch_tc_filter(mcb_ctx* ctx, const float* Zhi, const float* Zlo, int64_t rows_alloc, int64_t a_row0,
+                      int64_t a_rows, int64_t b_rows, int32_t Gpad, const float* thr, uint64_t* cand,
+                      uint32_t* cnt, int32_t cap)
+{
+    if (a_rows == 0 || b_rows == 0) return;
+    tc_init();
+    MCB_CHECK(Gpad % BK == 0, "Gpad must be a multiple of 32");
+    const CUtensorMap ah = make_map(Zhi, rows_alloc, Gpad, BM);
+    const CUtensorMap al = make_map(Zlo, rows_alloc, Gpad, BM);
+    const CUtensorMap bh = make_map(Zhi, rows_alloc, Gpad, BN);
+    const CUtensorMap bl = make_map(Zlo, rows_alloc, Gpad, BN);
+    TcParams prm{};
+    prm.a_row0 = a_row0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK;
+    prm.m_tiles = (int32_t)ceil_div(a_rows, BM); prm.n_tiles = (int32_t)ceil_div(b_rows, BN);
+    prm.thr = thr; prm.cand = cand; prm.cnt = cnt; prm.cap = cap;
+    launch_tc<3, 1>(ctx, ah, al, bh, bl, prm);
+}
+
+// validation entry: full 3-pass product stored to C (used by tests to check the tensor-core path
+// element by element against the SIMT kernel and fp64)
+void launch_tc_store3(mcb_ctx* ctx, const float* Zhi, const float* Zlo, int64_t rows_alloc, int64_t a_rows,
+                      int64_t b_rows, int32_t Gpad, float* C, int64_t ldc)
+{
+    if (a_rows == 0 || b_rows == 0) return;
+    tc_init();
+    const CUtensorMap ah = make_map(Zhi, rows_alloc, Gpad, BM);
+    const CUtensorMap al = make_map(Zlo, rows_alloc, Gpad, BM);
+    const CUtensorMap bh = make_map(Zhi, rows_alloc, Gpad, BN);
+    const CUtensorMap bl = make_map(Zlo, rows_alloc, Gpad, BN);
+    TcParams prm{};
+    prm.a_row0 = 0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK;
+    prm.m_tiles = (int32_t)ceil_div(a_rows, BM); prm.n_tiles = (int32_t)ceil_div(b_rows, BN);
+    prm.C = C; prm.ldc = ldc;
+    launch_tc<3, 0>(ctx, ah, al, bh, bl, prm);
+}
+
+}  // namespace mcb

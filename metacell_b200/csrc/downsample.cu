@@ -1,0 +1,196 @@
+// downsample.cu -- scm_downsamp (reference R/utils.r:30-69) and colSums on a device-resident CSC.
+//
+// Semantics restated from the reference:
+//   umis = umis[, colSums(umis) >= n]                              (R/utils.r:34)
+//   per cell: tabulate(sample(rep(1:m, times = v), size = n))      (R/utils.r:36-39)
+// i.e. a uniformly random floor(n)-subset of the cell's UMIs, counted per gene.  R's Mersenne
+// Twister stream is not reproduced (DESIGN.md "RNG"): UMI t of cell c gets the 64-bit key
+// (Philox4x32-10(seed; t>>2, c)[t&3] << 32) | t and the floor(n) smallest keys are kept -- the same
+// distribution as sample(replace = FALSE), independent of evaluation order, and bit-identical
+// to the CPU oracle (oracle/mc_oracle.c orc_downsample).
+//
+// HBM-bound integer work: one CTA per cell, the counts are read twice (sum, final count) and
+// written once; the keys are regenerated in registers per radix pass instead of being stored.
+#include "internal.h"
+
+namespace mcb {
+
+constexpr int DS_THREADS = 256;
+
+__global__ void convert_x_kernel(const double* __restrict__ xd, uint32_t* __restrict__ x, int64_t nnz)
+{
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x) {
+        double v = xd[e];
+        x[e] = v > 0.0 ? (uint32_t)__double2ll_rn(v) : 0u;
+    }
+}
+__global__ void x_to_double_kernel(const uint32_t* __restrict__ x, double* __restrict__ xd, int64_t nnz)
+{
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
+        xd[e] = (double)x[e];
+}
+
+__global__ void col_sums_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t* __restrict__ x,
+                                int64_t* __restrict__ tot)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp; c < ncells; c += nwarps) {
+        long long s = 0;
+        for (int64_t e = p[c] + lane; e < p[c + 1]; e += 32) s += x[e];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) tot[c] = s;
+    }
+}
+
+__device__ __forceinline__ uint64_t ds_key(uint32_t o, uint32_t t) { return ((uint64_t)o << 32) | (uint64_t)t; }
+
+// block-wide exclusive scan of one int64 per thread; returns exclusive prefix, *total = block sum
+__device__ __forceinline__ long long block_excl_scan(long long v, long long* warp_tot /* [NT/32 + 1] */, long long* total)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    long long inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        long long u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    __syncthreads();                       // protect warp_tot reuse
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    long long base = 0, all = 0;
+    const int nw = blockDim.x >> 5;
+    for (int q = 0; q < nw; ++q) { long long t = warp_tot[q]; if (q < w) base += t; all += t; }
+    *total = all;
+    return base + inc - v;
+}
+
+__global__ void __launch_bounds__(DS_THREADS)
+downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t* __restrict__ x, double n,
+                  uint32_t seed_lo, uint32_t seed_hi, int add_non_dsamp, uint32_t* __restrict__ out_x,
+                  uint8_t* __restrict__ kept)
+{
+    __shared__ uint32_t hist[256];
+    __shared__ long long warp_tot[DS_THREADS / 32 + 1];
+    __shared__ unsigned long long s_prefix, s_thr;
+    __shared__ long long s_krem;
+    __shared__ int s_done;
+
+    const long long d = (long long)floor(n);
+    for (int64_t c = blockIdx.x; c < ncells; c += gridDim.x) {
+        const int64_t e0 = p[c], e1 = p[c + 1];
+        // 1. column sum
+        long long part = 0;
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += DS_THREADS) part += x[e];
+        long long tot;
+        (void)block_excl_scan(part, warp_tot, &tot);
+        if ((double)tot < n) {             // dropped cell (R/utils.r:34)
+            for (int64_t e = e0 + threadIdx.x; e < e1; e += DS_THREADS) out_x[e] = add_non_dsamp ? x[e] : 0u;
+            if (threadIdx.x == 0) kept[c] = 0;
+            continue;
+        }
+        if (threadIdx.x == 0) kept[c] = 1;
+        if (tot == d) {                    // every UMI is drawn
+            for (int64_t e = e0 + threadIdx.x; e < e1; e += DS_THREADS) out_x[e] = x[e];
+            continue;
+        }
+        // 2. radix select of the d-th smallest 64-bit key (index d-1), 8 bits per pass from the top
+        if (threadIdx.x == 0) { s_prefix = 0ull; s_krem = d - 1; s_done = 0; s_thr = ~0ull; }
+        __syncthreads();
+        const uint32_t c_lo = (uint32_t)c, c_hi = (uint32_t)((uint64_t)c >> 32);
+        const long long ngroups = (tot + 3) >> 2;
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            const unsigned long long decided = pass == 0 ? 0ull : (~0ull << (shift + 8));
+            const unsigned long long prefix = s_prefix;
+            hist[threadIdx.x] = 0;         // DS_THREADS == 256
+            __syncthreads();
+            for (long long g = threadIdx.x; g < ngroups; g += DS_THREADS) {
+                uint32_t o[4];
+                philox4x32_10((uint32_t)g, c_lo, c_hi, TAG_DOWNSAMP, seed_lo, seed_hi, o);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const long long t = (g << 2) + q;
+                    if (t < tot) {
+                        const uint64_t key = ds_key(o[q], (uint32_t)t);
+                        if ((key & decided) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                long long k = s_krem, cum = 0;
+                int dg = 0;
+                for (; dg < 256; ++dg) { if (cum + (long long)hist[dg] > k) break; cum += hist[dg]; }
+                const unsigned long long np = prefix | ((unsigned long long)dg << shift);
+                s_prefix = np;
+                s_krem = k - cum;
+                if (k - cum == (long long)hist[dg] - 1 || pass == 7) {
+                    // the bucket's largest element is the threshold: everything in it is kept
+                    s_thr = np | (shift ? ((1ull << shift) - 1ull) : 0ull);
+                    s_done = 1;
+                }
+            }
+            __syncthreads();
+            if (s_done) break;
+        }
+        const uint64_t thr = s_thr;
+        // 3. per stored entry: how many of its UMIs have key <= thr
+        long long run = 0;
+        for (int64_t base = e0; base < e1; base += DS_THREADS) {
+            const int64_t e = base + threadIdx.x;
+            const long long xe = e < e1 ? (long long)x[e] : 0;
+            long long chunk_tot;
+            const long long start = run + block_excl_scan(xe, warp_tot, &chunk_tot);
+            run += chunk_tot;
+            if (e < e1) {
+                uint32_t cnt = 0;
+                long long cur_g = -1;
+                uint32_t o[4] = {0, 0, 0, 0};
+                for (long long t = start; t < start + xe; ++t) {
+                    const long long g = t >> 2;
+                    if (g != cur_g) { philox4x32_10((uint32_t)g, c_lo, c_hi, TAG_DOWNSAMP, seed_lo, seed_hi, o); cur_g = g; }
+                    cnt += (ds_key(o[t & 3], (uint32_t)t) <= thr) ? 1u : 0u;
+                }
+                out_x[e] = cnt;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+void launch_convert_x(mcb_ctx* ctx, const double* d_xd, uint32_t* d_x, int64_t nnz)
+{
+    if (nnz == 0) return;
+    int grid = (int)std::min<int64_t>(ceil_div(nnz, 256), (int64_t)ctx->num_sms * 16);
+    convert_x_kernel<<<grid, 256, 0, ctx->stream>>>(d_xd, d_x, nnz);
+    MCB_LAUNCH_CHECK();
+}
+void launch_x_to_double(mcb_ctx* ctx, const uint32_t* d_x, double* d_xd, int64_t nnz)
+{
+    if (nnz == 0) return;
+    int grid = (int)std::min<int64_t>(ceil_div(nnz, 256), (int64_t)ctx->num_sms * 16);
+    x_to_double_kernel<<<grid, 256, 0, ctx->stream>>>(d_x, d_xd, nnz);
+    MCB_LAUNCH_CHECK();
+}
+void launch_col_sums(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const uint32_t* x, int64_t* tot)
+{
+    if (ncells == 0) return;
+    int grid = (int)std::min<int64_t>(ceil_div(ncells, 8), (int64_t)ctx->num_sms * 16);
+    col_sums_kernel<<<grid, 256, 0, ctx->stream>>>(ncells, p, x, tot);
+    MCB_LAUNCH_CHECK();
+}
+void launch_downsample(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const uint32_t* x, double n, uint64_t seed,
+                       int add_non_dsamp, uint32_t* out_x, uint8_t* kept)
+{
+    if (ncells == 0) return;
+    MCB_CHECK(n >= 1.0, "MC-ERR: downsample depth must be >= 1");
+    int grid = (int)std::min<int64_t>(ncells, (int64_t)ctx->num_sms * 8);
+    downsample_kernel<<<grid, DS_THREADS, 0, ctx->stream>>>(ncells, p, x, n, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                             add_non_dsamp, out_x, kept);
+    MCB_LAUNCH_CHECK();
+}
+
+}  // namespace mcb

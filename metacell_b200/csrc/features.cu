@@ -1,0 +1,251 @@
+// features.cu -- gset_get_feat_mat row subset (reference R/gset.r:192-197) + the bknn transform
+// log2(1 + k_nonz_exp * u) (R/cgraph_knn.r:13-14, k = scm_k_nonz_exp = 7) + per-cell
+// standardisation, so that Pearson cor(i, j) (what tgs_cor_knn computes, R/utils.r:119) becomes a
+// plain dot product of rows of Z.
+//
+// Layout in HBM: Z is [Mpad][Gpad] fp32 row-major (one row per *valid* cell, K-major for both
+// GEMM operands), stored as two TF32-exact planes Zhi + Zlo = fp32(z) for the 3-pass split-TF32
+// contraction.  Gpad is G rounded up to 32 (one 128-byte swizzle atom per k-block); padded columns
+// and padded rows are zero.  Cells whose feature vector has zero variance (NA correlations in R,
+// R/cgraph_knn_mcnorm.r:25) are dropped here: rowpos compacts the valid cells.
+//
+// HBM-bound sparse-to-dense work: read nnz * 8 B twice, write M * Gpad * 8 B once, coalesced.
+#include "internal.h"
+
+namespace mcb {
+
+// one warp per cell: sum / sum of squares of the transformed feature entries in fp64
+__global__ void feat_stats_kernel(int64_t ncells, const int64_t* __restrict__ p, const int32_t* __restrict__ ridx,
+                                  const uint32_t* __restrict__ x, const int32_t* __restrict__ feat_map, int32_t G,
+                                  double k_nonz, double* __restrict__ mu_out, double* __restrict__ inv_out,
+                                  int32_t* __restrict__ valid)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp; c < ncells; c += nwarps) {
+        double s = 0.0;
+        int cnt = 0;
+        for (int64_t e = p[c] + lane; e < p[c + 1]; e += 32) {
+            const uint32_t u = x[e];
+            if (u == 0) continue;
+            if (feat_map[ridx[e]] < 0) continue;
+            s += log2(1.0 + k_nonz * (double)u);
+            ++cnt;
+        }
+        s = warp_reduce_sum(s);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        const double mu = s / (double)G;
+        double s2 = 0.0;                     // second pass (entries are L1/L2 hot): sum (v - mu)^2
+        for (int64_t e = p[c] + lane; e < p[c + 1]; e += 32) {
+            const uint32_t u = x[e];
+            if (u == 0) continue;
+            if (feat_map[ridx[e]] < 0) continue;
+            const double dlt = log2(1.0 + k_nonz * (double)u) - mu;
+            s2 += dlt * dlt;
+        }
+        s2 = warp_reduce_sum(s2);
+        if (lane == 0) {
+            // the (G - cnt) zero entries each contribute mu^2
+            const double ss = s2 + (double)(G - cnt) * mu * mu;
+            const bool ok = cnt > 0 && ss >= 1e-20;
+            mu_out[c] = mu;
+            inv_out[c] = ok ? 1.0 / sqrt(ss) : 0.0;
+            valid[c] = ok ? 1 : 0;
+        }
+    }
+}
+
+// single-block exclusive scan (n up to a few million; negligible next to the GEMM)
+template <typename T>
+__global__ void __launch_bounds__(1024) excl_scan_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t n,
+                                                          T* __restrict__ total)
+{
+    __shared__ T warp_tot[32];
+    __shared__ T carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const T v = i < n ? in[i] : (T)0;
+        T inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        T wbase = 0, all = 0;
+        for (int q = 0; q < 32; ++q) { T t = warp_tot[q]; if (q < w) wbase += t; all += t; }
+        const T carry = carry_s;
+        if (i < n) out[i] = carry + wbase + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + all;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry_s;
+}
+
+// one CTA per cell: build the standardised row in shared memory, write the hi/lo planes coalesced
+constexpr int FR_THREADS = 128;
+__global__ void __launch_bounds__(FR_THREADS)
+feat_rows_kernel(int64_t ncells, const int64_t* __restrict__ p, const int32_t* __restrict__ ridx,
+                 const uint32_t* __restrict__ x, const int32_t* __restrict__ feat_map, int32_t G, int32_t Gpad,
+                 double k_nonz, const double* __restrict__ mu_in, const double* __restrict__ inv_in,
+                 const int32_t* __restrict__ valid, const int32_t* __restrict__ rowpos, float* __restrict__ Zhi,
+                 float* __restrict__ Zlo, int32_t* __restrict__ cell_of_row)
+{
+    extern __shared__ float srow[];        // [Gpad]
+    for (int64_t c = blockIdx.x; c < ncells; c += gridDim.x) {
+        if (!valid[c]) continue;           // uniform per block
+        const double mu = mu_in[c], inv = inv_in[c];
+        const float base = (float)((0.0 - mu) * inv);
+        for (int g = threadIdx.x; g < Gpad; g += FR_THREADS) srow[g] = g < G ? base : 0.0f;
+        __syncthreads();
+        for (int64_t e = p[c] + threadIdx.x; e < p[c + 1]; e += FR_THREADS) {
+            const uint32_t u = x[e];
+            if (u == 0) continue;
+            const int32_t f = feat_map[ridx[e]];
+            if (f < 0) continue;
+            const double v = log2(1.0 + k_nonz * (double)u);
+            srow[f] = (float)((v - mu) * inv);
+        }
+        __syncthreads();
+        const int64_t r = rowpos[c];
+        float* hi = Zhi + r * (int64_t)Gpad;
+        float* lo = Zlo + r * (int64_t)Gpad;
+        for (int g = threadIdx.x; g < Gpad; g += FR_THREADS) {
+            const float z = srow[g];
+            const float h = tf32_round(z);
+            hi[g] = h;
+            lo[g] = tf32_round(z - h);
+        }
+        if (threadIdx.x == 0) cell_of_row[r] = (int32_t)c;
+        __syncthreads();
+    }
+}
+
+// out[q][:] = Z[rows[q]][:]   (builds the contiguous sample operand of the threshold pass)
+__global__ void gather_rows_kernel(const float* __restrict__ Z, int32_t Gpad, const int32_t* __restrict__ rows,
+                                   int32_t nrows, float* __restrict__ out)
+{
+    const int vec = Gpad >> 2;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (int64_t)nrows * vec;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = idx / vec;
+        const int v = (int)(idx % vec);
+        const int32_t r = rows[q];
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r >= 0) val = reinterpret_cast<const float4*>(Z + (int64_t)r * Gpad)[v];
+        reinterpret_cast<float4*>(out + q * (int64_t)Gpad)[v] = val;
+    }
+}
+
+// ---- dense input (tgs_cor_graph(x = feat, ...), reference R/utils.r:115): x is the R matrix
+// genes x cells, column-major, i.e. one contiguous fp64 vector of G values per cell -------------
+__global__ void __launch_bounds__(128)
+dense_stats_kernel(int64_t ncells, const double* __restrict__ x, int32_t G, double* __restrict__ mu_out,
+                   double* __restrict__ inv_out, int32_t* __restrict__ valid)
+{
+    __shared__ double red[4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int64_t c = blockIdx.x; c < ncells; c += gridDim.x) {
+        const double* v = x + c * (int64_t)G;
+        double s = 0.0;
+        for (int g = threadIdx.x; g < G; g += 128) s += v[g];
+        s = warp_reduce_sum(s);
+        if (lane == 0) red[w] = s;
+        __syncthreads();
+        const double mu = (red[0] + red[1] + red[2] + red[3]) / (double)G;
+        __syncthreads();
+        double s2 = 0.0;
+        for (int g = threadIdx.x; g < G; g += 128) { const double d = v[g] - mu; s2 += d * d; }
+        s2 = warp_reduce_sum(s2);
+        if (lane == 0) red[w] = s2;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double ss = red[0] + red[1] + red[2] + red[3];
+            const bool ok = ss >= 1e-20;      // also false for NaN
+            mu_out[c] = mu; inv_out[c] = ok ? 1.0 / sqrt(ss) : 0.0; valid[c] = ok ? 1 : 0;
+        }
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(128)
+dense_rows_kernel(int64_t ncells, const double* __restrict__ x, int32_t G, int32_t Gpad, const double* __restrict__ mu_in,
+                  const double* __restrict__ inv_in, const int32_t* __restrict__ valid, const int32_t* __restrict__ rowpos,
+                  float* __restrict__ Zhi, float* __restrict__ Zlo, int32_t* __restrict__ cell_of_row)
+{
+    for (int64_t c = blockIdx.x; c < ncells; c += gridDim.x) {
+        if (!valid[c]) continue;
+        const double mu = mu_in[c], inv = inv_in[c];
+        const double* v = x + c * (int64_t)G;
+        const int64_t r = rowpos[c];
+        for (int g = threadIdx.x; g < Gpad; g += 128) {
+            const float z = g < G ? (float)((v[g] - mu) * inv) : 0.0f;
+            const float h = tf32_round(z);
+            Zhi[r * (int64_t)Gpad + g] = h;
+            Zlo[r * (int64_t)Gpad + g] = tf32_round(z - h);
+        }
+        if (threadIdx.x == 0) cell_of_row[r] = (int32_t)c;
+    }
+}
+
+void launch_dense_stats(mcb_ctx* ctx, int64_t ncells, const double* x, int32_t G, double* mu, double* inv, int32_t* valid)
+{
+    if (ncells == 0) return;
+    int grid = (int)std::min<int64_t>(ncells, (int64_t)ctx->num_sms * 16);
+    dense_stats_kernel<<<grid, 128, 0, ctx->stream>>>(ncells, x, G, mu, inv, valid);
+    MCB_LAUNCH_CHECK();
+}
+void launch_dense_rows(mcb_ctx* ctx, int64_t ncells, const double* x, int32_t G, int32_t Gpad, const double* mu,
+                       const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zhi, float* Zlo,
+                       int32_t* cell_of_row)
+{
+    if (ncells == 0) return;
+    int grid = (int)std::min<int64_t>(ncells, (int64_t)ctx->num_sms * 16);
+    dense_rows_kernel<<<grid, 128, 0, ctx->stream>>>(ncells, x, G, Gpad, mu, inv, valid, rowpos, Zhi, Zlo, cell_of_row);
+    MCB_LAUNCH_CHECK();
+}
+
+void launch_feat_stats(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const int32_t* ridx, const uint32_t* x,
+                       const int32_t* feat_map, int32_t G, double k_nonz, double* mu, double* inv, int32_t* valid)
+{
+    if (ncells == 0) return;
+    int grid = (int)std::min<int64_t>(ceil_div(ncells, 8), (int64_t)ctx->num_sms * 16);
+    feat_stats_kernel<<<grid, 256, 0, ctx->stream>>>(ncells, p, ridx, x, feat_map, G, k_nonz, mu, inv, valid);
+    MCB_LAUNCH_CHECK();
+}
+void launch_exclusive_scan_i32(mcb_ctx* ctx, const int32_t* in, int32_t* out, int64_t n, int32_t* total)
+{
+    excl_scan_kernel<int32_t><<<1, 1024, 0, ctx->stream>>>(in, out, n, total);
+    MCB_LAUNCH_CHECK();
+}
+void launch_exclusive_scan_i64(mcb_ctx* ctx, const int64_t* in, int64_t* out, int64_t n, int64_t* total)
+{
+    excl_scan_kernel<long long><<<1, 1024, 0, ctx->stream>>>((const long long*)in, (long long*)out, n, (long long*)total);
+    MCB_LAUNCH_CHECK();
+}
+void launch_feat_rows(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const int32_t* ridx, const uint32_t* x,
+                      const int32_t* feat_map, int32_t G, int32_t Gpad, double k_nonz, const double* mu,
+                      const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zhi, float* Zlo,
+                      int32_t* cell_of_row)
+{
+    if (ncells == 0) return;
+    int grid = (int)std::min<int64_t>(ncells, (int64_t)ctx->num_sms * 16);
+    feat_rows_kernel<<<grid, FR_THREADS, (size_t)Gpad * sizeof(float), ctx->stream>>>(
+        ncells, p, ridx, x, feat_map, G, Gpad, k_nonz, mu, inv, valid, rowpos, Zhi, Zlo, cell_of_row);
+    MCB_LAUNCH_CHECK();
+}
+void launch_gather_rows(mcb_ctx* ctx, const float* Z, int32_t Gpad, const int32_t* rows, int32_t nrows, float* out)
+{
+    if (nrows == 0) return;
+    int grid = (int)std::min<int64_t>(ceil_div((int64_t)nrows * (Gpad / 4), 256), (int64_t)ctx->num_sms * 16);
+    gather_rows_kernel<<<grid, 256, 0, ctx->stream>>>(Z, Gpad, rows, nrows, out);
+    MCB_LAUNCH_CHECK();
+}
+
+}  // namespace mcb

@@ -1,0 +1,142 @@
+// internal.h -- host-side structures behind the opaque handles of include/mcb200.h and the
+// launcher prototypes of the CUDA stages.  Not part of the ABI.
+#pragma once
+#include "common.cuh"
+#include <algorithm>
+#include <memory>
+#include <vector>
+#include <string>
+
+struct mcb_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr;
+    // options
+    int gemm_impl = 0;       // 0 tcgen05, 1 simt
+    int profile = 0;
+    int keep_self = 0;
+    int thresh_strict = 1;
+    // stage timers
+    struct Stage { const char* name; cudaEvent_t a, b; int64_t launches; };
+    std::vector<Stage> stages;
+    struct Agg { const char* name; float ms; int64_t launches; };
+    std::vector<Agg> agg;
+};
+
+namespace mcb {
+
+// stream-ordered device buffer from the context's pool (memory stays cached in the pool)
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    mcb_ctx* ctx = nullptr;
+    DevBuf() {}
+    DevBuf(mcb_ctx* c, size_t count) { alloc(c, count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept { p = o.p; n = o.n; ctx = o.ctx; o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; n = o.n; ctx = o.ctx; o.p = nullptr; o.n = 0; return *this; }
+    void alloc(mcb_ctx* c, size_t count)
+    {
+        release();
+        ctx = c; n = count;
+        if (count == 0) { p = nullptr; return; }
+        MCB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), c->stream));
+    }
+    void zero() { if (p) MCB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx->stream)); }
+    void release()
+    {
+        if (p) cudaFreeAsync(p, ctx->stream);
+        p = nullptr; n = 0;
+    }
+    ~DevBuf() { release(); }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+struct StageTimer {
+    mcb_ctx* ctx; int idx = -1;
+    StageTimer(mcb_ctx* c, const char* name, int64_t launches = 1);
+    ~StageTimer();
+};
+
+// ---- launchers (each enqueues on ctx->stream; no host sync unless stated) -------------------
+
+// downsample.cu
+void launch_convert_x(mcb_ctx* ctx, const double* d_xd, uint32_t* d_x, int64_t nnz);
+void launch_col_sums(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const uint32_t* x, int64_t* tot);
+void launch_downsample(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const uint32_t* x, double n, uint64_t seed,
+                       int add_non_dsamp, uint32_t* out_x, uint8_t* kept);
+void launch_x_to_double(mcb_ctx* ctx, const uint32_t* d_x, double* d_xd, int64_t nnz);
+
+// features.cu
+void launch_feat_stats(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const int32_t* ridx, const uint32_t* x,
+                       const int32_t* feat_map, int32_t G, double k_nonz, double* mu, double* inv, int32_t* valid);
+void launch_exclusive_scan_i32(mcb_ctx* ctx, const int32_t* in, int32_t* out, int64_t n, int32_t* total);
+void launch_feat_rows(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const int32_t* ridx, const uint32_t* x,
+                      const int32_t* feat_map, int32_t G, int32_t Gpad, double k_nonz, const double* mu,
+                      const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zhi, float* Zlo,
+                      int32_t* cell_of_row);
+void launch_dense_stats(mcb_ctx* ctx, int64_t ncells, const double* x, int32_t G, double* mu, double* inv, int32_t* valid);
+void launch_dense_rows(mcb_ctx* ctx, int64_t ncells, const double* x, int32_t G, int32_t Gpad, const double* mu,
+                       const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zhi, float* Zlo,
+                       int32_t* cell_of_row);
+void launch_gather_rows(mcb_ctx* ctx, const float* Z, int32_t Gpad, const int32_t* rows, int32_t nrows, float* out);
+
+// corknn_simt.cu : C[i][j] = sum_g (Ahi+Alo)[i][g] * (Bhi+Blo)[j][g] in fp32 on the CUDA cores
+void launch_simt_store(mcb_ctx* ctx, const float* Ahi, const float* Alo, int64_t a_rows, const float* Bhi,
+                       const float* Blo, int64_t b_rows, int32_t Gpad, float* C, int64_t ldc);
+void launch_simt_filter(mcb_ctx* ctx, const float* Ahi, const float* Alo, int64_t a_row0, int64_t a_rows,
+                        const float* Bhi, const float* Blo, int64_t b_rows, int32_t Gpad, const float* thr,
+                        uint64_t* cand, uint32_t* cnt, int32_t cap);
+
+// corknn_tc.cu : the tcgen05 / TMEM / TMA kernels
+void tc_init();   // resolves cuTensorMapEncodeTiled
+void launch_tc_store(mcb_ctx* ctx, const float* Ahi, int64_t a_rows_pad, const float* Bhi, int64_t b_rows_pad,
+                     int32_t Gpad, float* C, int64_t ldc, int64_t a_rows, int64_t b_rows);
+void launch_tc_store3(mcb_ctx* ctx, const float* Zhi, const float* Zlo, int64_t rows_alloc, int64_t a_rows,
+                      int64_t b_rows, int32_t Gpad, float* C, int64_t ldc);
+void launch_tc_filter(mcb_ctx* ctx, const float* Zhi, const float* Zlo, int64_t rows_pad_total, int64_t a_row0,
+                      int64_t a_rows, int64_t b_rows, int32_t Gpad, const float* thr, uint64_t* cand,
+                      uint32_t* cnt, int32_t cap);
+
+// select.cu
+void launch_sample_threshold(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t rows, int32_t S, int32_t r,
+                             float eps, float* thr);
+void launch_topk_rows(mcb_ctx* ctx, const uint64_t* cand, const uint32_t* cnt, int32_t cap, int64_t row0,
+                      int64_t rows, int32_t kc_out, int32_t Kc, int32_t* knn_col, float* knn_cor, int32_t* fail_flag);
+void launch_compact_flags(mcb_ctx* ctx, const int32_t* flag, int64_t n, int32_t* list, int32_t* n_out);
+void launch_topk_big(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t M, const int32_t* rows, int32_t nrows,
+                     int64_t row0, int32_t kc_out, int32_t Kc, int32_t* knn_col, float* knn_cor);
+
+// balance.cu
+void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t Kc, int32_t H, int32_t rank_bits,
+                       uint32_t* table);
+void launch_mutual(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* table, int64_t row0, int64_t rows,
+                   int32_t Kc, int32_t H, int32_t rank_bits, int64_t smax, int strict, int keep_self, int32_t kin,
+                   uint32_t* sym, uint64_t* thr_in);
+void launch_prune(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* sym, const uint64_t* thr_in, int64_t row0,
+                  int64_t rows, int32_t Kc, int32_t K, int32_t* out_deg, int32_t* out_dst, int32_t* out_s);
+void launch_widen_i32(mcb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n);
+void launch_emit_edges(mcb_ctx* ctx, const int32_t* out_deg, const int32_t* out_dst, const int64_t* offs,
+                       const int32_t* cell_of_row, int64_t row0, int64_t rows, int32_t K, int32_t* src, int32_t* dst,
+                       double* w);
+
+// coclust.cu
+struct CoverGraph {
+    int32_t N; const int64_t* optr; const int32_t* odst; const uint32_t* ow;
+    const int64_t* iptr; const int32_t* isrc; const uint32_t* iw;
+};
+void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
+                        const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling,
+                        int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap, int32_t* mc /* [n_local][N] */,
+                        int32_t* f_ws /* [n_local][N] */, int32_t* sweeps, int32_t* status);
+void launch_cooccur(mcb_ctx* ctx, int32_t N, int32_t n_local, const int32_t* mc, int32_t ncl_cap, uint32_t* cnt,
+                    int32_t* nsamp, int32_t* ws_order /* [n_local][N] */, int32_t* ws_start /* [n_local][ncl_cap+1] */);
+void launch_count_pairs(mcb_ctx* ctx, int32_t N, const uint32_t* cnt, int64_t* row_counts);
+void launch_extract_pairs(mcb_ctx* ctx, int32_t N, const uint32_t* cnt, const int64_t* row_offs, int32_t* n1,
+                          int32_t* n2, int32_t* c);
+void launch_exclusive_scan_i64(mcb_ctx* ctx, const int64_t* in, int64_t* out, int64_t n, int64_t* total);
+
+}  // namespace mcb

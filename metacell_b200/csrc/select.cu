@@ -1,0 +1,230 @@
+// select.cu -- per-row selection kernels around the correlation contraction of tgs_cor_knn
+// (reference call site R/utils.r:119: the K*k_expand best-correlated cells of every cell, ranked
+// 1..Kc with the cell itself at rank 1, R/atlas.r:475-476).
+//
+//   sample_threshold : r-th largest of each row of the sampled correlation block  -> filter threshold
+//   topk_rows        : sort one row's filtered candidates, emit the ranked kNN list
+//   topk_big         : exact selection over a full correlation row (rows whose window was missed)
+//
+// All three are shared-memory radix-select / bitonic-sort kernels, one CTA per row; their HBM
+// traffic is one read of the candidates and one write of the list.
+#include "internal.h"
+
+namespace mcb {
+
+constexpr int SEL_THREADS = 256;
+
+// ---------------------------------------------------------------------------------------------
+// thr[row] = (r-th largest of C[row][0..S)) - eps ; -2 if r > S
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS)
+sample_threshold_kernel(const float* __restrict__ C, int64_t ldc, int64_t rows, int32_t S, int32_t r, float eps,
+                        float* __restrict__ thr)
+{
+    extern __shared__ uint32_t skeys[];     // [S] ordered keys
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix;
+    __shared__ int s_k;
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        if (r > S) { if (threadIdx.x == 0) thr[row] = -2.0f; continue; }
+        const float* c = C + row * ldc;
+        for (int j = threadIdx.x; j < S; j += SEL_THREADS) skeys[j] = float_to_ordered(c[j]);
+        if (threadIdx.x == 0) { s_prefix = 0u; s_k = S - r; }   // k-th smallest, 0-based
+        __syncthreads();
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 24 - 8 * pass;
+            const uint32_t decided = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+            const uint32_t prefix = s_prefix;
+            hist[threadIdx.x] = 0;
+            __syncthreads();
+            for (int j = threadIdx.x; j < S; j += SEL_THREADS) {
+                const uint32_t k = skeys[j];
+                if ((k & decided) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int k = s_k, cum = 0, dg = 0;
+                for (; dg < 256; ++dg) { if (cum + (int)hist[dg] > k) break; cum += hist[dg]; }
+                s_prefix = prefix | ((uint32_t)dg << shift);
+                s_k = k - cum;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) thr[row] = ordered_to_float(s_prefix) - eps;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// candidates of one row -> ranked kNN list.  cand keys are (cor desc, col asc) ascending u64.
+// fail_flag[row] = 1 when the row's candidate count fell outside [kc_out-1, cap].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS)
+topk_rows_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, int32_t cap, int64_t row0,
+                 int64_t rows, int32_t kc_out, int32_t Kc, int32_t* __restrict__ knn_col, float* __restrict__ knn_cor,
+                 int32_t* __restrict__ fail_flag)
+{
+    extern __shared__ uint64_t sk[];        // [pow2(cap)]
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const uint32_t n = cnt[row];
+        int32_t* oc = knn_col + row * (int64_t)Kc;
+        float* ov = knn_cor + row * (int64_t)Kc;
+        if (n > (uint32_t)cap || (int64_t)n < (int64_t)kc_out - 1) {
+            if (threadIdx.x == 0) fail_flag[row] = 1;
+            continue;
+        }
+        if (threadIdx.x == 0) fail_flag[row] = 0;
+        const int np2 = next_pow2((int)n < 2 ? 2 : (int)n);
+        const uint64_t* src = cand + row * (int64_t)cap;
+        for (int q = threadIdx.x; q < np2; q += SEL_THREADS) sk[q] = q < (int)n ? src[q] : ~0ull;
+        __syncthreads();
+        bitonic_sort_u64<SEL_THREADS>(sk, np2);
+        for (int q = threadIdx.x; q < Kc; q += SEL_THREADS) {
+            if (q == 0) { oc[0] = (int32_t)(row0 + row); ov[0] = 1.0f; }
+            else if (q < kc_out) { const uint64_t k = sk[q - 1]; oc[q] = (int32_t)cand_key_col(k); ov[q] = cand_key_cor(k); }
+            else { oc[q] = -1; ov[q] = 0.0f; }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact selection over a full correlation row held in global memory (fp32, M values):
+// the kc_out-1 best columns != self by (cor desc, col asc).  One CTA per listed row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS)
+topk_big_kernel(const float* __restrict__ C, int64_t ldc, int64_t M, const int32_t* __restrict__ rows, int32_t nrows,
+                int64_t row0, int32_t kc_out, int32_t Kc, int32_t* __restrict__ knn_col, float* __restrict__ knn_cor)
+{
+    extern __shared__ uint64_t sk[];        // [pow2(kc_out)]
+    __shared__ uint32_t hist[256];
+    __shared__ unsigned long long s_prefix, s_thr;
+    __shared__ long long s_k;
+    __shared__ int s_done, s_fill;
+    for (int q = blockIdx.x; q < nrows; q += gridDim.x) {
+        const int64_t lrow = rows[q];               // local row (relative to row0)
+        const int64_t self = row0 + lrow;
+        const float* c = C + (int64_t)q * ldc;
+        const int want = kc_out - 1;
+        int32_t* oc = knn_col + lrow * (int64_t)Kc;
+        float* ov = knn_cor + lrow * (int64_t)Kc;
+        if (want <= 0) {
+            for (int t = threadIdx.x; t < Kc; t += SEL_THREADS) { oc[t] = t == 0 ? (int32_t)self : -1; ov[t] = t == 0 ? 1.f : 0.f; }
+            continue;
+        }
+        if (threadIdx.x == 0) { s_prefix = 0ull; s_k = want - 1; s_done = 0; s_thr = ~0ull; s_fill = 0; }
+        __syncthreads();
+        for (int pass = 0; pass < 8; ++pass) {
+            const int shift = 56 - 8 * pass;
+            const unsigned long long decided = pass == 0 ? 0ull : (~0ull << (shift + 8));
+            const unsigned long long prefix = s_prefix;
+            hist[threadIdx.x] = 0;
+            __syncthreads();
+            for (int64_t j = threadIdx.x; j < M; j += SEL_THREADS) {
+                if (j == self) continue;
+                const uint64_t key = cand_key(c[j], (uint32_t)j);
+                if ((key & decided) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                long long k = s_k, cum = 0;
+                int dg = 0;
+                for (; dg < 256; ++dg) { if (cum + (long long)hist[dg] > k) break; cum += hist[dg]; }
+                const unsigned long long np = prefix | ((unsigned long long)dg << shift);
+                s_prefix = np; s_k = k - cum;
+                if (k - cum == (long long)hist[dg] - 1 || pass == 7) {
+                    s_thr = np | (shift ? ((1ull << shift) - 1ull) : 0ull);
+                    s_done = 1;
+                }
+            }
+            __syncthreads();
+            if (s_done) break;
+        }
+        const uint64_t thr = s_thr;
+        const int np2 = next_pow2(want < 2 ? 2 : want);
+        for (int t = threadIdx.x; t < np2; t += SEL_THREADS) sk[t] = ~0ull;
+        __syncthreads();
+        for (int64_t j = threadIdx.x; j < M; j += SEL_THREADS) {
+            if (j == self) continue;
+            const uint64_t key = cand_key(c[j], (uint32_t)j);
+            if (key <= thr) { const int pos = atomicAdd(&s_fill, 1); if (pos < np2) sk[pos] = key; }
+        }
+        __syncthreads();
+        bitonic_sort_u64<SEL_THREADS>(sk, np2);
+        for (int t = threadIdx.x; t < Kc; t += SEL_THREADS) {
+            if (t == 0) { oc[0] = (int32_t)self; ov[0] = 1.0f; }
+            else if (t < kc_out) { const uint64_t k = sk[t - 1]; oc[t] = (int32_t)cand_key_col(k); ov[t] = cand_key_cor(k); }
+            else { oc[t] = -1; ov[t] = 0.0f; }
+        }
+        __syncthreads();
+    }
+}
+
+// compact the flagged rows into a list; *n_out = count
+__global__ void compact_flags_kernel(const int32_t* __restrict__ flag, int64_t n, int32_t* __restrict__ list,
+                                     int32_t* __restrict__ n_out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (flag[i]) { const int pos = atomicAdd(n_out, 1); list[pos] = (int32_t)i; }
+}
+
+void launch_sample_threshold(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t rows, int32_t S, int32_t r,
+                             float eps, float* thr)
+{
+    if (rows == 0) return;
+    const size_t smem = (size_t)S * sizeof(uint32_t);
+    MCB_CHECK(smem <= 200 * 1024, "sample_threshold: sample too large for shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        MCB_CUDA(cudaFuncSetAttribute(sample_threshold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
+    sample_threshold_kernel<<<grid, SEL_THREADS, smem, ctx->stream>>>(C, ldc, rows, S, r, eps, thr);
+    MCB_LAUNCH_CHECK();
+}
+
+void launch_topk_rows(mcb_ctx* ctx, const uint64_t* cand, const uint32_t* cnt, int32_t cap, int64_t row0,
+                      int64_t rows, int32_t kc_out, int32_t Kc, int32_t* knn_col, float* knn_cor, int32_t* fail_flag)
+{
+    if (rows == 0) return;
+    int np2 = 2; while (np2 < cap) np2 <<= 1;
+    const size_t smem = (size_t)np2 * sizeof(uint64_t);
+    MCB_CHECK(smem <= 200 * 1024, "topk_rows: candidate capacity too large for shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        MCB_CUDA(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
+    topk_rows_kernel<<<grid, SEL_THREADS, smem, ctx->stream>>>(cand, cnt, cap, row0, rows, kc_out, Kc, knn_col,
+                                                                knn_cor, fail_flag);
+    MCB_LAUNCH_CHECK();
+}
+
+void launch_compact_flags(mcb_ctx* ctx, const int32_t* flag, int64_t n, int32_t* list, int32_t* n_out)
+{
+    MCB_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t), ctx->stream));
+    if (n == 0) return;
+    int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->num_sms * 8);
+    compact_flags_kernel<<<grid, 256, 0, ctx->stream>>>(flag, n, list, n_out);
+    MCB_LAUNCH_CHECK();
+}
+
+void launch_topk_big(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t M, const int32_t* rows, int32_t nrows,
+                     int64_t row0, int32_t kc_out, int32_t Kc, int32_t* knn_col, float* knn_cor)
+{
+    if (nrows == 0) return;
+    int np2 = 2; while (np2 < kc_out) np2 <<= 1;
+    const size_t smem = (size_t)np2 * sizeof(uint64_t);
+    MCB_CHECK(smem <= 200 * 1024, "topk_big: Kc too large for shared memory");
+    static size_t configured = 0;
+    if (smem > configured) {
+        MCB_CUDA(cudaFuncSetAttribute(topk_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    topk_big_kernel<<<nrows, SEL_THREADS, smem, ctx->stream>>>(C, ldc, M, rows, nrows, row0, kc_out, Kc, knn_col, knn_cor);
+    MCB_LAUNCH_CHECK();
+}
+
+}  // namespace mcb

@@ -1,0 +1,83 @@
+"""GPU parity of the resampled co-clustering stage (A8) against the CPU oracle: per-resample cluster
+assignments, sweep counts and the integer co-occurrence matrix must be bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _graph(oracle, ncells=900, K=15, seed=5):
+    from metacell_b200 import synth
+    from conftest import feat_map_of
+    m = synth.make_umi_matrix(ncells, 400, n_types=6, median_umis=2000.0, seed=seed)
+    feats = np.arange(0, 400, 2, dtype=np.int32)
+    Z, valid = oracle.features(m.indptr, m.indices, m.data, feat_map_of(m.ngenes, feats), feats.size)
+    assert valid.all()
+    col, _ = oracle.cor_knn(Z, K * 10)
+    deg, dst, _ = oracle.balance(col, K)
+    return oracle.edges_from_balance(deg, dst, K)
+
+
+@pytest.mark.parametrize("ncells,K,min_size,n_resamp", [(900, 15, 8, 6), (1500, 30, 20, 4)])
+def test_cover_assignments_and_counts_bit_exact(ctx, oracle, ncells, K, min_size, n_resamp):
+    from metacell_b200 import _lib, synth
+    src, dst, w = _graph(oracle, ncells, K)
+    sets, seeds = synth.resample_sets(ncells, 0.75, n_resamp, 11)
+    cc = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, min_size, 1.05, 10)
+    mc, sweeps = cc.assignments()
+    csr = oracle.graph_to_csr(ncells, src, dst, w)
+    for r in range(n_resamp):
+        omc, osw = oracle.graph_cover(ncells, csr, sets[r], min_size, 1.05, 10, int(seeds[r]))
+        assert sweeps[r] == osw, (r, sweeps[r], osw)
+        assert np.array_equal(mc[r], omc), r
+    n1, n2, cnt, ns = cc.pairs()
+    ocnt, ons, _ = oracle.coclust(ncells, csr, sets, seeds, min_size, 1.05, 10)
+    dense = np.zeros((ncells, ncells), np.uint32)
+    dense[n1, n2] = cnt
+    assert np.array_equal(dense, ocnt)
+    assert np.array_equal(ns, ons)
+    # invariants
+    assert np.all(n1 < n2) and np.all(cnt > 0)
+    assert ns.sum() == n_resamp * sets.shape[1] and ns.max() <= n_resamp
+    assert np.all(cnt <= np.minimum(ns[n1], ns[n2]))
+    order = np.lexsort((n2, n1))
+    assert np.array_equal(order, np.arange(n1.size))               # sorted output
+    cc.destroy()
+
+
+def test_rank_sharding_sums_to_whole(ctx, oracle):
+    """resamples strided over 3 emulated ranks: counters add up to the single-rank result"""
+    from metacell_b200 import _lib, synth
+    ncells = 700
+    src, dst, w = _graph(oracle, ncells, 12)
+    sets, seeds = synth.resample_sets(ncells, 0.75, 7, 2)
+    whole = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, 8, 1.05, 10)
+    n1, n2, cnt, ns = whole.pairs()
+    dense = np.zeros((ncells, ncells), np.int64)
+    dense[n1, n2] = cnt
+    acc = np.zeros_like(dense)
+    accs = np.zeros(ncells, np.int64)
+    for r in range(3):
+        part = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, 8, 1.05, 10, rank=r, nranks=3)
+        a, b, c, s = part.pairs()
+        acc[a, b] += c
+        accs += s
+        part.destroy()
+    assert np.array_equal(acc, dense) and np.array_equal(accs, ns)
+    whole.destroy()
+
+
+def test_api_mirror_coclust(ctx, oracle, tmp_path):
+    """mcell_coclust_from_graph_resamp through the host mirror (reference R/coclust_graph_cov.r:13-58)"""
+    from metacell_b200 import api
+    ncells = 600
+    src, dst, w = _graph(oracle, ncells, 10)
+    api.scdb_init(str(tmp_path), force_reinit=True)
+    api.scdb_add_cgraph("g", api.tgCellGraph({"mc1": src, "mc2": dst, "w": w}, [f"c{i}" for i in range(ncells)]))
+    coc = api.mcell_coclust_from_graph_resamp("coc", "g", 8, 0.75, 5, ctx=ctx)
+    assert api.scdb_coclust("coc") is coc
+    assert coc.n_samp.sum() == 5 * round(0.75 * ncells)
+    with pytest.raises(api.McbError, match="MC-ERR"):
+        api.mcell_coclust_from_graph_resamp("coc2", "missing", 8, 0.75, 5, ctx=ctx)
+    with pytest.raises(api.McbError, match="MC-ERR"):
+        api.tgCoClust("missing", coc.coclust, coc.n_samp)
