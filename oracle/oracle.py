@@ -17,7 +17,7 @@ _SO = os.path.join(_HERE, "_build", "libmc_oracle.so")
 def build(force=False):
     src = os.path.join(_HERE, "mc_oracle.c")
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        # -march=native objects do not travel between hosts: rebuild when the CPU differs
+        # built with -mavx2 (no -march=native) so the object travels to the GPU box
         subprocess.check_call(["make", "-C", _HERE, "-B"], stdout=subprocess.DEVNULL)
     return _SO
 
