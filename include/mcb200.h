@@ -39,6 +39,7 @@ typedef struct mcb_coclust mcb_coclust;  /* one resampled co-clustering run     
 
 int         mcb_version(void);
 const char* mcb_last_error(void);
+int64_t     mcb_launch_count(void);       /* kernels this library has launched in this process */
 
 /* ---- context ------------------------------------------------------------------------------ */
 int   mcb_ctx_create(int device, mcb_ctx** out);

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libmcb200.so")
 
 # every symbol include/mcb200.h declares (tests check the .so exports exactly these)
 SYMBOLS = [
-    "mcb_version", "mcb_last_error", "mcb_ctx_create", "mcb_ctx_destroy", "mcb_ctx_sync", "mcb_ctx_stream",
+    "mcb_version", "mcb_last_error", "mcb_launch_count", "mcb_ctx_create", "mcb_ctx_destroy", "mcb_ctx_sync", "mcb_ctx_stream",
     "mcb_ctx_set_option", "mcb_ctx_timings", "mcb_ctx_timings_reset", "mcb_downsamp_depth", "mcb_csc_upload",
     "mcb_csc_wrap_device", "mcb_csc_free", "mcb_csc_col_sums", "mcb_csc_downsample", "mcb_csc_download",
     "mcb_cgraph_create", "mcb_cgraph_create_dense", "mcb_cgraph_destroy", "mcb_cgraph_num_valid",
@@ -41,10 +41,15 @@ def lib():
         L = C.CDLL(LIB_PATH)
         L.mcb_last_error.restype = C.c_char_p
         L.mcb_ctx_stream.restype = C.c_void_p
+        L.mcb_launch_count.restype = C.c_int64
         for name in ("mcb_ctx_destroy", "mcb_csc_free", "mcb_cgraph_destroy", "mcb_coclust_destroy", "mcb_free"):
             getattr(L, name).restype = None
         _lib = L
     return _lib
+
+
+def launch_count():
+    return int(lib().mcb_launch_count())
 
 
 def check(rc):

@@ -26,7 +26,9 @@ void mcb::set_error(const char* msg) { g_err = msg ? msg : ""; }
     catch (const std::exception& e) { mcb::set_error(e.what()); return 4; }                    \
     catch (...) { mcb::set_error("unknown error"); return 5; }
 
+std::atomic<long long> mcb::g_launches{0};
 extern "C" int mcb_version(void) { return 100; }
+extern "C" int64_t mcb_launch_count(void) { return (int64_t)mcb::g_launches.load(); }
 extern "C" const char* mcb_last_error(void) { return g_err.c_str(); }
 
 // ---------------------------------------------------------------------------------------------
@@ -89,14 +91,20 @@ extern "C" int mcb_ctx_create(int device, mcb_ctx** out)
     *out = c;
     MCB_API_END
 }
-extern "C" void mcb_ctx_destroy(mcb_ctx* ctx)
+void mcb::ctx_retain(mcb_ctx* c) { c->refs.fetch_add(1); }
+void mcb::ctx_release(mcb_ctx* ctx)
 {
-    if (!ctx) return;
+    if (ctx->refs.fetch_sub(1) != 1) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     resolve_timers(ctx);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+// the context stays alive until the last handle created from it is gone
+extern "C" void mcb_ctx_destroy(mcb_ctx* ctx)
+{
+    if (ctx) mcb::ctx_release(ctx);
 }
 extern "C" int mcb_ctx_sync(mcb_ctx* ctx)
 {
@@ -167,6 +175,7 @@ extern "C" int mcb_downsamp_depth(const int64_t* col_sums, int64_t ncells, doubl
 // CSC matrix
 // ---------------------------------------------------------------------------------------------
 struct mcb_csc {
+    CtxRef ref;
     mcb_ctx* ctx = nullptr;
     int32_t ngenes = 0;
     int64_t ncells = 0, nnz = 0;
@@ -185,7 +194,7 @@ extern "C" int mcb_csc_upload(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, cons
     MCB_CHECK(p[0] == 0 && nnz >= 0, "mcb_csc_upload: malformed column pointer");
     MCB_CHECK(nnz == 0 || (i && x), "mcb_csc_upload: null index/value array");
     std::unique_ptr<mcb_csc> m(new mcb_csc());
-    m->ctx = ctx; m->ngenes = ngenes; m->ncells = ncells; m->nnz = nnz;
+    m->ref.set(ctx); m->ctx = ctx; m->ngenes = ngenes; m->ncells = ncells; m->nnz = nnz;
     StageTimer t(ctx, "h2d_csc");
     m->own_p.alloc(ctx, (size_t)ncells + 1);
     m->own_i.alloc(ctx, (size_t)nnz);
@@ -208,7 +217,7 @@ extern "C" int mcb_csc_wrap_device(mcb_ctx* ctx, int32_t ngenes, int64_t ncells,
     MCB_CHECK(ctx && dev_p && out, "mcb_csc_wrap_device: null argument");
     MCB_CUDA(cudaSetDevice(ctx->device));
     std::unique_ptr<mcb_csc> m(new mcb_csc());
-    m->ctx = ctx; m->ngenes = ngenes; m->ncells = ncells;
+    m->ref.set(ctx); m->ctx = ctx; m->ngenes = ngenes; m->ncells = ncells;
     int64_t nnz = 0;
     MCB_CUDA(cudaMemcpy(&nnz, dev_p + ncells, sizeof(int64_t), cudaMemcpyDeviceToHost));
     m->nnz = nnz; m->p = dev_p; m->i = dev_i; m->x = dev_x;
@@ -236,7 +245,7 @@ extern "C" int mcb_csc_downsample(mcb_ctx* ctx, const mcb_csc* m, double n, uint
     MCB_CHECK(n >= 1.0, "MC-ERR: downsample depth must be >= 1");
     MCB_CUDA(cudaSetDevice(ctx->device));
     std::unique_ptr<mcb_csc> d(new mcb_csc());
-    d->ctx = ctx; d->ngenes = m->ngenes; d->ncells = m->ncells; d->nnz = m->nnz;
+    d->ref.set(ctx); d->ctx = ctx; d->ngenes = m->ngenes; d->ncells = m->ncells; d->nnz = m->nnz;
     d->p = m->p; d->i = m->i;                      // shares structure with the input (caller keeps it alive)
     d->own_x.alloc(ctx, (size_t)m->nnz);
     d->kept.alloc(ctx, (size_t)m->ncells);
@@ -275,6 +284,7 @@ void launch_tc_store3(mcb_ctx* ctx, const float* Zhi, const float* Zlo, int64_t 
 }
 
 struct mcb_cgraph {
+    CtxRef ref;
     mcb_ctx* ctx = nullptr;
     int64_t ncells = 0; int32_t G = 0, Gpad = 0;
     int64_t M = 0, Mpad = 0;
@@ -307,7 +317,7 @@ extern "C" int mcb_cgraph_create(mcb_ctx* ctx, const mcb_csc* m, const int32_t* 
         fmap[feat_rows[g]] = g;
     }
     std::unique_ptr<mcb_cgraph> g(new mcb_cgraph());
-    g->ctx = ctx; g->ncells = m->ncells; g->G = G; g->Gpad = (int32_t)round_up(G, 32);
+    g->ref.set(ctx); g->ctx = ctx; g->ncells = m->ncells; g->G = G; g->Gpad = (int32_t)round_up(G, 32);
     DevBuf<int32_t> d_fmap(ctx, fmap.size());
     MCB_CUDA(cudaMemcpyAsync(d_fmap.p, fmap.data(), fmap.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     DevBuf<double> mu(ctx, (size_t)m->ncells), inv(ctx, (size_t)m->ncells);
@@ -346,7 +356,7 @@ extern "C" int mcb_cgraph_create_dense(mcb_ctx* ctx, const double* x, int32_t G,
     MCB_CHECK(G >= 2 && ncells >= 1, "MC-ERR: need at least 2 feature genes and 1 cell");
     MCB_CUDA(cudaSetDevice(ctx->device));
     std::unique_ptr<mcb_cgraph> g(new mcb_cgraph());
-    g->ctx = ctx; g->ncells = ncells; g->G = G; g->Gpad = (int32_t)round_up(G, 32);
+    g->ref.set(ctx); g->ctx = ctx; g->ncells = ncells; g->G = G; g->Gpad = (int32_t)round_up(G, 32);
     DevBuf<double> dx(ctx, (size_t)ncells * G);
     {
         StageTimer t(ctx, "h2d_dense");
@@ -763,6 +773,7 @@ extern "C" int mcb_cgraph_bknn(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, con
 // resampled co-clustering
 // ---------------------------------------------------------------------------------------------
 struct mcb_coclust {
+    CtxRef ref;
     mcb_ctx* ctx = nullptr;
     int32_t N = 0, n_local = 0, ncl_cap = 0;
     DevBuf<uint32_t> cnt; DevBuf<int32_t> nsamp;
@@ -813,7 +824,7 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
     std::vector<int32_t> ids;
     for (int32_t r = rank; r < n_resamp; r += nranks) ids.push_back(r);
     std::unique_ptr<mcb_coclust> c(new mcb_coclust());
-    c->ctx = ctx; c->N = N; c->n_local = (int32_t)ids.size();
+    c->ref.set(ctx); c->ctx = ctx; c->N = N; c->n_local = (int32_t)ids.size();
     c->ncl_cap = n_s / (min_mc_size > 0 ? min_mc_size + 1 : 1) + 2;
     const int32_t nl = c->n_local;
 

@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <string>
 #include <stdexcept>
+#include <atomic>
 
 namespace mcb {
 
@@ -40,7 +41,8 @@ void set_error(const char* msg);
         }                                                                                      \
     } while (0)
 
-#define MCB_LAUNCH_CHECK() MCB_CUDA(cudaGetLastError())
+extern std::atomic<long long> g_launches;   // kernels launched by this library (bench: gpu_launches)
+#define MCB_LAUNCH_CHECK() do { ++::mcb::g_launches; MCB_CUDA(cudaGetLastError()); } while (0)
 
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

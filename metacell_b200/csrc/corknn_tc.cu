@@ -5,19 +5,24 @@
 //   C[i][j] = sum_g Z[i][g] * Z[j][g]          Z = standardised log-feature rows (features.cu)
 //
 // Precision: 3-pass split-TF32.  Z is stored as two TF32-exact planes (Zhi + Zlo); per k-block the
-// kernel issues  hi*hi, hi*lo, lo*hi  into the same FP32 TMEM accumulator, which keeps the result
+// kernel issues  hi*hi, hi*lo, lo*hi  into FP32 TMEM accumulators, which keeps the result
 // within ~1e-6 of fp32 (DESIGN.md "Precision").  NPASS = 1 (hi*hi only) is used by the threshold
 // sampling pass where 1e-3 accuracy is enough.
 //
 // Kernel shape (persistent, warp specialised, one CTA per SM, cta_group::1):
 //   warp 0      TMA producer : cp.async.bulk.tensor 2D tiles, 128-byte swizzle, NSTAGE-deep ring
-//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=256, K=8)
-//                              into one of two 256-column TMEM accumulators; owns TMEM alloc/dealloc
-//   warps 2..5  epilogue     : tcgen05.ld 32x32b.x32, then either
+//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma.kind::tf32 (M=128, N=256, K=8);
+//                              owns TMEM alloc/dealloc.  TMEM columns [0,256) accumulate hi*hi,
+//                              columns [256,512) the two cross terms: the tensor core truncates
+//                              when it adds into a large accumulator (measured ~1 ulp per MMA), so
+//                              keeping the 2^-11-sized cross terms out of the main sum cuts the
+//                              accumulated truncation error 3x (DESIGN.md "Precision")
+//   warps 2..9  epilogue     : tcgen05.ld 32x32b.x32 of main + cross, add, then either
 //                                STORE  : write the fp32 tile (sample block of the threshold pass), or
 //                                FILTER : keep (i, j, c) with c >= thr[i], j != i -> append to the
 //                                         row's candidate buffer (global atomics; ~1.5% of elements)
-//   Double-buffered TMEM lets the epilogue of tile t overlap the MMAs of tile t+1.
+//   The two accumulators fill TMEM, so the MMA warp waits while the 8 epilogue warps drain a tile
+//   (~3% of a tile's MMA time at G = 1000).
 // Tile order: groups of GROUP_M row tiles sweep the column tiles together so the A panel of the
 // group (GROUP_M x 1 MB) stays L2 resident and each B tile is fetched from HBM once per group.
 #include "internal.h"
@@ -32,7 +37,8 @@ constexpr int BN = 256;            // columns of C per tile (TMEM columns per ac
 constexpr int BK = 32;             // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int UMMA_K = 8;          // tf32
 constexpr int GROUP_M = 16;
-constexpr int TC_THREADS = 192;    // 6 warps
+constexpr int TC_THREADS = 320;    // 10 warps: TMA, MMA, 8 epilogue
+constexpr int EPI_WARPS = 8;
 constexpr uint32_t TMEM_COLS = 512;
 
 template <int NPASS> struct TcCfg {
@@ -80,9 +86,9 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES);
     uint64_t* full_bar = bars;                       // [NSTAGE]
     uint64_t* empty_bar = bars + Cfg::NSTAGE;        // [NSTAGE]
-    uint64_t* tfull_bar = bars + 2 * Cfg::NSTAGE;    // [2]
-    uint64_t* tempty_bar = bars + 2 * Cfg::NSTAGE + 2;   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::NSTAGE + 4);
+    uint64_t* tfull_bar = bars + 2 * Cfg::NSTAGE;    // accumulators complete -> epilogue
+    uint64_t* tempty_bar = bars + 2 * Cfg::NSTAGE + 1;   // epilogue drained -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::NSTAGE + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = prm.m_tiles * prm.n_tiles;
@@ -91,7 +97,7 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         prefetch_tensormap(&map_a_hi); prefetch_tensormap(&map_b_hi);
         if (NPASS == 3) { prefetch_tensormap(&map_a_lo); prefetch_tensormap(&map_b_lo); }
         for (int s = 0; s < Cfg::NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], 4); }
+        mbar_init(tfull_bar, 1); mbar_init(tempty_bar, EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -128,13 +134,11 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_tf32(BM, BN);
             int stage = 0; uint32_t phase = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            uint32_t tphase = 0;
+            const uint32_t d_main = tmem_base, d_cross = tmem_base + (uint32_t)BN;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar, tphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < prm.num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -146,40 +150,50 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);     // 32 bytes per k step
-                        mma_tf32_ss(d_tmem, a_hi + koff, b_hi + koff, idesc, (kb | k) != 0 ? 1u : 0u);
+                        const uint32_t accum = (kb | k) != 0 ? 1u : 0u;    // first k-step overwrites
+                        mma_tf32_ss(d_main, a_hi + koff, b_hi + koff, idesc, accum);
                         if (NPASS == 3) {
-                            mma_tf32_ss(d_tmem, a_hi + koff, b_lo + koff, idesc, 1u);
-                            mma_tf32_ss(d_tmem, a_lo + koff, b_hi + koff, idesc, 1u);
+                            mma_tf32_ss(d_cross, a_hi + koff, b_lo + koff, idesc, accum);
+                            mma_tf32_ss(d_cross, a_lo + koff, b_hi + koff, idesc, 1u);
                         }
                     }
                     tc_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
                     if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull_bar[acc]);                // accumulator complete -> epilogue
+                tc_commit(tfull_bar);                      // accumulators complete -> epilogue
+                tphase ^= 1;
             }
         }
     } else {
-        // ===== epilogue warps 2..5 : TMEM lanes (warp % 4) * 32 .. + 31 =====
+        // ===== epilogue warps 2..9 : TMEM lanes (warp % 4) * 32 .. + 31, column half (warp - 2) / 4 =====
         const int quarter = warp & 3;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int half = (warp - 2) >> 2;
+        uint32_t tphase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             int m_blk, n_blk;
             tile_coords(tile, prm.m_tiles, prm.n_tiles, m_blk, n_blk);
-            const int acc = it & 1;
-            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
             const int64_t lrow = (int64_t)m_blk * BM + quarter * 32 + lane;       // local row
             const bool row_ok = lrow < prm.a_rows;
             const int64_t n0 = (int64_t)n_blk * BN;
             float t = 0.f;
             if (MODE == 1) t = row_ok ? prm.thr[lrow] : __int_as_float(0x7f800000);
-            mbar_wait(&tfull_bar[acc], acc_phase);
+            mbar_wait(tfull_bar, tphase);
+            tphase ^= 1;
             tc_fence_after();
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
                 uint32_t v[32];
                 tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
-                tmem_ld_wait();
+                if (NPASS == 3) {
+                    uint32_t u[32];
+                    tmem_ld_32x32(taddr0 + (uint32_t)(BN + c * 32), u);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) + __uint_as_float(u[q]));
+                } else {
+                    tmem_ld_wait();
+                }
                 const int64_t col0 = n0 + c * 32;
                 if (MODE == 0) {
                     if (row_ok && col0 < prm.b_rows) {
@@ -212,7 +226,7 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) mbar_arrive(tempty_bar);
         }
     }
 

@@ -3,11 +3,13 @@
 #pragma once
 #include "common.cuh"
 #include <algorithm>
+#include <atomic>
 #include <memory>
 #include <vector>
 #include <string>
 
 struct mcb_ctx {
+    std::atomic<int> refs{1};   // the creator + every live handle; destroyed when it drops to 0
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
@@ -53,6 +55,18 @@ struct DevBuf {
     }
     ~DevBuf() { release(); }
     size_t bytes() const { return n * sizeof(T); }
+};
+
+// declared FIRST in every handle struct so it is destroyed LAST (after the DevBufs that use the ctx)
+void ctx_retain(mcb_ctx* c);
+void ctx_release(mcb_ctx* c);
+struct CtxRef {
+    mcb_ctx* c = nullptr;
+    CtxRef() {}
+    CtxRef(const CtxRef&) = delete;
+    CtxRef& operator=(const CtxRef&) = delete;
+    void set(mcb_ctx* ctx) { c = ctx; ctx_retain(ctx); }
+    ~CtxRef() { if (c) ctx_release(c); }
 };
 
 struct StageTimer {

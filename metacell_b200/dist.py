@@ -73,8 +73,9 @@ class CudaCGraphEngine:
         torch.cuda.synchronize(self.device)
 
 
-def cgraph_sharded(engine, K, k_expand, k_beta, rank, world, group=None):
-    """Runs A5..A7 with rows sharded over `world` ranks.  Returns this rank's (src, dst, w)."""
+def cgraph_sharded(engine, K, k_expand, k_beta, rank, world, group=None, fetch_edges=True):
+    """Runs A5..A7 with rows sharded over `world` ranks.  Returns this rank's (src, dst, w), or the edge
+    count when fetch_edges is False (edges stay on the device)."""
     engine.knn(K, k_expand, rank, world)
     if world > 1:
         full = engine.knn_full(world)
@@ -87,8 +88,8 @@ def cgraph_sharded(engine, K, k_expand, k_beta, rank, world, group=None):
         engine.sync()
         _all_gather_blocks(full, rank, world, group)
         engine.sync()
-    engine.prune()
-    return engine.edges()
+    n = engine.prune()
+    return engine.edges() if fetch_edges else n
 
 
 def gather_edges(src, dst, w, rank, world, device=None, group=None):

@@ -90,11 +90,11 @@ def test_features_match_oracle(ctx, oracle):
 
 
 # ---- the contraction itself ----------------------------------------------------------------------
-@pytest.mark.parametrize("G", [96, 600])
+@pytest.mark.parametrize("G", [96, 600, 1000])
 def test_correlation_kernels_vs_fp64(ctx, oracle, G):
     """tcgen05 3-pass split-TF32 block == SIMT fp32 block == fp64 within 1e-5 (measured, printed)."""
     from metacell_b200 import _lib
-    m = _small(ncells=700, ngenes=700)
+    m = _small(ncells=700, ngenes=1000)
     feats = np.arange(G, dtype=np.int32)
     csc = _upload(ctx, m)
     g = _lib.CGraph.from_csc(ctx, csc, feats, 7.0)
@@ -116,22 +116,21 @@ def test_correlation_kernels_vs_fp64(ctx, oracle, G):
 
 
 # ---- A5 ------------------------------------------------------------------------------------------
-def _knn_parity(col, cor, ocol, ocor, tol=COR_TOL):
-    assert col.shape == ocol.shape
+def _knn_parity(col, cor, ocol_x, ocor_x, tol=COR_TOL):
+    """ocol_x / ocor_x: oracle lists computed a few ranks deeper than `col`, so that the tie partner of
+    the last rank is visible.  Disagreements are only allowed inside runs of correlations tied within tol."""
+    kc = col.shape[1]
+    ocol, ocor = ocol_x[:, :kc], ocor_x[:, :kc]
     assert np.abs(cor - ocor).max() < tol
     assert np.array_equal(col[:, 0], ocol[:, 0])                      # self is rank 1 (R/atlas.r:475-476)
     diff = col != ocol
     if diff.any():
-        # every disagreement must be a swap inside a run of correlations tied within the tolerance
         r, q = np.nonzero(diff)
         for i, j in zip(r, q):
-            lo = max(j - 1, 0)
-            hi = min(j + 1, col.shape[1] - 1)
-            near = min(abs(ocor[i, j] - ocor[i, lo]) if lo != j else np.inf, abs(ocor[i, j] - ocor[i, hi]) if hi != j else np.inf)
-            assert near < 2 * tol, (i, j, ocor[i, lo:hi + 1], cor[i, lo:hi + 1])
-        # and the sets agree except for the boundary element
+            nb = [abs(ocor_x[i, j] - ocor_x[i, jj]) for jj in (j - 1, j + 1) if 0 < jj < ocor_x.shape[1] and ocol_x[i, jj] >= 0]
+            assert nb and min(nb) < 2 * tol, (i, j, ocor_x[i, max(j - 1, 0):j + 2], cor[i, max(j - 1, 0):j + 2])
         for i in np.unique(r):
-            assert len(set(col[i]) ^ set(ocol[i])) <= 2
+            assert len(set(col[i]) ^ set(ocol[i])) <= 2 * int(diff[i].sum())
     return float((~diff).mean())
 
 
@@ -151,7 +150,7 @@ def test_cor_knn_parity(ctx, oracle, impl, ncells, K, kx):
     finally:
         ctx.set_option("gemm_impl", 0)
     Z, valid = oracle.features(m.indptr, m.indices, m.data, feat_map_of(m.ngenes, feats), feats.size)
-    ocol, ocor = oracle.cor_knn(Z[valid], K * kx)
+    ocol, ocor = oracle.cor_knn(Z[valid], K * kx + 8)
     agree = _knn_parity(col, cor, ocol, ocor)
     print(f"impl={impl} N={ncells} Kc={K * kx}: agreement {agree:.6f} stats {stats}")
     g.destroy()
@@ -178,7 +177,7 @@ def test_cor_knn_duplicate_cells_and_ties(ctx, oracle):
     assert col[10, 1] == 11 and col[11, 1] == 10
     assert abs(cor[10, 1] - 1.0) < COR_TOL
     Z, valid = oracle.features(m2.indptr, m2.indices, m2.data, feat_map_of(m2.ngenes, feats), feats.size)
-    ocol, ocor = oracle.cor_knn(Z[valid], 100)
+    ocol, ocor = oracle.cor_knn(Z[valid], 108)
     _knn_parity(col, cor, ocol, ocor)
     g.destroy()
 
