@@ -9,6 +9,7 @@
 #include <cstring>
 #include <random>
 #include <vector>
+#include <cuda_fp16.h>
 
 using namespace mcb;
 
@@ -276,19 +277,14 @@ extern "C" int mcb_csc_download(mcb_ctx* ctx, const mcb_csc* m, double* host_x, 
 // ---------------------------------------------------------------------------------------------
 // balanced K-nn cell graph
 // ---------------------------------------------------------------------------------------------
-namespace mcb {
-void launch_compact_flags(mcb_ctx* ctx, const int32_t* flag, int64_t n, int32_t* list, int32_t* n_out);
-void launch_widen_i32(mcb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n);
-void launch_tc_store3(mcb_ctx* ctx, const float* Zhi, const float* Zlo, int64_t rows_alloc, int64_t a_rows,
-                      int64_t b_rows, int32_t Gpad, float* C, int64_t ldc);
-}
 
 struct mcb_cgraph {
     CtxRef ref;
     mcb_ctx* ctx = nullptr;
     int64_t ncells = 0; int32_t G = 0, Gpad = 0;
     int64_t M = 0, Mpad = 0;
-    DevBuf<float> Zhi, Zlo;
+    DevBuf<float> Zf;              // fp32 plane (CUDA-core kernels)
+    DevBuf<__half> Zh, Zl;         // fp16 hi / lo planes of z * 2^12 (tensor-core kernels)
     DevBuf<int32_t> cell_of_row;
     // knn
     int32_t K = 0, k_expand = 0, Kc = 0, kc_out = 0, rank = 0, nranks = 1;
@@ -302,6 +298,20 @@ struct mcb_cgraph {
     int64_t n_edges = 0;
     DevBuf<int32_t> e_src, e_dst; DevBuf<double> e_w;
 };
+
+static void alloc_planes(mcb_cgraph* g, int64_t M)
+{
+    mcb_ctx* ctx = g->ctx;
+    const size_t n = (size_t)g->Mpad * g->Gpad;
+    g->Zf.alloc(ctx, n); g->Zh.alloc(ctx, n); g->Zl.alloc(ctx, n);
+    g->cell_of_row.alloc(ctx, (size_t)std::max<int64_t>(M, 1));
+    if (g->Mpad > M) {     // zero the padding rows
+        const size_t off = (size_t)M * g->Gpad, cnt = (size_t)(g->Mpad - M) * g->Gpad;
+        MCB_CUDA(cudaMemsetAsync(g->Zf.p + off, 0, cnt * sizeof(float), ctx->stream));
+        MCB_CUDA(cudaMemsetAsync(g->Zh.p + off, 0, cnt * sizeof(__half), ctx->stream));
+        MCB_CUDA(cudaMemsetAsync(g->Zl.p + off, 0, cnt * sizeof(__half), ctx->stream));
+    }
+}
 
 extern "C" int mcb_cgraph_create(mcb_ctx* ctx, const mcb_csc* m, const int32_t* feat_rows, int32_t G, double k_nonz,
                                  mcb_cgraph** out)
@@ -317,7 +327,7 @@ extern "C" int mcb_cgraph_create(mcb_ctx* ctx, const mcb_csc* m, const int32_t* 
         fmap[feat_rows[g]] = g;
     }
     std::unique_ptr<mcb_cgraph> g(new mcb_cgraph());
-    g->ref.set(ctx); g->ctx = ctx; g->ncells = m->ncells; g->G = G; g->Gpad = (int32_t)round_up(G, 32);
+    g->ref.set(ctx); g->ctx = ctx; g->ncells = m->ncells; g->G = G; g->Gpad = (int32_t)round_up(G, 64);
     DevBuf<int32_t> d_fmap(ctx, fmap.size());
     MCB_CUDA(cudaMemcpyAsync(d_fmap.p, fmap.data(), fmap.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     DevBuf<double> mu(ctx, (size_t)m->ncells), inv(ctx, (size_t)m->ncells);
@@ -331,17 +341,11 @@ extern "C" int mcb_cgraph_create(mcb_ctx* ctx, const mcb_csc* m, const int32_t* 
     MCB_CUDA(cudaMemcpyAsync(&M, total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
     g->M = M; g->Mpad = round_up(std::max<int64_t>(M, 1), 256);
-    g->Zhi.alloc(ctx, (size_t)g->Mpad * g->Gpad);
-    g->Zlo.alloc(ctx, (size_t)g->Mpad * g->Gpad);
-    g->cell_of_row.alloc(ctx, (size_t)std::max<int64_t>(M, 1));
-    if (g->Mpad > M) {     // zero the padding rows
-        MCB_CUDA(cudaMemsetAsync(g->Zhi.p + (size_t)M * g->Gpad, 0, (size_t)(g->Mpad - M) * g->Gpad * sizeof(float), ctx->stream));
-        MCB_CUDA(cudaMemsetAsync(g->Zlo.p + (size_t)M * g->Gpad, 0, (size_t)(g->Mpad - M) * g->Gpad * sizeof(float), ctx->stream));
-    }
+    alloc_planes(g.get(), M);
     {
         StageTimer t(ctx, "feat_rows");
         launch_feat_rows(ctx, m->ncells, m->p, m->i, m->x, d_fmap.p, G, g->Gpad, k_nonz, mu.p, inv.p, valid.p, rowpos.p,
-                         g->Zhi.p, g->Zlo.p, g->cell_of_row.p);
+                         g->Zf.p, g->Zh.p, g->Zl.p, g->cell_of_row.p);
     }
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));     // temporaries die here
     *out = g.release();
@@ -356,7 +360,7 @@ extern "C" int mcb_cgraph_create_dense(mcb_ctx* ctx, const double* x, int32_t G,
     MCB_CHECK(G >= 2 && ncells >= 1, "MC-ERR: need at least 2 feature genes and 1 cell");
     MCB_CUDA(cudaSetDevice(ctx->device));
     std::unique_ptr<mcb_cgraph> g(new mcb_cgraph());
-    g->ref.set(ctx); g->ctx = ctx; g->ncells = ncells; g->G = G; g->Gpad = (int32_t)round_up(G, 32);
+    g->ref.set(ctx); g->ctx = ctx; g->ncells = ncells; g->G = G; g->Gpad = (int32_t)round_up(G, 64);
     DevBuf<double> dx(ctx, (size_t)ncells * G);
     {
         StageTimer t(ctx, "h2d_dense");
@@ -373,16 +377,10 @@ extern "C" int mcb_cgraph_create_dense(mcb_ctx* ctx, const double* x, int32_t G,
     MCB_CUDA(cudaMemcpyAsync(&M, total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
     g->M = M; g->Mpad = round_up(std::max<int64_t>(M, 1), 256);
-    g->Zhi.alloc(ctx, (size_t)g->Mpad * g->Gpad);
-    g->Zlo.alloc(ctx, (size_t)g->Mpad * g->Gpad);
-    g->cell_of_row.alloc(ctx, (size_t)std::max<int64_t>(M, 1));
-    if (g->Mpad > M) {
-        MCB_CUDA(cudaMemsetAsync(g->Zhi.p + (size_t)M * g->Gpad, 0, (size_t)(g->Mpad - M) * g->Gpad * sizeof(float), ctx->stream));
-        MCB_CUDA(cudaMemsetAsync(g->Zlo.p + (size_t)M * g->Gpad, 0, (size_t)(g->Mpad - M) * g->Gpad * sizeof(float), ctx->stream));
-    }
+    alloc_planes(g.get(), M);
     {
         StageTimer t(ctx, "feat_rows");
-        launch_dense_rows(ctx, ncells, dx.p, G, g->Gpad, mu.p, inv.p, valid.p, rowpos.p, g->Zhi.p, g->Zlo.p, g->cell_of_row.p);
+        launch_dense_rows(ctx, ncells, dx.p, G, g->Gpad, mu.p, inv.p, valid.p, rowpos.p, g->Zf.p, g->Zh.p, g->Zl.p, g->cell_of_row.p);
     }
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
     *out = g.release();
@@ -416,16 +414,10 @@ extern "C" int mcb_cgraph_features(mcb_cgraph* g, float* host_z)
     MCB_CHECK(g && host_z, "null argument");
     mcb_ctx* ctx = g->ctx;
     MCB_CUDA(cudaSetDevice(ctx->device));
-    // z = hi + lo, unpadded [M][G]
-    std::vector<float> hi((size_t)g->M * g->Gpad), lo((size_t)g->M * g->Gpad);
-    if (g->M) {
-        MCB_CUDA(cudaMemcpyAsync(hi.data(), g->Zhi.p, hi.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        MCB_CUDA(cudaMemcpyAsync(lo.data(), g->Zlo.p, lo.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    }
+    std::vector<float> z((size_t)g->M * g->Gpad);
+    if (g->M) MCB_CUDA(cudaMemcpyAsync(z.data(), g->Zf.p, z.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (int64_t r = 0; r < g->M; ++r)
-        for (int32_t c = 0; c < g->G; ++c)
-            host_z[r * g->G + c] = hi[(size_t)r * g->Gpad + c] + lo[(size_t)r * g->Gpad + c];
+    for (int64_t r = 0; r < g->M; ++r) memcpy(host_z + r * g->G, z.data() + (size_t)r * g->Gpad, sizeof(float) * (size_t)g->G);
     MCB_API_END
 }
 
@@ -496,11 +488,13 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     }
     DevBuf<int32_t> d_samp(ctx, (size_t)Spad);
     MCB_CUDA(cudaMemcpyAsync(d_samp.p, samp.data(), sizeof(int32_t) * (size_t)Spad, cudaMemcpyHostToDevice, ctx->stream));
-    DevBuf<float> Zs(ctx, (size_t)Spad * Gpad);
+    DevBuf<__half> Zs(ctx, ctx->gemm_impl == 0 ? (size_t)Spad * Gpad : 0);
+    DevBuf<float> Zsf(ctx, ctx->gemm_impl == 0 ? 0 : (size_t)Spad * Gpad);
     DevBuf<float> thr(ctx, (size_t)rows);
     {
         StageTimer t(ctx, "sample_gather");
-        launch_gather_rows(ctx, g->Zhi.p, Gpad, d_samp.p, (int32_t)Spad, Zs.p);
+        if (ctx->gemm_impl == 0) launch_gather_rows(ctx, g->Zh.p, (int64_t)Gpad * sizeof(__half), d_samp.p, (int32_t)Spad, Zs.p);
+        else launch_gather_rows(ctx, g->Zf.p, (int64_t)Gpad * sizeof(float), d_samp.p, (int32_t)Spad, Zsf.p);
     }
     {
         int64_t chunk = std::max<int64_t>(128, ((int64_t)2 << 30) / (Spad * 4) / 128 * 128);
@@ -512,10 +506,10 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
             {
                 StageTimer t(ctx, "cor_sample_gemm");
                 if (ctx->gemm_impl == 0)
-                    launch_tc_store(ctx, g->Zhi.p + (size_t)(row0 + c0) * Gpad, g->Mpad - (row0 + c0), Zs.p, Spad, Gpad,
+                    launch_tc_store(ctx, g->Zh.p + (size_t)(row0 + c0) * Gpad, g->Mpad - (row0 + c0), Zs.p, Spad, Gpad,
                                     Cs.p, Spad, nr, S);
                 else
-                    launch_simt_store(ctx, g->Zhi.p + (size_t)(row0 + c0) * Gpad, nullptr, nr, Zs.p, nullptr, S, Gpad, Cs.p, Spad);
+                    launch_simt_store(ctx, g->Zf.p + (size_t)(row0 + c0) * Gpad, nr, Zsf.p, S, Gpad, Cs.p, Spad);
             }
             {
                 StageTimer t(ctx, "sample_threshold");
@@ -530,10 +524,9 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     {
         StageTimer t(ctx, "cor_filter_gemm");
         if (ctx->gemm_impl == 0)
-            launch_tc_filter(ctx, g->Zhi.p, g->Zlo.p, g->Mpad, row0, rows, M, Gpad, thr.p, cand.p, cnt.p, cap);
+            launch_tc_filter(ctx, g->Zh.p, g->Zl.p, g->Mpad, row0, rows, M, Gpad, thr.p, cand.p, cnt.p, cap);
         else
-            launch_simt_filter(ctx, g->Zhi.p + (size_t)row0 * Gpad, g->Zlo.p + (size_t)row0 * Gpad, row0, rows, g->Zhi.p,
-                               g->Zlo.p, M, Gpad, thr.p, cand.p, cnt.p, cap);
+            launch_simt_filter(ctx, g->Zf.p + (size_t)row0 * Gpad, row0, rows, g->Zf.p, M, Gpad, thr.p, cand.p, cnt.p, cap);
     }
     // ---- ranked lists -------------------------------------------------------------------------
     DevBuf<int32_t> fail(ctx, (size_t)rows), fail_list(ctx, (size_t)rows), n_fail_d(ctx, 1);
@@ -551,7 +544,7 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
         // rows whose candidate count missed [kc_out-1, cap]: exact fp32 row on the CUDA cores
         StageTimer t(ctx, "knn_exact_rows");
         const int32_t B = 64;
-        DevBuf<float> Ah(ctx, (size_t)B * Gpad), Al(ctx, (size_t)B * Gpad), Cf(ctx, (size_t)B * M);
+        DevBuf<float> Af(ctx, (size_t)B * Gpad), Cf(ctx, (size_t)B * M);
         DevBuf<int32_t> glist(ctx, (size_t)B);
         std::vector<int32_t> hl((size_t)n_fail), gl((size_t)B);
         MCB_CUDA(cudaMemcpyAsync(hl.data(), fail_list.p, sizeof(int32_t) * (size_t)n_fail, cudaMemcpyDeviceToHost, ctx->stream));
@@ -560,9 +553,8 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
             const int32_t nb = std::min(B, n_fail - b0);
             for (int32_t q = 0; q < nb; ++q) gl[q] = (int32_t)(row0 + hl[b0 + q]);
             MCB_CUDA(cudaMemcpyAsync(glist.p, gl.data(), sizeof(int32_t) * (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
-            launch_gather_rows(ctx, g->Zhi.p, Gpad, glist.p, nb, Ah.p);
-            launch_gather_rows(ctx, g->Zlo.p, Gpad, glist.p, nb, Al.p);
-            launch_simt_store(ctx, Ah.p, Al.p, nb, g->Zhi.p, g->Zlo.p, M, Gpad, Cf.p, M);
+            launch_gather_rows(ctx, g->Zf.p, (int64_t)Gpad * sizeof(float), glist.p, nb, Af.p);
+            launch_simt_store(ctx, Af.p, nb, g->Zf.p, M, Gpad, Cf.p, M);
             launch_topk_big(ctx, Cf.p, M, M, fail_list.p + b0, nb, row0, kc_out, Kc, own_col, g->knn_cor.p);
             MCB_CUDA(cudaStreamSynchronize(ctx->stream));      // gl is reused
         }
@@ -628,7 +620,7 @@ extern "C" int mcb_cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
     g->H = H;
     MCB_CHECK(M < ((int64_t)1 << (32 - g->rank_bits)) - 1, "MC-ERR: too many cells for the packed rank table at this K * k_expand");
     // drop the feature planes: they are not needed after the kNN stage and the table is large
-    g->Zhi.release(); g->Zlo.release();
+    g->Zf.release(); g->Zh.release(); g->Zl.release();
     DevBuf<uint32_t> table(ctx, (size_t)M * H);
     g->sym.alloc(ctx, (size_t)std::max<int64_t>(g->rows, 1) * Kc);
     g->thr_in.alloc(ctx, (size_t)g->nranks * g->rows_per_rank);
@@ -711,16 +703,16 @@ extern "C" int mcb_cgraph_edges(mcb_cgraph* g, int32_t* host_src, int32_t* host_
 extern "C" int mcb_cgraph_debug_cor(mcb_cgraph* g, int impl, int64_t a_rows, int64_t b_rows, float* host_c)
 {
     MCB_API_BEGIN
-    MCB_CHECK(g && g->Zhi.p && host_c, "mcb_cgraph_debug_cor: features not available");
+    MCB_CHECK(g && g->Zf.p && host_c, "mcb_cgraph_debug_cor: features not available");
     MCB_CHECK(a_rows <= g->M && b_rows <= g->M, "mcb_cgraph_debug_cor: block exceeds matrix");
     mcb_ctx* ctx = g->ctx;
     MCB_CUDA(cudaSetDevice(ctx->device));
     const int64_t ldc = round_up(b_rows, 4);
     DevBuf<float> C(ctx, (size_t)a_rows * ldc);
     C.zero();
-    if (impl == 0) launch_tc_store3(ctx, g->Zhi.p, g->Zlo.p, g->Mpad, a_rows, b_rows, g->Gpad, C.p, ldc);
-    else if (impl == 2) launch_tc_store(ctx, g->Zhi.p, g->Mpad, g->Zhi.p, g->Mpad, g->Gpad, C.p, ldc, a_rows, b_rows);
-    else launch_simt_store(ctx, g->Zhi.p, g->Zlo.p, a_rows, g->Zhi.p, g->Zlo.p, b_rows, g->Gpad, C.p, ldc);
+    if (impl == 0) launch_tc_store3(ctx, g->Zh.p, g->Zl.p, g->Mpad, a_rows, b_rows, g->Gpad, C.p, ldc);
+    else if (impl == 2) launch_tc_store(ctx, g->Zh.p, g->Mpad, g->Zh.p, g->Mpad, g->Gpad, C.p, ldc, a_rows, b_rows);
+    else launch_simt_store(ctx, g->Zf.p, a_rows, g->Zf.p, b_rows, g->Gpad, C.p, ldc);
     std::vector<float> h((size_t)a_rows * ldc);
     MCB_CUDA(cudaMemcpyAsync(h.data(), C.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -68,6 +68,10 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// fp16 operand planes hold z * 2^12 (features.cu); the contraction is rescaled by 2^-24 in the epilogue
+constexpr float Z_PRESCALE = 4096.0f;
+constexpr float C_RESCALE = 1.0f / (4096.0f * 4096.0f);
+
 constexpr uint32_t TAG_DOWNSAMP = 0x4453u;   // 'DS'
 constexpr uint32_t TAG_COVER    = 0x4743u;   // 'GC'
 constexpr uint32_t STREAM_SEED  = 1u;

@@ -3,14 +3,17 @@
 // standardisation, so that Pearson cor(i, j) (what tgs_cor_knn computes, R/utils.r:119) becomes a
 // plain dot product of rows of Z.
 //
-// Layout in HBM: Z is [Mpad][Gpad] fp32 row-major (one row per *valid* cell, K-major for both
-// GEMM operands), stored as two TF32-exact planes Zhi + Zlo = fp32(z) for the 3-pass split-TF32
-// contraction.  Gpad is G rounded up to 32 (one 128-byte swizzle atom per k-block); padded columns
-// and padded rows are zero.  Cells whose feature vector has zero variance (NA correlations in R,
+// Layout in HBM: Z is [Mpad][Gpad] row-major (one row per *valid* cell, K-major for both GEMM
+// operands), stored three times: Zf = fp32(z) for the CUDA-core kernels, and two FP16 planes
+// Zh + Zl = z * 2^12 (hi = fp16(z*S), lo = fp16(z*S - hi)) for the 3-pass split contraction on the
+// tensor cores.  Gpad is G rounded up to 64 (one 128-byte swizzle row of fp16 per k-block); padded
+// columns and padded rows are zero.  Cells whose feature vector has zero variance (NA correlations in R,
 // R/cgraph_knn_mcnorm.r:25) are dropped here: rowpos compacts the valid cells.
 //
 // HBM-bound sparse-to-dense work: read nnz * 8 B twice, write M * Gpad * 8 B once, coalesced.
+// The fp16 prescale 2^12 keeps every |z| >= 2^-15 in the normal fp16 range for the lo plane.
 #include "internal.h"
+#include <cuda_fp16.h>
 
 namespace mcb {
 
@@ -89,14 +92,23 @@ __global__ void __launch_bounds__(1024) excl_scan_kernel(const T* __restrict__ i
     if (threadIdx.x == 0 && total) *total = carry_s;
 }
 
-// one CTA per cell: build the standardised row in shared memory, write the hi/lo planes coalesced
+// z -> (hi, lo) fp16 planes with the 2^12 prescale
+__device__ __forceinline__ void split_store(float z, __half* hi, __half* lo)
+{
+    const float zs = z * Z_PRESCALE;
+    const __half h = __float2half_rn(zs);
+    *hi = h;
+    *lo = __float2half_rn(zs - __half2float(h));
+}
+
+// one CTA per cell: build the standardised row in shared memory, write the three planes coalesced
 constexpr int FR_THREADS = 128;
 __global__ void __launch_bounds__(FR_THREADS)
 feat_rows_kernel(int64_t ncells, const int64_t* __restrict__ p, const int32_t* __restrict__ ridx,
                  const uint32_t* __restrict__ x, const int32_t* __restrict__ feat_map, int32_t G, int32_t Gpad,
                  double k_nonz, const double* __restrict__ mu_in, const double* __restrict__ inv_in,
-                 const int32_t* __restrict__ valid, const int32_t* __restrict__ rowpos, float* __restrict__ Zhi,
-                 float* __restrict__ Zlo, int32_t* __restrict__ cell_of_row)
+                 const int32_t* __restrict__ valid, const int32_t* __restrict__ rowpos, float* __restrict__ Zf,
+                 __half* __restrict__ Zh, __half* __restrict__ Zl, int32_t* __restrict__ cell_of_row)
 {
     extern __shared__ float srow[];        // [Gpad]
     for (int64_t c = blockIdx.x; c < ncells; c += gridDim.x) {
@@ -115,32 +127,28 @@ feat_rows_kernel(int64_t ncells, const int64_t* __restrict__ p, const int32_t* _
         }
         __syncthreads();
         const int64_t r = rowpos[c];
-        float* hi = Zhi + r * (int64_t)Gpad;
-        float* lo = Zlo + r * (int64_t)Gpad;
         for (int g = threadIdx.x; g < Gpad; g += FR_THREADS) {
             const float z = srow[g];
-            const float h = tf32_round(z);
-            hi[g] = h;
-            lo[g] = tf32_round(z - h);
+            Zf[r * (int64_t)Gpad + g] = z;
+            split_store(z, Zh + r * (int64_t)Gpad + g, Zl + r * (int64_t)Gpad + g);
         }
         if (threadIdx.x == 0) cell_of_row[r] = (int32_t)c;
         __syncthreads();
     }
 }
 
-// out[q][:] = Z[rows[q]][:]   (builds the contiguous sample operand of the threshold pass)
-__global__ void gather_rows_kernel(const float* __restrict__ Z, int32_t Gpad, const int32_t* __restrict__ rows,
-                                   int32_t nrows, float* __restrict__ out)
+// out[q][:] = Z[rows[q]][:] for rows of row_bytes bytes (multiple of 16); rows[q] < 0 -> zeros
+__global__ void gather_rows_kernel(const uint4* __restrict__ Z, int32_t row_vecs, const int32_t* __restrict__ rows,
+                                   int32_t nrows, uint4* __restrict__ out)
 {
-    const int vec = Gpad >> 2;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (int64_t)nrows * vec;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < (int64_t)nrows * row_vecs;
          idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t q = idx / vec;
-        const int v = (int)(idx % vec);
+        const int64_t q = idx / row_vecs;
+        const int v = (int)(idx % row_vecs);
         const int32_t r = rows[q];
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r >= 0) val = reinterpret_cast<const float4*>(Z + (int64_t)r * Gpad)[v];
-        reinterpret_cast<float4*>(out + q * (int64_t)Gpad)[v] = val;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (r >= 0) val = Z[(int64_t)r * row_vecs + v];
+        out[q * (int64_t)row_vecs + v] = val;
     }
 }
 
@@ -177,7 +185,7 @@ dense_stats_kernel(int64_t ncells, const double* __restrict__ x, int32_t G, doub
 __global__ void __launch_bounds__(128)
 dense_rows_kernel(int64_t ncells, const double* __restrict__ x, int32_t G, int32_t Gpad, const double* __restrict__ mu_in,
                   const double* __restrict__ inv_in, const int32_t* __restrict__ valid, const int32_t* __restrict__ rowpos,
-                  float* __restrict__ Zhi, float* __restrict__ Zlo, int32_t* __restrict__ cell_of_row)
+                  float* __restrict__ Zf, __half* __restrict__ Zh, __half* __restrict__ Zl, int32_t* __restrict__ cell_of_row)
 {
     for (int64_t c = blockIdx.x; c < ncells; c += gridDim.x) {
         if (!valid[c]) continue;
@@ -186,9 +194,8 @@ dense_rows_kernel(int64_t ncells, const double* __restrict__ x, int32_t G, int32
         const int64_t r = rowpos[c];
         for (int g = threadIdx.x; g < Gpad; g += 128) {
             const float z = g < G ? (float)((v[g] - mu) * inv) : 0.0f;
-            const float h = tf32_round(z);
-            Zhi[r * (int64_t)Gpad + g] = h;
-            Zlo[r * (int64_t)Gpad + g] = tf32_round(z - h);
+            Zf[r * (int64_t)Gpad + g] = z;
+            split_store(z, Zh + r * (int64_t)Gpad + g, Zl + r * (int64_t)Gpad + g);
         }
         if (threadIdx.x == 0) cell_of_row[r] = (int32_t)c;
     }
@@ -202,12 +209,12 @@ void launch_dense_stats(mcb_ctx* ctx, int64_t ncells, const double* x, int32_t G
     MCB_LAUNCH_CHECK();
 }
 void launch_dense_rows(mcb_ctx* ctx, int64_t ncells, const double* x, int32_t G, int32_t Gpad, const double* mu,
-                       const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zhi, float* Zlo,
+                       const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zf, void* Zh, void* Zl,
                        int32_t* cell_of_row)
 {
     if (ncells == 0) return;
     int grid = (int)std::min<int64_t>(ncells, (int64_t)ctx->num_sms * 16);
-    dense_rows_kernel<<<grid, 128, 0, ctx->stream>>>(ncells, x, G, Gpad, mu, inv, valid, rowpos, Zhi, Zlo, cell_of_row);
+    dense_rows_kernel<<<grid, 128, 0, ctx->stream>>>(ncells, x, G, Gpad, mu, inv, valid, rowpos, Zf, (__half*)Zh, (__half*)Zl, cell_of_row);
     MCB_LAUNCH_CHECK();
 }
 
@@ -231,20 +238,22 @@ void launch_exclusive_scan_i64(mcb_ctx* ctx, const int64_t* in, int64_t* out, in
 }
 void launch_feat_rows(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const int32_t* ridx, const uint32_t* x,
                       const int32_t* feat_map, int32_t G, int32_t Gpad, double k_nonz, const double* mu,
-                      const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zhi, float* Zlo,
+                      const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zf, void* Zh, void* Zl,
                       int32_t* cell_of_row)
 {
     if (ncells == 0) return;
     int grid = (int)std::min<int64_t>(ncells, (int64_t)ctx->num_sms * 16);
     feat_rows_kernel<<<grid, FR_THREADS, (size_t)Gpad * sizeof(float), ctx->stream>>>(
-        ncells, p, ridx, x, feat_map, G, Gpad, k_nonz, mu, inv, valid, rowpos, Zhi, Zlo, cell_of_row);
+        ncells, p, ridx, x, feat_map, G, Gpad, k_nonz, mu, inv, valid, rowpos, Zf, (__half*)Zh, (__half*)Zl, cell_of_row);
     MCB_LAUNCH_CHECK();
 }
-void launch_gather_rows(mcb_ctx* ctx, const float* Z, int32_t Gpad, const int32_t* rows, int32_t nrows, float* out)
+void launch_gather_rows(mcb_ctx* ctx, const void* Z, int64_t row_bytes, const int32_t* rows, int32_t nrows, void* out)
 {
     if (nrows == 0) return;
-    int grid = (int)std::min<int64_t>(ceil_div((int64_t)nrows * (Gpad / 4), 256), (int64_t)ctx->num_sms * 16);
-    gather_rows_kernel<<<grid, 256, 0, ctx->stream>>>(Z, Gpad, rows, nrows, out);
+    MCB_CHECK(row_bytes % 16 == 0, "gather_rows: row size must be a multiple of 16 bytes");
+    const int32_t rv = (int32_t)(row_bytes / 16);
+    int grid = (int)std::min<int64_t>(ceil_div((int64_t)nrows * rv, 256), (int64_t)ctx->num_sms * 16);
+    gather_rows_kernel<<<grid, 256, 0, ctx->stream>>>((const uint4*)Z, rv, rows, nrows, (uint4*)out);
     MCB_LAUNCH_CHECK();
 }
 

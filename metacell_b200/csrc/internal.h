@@ -90,28 +90,27 @@ void launch_feat_stats(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const int
 void launch_exclusive_scan_i32(mcb_ctx* ctx, const int32_t* in, int32_t* out, int64_t n, int32_t* total);
 void launch_feat_rows(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const int32_t* ridx, const uint32_t* x,
                       const int32_t* feat_map, int32_t G, int32_t Gpad, double k_nonz, const double* mu,
-                      const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zhi, float* Zlo,
+                      const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zf, void* Zh, void* Zl,
                       int32_t* cell_of_row);
 void launch_dense_stats(mcb_ctx* ctx, int64_t ncells, const double* x, int32_t G, double* mu, double* inv, int32_t* valid);
 void launch_dense_rows(mcb_ctx* ctx, int64_t ncells, const double* x, int32_t G, int32_t Gpad, const double* mu,
-                       const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zhi, float* Zlo,
+                       const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zf, void* Zh, void* Zl,
                        int32_t* cell_of_row);
-void launch_gather_rows(mcb_ctx* ctx, const float* Z, int32_t Gpad, const int32_t* rows, int32_t nrows, float* out);
+void launch_gather_rows(mcb_ctx* ctx, const void* Z, int64_t row_bytes, const int32_t* rows, int32_t nrows, void* out);
 
-// corknn_simt.cu : C[i][j] = sum_g (Ahi+Alo)[i][g] * (Bhi+Blo)[j][g] in fp32 on the CUDA cores
-void launch_simt_store(mcb_ctx* ctx, const float* Ahi, const float* Alo, int64_t a_rows, const float* Bhi,
-                       const float* Blo, int64_t b_rows, int32_t Gpad, float* C, int64_t ldc);
-void launch_simt_filter(mcb_ctx* ctx, const float* Ahi, const float* Alo, int64_t a_row0, int64_t a_rows,
-                        const float* Bhi, const float* Blo, int64_t b_rows, int32_t Gpad, const float* thr,
-                        uint64_t* cand, uint32_t* cnt, int32_t cap);
+// corknn_simt.cu : C[i][j] = sum_g A[i][g] * B[j][g] on the CUDA cores, fp32 inputs, fp64 accumulate
+void launch_simt_store(mcb_ctx* ctx, const float* A, int64_t a_rows, const float* B, int64_t b_rows, int32_t Gpad,
+                       float* C, int64_t ldc);
+void launch_simt_filter(mcb_ctx* ctx, const float* A, int64_t a_row0, int64_t a_rows, const float* B, int64_t b_rows,
+                        int32_t Gpad, const float* thr, uint64_t* cand, uint32_t* cnt, int32_t cap);
 
-// corknn_tc.cu : the tcgen05 / TMEM / TMA kernels
+// corknn_tc.cu : the tcgen05 / TMEM / TMA kernels on the fp16 hi/lo planes (void* = __half*)
 void tc_init();   // resolves cuTensorMapEncodeTiled
-void launch_tc_store(mcb_ctx* ctx, const float* Ahi, int64_t a_rows_pad, const float* Bhi, int64_t b_rows_pad,
+void launch_tc_store(mcb_ctx* ctx, const void* Ah, int64_t a_rows_alloc, const void* Bh, int64_t b_rows_alloc,
                      int32_t Gpad, float* C, int64_t ldc, int64_t a_rows, int64_t b_rows);
-void launch_tc_store3(mcb_ctx* ctx, const float* Zhi, const float* Zlo, int64_t rows_alloc, int64_t a_rows,
+void launch_tc_store3(mcb_ctx* ctx, const void* Zh, const void* Zl, int64_t rows_alloc, int64_t a_rows,
                       int64_t b_rows, int32_t Gpad, float* C, int64_t ldc);
-void launch_tc_filter(mcb_ctx* ctx, const float* Zhi, const float* Zlo, int64_t rows_pad_total, int64_t a_row0,
+void launch_tc_filter(mcb_ctx* ctx, const void* Zh, const void* Zl, int64_t rows_alloc, int64_t a_row0,
                       int64_t a_rows, int64_t b_rows, int32_t Gpad, const float* thr, uint64_t* cand,
                       uint32_t* cnt, int32_t cap);
 

@@ -98,7 +98,17 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr)         // whole wa
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "n"(COLS) : "memory");
 }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], TF32 inputs, FP32 accumulate; issued by ONE thread
+// D[tmem] (+)= A[smem desc] * B[smem desc], FP16 inputs, FP32 accumulate; issued by ONE thread
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// same with TF32 inputs (kept for A/B measurements of the operand format, DESIGN.md "Precision")
 __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
@@ -142,6 +152,16 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr)
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, shape M x N
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N)
+{
+    return (1u << 4)              // c_format  = F32
+         | (0u << 7)              // a_format  = F16
+         | (0u << 10)             // b_format  = F16
+         | (0u << 15) | (0u << 16)   // a_major, b_major = K
+         | ((N >> 3) << 17)       // n_dim
+         | ((M >> 4) << 24);      // m_dim
 }
 // kind::tf32 instruction descriptor: D = F32, A = B = TF32, both K-major, shape M x N
 __host__ __device__ constexpr uint32_t make_idesc_tf32(uint32_t M, uint32_t N)

@@ -1,0 +1,83 @@
+"""Host-side mirror of the reference interface (metacell_b200/api.py): containers, scdb, parameters,
+error behaviour -- everything that needs no GPU."""
+import numpy as np
+import pytest
+
+
+def test_params_follow_reference_yaml():
+    from metacell_b200 import api
+    assert api.get_param("scm_k_nonz_exp") == 7                       # metacell_params.yaml:44
+    assert api.get_param("scm_balance_graph_k_beta") == 3             # :50
+    assert api.get_param("scm_balance_graph_k_expand") == 10          # :51
+    assert api.get_param("scm_tgs_clust_cool") == 1.05 and api.get_param("scm_tgs_clust_burn_in") == 10
+    assert api.get_param("mc_rseed") == 42
+    api.set_param("mc_rseed", 7)
+    assert api.get_param("mc_rseed") == 7
+    api.set_param("mc_rseed", 42)
+    with pytest.raises(api.McbError, match="MC-ERR"):
+        api.get_param("nope")
+
+
+def test_scdb_roundtrip_and_errors(tmp_path):
+    from metacell_b200 import api
+    with pytest.raises(api.McbError, match="MC-ERR"):
+        api.scdb_init(str(tmp_path / "missing"))
+    api.scdb_init(str(tmp_path), force_reinit=True)
+    cg = api.tgCellGraph({"mc1": np.array([0, 1]), "mc2": np.array([1, 2]), "w": np.array([1.0, 0.5])}, ["a", "b", "c"])
+    api.scdb_add_cgraph("g1", cg)
+    assert (tmp_path / "cgraph.g1.pkl").exists()                      # "<base>/<type>.<id>" naming, R/scdb.r:100-131
+    api.scdb_init(str(tmp_path), force_reinit=True)                   # drops the cache -> reload from disk
+    back = api.scdb_cgraph("g1")
+    assert back.cell_names == ["a", "b", "c"] and np.array_equal(back.edges["mc2"], [1, 2])
+    assert api.scdb_cgraph("none") is None
+    coc = api.tgCoClust("g1", {"node1": np.array([0]), "node2": np.array([1]), "cnt": np.array([3])}, np.array([1, 1, 1]))
+    api.scdb_add_coclust("c1", coc)
+    assert api.scdb_coclust("c1").graph_id == "g1"
+    with pytest.raises(api.McbError, match="MC-ERR"):
+        api.tgCoClust("g1", {"node1": [0], "node2": [1]}, [1])        # missing cnt column (R/coclust.r:39-41)
+    with pytest.raises(api.McbError, match="MC-ERR"):
+        api.tgCoClust("nope", {"node1": [0], "node2": [1], "cnt": [1]}, [1])
+
+
+def test_cell_graph_container(capsys):
+    from metacell_b200 import api
+    cg = api.tgCellGraph({"mc1": np.array([0, 0]), "mc2": np.array([1, 2]), "w": np.array([1.0, 0.9])}, ["a", "b", "c", "d"])
+    assert cg.nodes == ["a", "b", "c"]
+    assert "missing 1 nodes" in capsys.readouterr().err              # R/cgraph.r:36-39
+    with pytest.raises(api.McbError, match="MC-ERR"):
+        api.tgCellGraph({"mc1": [0], "mc2": [1]}, ["a", "b"])
+
+
+def test_feature_rows_follow_gene_set_order():
+    from metacell_b200 import api
+    mat = api.tgScMat([0, 1, 2], [0, 3], [1.0, 2.0], genes=["g0", "g1", "g2", "g3"])
+    gs = api.tgGeneSets({"g3": 1, "gX": 1, "g1": 2, "g0": 1})
+    assert api._feature_rows(gs, mat).tolist() == [3, 1, 0]           # intersect(names(gset), rownames), R/gset.r:192-197
+    with pytest.raises(api.McbError, match="MC-ERR"):
+        api._feature_rows(api.tgGeneSets({"g0": 1}), mat)
+
+
+def test_missing_objects_raise_reference_style_errors(tmp_path):
+    from metacell_b200 import api
+    api.scdb_init(str(tmp_path), force_reinit=True)
+    with pytest.raises(api.McbError, match="MC-ERR: non existing gset"):
+        api.mcell_add_cgraph_from_mat_bknn("m", "gs", "g", 100)
+    with pytest.raises(api.McbError, match="MC-ERR: cell graph id"):
+        api.mcell_coclust_from_graph_resamp("c", "g", 20, 0.75, 10)
+
+
+def test_resample_index_sets():
+    from metacell_b200 import api
+    sets, seeds = api.resample_index_sets(1000, 0.75, 6, 42)
+    assert sets.shape == (6, 750) and seeds.shape == (6,) and seeds.dtype == np.uint64
+    assert np.all(np.diff(sets, axis=1) > 0) and sets.min() >= 0 and sets.max() < 1000
+    s2, d2 = api.resample_index_sets(1000, 0.75, 6, 42)
+    assert np.array_equal(sets, s2) and np.array_equal(seeds, d2)
+    assert len({tuple(r) for r in sets}) == 6
+
+
+def test_synth_shapes():
+    from metacell_b200 import synth
+    m = synth.make_umi_matrix(300, 200, n_types=5, median_umis=1000.0, seed=1)
+    assert m.indptr.size == 301 and m.indices.max() < 200 and m.data.min() >= 1
+    assert abs(np.median(m.col_sums()) / 1000.0 - 1.0) < 0.5
