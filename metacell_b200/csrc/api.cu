@@ -520,13 +520,35 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     // ---- filter pass: full 3-pass contraction, candidates above the row threshold ------------
     DevBuf<uint64_t> cand(ctx, (size_t)rows * cap);
     DevBuf<uint32_t> cnt(ctx, (size_t)rows);
-    cnt.zero();
-    {
+    if (ctx->gemm_impl == 0) {
+        // the epilogue appends records to pool chunks; expected records ~ rows * (count at the sampled threshold)
+        const uint32_t crec = tc_pool_chunk_records();
+        double expect = (double)rows * (r_sel > S ? (double)M : (double)r_sel * (double)M / (double)S);
+        for (int attempt = 0;; ++attempt) {
+            const uint32_t n_chunks = (uint32_t)std::min<double>(4.0e6, expect * 1.3 / crec + tc_pool_min_chunks(ctx));
+            DevBuf<uint4> records(ctx, (size_t)n_chunks * crec);
+            DevBuf<uint32_t> chunk_fill(ctx, (size_t)n_chunks), ctl(ctx, 2);
+            chunk_fill.zero(); ctl.zero(); cnt.zero();
+            CandPool pool{records.p, ctl.p, chunk_fill.p, n_chunks, ctl.p + 1};
+            {
+                StageTimer t(ctx, "cor_filter_gemm");
+                launch_tc_filter(ctx, g->Zh.p, g->Zl.p, g->Mpad, row0, rows, M, Gpad, thr.p, pool);
+            }
+            {
+                StageTimer t(ctx, "cand_scatter");
+                launch_scatter_candidates(ctx, pool, cand.p, cnt.p, cap);
+            }
+            uint32_t hctl[2] = {0, 0};
+            MCB_CUDA(cudaMemcpyAsync(hctl, ctl.p, sizeof(hctl), cudaMemcpyDeviceToHost, ctx->stream));
+            MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (!hctl[1]) break;
+            MCB_CHECK(attempt < 3, "MC-ERR: candidate pool overflow (correlation structure far from the sampled estimate)");
+            expect *= 2.0;          // the pool ran out: repeat the pass with twice the room
+        }
+    } else {
+        cnt.zero();
         StageTimer t(ctx, "cor_filter_gemm");
-        if (ctx->gemm_impl == 0)
-            launch_tc_filter(ctx, g->Zh.p, g->Zl.p, g->Mpad, row0, rows, M, Gpad, thr.p, cand.p, cnt.p, cap);
-        else
-            launch_simt_filter(ctx, g->Zf.p + (size_t)row0 * Gpad, row0, rows, g->Zf.p, M, Gpad, thr.p, cand.p, cnt.p, cap);
+        launch_simt_filter(ctx, g->Zf.p + (size_t)row0 * Gpad, row0, rows, g->Zf.p, M, Gpad, thr.p, cand.p, cnt.p, cap);
     }
     // ---- ranked lists -------------------------------------------------------------------------
     DevBuf<int32_t> fail(ctx, (size_t)rows), fail_list(ctx, (size_t)rows), n_fail_d(ctx, 1);

@@ -110,9 +110,16 @@ void launch_tc_store(mcb_ctx* ctx, const void* Ah, int64_t a_rows_alloc, const v
                      int32_t Gpad, float* C, int64_t ldc, int64_t a_rows, int64_t b_rows);
 void launch_tc_store3(mcb_ctx* ctx, const void* Zh, const void* Zl, int64_t rows_alloc, int64_t a_rows,
                       int64_t b_rows, int32_t Gpad, float* C, int64_t ldc);
+// candidate records (uint4 = key lo, key hi, local row, 0) appended by the filter epilogue in chunks
+struct CandPool {
+    void* records; uint32_t* cursor; uint32_t* chunk_fill; uint32_t n_chunks; uint32_t* overflow;
+};
+uint32_t tc_pool_chunk_records();
+uint32_t tc_pool_min_chunks(mcb_ctx* ctx);
 void launch_tc_filter(mcb_ctx* ctx, const void* Zh, const void* Zl, int64_t rows_alloc, int64_t a_row0,
-                      int64_t a_rows, int64_t b_rows, int32_t Gpad, const float* thr, uint64_t* cand,
-                      uint32_t* cnt, int32_t cap);
+                      int64_t a_rows, int64_t b_rows, int32_t Gpad, const float* thr, const CandPool& pool);
+// select.cu: bin the pool's records into the per-row candidate lists (cnt counts every record, also past cap)
+void launch_scatter_candidates(mcb_ctx* ctx, const CandPool& pool, uint64_t* cand, uint32_t* cnt, int32_t cap);
 
 // select.cu
 void launch_sample_threshold(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t rows, int32_t S, int32_t r,

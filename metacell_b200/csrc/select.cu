@@ -160,6 +160,28 @@ topk_big_kernel(const float* __restrict__ C, int64_t ldc, int64_t M, const int32
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// records of the filter epilogue -> per-row candidate lists.  One CTA per pool chunk; the returning
+// atomics that hand out list positions are independent across threads, so their latency is hidden by
+// parallelism here instead of stalling the GEMM epilogue.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+scatter_candidates_kernel(const uint4* __restrict__ records, const uint32_t* __restrict__ cursor,
+                          const uint32_t* __restrict__ chunk_fill, uint32_t pool_chunks, uint32_t chunk_records,
+                          uint64_t* __restrict__ cand, uint32_t* __restrict__ cnt, int32_t cap)
+{
+    const uint32_t used = min(*cursor, pool_chunks);
+    for (uint32_t ch = blockIdx.x; ch < used; ch += gridDim.x) {
+        const uint32_t n = min(chunk_fill[ch], chunk_records);
+        const uint4* r = records + (size_t)ch * chunk_records;
+        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+            const uint4 rec = r[e];
+            const uint32_t pos = atomicAdd(&cnt[rec.z], 1u);
+            if (pos < (uint32_t)cap) cand[(size_t)rec.z * cap + pos] = ((uint64_t)rec.y << 32) | rec.x;
+        }
+    }
+}
+
 // compact the flagged rows into a list; *n_out = count
 __global__ void compact_flags_kernel(const int32_t* __restrict__ flag, int64_t n, int32_t* __restrict__ list,
                                      int32_t* __restrict__ n_out)
@@ -199,6 +221,14 @@ void launch_topk_rows(mcb_ctx* ctx, const uint64_t* cand, const uint32_t* cnt, i
     int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
     topk_rows_kernel<<<grid, SEL_THREADS, smem, ctx->stream>>>(cand, cnt, cap, row0, rows, kc_out, Kc, knn_col,
                                                                 knn_cor, fail_flag);
+    MCB_LAUNCH_CHECK();
+}
+
+void launch_scatter_candidates(mcb_ctx* ctx, const CandPool& pool, uint64_t* cand, uint32_t* cnt, int32_t cap)
+{
+    int grid = (int)std::min<int64_t>(pool.n_chunks, (int64_t)ctx->num_sms * 8);
+    scatter_candidates_kernel<<<grid, 256, 0, ctx->stream>>>((const uint4*)pool.records, pool.cursor, pool.chunk_fill,
+                                                             pool.n_chunks, tc_pool_chunk_records(), cand, cnt, cap);
     MCB_LAUNCH_CHECK();
 }
 
