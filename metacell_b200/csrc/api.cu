@@ -65,6 +65,54 @@ static void resolve_timers(mcb_ctx* ctx)
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
+static size_t block_size(size_t bytes) { return (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1); }   // 2 MB granules
+
+void* mcb_ctx::dev_alloc(size_t bytes)
+{
+    const size_t sz = block_size(bytes);
+    {
+        std::lock_guard<std::mutex> lk(alloc_mu);
+        auto it = free_blocks.find(sz);
+        if (it != free_blocks.end()) {
+            void* p = it->second;
+            free_blocks.erase(it);
+            cached_bytes -= sz; live_bytes += sz;
+            return p;
+        }
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, sz);
+    if (e == cudaErrorMemoryAllocation) {        // give the cache back and retry once
+        cudaGetLastError();
+        MCB_CUDA(cudaStreamSynchronize(stream));
+        trim();
+        e = cudaMalloc(&p, sz);
+    }
+    if (e != cudaSuccess) {
+        char b[200];
+        snprintf(b, sizeof(b), "MC-ERR: device allocation of %zu MB failed: %s", sz >> 20, cudaGetErrorString(e));
+        cudaGetLastError();
+        throw mcb::Error(2, b);
+    }
+    std::lock_guard<std::mutex> lk(alloc_mu);
+    live_bytes += sz;
+    return p;
+}
+void mcb_ctx::dev_free(void* p, size_t bytes)
+{
+    const size_t sz = block_size(bytes);
+    std::lock_guard<std::mutex> lk(alloc_mu);
+    free_blocks.emplace(sz, p);
+    cached_bytes += sz; live_bytes -= sz;
+}
+void mcb_ctx::trim()
+{
+    std::lock_guard<std::mutex> lk(alloc_mu);
+    for (auto& kv : free_blocks) cudaFree(kv.second);
+    free_blocks.clear();
+    cached_bytes = 0;
+}
+
 extern "C" int mcb_ctx_create(int device, mcb_ctx** out)
 {
     MCB_API_BEGIN
@@ -86,9 +134,6 @@ extern "C" int mcb_ctx_create(int device, mcb_ctx** out)
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     MCB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    MCB_CUDA(cudaDeviceGetDefaultMemPool(&c->pool, device));
-    uint64_t thresh = UINT64_MAX;
-    MCB_CUDA(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     *out = c;
     MCB_API_END
 }
@@ -99,6 +144,7 @@ void mcb::ctx_release(mcb_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     resolve_timers(ctx);
+    ctx->trim();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -123,6 +169,7 @@ extern "C" int mcb_ctx_set_option(mcb_ctx* ctx, const char* key, int64_t value)
     else if (!strcmp(key, "profile")) ctx->profile = (int)value;
     else if (!strcmp(key, "keep_self")) ctx->keep_self = (int)value;
     else if (!strcmp(key, "thresh_strict")) ctx->thresh_strict = (int)value;
+    else if (!strcmp(key, "trim")) { MCB_CUDA(cudaStreamSynchronize(ctx->stream)); ctx->trim(); }
     else throw Error(1, std::string("unknown option: ") + key);
     MCB_API_END
 }

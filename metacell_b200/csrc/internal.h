@@ -7,13 +7,23 @@
 #include <memory>
 #include <vector>
 #include <string>
+#include <map>
+#include <mutex>
 
 struct mcb_ctx {
     std::atomic<int> refs{1};   // the creator + every live handle; destroyed when it drops to 0
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
-    cudaMemPool_t pool = nullptr;
+    // size-keyed cache of device blocks: a step repeats the same allocation sizes, so after the first
+    // step no allocation reaches the driver (driver allocation calls were measured to stall for tens of
+    // ms under a busy host).  Reuse is safe because every user of a block is ordered on `stream`.
+    std::multimap<size_t, void*> free_blocks;
+    size_t cached_bytes = 0, live_bytes = 0;
+    std::mutex alloc_mu;
+    void* dev_alloc(size_t bytes);
+    void dev_free(void* p, size_t bytes);
+    void trim();
     // options
     int gemm_impl = 0;       // 0 tcgen05, 1 simt
     int profile = 0;
@@ -45,12 +55,12 @@ struct DevBuf {
         release();
         ctx = c; n = count;
         if (count == 0) { p = nullptr; return; }
-        MCB_CUDA(cudaMallocAsync((void**)&p, count * sizeof(T), c->stream));
+        p = (T*)c->dev_alloc(count * sizeof(T));
     }
     void zero() { if (p) MCB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), ctx->stream)); }
     void release()
     {
-        if (p) cudaFreeAsync(p, ctx->stream);
+        if (p) ctx->dev_free(p, n * sizeof(T));
         p = nullptr; n = 0;
     }
     ~DevBuf() { release(); }

@@ -1,0 +1,63 @@
+# mcb200.R -- R side of the drop-in: same names and signatures as the reference functions they replace.
+# NOT RUN IN THIS REPOSITORY (no R in the image, SURVEY.md 0.4).  Everything outside the arithmetic --
+# scdb look-ups, get_param, messages, seed save/restore, object construction -- is unchanged reference
+# behaviour; only the marked calls move behind .Call.
+
+# replaces scm_downsamp (R/utils.r:30-69)
+scm_downsamp = function(umis, n)
+{
+	old_seed = .set_seed(get_param("mc_rseed"))
+	r = .Call("mcbr_downsample", umis@p, umis@i, umis@x, nrow(umis), as.numeric(n),
+	          as.numeric(get_param("mc_rseed")), FALSE, PACKAGE = "mcb200")
+	ds = umis
+	ds@x = r$x
+	ds = Matrix::drop0(ds[, r$kept])          # cells with < n UMIs are dropped (R/utils.r:34)
+	.restore_seed(old_seed)
+	return(ds)
+}
+
+# replaces tgs_cor_graph (R/utils.r:115-123); k_alpha stays accepted and ignored as in the reference
+tgs_cor_graph = function(x, knn, k_expand, k_alpha, k_beta)
+{
+	r = .Call("mcbr_cor_graph_dense", x, as.integer(knn), as.integer(k_expand), as.integer(k_beta), PACKAGE = "mcb200")
+	nms = colnames(x)
+	data.frame(col1 = factor(nms[r$mc1], levels = nms), col2 = factor(nms[r$mc2], levels = nms), weight = r$w)
+}
+
+# replaces mcell_add_cgraph_from_mat_bknn (R/cgraph_knn.r:10-25): the sparse matrix and the feature rows go
+# straight to the GPU, so the dense genes x cells double matrix (8 GB at 1M cells) is never built on the host
+mcell_add_cgraph_from_mat_bknn = function(mat_id, gset_id, graph_id, K, dsamp = F)
+{
+	gset = scdb_gset(gset_id)
+	if(is.null(gset)) stop("MC-ERR: non existing gset ", gset_id, " when trying to get feature matrix")
+	mat = scdb_mat(mat_id)
+	if(is.null(mat)) stop("MC-ERR: non existing mat ", mat_id, " when trying to get feature matrix")
+	umis = mat@mat
+	feat_rows = match(intersect(names(gset@gene_set), rownames(umis)), rownames(umis))     # R/gset.r:192-197
+	message("will build balanced knn graph on ", ncol(umis), " cells and ", length(feat_rows),
+	        " genes, this can be a bit heavy for >20,000 cells")
+	r = .Call("mcbr_cgraph_bknn", umis@p, umis@i, umis@x, nrow(umis), as.integer(feat_rows), as.integer(K),
+	          as.integer(get_param("scm_balance_graph_k_expand")), as.integer(get_param("scm_balance_graph_k_beta")),
+	          as.numeric(get_param("scm_k_nonz_exp")), as.logical(dsamp), as.numeric(get_param("mc_rseed")),
+	          PACKAGE = "mcb200")
+	cnames = colnames(umis)
+	gr = data.frame(mc1 = factor(cnames[r$mc1], levels = cnames), mc2 = factor(cnames[r$mc2], levels = cnames), w = r$w)
+	scdb_add_cgraph(graph_id, tgCellGraph(gr, cnames))
+}
+
+# replaces the tgs_graph_cover_resample call inside mcell_coclust_from_graph_resamp (R/coclust_graph_cov.r:41);
+# the wrapper around it (:13-58) is unchanged.  Seeds and index sets are drawn here, on the host.
+tgs_graph_cover_resample = function(edges, knn, min_mc_size, cooling, burn_in, p_resamp, n_resamp, method = "full")
+{
+	if(method != "full") stop("MC-ERR: only method = \"full\" is supported")
+	nodes = levels(edges$col1)
+	N = length(nodes)
+	n_s = round(p_resamp * N)
+	samples = sapply(1:n_resamp, function(i) sort(sample.int(N, n_s)))            # n_s x n_resamp, ascending
+	seeds = floor(runif(n_resamp) * 2^52)
+	r = .Call("mcbr_coclust", N, as.integer(edges$col1), as.integer(edges$col2), as.numeric(edges$weight),
+	          samples, seeds, as.integer(min_mc_size), as.numeric(cooling), as.integer(burn_in), PACKAGE = "mcb200")
+	list(co_cluster = data.frame(node1 = factor(nodes[r$node1], levels = nodes),
+	                             node2 = factor(nodes[r$node2], levels = nodes), cnt = r$cnt),
+	     samples = r$samples)
+}

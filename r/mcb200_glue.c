@@ -1,0 +1,162 @@
+/*
+ * mcb200_glue.c -- the `.Call` shim a metacell maintainer adds to bind libmcb200.so (include/mcb200.h).
+ *
+ * NOT COMPILED IN THIS REPOSITORY'S IMAGE: it needs R's headers (Rinternals.h), which are absent here
+ * and on the GPU box.  It is deliberately mechanical: every function unpacks SEXPs into
+ * the plain pointers of the C ABI, calls one or a few mcb_* entry points, and repacks the result.  All
+ * arithmetic stays behind the ABI.  Build inside the R package with
+ *     PKG_LIBS = -L<dir> -lmcb200      (src/Makevars)
+ *
+ * Error convention of the reference: stop("MC-ERR: ...") (R/coclust_graph_cov.r:24, R/gset.r:157) ->
+ * Rf_error("%s", mcb_last_error()); library messages already start with "MC-ERR:" where they restate a
+ * reference check.  Indices cross the boundary 0-based and become 1-based here.
+ */
+#include <R.h>
+#include <Rinternals.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include "mcb200.h"
+
+static mcb_ctx* g_ctx = NULL;
+
+static mcb_ctx* ctx(void)
+{
+    if (!g_ctx && mcb_ctx_create(0, &g_ctx) != 0) Rf_error("%s", mcb_last_error());
+    return g_ctx;
+}
+#define CHECK(call) do { if ((call) != 0) Rf_error("%s", mcb_last_error()); } while (0)
+
+/* dgCMatrix@p is int32 in R; the ABI takes int64 column pointers */
+static int64_t* widen_p(SEXP p, R_xlen_t* ncells)
+{
+    R_xlen_t n = XLENGTH(p);
+    int64_t* out = (int64_t*)R_alloc((size_t)n, sizeof(int64_t));
+    for (R_xlen_t k = 0; k < n; ++k) out[k] = INTEGER(p)[k];
+    *ncells = n - 1;
+    return out;
+}
+
+/* scm_downsamp(umis, n) (reference R/utils.r:30-69): returns list(x = numeric(nnz), kept = logical(ncells)) */
+SEXP mcbr_downsample(SEXP p, SEXP i, SEXP x, SEXP ngenes, SEXP n, SEXP seed, SEXP add_non_dsamp)
+{
+    R_xlen_t ncells;
+    int64_t* p64 = widen_p(p, &ncells);
+    mcb_csc *m = NULL, *d = NULL;
+    CHECK(mcb_csc_upload(ctx(), asInteger(ngenes), (int64_t)ncells, p64, INTEGER(i), REAL(x), &m));
+    if (mcb_csc_downsample(ctx(), m, asReal(n), (uint64_t)asReal(seed), asLogical(add_non_dsamp), &d) != 0) {
+        mcb_csc_free(m);
+        Rf_error("%s", mcb_last_error());
+    }
+    SEXP out_x = PROTECT(allocVector(REALSXP, XLENGTH(x)));
+    SEXP kept = PROTECT(allocVector(LGLSXP, ncells));
+    uint8_t* k8 = (uint8_t*)R_alloc((size_t)ncells, 1);
+    int rc = mcb_csc_download(ctx(), d, REAL(out_x), k8);
+    mcb_csc_free(d);
+    mcb_csc_free(m);
+    if (rc != 0) Rf_error("%s", mcb_last_error());
+    for (R_xlen_t c = 0; c < ncells; ++c) LOGICAL(kept)[c] = k8[c];
+    SEXP res = PROTECT(mkNamed(VECSXP, (const char*[]){"x", "kept", ""}));
+    SET_VECTOR_ELT(res, 0, out_x);
+    SET_VECTOR_ELT(res, 1, kept);
+    UNPROTECT(3);
+    return res;
+}
+
+/* colSums + scm_which_downsamp_n (reference R/scmat.r:399-407) */
+SEXP mcbr_downsamp_depth(SEXP col_sums)
+{
+    R_xlen_t n = XLENGTH(col_sums);
+    int64_t* cs = (int64_t*)R_alloc((size_t)n, sizeof(int64_t));
+    for (R_xlen_t k = 0; k < n; ++k) cs[k] = (int64_t)REAL(col_sums)[k];
+    double depth = 0;
+    CHECK(mcb_downsamp_depth(cs, (int64_t)n, &depth));
+    return ScalarReal(depth);
+}
+
+static SEXP edges_to_list(int64_t ne, const int32_t* src, const int32_t* dst, const double* w, int64_t nvalid)
+{
+    SEXP mc1 = PROTECT(allocVector(INTSXP, ne)), mc2 = PROTECT(allocVector(INTSXP, ne)), ww = PROTECT(allocVector(REALSXP, ne));
+    for (int64_t e = 0; e < ne; ++e) { INTEGER(mc1)[e] = src[e] + 1; INTEGER(mc2)[e] = dst[e] + 1; REAL(ww)[e] = w[e]; }
+    SEXP res = PROTECT(mkNamed(VECSXP, (const char*[]){"mc1", "mc2", "w", "n_valid", ""}));
+    SET_VECTOR_ELT(res, 0, mc1); SET_VECTOR_ELT(res, 1, mc2); SET_VECTOR_ELT(res, 2, ww);
+    SET_VECTOR_ELT(res, 3, ScalarReal((double)nvalid));
+    UNPROTECT(4);
+    return res;
+}
+
+/* body of mcell_add_cgraph_from_mat_bknn (reference R/cgraph_knn.r:10-25): sparse matrix + feature rows in,
+ * (mc1, mc2, w) integer codes into colnames(mat) out */
+SEXP mcbr_cgraph_bknn(SEXP p, SEXP i, SEXP x, SEXP ngenes, SEXP feat_rows, SEXP K, SEXP k_expand, SEXP k_beta,
+                      SEXP k_nonz, SEXP dsamp, SEXP seed)
+{
+    R_xlen_t ncells;
+    int64_t* p64 = widen_p(p, &ncells);
+    R_xlen_t G = XLENGTH(feat_rows);
+    int32_t* fr = (int32_t*)R_alloc((size_t)G, sizeof(int32_t));
+    for (R_xlen_t g = 0; g < G; ++g) fr[g] = INTEGER(feat_rows)[g] - 1;
+    int64_t ne = 0, nvalid = 0;
+    int32_t *src = NULL, *dst = NULL;
+    double* w = NULL;
+    CHECK(mcb_cgraph_bknn(ctx(), asInteger(ngenes), (int64_t)ncells, p64, INTEGER(i), REAL(x), fr, (int32_t)G, asInteger(K),
+                          asInteger(k_expand), asInteger(k_beta), asReal(k_nonz), asLogical(dsamp), (uint64_t)asReal(seed),
+                          &ne, &src, &dst, &w, &nvalid));
+    SEXP res = edges_to_list(ne, src, dst, w, nvalid);
+    mcb_free(src); mcb_free(dst); mcb_free(w);
+    return res;
+}
+
+/* tgs_cor_graph(x, knn, k_expand, k_alpha, k_beta) (reference R/utils.r:115-123) on a dense genes x cells matrix */
+SEXP mcbr_cor_graph_dense(SEXP x, SEXP K, SEXP k_expand, SEXP k_beta)
+{
+    SEXP dim = getAttrib(x, R_DimSymbol);
+    const int32_t G = INTEGER(dim)[0];
+    const int64_t ncells = INTEGER(dim)[1];
+    mcb_cgraph* g = NULL;
+    CHECK(mcb_cgraph_create_dense(ctx(), REAL(x), G, ncells, &g));
+    int64_t ne = 0, nvalid = 0;
+    int rc = mcb_cgraph_knn(g, asInteger(K), asInteger(k_expand), 0, 1);
+    if (!rc) rc = mcb_cgraph_mutual(g, asInteger(k_beta));
+    if (!rc) rc = mcb_cgraph_prune(g, &ne);
+    if (rc) { mcb_cgraph_destroy(g); Rf_error("%s", mcb_last_error()); }
+    int32_t* src = (int32_t*)R_alloc((size_t)(ne ? ne : 1), sizeof(int32_t));
+    int32_t* dst = (int32_t*)R_alloc((size_t)(ne ? ne : 1), sizeof(int32_t));
+    double* w = (double*)R_alloc((size_t)(ne ? ne : 1), sizeof(double));
+    rc = mcb_cgraph_edges(g, src, dst, w);
+    mcb_cgraph_num_valid(g, &nvalid);
+    mcb_cgraph_destroy(g);
+    if (rc) Rf_error("%s", mcb_last_error());
+    return edges_to_list(ne, src, dst, w, nvalid);
+}
+
+/* tgs_graph_cover_resample(..., method = "full") (reference R/coclust_graph_cov.r:41).
+ * samples: integer matrix n_s x n_resamp (one resample per COLUMN, 1-based, ascending); seeds: numeric */
+SEXP mcbr_coclust(SEXP n_nodes, SEXP col1, SEXP col2, SEXP weight, SEXP samples, SEXP seeds, SEXP min_mc_size,
+                  SEXP cooling, SEXP burn_in)
+{
+    const int32_t N = asInteger(n_nodes);
+    const int64_t ne = XLENGTH(col1);
+    SEXP sdim = getAttrib(samples, R_DimSymbol);
+    const int32_t n_s = INTEGER(sdim)[0], n_resamp = INTEGER(sdim)[1];
+    int32_t* src = (int32_t*)R_alloc((size_t)(ne ? ne : 1), sizeof(int32_t));
+    int32_t* dst = (int32_t*)R_alloc((size_t)(ne ? ne : 1), sizeof(int32_t));
+    for (int64_t e = 0; e < ne; ++e) { src[e] = INTEGER(col1)[e] - 1; dst[e] = INTEGER(col2)[e] - 1; }
+    int32_t* smp = (int32_t*)R_alloc((size_t)n_s * n_resamp, sizeof(int32_t));
+    for (int64_t q = 0; q < (int64_t)n_s * n_resamp; ++q) smp[q] = INTEGER(samples)[q] - 1;     /* column-major == [n_resamp][n_s] */
+    uint64_t* sd = (uint64_t*)R_alloc((size_t)n_resamp, sizeof(uint64_t));
+    for (int32_t r = 0; r < n_resamp; ++r) sd[r] = (uint64_t)REAL(seeds)[r];
+    mcb_coclust* c = NULL;
+    CHECK(mcb_coclust_run(ctx(), N, ne, src, dst, REAL(weight), n_resamp, n_s, smp, sd, asInteger(min_mc_size), asReal(cooling),
+                          asInteger(burn_in), 1000, 0, 1, &c));
+    int64_t np = 0;
+    if (mcb_coclust_extract(c, &np) != 0) { mcb_coclust_destroy(c); Rf_error("%s", mcb_last_error()); }
+    SEXP n1 = PROTECT(allocVector(INTSXP, np)), n2 = PROTECT(allocVector(INTSXP, np)), cnt = PROTECT(allocVector(INTSXP, np));
+    SEXP ns = PROTECT(allocVector(INTSXP, N));
+    int rc = mcb_coclust_pairs(c, INTEGER(n1), INTEGER(n2), INTEGER(cnt), INTEGER(ns));
+    mcb_coclust_destroy(c);
+    if (rc) { UNPROTECT(4); Rf_error("%s", mcb_last_error()); }
+    for (int64_t q = 0; q < np; ++q) { INTEGER(n1)[q] += 1; INTEGER(n2)[q] += 1; }
+    SEXP res = PROTECT(mkNamed(VECSXP, (const char*[]){"node1", "node2", "cnt", "samples", ""}));
+    SET_VECTOR_ELT(res, 0, n1); SET_VECTOR_ELT(res, 1, n2); SET_VECTOR_ELT(res, 2, cnt); SET_VECTOR_ELT(res, 3, ns);
+    UNPROTECT(5);
+    return res;
+}
