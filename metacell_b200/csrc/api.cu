@@ -494,7 +494,7 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     MCB_CHECK(g, "null argument");
     MCB_CHECK(K >= 1 && k_expand >= 1, "MC-ERR: K and k_expand must be >= 1");
     MCB_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
-    MCB_CHECK((int64_t)K * k_expand <= 8192, "MC-ERR: K * k_expand above 8192 is not supported");
+    MCB_CHECK((int64_t)K * k_expand <= 4096, "MC-ERR: K * k_expand above 4096 is not supported");
     MCB_CHECK(g->M >= 2, "MC-ERR: fewer than 2 cells with non-constant features");
     mcb_ctx* ctx = g->ctx;
     MCB_CUDA(cudaSetDevice(ctx->device));
@@ -517,7 +517,7 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     const int64_t Spad = round_up(S, 256);
     int32_t r_sel = 0, cap = 0;
     sample_rule(M, S, kc_out, r_sel, cap);
-    MCB_CHECK(cap <= 16384, "MC-ERR: K * k_expand is too large relative to the number of cells for this build");
+    MCB_CHECK(cap <= 4096, "MC-ERR: K * k_expand is too large relative to the number of cells for this build");
     g->cap = cap; g->n_sample = (int32_t)S;
     std::vector<int32_t> samp((size_t)Spad, -1);
     {

@@ -60,19 +60,23 @@ __device__ __forceinline__ uint32_t hash_lookup(const uint32_t* __restrict__ tab
 }
 
 // mutual scores s(i, r) and the in-degree threshold of every owned row
+template <int IPT>      // 256 * IPT >= Kc keys sorted per row, register resident
 __global__ void __launch_bounds__(BAL_THREADS)
 mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ table, int64_t row0, int64_t rows,
               int32_t Kc, int32_t H, int32_t log2H, int32_t rank_bits, long long smax, int strict, int keep_self,
               int32_t kin, uint32_t* __restrict__ sym, uint64_t* __restrict__ thr_in)
 {
-    extern __shared__ uint64_t sk[];        // [pow2(Kc)]
-    int np2 = 2; while (np2 < Kc) np2 <<= 1;
+    extern __shared__ uint64_t sk[];        // [256 * IPT]
+    constexpr int NP = 256 * IPT;
     for (int64_t lrow = blockIdx.x; lrow < rows; lrow += gridDim.x) {
         const int64_t i = row0 + lrow;
         const int32_t* kc = knn_col + i * (int64_t)Kc;
         uint32_t* so = sym + lrow * (int64_t)Kc;
-        for (int r = threadIdx.x; r < np2; r += BAL_THREADS) {
-            uint64_t key = ~0ull;
+        uint64_t key[IPT];
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int r = q * BAL_THREADS + threadIdx.x;          // coalesced over the rank list (any order sorts)
+            uint64_t kv = ~0ull;
             if (r < Kc) {
                 const int32_t j = kc[r];
                 uint32_t sv = 0;
@@ -81,30 +85,37 @@ mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ 
                                                            : hash_lookup(table + (int64_t)j * H, H, log2H, rank_bits, (uint32_t)i);
                     if (rji) {
                         const long long s = (long long)(r + 1) * (long long)rji;
-                        if (strict ? (s < smax) : (s <= smax)) { sv = (uint32_t)s; key = ((uint64_t)s << 32) | (uint32_t)j; }
+                        if (strict ? (s < smax) : (s <= smax)) { sv = (uint32_t)s; kv = ((uint64_t)s << 32) | (uint32_t)j; }
                     }
                 }
                 so[r] = sv;
             }
-            sk[r] = key;
+            key[q] = kv;
+        }
+        bitonic_sort_regs_u64<IPT>(key, sk);
+        // thr_in = the kin-th smallest key if more than kin mutual edges exist: needs elements kin-1 and kin
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int e = threadIdx.x * IPT + q;
+            if (e == kin - 1 || e == kin) sk[e - (kin - 1)] = key[q];
         }
         __syncthreads();
-        bitonic_sort_u64<BAL_THREADS>(sk, np2);
         if (threadIdx.x == 0)
-            thr_in[i] = (kin >= 1 && kin < np2 && sk[kin] != ~0ull) ? sk[kin - 1] : ~0ull;
+            thr_in[i] = (kin >= 1 && kin < NP && sk[1] != ~0ull) ? sk[0] : ~0ull;
         __syncthreads();
     }
 }
 
 // out-degree prune: survivors of the target's in-degree cut, best K by (s, target)
+template <int IPT>
 __global__ void __launch_bounds__(BAL_THREADS)
 prune_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ sym, const uint64_t* __restrict__ thr_in,
              int64_t row0, int64_t rows, int32_t Kc, int32_t K, int32_t* __restrict__ out_deg,
              int32_t* __restrict__ out_dst, int32_t* __restrict__ out_s)
 {
-    extern __shared__ uint64_t sk[];
+    extern __shared__ uint64_t sk[];        // [256 * IPT]
     __shared__ int s_n;
-    int np2 = 2; while (np2 < Kc) np2 <<= 1;
     for (int64_t lrow = blockIdx.x; lrow < rows; lrow += gridDim.x) {
         const int64_t i = row0 + lrow;
         const int32_t* kc = knn_col + i * (int64_t)Kc;
@@ -112,21 +123,30 @@ prune_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ s
         if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
         int local = 0;
-        for (int r = threadIdx.x; r < np2; r += BAL_THREADS) {
-            uint64_t key = ~0ull;
+        uint64_t key[IPT];
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int r = q * BAL_THREADS + threadIdx.x;
+            uint64_t kv = ~0ull;
             if (r < Kc) {
                 const uint32_t s = so[r];
                 if (s) {
                     const int32_t j = kc[r];
                     const uint64_t inkey = ((uint64_t)s << 32) | (uint32_t)i;   // edge i -> j seen from target j
-                    if (inkey <= thr_in[j]) { key = ((uint64_t)s << 32) | (uint32_t)j; ++local; }
+                    if (inkey <= thr_in[j]) { kv = ((uint64_t)s << 32) | (uint32_t)j; ++local; }
                 }
             }
-            sk[r] = key;
+            key[q] = kv;
         }
         if (local) atomicAdd(&s_n, local);
+        bitonic_sort_regs_u64<IPT>(key, sk);
         __syncthreads();
-        bitonic_sort_u64<BAL_THREADS>(sk, np2);
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) {
+            const int e = threadIdx.x * IPT + q;
+            if (e < K) sk[e] = key[q];
+        }
+        __syncthreads();
         const int n = s_n < K ? s_n : K;
         if (threadIdx.x == 0) out_deg[lrow] = n;
         for (int q = threadIdx.x; q < K; q += BAL_THREADS) {
@@ -186,32 +206,58 @@ void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t 
     MCB_LAUNCH_CHECK();
 }
 
+template <int IPT>
+static void launch_mutual_t(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* table, int64_t row0, int64_t rows,
+                            int32_t Kc, int32_t H, int32_t rank_bits, int64_t smax, int strict, int keep_self, int32_t kin,
+                            uint32_t* sym, uint64_t* thr_in)
+{
+    static size_t configured = 0;
+    const size_t smem = (size_t)IPT * 256 * sizeof(uint64_t);
+    ensure_smem(mutual_kernel<IPT>, smem, configured);
+    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
+    mutual_kernel<IPT><<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, table, row0, rows, Kc, H, ilog2(H), rank_bits,
+                                                                  (long long)smax, strict, keep_self, kin, sym, thr_in);
+    MCB_LAUNCH_CHECK();
+}
+template <int IPT>
+static void launch_prune_t(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* sym, const uint64_t* thr_in, int64_t row0,
+                           int64_t rows, int32_t Kc, int32_t K, int32_t* out_deg, int32_t* out_dst, int32_t* out_s)
+{
+    static size_t configured = 0;
+    const size_t smem = (size_t)IPT * 256 * sizeof(uint64_t);
+    ensure_smem(prune_kernel<IPT>, smem, configured);
+    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
+    prune_kernel<IPT><<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, sym, thr_in, row0, rows, Kc, K, out_deg, out_dst, out_s);
+    MCB_LAUNCH_CHECK();
+}
+
+#define MCB_DISPATCH_IPT(Kc, CALL)                                   \
+    do {                                                              \
+        if ((Kc) <= 512) { CALL(2); }                                 \
+        else if ((Kc) <= 1024) { CALL(4); }                           \
+        else if ((Kc) <= 2048) { CALL(8); }                           \
+        else { CALL(16); }                                            \
+    } while (0)
+
 void launch_mutual(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* table, int64_t row0, int64_t rows,
                    int32_t Kc, int32_t H, int32_t rank_bits, int64_t smax, int strict, int keep_self, int32_t kin,
                    uint32_t* sym, uint64_t* thr_in)
 {
     if (rows == 0) return;
-    int np2 = 2; while (np2 < Kc) np2 <<= 1;
-    static size_t configured = 0;
-    const size_t smem = (size_t)np2 * sizeof(uint64_t);
-    ensure_smem(mutual_kernel, smem, configured);
-    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
-    mutual_kernel<<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, table, row0, rows, Kc, H, ilog2(H), rank_bits,
-                                                             (long long)smax, strict, keep_self, kin, sym, thr_in);
-    MCB_LAUNCH_CHECK();
+    MCB_CHECK(Kc <= 4096, "MC-ERR: K * k_expand above 4096 is not supported");
+#define CALL(I) launch_mutual_t<I>(ctx, knn_col, table, row0, rows, Kc, H, rank_bits, smax, strict, keep_self, kin, sym, thr_in)
+    MCB_DISPATCH_IPT(Kc, CALL);
+#undef CALL
 }
 
 void launch_prune(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* sym, const uint64_t* thr_in, int64_t row0,
                   int64_t rows, int32_t Kc, int32_t K, int32_t* out_deg, int32_t* out_dst, int32_t* out_s)
 {
     if (rows == 0) return;
-    int np2 = 2; while (np2 < Kc) np2 <<= 1;
-    static size_t configured = 0;
-    const size_t smem = (size_t)np2 * sizeof(uint64_t);
-    ensure_smem(prune_kernel, smem, configured);
-    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
-    prune_kernel<<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, sym, thr_in, row0, rows, Kc, K, out_deg, out_dst, out_s);
-    MCB_LAUNCH_CHECK();
+    MCB_CHECK(Kc <= 4096, "MC-ERR: K * k_expand above 4096 is not supported");
+#define CALL(I) launch_prune_t<I>(ctx, knn_col, sym, thr_in, row0, rows, Kc, K, out_deg, out_dst, out_s)
+    MCB_DISPATCH_IPT(Kc, CALL);
+#undef CALL
 }
 
 void launch_widen_i32(mcb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n)

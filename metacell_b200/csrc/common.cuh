@@ -128,6 +128,97 @@ __device__ __forceinline__ void bitonic_sort_u64(uint64_t* s, int n)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// register-resident bitonic sort of N = 256 * IPT u64 keys by a 256-thread block, ascending.
+// Element e = tid * IPT + r lives in key[r] of thread tid.  Compare-exchange partners closer than IPT
+// are in the same thread, closer than 32 * IPT in the same warp (shuffles); only the log2(N / (32 IPT))
+// widest strides go through shared memory (N u64 of scratch, conflict-free [r][tid] layout).  The
+// all-shared-memory version above is bound by shared-memory bandwidth (4 accesses per exchange).
+// ---------------------------------------------------------------------------------------------
+template <int IPT>
+__device__ __forceinline__ void bitonic_sort_regs_u64(uint64_t (&key)[IPT], uint64_t* scratch)
+{
+    constexpr int N = IPT * 256;
+    const int tid = threadIdx.x, lane = tid & 31;
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j < IPT) {
+#pragma unroll
+                for (int r = 0; r < IPT; ++r) {
+                    if ((r & j) == 0) {
+                        const bool up = (((tid * IPT + r) & k) == 0);
+                        const uint64_t a = key[r], b = key[r | j];
+                        if ((a > b) == up) { key[r] = b; key[r | j] = a; }
+                    }
+                }
+            } else if (j < IPT * 32) {
+                const int lj = j / IPT;
+                const bool lower = (lane & lj) == 0;
+#pragma unroll
+                for (int r = 0; r < IPT; ++r) {
+                    const bool up = (((tid * IPT + r) & k) == 0);
+                    const uint64_t other = __shfl_xor_sync(0xffffffffu, (unsigned long long)key[r], lj);
+                    const bool keep_min = (lower == up);
+                    key[r] = keep_min ? (key[r] < other ? key[r] : other) : (key[r] > other ? key[r] : other);
+                }
+            } else {
+                const int tj = j / IPT;                      // partner thread distance
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < IPT; ++r) scratch[r * 256 + tid] = key[r];
+                __syncthreads();
+                const bool lower = (tid & tj) == 0;
+#pragma unroll
+                for (int r = 0; r < IPT; ++r) {
+                    const bool up = (((tid * IPT + r) & k) == 0);
+                    const uint64_t other = scratch[r * 256 + (tid ^ tj)];
+                    const bool keep_min = (lower == up);
+                    key[r] = keep_min ? (key[r] < other ? key[r] : other) : (key[r] > other ? key[r] : other);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// one warp: smallest bucket d of counts[0 .. 32 * PER) whose inclusive cumulative count exceeds k;
+// `before` = cumulative count of the buckets below d.  Result valid in every lane.  Replaces the
+// 256-step single-thread scans of the radix-select kernels (each step a dependent smem load).
+// ---------------------------------------------------------------------------------------------
+template <int PER>
+__device__ __forceinline__ void warp_find_bucket(const uint32_t* counts, long long k, int& d, long long& before)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t c[PER];
+    long long s = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) { c[q] = counts[lane * PER + q]; s += c[q]; }
+    long long incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const long long excl = incl - s;
+    const unsigned owner_mask = __ballot_sync(0xffffffffu, excl <= k && k < incl);
+    const int owner = owner_mask ? __ffs(owner_mask) - 1 : 31;
+    int dd = lane * PER + PER - 1;
+    long long bb = excl;
+    if (lane == owner) {
+        long long run = excl;
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            if (run + c[q] > k) { dd = lane * PER + q; bb = run; break; }
+            run += c[q];
+            bb = run;
+        }
+    }
+    d = __shfl_sync(0xffffffffu, dd, owner);
+    before = __shfl_sync(0xffffffffu, bb, owner);
+}
+
 __device__ __forceinline__ int next_pow2(int n)
 {
     int p = 1;

@@ -120,17 +120,20 @@ downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t*
                 }
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                long long k = s_krem, cum = 0;
-                int dg = 0;
-                for (; dg < 256; ++dg) { if (cum + (long long)hist[dg] > k) break; cum += hist[dg]; }
-                const unsigned long long np = prefix | ((unsigned long long)dg << shift);
-                s_prefix = np;
-                s_krem = k - cum;
-                if (k - cum == (long long)hist[dg] - 1 || pass == 7) {
-                    // the bucket's largest element is the threshold: everything in it is kept
-                    s_thr = np | (shift ? ((1ull << shift) - 1ull) : 0ull);
-                    s_done = 1;
+            if (threadIdx.x < 32) {
+                int dg; long long cum;
+                const long long k = s_krem;
+                warp_find_bucket<8>(hist, k, dg, cum);
+                __syncwarp();
+                if (threadIdx.x == 0) {
+                    const unsigned long long np = prefix | ((unsigned long long)dg << shift);
+                    s_prefix = np;
+                    s_krem = k - cum;
+                    if (k - cum == (long long)hist[dg] - 1 || pass == 7) {
+                        // the bucket's largest element is the threshold: everything in it is kept
+                        s_thr = np | (shift ? ((1ull << shift) - 1ull) : 0ull);
+                        s_done = 1;
+                    }
                 }
             }
             __syncthreads();

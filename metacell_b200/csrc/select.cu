@@ -16,41 +16,107 @@ constexpr int SEL_THREADS = 256;
 
 // ---------------------------------------------------------------------------------------------
 // thr[row] = (r-th largest of C[row][0..S)) - eps ; -2 if r > S
+// Two levels: a 4096-bin linear histogram of the correlations over [-1, 1] (well spread, so the
+// shared-memory atomics do not pile onto a few exponent bins) locates the bin holding the answer;
+// only that bin's few values go through the exact 4 x 8-bit radix select.
 // ---------------------------------------------------------------------------------------------
+constexpr int THR_BINS = 4096;
+
+__device__ __forceinline__ int lin_bin(float c)
+{
+    int b = (int)((c + 1.0f) * (THR_BINS / 2));
+    return b < 0 ? 0 : (b >= THR_BINS ? THR_BINS - 1 : b);
+}
+
+// exact k-th smallest (0-based) of keys[0..n) held in shared memory; all SEL_THREADS threads call it
+__device__ uint32_t radix_kth_smallest(const uint32_t* keys, int n, int k, uint32_t* hist /*[256]*/, uint32_t* s_prefix, int* s_k)
+{
+    if (threadIdx.x == 0) { *s_prefix = 0u; *s_k = k; }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        const uint32_t decided = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        const uint32_t prefix = *s_prefix;
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (int j = threadIdx.x; j < n; j += SEL_THREADS) {
+            const uint32_t key = keys[j];
+            if ((key & decided) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int dg; long long before;
+            warp_find_bucket<8>(hist, (long long)*s_k, dg, before);
+            __syncwarp();
+            if (threadIdx.x == 0) { *s_prefix = prefix | ((uint32_t)dg << shift); *s_k = *s_k - (int)before; }
+        }
+        __syncthreads();
+    }
+    return *s_prefix;
+}
+
+// exact r-th largest (1-based) of keys[0..n) in shared memory through the two-level scheme; all threads call it.
+// bins: [THR_BINS] scratch; returns the key.  n >= r >= 1.
+struct SelScratch { uint32_t hist[256]; uint32_t part[SEL_THREADS]; uint32_t chunk[32]; uint32_t prefix; int k, bin, rank, n; };
+
+__device__ uint32_t bin_select(const uint32_t* keys, int n, int r, uint32_t* bins, SelScratch& sc)
+{
+    constexpr int BPT = THR_BINS / SEL_THREADS;     // bins per thread
+    static_assert(BPT <= 32, "one lane per bin of a chunk");
+    for (int b = threadIdx.x; b < THR_BINS; b += SEL_THREADS) bins[b] = 0;
+    if (threadIdx.x == 0) sc.n = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += SEL_THREADS) atomicAdd(&bins[lin_bin(ordered_to_float(keys[j]))], 1u);
+    __syncthreads();
+    uint32_t mine = 0;
+#pragma unroll
+    for (int q = 0; q < BPT; ++q) mine += bins[threadIdx.x * BPT + q];
+    sc.part[threadIdx.x] = mine;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // the r-th largest is the (n - r)-th smallest (0-based): chunk of BPT bins, then the bin inside it
+        int t, b; long long before_t, before_b;
+        warp_find_bucket<SEL_THREADS / 32>(sc.part, (long long)(n - r), t, before_t);
+        sc.chunk[threadIdx.x] = threadIdx.x < BPT ? bins[t * BPT + threadIdx.x] : 0u;
+        __syncwarp();
+        warp_find_bucket<1>(sc.chunk, (long long)(n - r) - before_t, b, before_b);
+        if (threadIdx.x == 0) {
+            sc.bin = t * BPT + b;
+            const int below = (int)((long long)(n - r) - before_t - before_b);   // position from the bottom inside the bin
+            sc.rank = (int)bins[t * BPT + b] - below;                            // 1-based rank from the top inside it
+        }
+    }
+    __syncthreads();
+    const int bsel = sc.bin;
+    const int n_in = (int)bins[bsel];
+    __syncthreads();
+    if (n_in > THR_BINS) return radix_kth_smallest(keys, n, n - r, sc.hist, &sc.prefix, &sc.k);   // degenerate: one huge bin
+    for (int j = threadIdx.x; j < n; j += SEL_THREADS) {
+        const uint32_t k = keys[j];
+        if (lin_bin(ordered_to_float(k)) == bsel) bins[atomicAdd(&sc.n, 1)] = k;
+    }
+    __syncthreads();
+    return radix_kth_smallest(bins, n_in, n_in - sc.rank, sc.hist, &sc.prefix, &sc.k);
+}
+
 __global__ void __launch_bounds__(SEL_THREADS)
 sample_threshold_kernel(const float* __restrict__ C, int64_t ldc, int64_t rows, int32_t S, int32_t r, float eps,
                         float* __restrict__ thr)
 {
-    extern __shared__ uint32_t skeys[];     // [S] ordered keys
-    __shared__ uint32_t hist[256];
-    __shared__ uint32_t s_prefix;
-    __shared__ int s_k;
+    extern __shared__ uint32_t dyn[];
+    uint32_t* skeys = dyn;                  // [S] ordered keys
+    uint32_t* bins = dyn + S;               // [THR_BINS]
+    __shared__ SelScratch sc;
+    // (A variant that first bounded the answer with a quantile of a 512-value sub-sample and ran the exact
+    //  selection on the short list above the bound was measured slower -- 8.7 vs 4.8 ms at C2: the kernel is
+    //  bound by its chain of block-wide phases, not by the number of shared-memory atomics.)
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
         if (r > S) { if (threadIdx.x == 0) thr[row] = -2.0f; continue; }
         const float* c = C + row * ldc;
         for (int j = threadIdx.x; j < S; j += SEL_THREADS) skeys[j] = float_to_ordered(c[j]);
-        if (threadIdx.x == 0) { s_prefix = 0u; s_k = S - r; }   // k-th smallest, 0-based
         __syncthreads();
-        for (int pass = 0; pass < 4; ++pass) {
-            const int shift = 24 - 8 * pass;
-            const uint32_t decided = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-            const uint32_t prefix = s_prefix;
-            hist[threadIdx.x] = 0;
-            __syncthreads();
-            for (int j = threadIdx.x; j < S; j += SEL_THREADS) {
-                const uint32_t k = skeys[j];
-                if ((k & decided) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                int k = s_k, cum = 0, dg = 0;
-                for (; dg < 256; ++dg) { if (cum + (int)hist[dg] > k) break; cum += hist[dg]; }
-                s_prefix = prefix | ((uint32_t)dg << shift);
-                s_k = k - cum;
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) thr[row] = ordered_to_float(s_prefix) - eps;
+        const uint32_t key = bin_select(skeys, S, r, bins, sc);
+        if (threadIdx.x == 0) thr[row] = ordered_to_float(key) - eps;
         __syncthreads();
     }
 }
@@ -59,12 +125,13 @@ sample_threshold_kernel(const float* __restrict__ C, int64_t ldc, int64_t rows, 
 // candidates of one row -> ranked kNN list.  cand keys are (cor desc, col asc) ascending u64.
 // fail_flag[row] = 1 when the row's candidate count fell outside [kc_out-1, cap].
 // ---------------------------------------------------------------------------------------------
+template <int IPT>      // sorts up to 256 * IPT candidates per row
 __global__ void __launch_bounds__(SEL_THREADS)
 topk_rows_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, int32_t cap, int64_t row0,
                  int64_t rows, int32_t kc_out, int32_t Kc, int32_t* __restrict__ knn_col, float* __restrict__ knn_cor,
                  int32_t* __restrict__ fail_flag)
 {
-    extern __shared__ uint64_t sk[];        // [pow2(cap)]
+    extern __shared__ uint64_t sk[];        // [256 * IPT]
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
         const uint32_t n = cnt[row];
         int32_t* oc = knn_col + row * (int64_t)Kc;
@@ -74,11 +141,18 @@ topk_rows_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__
             continue;
         }
         if (threadIdx.x == 0) fail_flag[row] = 0;
-        const int np2 = next_pow2((int)n < 2 ? 2 : (int)n);
         const uint64_t* src = cand + row * (int64_t)cap;
-        for (int q = threadIdx.x; q < np2; q += SEL_THREADS) sk[q] = q < (int)n ? src[q] : ~0ull;
+        uint64_t key[IPT];
+#pragma unroll
+        for (int r = 0; r < IPT; ++r) {
+            const int e = threadIdx.x * IPT + r;
+            key[r] = e < (int)n ? src[e] : ~0ull;
+        }
+        bitonic_sort_regs_u64<IPT>(key, sk);
         __syncthreads();
-        bitonic_sort_u64<SEL_THREADS>(sk, np2);
+#pragma unroll
+        for (int r = 0; r < IPT; ++r) sk[threadIdx.x * IPT + r] = key[r];
+        __syncthreads();
         for (int q = threadIdx.x; q < Kc; q += SEL_THREADS) {
             if (q == 0) { oc[0] = (int32_t)(row0 + row); ov[0] = 1.0f; }
             else if (q < kc_out) { const uint64_t k = sk[q - 1]; oc[q] = (int32_t)cand_key_col(k); ov[q] = cand_key_cor(k); }
@@ -126,15 +200,18 @@ topk_big_kernel(const float* __restrict__ C, int64_t ldc, int64_t M, const int32
                 if ((key & decided) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                long long k = s_k, cum = 0;
-                int dg = 0;
-                for (; dg < 256; ++dg) { if (cum + (long long)hist[dg] > k) break; cum += hist[dg]; }
-                const unsigned long long np = prefix | ((unsigned long long)dg << shift);
-                s_prefix = np; s_k = k - cum;
-                if (k - cum == (long long)hist[dg] - 1 || pass == 7) {
-                    s_thr = np | (shift ? ((1ull << shift) - 1ull) : 0ull);
-                    s_done = 1;
+            if (threadIdx.x < 32) {
+                int dg; long long cum;
+                const long long k = s_k;
+                warp_find_bucket<8>(hist, k, dg, cum);
+                __syncwarp();
+                if (threadIdx.x == 0) {
+                    const unsigned long long np = prefix | ((unsigned long long)dg << shift);
+                    s_prefix = np; s_k = k - cum;
+                    if (k - cum == (long long)hist[dg] - 1 || pass == 7) {
+                        s_thr = np | (shift ? ((1ull << shift) - 1ull) : 0ull);
+                        s_done = 1;
+                    }
                 }
             }
             __syncthreads();
@@ -194,7 +271,7 @@ void launch_sample_threshold(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t 
                              float eps, float* thr)
 {
     if (rows == 0) return;
-    const size_t smem = (size_t)S * sizeof(uint32_t);
+    const size_t smem = ((size_t)S + THR_BINS) * sizeof(uint32_t);
     MCB_CHECK(smem <= 200 * 1024, "sample_threshold: sample too large for shared memory");
     static size_t configured = 0;
     if (smem > configured) {
@@ -206,22 +283,31 @@ void launch_sample_threshold(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t 
     MCB_LAUNCH_CHECK();
 }
 
+template <int IPT>
+static void launch_topk_rows_t(mcb_ctx* ctx, const uint64_t* cand, const uint32_t* cnt, int32_t cap, int64_t row0,
+                               int64_t rows, int32_t kc_out, int32_t Kc, int32_t* knn_col, float* knn_cor, int32_t* fail_flag)
+{
+    const size_t smem = (size_t)IPT * 256 * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured && smem > 48 * 1024) {
+        MCB_CUDA(cudaFuncSetAttribute(topk_rows_kernel<IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
+    topk_rows_kernel<IPT><<<grid, SEL_THREADS, smem, ctx->stream>>>(cand, cnt, cap, row0, rows, kc_out, Kc, knn_col,
+                                                                     knn_cor, fail_flag);
+    MCB_LAUNCH_CHECK();
+}
+
 void launch_topk_rows(mcb_ctx* ctx, const uint64_t* cand, const uint32_t* cnt, int32_t cap, int64_t row0,
                       int64_t rows, int32_t kc_out, int32_t Kc, int32_t* knn_col, float* knn_cor, int32_t* fail_flag)
 {
     if (rows == 0) return;
-    int np2 = 2; while (np2 < cap) np2 <<= 1;
-    const size_t smem = (size_t)np2 * sizeof(uint64_t);
-    MCB_CHECK(smem <= 200 * 1024, "topk_rows: candidate capacity too large for shared memory");
-    static size_t configured = 0;
-    if (smem > configured) {
-        MCB_CUDA(cudaFuncSetAttribute(topk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
-    topk_rows_kernel<<<grid, SEL_THREADS, smem, ctx->stream>>>(cand, cnt, cap, row0, rows, kc_out, Kc, knn_col,
-                                                                knn_cor, fail_flag);
-    MCB_LAUNCH_CHECK();
+    MCB_CHECK(cap <= 4096, "MC-ERR: K * k_expand is too large relative to the number of cells for this build");
+    if (cap <= 512) launch_topk_rows_t<2>(ctx, cand, cnt, cap, row0, rows, kc_out, Kc, knn_col, knn_cor, fail_flag);
+    else if (cap <= 1024) launch_topk_rows_t<4>(ctx, cand, cnt, cap, row0, rows, kc_out, Kc, knn_col, knn_cor, fail_flag);
+    else if (cap <= 2048) launch_topk_rows_t<8>(ctx, cand, cnt, cap, row0, rows, kc_out, Kc, knn_col, knn_cor, fail_flag);
+    else launch_topk_rows_t<16>(ctx, cand, cnt, cap, row0, rows, kc_out, Kc, knn_col, knn_cor, fail_flag);
 }
 
 void launch_scatter_candidates(mcb_ctx* ctx, const CandPool& pool, uint64_t* cand, uint32_t* cnt, int32_t cap)
