@@ -46,7 +46,7 @@ int   mcb_ctx_create(int device, mcb_ctx** out);
 void  mcb_ctx_destroy(mcb_ctx* ctx);
 int   mcb_ctx_sync(mcb_ctx* ctx);
 void* mcb_ctx_stream(mcb_ctx* ctx);                   /* cudaStream_t all kernels are launched on */
-/* options: "gemm_impl" 0 = tcgen05 (default) | 1 = SIMT fp32 validation kernel;
+/* options: "gemm_impl" 0 = tcgen05 CTA-pair kernel (default) | 2 = tcgen05 1-SM kernel | 1 = CUDA-core validation kernel;
  *          "profile"   1 = record per-stage CUDA-event timings (mcb_ctx_timings);
  *          "keep_self" 1 = keep self edges in the balanced graph (default 0);
  *          "thresh_strict" 1 = s < K*K*k_expand (default), 0 = s <= ...;

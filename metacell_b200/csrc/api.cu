@@ -535,12 +535,12 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     }
     DevBuf<int32_t> d_samp(ctx, (size_t)Spad);
     MCB_CUDA(cudaMemcpyAsync(d_samp.p, samp.data(), sizeof(int32_t) * (size_t)Spad, cudaMemcpyHostToDevice, ctx->stream));
-    DevBuf<__half> Zs(ctx, ctx->gemm_impl == 0 ? (size_t)Spad * Gpad : 0);
-    DevBuf<float> Zsf(ctx, ctx->gemm_impl == 0 ? 0 : (size_t)Spad * Gpad);
+    DevBuf<__half> Zs(ctx, ctx->gemm_impl != 1 ? (size_t)Spad * Gpad : 0);
+    DevBuf<float> Zsf(ctx, ctx->gemm_impl != 1 ? 0 : (size_t)Spad * Gpad);
     DevBuf<float> thr(ctx, (size_t)rows);
     {
         StageTimer t(ctx, "sample_gather");
-        if (ctx->gemm_impl == 0) launch_gather_rows(ctx, g->Zh.p, (int64_t)Gpad * sizeof(__half), d_samp.p, (int32_t)Spad, Zs.p);
+        if (ctx->gemm_impl != 1) launch_gather_rows(ctx, g->Zh.p, (int64_t)Gpad * sizeof(__half), d_samp.p, (int32_t)Spad, Zs.p);
         else launch_gather_rows(ctx, g->Zf.p, (int64_t)Gpad * sizeof(float), d_samp.p, (int32_t)Spad, Zsf.p);
     }
     {
@@ -552,7 +552,7 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
             const int64_t nr = std::min(chunk, rows - c0);
             {
                 StageTimer t(ctx, "cor_sample_gemm");
-                if (ctx->gemm_impl == 0)
+                if (ctx->gemm_impl != 1)
                     launch_tc_store(ctx, g->Zh.p + (size_t)(row0 + c0) * Gpad, g->Mpad - (row0 + c0), Zs.p, Spad, Gpad,
                                     Cs.p, Spad, nr, S);
                 else
@@ -567,7 +567,7 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     // ---- filter pass: full 3-pass contraction, candidates above the row threshold ------------
     DevBuf<uint64_t> cand(ctx, (size_t)rows * cap);
     DevBuf<uint32_t> cnt(ctx, (size_t)rows);
-    if (ctx->gemm_impl == 0) {
+    if (ctx->gemm_impl != 1) {
         // the epilogue appends records to pool chunks; expected records ~ rows * (count at the sampled threshold)
         const uint32_t crec = tc_pool_chunk_records();
         double expect = (double)rows * (r_sel > S ? (double)M : (double)r_sel * (double)M / (double)S);

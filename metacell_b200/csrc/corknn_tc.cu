@@ -20,7 +20,7 @@
 //                              when it adds into a large accumulator (measured ~1 ulp per MMA), so
 //                              keeping the 2^-11-sized cross terms out of the main sum cuts the
 //                              accumulated truncation error 3x (DESIGN.md "Precision")
-//   warps 2..9  epilogue     : tcgen05.ld 32x32b.x32 of main + cross, add, then either
+//   warps 4..11 epilogue     : tcgen05.ld 32x32b.x32 of main + cross, add, then either
 //                                STORE  : write the fp32 tile (sample block of the threshold pass), or
 //                                FILTER : keep (i, j, c) with c >= thr[i], j != i (~1.5% of elements) and
 //                                         append (row, key) records to warp-private 32 KB chunks taken
@@ -39,6 +39,7 @@
 // group (GROUP_M x 1 MB) stays L2 resident and each B tile is fetched from HBM once per group.
 #include "internal.h"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace mcb {
 
@@ -50,8 +51,10 @@ constexpr int BK = 64;             // fp16 elements per k-block = one 128-byte s
 constexpr int UMMA_K = 16;         // kind::f16
 constexpr int ELT = 2;             // bytes per operand element
 constexpr int GROUP_M = 16;
-constexpr int TC_THREADS = 320;    // 10 warps: TMA, MMA, 8 epilogue
+constexpr int TC_THREADS = 384;    // 12 warps = 3 warpgroups: {TMA, MMA, 2 idle}, 2 x 4 epilogue warps
+constexpr int EPI_WARP0 = 4;       // first epilogue warp (warpgroup aligned: warp % 4 = TMEM lane quarter)
 constexpr int EPI_WARPS = 8;
+constexpr uint32_t REGS_CTRL = 56, REGS_EPI = 224;   // setmaxnreg: 128 * 56 + 256 * 224 = 384 * 168 (the CTA's pool; inc blocks forever if it asks for more)
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t POOL_CHUNK = 2048; // records (16 B each) per pool chunk; >= 32 lanes x 64 records
 constexpr int FILTER_CM = 1;        // CTAs per cluster in the FILTER kernel (B tile multicast)
@@ -71,6 +74,7 @@ struct TcParams {
     int64_t b_rows;      // valid columns
     int32_t num_kb;      // Gpad / BK
     int32_t m_tiles, n_tiles, total_tiles;
+    int32_t dbg;         // diagnostics (MCB_TC_DEBUG): 1 = epilogue only waits, 2 = epilogue only reads TMEM
     // STORE
     float* C; int64_t ldc;
     // FILTER: per-row thresholds in, candidate records out (chunk pool)
@@ -112,6 +116,256 @@ __device__ __forceinline__ bool below_diagonal(int m_blk, int n_blk)
     return MODE == 2 && CM == 1 && (n_blk + 1) * BN <= m_blk * BM + 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// epilogue of one 128-row x 256-column tile for one epilogue warp (TMEM lanes quarter*32.., column half):
+// wait for the accumulators, read main (+ cross), then STORE the tile or FILTER it into candidate records.
+// Shared by the 1-SM and the 2-SM kernels (in the latter every CTA drains its own 128 rows).
+// ---------------------------------------------------------------------------------------------
+template <int NPASS, int MODE>
+__device__ __forceinline__ void epilogue_tile(const TcParams& prm, uint32_t tmem_base, int quarter, int half, int lane,
+                                              int m_blk, int n_blk, float* tcol, uint64_t* tfull_bar, uint32_t tphase,
+                                              uint32_t& chunk_id, uint32_t& fill, bool& have_chunk)
+{
+    const int64_t lrow = (int64_t)m_blk * BM + quarter * 32 + lane;       // local row
+    const bool row_ok = lrow < prm.a_rows;
+    const int64_t n0 = (int64_t)n_blk * BN;
+    float t = 0.f;
+    if (MODE >= 1) t = row_ok ? prm.thr[lrow] : __int_as_float(0x7f800000);
+    if (MODE == 2) {
+        __syncwarp();
+#pragma unroll
+        for (int q = lane; q < BN / 2; q += 32) {
+            const int64_t col = n0 + half * (BN / 2) + q;
+            tcol[q] = col < prm.b_rows ? prm.thr[col] : __int_as_float(0x7f800000);
+        }
+        __syncwarp();
+    }
+    mbar_wait(tfull_bar, tphase);
+    tc_fence_after();
+    if (prm.dbg == 1) return;
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+    for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
+        if (NPASS == 3) {
+            uint32_t u[32];
+            tmem_ld_32x32(taddr0 + (uint32_t)(BN + c * 32), u);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+                v[q] = __float_as_uint((__uint_as_float(v[q]) + __uint_as_float(u[q])) * C_RESCALE);
+        } else {
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) * C_RESCALE);
+        }
+        const int64_t col0 = n0 + c * 32;
+        if (prm.dbg == 2) { if (__uint_as_float(v[lane & 31]) == 123.456f) prm.overflow[0] = 2u; continue; }
+        if (MODE == 0) {
+            if (row_ok && col0 < prm.b_rows) {
+                float* dst = prm.C + lrow * prm.ldc + col0;
+                if (col0 + 32 <= prm.b_rows) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        reinterpret_cast<float4*>(dst)[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                        __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        if (col0 + q < prm.b_rows) dst[q] = __uint_as_float(v[q]);
+                }
+            }
+        } else {
+            // pass masks of this lane's 32 values: bit q of mr -> record for row lrow (column col0 + q),
+            // bit q of mcm (symmetric mode) -> record for row col0 + q (column lrow)
+            uint32_t mr = 0, mcm = 0;
+            if (MODE == 1) {
+                const int64_t self = prm.a_row0 + lrow;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int64_t col = col0 + q;
+                    const bool ok = row_ok && col < prm.b_rows && col != self;
+                    mr |= (ok && __uint_as_float(v[q]) >= t) ? (1u << q) : 0u;
+                }
+            } else {
+                const float* tc = tcol + (c - half * (BN / 64)) * 32;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int64_t col = col0 + q;
+                    const bool ok = row_ok && col > lrow && col < prm.b_rows;     // each unordered pair once
+                    const float cv = __uint_as_float(v[q]);
+                    mr |= (ok && cv >= t) ? (1u << q) : 0u;
+                    mcm |= (ok && cv >= tc[q]) ? (1u << q) : 0u;
+                }
+            }
+            const uint32_t n = (uint32_t)(__popc(mr) + __popc(mcm));
+            uint32_t incl = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (total) {                                   // warp-uniform
+                if (!have_chunk || fill + total > POOL_CHUNK) {
+                    if (have_chunk && lane == 0 && chunk_id < prm.pool_chunks) prm.chunk_fill[chunk_id] = fill;
+                    uint32_t id = 0;
+                    if (lane == 0) id = atomicAdd(prm.pool_cursor, 1u);      // one per ~2048 records
+                    chunk_id = __shfl_sync(0xffffffffu, id, 0);
+                    fill = 0; have_chunk = true;
+                    if (chunk_id >= prm.pool_chunks && lane == 0) *prm.overflow = 1u;
+                }
+                if (chunk_id < prm.pool_chunks) {
+                    uint4* dst = prm.pool + (size_t)chunk_id * POOL_CHUNK + fill + (incl - n);
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        if (mr & (1u << q)) {
+                            const uint64_t key = cand_key(__uint_as_float(v[q]), (uint32_t)(col0 + q));
+                            *dst++ = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)lrow, 0u);
+                        }
+                    if (MODE == 2) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q)
+                            if (mcm & (1u << q)) {
+                                const uint64_t key = cand_key(__uint_as_float(v[q]), (uint32_t)lrow);
+                                *dst++ = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)(col0 + q), 0u);
+                            }
+                    }
+                }
+                fill += total;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// FILTER epilogue of one 128-row x 256-column tile for one epilogue warp.  The accumulators fill TMEM, so
+// the MMA warp cannot start the next tile until this tile is drained: the warp therefore first copies its
+// whole 32 x 128 slice (main + cross summed) into registers, releases TMEM at once (`release`), and only
+// then does the threshold tests and record writes -- which now overlap the next tile's MMAs.  (Measured at
+// C2: filtering straight out of TMEM cost 10 ms of a 32 ms kernel.)  Thresholds are compared in
+// accumulator units (x 2^24, exact), so only passing values are rescaled.
+// ---------------------------------------------------------------------------------------------
+template <int MODE, class Release>
+__device__ __forceinline__ void epilogue_filter_tile(const TcParams& prm, uint32_t tmem_base, int quarter, int half, int lane,
+                                                     int m_blk, int n_blk, float* tcol, uint64_t* tfull_bar, uint32_t tphase,
+                                                     uint32_t& chunk_id, uint32_t& fill, bool& have_chunk, Release release)
+{
+    constexpr int NCH = BN / 64;                       // 32-column chunks per warp
+    constexpr float INV = 1.0f / C_RESCALE;            // 2^24
+    const float inf = __int_as_float(0x7f800000);
+    const int64_t row_base = (int64_t)m_blk * BM;
+    const int64_t lrow = row_base + quarter * 32 + lane;                  // local row
+    const bool row_ok = lrow < prm.a_rows;
+    const int64_t c_base = (int64_t)n_blk * BN + half * (BN / 2);         // first column of this warp's slice
+    const float ts = row_ok ? prm.thr[lrow] * INV : inf;
+    bool interior = c_base + BN / 2 <= prm.b_rows && row_base + BM <= prm.a_rows;   // warp-uniform
+    if (MODE == 2) {
+        __syncwarp();
+#pragma unroll
+        for (int q = lane; q < BN / 2; q += 32) {
+            const int64_t col = c_base + q;
+            tcol[q] = col < prm.b_rows ? prm.thr[col] * INV : inf;
+        }
+        __syncwarp();
+        interior = interior && c_base >= row_base + BM;                   // every column is right of every row
+    } else {
+        const int64_t self0 = prm.a_row0 + row_base;
+        interior = interior && (self0 + BM <= c_base || self0 >= c_base + BN / 2);   // no self column in the slice
+    }
+    mbar_wait(tfull_bar, tphase);
+    tc_fence_after();
+    if (prm.dbg == 1) { release(); return; }
+    uint32_t v[NCH * 32];
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * (BN / 2));
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        uint32_t u[32];
+        tmem_ld_32x32_p(taddr0 + (uint32_t)(c * 32), v + c * 32);
+        tmem_ld_32x32(taddr0 + (uint32_t)(BN + c * 32), u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[c * 32 + q] = __float_as_uint(__uint_as_float(v[c * 32 + q]) + __uint_as_float(u[q]));
+    }
+    release();                                          // TMEM is free: the next tile's MMAs may start
+    if (prm.dbg == 2) { if (__uint_as_float(v[5]) == 123.456f) prm.overflow[0] = 2u; return; }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const uint32_t* vc = v + c * 32;
+        const int64_t col0 = c_base + c * 32;
+        uint32_t mr = 0, mcm = 0;
+        if (interior) {
+            const float4* tc4 = reinterpret_cast<const float4*>(tcol + c * 32);      // 16-byte aligned, broadcast reads
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+                float4 tq = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MODE == 2) tq = tc4[q4];
+                const float c0 = __uint_as_float(vc[4 * q4]), c1 = __uint_as_float(vc[4 * q4 + 1]);
+                const float c2 = __uint_as_float(vc[4 * q4 + 2]), c3 = __uint_as_float(vc[4 * q4 + 3]);
+                mr |= (c0 >= ts ? (1u << (4 * q4)) : 0u) | (c1 >= ts ? (2u << (4 * q4)) : 0u) |
+                      (c2 >= ts ? (4u << (4 * q4)) : 0u) | (c3 >= ts ? (8u << (4 * q4)) : 0u);
+                if (MODE == 2)
+                    mcm |= (c0 >= tq.x ? (1u << (4 * q4)) : 0u) | (c1 >= tq.y ? (2u << (4 * q4)) : 0u) |
+                           (c2 >= tq.z ? (4u << (4 * q4)) : 0u) | (c3 >= tq.w ? (8u << (4 * q4)) : 0u);
+            }
+        } else if (MODE == 1) {
+            const int64_t self = prm.a_row0 + lrow;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int64_t col = col0 + q;
+                const bool ok = row_ok && col < prm.b_rows && col != self;
+                mr |= (ok && __uint_as_float(vc[q]) >= ts) ? (1u << q) : 0u;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int64_t col = col0 + q;
+                const bool ok = row_ok && col > lrow && col < prm.b_rows;     // each unordered pair once
+                const float cv = __uint_as_float(vc[q]);
+                mr |= (ok && cv >= ts) ? (1u << q) : 0u;
+                mcm |= (ok && cv >= tcol[c * 32 + q]) ? (1u << q) : 0u;
+            }
+        }
+        const uint32_t n = (uint32_t)(__popc(mr) + __popc(mcm));
+        uint32_t incl = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total) {                                   // warp-uniform
+            if (!have_chunk || fill + total > POOL_CHUNK) {
+                if (have_chunk && lane == 0 && chunk_id < prm.pool_chunks) prm.chunk_fill[chunk_id] = fill;
+                uint32_t id = 0;
+                if (lane == 0) id = atomicAdd(prm.pool_cursor, 1u);      // one per ~2048 records
+                chunk_id = __shfl_sync(0xffffffffu, id, 0);
+                fill = 0; have_chunk = true;
+                if (chunk_id >= prm.pool_chunks && lane == 0) *prm.overflow = 1u;
+            }
+            if (chunk_id < prm.pool_chunks) {
+                uint4* dst = prm.pool + (size_t)chunk_id * POOL_CHUNK + fill + (incl - n);
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                    if (mr & (1u << q)) {
+                        const uint64_t key = cand_key(__uint_as_float(vc[q]) * C_RESCALE, (uint32_t)(col0 + q));
+                        *dst++ = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)lrow, 0u);
+                    }
+                if (MODE == 2) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q)
+                        if (mcm & (1u << q)) {
+                            const uint64_t key = cand_key(__uint_as_float(vc[q]) * C_RESCALE, (uint32_t)lrow);
+                            *dst++ = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)(col0 + q), 0u);
+                        }
+                }
+            }
+            fill += total;
+        }
+    }
+}
+
 template <int NPASS, int MODE, int CM>   // MODE 0 = STORE, 1 = FILTER, 2 = symmetric FILTER; CM = CTAs per cluster sharing a B tile
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -151,6 +405,8 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    if (warp < EPI_WARP0) {
+    setmaxnreg_dec<REGS_CTRL>();
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
@@ -229,13 +485,15 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                 tphase ^= 1;
             }
         }
+    }
     } else {
-        // ===== epilogue warps 2..9 : TMEM lanes (warp % 4) * 32 .. + 31, column half (warp - 2) / 4 =====
+        setmaxnreg_inc<REGS_EPI>();
+        // ===== epilogue warps 4..11 : TMEM lanes (warp % 4) * 32 .. + 31, column half (warp - 4) / 4 =====
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - EPI_WARP0) >> 2;
         uint32_t tphase = 0;
         TileIter iter = iter0;
-        float* tcol = reinterpret_cast<float*>(tmem_slot + 4) + (warp - 2) * (BN / 2);    // per-warp column thresholds (MODE 2)
+        float* tcol = reinterpret_cast<float*>(tmem_slot + 4) + (warp - EPI_WARP0) * (BN / 2);    // per-warp column thresholds (MODE 2)
         uint32_t chunk_id = 0, fill = 0;          // this warp's open record chunk (warp-uniform)
         bool have_chunk = false;
         for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
@@ -243,119 +501,16 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             iter.coords(tile, m_blk, n_blk);
             m_blk = m_blk * CM + crank;
             if (below_diagonal<MODE, CM>(m_blk, n_blk)) continue;
-            const int64_t lrow = (int64_t)m_blk * BM + quarter * 32 + lane;       // local row
-            const bool row_ok = lrow < prm.a_rows;
-            const int64_t n0 = (int64_t)n_blk * BN;
-            float t = 0.f;
-            if (MODE >= 1) t = row_ok ? prm.thr[lrow] : __int_as_float(0x7f800000);
-            if (MODE == 2) {
-                __syncwarp();
-#pragma unroll
-                for (int q = lane; q < BN / 2; q += 32) {
-                    const int64_t col = n0 + half * (BN / 2) + q;
-                    tcol[q] = col < prm.b_rows ? prm.thr[col] : __int_as_float(0x7f800000);
-                }
-                __syncwarp();
+            auto release = [&]() { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(tempty_bar); };
+            if (MODE == 0) {
+                epilogue_tile<NPASS, MODE>(prm, tmem_base, quarter, half, lane, m_blk, n_blk, tcol, tfull_bar, tphase,
+                                           chunk_id, fill, have_chunk);
+                release();
+            } else {
+                epilogue_filter_tile<(MODE == 0 ? 1 : MODE)>(prm, tmem_base, quarter, half, lane, m_blk, n_blk, tcol, tfull_bar,
+                                                             tphase, chunk_id, fill, have_chunk, release);
             }
-            mbar_wait(tfull_bar, tphase);
             tphase ^= 1;
-            tc_fence_after();
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(quarter * 32) << 16);
-#pragma unroll 1
-            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr0 + (uint32_t)(c * 32), v);
-                if (NPASS == 3) {
-                    uint32_t u[32];
-                    tmem_ld_32x32(taddr0 + (uint32_t)(BN + c * 32), u);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int q = 0; q < 32; ++q)
-                        v[q] = __float_as_uint((__uint_as_float(v[q]) + __uint_as_float(u[q])) * C_RESCALE);
-                } else {
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(__uint_as_float(v[q]) * C_RESCALE);
-                }
-                const int64_t col0 = n0 + c * 32;
-                if (MODE == 0) {
-                    if (row_ok && col0 < prm.b_rows) {
-                        float* dst = prm.C + lrow * prm.ldc + col0;
-                        if (col0 + 32 <= prm.b_rows) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                reinterpret_cast<float4*>(dst)[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                                                                __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 32; ++q)
-                                if (col0 + q < prm.b_rows) dst[q] = __uint_as_float(v[q]);
-                        }
-                    }
-                } else {
-                    // pass masks of this lane's 32 values: bit q of mr -> record for row lrow (column col0 + q),
-                    // bit q of mcm (symmetric mode) -> record for row col0 + q (column lrow)
-                    uint32_t mr = 0, mcm = 0;
-                    if (MODE == 1) {
-                        const int64_t self = prm.a_row0 + lrow;
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            const int64_t col = col0 + q;
-                            const bool ok = row_ok && col < prm.b_rows && col != self;
-                            mr |= (ok && __uint_as_float(v[q]) >= t) ? (1u << q) : 0u;
-                        }
-                    } else {
-                        const float* tc = tcol + (c - half * (BN / 64)) * 32;
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) {
-                            const int64_t col = col0 + q;
-                            const bool ok = row_ok && col > lrow && col < prm.b_rows;     // each unordered pair once
-                            const float cv = __uint_as_float(v[q]);
-                            mr |= (ok && cv >= t) ? (1u << q) : 0u;
-                            mcm |= (ok && cv >= tc[q]) ? (1u << q) : 0u;
-                        }
-                    }
-                    const uint32_t n = (uint32_t)(__popc(mr) + __popc(mcm));
-                    uint32_t incl = n;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o) incl += up;
-                    }
-                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-                    if (total) {                                   // warp-uniform
-                        if (!have_chunk || fill + total > POOL_CHUNK) {
-                            if (have_chunk && lane == 0 && chunk_id < prm.pool_chunks) prm.chunk_fill[chunk_id] = fill;
-                            uint32_t id = 0;
-                            if (lane == 0) id = atomicAdd(prm.pool_cursor, 1u);      // one per ~2048 records
-                            chunk_id = __shfl_sync(0xffffffffu, id, 0);
-                            fill = 0; have_chunk = true;
-                            if (chunk_id >= prm.pool_chunks && lane == 0) *prm.overflow = 1u;
-                        }
-                        if (chunk_id < prm.pool_chunks) {
-                            uint4* dst = prm.pool + (size_t)chunk_id * POOL_CHUNK + fill + (incl - n);
-#pragma unroll
-                            for (int q = 0; q < 32; ++q)
-                                if (mr & (1u << q)) {
-                                    const uint64_t key = cand_key(__uint_as_float(v[q]), (uint32_t)(col0 + q));
-                                    *dst++ = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)lrow, 0u);
-                                }
-                            if (MODE == 2) {
-#pragma unroll
-                                for (int q = 0; q < 32; ++q)
-                                    if (mcm & (1u << q)) {
-                                        const uint64_t key = cand_key(__uint_as_float(v[q]), (uint32_t)lrow);
-                                        *dst++ = make_uint4((uint32_t)key, (uint32_t)(key >> 32), (uint32_t)(col0 + q), 0u);
-                                    }
-                            }
-                        }
-                        fill += total;
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar);
         }
         if (MODE >= 1 && have_chunk && lane == 0 && chunk_id < prm.pool_chunks) prm.chunk_fill[chunk_id] = fill;
     }
@@ -364,6 +519,158 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     __syncthreads();
     if (CM > 1) cluster_sync_all();        // no CTA exits while its peer may still signal its barriers
     if (warp == 1) { tc_fence_after(); tmem_dealloc<TMEM_COLS>(tmem_base); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair version of the FILTER kernels (tcgen05 cta_group::2).  The kernel above is bound by the
+// L2 -> SM operand feed, so this one halves the B bytes every SM receives: a cluster of two CTAs
+// contracts a 256-row x 256-column tile with M = 256 UMMAs issued by the leader CTA; each CTA holds
+// its own 128 A rows and only HALF of the B tile (the tensor core reads the other half from the peer's
+// shared memory), i.e. 64 KB instead of 96 KB per k-block, which also makes room for a third stage.
+// Every CTA drains its own 128 accumulator rows with the same epilogue.
+//   full[s]   (leader's)  : leader's producer arrives once expecting both CTAs' bytes; both CTAs' TMA
+//                           loads complete their bytes on it (cp.async.bulk.tensor ... cta_group::2)
+//   empty[s]  (each CTA)  : leader's tcgen05.commit.cta_group::2 multicast when the stage's MMAs retire
+//   tfull     (each CTA)  : same multicast commit after the last k-block of a tile
+//   tempty    (leader's)  : 2 x EPI_WARPS arrivals (the peer's warps arrive through the cluster window)
+// ---------------------------------------------------------------------------------------------
+struct Tc2Cfg {
+    static constexpr int A_BYTES = BM * BK * ELT;                    // 16 KB per plane (this CTA's 128 rows)
+    static constexpr int B_BYTES = (BN / 2) * BK * ELT;              // 16 KB per plane (this CTA's half of B)
+    static constexpr int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);      // 64 KB
+    static constexpr int NSTAGE = 3;
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 + 256 + EPI_WARPS * (BN / 2) * 4;
+};
+
+template <int MODE>   // 1 = FILTER, 2 = symmetric FILTER
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+tc_cor2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const TcParams prm)
+{
+    using Cfg = Tc2Cfg;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                       // [NSTAGE] used in the leader
+    uint64_t* empty_bar = bars + Cfg::NSTAGE;        // [NSTAGE]
+    uint64_t* tfull_bar = bars + 2 * Cfg::NSTAGE;
+    uint64_t* tempty_bar = bars + 2 * Cfg::NSTAGE + 1;   // used in the leader
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::NSTAGE + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = (int)cluster_ctarank();
+    const bool leader = crank == 0;
+    const int m_units = (prm.m_tiles + 1) / 2;       // 256-row units
+    const TileIter iter0(m_units, prm.n_tiles, MODE == 2 ? 1 : 0, 2 * BM);
+    const int total_tiles = prm.total_tiles;
+    const int unit0 = (int)blockIdx.x / 2, unit_stride = (int)gridDim.x / 2;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&map_hi); prefetch_tensormap(&map_lo);
+        for (int s = 0; s < Cfg::NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tfull_bar, 1); mbar_init(tempty_bar, 2 * EPI_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // a 256 x 256 pair tile entirely below the diagonal holds no pair (i, j > i)
+    auto skip = [&](int unit, int n_blk) { return MODE == 2 && (n_blk + 1) * BN <= unit * 2 * BM + 1; };
+
+    if (warp < EPI_WARP0) {
+    setmaxnreg_dec<REGS_CTRL>();
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs) =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            TileIter iter = iter0;
+            for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+                int unit, n_blk;
+                iter.coords(tile, unit, n_blk);
+                if (skip(unit, n_blk)) continue;
+                const int32_t m0 = (int32_t)(prm.a_row0 + ((int64_t)unit * 2 + crank) * BM);
+                const int32_t n0 = n_blk * BN + crank * (BN / 2);
+                for (int kb = 0; kb < prm.num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+                    if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+                    const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);       // the leader's barrier
+                    tma_load_2d_2sm(st, &map_hi, fb, kb * BK, m0);
+                    tma_load_2d_2sm(st + Cfg::A_BYTES, &map_lo, fb, kb * BK, m0);
+                    tma_load_2d_2sm(st + 2 * Cfg::A_BYTES, &map_hi, fb, kb * BK, n0);
+                    tma_load_2d_2sm(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES, &map_lo, fb, kb * BK, n0);
+                    if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (leader CTA only) =====
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc_f16(2 * BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            uint32_t tphase = 0;
+            const uint32_t d_main = tmem_base, d_cross = tmem_base + (uint32_t)BN;
+            TileIter iter = iter0;
+            for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+                int unit, n_blk;
+                iter.coords(tile, unit, n_blk);
+                if (skip(unit, n_blk)) continue;
+                mbar_wait(tempty_bar, tphase ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < prm.num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t st = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t a_hi = make_sw128_kmajor_desc(st);
+                    const uint64_t a_lo = make_sw128_kmajor_desc(st + Cfg::A_BYTES);
+                    const uint64_t b_hi = make_sw128_kmajor_desc(st + 2 * Cfg::A_BYTES);
+                    const uint64_t b_lo = make_sw128_kmajor_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * ELT) >> 4);
+                        const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+                        mma_f16_ss_2sm(d_main, a_hi + koff, b_hi + koff, idesc, accum);
+                        mma_f16_ss_2sm(d_cross, a_hi + koff, b_lo + koff, idesc, accum);
+                        mma_f16_ss_2sm(d_cross, a_lo + koff, b_hi + koff, idesc, 1u);
+                    }
+                    tc_commit_2sm_mc(&empty_bar[stage], (uint16_t)3);     // both CTAs may refill the stage
+                    if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_2sm_mc(tfull_bar, (uint16_t)3);                 // both CTAs drain their 128 rows
+                tphase ^= 1;
+            }
+        }
+    }
+    } else {
+        setmaxnreg_inc<REGS_EPI>();
+        // ===== epilogue warps 4..11 (both CTAs) =====
+        const int quarter = warp & 3;
+        const int half = (warp - EPI_WARP0) >> 2;
+        uint32_t tphase = 0;
+        TileIter iter = iter0;
+        float* tcol = reinterpret_cast<float*>(tmem_slot + 4) + (warp - EPI_WARP0) * (BN / 2);
+        uint32_t chunk_id = 0, fill = 0;
+        bool have_chunk = false;
+        const uint32_t tempty_leader = mapa_u32(smem_u32(tempty_bar), 0);
+        for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+            int unit, n_blk;
+            iter.coords(tile, unit, n_blk);
+            if (skip(unit, n_blk)) continue;
+            auto release = [&]() { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive_cluster(tempty_leader); };
+            epilogue_filter_tile<MODE>(prm, tmem_base, quarter, half, lane, unit * 2 + crank, n_blk, tcol, tfull_bar, tphase,
+                                       chunk_id, fill, have_chunk, release);
+            tphase ^= 1;
+        }
+        if (have_chunk && lane == 0 && chunk_id < prm.pool_chunks) prm.chunk_fill[chunk_id] = fill;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc_2sm<TMEM_COLS>(tmem_base); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -414,6 +721,7 @@ static void launch_tc(mcb_ctx* ctx, const CUtensorMap& ah, const CUtensorMap& al
         configured = true;
     }
     TcParams p2 = prm;
+    p2.dbg = (MODE != 0 && getenv("MCB_TC_DEBUG")) ? atoi(getenv("MCB_TC_DEBUG")) : 0;
     p2.total_tiles = TileIter((int)ceil_div(prm.m_tiles, CM), prm.n_tiles, MODE == 2 ? 1 : 0, CM * BM).total();
     const int units = p2.total_tiles;
     const int grid = std::min(units, ctx->num_sms / CM) * CM;
@@ -445,6 +753,22 @@ void launch_tc_store(mcb_ctx* ctx, const void* Ahi, int64_t a_rows_alloc, const 
     launch_tc<1, 0, 1>(ctx, ah, ah, bh, bh, prm);
 }
 
+template <int MODE>
+static void launch_tc2(mcb_ctx* ctx, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& prm)
+{
+    static bool configured = false;
+    if (!configured) {
+        MCB_CUDA(cudaFuncSetAttribute(tc_cor2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    TcParams p2 = prm;
+    p2.dbg = getenv("MCB_TC_DEBUG") ? atoi(getenv("MCB_TC_DEBUG")) : 0;
+    p2.total_tiles = TileIter((int)ceil_div(prm.m_tiles, 2), prm.n_tiles, MODE == 2 ? 1 : 0, 2 * BM).total();
+    const int pairs = std::min(p2.total_tiles, ctx->num_sms / 2);
+    tc_cor2_kernel<MODE><<<2 * pairs, TC_THREADS, Tc2Cfg::SMEM_BYTES, ctx->stream>>>(mh, ml, p2);   // __cluster_dims__(2,1,1)
+    MCB_LAUNCH_CHECK();
+}
+
 uint32_t tc_pool_chunk_records() { return POOL_CHUNK; }
 uint32_t tc_pool_min_chunks(mcb_ctx* ctx) { return (uint32_t)(EPI_WARPS * ctx->num_sms + 64); }   // one open chunk per warp
 
@@ -465,9 +789,14 @@ void launch_tc_filter(mcb_ctx* ctx, const void* Zhi, const void* Zlo, int64_t ro
     prm.thr = thr;
     prm.pool = reinterpret_cast<uint4*>(pool.records); prm.pool_cursor = pool.cursor; prm.chunk_fill = pool.chunk_fill;
     prm.pool_chunks = pool.n_chunks; prm.overflow = pool.overflow;
-    // the whole square on one rank: every unordered pair is contracted once and serves both rows
-    if (a_row0 == 0 && a_rows == b_rows) launch_tc<3, 2, FILTER_CM>(ctx, ah, al, bh, bl, prm);
-    else launch_tc<3, 1, FILTER_CM>(ctx, ah, al, bh, bl, prm);
+    const bool sym = a_row0 == 0 && a_rows == b_rows;   // whole square on one rank: each unordered pair contracted once
+    if (ctx->gemm_impl == 2) {                          // 1-SM kernel (A/B measurements)
+        if (sym) launch_tc<3, 2, FILTER_CM>(ctx, ah, al, bh, bl, prm);
+        else launch_tc<3, 1, FILTER_CM>(ctx, ah, al, bh, bl, prm);
+        return;
+    }
+    if (sym) launch_tc2<2>(ctx, ah, al, prm);
+    else launch_tc2<1>(ctx, ah, al, prm);
 }
 
 // validation entry: full 3-pass product stored to C (used by tests to check the tensor-core path
