@@ -50,7 +50,9 @@ void* mcb_ctx_stream(mcb_ctx* ctx);                   /* cudaStream_t all kernel
  *          "profile"   1 = record per-stage CUDA-event timings (mcb_ctx_timings);
  *          "keep_self" 1 = keep self edges in the balanced graph (default 0);
  *          "thresh_strict" 1 = s < K*K*k_expand (default), 0 = s <= ...;
- *          "trim"      release the context's cache of device blocks back to the driver          */
+ *          "trim"      release the context's cache of device blocks back to the driver;
+ *          "cap_override" n > 0: test hook, caps the per-row candidate capacity so rows take the
+ *                      exact-row path                                                           */
 int   mcb_ctx_set_option(mcb_ctx* ctx, const char* key, int64_t value);
 /* stage timings of the calls since the last mcb_ctx_timings_reset (needs option profile=1).
  * Writes up to cap entries; *n receives the number available.  names[i] are static strings.  */

@@ -169,6 +169,7 @@ extern "C" int mcb_ctx_set_option(mcb_ctx* ctx, const char* key, int64_t value)
     else if (!strcmp(key, "profile")) ctx->profile = (int)value;
     else if (!strcmp(key, "keep_self")) ctx->keep_self = (int)value;
     else if (!strcmp(key, "thresh_strict")) ctx->thresh_strict = (int)value;
+    else if (!strcmp(key, "cap_override")) ctx->cap_override = (int)value;
     else if (!strcmp(key, "trim")) { MCB_CUDA(cudaStreamSynchronize(ctx->stream)); ctx->trim(); }
     else throw Error(1, std::string("unknown option: ") + key);
     MCB_API_END
@@ -518,6 +519,7 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     int32_t r_sel = 0, cap = 0;
     sample_rule(M, S, kc_out, r_sel, cap);
     MCB_CHECK(cap <= 4096, "MC-ERR: K * k_expand is too large relative to the number of cells for this build");
+    if (ctx->cap_override > 0) cap = std::min(cap, ctx->cap_override);
     g->cap = cap; g->n_sample = (int32_t)S;
     std::vector<int32_t> samp((size_t)Spad, -1);
     {
@@ -610,21 +612,32 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
     g->n_fallback = n_fail;
     if (n_fail > 0) {
-        // rows whose candidate count missed [kc_out-1, cap]: exact fp32 row on the CUDA cores
+        // rows whose candidate count missed [kc_out-1, cap]: their full correlation rows through the 3-pass
+        // tensor-core kernel in STORE mode (same arithmetic as the filter kernel), then an exact global select;
+        // with "gemm_impl" = 1 the CUDA-core kernel plays that role
         StageTimer t(ctx, "knn_exact_rows");
-        const int32_t B = 64;
-        DevBuf<float> Af(ctx, (size_t)B * Gpad), Cf(ctx, (size_t)B * M);
+        const int32_t B = 128;
+        const int64_t ldcf = round_up(M, 4);            // 16-byte aligned rows for the vector stores
+        DevBuf<float> Cf(ctx, (size_t)B * ldcf);
+        DevBuf<__half> Ah(ctx, ctx->gemm_impl != 1 ? (size_t)B * Gpad : 0), Al(ctx, ctx->gemm_impl != 1 ? (size_t)B * Gpad : 0);
+        DevBuf<float> Af(ctx, ctx->gemm_impl != 1 ? 0 : (size_t)B * Gpad);
         DevBuf<int32_t> glist(ctx, (size_t)B);
         std::vector<int32_t> hl((size_t)n_fail), gl((size_t)B);
         MCB_CUDA(cudaMemcpyAsync(hl.data(), fail_list.p, sizeof(int32_t) * (size_t)n_fail, cudaMemcpyDeviceToHost, ctx->stream));
         MCB_CUDA(cudaStreamSynchronize(ctx->stream));
         for (int32_t b0 = 0; b0 < n_fail; b0 += B) {
             const int32_t nb = std::min(B, n_fail - b0);
-            for (int32_t q = 0; q < nb; ++q) gl[q] = (int32_t)(row0 + hl[b0 + q]);
-            MCB_CUDA(cudaMemcpyAsync(glist.p, gl.data(), sizeof(int32_t) * (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
-            launch_gather_rows(ctx, g->Zf.p, (int64_t)Gpad * sizeof(float), glist.p, nb, Af.p);
-            launch_simt_store(ctx, Af.p, nb, g->Zf.p, M, Gpad, Cf.p, M);
-            launch_topk_big(ctx, Cf.p, M, M, fail_list.p + b0, nb, row0, kc_out, Kc, own_col, g->knn_cor.p);
+            for (int32_t q = 0; q < B; ++q) gl[q] = q < nb ? (int32_t)(row0 + hl[b0 + q]) : -1;      // -1 -> zero row
+            MCB_CUDA(cudaMemcpyAsync(glist.p, gl.data(), sizeof(int32_t) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
+            if (ctx->gemm_impl != 1) {
+                launch_gather_rows(ctx, g->Zh.p, (int64_t)Gpad * sizeof(__half), glist.p, B, Ah.p);
+                launch_gather_rows(ctx, g->Zl.p, (int64_t)Gpad * sizeof(__half), glist.p, B, Al.p);
+                launch_tc_store3_ab(ctx, Ah.p, Al.p, B, g->Zh.p, g->Zl.p, g->Mpad, nb, M, Gpad, Cf.p, ldcf);
+            } else {
+                launch_gather_rows(ctx, g->Zf.p, (int64_t)Gpad * sizeof(float), glist.p, B, Af.p);
+                launch_simt_store(ctx, Af.p, nb, g->Zf.p, M, Gpad, Cf.p, ldcf);
+            }
+            launch_topk_big(ctx, Cf.p, ldcf, M, fail_list.p + b0, nb, row0, kc_out, Kc, own_col, g->knn_cor.p);
             MCB_CUDA(cudaStreamSynchronize(ctx->stream));      // gl is reused
         }
     }

@@ -799,6 +799,24 @@ void launch_tc_filter(mcb_ctx* ctx, const void* Zhi, const void* Zlo, int64_t ro
     else launch_tc2<1>(ctx, ah, al, prm);
 }
 
+// 3-pass product of separate A and B operands stored to C (exact rows of the kNN stage)
+void launch_tc_store3_ab(mcb_ctx* ctx, const void* Ahi, const void* Alo, int64_t a_rows_alloc, const void* Bhi, const void* Blo,
+                         int64_t b_rows_alloc, int64_t a_rows, int64_t b_rows, int32_t Gpad, float* C, int64_t ldc)
+{
+    if (a_rows == 0 || b_rows == 0) return;
+    tc_init();
+    MCB_CHECK(ldc % 4 == 0, "tc store: ldc must be a multiple of 4");
+    const CUtensorMap ah = make_map(Ahi, a_rows_alloc, Gpad, BM);
+    const CUtensorMap al = make_map(Alo, a_rows_alloc, Gpad, BM);
+    const CUtensorMap bh = make_map(Bhi, b_rows_alloc, Gpad, BN);
+    const CUtensorMap bl = make_map(Blo, b_rows_alloc, Gpad, BN);
+    TcParams prm{};
+    prm.a_row0 = 0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK;
+    prm.m_tiles = (int32_t)ceil_div(a_rows, BM); prm.n_tiles = (int32_t)ceil_div(b_rows, BN);
+    prm.C = C; prm.ldc = ldc;
+    launch_tc<3, 0, 1>(ctx, ah, al, bh, bl, prm);
+}
+
 // validation entry: full 3-pass product stored to C (used by tests to check the tensor-core path
 // element by element against the SIMT kernel and fp64)
 void launch_tc_store3(mcb_ctx* ctx, const void* Zhi, const void* Zlo, int64_t rows_alloc, int64_t a_rows,

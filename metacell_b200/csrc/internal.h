@@ -29,6 +29,7 @@ struct mcb_ctx {
     int profile = 0;
     int keep_self = 0;
     int thresh_strict = 1;
+    int cap_override = 0;    // test hook: shrink the candidate capacity so rows take the exact-row path
     // stage timers
     struct Stage { const char* name; cudaEvent_t a, b; int64_t launches; };
     std::vector<Stage> stages;
@@ -126,6 +127,8 @@ struct CandPool {
 };
 uint32_t tc_pool_chunk_records();
 uint32_t tc_pool_min_chunks(mcb_ctx* ctx);
+void launch_tc_store3_ab(mcb_ctx* ctx, const void* Ahi, const void* Alo, int64_t a_rows_alloc, const void* Bhi, const void* Blo,
+                         int64_t b_rows_alloc, int64_t a_rows, int64_t b_rows, int32_t Gpad, float* C, int64_t ldc);
 void launch_tc_filter(mcb_ctx* ctx, const void* Zh, const void* Zl, int64_t rows_alloc, int64_t a_row0,
                       int64_t a_rows, int64_t b_rows, int32_t Gpad, const float* thr, const CandPool& pool);
 // select.cu: bin the pool's records into the per-row candidate lists (cnt counts every record, also past cap)

@@ -156,6 +156,31 @@ def test_cor_knn_parity(ctx, oracle, impl, ncells, K, kx):
     g.destroy()
 
 
+@pytest.mark.parametrize("impl", [0, 1])
+def test_cor_knn_exact_row_path(ctx, oracle, impl):
+    """rows whose candidate count misses the window are redone exactly: force it for most rows"""
+    from metacell_b200 import _lib
+    m = _small(ncells=1500)
+    feats = np.arange(0, 500, 2, dtype=np.int32)
+    csc = _upload(ctx, m)
+    ctx.set_option("gemm_impl", impl)
+    ctx.set_option("cap_override", 230)
+    try:
+        g = _lib.CGraph.from_csc(ctx, csc, feats, 7.0)
+        g.knn(20, 10)
+        col, cor = g.download_knn()
+        stats = g.knn_stats()
+    finally:
+        ctx.set_option("gemm_impl", 0)
+        ctx.set_option("cap_override", 0)
+    assert stats["fallback_rows"] > 100, stats
+    Z, valid = oracle.features(m.indptr, m.indices, m.data, feat_map_of(m.ngenes, feats), feats.size)
+    ocol, ocor = oracle.cor_knn(Z[valid], 208)
+    agree = _knn_parity(col, cor, ocol, ocor)
+    print(f"exact-row path impl={impl}: {stats['fallback_rows']} rows, agreement {agree:.6f}")
+    g.destroy()
+
+
 def test_cor_knn_duplicate_cells_and_ties(ctx, oracle):
     """exact duplicate cells give exactly tied correlations: self still rank 1, ties by lower index"""
     from metacell_b200 import _lib
