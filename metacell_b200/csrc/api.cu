@@ -902,6 +902,15 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
     c->ncl_cap = n_s / (min_mc_size > 0 ? min_mc_size + 1 : 1) + 2;
     const int32_t nl = c->n_local;
 
+    int32_t max_out = 0, max_in = 0;
+    for (int32_t v = 0; v < N; ++v) {
+        max_out = std::max<int32_t>(max_out, (int32_t)(optr[v + 1] - optr[v]));
+        max_in = std::max<int32_t>(max_in, (int32_t)(iptr[v + 1] - iptr[v]));
+    }
+    const bool small = n_edges < ((int64_t)1 << 31);
+    std::vector<int32_t> optr32(small ? optr.begin() : optr.begin(), small ? optr.end() : optr.begin());
+    std::vector<int32_t> iptr32(small ? iptr.begin() : iptr.begin(), small ? iptr.end() : iptr.begin());
+    DevBuf<int32_t> d_optr32(ctx, optr32.size()), d_iptr32(ctx, iptr32.size());
     DevBuf<int64_t> d_optr(ctx, optr.size()), d_iptr(ctx, iptr.size());
     DevBuf<int32_t> d_odst(ctx, odst.size()), d_isrc(ctx, isrc.size());
     DevBuf<uint32_t> d_ow(ctx, ow.size()), d_iw(ctx, iw.size());
@@ -911,6 +920,10 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
         StageTimer t(ctx, "h2d_graph");
         MCB_CUDA(cudaMemcpyAsync(d_optr.p, optr.data(), optr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
         MCB_CUDA(cudaMemcpyAsync(d_iptr.p, iptr.data(), iptr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (small) {
+            MCB_CUDA(cudaMemcpyAsync(d_optr32.p, optr32.data(), optr32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            MCB_CUDA(cudaMemcpyAsync(d_iptr32.p, iptr32.data(), iptr32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
         if (n_edges) {
             MCB_CUDA(cudaMemcpyAsync(d_odst.p, odst.data(), odst.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
             MCB_CUDA(cudaMemcpyAsync(d_isrc.p, isrc.data(), isrc.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -932,7 +945,7 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
     CoverGraph cg{N, d_optr.p, d_odst.p, d_ow.p, d_iptr.p, d_isrc.p, d_iw.p};
     {
         StageTimer t(ctx, "graph_cover");
-        launch_graph_cover(ctx, cg, nl, d_ids.p, n_s, d_samples.p, d_seeds.p, min_mc_size, cooling, burn_in, max_sweeps,
+        launch_graph_cover(ctx, cg, small ? d_optr32.p : nullptr, small ? d_iptr32.p : nullptr, max_out, max_in, nl, d_ids.p, n_s, d_samples.p, d_seeds.p, min_mc_size, cooling, burn_in, max_sweeps,
                            c->ncl_cap, c->mc.p, f_ws.p, c->sweeps.p, status.p);
     }
     {

@@ -161,7 +161,9 @@ struct CoverGraph {
     int32_t N; const int64_t* optr; const int32_t* odst; const uint32_t* ow;
     const int64_t* iptr; const int32_t* isrc; const uint32_t* iw;
 };
-void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
+// optr32 / iptr32: 32-bit copies of the CSR offsets (null when n_edges >= 2^31); max_out / max_in: largest degrees
+void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32, const int32_t* iptr32, int32_t max_out,
+                        int32_t max_in, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
                         const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling,
                         int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap, int32_t* mc /* [n_local][N] */,
                         int32_t* f_ws /* [n_local][N] */, int32_t* sweeps, int32_t* status);

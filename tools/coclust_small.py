@@ -1,0 +1,15 @@
+"""small co-clustering run for profiling: C3-shaped graph, 148 resamples"""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from metacell_b200 import _lib, synth
+ctx = _lib.Context(0)
+m = synth.make_umi_matrix(8000, 600, n_types=12, median_umis=3000.0, seed=1239)
+csc = _lib.Csc.upload(ctx, m.ngenes, m.indptr, m.indices, m.data.astype(np.float64))
+g = _lib.CGraph.from_csc(ctx, csc, np.arange(600, dtype=np.int32), 7.0)
+g.knn(100, 10); g.mutual(3); g.prune()
+src, dst, w = g.edges()
+g.destroy(); csc.free()
+sets, seeds = synth.resample_sets(m.ncells, 0.75, 148, 77)
+cc = _lib.CoClust(ctx, m.ncells, src, dst, w, sets, seeds, 20, 1.05, 10)
+print("pairs", cc.pairs()[0].size)
