@@ -92,6 +92,18 @@ int  mcb_cgraph_features(mcb_cgraph* g, float* host_z /* [M][G] */);      /* tes
 /* A5: tgs_cor_knn(x, y = x, knn = K*k_expand) for the rows owned by `rank` of `nranks`
  * (contiguous split of the M valid cells).  Self is rank 1 (R/atlas.r:475-476).                */
 int  mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks);
+/* Symmetric multi-GPU form of the same stage (every unordered cell pair is contracted once across all ranks):
+ *   knn_begin        sampling pass, thresholds of the owned rows
+ *   knn_thr_buffer   float [nranks * rows_per_rank] threshold buffer: all-gather it in place
+ *   knn_filter       this rank's share of the symmetric tile list -> candidate records for rows of EVERY rank,
+ *                    grouped by owner rank: *dev_send = uint4 records, send_counts[nranks] = records per owner
+ *   knn_recv_buffer  room for the records this rank receives in the all-to-all
+ *   knn_finish       bin the received records, rank them, exact rows; then continue as after mcb_cgraph_knn  */
+int  mcb_cgraph_knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks);
+int  mcb_cgraph_knn_thr_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank);
+int  mcb_cgraph_knn_filter(mcb_cgraph* g, void** dev_send, int64_t* send_counts /* [nranks] */);
+int  mcb_cgraph_knn_recv_buffer(mcb_cgraph* g, int64_t n_records, void** dev_recv);
+int  mcb_cgraph_knn_finish(mcb_cgraph* g, int64_t n_records);
 /* the full [nranks * rows_per_rank][Kc] int32 kNN column buffer on the device; this rank's block
  * starts at row rank * rows_per_rank.  The host plumbing all-gathers it in place (NCCL).       */
 int  mcb_cgraph_knn_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank, int32_t* Kc);

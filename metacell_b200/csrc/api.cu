@@ -339,6 +339,11 @@ struct mcb_cgraph {
     int64_t rows_per_rank = 0, row0 = 0, rows = 0;
     DevBuf<int32_t> knn_col; DevBuf<float> knn_cor;
     int64_t n_fallback = 0, n_candidates = 0; int32_t cap = 0, n_sample = 0;
+    double expect_per_row = 0.0; int exchange = 0;
+    DevBuf<float> thr_all;                               // filter thresholds, [nranks * rows_per_rank]
+    DevBuf<uint64_t> cand; DevBuf<uint32_t> cnt;         // per-row candidate lists of the owned rows
+    DevBuf<uint4> pool_records; DevBuf<uint32_t> pool_fill, pool_ctl; uint32_t pool_chunks = 0;
+    DevBuf<uint4> send, recv; std::vector<int64_t> send_counts;   // symmetric multi-GPU record exchange
     // balance
     int32_t H = 0, rank_bits = 0, k_beta = 0;
     DevBuf<uint32_t> sym; DevBuf<uint64_t> thr_in;
@@ -489,16 +494,20 @@ static void sample_rule(int64_t M, int64_t S, int32_t kc_out, int32_t& r_out, in
     r_out = r; cap_out = (int32_t)cap;
 }
 
-extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks)
+// ---- the kNN stage in three steps (the multi-GPU plumbing exchanges data between them) -------------------
+//   knn_begin  : sizes, sampling pass, per-row thresholds of the owned rows (block of thr_all)
+//   knn_filter : full 3-pass contraction.  exchange = 0: the rank's own rows (symmetric on one rank, rectangular
+//                otherwise) into the pool;  exchange = 1 (multi-GPU): the rank's share of the SYMMETRIC tile list,
+//                records for rows of every rank, partitioned by owner into g->send
+//   knn_finish : bin records (pool, or the received buffer) into candidate lists, ranked lists, exact rows
+static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks)
 {
-    MCB_API_BEGIN
-    MCB_CHECK(g, "null argument");
     MCB_CHECK(K >= 1 && k_expand >= 1, "MC-ERR: K and k_expand must be >= 1");
     MCB_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
     MCB_CHECK((int64_t)K * k_expand <= 4096, "MC-ERR: K * k_expand above 4096 is not supported");
     MCB_CHECK(g->M >= 2, "MC-ERR: fewer than 2 cells with non-constant features");
+    MCB_CHECK(g->Zf.p, "mcb_cgraph_knn: the feature planes were released (call before mcb_cgraph_mutual)");
     mcb_ctx* ctx = g->ctx;
-    MCB_CUDA(cudaSetDevice(ctx->device));
     const int64_t M = g->M;
     const int32_t Gpad = g->Gpad;
     g->K = K; g->k_expand = k_expand; g->Kc = K * k_expand; g->kc_out = (int32_t)std::min<int64_t>(g->Kc, M);
@@ -510,8 +519,12 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     const int32_t Kc = g->Kc, kc_out = g->kc_out;
     g->knn_col.alloc(ctx, (size_t)nranks * g->rows_per_rank * Kc);
     g->knn_cor.alloc(ctx, (size_t)std::max<int64_t>(rows, 1) * Kc);
-    if (rows == 0) { MCB_CUDA(cudaStreamSynchronize(ctx->stream)); return 0; }
-
+    g->thr_all.alloc(ctx, (size_t)nranks * g->rows_per_rank);
+    {   // rows past M (padding of the last rank's block) never pass
+        std::vector<float> inf((size_t)nranks * g->rows_per_rank, INFINITY);
+        MCB_CUDA(cudaMemcpyAsync(g->thr_all.p, inf.data(), inf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     // ---- sampling pass: per-row filter threshold from a random column sample -----------------
     int64_t S = std::min<int64_t>(32768, round_up(ceil_div(128 * M, kc_out), 256));
     if (S >= M) S = M;
@@ -521,6 +534,8 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     MCB_CHECK(cap <= 4096, "MC-ERR: K * k_expand is too large relative to the number of cells for this build");
     if (ctx->cap_override > 0) cap = std::min(cap, ctx->cap_override);
     g->cap = cap; g->n_sample = (int32_t)S;
+    g->expect_per_row = r_sel > S ? (double)M : (double)r_sel * (double)M / (double)S;
+    if (rows == 0) return;
     std::vector<int32_t> samp((size_t)Spad, -1);
     {
         if (S >= M) { for (int64_t q = 0; q < M; ++q) samp[q] = (int32_t)q; }
@@ -539,72 +554,116 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     MCB_CUDA(cudaMemcpyAsync(d_samp.p, samp.data(), sizeof(int32_t) * (size_t)Spad, cudaMemcpyHostToDevice, ctx->stream));
     DevBuf<__half> Zs(ctx, ctx->gemm_impl != 1 ? (size_t)Spad * Gpad : 0);
     DevBuf<float> Zsf(ctx, ctx->gemm_impl != 1 ? 0 : (size_t)Spad * Gpad);
-    DevBuf<float> thr(ctx, (size_t)rows);
+    float* thr = g->thr_all.p + row0;
     {
         StageTimer t(ctx, "sample_gather");
         if (ctx->gemm_impl != 1) launch_gather_rows(ctx, g->Zh.p, (int64_t)Gpad * sizeof(__half), d_samp.p, (int32_t)Spad, Zs.p);
         else launch_gather_rows(ctx, g->Zf.p, (int64_t)Gpad * sizeof(float), d_samp.p, (int32_t)Spad, Zsf.p);
     }
-    {
-        int64_t chunk = std::max<int64_t>(128, ((int64_t)2 << 30) / (Spad * 4) / 128 * 128);
-        chunk = std::min(chunk, round_up(rows, 128));
-        DevBuf<float> Cs(ctx, (size_t)chunk * Spad);
-        const float eps = 1.0f / 512.0f;      // covers the 1-pass TF32 error of the sampled correlations
-        for (int64_t c0 = 0; c0 < rows; c0 += chunk) {
-            const int64_t nr = std::min(chunk, rows - c0);
-            {
-                StageTimer t(ctx, "cor_sample_gemm");
-                if (ctx->gemm_impl != 1)
-                    launch_tc_store(ctx, g->Zh.p + (size_t)(row0 + c0) * Gpad, g->Mpad - (row0 + c0), Zs.p, Spad, Gpad,
-                                    Cs.p, Spad, nr, S);
-                else
-                    launch_simt_store(ctx, g->Zf.p + (size_t)(row0 + c0) * Gpad, nr, Zsf.p, S, Gpad, Cs.p, Spad);
-            }
-            {
-                StageTimer t(ctx, "sample_threshold");
-                launch_sample_threshold(ctx, Cs.p, Spad, nr, (int32_t)S, r_sel, eps, thr.p + c0);
-            }
+    int64_t chunk = std::max<int64_t>(128, ((int64_t)2 << 30) / (Spad * 4) / 128 * 128);
+    chunk = std::min(chunk, round_up(rows, 128));
+    DevBuf<float> Cs(ctx, (size_t)chunk * Spad);
+    const float eps = 1.0f / 512.0f;      // covers the 1-pass error of the sampled correlations
+    for (int64_t c0 = 0; c0 < rows; c0 += chunk) {
+        const int64_t nr = std::min(chunk, rows - c0);
+        {
+            StageTimer t(ctx, "cor_sample_gemm");
+            if (ctx->gemm_impl != 1)
+                launch_tc_store(ctx, g->Zh.p + (size_t)(row0 + c0) * Gpad, g->Mpad - (row0 + c0), Zs.p, Spad, Gpad,
+                                Cs.p, Spad, nr, S);
+            else
+                launch_simt_store(ctx, g->Zf.p + (size_t)(row0 + c0) * Gpad, nr, Zsf.p, S, Gpad, Cs.p, Spad);
+        }
+        {
+            StageTimer t(ctx, "sample_threshold");
+            launch_sample_threshold(ctx, Cs.p, Spad, nr, (int32_t)S, r_sel, eps, thr + c0);
         }
     }
-    // ---- filter pass: full 3-pass contraction, candidates above the row threshold ------------
-    DevBuf<uint64_t> cand(ctx, (size_t)rows * cap);
-    DevBuf<uint32_t> cnt(ctx, (size_t)rows);
-    if (ctx->gemm_impl != 1) {
-        // the epilogue appends records to pool chunks; expected records ~ rows * (count at the sampled threshold)
-        const uint32_t crec = tc_pool_chunk_records();
-        double expect = (double)rows * (r_sel > S ? (double)M : (double)r_sel * (double)M / (double)S);
-        for (int attempt = 0;; ++attempt) {
-            const uint32_t n_chunks = (uint32_t)std::min<double>(4.0e6, expect * 1.3 / crec + tc_pool_min_chunks(ctx));
-            DevBuf<uint4> records(ctx, (size_t)n_chunks * crec);
-            DevBuf<uint32_t> chunk_fill(ctx, (size_t)n_chunks), ctl(ctx, 2);
-            chunk_fill.zero(); ctl.zero(); cnt.zero();
-            CandPool pool{records.p, ctl.p, chunk_fill.p, n_chunks, ctl.p + 1};
-            {
-                StageTimer t(ctx, "cor_filter_gemm");
-                launch_tc_filter(ctx, g->Zh.p, g->Zl.p, g->Mpad, row0, rows, M, Gpad, thr.p, pool);
-            }
-            {
-                StageTimer t(ctx, "cand_scatter");
-                launch_scatter_candidates(ctx, pool, cand.p, cnt.p, cap);
-            }
-            uint32_t hctl[2] = {0, 0};
-            MCB_CUDA(cudaMemcpyAsync(hctl, ctl.p, sizeof(hctl), cudaMemcpyDeviceToHost, ctx->stream));
-            MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (!hctl[1]) break;
-            MCB_CHECK(attempt < 3, "MC-ERR: candidate pool overflow (correlation structure far from the sampled estimate)");
-            expect *= 2.0;          // the pool ran out: repeat the pass with twice the room
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));        // samp / temporaries die here
+}
+
+static void knn_filter(mcb_cgraph* g, int exchange)
+{
+    mcb_ctx* ctx = g->ctx;
+    const int64_t M = g->M, rows = g->rows, row0 = g->row0;
+    const int32_t Gpad = g->Gpad, cap = g->cap, nranks = g->nranks;
+    g->exchange = exchange;
+    g->cand.alloc(ctx, (size_t)std::max<int64_t>(rows, 1) * cap);
+    g->cnt.alloc(ctx, (size_t)std::max<int64_t>(rows, 1));
+    g->cnt.zero();
+    g->send_counts.assign((size_t)nranks, 0);
+    if (ctx->gemm_impl == 1) {      // CUDA-core validation path: straight into the candidate lists, own rows only
+        MCB_CHECK(!exchange, "the symmetric multi-GPU exchange needs the tensor-core kernels");
+        g->pool_records.release();
+        if (rows) {
+            StageTimer t(ctx, "cor_filter_gemm");
+            launch_simt_filter(ctx, g->Zf.p + (size_t)row0 * Gpad, row0, rows, g->Zf.p, M, Gpad, g->thr_all.p + row0, g->cand.p, g->cnt.p, cap);
         }
-    } else {
-        cnt.zero();
-        StageTimer t(ctx, "cor_filter_gemm");
-        launch_simt_filter(ctx, g->Zf.p + (size_t)row0 * Gpad, row0, rows, g->Zf.p, M, Gpad, thr.p, cand.p, cnt.p, cap);
+        return;
+    }
+    // the epilogue appends records to pool chunks; expected records ~ (rows served) x (count at the sampled threshold)
+    const uint32_t crec = tc_pool_chunk_records();
+    double expect = (exchange ? (double)M / nranks : (double)rows) * g->expect_per_row;
+    for (int attempt = 0;; ++attempt) {
+        const uint32_t n_chunks = (uint32_t)std::min<double>(4.0e6, expect * 1.3 / crec + tc_pool_min_chunks(ctx));
+        g->pool_records.alloc(ctx, (size_t)n_chunks * crec);
+        g->pool_fill.alloc(ctx, (size_t)n_chunks);
+        g->pool_ctl.alloc(ctx, 2);
+        g->pool_fill.zero(); g->pool_ctl.zero();
+        g->pool_chunks = n_chunks;
+        CandPool pool{g->pool_records.p, g->pool_ctl.p, g->pool_fill.p, n_chunks, g->pool_ctl.p + 1};
+        {
+            StageTimer t(ctx, "cor_filter_gemm");
+            if (exchange) launch_tc_filter(ctx, g->Zh.p, g->Zl.p, g->Mpad, 0, M, M, Gpad, g->thr_all.p, pool, g->rank, nranks);
+            else if (rows) launch_tc_filter(ctx, g->Zh.p, g->Zl.p, g->Mpad, row0, rows, M, Gpad, g->thr_all.p + row0, pool);
+        }
+        uint32_t hctl[2] = {0, 0};
+        MCB_CUDA(cudaMemcpyAsync(hctl, g->pool_ctl.p, sizeof(hctl), cudaMemcpyDeviceToHost, ctx->stream));
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (!hctl[1]) break;
+        MCB_CHECK(attempt < 3, "MC-ERR: candidate pool overflow (correlation structure far from the sampled estimate)");
+        expect *= 2.0;          // the pool ran out: repeat the pass with twice the room
+    }
+    if (exchange) {
+        // group the records by owner rank for the all-to-all
+        StageTimer t(ctx, "records_partition", 2);
+        CandPool pool{g->pool_records.p, g->pool_ctl.p, g->pool_fill.p, g->pool_chunks, g->pool_ctl.p + 1};
+        DevBuf<uint64_t> counts(ctx, (size_t)nranks), base(ctx, (size_t)nranks), cur(ctx, (size_t)nranks);
+        counts.zero(); cur.zero();
+        launch_count_records_by_dest(ctx, pool, g->rows_per_rank, nranks, counts.p);
+        std::vector<uint64_t> hc((size_t)nranks), hb((size_t)nranks);
+        MCB_CUDA(cudaMemcpyAsync(hc.data(), counts.p, sizeof(uint64_t) * (size_t)nranks, cudaMemcpyDeviceToHost, ctx->stream));
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        uint64_t tot = 0;
+        for (int32_t r = 0; r < nranks; ++r) { hb[r] = tot; tot += hc[r]; g->send_counts[r] = (int64_t)hc[r]; }
+        MCB_CUDA(cudaMemcpyAsync(base.p, hb.data(), sizeof(uint64_t) * (size_t)nranks, cudaMemcpyHostToDevice, ctx->stream));
+        g->send.alloc(ctx, (size_t)std::max<uint64_t>(tot, 1));
+        launch_partition_records(ctx, pool, g->rows_per_rank, nranks, base.p, cur.p, g->send.p);
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        g->pool_records.release();
+    }
+}
+
+static void knn_finish(mcb_cgraph* g, int64_t n_recv)
+{
+    mcb_ctx* ctx = g->ctx;
+    const int64_t M = g->M, rows = g->rows, row0 = g->row0;
+    const int32_t Gpad = g->Gpad, cap = g->cap, Kc = g->Kc, kc_out = g->kc_out;
+    if (rows == 0) { MCB_CUDA(cudaStreamSynchronize(ctx->stream)); return; }
+    if (ctx->gemm_impl != 1) {
+        StageTimer t(ctx, "cand_scatter");
+        if (g->exchange) launch_scatter_flat(ctx, g->recv.p, n_recv, row0, g->cand.p, g->cnt.p, cap);
+        else {
+            CandPool pool{g->pool_records.p, g->pool_ctl.p, g->pool_fill.p, g->pool_chunks, g->pool_ctl.p + 1};
+            launch_scatter_candidates(ctx, pool, g->cand.p, g->cnt.p, cap);
+        }
     }
     // ---- ranked lists -------------------------------------------------------------------------
     DevBuf<int32_t> fail(ctx, (size_t)rows), fail_list(ctx, (size_t)rows), n_fail_d(ctx, 1);
     int32_t* own_col = g->knn_col.p + (size_t)row0 * Kc;
     {
         StageTimer t(ctx, "topk_rows");
-        launch_topk_rows(ctx, cand.p, cnt.p, cap, row0, rows, kc_out, Kc, own_col, g->knn_cor.p, fail.p);
+        launch_topk_rows(ctx, g->cand.p, g->cnt.p, cap, row0, rows, kc_out, Kc, own_col, g->knn_cor.p, fail.p);
     }
     launch_compact_flags(ctx, fail.p, rows, fail_list.p, n_fail_d.p);
     int32_t n_fail = 0;
@@ -643,12 +702,68 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     }
     {   // statistics for DESIGN / bench: how selective the filter was
         std::vector<uint32_t> hc((size_t)rows);
-        MCB_CUDA(cudaMemcpyAsync(hc.data(), cnt.p, sizeof(uint32_t) * (size_t)rows, cudaMemcpyDeviceToHost, ctx->stream));
+        MCB_CUDA(cudaMemcpyAsync(hc.data(), g->cnt.p, sizeof(uint32_t) * (size_t)rows, cudaMemcpyDeviceToHost, ctx->stream));
         MCB_CUDA(cudaStreamSynchronize(ctx->stream));
         int64_t tot = 0;
         for (auto v : hc) tot += v;
         g->n_candidates = tot;
     }
+    g->cand.release(); g->cnt.release(); g->pool_records.release(); g->pool_fill.release(); g->send.release(); g->recv.release();
+}
+
+extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g, "null argument");
+    MCB_CUDA(cudaSetDevice(g->ctx->device));
+    knn_begin(g, K, k_expand, rank, nranks);
+    knn_filter(g, 0);
+    knn_finish(g, 0);
+    MCB_API_END
+}
+// ---- staged form for the symmetric multi-GPU schedule (metacell_b200/dist.py shows the sequence) ------------------
+extern "C" int mcb_cgraph_knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g, "null argument");
+    MCB_CUDA(cudaSetDevice(g->ctx->device));
+    knn_begin(g, K, k_expand, rank, nranks);
+    MCB_API_END
+}
+extern "C" int mcb_cgraph_knn_thr_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && g->thr_all.p, "mcb_cgraph_knn_thr_buffer: run mcb_cgraph_knn_begin first");
+    if (dev_ptr) *dev_ptr = g->thr_all.p;
+    if (rows_per_rank) *rows_per_rank = g->rows_per_rank;
+    MCB_API_END
+}
+extern "C" int mcb_cgraph_knn_filter(mcb_cgraph* g, void** dev_send, int64_t* send_counts)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && g->thr_all.p, "mcb_cgraph_knn_filter: run mcb_cgraph_knn_begin first");
+    MCB_CUDA(cudaSetDevice(g->ctx->device));
+    knn_filter(g, 1);
+    if (dev_send) *dev_send = g->send.p;
+    if (send_counts) for (int32_t r = 0; r < g->nranks; ++r) send_counts[r] = g->send_counts[r];
+    MCB_API_END
+}
+extern "C" int mcb_cgraph_knn_recv_buffer(mcb_cgraph* g, int64_t n_records, void** dev_recv)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && dev_recv && n_records >= 0, "mcb_cgraph_knn_recv_buffer: bad argument");
+    MCB_CUDA(cudaSetDevice(g->ctx->device));
+    g->recv.alloc(g->ctx, (size_t)std::max<int64_t>(n_records, 1));
+    MCB_CUDA(cudaStreamSynchronize(g->ctx->stream));
+    *dev_recv = g->recv.p;
+    MCB_API_END
+}
+extern "C" int mcb_cgraph_knn_finish(mcb_cgraph* g, int64_t n_records)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && g->cand.p, "mcb_cgraph_knn_finish: run mcb_cgraph_knn_filter first");
+    MCB_CUDA(cudaSetDevice(g->ctx->device));
+    knn_finish(g, n_records);
     MCB_API_END
 }
 

@@ -74,6 +74,9 @@ struct TcParams {
     int64_t b_rows;      // valid columns
     int32_t num_kb;      // Gpad / BK
     int32_t m_tiles, n_tiles, total_tiles;
+    // rank partition of the tile list (symmetric multi-GPU): this launch takes the runs of part_block consecutive
+    // tiles whose run index is congruent to `part` modulo `nparts`; local_tiles = how many that is
+    int32_t part_block, nparts, part, local_tiles;
     int32_t dbg;         // diagnostics (MCB_TC_DEBUG): 1 = epilogue only waits, 2 = epilogue only reads TMEM
     // STORE
     float* C; int64_t ldc;
@@ -108,6 +111,19 @@ struct TileIter {
         n_blk = ns(g) + within / c;
     }
 };
+
+// l-th tile of this launch's share of the tile list (identity when nparts == 1)
+__device__ __forceinline__ int part_tile(const TcParams& prm, int l)
+{
+    return ((l / prm.part_block) * prm.nparts + prm.part) * prm.part_block + (l % prm.part_block);
+}
+static int part_count(int total, int part_block, int nparts, int part)      // host: size of that share
+{
+    const int runs = total / part_block, tail = total % part_block;
+    int n = (runs / nparts) * part_block + ((runs % nparts) > part ? part_block : 0);
+    if (tail && (runs % nparts) == part) n += tail;
+    return n;
+}
 
 // symmetric mode: a tile whose last column does not exceed its first row holds no pair (i, j > i)
 template <int MODE, int CM>
@@ -388,7 +404,6 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     const int crank = CM > 1 ? (int)cluster_ctarank() : 0;
     const int m_units = (prm.m_tiles + CM - 1) / CM;
     const TileIter iter0(m_units, prm.n_tiles, MODE == 2 ? 1 : 0, CM * BM);
-    const int total_tiles = prm.total_tiles;
     const int unit0 = (int)blockIdx.x / CM, unit_stride = (int)gridDim.x / CM;
 
     if (warp == 0 && lane == 0) {
@@ -412,7 +427,8 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             TileIter iter = iter0;
-            for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+            for (int l = unit0; l < prm.local_tiles; l += unit_stride) {
+                const int tile = part_tile(prm, l);
                 int m_blk, n_blk;
                 iter.coords(tile, m_blk, n_blk);
                 m_blk = m_blk * CM + crank;
@@ -450,7 +466,8 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
             uint32_t tphase = 0;
             const uint32_t d_main = tmem_base, d_cross = tmem_base + (uint32_t)BN;
             TileIter iter = iter0;
-            for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+            for (int l = unit0; l < prm.local_tiles; l += unit_stride) {
+                const int tile = part_tile(prm, l);
                 if (MODE == 2) {
                     int m_blk, n_blk;
                     iter.coords(tile, m_blk, n_blk);
@@ -496,7 +513,8 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         float* tcol = reinterpret_cast<float*>(tmem_slot + 4) + (warp - EPI_WARP0) * (BN / 2);    // per-warp column thresholds (MODE 2)
         uint32_t chunk_id = 0, fill = 0;          // this warp's open record chunk (warp-uniform)
         bool have_chunk = false;
-        for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+        for (int l = unit0; l < prm.local_tiles; l += unit_stride) {
+                const int tile = part_tile(prm, l);
             int m_blk, n_blk;
             iter.coords(tile, m_blk, n_blk);
             m_blk = m_blk * CM + crank;
@@ -561,7 +579,6 @@ tc_cor2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
     const bool leader = crank == 0;
     const int m_units = (prm.m_tiles + 1) / 2;       // 256-row units
     const TileIter iter0(m_units, prm.n_tiles, MODE == 2 ? 1 : 0, 2 * BM);
-    const int total_tiles = prm.total_tiles;
     const int unit0 = (int)blockIdx.x / 2, unit_stride = (int)gridDim.x / 2;
 
     if (warp == 0 && lane == 0) {
@@ -587,7 +604,8 @@ tc_cor2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             TileIter iter = iter0;
-            for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+            for (int l = unit0; l < prm.local_tiles; l += unit_stride) {
+                const int tile = part_tile(prm, l);
                 int unit, n_blk;
                 iter.coords(tile, unit, n_blk);
                 if (skip(unit, n_blk)) continue;
@@ -614,7 +632,8 @@ tc_cor2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
             uint32_t tphase = 0;
             const uint32_t d_main = tmem_base, d_cross = tmem_base + (uint32_t)BN;
             TileIter iter = iter0;
-            for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+            for (int l = unit0; l < prm.local_tiles; l += unit_stride) {
+                const int tile = part_tile(prm, l);
                 int unit, n_blk;
                 iter.coords(tile, unit, n_blk);
                 if (skip(unit, n_blk)) continue;
@@ -655,7 +674,8 @@ tc_cor2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
         uint32_t chunk_id = 0, fill = 0;
         bool have_chunk = false;
         const uint32_t tempty_leader = mapa_u32(smem_u32(tempty_bar), 0);
-        for (int tile = unit0; tile < total_tiles; tile += unit_stride) {
+        for (int l = unit0; l < prm.local_tiles; l += unit_stride) {
+                const int tile = part_tile(prm, l);
             int unit, n_blk;
             iter.coords(tile, unit, n_blk);
             if (skip(unit, n_blk)) continue;
@@ -723,7 +743,10 @@ static void launch_tc(mcb_ctx* ctx, const CUtensorMap& ah, const CUtensorMap& al
     TcParams p2 = prm;
     p2.dbg = (MODE != 0 && getenv("MCB_TC_DEBUG")) ? atoi(getenv("MCB_TC_DEBUG")) : 0;
     p2.total_tiles = TileIter((int)ceil_div(prm.m_tiles, CM), prm.n_tiles, MODE == 2 ? 1 : 0, CM * BM).total();
-    const int units = p2.total_tiles;
+    if (p2.nparts < 1) { p2.nparts = 1; p2.part = 0; }
+    p2.part_block = GROUP_M;
+    p2.local_tiles = part_count(p2.total_tiles, p2.part_block, p2.nparts, p2.part);
+    const int units = std::max(1, p2.local_tiles);
     const int grid = std::min(units, ctx->num_sms / CM) * CM;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -764,7 +787,10 @@ static void launch_tc2(mcb_ctx* ctx, const CUtensorMap& mh, const CUtensorMap& m
     TcParams p2 = prm;
     p2.dbg = getenv("MCB_TC_DEBUG") ? atoi(getenv("MCB_TC_DEBUG")) : 0;
     p2.total_tiles = TileIter((int)ceil_div(prm.m_tiles, 2), prm.n_tiles, MODE == 2 ? 1 : 0, 2 * BM).total();
-    const int pairs = std::min(p2.total_tiles, ctx->num_sms / 2);
+    if (p2.nparts < 1) { p2.nparts = 1; p2.part = 0; }
+    p2.part_block = GROUP_M;
+    p2.local_tiles = part_count(p2.total_tiles, p2.part_block, p2.nparts, p2.part);
+    const int pairs = std::max(1, std::min(p2.local_tiles, ctx->num_sms / 2));
     tc_cor2_kernel<MODE><<<2 * pairs, TC_THREADS, Tc2Cfg::SMEM_BYTES, ctx->stream>>>(mh, ml, p2);   // __cluster_dims__(2,1,1)
     MCB_LAUNCH_CHECK();
 }
@@ -773,7 +799,8 @@ uint32_t tc_pool_chunk_records() { return POOL_CHUNK; }
 uint32_t tc_pool_min_chunks(mcb_ctx* ctx) { return (uint32_t)(EPI_WARPS * ctx->num_sms + 64); }   // one open chunk per warp
 
 void launch_tc_filter(mcb_ctx* ctx, const void* Zhi, const void* Zlo, int64_t rows_alloc, int64_t a_row0,
-                      int64_t a_rows, int64_t b_rows, int32_t Gpad, const float* thr, const CandPool& pool)
+                      int64_t a_rows, int64_t b_rows, int32_t Gpad, const float* thr, const CandPool& pool, int32_t part,
+                      int32_t nparts)
 {
     if (a_rows == 0 || b_rows == 0) return;
     tc_init();
@@ -789,6 +816,7 @@ void launch_tc_filter(mcb_ctx* ctx, const void* Zhi, const void* Zlo, int64_t ro
     prm.thr = thr;
     prm.pool = reinterpret_cast<uint4*>(pool.records); prm.pool_cursor = pool.cursor; prm.chunk_fill = pool.chunk_fill;
     prm.pool_chunks = pool.n_chunks; prm.overflow = pool.overflow;
+    prm.part = part; prm.nparts = nparts;
     const bool sym = a_row0 == 0 && a_rows == b_rows;   // whole square on one rank: each unordered pair contracted once
     if (ctx->gemm_impl == 2) {                          // 1-SM kernel (A/B measurements)
         if (sym) launch_tc<3, 2, FILTER_CM>(ctx, ah, al, bh, bl, prm);

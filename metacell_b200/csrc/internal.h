@@ -130,7 +130,13 @@ uint32_t tc_pool_min_chunks(mcb_ctx* ctx);
 void launch_tc_store3_ab(mcb_ctx* ctx, const void* Ahi, const void* Alo, int64_t a_rows_alloc, const void* Bhi, const void* Blo,
                          int64_t b_rows_alloc, int64_t a_rows, int64_t b_rows, int32_t Gpad, float* C, int64_t ldc);
 void launch_tc_filter(mcb_ctx* ctx, const void* Zh, const void* Zl, int64_t rows_alloc, int64_t a_row0,
-                      int64_t a_rows, int64_t b_rows, int32_t Gpad, const float* thr, const CandPool& pool);
+                      int64_t a_rows, int64_t b_rows, int32_t Gpad, const float* thr, const CandPool& pool, int32_t part = 0,
+                      int32_t nparts = 1);
+// select.cu: symmetric multi-GPU record exchange helpers
+void launch_count_records_by_dest(mcb_ctx* ctx, const CandPool& pool, int64_t rows_per_rank, int32_t nranks, uint64_t* counts);
+void launch_partition_records(mcb_ctx* ctx, const CandPool& pool, int64_t rows_per_rank, int32_t nranks, const uint64_t* base,
+                              uint64_t* cursor, void* send);
+void launch_scatter_flat(mcb_ctx* ctx, const void* records, int64_t n, int64_t row0, uint64_t* cand, uint32_t* cnt, int32_t cap);
 // select.cu: bin the pool's records into the per-row candidate lists (cnt counts every record, also past cap)
 void launch_scatter_candidates(mcb_ctx* ctx, const CandPool& pool, uint64_t* cand, uint32_t* cnt, int32_t cap);
 

@@ -283,6 +283,71 @@ scatter_candidates_kernel(const uint4* __restrict__ records, const uint32_t* __r
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// symmetric multi-GPU: a rank's filter pass yields records for rows owned by every rank.  Records are
+// grouped by owner (row / rows_per_rank) into one send buffer (NCCL all-to-all by the host plumbing),
+// and the received records are binned like local ones.
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_RANKS = 64;
+
+__global__ void __launch_bounds__(256)
+count_records_by_dest_kernel(const uint4* __restrict__ records, const uint32_t* __restrict__ cursor,
+                             const uint32_t* __restrict__ chunk_fill, uint32_t pool_chunks, uint32_t chunk_records,
+                             uint32_t rows_per_rank, int nranks, unsigned long long* __restrict__ counts)
+{
+    __shared__ uint32_t sc[MAX_RANKS];
+    const uint32_t used = min(*cursor, pool_chunks);
+    for (uint32_t ch = blockIdx.x; ch < used; ch += gridDim.x) {
+        if (threadIdx.x < MAX_RANKS) sc[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t n = min(chunk_fill[ch], chunk_records);
+        const uint4* r = records + (size_t)ch * chunk_records;
+        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) atomicAdd(&sc[r[e].z / rows_per_rank], 1u);
+        __syncthreads();
+        if (threadIdx.x < nranks && sc[threadIdx.x]) atomicAdd(&counts[threadIdx.x], (unsigned long long)sc[threadIdx.x]);
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256)
+partition_records_kernel(const uint4* __restrict__ records, const uint32_t* __restrict__ cursor,
+                         const uint32_t* __restrict__ chunk_fill, uint32_t pool_chunks, uint32_t chunk_records,
+                         uint32_t rows_per_rank, int nranks, const unsigned long long* __restrict__ base,
+                         unsigned long long* __restrict__ cur, uint4* __restrict__ send)
+{
+    __shared__ uint32_t sc[MAX_RANKS];
+    __shared__ unsigned long long sb[MAX_RANKS];
+    const uint32_t used = min(*cursor, pool_chunks);
+    for (uint32_t ch = blockIdx.x; ch < used; ch += gridDim.x) {
+        if (threadIdx.x < MAX_RANKS) sc[threadIdx.x] = 0;
+        __syncthreads();
+        const uint32_t n = min(chunk_fill[ch], chunk_records);
+        const uint4* r = records + (size_t)ch * chunk_records;
+        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) atomicAdd(&sc[r[e].z / rows_per_rank], 1u);
+        __syncthreads();
+        if (threadIdx.x < nranks) {      // reserve this chunk's range in every destination segment
+            sb[threadIdx.x] = base[threadIdx.x] + (sc[threadIdx.x] ? atomicAdd(&cur[threadIdx.x], (unsigned long long)sc[threadIdx.x]) : 0ull);
+            sc[threadIdx.x] = 0;
+        }
+        __syncthreads();
+        for (uint32_t e = threadIdx.x; e < n; e += blockDim.x) {
+            const uint4 rec = r[e];
+            const uint32_t d = rec.z / rows_per_rank;
+            send[sb[d] + atomicAdd(&sc[d], 1u)] = rec;
+        }
+        __syncthreads();
+    }
+}
+__global__ void scatter_flat_kernel(const uint4* __restrict__ records, int64_t n, uint32_t row0, uint64_t* __restrict__ cand,
+                                    uint32_t* __restrict__ cnt, int32_t cap)
+{
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 rec = records[e];
+        const uint32_t lrow = rec.z - row0;
+        const uint32_t pos = atomicAdd(&cnt[lrow], 1u);
+        if (pos < (uint32_t)cap) cand[(size_t)lrow * cap + pos] = ((uint64_t)rec.y << 32) | rec.x;
+    }
+}
+
 // compact the flagged rows into a list; *n_out = count
 __global__ void compact_flags_kernel(const int32_t* __restrict__ flag, int64_t n, int32_t* __restrict__ list,
                                      int32_t* __restrict__ n_out)
@@ -332,6 +397,32 @@ void launch_scatter_candidates(mcb_ctx* ctx, const CandPool& pool, uint64_t* can
     int grid = (int)std::min<int64_t>(pool.n_chunks, (int64_t)ctx->num_sms * 8);
     scatter_candidates_kernel<<<grid, 256, 0, ctx->stream>>>((const uint4*)pool.records, pool.cursor, pool.chunk_fill,
                                                              pool.n_chunks, tc_pool_chunk_records(), cand, cnt, cap);
+    MCB_LAUNCH_CHECK();
+}
+
+void launch_count_records_by_dest(mcb_ctx* ctx, const CandPool& pool, int64_t rows_per_rank, int32_t nranks, uint64_t* counts)
+{
+    MCB_CHECK(nranks <= MAX_RANKS, "too many ranks");
+    int grid = (int)std::min<int64_t>(pool.n_chunks, (int64_t)ctx->num_sms * 8);
+    count_records_by_dest_kernel<<<grid, 256, 0, ctx->stream>>>((const uint4*)pool.records, pool.cursor, pool.chunk_fill, pool.n_chunks,
+                                                                tc_pool_chunk_records(), (uint32_t)rows_per_rank, nranks,
+                                                                (unsigned long long*)counts);
+    MCB_LAUNCH_CHECK();
+}
+void launch_partition_records(mcb_ctx* ctx, const CandPool& pool, int64_t rows_per_rank, int32_t nranks, const uint64_t* base,
+                              uint64_t* cursor, void* send)
+{
+    int grid = (int)std::min<int64_t>(pool.n_chunks, (int64_t)ctx->num_sms * 8);
+    partition_records_kernel<<<grid, 256, 0, ctx->stream>>>((const uint4*)pool.records, pool.cursor, pool.chunk_fill, pool.n_chunks,
+                                                            tc_pool_chunk_records(), (uint32_t)rows_per_rank, nranks,
+                                                            (const unsigned long long*)base, (unsigned long long*)cursor, (uint4*)send);
+    MCB_LAUNCH_CHECK();
+}
+void launch_scatter_flat(mcb_ctx* ctx, const void* records, int64_t n, int64_t row0, uint64_t* cand, uint32_t* cnt, int32_t cap)
+{
+    if (n == 0) return;
+    int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->num_sms * 16);
+    scatter_flat_kernel<<<grid, 256, 0, ctx->stream>>>((const uint4*)records, n, (uint32_t)row0, cand, cnt, cap);
     MCB_LAUNCH_CHECK();
 }
 

@@ -51,6 +51,26 @@ class CudaCGraphEngine:
     def knn(self, K, k_expand, rank, world):
         self.g.knn(K, k_expand, rank, world)
 
+    # staged kNN (symmetric schedule): thresholds, record exchange, finish
+    def knn_begin(self, K, k_expand, rank, world):
+        self.g.knn_begin(K, k_expand, rank, world)
+
+    def knn_thr_full(self, world):
+        ptr, rpr = self.g.knn_thr_buffer()
+        return device_view(ptr, world * rpr * 4, torch.float32, self.device)
+
+    def knn_filter(self):
+        return self.g.knn_filter()
+
+    def records_view(self, ptr, n_records):
+        return device_view(ptr, max(n_records, 1) * 16, torch.int32, self.device)[: n_records * 4]
+
+    def knn_recv_buffer(self, n):
+        return self.g.knn_recv_buffer(n)
+
+    def knn_finish(self, n):
+        self.g.knn_finish(n)
+
     def knn_full(self, world):
         ptr, rpr, kc = self.g.knn_buffer()
         return device_view(ptr, world * rpr * kc * 4, torch.int32, self.device)
@@ -73,10 +93,41 @@ class CudaCGraphEngine:
         torch.cuda.synchronize(self.device)
 
 
-def cgraph_sharded(engine, K, k_expand, k_beta, rank, world, group=None, fetch_edges=True):
+def _knn_symmetric(engine, K, k_expand, rank, world, group=None):
+    """kNN stage with every unordered cell pair contracted once across all ranks: each rank takes a share of
+    the symmetric tile list and produces candidate records for rows of every rank; the records travel to
+    their owners in one NCCL all-to-all.  Exchanges: thresholds (all-gather), record counts (all-gather),
+    records (all-to-all)."""
+    engine.knn_begin(K, k_expand, rank, world)
+    thr = engine.knn_thr_full(world)
+    engine.sync()
+    _all_gather_blocks(thr, rank, world, group)
+    engine.sync()
+    send_ptr, counts = engine.knn_filter()
+    dev = thr.device
+    mine = torch.tensor(counts, dtype=torch.int64, device=dev)
+    allc = torch.empty(world * world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allc, mine, group=group)
+    recv_counts = allc.view(world, world)[:, rank].tolist()
+    n_send, n_recv = int(sum(counts)), int(sum(recv_counts))
+    recv_ptr = engine.knn_recv_buffer(n_recv)
+    send_t = engine.records_view(send_ptr, n_send)
+    recv_t = engine.records_view(recv_ptr, n_recv)
+    engine.sync()
+    dist.all_to_all_single(recv_t, send_t, output_split_sizes=[int(c) * 4 for c in recv_counts],
+                           input_split_sizes=[int(c) * 4 for c in counts], group=group)
+    engine.sync()
+    engine.knn_finish(n_recv)
+
+
+def cgraph_sharded(engine, K, k_expand, k_beta, rank, world, group=None, fetch_edges=True, symmetric=True):
     """Runs A5..A7 with rows sharded over `world` ranks.  Returns this rank's (src, dst, w), or the edge
-    count when fetch_edges is False (edges stay on the device)."""
-    engine.knn(K, k_expand, rank, world)
+    count when fetch_edges is False (edges stay on the device).  symmetric=False keeps the exchange-free
+    rectangular schedule (each rank contracts its rows against all columns: twice the tensor work)."""
+    if world > 1 and symmetric and hasattr(engine, "knn_begin"):
+        _knn_symmetric(engine, K, k_expand, rank, world, group)
+    else:
+        engine.knn(K, k_expand, rank, world)
     if world > 1:
         full = engine.knn_full(world)
         engine.sync()
