@@ -696,7 +696,7 @@ static void knn_finish(mcb_cgraph* g, int64_t n_recv)
                 launch_gather_rows(ctx, g->Zf.p, (int64_t)Gpad * sizeof(float), glist.p, B, Af.p);
                 launch_simt_store(ctx, Af.p, nb, g->Zf.p, M, Gpad, Cf.p, ldcf);
             }
-            launch_topk_big(ctx, Cf.p, ldcf, M, fail_list.p + b0, nb, row0, kc_out, Kc, own_col, g->knn_cor.p);
+            launch_topk_big(ctx, Cf.p, ldcf, M, fail_list.p + b0, nb, row0, kc_out, Kc, g->thr_all.p + row0, own_col, g->knn_cor.p);
             MCB_CUDA(cudaStreamSynchronize(ctx->stream));      // gl is reused
         }
     }

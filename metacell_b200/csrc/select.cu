@@ -192,9 +192,10 @@ topk_rows_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SEL_THREADS)
 topk_big_kernel(const float* __restrict__ C, int64_t ldc, int64_t M, const int32_t* __restrict__ rows, int32_t nrows,
-                int64_t row0, int32_t kc_out, int32_t Kc, int32_t* __restrict__ knn_col, float* __restrict__ knn_cor)
+                int64_t row0, int32_t kc_out, int32_t Kc, const float* __restrict__ thr_rows, int32_t np2s,
+                int32_t* __restrict__ knn_col, float* __restrict__ knn_cor)
 {
-    extern __shared__ uint64_t sk[];        // [pow2(kc_out)]
+    extern __shared__ uint64_t sk[];        // [np2s >= pow2(kc_out)]
     __shared__ uint32_t hist[256];
     __shared__ unsigned long long s_prefix, s_thr;
     __shared__ long long s_k;
@@ -212,6 +213,34 @@ topk_big_kernel(const float* __restrict__ C, int64_t ldc, int64_t M, const int32
         }
         if (threadIdx.x == 0) { s_prefix = 0ull; s_k = want - 1; s_done = 0; s_thr = ~0ull; s_fill = 0; }
         __syncthreads();
+        // common case (the row overflowed its candidate capacity): everything wanted lies above the row's filter
+        // threshold, and only a few thousand values do -> collect them in one pass and sort in shared memory
+        if (thr_rows) {
+            const float t = thr_rows[lrow];
+            for (int64_t j0 = 0; j0 < M; j0 += SEL_THREADS) {
+                const int64_t j = j0 + threadIdx.x;
+                const bool in = j < M && j != self && c[j] >= t;
+                if (in) { const int pos = atomicAdd(&s_fill, 1); if (pos < np2s) sk[pos] = cand_key(c[j], (uint32_t)j); }
+            }
+            __syncthreads();
+            const int got = s_fill;
+            __syncthreads();
+            if (got >= want && got <= np2s) {
+                const int np2 = next_pow2(got < 2 ? 2 : got);
+                for (int tq = got + threadIdx.x; tq < np2; tq += SEL_THREADS) sk[tq] = ~0ull;
+                __syncthreads();
+                bitonic_sort_u64<SEL_THREADS>(sk, np2);
+                for (int tq = threadIdx.x; tq < Kc; tq += SEL_THREADS) {
+                    if (tq == 0) { oc[0] = (int32_t)self; ov[0] = 1.0f; }
+                    else if (tq < kc_out) { const uint64_t k = sk[tq - 1]; oc[tq] = (int32_t)cand_key_col(k); ov[tq] = cand_key_cor(k); }
+                    else { oc[tq] = -1; ov[tq] = 0.0f; }
+                }
+                __syncthreads();
+                continue;
+            }
+            if (threadIdx.x == 0) s_fill = 0;
+            __syncthreads();
+        }
         for (int pass = 0; pass < 8; ++pass) {
             const int shift = 56 - 8 * pass;
             const unsigned long long decided = pass == 0 ? 0ull : (~0ull << (shift + 8));
@@ -436,10 +465,11 @@ void launch_compact_flags(mcb_ctx* ctx, const int32_t* flag, int64_t n, int32_t*
 }
 
 void launch_topk_big(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t M, const int32_t* rows, int32_t nrows,
-                     int64_t row0, int32_t kc_out, int32_t Kc, int32_t* knn_col, float* knn_cor)
+                     int64_t row0, int32_t kc_out, int32_t Kc, const float* thr_rows, int32_t* knn_col, float* knn_cor)
 {
     if (nrows == 0) return;
     int np2 = 2; while (np2 < kc_out) np2 <<= 1;
+    if (thr_rows) np2 = std::max(np2, 4096);
     const size_t smem = (size_t)np2 * sizeof(uint64_t);
     MCB_CHECK(smem <= 200 * 1024, "topk_big: Kc too large for shared memory");
     static size_t configured = 0;
@@ -447,7 +477,7 @@ void launch_topk_big(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t M, const
         MCB_CUDA(cudaFuncSetAttribute(topk_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    topk_big_kernel<<<nrows, SEL_THREADS, smem, ctx->stream>>>(C, ldc, M, rows, nrows, row0, kc_out, Kc, knn_col, knn_cor);
+    topk_big_kernel<<<nrows, SEL_THREADS, smem, ctx->stream>>>(C, ldc, M, rows, nrows, row0, kc_out, Kc, thr_rows, np2, knn_col, knn_cor);
     MCB_LAUNCH_CHECK();
 }
 
