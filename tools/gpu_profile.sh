@@ -8,7 +8,7 @@ $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_list.log 2>&1
 echo "list exit $?"
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:tc_cor_kernelILi3ELi2 -s 1 -c 1 \
+ncu --set full --clock-control none --import-source on --kernel-name-base mangled -k regex:tc_cor2_kernelILi2 -s 1 -c 1 \
     -o gpurun_out/${TAG}_prof_tc -f $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "full exit $?"
 ls -la gpurun_out | tail -8
