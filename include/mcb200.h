@@ -141,6 +141,11 @@ int  mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* sr
                      const uint64_t* seeds, int32_t min_mc_size, double cooling, int32_t burn_in,
                      int32_t max_sweeps, int32_t rank, int32_t nranks, mcb_coclust** out);
 void mcb_coclust_destroy(mcb_coclust* c);
+/* tgs_graph_cover(edges, min_mc_size, cooling, burn_in) (R/mc_graphcov.r:27, R/mc_from_coclust.r:247): one cover over
+ * all N nodes.  host_cluster[v] = 0 for outliers (R/mc_graphcov.r:28), otherwise a cluster id >= 1.            */
+int  mcb_graph_cover(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst, const double* w,
+                     int32_t min_mc_size, double cooling, int32_t burn_in, int32_t max_sweeps, uint64_t seed,
+                     int32_t* host_cluster /* [N] */, int32_t* n_sweeps);
 /* device buffers for the NCCL reduce: uint32 cnt[N][N] (upper triangle) and int32 nsamp[N]     */
 int  mcb_coclust_buffers(mcb_coclust* c, void** dev_cnt, void** dev_nsamp);
 /* per-resample cluster assignment of this rank's resamples (debug / parity): mc[r][v] in

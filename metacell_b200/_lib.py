@@ -21,7 +21,7 @@ SYMBOLS = [
     "mcb_cgraph_knn_filter", "mcb_cgraph_knn_recv_buffer", "mcb_cgraph_knn_finish", "mcb_cgraph_knn_buffer",
     "mcb_cgraph_download_knn", "mcb_cgraph_knn_stats", "mcb_cgraph_mutual", "mcb_cgraph_thr_buffer",
     "mcb_cgraph_prune", "mcb_cgraph_edges", "mcb_cgraph_debug_cor", "mcb_cgraph_bknn", "mcb_free",
-    "mcb_coclust_run", "mcb_coclust_destroy", "mcb_coclust_buffers", "mcb_coclust_assignments",
+    "mcb_coclust_run", "mcb_graph_cover", "mcb_coclust_destroy", "mcb_coclust_buffers", "mcb_coclust_assignments",
     "mcb_coclust_extract", "mcb_coclust_pairs",
 ]
 
@@ -394,3 +394,16 @@ class CoClust:
         check(lib().mcb_coclust_pairs(self.h, ptr(n1, C.c_int32), ptr(n2, C.c_int32), ptr(cnt, C.c_int32),
                                       ptr(samples, C.c_int32)))
         return n1[:n], n2[:n], cnt[:n], samples
+
+
+def graph_cover(ctx, N, src, dst, w, min_mc_size, cooling, burn_in, seed, max_sweeps=1000):
+    """mcb_graph_cover: one cover over all nodes; returns (cluster[N] with 0 = outlier, sweeps)."""
+    src = as_c(src, np.int32)
+    dst = as_c(dst, np.int32)
+    w = as_c(w, np.float64)
+    out = np.zeros(N, dtype=np.int32)
+    sw = C.c_int32(0)
+    check(lib().mcb_graph_cover(ctx.h, C.c_int32(N), C.c_int64(src.size), ptr(src, C.c_int32), ptr(dst, C.c_int32),
+                                ptr(w, C.c_double), C.c_int32(min_mc_size), C.c_double(cooling), C.c_int32(burn_in),
+                                C.c_int32(max_sweeps), C.c_uint64(int(seed)), ptr(out, C.c_int32), C.byref(sw)))
+    return out, int(sw.value)

@@ -17,6 +17,11 @@ Mirrored entry points (reference file:line):
     mcell_add_cgraph_from_mat_bknn             R/cgraph_knn.r:10-25
     tgs_graph_cover_resample                   tgstat call at R/coclust_graph_cov.r:41
     mcell_coclust_from_graph_resamp            R/coclust_graph_cov.r:13-58
+and, as the first callers on either side of the path:
+    tgs_graph_cover                            tgstat call at R/mc_graphcov.r:27, R/mc_from_coclust.r:247
+    mcell_add_mc_from_graph                    R/mc_graphcov.r:9-41 (up to the cluster assignment)
+    mcell_coclust_filt_by_k_deg                R/coclust.r:58-84
+    mcell_mc_from_coclust_balanced             R/mc_from_coclust.r:215-263 (up to the cluster assignment)
 """
 import os
 import pickle
@@ -380,3 +385,89 @@ def mcell_coclust_from_graph_resamp(coc_id, graph_id, min_mc_size, p_resamp, n_r
     coc = tgCoClust(graph_id, resamp["co_cluster"], resamp["samples"])
     scdb_add_coclust(coc_id, coc)
     return coc
+
+
+# ------------------------------------------------------------------------------------------------
+# SURVEY 8f, first "next" rows: the single graph cover and the callers immediately after the path.
+# Building the tgMCCov object (footprints etc., R/mc.r) is out of scope: these return the assignment.
+# ------------------------------------------------------------------------------------------------
+def tgs_graph_cover(edges, min_mc_size, cooling, burn_in, n_nodes=None, seed=None, ctx=None, max_sweeps=1000):
+    """tgstat call of reference R/mc_graphcov.r:27: edges = dict col1, col2, weight (0-based codes).
+    Returns dict(node, cluster) with cluster 0 = outlier (R/mc_graphcov.r:28)."""
+    ctx = _ctx(ctx)
+    src, dst, w = edges["col1"], edges["col2"], edges["weight"]
+    N = int(n_nodes if n_nodes is not None else max(int(np.max(src)), int(np.max(dst))) + 1)
+    cluster, _ = _lib.graph_cover(ctx, N, src, dst, w, int(min_mc_size), float(cooling), int(burn_in),
+                                  get_param("mc_rseed") if seed is None else seed, max_sweeps)
+    return {"node": np.arange(N, dtype=np.int32), "cluster": cluster}
+
+
+def _mc_from_cover(node_clust, cell_names):
+    f_outlier = node_clust["cluster"] == 0
+    outliers = [cell_names[i] for i in node_clust["node"][f_outlier]]
+    _, mc = np.unique(node_clust["cluster"][~f_outlier], return_inverse=True)          # as.integer(as.factor(cluster))
+    names = [cell_names[i] for i in node_clust["node"][~f_outlier]]
+    return {"mc": dict(zip(names, (mc + 1).tolist())), "outliers": outliers}
+
+
+def mcell_add_mc_from_graph(mc_id, graph_id, mat_id, min_mc_size, ctx=None):
+    """reference R/mc_graphcov.r:9-41 up to the cluster assignment (the tgMCCov object itself is out of scope)."""
+    graph = scdb_cgraph(graph_id)
+    if graph is None:
+        raise McbError(f"MC-ERR: cell graph id {graph_id} is missing when running add_mc_from_graph")
+    mat = scdb_mat(mat_id)
+    if mat is None:
+        raise McbError(f"MC-ERR: mat id {mat_id} is missing when running add_mc_from_graph")
+    _message("running graph clustering now - one iteration no bootstrap")
+    edges = {"col1": graph.edges["mc1"], "col2": graph.edges["mc2"], "weight": graph.edges["w"]}
+    node_clust = tgs_graph_cover(edges, min_mc_size, get_param("scm_tgs_clust_cool"), get_param("scm_tgs_clust_burn_in"),
+                                 n_nodes=len(graph.cell_names), ctx=ctx)
+    res = _mc_from_cover(node_clust, mat.cells)
+    _message(f"building metacell object, #mc {max(res['mc'].values()) if res['mc'] else 0}")
+    _scdb_add("mc", mc_id, res)
+    return res
+
+
+def mcell_coclust_filt_by_k_deg(coc_id, K, alpha):
+    """reference R/coclust.r:58-84: boolean filter over the co-cluster rows.  thresh_K[node] = number of distinct
+    count levels v (over the whole table) for which the node has more than K incident rows with cnt >= v; a row is
+    kept when thresh_K of either endpoint is below cnt * alpha.  Host logic, as in the reference."""
+    coc = scdb_coclust(coc_id)
+    if coc is None:
+        raise McbError(f"MC-ERR: coclust {coc_id} is missing when trying to derive K-deg filter")
+    n1, n2, cnt = coc.coclust["node1"], coc.coclust["node2"], coc.coclust["cnt"]
+    nnodes = coc.n_samp.size
+    levels = np.unique(cnt)                                                 # columns of table(), ascending
+    lev = np.searchsorted(levels, cnt)
+    deg_wgt = np.zeros((nnodes, levels.size), dtype=np.int64)
+    np.add.at(deg_wgt, (n1, lev), 1)
+    np.add.at(deg_wgt, (n2, lev), 1)
+    deg_cum = np.cumsum(deg_wgt[:, ::-1], axis=1)                          # cumsum(rev(x))
+    thresh = (deg_cum > K).sum(axis=1).astype(np.float64)
+    present = deg_wgt.sum(axis=1) > 0
+    thresh[~present] = np.nan                                               # nodes absent from the table stay NA in R
+    with np.errstate(invalid="ignore"):
+        return (thresh[n1] < cnt * alpha) | (thresh[n2] < cnt * alpha)
+
+
+def mcell_mc_from_coclust_balanced(mc_id, coc_id, mat_id, K, min_mc_size, alpha=2, ctx=None):
+    """reference R/mc_from_coclust.r:215-263 up to the cluster assignment."""
+    coc = scdb_coclust(coc_id)
+    if coc is None:
+        raise McbError(f"MC-ERR: coclust {coc_id} is missing when running mc from coclust")
+    mat = scdb_mat(mat_id)
+    if mat is None:
+        raise McbError(f"MC-ERR: mat id {mat_id} is missing when running add_mc_from_graph")
+    filt = mcell_coclust_filt_by_k_deg(coc_id, K, alpha)
+    n1, n2, cnt = (coc.coclust[k][filt] for k in ("node1", "node2", "cnt"))
+    _message(f"filtered {filt.size - int(filt.sum())} left with {int(filt.sum())} based on co-cluster imbalance")
+    w = cnt / float(cnt.max()) if cnt.size else cnt.astype(np.float64)
+    keep = n1 != n2                                                         # :241
+    n1, n2, w = n1[keep], n2[keep], w[keep]
+    edges = {"col1": np.concatenate([n1, n2]), "col2": np.concatenate([n2, n1]), "weight": np.concatenate([w, w])}   # :242-245
+    node_clust = tgs_graph_cover(edges, min_mc_size, get_param("scm_tgs_clust_cool"), get_param("scm_tgs_clust_burn_in"),
+                                 n_nodes=coc.n_samp.size, ctx=ctx)
+    res = _mc_from_cover(node_clust, mat.cells)
+    _message(f"building metacell object, #mc {max(res['mc'].values()) if res['mc'] else 0}")
+    _scdb_add("mc", mc_id, res)
+    return res

@@ -1074,6 +1074,32 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
     *out = c.release();
     MCB_API_END
 }
+// tgs_graph_cover(edges, min_mc_size, cooling, burn_in) (reference call sites R/mc_graphcov.r:27,
+// R/mc_from_coclust.r:247): ONE cover over all nodes.  cluster[v] = 0 for outliers (R/mc_graphcov.r:28),
+// 1..n for covered nodes (ids are the cover's seeding order, not compacted).
+extern "C" int mcb_graph_cover(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst,
+                               const double* w, int32_t min_mc_size, double cooling, int32_t burn_in, int32_t max_sweeps,
+                               uint64_t seed, int32_t* host_cluster, int32_t* n_sweeps)
+{
+    mcb_coclust* c = nullptr;
+    int rc = 0;
+    {
+        if (!host_cluster || N < 1) { mcb::set_error("mcb_graph_cover: bad argument"); return 1; }
+        std::vector<int32_t> all((size_t)N);
+        for (int32_t v = 0; v < N; ++v) all[v] = v;
+        rc = mcb_coclust_run(ctx, N, n_edges, src, dst, w, 1, N, all.data(), &seed, min_mc_size, cooling, burn_in, max_sweeps,
+                             0, 1, &c);
+    }
+    if (rc) return rc;
+    int32_t nl = 0, sw = 0;
+    rc = mcb_coclust_assignments(c, host_cluster, &sw, &nl);
+    mcb_coclust_destroy(c);
+    if (rc) return rc;
+    for (int32_t v = 0; v < N; ++v) host_cluster[v] = host_cluster[v] < 0 ? 0 : host_cluster[v] + 1;
+    if (n_sweeps) *n_sweeps = sw;
+    return 0;
+}
+
 extern "C" void mcb_coclust_destroy(mcb_coclust* c)
 {
     if (!c) return;

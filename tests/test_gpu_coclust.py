@@ -81,3 +81,29 @@ def test_api_mirror_coclust(ctx, oracle, tmp_path):
         api.mcell_coclust_from_graph_resamp("coc2", "missing", 8, 0.75, 5, ctx=ctx)
     with pytest.raises(api.McbError, match="MC-ERR"):
         api.tgCoClust("missing", coc.coclust, coc.n_samp)
+
+
+def test_single_graph_cover_and_mc_from_coclust(ctx, oracle, tmp_path):
+    """tgs_graph_cover (reference R/mc_graphcov.r:27) == one oracle cover over all nodes, and the two callers after the
+    path (mcell_add_mc_from_graph, mcell_mc_from_coclust_balanced) run through the mirror"""
+    from metacell_b200 import api, _lib
+    ncells = 700
+    src, dst, w = _graph(oracle, ncells, 12)
+    cluster, sweeps = _lib.graph_cover(ctx, ncells, src, dst, w, 8, 1.05, 10, 42)
+    csr = oracle.graph_to_csr(ncells, src, dst, w)
+    omc, osw = oracle.graph_cover(ncells, csr, np.arange(ncells, dtype=np.int32), 8, 1.05, 10, 42)
+    assert sweeps == osw and np.array_equal(cluster, np.where(omc < 0, 0, omc + 1))
+    api.scdb_init(str(tmp_path), force_reinit=True)
+    cells = [f"c{i}" for i in range(ncells)]
+    api.scdb_add_mat("m", api.tgScMat([0] * (ncells + 1), [], [], genes=["g"], cells=cells))
+    api.scdb_add_cgraph("g", api.tgCellGraph({"mc1": src, "mc2": dst, "w": w}, cells))
+    res = api.mcell_add_mc_from_graph("mc1", "g", "m", 8, ctx=ctx)
+    assert len(res["mc"]) + len(res["outliers"]) == ncells
+    assert sorted(set(res["mc"].values())) == list(range(1, max(res["mc"].values()) + 1))      # as.integer(as.factor())
+    coc = api.mcell_coclust_from_graph_resamp("coc", "g", 8, 0.75, 20, ctx=ctx)
+    filt = api.mcell_coclust_filt_by_k_deg("coc", 10, 2)
+    assert filt.dtype == bool and filt.size == coc.coclust["cnt"].size and 0 < filt.sum() <= filt.size
+    res2 = api.mcell_mc_from_coclust_balanced("mc2", "coc", "m", 10, 8, alpha=2, ctx=ctx)
+    assert len(res2["mc"]) + len(res2["outliers"]) == ncells and len(res2["mc"]) > ncells // 2
+    with pytest.raises(api.McbError, match="MC-ERR"):
+        api.mcell_mc_from_coclust_balanced("mc3", "nope", "m", 10, 8, ctx=ctx)

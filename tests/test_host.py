@@ -81,3 +81,33 @@ def test_synth_shapes():
     m = synth.make_umi_matrix(300, 200, n_types=5, median_umis=1000.0, seed=1)
     assert m.indptr.size == 301 and m.indices.max() < 200 and m.data.min() >= 1
     assert abs(np.median(m.col_sums()) / 1000.0 - 1.0) < 0.5
+
+
+def test_coclust_filt_by_k_deg_matches_r_logic(tmp_path):
+    """mcell_coclust_filt_by_k_deg against a literal loop restatement of R/coclust.r:58-84"""
+    from metacell_b200 import api
+    rng = np.random.default_rng(5)
+    nn = 40
+    pairs = [(a, b) for a in range(nn) for b in range(a + 1, nn) if rng.random() < 0.3]
+    n1 = np.array([p[0] for p in pairs]); n2 = np.array([p[1] for p in pairs])
+    cnt = rng.integers(1, 12, size=len(pairs))
+    api.scdb_init(str(tmp_path), force_reinit=True)
+    api.scdb_add_cgraph("g", api.tgCellGraph({"mc1": n1, "mc2": n2, "w": np.ones(len(pairs))}, [f"c{i}" for i in range(nn)]))
+    api.scdb_add_coclust("coc", api.tgCoClust("g", {"node1": n1, "node2": n2, "cnt": cnt}, np.full(nn, 20)))
+    K, alpha = 4, 2
+    got = api.mcell_coclust_filt_by_k_deg("coc", K, alpha)
+    levels = sorted(set(cnt.tolist()))
+    thresh = {}
+    for v in range(nn):
+        mine = [c for a, b, c in zip(n1, n2, cnt) if a == v or b == v]
+        if not mine:
+            continue
+        cum, t = 0, 0
+        for lv in reversed(levels):                     # cumsum(rev(table row))
+            cum += sum(1 for c in mine if c == lv)
+            t += cum > K
+        thresh[v] = t
+    exp = np.array([(thresh[a] < c * alpha) or (thresh[b] < c * alpha) for a, b, c in zip(n1, n2, cnt)])
+    assert np.array_equal(got, exp)
+    with pytest.raises(api.McbError, match="MC-ERR"):
+        api.mcell_coclust_filt_by_k_deg("nope", K, alpha)
