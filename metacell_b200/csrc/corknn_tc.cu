@@ -395,9 +395,12 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::NSTAGE * Cfg::STAGE_BYTES);
     uint64_t* full_bar = bars;                       // [NSTAGE]
     uint64_t* empty_bar = bars + Cfg::NSTAGE;        // [NSTAGE]
-    uint64_t* tfull_bar = bars + 2 * Cfg::NSTAGE;    // accumulators complete -> epilogue
-    uint64_t* tempty_bar = bars + 2 * Cfg::NSTAGE + 1;   // epilogue drained -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::NSTAGE + 2);
+    // NPASS == 1 needs only one 256-column accumulator per tile, so it double-buffers TMEM (tile t drains while
+    // tile t + 1 accumulates); NPASS == 3 fills all 512 columns with main + cross and uses buffer 0 only
+    constexpr int NACC = NPASS == 1 ? 2 : 1;
+    uint64_t* tfull_bar = bars + 2 * Cfg::NSTAGE;        // [2] accumulators complete -> epilogue
+    uint64_t* tempty_bar = bars + 2 * Cfg::NSTAGE + 2;   // [2] epilogue drained -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::NSTAGE + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // work units are "cluster tiles": CM vertically adjacent row tiles x one column tile
@@ -410,7 +413,7 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         prefetch_tensormap(&map_a_hi); prefetch_tensormap(&map_b_hi);
         if (NPASS == 3) { prefetch_tensormap(&map_a_lo); prefetch_tensormap(&map_b_lo); }
         for (int s = 0; s < Cfg::NSTAGE; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CM); }
-        mbar_init(tfull_bar, 1); mbar_init(tempty_bar, EPI_WARPS);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull_bar[a], 1); mbar_init(&tempty_bar[a], EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -463,8 +466,7 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16(BM, BN);
             int stage = 0; uint32_t phase = 0;
-            uint32_t tphase = 0;
-            const uint32_t d_main = tmem_base, d_cross = tmem_base + (uint32_t)BN;
+            int it = 0;
             TileIter iter = iter0;
             for (int l = unit0; l < prm.local_tiles; l += unit_stride) {
                 const int tile = part_tile(prm, l);
@@ -473,7 +475,11 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     iter.coords(tile, m_blk, n_blk);
                     if (below_diagonal<MODE, CM>(m_blk * CM + crank, n_blk)) continue;
                 }
-                mbar_wait(tempty_bar, tphase ^ 1);
+                const int acc = it % NACC;
+                const uint32_t tphase = (uint32_t)(it / NACC) & 1u;
+                ++it;
+                const uint32_t d_main = tmem_base + (uint32_t)(acc * BN), d_cross = tmem_base + (uint32_t)BN;
+                mbar_wait(&tempty_bar[acc], tphase ^ 1);
                 tc_fence_after();
                 for (int kb = 0; kb < prm.num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
@@ -498,8 +504,7 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     else tc_commit_mc(&empty_bar[stage], (uint16_t)((1u << CM) - 1u));
                     if (++stage == Cfg::NSTAGE) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tfull_bar);                      // accumulators complete -> epilogue
-                tphase ^= 1;
+                tc_commit(&tfull_bar[acc]);                // accumulators complete -> epilogue
             }
         }
     }
@@ -508,27 +513,29 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         // ===== epilogue warps 4..11 : TMEM lanes (warp % 4) * 32 .. + 31, column half (warp - 4) / 4 =====
         const int quarter = warp & 3;
         const int half = (warp - EPI_WARP0) >> 2;
-        uint32_t tphase = 0;
+        int it = 0;
         TileIter iter = iter0;
         float* tcol = reinterpret_cast<float*>(tmem_slot + 4) + (warp - EPI_WARP0) * (BN / 2);    // per-warp column thresholds (MODE 2)
         uint32_t chunk_id = 0, fill = 0;          // this warp's open record chunk (warp-uniform)
         bool have_chunk = false;
         for (int l = unit0; l < prm.local_tiles; l += unit_stride) {
-                const int tile = part_tile(prm, l);
+            const int tile = part_tile(prm, l);
             int m_blk, n_blk;
             iter.coords(tile, m_blk, n_blk);
             m_blk = m_blk * CM + crank;
             if (below_diagonal<MODE, CM>(m_blk, n_blk)) continue;
-            auto release = [&]() { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(tempty_bar); };
+            const int acc = it % NACC;
+            const uint32_t tphase = (uint32_t)(it / NACC) & 1u;
+            ++it;
+            auto release = [&]() { tc_fence_before(); __syncwarp(); if (lane == 0) mbar_arrive(&tempty_bar[acc]); };
             if (MODE == 0) {
-                epilogue_tile<NPASS, MODE>(prm, tmem_base, quarter, half, lane, m_blk, n_blk, tcol, tfull_bar, tphase,
-                                           chunk_id, fill, have_chunk);
+                epilogue_tile<NPASS, MODE>(prm, tmem_base + (uint32_t)(acc * BN), quarter, half, lane, m_blk, n_blk, tcol,
+                                           &tfull_bar[acc], tphase, chunk_id, fill, have_chunk);
                 release();
             } else {
-                epilogue_filter_tile<(MODE == 0 ? 1 : MODE)>(prm, tmem_base, quarter, half, lane, m_blk, n_blk, tcol, tfull_bar,
+                epilogue_filter_tile<(MODE == 0 ? 1 : MODE)>(prm, tmem_base, quarter, half, lane, m_blk, n_blk, tcol, &tfull_bar[acc],
                                                              tphase, chunk_id, fill, have_chunk, release);
             }
-            tphase ^= 1;
         }
         if (MODE >= 1 && have_chunk && lane == 0 && chunk_id < prm.pool_chunks) prm.chunk_fill[chunk_id] = fill;
     }

@@ -394,6 +394,121 @@ void launch_sample_threshold(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t 
     MCB_LAUNCH_CHECK();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Same result with less sorting: the row holds ~1.5 x the wanted number of candidates, so a monotone
+// 2048-bin histogram of the keys first finds the bin of the (kc_out-1)-th best; only the keys up to that
+// bin (a handful more than wanted) are compacted and sorted with the smaller IPT_OUT network.  Falls back
+// to sorting everything when ties make the selected set exceed 256 * IPT_OUT keys.
+// ---------------------------------------------------------------------------------------------
+constexpr int TOPK_BINS = 2048;
+
+template <int IPT_IN, int IPT_OUT>
+__global__ void __launch_bounds__(SEL_THREADS)
+topk_select_rows_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, int32_t cap, int64_t row0,
+                        int64_t rows, int32_t kc_out, int32_t Kc, int32_t* __restrict__ knn_col, float* __restrict__ knn_cor,
+                        int32_t* __restrict__ fail_flag)
+{
+    extern __shared__ uint64_t sk[];        // [256 * IPT_IN]
+    __shared__ uint32_t hist[TOPK_BINS];
+    __shared__ uint32_t s_min[SEL_THREADS / 32], s_max[SEL_THREADS / 32];
+    __shared__ int s_bin, s_total, s_n;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        const uint32_t n = cnt[row];
+        int32_t* oc = knn_col + row * (int64_t)Kc;
+        float* ov = knn_cor + row * (int64_t)Kc;
+        if (n > (uint32_t)cap || (int64_t)n < (int64_t)kc_out - 1) {
+            if (threadIdx.x == 0) fail_flag[row] = 1;
+            continue;
+        }
+        if (threadIdx.x == 0) { fail_flag[row] = 0; s_n = 0; }
+        const int want = kc_out - 1;
+        const uint64_t* src = cand + row * (int64_t)cap;
+        uint64_t key[IPT_IN];
+        uint32_t kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+        for (int r = 0; r < IPT_IN; ++r) {
+            const int e = r * SEL_THREADS + threadIdx.x;          // coalesced; order is irrelevant before the sort
+            key[r] = e < (int)n ? src[e] : ~0ull;
+            if (e < (int)n) { const uint32_t h = (uint32_t)(key[r] >> 32); kmin = min(kmin, h); kmax = max(kmax, h); }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+            kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+        }
+        if (lane == 0) { s_min[wid] = kmin; s_max[wid] = kmax; }
+        for (int b = threadIdx.x; b < TOPK_BINS; b += SEL_THREADS) hist[b] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < SEL_THREADS / 32; ++w) { kmin = min(kmin, s_min[w]); kmax = max(kmax, s_max[w]); }
+        int shift = 0;
+        while (((kmax - kmin) >> shift) >= (uint32_t)TOPK_BINS) ++shift;
+#pragma unroll
+        for (int r = 0; r < IPT_IN; ++r)
+            if (key[r] != ~0ull) atomicAdd(&hist[((uint32_t)(key[r] >> 32) - kmin) >> shift], 1u);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int b = 0; long long before = 0;
+            if (want > 0) warp_find_bucket<TOPK_BINS / 32>(hist, (long long)(want - 1), b, before);
+            if (threadIdx.x == 0) { s_bin = b; s_total = want > 0 ? (int)before + (int)hist[b] : 0; }
+        }
+        __syncthreads();
+        const int bsel = s_bin, total = s_total;
+        if (total <= 256 * IPT_OUT) {
+            // compact the keys of the bins up to bsel (warp-aggregated positions), pad, sort the short list
+#pragma unroll
+            for (int r = 0; r < IPT_IN; ++r) {
+                const bool in = key[r] != ~0ull && (int)((((uint32_t)(key[r] >> 32) - kmin) >> shift)) <= bsel;
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                int base = 0;
+                if (lane == 0 && m) base = atomicAdd(&s_n, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (in) sk[base + __popc(m & ((1u << lane) - 1u))] = key[r];
+            }
+            __syncthreads();
+            for (int q = total + threadIdx.x; q < 256 * IPT_OUT; q += SEL_THREADS) sk[q] = ~0ull;
+            __syncthreads();
+            uint64_t k2[IPT_OUT];
+#pragma unroll
+            for (int r = 0; r < IPT_OUT; ++r) k2[r] = sk[r * SEL_THREADS + threadIdx.x];
+            __syncthreads();
+            bitonic_sort_regs_u64<IPT_OUT>(k2, sk);
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < IPT_OUT; ++r) sk[threadIdx.x * IPT_OUT + r] = k2[r];
+        } else {
+            bitonic_sort_regs_u64<IPT_IN>(key, sk);
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < IPT_IN; ++r) sk[threadIdx.x * IPT_IN + r] = key[r];
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < Kc; q += SEL_THREADS) {
+            if (q == 0) { oc[0] = (int32_t)(row0 + row); ov[0] = 1.0f; }
+            else if (q < kc_out) { const uint64_t k = sk[q - 1]; oc[q] = (int32_t)cand_key_col(k); ov[q] = cand_key_cor(k); }
+            else { oc[q] = -1; ov[q] = 0.0f; }
+        }
+        __syncthreads();
+    }
+}
+
+template <int IPT_IN, int IPT_OUT>
+static void launch_topk_select_t(mcb_ctx* ctx, const uint64_t* cand, const uint32_t* cnt, int32_t cap, int64_t row0,
+                                 int64_t rows, int32_t kc_out, int32_t Kc, int32_t* knn_col, float* knn_cor, int32_t* fail_flag)
+{
+    const size_t smem = (size_t)IPT_IN * 256 * sizeof(uint64_t);
+    static bool configured = false;
+    if (!configured && smem > 40 * 1024) {
+        MCB_CUDA(cudaFuncSetAttribute(topk_select_rows_kernel<IPT_IN, IPT_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
+    topk_select_rows_kernel<IPT_IN, IPT_OUT><<<grid, SEL_THREADS, smem, ctx->stream>>>(cand, cnt, cap, row0, rows, kc_out, Kc,
+                                                                                        knn_col, knn_cor, fail_flag);
+    MCB_LAUNCH_CHECK();
+}
+
 template <int IPT>
 static void launch_topk_rows_t(mcb_ctx* ctx, const uint64_t* cand, const uint32_t* cnt, int32_t cap, int64_t row0,
                                int64_t rows, int32_t kc_out, int32_t Kc, int32_t* knn_col, float* knn_cor, int32_t* fail_flag)
@@ -415,6 +530,11 @@ void launch_topk_rows(mcb_ctx* ctx, const uint64_t* cand, const uint32_t* cnt, i
 {
     if (rows == 0) return;
     MCB_CHECK(cap <= 4096, "MC-ERR: K * k_expand is too large relative to the number of cells for this build");
+    // select-then-sort when the wanted list fits a sorting network half (or less) the size of the candidate capacity
+    const int want = kc_out - 1 + 16;       // a little room for the boundary bin
+    if (cap > 1024 && cap <= 2048 && want <= 1024) { launch_topk_select_t<8, 4>(ctx, cand, cnt, cap, row0, rows, kc_out, Kc, knn_col, knn_cor, fail_flag); return; }
+    if (cap > 2048 && want <= 1024) { launch_topk_select_t<16, 4>(ctx, cand, cnt, cap, row0, rows, kc_out, Kc, knn_col, knn_cor, fail_flag); return; }
+    if (cap > 2048 && want <= 2048) { launch_topk_select_t<16, 8>(ctx, cand, cnt, cap, row0, rows, kc_out, Kc, knn_col, knn_cor, fail_flag); return; }
     if (cap <= 512) launch_topk_rows_t<2>(ctx, cand, cnt, cap, row0, rows, kc_out, Kc, knn_col, knn_cor, fail_flag);
     else if (cap <= 1024) launch_topk_rows_t<4>(ctx, cand, cnt, cap, row0, rows, kc_out, Kc, knn_col, knn_cor, fail_flag);
     else if (cap <= 2048) launch_topk_rows_t<8>(ctx, cand, cnt, cap, row0, rows, kc_out, Kc, knn_col, knn_cor, fail_flag);
