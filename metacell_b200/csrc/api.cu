@@ -855,7 +855,7 @@ extern "C" int mcb_cgraph_prune(mcb_cgraph* g, int64_t* n_edges)
     g->out_s.alloc(ctx, rk);
     {
         StageTimer t(ctx, "balance_prune");
-        launch_prune(ctx, g->knn_col.p, g->sym.p, g->thr_in.p, g->row0, rows, g->Kc, K, g->out_deg.p, g->out_dst.p, g->out_s.p);
+        launch_prune(ctx, g->knn_col.p, g->sym.p, g->thr_in.p, g->row0, rows, g->Kc, K, (int64_t)g->K * g->K * g->k_expand, g->out_deg.p, g->out_dst.p, g->out_s.p);
     }
     DevBuf<int64_t> deg64(ctx, (size_t)std::max<int64_t>(rows, 1)), offs(ctx, (size_t)std::max<int64_t>(rows, 1)), total(ctx, 1);
     int64_t ne = 0;

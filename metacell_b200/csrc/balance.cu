@@ -18,6 +18,7 @@ namespace mcb {
 
 constexpr int BAL_THREADS = 256;
 constexpr uint32_t HASH_EMPTY = 0xffffffffu;
+constexpr int BAL_BINS = 2048;         // histogram of the rank products s used to select instead of sorting
 
 __device__ __forceinline__ uint32_t hash_slot(uint32_t key, int log2H) { return (key * 2654435761u) >> (32 - log2H); }
 
@@ -67,7 +68,10 @@ mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ 
               int32_t kin, uint32_t* __restrict__ sym, uint64_t* __restrict__ thr_in)
 {
     extern __shared__ uint64_t sk[];        // [256 * IPT]
-    constexpr int NP = 256 * IPT;
+    __shared__ uint32_t hist[BAL_BINS];
+    __shared__ int s_n, s_sel, s_bin, s_before;
+    int bin_shift = 0;
+    while ((smax >> bin_shift) >= BAL_BINS) ++bin_shift;
     for (int64_t lrow = blockIdx.x; lrow < rows; lrow += gridDim.x) {
         const int64_t i = row0 + lrow;
         const int32_t* kc = knn_col + i * (int64_t)Kc;
@@ -92,17 +96,46 @@ mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ 
             }
             key[q] = kv;
         }
-        bitonic_sort_regs_u64<IPT>(key, sk);
-        // thr_in = the kin-th smallest key if more than kin mutual edges exist: needs elements kin-1 and kin
-        __syncthreads();
+        // thr_in = the kin-th smallest key when more than kin mutual edges exist.  A 2048-bin histogram of the
+        // scores s locates its bin; only that bin's few keys are sorted (256-key network).  Ties that overfill
+        // the bin fall back to sorting the whole row.
+        int local = 0;
 #pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            const int e = threadIdx.x * IPT + q;
-            if (e == kin - 1 || e == kin) sk[e - (kin - 1)] = key[q];
-        }
+        for (int q = 0; q < IPT; ++q) local += key[q] != ~0ull;
+        if (threadIdx.x == 0) { s_n = 0; s_sel = 0; }
+        for (int q = threadIdx.x; q < BAL_BINS; q += BAL_THREADS) hist[q] = 0;
         __syncthreads();
-        if (threadIdx.x == 0)
-            thr_in[i] = (kin >= 1 && kin < NP && sk[1] != ~0ull) ? sk[0] : ~0ull;
+        if (local) atomicAdd(&s_n, local);
+#pragma unroll
+        for (int q = 0; q < IPT; ++q) if (key[q] != ~0ull) atomicAdd(&hist[(uint32_t)(key[q] >> 32) >> bin_shift], 1u);
+        __syncthreads();
+        const int n_mut = s_n;
+        uint64_t thr = ~0ull;
+        if (kin >= 1 && n_mut > kin) {
+            if (threadIdx.x < 32) {
+                int bb; long long before;
+                warp_find_bucket<BAL_BINS / 32>(hist, (long long)(kin - 1), bb, before);
+                if (threadIdx.x == 0) { s_bin = bb; s_before = (int)before; }
+            }
+            __syncthreads();
+            const int bsel = s_bin, m = (int)hist[bsel], idx = kin - 1 - s_before;
+            if (m <= 256) {
+#pragma unroll
+                for (int q = 0; q < IPT; ++q)
+                    if (key[q] != ~0ull && (int)((uint32_t)(key[q] >> 32) >> bin_shift) == bsel) sk[atomicAdd(&s_sel, 1)] = key[q];
+                __syncthreads();
+                uint64_t k1[1] = {threadIdx.x < m ? sk[threadIdx.x] : ~0ull};
+                __syncthreads();
+                bitonic_sort_regs_u64<1>(k1, sk);
+                if (threadIdx.x == idx) thr_in[i] = k1[0];
+            } else {
+                bitonic_sort_regs_u64<IPT>(key, sk);
+#pragma unroll
+                for (int q = 0; q < IPT; ++q) if (threadIdx.x * IPT + q == kin - 1) thr_in[i] = key[q];
+            }
+        } else if (threadIdx.x == 0) {
+            thr_in[i] = thr;
+        }
         __syncthreads();
     }
 }
@@ -111,11 +144,14 @@ mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ 
 template <int IPT>
 __global__ void __launch_bounds__(BAL_THREADS)
 prune_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ sym, const uint64_t* __restrict__ thr_in,
-             int64_t row0, int64_t rows, int32_t Kc, int32_t K, int32_t* __restrict__ out_deg,
+             int64_t row0, int64_t rows, int32_t Kc, int32_t K, long long smax, int32_t* __restrict__ out_deg,
              int32_t* __restrict__ out_dst, int32_t* __restrict__ out_s)
 {
     extern __shared__ uint64_t sk[];        // [256 * IPT]
-    __shared__ int s_n;
+    __shared__ uint32_t hist[BAL_BINS];
+    __shared__ int s_n, s_sel, s_bin, s_before;
+    int bin_shift = 0;
+    while ((smax >> bin_shift) >= BAL_BINS) ++bin_shift;
     for (int64_t lrow = blockIdx.x; lrow < rows; lrow += gridDim.x) {
         const int64_t i = row0 + lrow;
         const int32_t* kc = knn_col + i * (int64_t)Kc;
@@ -138,13 +174,44 @@ prune_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ s
             }
             key[q] = kv;
         }
-        if (local) atomicAdd(&s_n, local);
-        bitonic_sort_regs_u64<IPT>(key, sk);
+        for (int q = threadIdx.x; q < BAL_BINS; q += BAL_THREADS) hist[q] = 0;
+        if (threadIdx.x == 0) s_sel = 0;
         __syncthreads();
+        if (local) atomicAdd(&s_n, local);
 #pragma unroll
-        for (int q = 0; q < IPT; ++q) {
-            const int e = threadIdx.x * IPT + q;
-            if (e < K) sk[e] = key[q];
+        for (int q = 0; q < IPT; ++q) if (key[q] != ~0ull) atomicAdd(&hist[(uint32_t)(key[q] >> 32) >> bin_shift], 1u);
+        __syncthreads();
+        // the K best survivors: histogram of s -> bin of the K-th; the keys up to that bin (a few more than K) are
+        // compacted and sorted with the 256-key network; more than 256 of them (ties) -> sort the whole row
+        const int n_surv = s_n;
+        int bsel = BAL_BINS - 1, total = n_surv;
+        if (n_surv > K) {
+            if (threadIdx.x < 32) {
+                int bb; long long before;
+                warp_find_bucket<BAL_BINS / 32>(hist, (long long)(K - 1), bb, before);
+                if (threadIdx.x == 0) { s_bin = bb; s_before = (int)before + (int)hist[bb]; }
+            }
+            __syncthreads();
+            bsel = s_bin; total = s_before;
+        }
+        if (total <= 256 && K <= 256) {
+#pragma unroll
+            for (int q = 0; q < IPT; ++q)
+                if (key[q] != ~0ull && (int)((uint32_t)(key[q] >> 32) >> bin_shift) <= bsel) sk[atomicAdd(&s_sel, 1)] = key[q];
+            __syncthreads();
+            uint64_t k1[1] = {threadIdx.x < total ? sk[threadIdx.x] : ~0ull};
+            __syncthreads();
+            bitonic_sort_regs_u64<1>(k1, sk);
+            __syncthreads();
+            sk[threadIdx.x] = k1[0];
+        } else {
+            bitonic_sort_regs_u64<IPT>(key, sk);
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < IPT; ++q) {
+                const int e = threadIdx.x * IPT + q;
+                if (e < K) sk[e] = key[q];
+            }
         }
         __syncthreads();
         const int n = s_n < K ? s_n : K;
@@ -221,13 +288,13 @@ static void launch_mutual_t(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t
 }
 template <int IPT>
 static void launch_prune_t(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* sym, const uint64_t* thr_in, int64_t row0,
-                           int64_t rows, int32_t Kc, int32_t K, int32_t* out_deg, int32_t* out_dst, int32_t* out_s)
+                           int64_t rows, int32_t Kc, int32_t K, int64_t smax, int32_t* out_deg, int32_t* out_dst, int32_t* out_s)
 {
     static size_t configured = 0;
     const size_t smem = (size_t)IPT * 256 * sizeof(uint64_t);
     ensure_smem(prune_kernel<IPT>, smem, configured);
     int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
-    prune_kernel<IPT><<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, sym, thr_in, row0, rows, Kc, K, out_deg, out_dst, out_s);
+    prune_kernel<IPT><<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, sym, thr_in, row0, rows, Kc, K, (long long)smax, out_deg, out_dst, out_s);
     MCB_LAUNCH_CHECK();
 }
 
@@ -251,11 +318,11 @@ void launch_mutual(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* table, 
 }
 
 void launch_prune(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* sym, const uint64_t* thr_in, int64_t row0,
-                  int64_t rows, int32_t Kc, int32_t K, int32_t* out_deg, int32_t* out_dst, int32_t* out_s)
+                  int64_t rows, int32_t Kc, int32_t K, int64_t smax, int32_t* out_deg, int32_t* out_dst, int32_t* out_s)
 {
     if (rows == 0) return;
     MCB_CHECK(Kc <= 4096, "MC-ERR: K * k_expand above 4096 is not supported");
-#define CALL(I) launch_prune_t<I>(ctx, knn_col, sym, thr_in, row0, rows, Kc, K, out_deg, out_dst, out_s)
+#define CALL(I) launch_prune_t<I>(ctx, knn_col, sym, thr_in, row0, rows, Kc, K, smax, out_deg, out_dst, out_s)
     MCB_DISPATCH_IPT(Kc, CALL);
 #undef CALL
 }

@@ -157,7 +157,7 @@ void launch_mutual(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* table, 
                    int32_t Kc, int32_t H, int32_t rank_bits, int64_t smax, int strict, int keep_self, int32_t kin,
                    uint32_t* sym, uint64_t* thr_in);
 void launch_prune(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* sym, const uint64_t* thr_in, int64_t row0,
-                  int64_t rows, int32_t Kc, int32_t K, int32_t* out_deg, int32_t* out_dst, int32_t* out_s);
+                  int64_t rows, int32_t Kc, int32_t K, int64_t smax, int32_t* out_deg, int32_t* out_dst, int32_t* out_s);
 void launch_widen_i32(mcb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n);
 void launch_emit_edges(mcb_ctx* ctx, const int32_t* out_deg, const int32_t* out_dst, const int64_t* offs,
                        const int32_t* cell_of_row, int64_t row0, int64_t rows, int32_t K, int32_t* src, int32_t* dst,
