@@ -290,18 +290,23 @@ def run_ours(a):
         if world == 1 and not a.no_cpu:
             cb, _, _ = cpu_port(a, m, feats, a.cpu_rows)
             line["cpu_baseline"] = cb
-        if world == 1 and not a.no_coclust:
-            line["coclust"] = bench_coclust(ctx, a)
+    coc = None if a.no_coclust else bench_coclust(ctx, a, rank, world)
+    if rank == 0:
+        if coc is not None:
+            line["coclust"] = coc
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def bench_coclust(ctx, a):
-    """C3: PBMC8k-shaped graph (8,000 cells, K=100), 500 resamples at p=0.75, min_mc_size=20."""
+def bench_coclust(ctx, a, rank=0, world=1):
+    """C3: PBMC8k-shaped graph (8,000 cells, K=100), 500 resamples at p=0.75, min_mc_size=20.  At world > 1 the
+    resamples are strided over the ranks and the counters are reduced to rank 0 over NCCL."""
     import torch
+    import torch.distributed as dist
     from metacell_b200 import _lib, synth
+    from metacell_b200 import dist as mdist
     m = synth.make_umi_matrix(8000, 600, n_types=12, median_umis=3000.0, seed=a.seed + 5)
     csc = _lib.Csc.upload(ctx, m.ngenes, m.indptr, m.indices, m.data.astype(np.float64))
     g = _lib.CGraph.from_csc(ctx, csc, np.arange(600, dtype=np.int32), 7.0)
@@ -310,24 +315,40 @@ def bench_coclust(ctx, a):
     g.destroy(); csc.free()
     sets, seeds = synth.resample_sets(m.ncells, 0.75, 500, 77)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=ctx.device)
-    warm = _lib.CoClust(ctx, m.ncells, src, dst, w, sets, seeds, 20, 1.05, 10)      # warm-up at the timed shape (block cache)
-    warm.pairs()
+
+    def run():
+        cc = _lib.CoClust(ctx, m.ncells, src, dst, w, sets, seeds, 20, 1.05, 10, rank=rank, nranks=world)
+        out = mdist.coclust_sharded(cc, rank, world)
+        return cc, out
+
+    warm, _ = run()                      # warm-up at the timed shape (block cache, NCCL buffers)
     warm.destroy()
-    ctx.set_option("profile", 1); ctx.timings_reset()
+    if rank == 0:
+        ctx.set_option("profile", 1); ctx.timings_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ctx.sync(); e0.record(stream)
-    cc = _lib.CoClust(ctx, m.ncells, src, dst, w, sets, seeds, 20, 1.05, 10)
-    n1, n2, cnt, ns = cc.pairs()
+    ctx.sync(); torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(); torch.cuda.synchronize()
+    e0.record(stream)
+    cc, out = run()
     e1.record(stream); ctx.sync(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    st = ctx.timings(); ctx.set_option("profile", 0)
-    _, sweeps = cc.assignments()
+    if world > 1:
+        dist.barrier(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    res = None
+    if rank == 0:
+        st = ctx.timings(); ctx.set_option("profile", 0)
+        _, sweeps = cc.assignments()
+        res = {"metric": "coclust resamples/sec", "value": 500.0 / (ms * 1e-3), "unit": "resamples/s", "ms": ms, "n_gpus": world,
+               "config": {"workload": "C3: 8,000 cells, balanced K=100 graph, 500 resamples, p=0.75, min_mc_size=20",
+                          "edges": int(src.size), "pairs": int(out[0].size), "mean_sweeps_rank0": float(np.mean(sweeps))},
+               "stages_ms_rank0": {k: round(v[0], 3) for k, v in st.items()},
+               "note": "host edge table in, host (node1,node2,cnt) out on rank 0; graph cover is latency-bound (DESIGN.md)"}
     cc.destroy()
-    return {"metric": "coclust resamples/sec", "value": 500.0 / (ms * 1e-3), "unit": "resamples/s", "ms": ms,
-            "config": {"workload": "C3: 8,000 cells, balanced K=100 graph, 500 resamples, p=0.75, min_mc_size=20",
-                       "edges": int(src.size), "pairs": int(n1.size), "mean_sweeps": float(np.mean(sweeps))},
-            "stages_ms": {k: round(v[0], 3) for k, v in st.items()},
-            "note": "host edge table in, host (node1,node2,cnt) out; graph cover is latency-bound (DESIGN.md)"}
+    return res
 
 
 if __name__ == "__main__":

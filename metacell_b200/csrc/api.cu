@@ -526,7 +526,7 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
         MCB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     // ---- sampling pass: per-row filter threshold from a random column sample -----------------
-    int64_t S = std::min<int64_t>(32768, round_up(ceil_div(128 * M, kc_out), 256));
+    int64_t S = std::min<int64_t>(262144, round_up(ceil_div(128 * M, kc_out), 256));     // ~128 sampled columns above the true cut
     if (S >= M) S = M;
     const int64_t Spad = round_up(S, 256);
     int32_t r_sel = 0, cap = 0;

@@ -35,11 +35,13 @@ class UmiMatrix:
 
 
 def make_umi_matrix(ncells, ngenes, n_types=20, median_umis=3000.0, size_sigma=0.4, dispersion=3.0,
-                    marker_frac=0.05, rare_types=0, seed=0, chunk=8192):
+                    marker_frac=0.05, rare_types=0, seed=0, chunk=8192, cell_seed=None):
     """NB(mean = s_c * mu_g * fold[type_c, g], dispersion r) counts.
 
     mu_g log-normal, s_c log-normal(sigma=size_sigma); every type up-regulates a random
     `marker_frac` of genes 4-16x.  `rare_types` of the types get <0.5% frequency (C5 shape).
+    `cell_seed` (optional) re-seeds the per-cell draws only, so several processes can generate different cell
+    shards of one population (same gene means / type programs from `seed`).
     """
     rng = np.random.default_rng(seed)
     mu = rng.lognormal(mean=0.0, sigma=1.2, size=ngenes)
@@ -49,6 +51,8 @@ def make_umi_matrix(ncells, ngenes, n_types=20, median_umis=3000.0, size_sigma=0
         g = rng.choice(ngenes, size=nmark, replace=False)
         fold[t, g] = 2.0 ** rng.uniform(2.0, 4.0, size=nmark)
     freq = rng.dirichlet(np.full(n_types, 3.0))
+    if cell_seed is not None:
+        rng = np.random.default_rng([seed, cell_seed])
     if rare_types > 0:
         freq[:rare_types] = rng.uniform(0.001, 0.005, size=rare_types)
         freq[rare_types:] *= (1.0 - freq[:rare_types].sum()) / freq[rare_types:].sum()
