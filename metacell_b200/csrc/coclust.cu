@@ -15,6 +15,7 @@
 // global arrays that stay L1/L2 resident.  Latency-bound, neither roofline binds.
 #include "internal.h"
 #include <cstdlib>
+#include <string>
 
 namespace mcb {
 
@@ -484,6 +485,512 @@ graph_cover_fast_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Speculative batch variant.  The sweep is a sequential Gauss-Seidel pass, but after the first sweeps a
+// visit rarely changes anything: the decision for node t+1 equals the one computed from the state before
+// node t unless node t moved.  So B consecutive nodes of the visit order are evaluated concurrently, one
+// per 128-thread sub-block, all against the state at the start of the batch; the first node of the batch
+// whose decision is a move is applied and the batch restarts right after it (later results are dropped).
+// Nodes before the first mover saw exactly the state the sequential pass shows them, so the assignment is
+// bit-identical to graph_cover_fast_kernel / orc_graph_cover; only the wall-clock order of evaluation
+// differs.  Warp arg-max uses redux on the score's bit pattern (scores are positive doubles, so their
+// bits order like unsigned integers) instead of a five-level shuffle tree.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int B, int IN_SLOTS>
+__global__ void __launch_bounds__(128 * B, 8 / B)
+graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict__ resamp_ids, int32_t n_s,
+                         const int32_t* __restrict__ samples, const uint64_t* __restrict__ seeds, int32_t min_size,
+                         double cooling, int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap, int32_t out_warps,
+                         int32_t* __restrict__ mc_all, int32_t* __restrict__ f_all, int32_t* __restrict__ sweeps_out,
+                         int32_t* __restrict__ status)
+{
+    constexpr int FT = 128;            // threads per sub-block (one visited node each)
+    constexpr int NT = FT * B;
+    constexpr int NW = NT / 32;
+    static_assert(4 * B <= 32, "one lane per (node, warp) partial");
+    extern __shared__ uint32_t dsm[];
+    int32_t* size = (int32_t*)dsm;                               // [ncl_cap]
+    uint32_t* wout = dsm + ncl_cap;                              // [B][2][ncl_cap]
+    uint32_t* win = wout + (size_t)2 * B * ncl_cap;              // [B][2][ncl_cap]
+    int32_t* vlist = (int32_t*)(win + (size_t)2 * B * ncl_cap);  // [n_s]
+    int16_t* mc_s = (int16_t*)(vlist + n_s);                     // [N]
+    __shared__ unsigned long long s_part[NT];
+    __shared__ unsigned long long s_pbits[2][B * 4];   // per-(node, warp) partial arg-max, double buffered by batch parity
+    __shared__ int s_pk[2][B * 4];
+    __shared__ int s_pick, s_flag;
+    __shared__ unsigned long long s_total;
+
+    const int N = g.N;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int sb = tid >> 7, ltid = tid & (FT - 1), lwid = ltid >> 5;
+    for (int lr = blockIdx.x; lr < n_local; lr += gridDim.x) {
+        const int rid = resamp_ids[lr];
+        const int32_t* S = samples + (int64_t)rid * n_s;
+        const uint64_t seed = seeds[rid];
+        const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
+        int32_t* f = f_all + (int64_t)lr * N;
+
+        for (int v = tid; v < N; v += NT) { mc_s[v] = -2; f[v] = 0; }
+        for (int k = tid; k < ncl_cap; k += NT) size[k] = 0;
+        for (int k = tid; k < 2 * B * ncl_cap; k += NT) { wout[k] = 0; win[k] = 0; }
+        if (tid < 4 * B) { s_pbits[0][tid] = s_pbits[1][tid] = 0ull; s_pk[0][tid] = s_pk[1][tid] = 0x7fffffff; }
+        __syncthreads();
+        for (int q = tid; q < n_s; q += NT) mc_s[S[q]] = -1;
+        __syncthreads();
+        for (int q = tid; q < n_s; q += NT) {
+            const int v = S[q];
+            int c = 0;
+            for (int e = g.optr[v]; e < g.optr[v + 1]; ++e) c += (mc_s[g.odst[e]] == -1);
+            f[v] = c;
+        }
+        __syncthreads();
+
+        // ---- seeding (as graph_cover_kernel, NT threads) -------------------------------------------
+        int ncl = 0;
+        int err = 0;
+        const int chunk = (n_s + NT - 1) / NT;
+        const int q0 = min(n_s, tid * chunk), q1 = min(n_s, q0 + chunk);
+        for (uint32_t iter = 0;; ++iter) {
+            unsigned long long part = 0;
+            for (int q = q0; q < q1; ++q) {
+                const int v = S[q];
+                const int fv = f[v];
+                if (mc_s[v] == -1 && fv >= min_size && fv > 0) part += (unsigned long long)fv * fv * fv;
+            }
+            s_part[tid] = part;
+            __syncthreads();
+            if (tid < 32) {
+                unsigned long long tot = 0;
+                for (int q = lane; q < NT; q += 32) tot += s_part[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                if (lane == 0) { s_total = tot; s_pick = -1; }
+            }
+            __syncthreads();
+            const unsigned long long total = s_total;
+            if (total == 0) break;
+            if (ncl >= ncl_cap) { err = 3; break; }
+            const unsigned long long r = cover_rng_u64(seed_lo, seed_hi, STREAM_SEED, iter, 0) % total;
+            // exclusive prefix of s_part at tid: warp-level partial sums first, then the tail inside the warp
+            unsigned long long excl = 0;
+            for (int q = 0; q < (tid & ~31); ++q) excl += s_part[q];
+            for (int q = (tid & ~31); q < tid; ++q) excl += s_part[q];
+            if (r >= excl && r < excl + part) {
+                unsigned long long cum = excl;
+                for (int q = q0; q < q1; ++q) {
+                    const int v = S[q];
+                    const int fv = f[v];
+                    if (mc_s[v] == -1 && fv >= min_size && fv > 0) {
+                        cum += (unsigned long long)fv * fv * fv;
+                        if (cum > r) { s_pick = v; break; }
+                    }
+                }
+            }
+            __syncthreads();
+            const int pick = s_pick;
+            const int k = ncl++;
+            if (tid == 0) { mc_s[pick] = (int16_t)k; s_flag = 1; }
+            __syncthreads();
+            const int oe0 = g.optr[pick], oe1 = g.optr[pick + 1];
+            for (int e = oe0 + tid; e < oe1; e += NT) {
+                const int u = g.odst[e];
+                if (mc_s[u] == -1) { mc_s[u] = (int16_t)k; atomicAdd(&s_flag, 1); }
+            }
+            __syncthreads();
+            if (tid == 0) size[k] = s_flag;
+            for (int e = oe0 - 1 + wid; e < oe1; e += NW) {
+                const int u = (e < oe0) ? pick : g.odst[e];
+                if (mc_s[u] != k || (e >= oe0 && u == pick)) continue;
+                for (int e2 = g.iptr[u] + lane; e2 < g.iptr[u + 1]; e2 += 32) atomicSub(&f[g.isrc[e2]], 1);
+            }
+            __syncthreads();
+        }
+        if (err) {
+            if (tid == 0) { status[lr] = err; sweeps_out[lr] = 0; }
+            for (int v = tid; v < N; v += NT) mc_all[(int64_t)lr * N + v] = mc_s[v];
+            __syncthreads();
+            continue;
+        }
+
+        // ---- reassignment sweeps, B speculative visits per batch ------------------------------------
+        uint32_t hb = 1;
+        while ((1ull << (2 * hb)) < (unsigned long long)n_s) ++hb;
+        double factor = 1.0;
+        int sweep = 0;
+        uint32_t parity = 0;
+        for (; sweep < max_sweeps; ++sweep) {
+            if (sweep > burn_in) factor = factor * cooling;
+            uint32_t rk[4];
+            {
+                const uint64_t w0 = cover_rng_u64(seed_lo, seed_hi, STREAM_PERM, (uint32_t)sweep, 0u);
+                const uint64_t w1 = cover_rng_u64(seed_lo, seed_hi, STREAM_PERM, (uint32_t)sweep, 1u);
+                rk[0] = (uint32_t)w0; rk[1] = (uint32_t)(w0 >> 32); rk[2] = (uint32_t)w1; rk[3] = (uint32_t)(w1 >> 32);
+            }
+            __syncthreads();
+            for (int t = tid; t < n_s; t += NT) vlist[t] = S[perm_index((uint32_t)t, (uint32_t)n_s, hb, rk)];
+            __syncthreads();
+            int moved = 0;
+            int t = 0;
+            int cur_t = -1, nxt_t = -1;
+            NodeEdges<IN_SLOTS> cur;
+            NodeOffs<IN_SLOTS> nxt;
+            cur.v = -1; nxt.v = -1;
+            while (t < n_s) {
+                const int my_t = t + sb;
+                if (cur_t != my_t) {              // start of sweep, or the previous batch ended on a move: reload
+                    cur = load_edges<FT, IN_SLOTS>(g, load_offs<IN_SLOTS>(g, vlist, my_t, n_s), ltid);
+                    cur_t = my_t;
+                    nxt_t = my_t + B;
+                    nxt = load_offs<IN_SLOTS>(g, vlist, nxt_t, n_s);
+                }
+                const NodeEdges<IN_SLOTS> pre = load_edges<FT, IN_SLOTS>(g, nxt, ltid);   // node my_t + B, in flight
+                const NodeOffs<IN_SLOTS> nxt2 = load_offs<IN_SLOTS>(g, vlist, nxt_t + B, n_s);
+                uint32_t* wo_b = wout + (size_t)(2 * sb + (parity & 1)) * ncl_cap;
+                uint32_t* wi_b = win + (size_t)(2 * sb + (parity & 1)) * ncl_cap;
+                const int v = cur.v;               // -1 beyond the end of the sweep
+                const int nb = min(B, n_s - t);
+                // current cluster of the batch's nodes, read before anything in this batch can move
+                int rcur = -3;
+                if (lane < 4 * B && (lane >> 2) < nb) rcur = (int)mc_s[vlist[t + (lane >> 2)]];
+                // [A] association of this sub-block's node towards its neighbouring clusters
+                int ko = -1, ki[IN_SLOTS];
+                if (cur.uo >= 0) { ko = (int)mc_s[cur.uo]; if (ko >= 0) atomicAdd(&wo_b[ko], cur.wo); }
+#pragma unroll
+                for (int s = 0; s < IN_SLOTS; ++s) {
+                    ki[s] = -1;
+                    if (cur.ui[s] >= 0) { ki[s] = (int)mc_s[cur.ui[s]]; if (ki[s] >= 0) atomicAdd(&wi_b[ki[s]], cur.wi[s]); }
+                }
+                named_bar_sync(1 + sb, FT);
+                // [B] best cluster among those reached by an out edge: per-warp partial (score bits, cluster)
+                if (lwid < out_warps) {
+                    unsigned long long bits = 0ull;
+                    if (ko >= 0) {
+                        const uint32_t wo = wo_b[ko], wi = wi_b[ko];
+                        if (wo != 0 && wi != 0) {
+                            const int curk = (int)mc_s[v];
+                            const double sz = (double)size[ko];
+                            double sc = (double)((unsigned long long)wo * (unsigned long long)wi) / (sz * sz);
+                            if (ko == curk) sc = sc * factor;
+                            bits = (unsigned long long)__double_as_longlong(sc);
+                        }
+                    }
+                    const uint32_t hi = (uint32_t)(bits >> 32), lo = (uint32_t)bits;
+                    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+                    const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+                    const bool top = bits != 0ull && hi == mh && lo == ml;
+                    const uint32_t mk = __reduce_min_sync(0xffffffffu, top ? (uint32_t)ko : 0x7fffffffu);
+                    if (lane == 0) { s_pbits[parity & 1][sb * 4 + lwid] = ((unsigned long long)mh << 32) | ml; s_pk[parity & 1][sb * 4 + lwid] = (int)mk; }
+                }
+                __syncthreads();
+                // [C] clear this batch's accumulators (next used two batches from now)
+                if (ko >= 0) wo_b[ko] = 0;
+#pragma unroll
+                for (int s = 0; s < IN_SLOTS; ++s) if (ki[s] >= 0) wi_b[ki[s]] = 0;
+                // [D] resolve: every warp finds the first node of the batch that moves
+                unsigned long long rb = 0ull; int rk_ = 0x7fffffff;
+                if (lane < 4 * B) {
+                    const int j = lane >> 2, w = lane & 3;
+                    if (w < out_warps && j < nb) { rb = s_pbits[parity & 1][lane]; rk_ = s_pk[parity & 1][lane]; }
+                }
+#pragma unroll
+                for (int o = 1; o <= 2; o <<= 1) {
+                    const unsigned long long ob = __shfl_xor_sync(0xffffffffu, rb, o);
+                    const int ok = __shfl_xor_sync(0xffffffffu, rk_, o);
+                    if (ob > rb || (ob == rb && ok < rk_)) { rb = ob; rk_ = ok; }
+                }
+                const bool mv = (lane < 4 * B) && ((lane >> 2) < nb) && rb != 0ull && rk_ != rcur;
+                const unsigned mvmask = __ballot_sync(0xffffffffu, mv);
+                parity ^= 1u;
+                cur = pre; cur_t = nxt_t; nxt = nxt2; nxt_t += B;
+                if (mvmask == 0u) {
+                    t += nb;
+                } else {
+                    const int jl = __ffs(mvmask) - 1;          // first lane of the first moving node
+                    const int bk = __shfl_sync(0xffffffffu, rk_, jl);
+                    const int curk = __shfl_sync(0xffffffffu, rcur, jl);
+                    const int js = jl >> 2;
+                    if (tid == 0) {
+                        if (curk >= 0) size[curk]--;
+                        size[bk]++;
+                        mc_s[vlist[t + js]] = (int16_t)bk;
+                    }
+                    ++moved;
+                    t += js + 1;
+                    __syncthreads();
+                }
+            }
+            if (moved == 0) { ++sweep; break; }
+        }
+        __syncthreads();
+        for (int v = tid; v < N; v += NT) mc_all[(int64_t)lr * N + v] = mc_s[v];
+        if (tid == 0) { sweeps_out[lr] = sweep; status[lr] = 0; }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-per-node speculative variant.  graph_cover_batch_kernel is issue-bound: four warps per visited
+// node execute ~1,300 warp instructions per visit although a node has only ~150-200 edges.  Here each
+// WARP evaluates one node of the batch (B = warps per CTA nodes per batch): edges are walked 32 at a time
+// from L1 (the CTA touches the edge lines of the following batch while it works on the current one),
+// the accumulators are warp-private so no barrier separates accumulation from scoring, and one block
+// barrier per batch resolves the first mover exactly as in graph_cover_batch_kernel.  Same arithmetic,
+// bit-identical assignment.  Requires out-degree <= 32 * OUT_SLOTS (host-checked).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void touch_line(const void* p)
+{
+    uint32_t sink;
+    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(sink) : "l"(p));
+    (void)sink;
+}
+
+template <int B, int OUT_SLOTS>
+__global__ void __launch_bounds__(32 * B, 1024 / (32 * B))
+graph_cover_warp_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict__ resamp_ids, int32_t n_s,
+                        const int32_t* __restrict__ samples, const uint64_t* __restrict__ seeds, int32_t min_size,
+                        double cooling, int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap, int32_t kin_stride,
+                        int32_t* __restrict__ mc_all, int32_t* __restrict__ f_all, int32_t* __restrict__ sweeps_out,
+                        int32_t* __restrict__ status)
+{
+    constexpr int NT = 32 * B;
+    static_assert(B <= 32, "one lane per node partial");
+    extern __shared__ uint32_t dsm[];
+    int32_t* size = (int32_t*)dsm;                               // [ncl_cap]
+    uint32_t* accO = dsm + ncl_cap;                              // [B][ncl_cap]
+    uint32_t* accI = accO + (size_t)B * ncl_cap;                 // [B][ncl_cap]
+    int32_t* vlist = (int32_t*)(accI + (size_t)B * ncl_cap);     // [n_s]
+    int16_t* mc_s = (int16_t*)(vlist + n_s);                     // [N]
+    int16_t* kin = mc_s + ((g.N + 1) & ~1);                      // [B][kin_stride] clusters of the node's in-neighbours
+    __shared__ unsigned long long s_part[NT];
+    __shared__ unsigned long long s_pbits[2][B];
+    __shared__ int s_pk[2][B];
+    __shared__ int s_pick, s_flag;
+    __shared__ unsigned long long s_total;
+    __shared__ int s_kcnt[B];
+
+    const int N = g.N;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int* mycnt = &s_kcnt[wid];
+    uint32_t* myO = accO + (size_t)wid * ncl_cap;
+    uint32_t* myI = accI + (size_t)wid * ncl_cap;
+    int16_t* mykin = kin + (size_t)wid * kin_stride;
+    for (int lr = blockIdx.x; lr < n_local; lr += gridDim.x) {
+        const int rid = resamp_ids[lr];
+        const int32_t* S = samples + (int64_t)rid * n_s;
+        const uint64_t seed = seeds[rid];
+        const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
+        int32_t* f = f_all + (int64_t)lr * N;
+
+        for (int v = tid; v < N; v += NT) { mc_s[v] = -2; f[v] = 0; }
+        for (int k = tid; k < ncl_cap; k += NT) size[k] = 0;
+        for (int k = tid; k < B * ncl_cap; k += NT) { accO[k] = 0; accI[k] = 0; }
+        if (tid < B) { s_pbits[0][tid] = s_pbits[1][tid] = 0ull; s_pk[0][tid] = s_pk[1][tid] = 0x7fffffff; s_kcnt[tid] = 0; }
+        __syncthreads();
+        for (int q = tid; q < n_s; q += NT) mc_s[S[q]] = -1;
+        __syncthreads();
+        for (int q = tid; q < n_s; q += NT) {
+            const int v = S[q];
+            int c = 0;
+            for (int e = g.optr[v]; e < g.optr[v + 1]; ++e) c += (mc_s[g.odst[e]] == -1);
+            f[v] = c;
+        }
+        __syncthreads();
+
+        // ---- seeding (as graph_cover_kernel, NT threads) -------------------------------------------
+        int ncl = 0;
+        int err = 0;
+        const int chunk = (n_s + NT - 1) / NT;
+        const int q0 = min(n_s, tid * chunk), q1 = min(n_s, q0 + chunk);
+        for (uint32_t iter = 0;; ++iter) {
+            unsigned long long part = 0;
+            for (int q = q0; q < q1; ++q) {
+                const int v = S[q];
+                const int fv = f[v];
+                if (mc_s[v] == -1 && fv >= min_size && fv > 0) part += (unsigned long long)fv * fv * fv;
+            }
+            s_part[tid] = part;
+            __syncthreads();
+            if (tid < 32) {
+                unsigned long long tot = 0;
+                for (int q = lane; q < NT; q += 32) tot += s_part[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                if (lane == 0) { s_total = tot; s_pick = -1; }
+            }
+            __syncthreads();
+            const unsigned long long total = s_total;
+            if (total == 0) break;
+            if (ncl >= ncl_cap) { err = 3; break; }
+            const unsigned long long r = cover_rng_u64(seed_lo, seed_hi, STREAM_SEED, iter, 0) % total;
+            unsigned long long excl = 0;
+            for (int q = 0; q < tid; ++q) excl += s_part[q];
+            if (r >= excl && r < excl + part) {
+                unsigned long long cum = excl;
+                for (int q = q0; q < q1; ++q) {
+                    const int v = S[q];
+                    const int fv = f[v];
+                    if (mc_s[v] == -1 && fv >= min_size && fv > 0) {
+                        cum += (unsigned long long)fv * fv * fv;
+                        if (cum > r) { s_pick = v; break; }
+                    }
+                }
+            }
+            __syncthreads();
+            const int pick = s_pick;
+            const int k = ncl++;
+            if (tid == 0) { mc_s[pick] = (int16_t)k; s_flag = 1; }
+            __syncthreads();
+            const int oe0 = g.optr[pick], oe1 = g.optr[pick + 1];
+            for (int e = oe0 + tid; e < oe1; e += NT) {
+                const int u = g.odst[e];
+                if (mc_s[u] == -1) { mc_s[u] = (int16_t)k; atomicAdd(&s_flag, 1); }
+            }
+            __syncthreads();
+            if (tid == 0) size[k] = s_flag;
+            for (int e = oe0 - 1 + wid; e < oe1; e += B) {
+                const int u = (e < oe0) ? pick : g.odst[e];
+                if (mc_s[u] != k || (e >= oe0 && u == pick)) continue;
+                for (int e2 = g.iptr[u] + lane; e2 < g.iptr[u + 1]; e2 += 32) atomicSub(&f[g.isrc[e2]], 1);
+            }
+            __syncthreads();
+        }
+        if (err) {
+            if (tid == 0) { status[lr] = err; sweeps_out[lr] = 0; }
+            for (int v = tid; v < N; v += NT) mc_all[(int64_t)lr * N + v] = mc_s[v];
+            __syncthreads();
+            continue;
+        }
+
+        // ---- reassignment sweeps, one node per warp, B speculative visits per batch -----------------
+        uint32_t hb = 1;
+        while ((1ull << (2 * hb)) < (unsigned long long)n_s) ++hb;
+        double factor = 1.0;
+        int sweep = 0;
+        uint32_t parity = 0;
+        for (; sweep < max_sweeps; ++sweep) {
+            if (sweep > burn_in) factor = factor * cooling;
+            uint32_t rk[4];
+            {
+                const uint64_t w0 = cover_rng_u64(seed_lo, seed_hi, STREAM_PERM, (uint32_t)sweep, 0u);
+                const uint64_t w1 = cover_rng_u64(seed_lo, seed_hi, STREAM_PERM, (uint32_t)sweep, 1u);
+                rk[0] = (uint32_t)w0; rk[1] = (uint32_t)(w0 >> 32); rk[2] = (uint32_t)w1; rk[3] = (uint32_t)(w1 >> 32);
+            }
+            __syncthreads();
+            for (int t = tid; t < n_s; t += NT) vlist[t] = S[perm_index((uint32_t)t, (uint32_t)n_s, hb, rk)];
+            __syncthreads();
+            int moved = 0;
+            int t = 0;
+            while (t < n_s) {
+                const int nb = min(B, n_s - t);
+                int rcur = -3;                     // current cluster of the batch's nodes, before anything can move
+                if (lane < nb) rcur = (int)mc_s[vlist[t + lane]];
+                const int my_t = t + wid;
+                unsigned long long bbits = 0ull; int bk = 0x7fffffff;
+                if (my_t < n_s) {
+                    const int v = vlist[my_t];
+                    const int o0 = __ldg(g.optr + v), o1 = __ldg(g.optr + v + 1);
+                    const int i0 = __ldg(g.iptr + v), i1 = __ldg(g.iptr + v + 1);
+                    // [A] association towards neighbouring clusters.  The lane whose add finds the accumulator at
+                    // zero owns that cluster for this visit: it scores it in [B] and clears it in [C].
+                    int ko[OUT_SLOTS];
+                    unsigned own = 0u;
+#pragma unroll
+                    for (int s = 0; s < OUT_SLOTS; ++s) {
+                        ko[s] = -1;
+                        const int e = o0 + s * 32 + lane;
+                        if (e < o1) {
+                            const int u = __ldg(g.odst + e);
+                            const uint32_t w = __ldg(g.ow + e);
+                            ko[s] = (int)mc_s[u];
+                            if (ko[s] >= 0 && atomicAdd(&myO[ko[s]], w) == 0u) own |= 1u << s;
+                        }
+                    }
+                    for (int e = i0 + lane; e < i1; e += 32) {
+                        const int u = __ldg(g.isrc + e);
+                        const uint32_t w = __ldg(g.iw + e);
+                        const int k = (int)mc_s[u];
+                        if (k >= 0 && atomicAdd(&myI[k], w) == 0u) mykin[atomicAdd(mycnt, 1)] = (int16_t)k;
+                    }
+                    // touch the edge lines of the node this warp expects in the next batch
+                    if (my_t + B < n_s) {
+                        const int vn = vlist[my_t + B];
+                        const int p0 = __ldg(g.optr + vn), p1 = __ldg(g.optr + vn + 1);
+                        const int r0 = __ldg(g.iptr + vn), r1 = __ldg(g.iptr + vn + 1);
+                        const int eo = p0 + 32 * lane, ei = r0 + 32 * lane;
+                        if (eo < p1 + 31 && p1 > p0) { const int a = min(eo, p1 - 1); touch_line(g.odst + a); touch_line(g.ow + a); }
+                        if (ei < r1 + 31 && r1 > r0) { const int a = min(ei, r1 - 1); touch_line(g.isrc + a); touch_line(g.iw + a); }
+                    }
+                    __syncwarp();
+                    // [B] best cluster among those reached by an out edge
+                    const int curk = (int)mc_s[v];
+#pragma unroll
+                    for (int s = 0; s < OUT_SLOTS; ++s) {
+                        const bool mine = (own >> s) & 1u;
+                        if (__any_sync(0xffffffffu, mine)) {
+                            if (mine) {
+                                const uint32_t wo = myO[ko[s]], wi = myI[ko[s]];
+                                if (wi != 0) {
+                                    const double sz = (double)size[ko[s]];
+                                    double sc = (double)((unsigned long long)wo * (unsigned long long)wi) / (sz * sz);
+                                    if (ko[s] == curk) sc = sc * factor;
+                                    const unsigned long long bits = (unsigned long long)__double_as_longlong(sc);
+                                    if (bits > bbits || (bits == bbits && ko[s] < bk)) { bbits = bits; bk = ko[s]; }
+                                }
+                            }
+                        }
+                    }
+                    const uint32_t hi = (uint32_t)(bbits >> 32), lo = (uint32_t)bbits;
+                    const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+                    const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+                    const bool top = bbits != 0ull && hi == mh && lo == ml;
+                    const uint32_t mk = __reduce_min_sync(0xffffffffu, top ? (uint32_t)bk : 0x7fffffffu);
+                    if (lane == 0) { s_pbits[parity & 1][wid] = ((unsigned long long)mh << 32) | ml; s_pk[parity & 1][wid] = (int)mk; }
+                    __syncwarp();
+                    // [C] clear the warp's accumulators
+#pragma unroll
+                    for (int s = 0; s < OUT_SLOTS; ++s) if ((own >> s) & 1u) myO[ko[s]] = 0;
+                    const int nin = *mycnt;
+                    for (int q = lane; q < nin; q += 32) myI[mykin[q]] = 0;
+                    __syncwarp();
+                    if (lane == 0) *mycnt = 0;
+                }
+                __syncthreads();
+                // [D] resolve: every warp finds the first node of the batch that moves
+                unsigned long long rb = 0ull; int rk_ = 0x7fffffff;
+                if (lane < nb) { rb = s_pbits[parity & 1][lane]; rk_ = s_pk[parity & 1][lane]; }
+                const bool mv = lane < nb && rb != 0ull && rk_ != rcur;
+                const unsigned mvmask = __ballot_sync(0xffffffffu, mv);
+                parity ^= 1u;
+                if (mvmask == 0u) {
+                    t += nb;
+                } else {
+                    const int js = __ffs(mvmask) - 1;
+                    const int nk = __shfl_sync(0xffffffffu, rk_, js);
+                    const int curk = __shfl_sync(0xffffffffu, rcur, js);
+                    if (tid == 0) {
+                        if (curk >= 0) size[curk]--;
+                        size[nk]++;
+                        mc_s[vlist[t + js]] = (int16_t)nk;
+                    }
+                    ++moved;
+                    t += js + 1;
+                    __syncthreads();
+                }
+            }
+            if (moved == 0) { ++sweep; break; }
+        }
+        __syncthreads();
+        for (int v = tid; v < N; v += NT) mc_all[(int64_t)lr * N + v] = mc_s[v];
+        if (tid == 0) { sweeps_out[lr] = sweep; status[lr] = 0; }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // co-occurrence: for every cluster of every local resample, cnt[min(a,b)][max(a,b)] += 1 for all
 // member pairs; nsamp[a] += 1 for every sampled node (mc[a] != -2).
 // One CTA per resample; members are grouped by a counting sort in global workspace.
@@ -587,6 +1094,41 @@ static void launch_cover_fast(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local
     MCB_LAUNCH_CHECK();
 }
 
+template <int B, int IN_SLOTS>
+static void launch_cover_batch(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
+                               const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling, int32_t burn_in,
+                               int32_t max_sweeps, int32_t ncl_cap, int32_t max_out, size_t smem, int32_t* mc, int32_t* f_ws,
+                               int32_t* sweeps, int32_t* status)
+{
+    static size_t configured = 0;
+    if (smem > configured) {
+        MCB_CUDA(cudaFuncSetAttribute(graph_cover_batch_kernel<B, IN_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int32_t out_warps = std::max(1, (int)ceil_div(max_out, 32));
+    graph_cover_batch_kernel<B, IN_SLOTS><<<n_local, 128 * B, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds,
+                                                                                    min_size, cooling, burn_in, max_sweeps,
+                                                                                    ncl_cap, out_warps, mc, f_ws, sweeps, status);
+    MCB_LAUNCH_CHECK();
+}
+
+template <int B, int OUT_SLOTS>
+static void launch_cover_warp(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
+                              const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling, int32_t burn_in,
+                              int32_t max_sweeps, int32_t ncl_cap, int32_t kin_stride, size_t smem, int32_t* mc, int32_t* f_ws,
+                              int32_t* sweeps, int32_t* status)
+{
+    static size_t configured = 0;
+    if (smem > configured) {
+        MCB_CUDA(cudaFuncSetAttribute(graph_cover_warp_kernel<B, OUT_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    graph_cover_warp_kernel<B, OUT_SLOTS><<<n_local, 32 * B, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds,
+                                                                                   min_size, cooling, burn_in, max_sweeps, ncl_cap,
+                                                                                   kin_stride, mc, f_ws, sweeps, status);
+    MCB_LAUNCH_CHECK();
+}
+
 void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32, const int32_t* iptr32, int32_t max_out,
                         int32_t max_in, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
                         const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling,
@@ -594,16 +1136,52 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
                         int32_t* sweeps, int32_t* status)
 {
     if (n_local == 0) return;
-    // fast kernels: size + 2 x (wout, win) + visit order + int16 mc[] in shared memory, edges of a node in registers
-    const size_t fast_smem = ((size_t)5 * ncl_cap + (size_t)n_s) * sizeof(uint32_t) + (size_t)g.N * sizeof(int16_t) + 16;
-    if (optr32 && fast_smem <= 200 * 1024 && ncl_cap < 32000 && !getenv("MCB_COVER_SLOW")) {
+    // Kernel choice (MCB_COVER_KERNEL overrides for tests/diagnostics: batch2|batch4|batch8|warp8|warp16|warp32|fast|slow):
+    //   batch4  speculative batches of 4 visits, 4 warps per node  (out-degree <= 128, in-degree <= 384)
+    //   warp16  speculative batches of 16 visits, 1 warp per node  (out-degree <= 256, any in-degree)
+    //   fast    sequential visits, state in shared memory
+    //   slow    sequential visits, mc[] in global memory (any size)
+    const char* ksel = getenv("MCB_COVER_KERNEL");
+    const std::string want = ksel ? ksel : (getenv("MCB_COVER_SLOW") ? "slow" : "auto");
+    const bool small_state = optr32 && ncl_cap < 32000;
+    if (small_state && want != "slow") {
         const FastGraph fg{g.N, optr32, g.odst, g.ow, iptr32, g.isrc, g.iw};
+        const bool auto_ = want == "auto";
+#define BATCH(BB)                                                                                                         \
+    if ((auto_ && BB == 4) || want == "batch" #BB) {                                                                      \
+        const size_t bsmem = ((size_t)(1 + 4 * BB) * ncl_cap + (size_t)n_s) * sizeof(uint32_t) + (size_t)g.N * sizeof(int16_t) + 16; \
+        if (max_out <= 128 && max_in <= 3 * 128 && bsmem <= 200 * 1024) {                                                 \
+            launch_cover_batch<BB, 3>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,      \
+                                      max_sweeps, ncl_cap, max_out, bsmem, mc, f_ws, sweeps, status);                     \
+            return;                                                                                                       \
+        }                                                                                                                 \
+    }
+        BATCH(4) BATCH(2) BATCH(8)
+#undef BATCH
+        const int32_t kin_stride = (int32_t)round_up((int64_t)std::max(std::min(max_in, ncl_cap), 1), 32) + 2;
+#define WARPK(BB, OS)                                                                                                    \
+    if ((auto_ && BB == 16) || want == "warp" #BB) {                                                                      \
+        const size_t wsmem = ((size_t)(1 + 2 * BB) * ncl_cap + (size_t)n_s) * sizeof(uint32_t) +                         \
+                             ((size_t)((g.N + 1) & ~1) + (size_t)BB * kin_stride) * sizeof(int16_t) + 16;                \
+        if (max_out <= 32 * OS && wsmem <= 200 * 1024) {                                                                  \
+            launch_cover_warp<BB, OS>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,     \
+                                      max_sweeps, ncl_cap, kin_stride, wsmem, mc, f_ws, sweeps, status);                  \
+            return;                                                                                                       \
+        }                                                                                                                 \
+    }
+        if (max_out <= 128) { WARPK(16, 4) WARPK(8, 4) WARPK(32, 4) }
+        else { WARPK(16, 8) WARPK(8, 8) }
+#undef WARPK
+        // fast kernels: size + 2 x (wout, win) + visit order + int16 mc[] in shared memory, edges of a node in registers
+        const size_t fast_smem = ((size_t)5 * ncl_cap + (size_t)n_s) * sizeof(uint32_t) + (size_t)g.N * sizeof(int16_t) + 16;
+        if (fast_smem <= 200 * 1024) {
 #define FAST(FT, SL) launch_cover_fast<FT, SL>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in, \
                                                max_sweeps, ncl_cap, max_out, fast_smem, mc, f_ws, sweeps, status)
-        if (max_out <= 128 && max_in <= 3 * 128) { FAST(128, 3); return; }
-        if (max_out <= 256 && max_in <= 3 * 256) { FAST(256, 3); return; }
-        if (max_out <= 256 && max_in <= 6 * 256) { FAST(256, 6); return; }
+            if (max_out <= 128 && max_in <= 3 * 128) { FAST(128, 3); return; }
+            if (max_out <= 256 && max_in <= 3 * 256) { FAST(256, 3); return; }
+            if (max_out <= 256 && max_in <= 6 * 256) { FAST(256, 6); return; }
 #undef FAST
+        }
     }
     const size_t smem = (size_t)ncl_cap * 3 * sizeof(uint32_t);
     MCB_CHECK(smem <= 200 * 1024, "MC-ERR: graph cover: too many potential clusters for shared memory");

@@ -107,3 +107,23 @@ def test_single_graph_cover_and_mc_from_coclust(ctx, oracle, tmp_path):
     assert len(res2["mc"]) + len(res2["outliers"]) == ncells and len(res2["mc"]) > ncells // 2
     with pytest.raises(api.McbError, match="MC-ERR"):
         api.mcell_mc_from_coclust_balanced("mc3", "nope", "m", 10, 8, ctx=ctx)
+
+
+@pytest.mark.parametrize("kernel", ["batch2", "batch4", "batch8", "warp8", "warp16", "warp32", "fast", "slow"])
+def test_graph_cover_kernel_variants_bit_exact(ctx, oracle, kernel, monkeypatch):
+    """Every cover kernel (speculative 4-warp batches, speculative warp-per-node, sequential shared-memory,
+    sequential global-memory) evaluates the same Gauss-Seidel pass: assignments and sweep counts must equal the
+    oracle's for each of them (MCB_COVER_KERNEL forces the choice inside launch_graph_cover)."""
+    from metacell_b200 import _lib, synth
+    ncells, min_size = 1100, 10
+    src, dst, w = _graph(oracle, ncells, 20, seed=9)
+    monkeypatch.setenv("MCB_COVER_KERNEL", kernel)
+    sets, seeds = synth.resample_sets(ncells, 0.75, 5, 4242)
+    cc = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, min_size, 1.05, 10)
+    mc, sweeps = cc.assignments()
+    cc.destroy()
+    csr = oracle.graph_to_csr(ncells, src, dst, w)
+    for r in range(sets.shape[0]):
+        omc, osw = oracle.graph_cover(ncells, csr, sets[r], min_size, 1.05, 10, int(seeds[r]))
+        assert sweeps[r] == osw, (kernel, r, sweeps[r], osw)
+        assert np.array_equal(mc[r], omc), (kernel, r)
