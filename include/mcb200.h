@@ -12,6 +12,7 @@
  *     R/scmat.r:399-407 scm_which_downsamp_n(mat)                         -> mcb_downsamp_depth
  *     R/gset.r:151-214 gset_get_feat_mat + R/cgraph_knn.r:13-14 log2(1+7u) -> mcb_cgraph_create
  *     R/cgraph_knn.r:10-25 mcell_add_cgraph_from_mat_bknn                 -> mcb_cgraph_bknn (one shot)
+ *     R/atlas.r:164-166   tgs_cor_knn(x, y, knn), y != x                     -> mcb_cor_knn_xy
  *     R/coclust_graph_cov.r:41 tgs_graph_cover_resample(method = "full")  -> mcb_coclust_*
  *
  * Conventions
@@ -122,6 +123,14 @@ int  mcb_cgraph_edges(mcb_cgraph* g, int32_t* host_src, int32_t* host_dst, doubl
 /* test hook: dense correlation block C[a_rows][b_rows] of the first rows of Z through one kernel:
  * impl 0 = tcgen05 3-pass split-TF32, 2 = tcgen05 1-pass TF32, 1 = SIMT fp32.  Call before _mutual. */
 int  mcb_cgraph_debug_cor(mcb_cgraph* g, int impl, int64_t a_rows, int64_t b_rows, float* host_c);
+
+/* tgs_cor_knn(x, y, knn) with y != x (reference call sites R/atlas.r:164-166,277,475-478,584): for every
+ * cell of x (nx cells, one contiguous vector of G doubles each) the knn cells of y with the highest
+ * Pearson correlation, by descending correlation (ties: lower y index).  host_col / host_cor are
+ * [nx][knn]; entries beyond the number of non-constant y cells, and all entries of a constant x cell,
+ * are col = -1 / cor = NaN (NA in R).  No self match is forced.  knn <= 4096.                      */
+int  mcb_cor_knn_xy(mcb_ctx* ctx, const double* x, int64_t nx, const double* y, int64_t ny, int32_t G,
+                    int32_t knn, int32_t* host_col, float* host_cor);
 
 /* one shot, single GPU, host in / host out: what mcell_add_cgraph_from_mat_bknn's body becomes.
  * dsamp != 0: depth rule + downsample + add back small cells first (R/cgraph_knn.r:12).

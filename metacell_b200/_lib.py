@@ -20,7 +20,7 @@ SYMBOLS = [
     "mcb_cgraph_valid_cells", "mcb_cgraph_features", "mcb_cgraph_knn", "mcb_cgraph_knn_begin", "mcb_cgraph_knn_thr_buffer",
     "mcb_cgraph_knn_filter", "mcb_cgraph_knn_recv_buffer", "mcb_cgraph_knn_finish", "mcb_cgraph_knn_buffer",
     "mcb_cgraph_download_knn", "mcb_cgraph_knn_stats", "mcb_cgraph_mutual", "mcb_cgraph_thr_buffer",
-    "mcb_cgraph_prune", "mcb_cgraph_edges", "mcb_cgraph_debug_cor", "mcb_cgraph_bknn", "mcb_free",
+    "mcb_cgraph_prune", "mcb_cgraph_edges", "mcb_cgraph_debug_cor", "mcb_cor_knn_xy", "mcb_cgraph_bknn", "mcb_free",
     "mcb_coclust_run", "mcb_graph_cover", "mcb_coclust_destroy", "mcb_coclust_buffers", "mcb_coclust_assignments",
     "mcb_coclust_extract", "mcb_coclust_pairs",
 ]
@@ -340,6 +340,19 @@ def cgraph_bknn_oneshot(ctx, ngenes, indptr, indices, data, feat_rows, K, k_expa
         lib().mcb_free(pd)
         lib().mcb_free(pw)
     return src, dst, w, int(nv.value)
+
+
+def cor_knn_xy(ctx, x_cells, y_cells, knn):
+    """mcb_cor_knn_xy: x_cells [nx][G], y_cells [ny][G] (one row per cell) -> col [nx][knn] int32, cor [nx][knn] f32."""
+    x = as_c(x_cells, np.float64)
+    y = as_c(y_cells, np.float64)
+    if x.ndim != 2 or y.ndim != 2 or x.shape[1] != y.shape[1]:
+        raise McbError("MC-ERR: tgs_cor_knn: x and y must have the same number of rows (genes)")
+    col = np.empty((x.shape[0], int(knn)), dtype=np.int32)
+    cor = np.empty((x.shape[0], int(knn)), dtype=np.float32)
+    check(lib().mcb_cor_knn_xy(ctx.h, ptr(x, C.c_double), C.c_int64(x.shape[0]), ptr(y, C.c_double), C.c_int64(y.shape[0]),
+                               C.c_int32(x.shape[1]), C.c_int32(int(knn)), ptr(col, C.c_int32), ptr(cor, C.c_float)))
+    return col, cor
 
 
 class CoClust:

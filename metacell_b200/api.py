@@ -255,10 +255,20 @@ def gset_get_feat_mat(gset_id, mat_id, downsamp=False, add_non_dsamp=False, down
 # A5 / A6: the tgstat trio
 # ------------------------------------------------------------------------------------------------
 def tgs_cor_knn(x, y=None, knn=None, ctx=None):
-    """tgs_cor_knn(x, y = x, knn): x is genes x cells (like the R matrix).  Returns dict col1, col2, cor,
-    rank (schema pinned by reference R/atlas.r:282,477,585); col1/col2 are 0-based cell codes."""
+    """tgs_cor_knn(x, y = x, knn): x (and y) are genes x cells (like the R matrices).  Returns dict col1, col2, cor,
+    rank (schema pinned by reference R/atlas.r:282,477,585); col1/col2 are 0-based cell codes (col2 indexes y's
+    columns).  y is x: self is rank 1 (R/atlas.r:475-476).  y is not x (atlas projection, R/atlas.r:164-166): the knn
+    best y cells per x cell, no forced self; NA correlations (constant cells) produce no rows."""
     if y is not None and y is not x:
-        raise McbError("MC-ERR: tgs_cor_knn with y != x is not on the accelerated path yet (SURVEY 8f rank 4)")
+        ctx = _ctx(ctx)
+        xa, ya = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+        if xa.shape[0] != ya.shape[0]:
+            raise McbError("MC-ERR: tgs_cor_knn: x and y must have the same number of rows (genes)")
+        col, cor = _lib.cor_knn_xy(ctx, np.ascontiguousarray(xa.T), np.ascontiguousarray(ya.T), int(knn))
+        ok = col >= 0
+        col1 = np.broadcast_to(np.arange(col.shape[0], dtype=np.int32)[:, None], col.shape)
+        rank = np.broadcast_to(np.arange(1, col.shape[1] + 1, dtype=np.int32)[None, :], col.shape)
+        return {"col1": col1[ok].astype(np.int32), "col2": col[ok], "cor": cor[ok].astype(np.float64), "rank": rank[ok].astype(np.int32)}
     ctx = _ctx(ctx)
     xt = np.ascontiguousarray(np.asarray(x, dtype=np.float64).T)
     g = _lib.CGraph.from_dense(ctx, xt)
@@ -296,6 +306,78 @@ def tgs_cor_graph(x, knn, k_expand, k_alpha, k_beta, ctx=None):
         return _graph_from_handle(g, knn, k_expand, k_beta)
     finally:
         g.destroy()
+
+
+# ------------------------------------------------------------------------------------------------
+# mcell_add_cgraph_from_mat_raw_knn (reference R/cgraph_knn.r:35-51)
+# ------------------------------------------------------------------------------------------------
+def mcell_add_cgraph_from_mat_raw_knn(mat_id, gset_id, graph_id, K, dsamp=False, ctx=None):
+    """Unbalanced K-nn graph: tgs_knn(tgs_cor(feat), K) keeps, per cell, the K best correlations of the full matrix
+    (the diagonal included, so self is rank 1) and weights them 1 - (rank-1)/K (R/cgraph_knn.r:43-46)."""
+    gset, mat = scdb_gset(gset_id), scdb_mat(mat_id)
+    if gset is None:
+        raise McbError(f"MC-ERR: non existing gset ({gset_id}) when trying to build a cell graph")
+    if mat is None:
+        raise McbError(f"MC-ERR: non existing mat ({mat_id}) when trying to build a cell graph")
+    ctx = _ctx(ctx)
+    rows = _feature_rows(gset, mat)
+    _message(f"will build raw knn graph on {mat.ncells} cells and {rows.size} genes, this can be a bit heavy for >20,000 cells")
+    csc = _upload(mat, ctx)
+    use = csc
+    if dsamp:       # gset_get_feat_mat(downsamp = dsamp, add_non_dsamp = dsamp), R/cgraph_knn.r:37
+        n = get_param("scm_n_downsamp_gstat")
+        if n is None:
+            n = _lib.downsamp_depth(csc.col_sums())
+        use = csc.downsample(float(n), get_param("mc_rseed"), add_non_dsamp=True)
+    g = _lib.CGraph.from_csc(ctx, use, rows, float(get_param("scm_k_nonz_exp")))
+    try:
+        g.knn(int(K), 1)
+        col, _ = g.download_knn()
+        cells = g.valid_cells()
+    finally:
+        g.destroy()
+        if use is not csc:
+            use.free()
+        csc.free()
+    kk = min(int(K), cells.size)
+    src = np.repeat(cells, kk)
+    dst = cells[col[:, :kk].reshape(-1)]
+    w = np.tile(1.0 - np.arange(kk, dtype=np.float64) / float(K), cells.size)       # gr$w = 1-(rank-1)/K
+    gr = tgCellGraph({"mc1": src.astype(np.int32), "mc2": dst.astype(np.int32), "w": w}, mat.cells)
+    scdb_add_cgraph(graph_id, gr)
+    return gr
+
+
+# ------------------------------------------------------------------------------------------------
+# mcell_mc_confusion_mat (reference R/mc_confusion.r:10-45)
+# ------------------------------------------------------------------------------------------------
+def mcell_mc_confusion_mat(mc_id, graph_id, K, ignore_mismatch=False):
+    """confu[a, b] = number of graph edges from a cell of metacell a to a cell of metacell b (1-based metacell ids
+    become 0-based rows here).  Host tabulation, as in the reference; the reference computes the edge filter
+    `w > 1-(K+1)/deg` and then overwrites it (R/mc_confusion.r:27-37), so all edges between covered cells count."""
+    graph = scdb_cgraph(graph_id)
+    if graph is None:
+        raise McbError(f"MC-ERR: cell graph id {graph_id} is missing when computing mc confusion")
+    mc = _scdb_get("mc", mc_id)
+    if mc is None:
+        raise McbError(f"MC-ERR: mc id {mc_id} is missing when computing mc confusion")
+    names = graph.cell_names
+    mc_map = np.full(len(names), -1, dtype=np.int64)
+    index = {nm: q for q, nm in enumerate(names)}
+    missing = 0
+    for nm, k in mc["mc"].items():
+        q = index.get(nm)
+        if q is None:
+            missing += 1
+        else:
+            mc_map[q] = k
+    if not ignore_mismatch and missing:
+        raise McbError("MC-ERR: graph is missing some of the cells in the mc cover when computing confusion, halting")
+    m1, m2 = mc_map[graph.edges["mc1"]], mc_map[graph.edges["mc2"]]
+    ok = (m1 > 0) & (m2 > 0)
+    N = int(max(m1[ok].max(initial=0), m2[ok].max(initial=0)))
+    confu = np.bincount((m1[ok] - 1) * N + (m2[ok] - 1), minlength=N * N).reshape(N, N)
+    return confu
 
 
 # ------------------------------------------------------------------------------------------------

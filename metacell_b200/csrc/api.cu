@@ -917,6 +917,65 @@ extern "C" int mcb_cgraph_debug_cor(mcb_cgraph* g, int impl, int64_t a_rows, int
     MCB_API_END
 }
 
+// tgs_cor_knn(x, y, knn) with y != x (reference call sites R/atlas.r:164-166,277,475-478,584):
+// for every cell of x the knn cells of y with the highest Pearson correlation, ranked.  Both inputs are
+// dense, one contiguous vector of G doubles per cell.  The full correlation rows go through the 3-pass
+// tensor-core kernel in STORE mode in row chunks and an exact per-row select; there is no self match.
+// Cells with a constant feature vector have NA correlations in R: a constant x cell gets col = -1 / cor = NaN,
+// a constant y cell is never listed.
+extern "C" int mcb_cor_knn_xy(mcb_ctx* ctx, const double* x, int64_t nx, const double* y, int64_t ny, int32_t G,
+                              int32_t knn, int32_t* host_col, float* host_cor)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && x && y && host_col && host_cor, "mcb_cor_knn_xy: null argument");
+    MCB_CHECK(knn >= 1, "MC-ERR: knn must be >= 1");
+    MCB_CHECK(knn <= 4096, "MC-ERR: knn above 4096 is not supported");
+    mcb_cgraph *gx = nullptr, *gy = nullptr;
+    struct Guard { mcb_cgraph*& a; mcb_cgraph*& b; ~Guard() { mcb_cgraph_destroy(a); mcb_cgraph_destroy(b); } } guard{gx, gy};
+    if (mcb_cgraph_create_dense(ctx, x, G, nx, &gx) != 0) throw std::runtime_error(mcb_last_error());
+    if (mcb_cgraph_create_dense(ctx, y, G, ny, &gy) != 0) throw std::runtime_error(mcb_last_error());
+    const int64_t Mx = gx->M, My = gy->M;
+    const int32_t Gpad = gx->Gpad;
+    const int32_t kk = (int32_t)std::min<int64_t>(knn, My);
+    for (int64_t q = 0; q < nx * (int64_t)knn; ++q) { host_col[q] = -1; host_cor[q] = std::nanf(""); }
+    if (Mx == 0 || My == 0) return 0;
+    const int64_t ldcf = round_up(My, 4);
+    int64_t B = std::min<int64_t>(4096, std::max<int64_t>(128, ((int64_t)1 << 28) / ldcf / 128 * 128));
+    B = std::min<int64_t>(B, round_up(Mx, 128));
+    DevBuf<float> Cf(ctx, (size_t)B * ldcf);
+    DevBuf<int32_t> rows(ctx, (size_t)B), col(ctx, (size_t)Mx * knn);
+    DevBuf<float> cor(ctx, (size_t)Mx * knn);
+    std::vector<int32_t> iota((size_t)B);
+    for (int64_t b0 = 0; b0 < Mx; b0 += B) {
+        const int64_t nb = std::min(B, Mx - b0);
+        for (int64_t q = 0; q < nb; ++q) iota[q] = (int32_t)(b0 + q);
+        MCB_CUDA(cudaMemcpyAsync(rows.p, iota.data(), sizeof(int32_t) * (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
+        {
+            StageTimer t(ctx, "cor_xy_gemm");
+            launch_tc_store3_ab(ctx, gx->Zh.p + (size_t)b0 * Gpad, gx->Zl.p + (size_t)b0 * Gpad, gx->Mpad - b0, gy->Zh.p, gy->Zl.p,
+                                gy->Mpad, nb, My, Gpad, Cf.p, ldcf);
+        }
+        {
+            StageTimer t(ctx, "topk_xy_rows");
+            launch_topk_big(ctx, Cf.p, ldcf, My, rows.p, (int32_t)nb, 0, kk, knn, nullptr, col.p, cor.p, false);
+        }
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));      // iota is reused
+    }
+    std::vector<int32_t> hcol((size_t)Mx * knn), cx((size_t)Mx), cy((size_t)My);
+    std::vector<float> hcor((size_t)Mx * knn);
+    MCB_CUDA(cudaMemcpyAsync(hcol.data(), col.p, sizeof(int32_t) * hcol.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaMemcpyAsync(hcor.data(), cor.p, sizeof(float) * hcor.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaMemcpyAsync(cx.data(), gx->cell_of_row.p, sizeof(int32_t) * cx.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaMemcpyAsync(cy.data(), gy->cell_of_row.p, sizeof(int32_t) * cy.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int64_t r = 0; r < Mx; ++r) {
+        int32_t* oc = host_col + (int64_t)cx[r] * knn;
+        float* ov = host_cor + (int64_t)cx[r] * knn;
+        for (int32_t t = 0; t < kk; ++t) { oc[t] = cy[hcol[r * knn + t]]; ov[t] = hcor[r * knn + t]; }
+    }
+    MCB_API_END
+}
+
 extern "C" int mcb_cgraph_bknn(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* p, const int32_t* i,
                                const double* x, const int32_t* feat_rows, int32_t G, int32_t K, int32_t k_expand,
                                int32_t k_beta, double k_nonz, int dsamp, uint64_t seed, int64_t* n_edges,

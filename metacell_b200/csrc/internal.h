@@ -148,7 +148,7 @@ void launch_topk_rows(mcb_ctx* ctx, const uint64_t* cand, const uint32_t* cnt, i
 void launch_compact_flags(mcb_ctx* ctx, const int32_t* flag, int64_t n, int32_t* list, int32_t* n_out);
 void launch_topk_big(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t M, const int32_t* rows, int32_t nrows,
                      int64_t row0, int32_t kc_out, int32_t Kc, const float* thr_rows /* [own rows] or null */,
-                     int32_t* knn_col, float* knn_cor);
+                     int32_t* knn_col, float* knn_cor, bool with_self = true);
 
 // balance.cu
 void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t Kc, int32_t H, int32_t rank_bits,

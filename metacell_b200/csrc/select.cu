@@ -190,6 +190,7 @@ topk_rows_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__
 // exact selection over a full correlation row held in global memory (fp32, M values):
 // the kc_out-1 best columns != self by (cor desc, col asc).  One CTA per listed row.
 // ---------------------------------------------------------------------------------------------
+template <bool WITH_SELF>    // WITH_SELF: x == y, the row's own column is forced to rank 1 and skipped in the scan
 __global__ void __launch_bounds__(SEL_THREADS)
 topk_big_kernel(const float* __restrict__ C, int64_t ldc, int64_t M, const int32_t* __restrict__ rows, int32_t nrows,
                 int64_t row0, int32_t kc_out, int32_t Kc, const float* __restrict__ thr_rows, int32_t np2s,
@@ -202,13 +203,13 @@ topk_big_kernel(const float* __restrict__ C, int64_t ldc, int64_t M, const int32
     __shared__ int s_done, s_fill;
     for (int q = blockIdx.x; q < nrows; q += gridDim.x) {
         const int64_t lrow = rows[q];               // local row (relative to row0)
-        const int64_t self = row0 + lrow;
+        const int64_t self = WITH_SELF ? row0 + lrow : -1;
         const float* c = C + (int64_t)q * ldc;
-        const int want = kc_out - 1;
+        const int want = WITH_SELF ? kc_out - 1 : kc_out;
         int32_t* oc = knn_col + lrow * (int64_t)Kc;
         float* ov = knn_cor + lrow * (int64_t)Kc;
         if (want <= 0) {
-            for (int t = threadIdx.x; t < Kc; t += SEL_THREADS) { oc[t] = t == 0 ? (int32_t)self : -1; ov[t] = t == 0 ? 1.f : 0.f; }
+            for (int t = threadIdx.x; t < Kc; t += SEL_THREADS) { oc[t] = (WITH_SELF && t == 0) ? (int32_t)self : -1; ov[t] = (WITH_SELF && t == 0) ? 1.f : 0.f; }
             continue;
         }
         if (threadIdx.x == 0) { s_prefix = 0ull; s_k = want - 1; s_done = 0; s_thr = ~0ull; s_fill = 0; }
@@ -231,8 +232,8 @@ topk_big_kernel(const float* __restrict__ C, int64_t ldc, int64_t M, const int32
                 __syncthreads();
                 bitonic_sort_u64<SEL_THREADS>(sk, np2);
                 for (int tq = threadIdx.x; tq < Kc; tq += SEL_THREADS) {
-                    if (tq == 0) { oc[0] = (int32_t)self; ov[0] = 1.0f; }
-                    else if (tq < kc_out) { const uint64_t k = sk[tq - 1]; oc[tq] = (int32_t)cand_key_col(k); ov[tq] = cand_key_cor(k); }
+                    if (WITH_SELF && tq == 0) { oc[0] = (int32_t)self; ov[0] = 1.0f; }
+                    else if (tq < kc_out) { const uint64_t k = sk[tq - (WITH_SELF ? 1 : 0)]; oc[tq] = (int32_t)cand_key_col(k); ov[tq] = cand_key_cor(k); }
                     else { oc[tq] = -1; ov[tq] = 0.0f; }
                 }
                 __syncthreads();
@@ -282,8 +283,8 @@ topk_big_kernel(const float* __restrict__ C, int64_t ldc, int64_t M, const int32
         __syncthreads();
         bitonic_sort_u64<SEL_THREADS>(sk, np2);
         for (int t = threadIdx.x; t < Kc; t += SEL_THREADS) {
-            if (t == 0) { oc[0] = (int32_t)self; ov[0] = 1.0f; }
-            else if (t < kc_out) { const uint64_t k = sk[t - 1]; oc[t] = (int32_t)cand_key_col(k); ov[t] = cand_key_cor(k); }
+            if (WITH_SELF && t == 0) { oc[0] = (int32_t)self; ov[0] = 1.0f; }
+            else if (t < kc_out) { const uint64_t k = sk[t - (WITH_SELF ? 1 : 0)]; oc[t] = (int32_t)cand_key_col(k); ov[t] = cand_key_cor(k); }
             else { oc[t] = -1; ov[t] = 0.0f; }
         }
         __syncthreads();
@@ -585,7 +586,8 @@ void launch_compact_flags(mcb_ctx* ctx, const int32_t* flag, int64_t n, int32_t*
 }
 
 void launch_topk_big(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t M, const int32_t* rows, int32_t nrows,
-                     int64_t row0, int32_t kc_out, int32_t Kc, const float* thr_rows, int32_t* knn_col, float* knn_cor)
+                     int64_t row0, int32_t kc_out, int32_t Kc, const float* thr_rows, int32_t* knn_col, float* knn_cor,
+                     bool with_self)
 {
     if (nrows == 0) return;
     int np2 = 2; while (np2 < kc_out) np2 <<= 1;
@@ -594,10 +596,14 @@ void launch_topk_big(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t M, const
     MCB_CHECK(smem <= 200 * 1024, "topk_big: Kc too large for shared memory");
     static size_t configured = 0;
     if (smem > configured) {
-        MCB_CUDA(cudaFuncSetAttribute(topk_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MCB_CUDA(cudaFuncSetAttribute(topk_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MCB_CUDA(cudaFuncSetAttribute(topk_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    topk_big_kernel<<<nrows, SEL_THREADS, smem, ctx->stream>>>(C, ldc, M, rows, nrows, row0, kc_out, Kc, thr_rows, np2, knn_col, knn_cor);
+    if (with_self)
+        topk_big_kernel<true><<<nrows, SEL_THREADS, smem, ctx->stream>>>(C, ldc, M, rows, nrows, row0, kc_out, Kc, thr_rows, np2, knn_col, knn_cor);
+    else
+        topk_big_kernel<false><<<nrows, SEL_THREADS, smem, ctx->stream>>>(C, ldc, M, rows, nrows, row0, kc_out, Kc, thr_rows, np2, knn_col, knn_cor);
     MCB_LAUNCH_CHECK();
 }
 

@@ -33,3 +33,34 @@ def cor_knn_blas(Z, Kc, row_begin=0, row_end=None, block=512):
         col[i0 - row_begin:i1 - row_begin, :kk] = part
         cor[i0 - row_begin:i1 - row_begin, :kk] = vals
     return col, cor
+
+
+def standardize_cells(X):
+    """A4 without the log transform: X [cells][G] -> (Z, valid); z = (x - mean) / sqrt(sum (x - mean)^2) per cell.
+    A cell whose vector is constant has NA correlations in R (R/cgraph_knn_mcnorm.r:25): valid = False."""
+    X = np.asarray(X, dtype=np.float64)
+    d = X - X.mean(axis=1, keepdims=True)
+    s = np.sqrt((d * d).sum(axis=1))
+    valid = s > 0
+    Z = np.zeros_like(d)
+    Z[valid] = d[valid] / s[valid, None]
+    return Z, valid
+
+
+def cor_knn_xy(X, Y, knn):
+    """tgs_cor_knn(x, y, knn) with y != x (reference call sites R/atlas.r:164-166,277,475-478,584), fp64:
+    per x cell the knn y cells with the highest Pearson correlation, (cor desc, y index asc); no self match.
+    Returns col [nx][knn] (-1 where NA), cor [nx][knn] (NaN where NA)."""
+    Zx, vx = standardize_cells(X)
+    Zy, vy = standardize_cells(Y)
+    yi = np.nonzero(vy)[0]
+    kk = min(int(knn), yi.size)
+    col = np.full((Zx.shape[0], int(knn)), -1, dtype=np.int32)
+    cor = np.full((Zx.shape[0], int(knn)), np.nan, dtype=np.float64)
+    if kk == 0:
+        return col, cor
+    C = Zx @ Zy[yi].T
+    order = np.lexsort((np.broadcast_to(np.arange(yi.size), C.shape), -C), axis=1)[:, :kk]
+    col[vx, :kk] = yi[order[vx]]
+    cor[vx, :kk] = np.take_along_axis(C, order, axis=1)[vx]
+    return col, cor

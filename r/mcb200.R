@@ -24,6 +24,18 @@ tgs_cor_graph = function(x, knn, k_expand, k_alpha, k_beta)
 	data.frame(col1 = factor(nms[r$mc1], levels = nms), col2 = factor(nms[r$mc2], levels = nms), weight = r$w)
 }
 
+# tgs_cor_knn for the y != x call sites (atlas projection, R/atlas.r:164-166,277,475-478,584); x == y keeps
+# going through tgs_cor_graph / mcell_add_cgraph_from_mat_bknn.  Same data.frame schema as tgstat's.
+tgs_cor_knn = function(x, y, knn, ...)
+{
+	r = .Call("mcbr_cor_knn_xy", x, y, as.integer(knn), PACKAGE = "mcb200")
+	ok = !is.na(as.vector(r$col))
+	nx = colnames(x); ny = colnames(y)
+	data.frame(col1 = factor(nx[rep(1:ncol(x), each = knn)], levels = nx)[ok],
+	           col2 = factor(ny[as.vector(r$col)], levels = ny)[ok],
+	           cor = as.vector(r$cor)[ok], rank = rep(1:knn, ncol(x))[ok])
+}
+
 # replaces mcell_add_cgraph_from_mat_bknn (R/cgraph_knn.r:10-25): the sparse matrix and the feature rows go
 # straight to the GPU, so the dense genes x cells double matrix (8 GB at 1M cells) is never built on the host
 mcell_add_cgraph_from_mat_bknn = function(mat_id, gset_id, graph_id, K, dsamp = F)

@@ -128,6 +128,26 @@ SEXP mcbr_cor_graph_dense(SEXP x, SEXP K, SEXP k_expand, SEXP k_beta)
     return edges_to_list(ne, src, dst, w, nvalid);
 }
 
+/* tgs_cor_knn(x, y, knn) with y != x (reference R/atlas.r:164-166,277,475-478,584): x, y dense genes x cells */
+SEXP mcbr_cor_knn_xy(SEXP x, SEXP y, SEXP knn)
+{
+    SEXP dx = getAttrib(x, R_DimSymbol), dy = getAttrib(y, R_DimSymbol);
+    if (INTEGER(dx)[0] != INTEGER(dy)[0]) Rf_error("MC-ERR: tgs_cor_knn: x and y must have the same number of rows");
+    const int32_t G = INTEGER(dx)[0], k = asInteger(knn);
+    const int64_t nx = INTEGER(dx)[1], ny = INTEGER(dy)[1];
+    SEXP col = PROTECT(allocMatrix(INTSXP, k, nx)), cor = PROTECT(allocMatrix(REALSXP, k, nx));   /* [nx][knn] row-major */
+    float* cf = (float*)R_alloc((size_t)nx * k, sizeof(float));
+    if (mcb_cor_knn_xy(ctx(), REAL(x), nx, REAL(y), ny, G, k, INTEGER(col), cf) != 0) { UNPROTECT(2); Rf_error("%s", mcb_last_error()); }
+    for (int64_t q = 0; q < nx * k; ++q) {
+        REAL(cor)[q] = INTEGER(col)[q] < 0 ? NA_REAL : (double)cf[q];
+        INTEGER(col)[q] = INTEGER(col)[q] < 0 ? NA_INTEGER : INTEGER(col)[q] + 1;
+    }
+    SEXP res = PROTECT(mkNamed(VECSXP, (const char*[]){"col", "cor", ""}));
+    SET_VECTOR_ELT(res, 0, col); SET_VECTOR_ELT(res, 1, cor);
+    UNPROTECT(3);
+    return res;
+}
+
 /* tgs_graph_cover_resample(..., method = "full") (reference R/coclust_graph_cov.r:41).
  * samples: integer matrix n_s x n_resamp (one resample per COLUMN, 1-based, ascending); seeds: numeric */
 SEXP mcbr_coclust(SEXP n_nodes, SEXP col1, SEXP col2, SEXP weight, SEXP samples, SEXP seeds, SEXP min_mc_size,
