@@ -13,6 +13,7 @@
  *     R/gset.r:151-214 gset_get_feat_mat + R/cgraph_knn.r:13-14 log2(1+7u) -> mcb_cgraph_create
  *     R/cgraph_knn.r:10-25 mcell_add_cgraph_from_mat_bknn                 -> mcb_cgraph_bknn (one shot)
  *     R/atlas.r:164-166   tgs_cor_knn(x, y, knn), y != x                     -> mcb_cor_knn_xy
+ *     R/gstats.r:65-205   scm_gene_stat per-gene statistics                  -> mcb_gene_stats
  *     R/coclust_graph_cov.r:41 tgs_graph_cover_resample(method = "full")  -> mcb_coclust_*
  *
  * Conventions
@@ -123,6 +124,17 @@ int  mcb_cgraph_edges(mcb_cgraph* g, int32_t* host_src, int32_t* host_dst, doubl
 /* test hook: dense correlation block C[a_rows][b_rows] of the first rows of Z through one kernel:
  * impl 0 = tcgen05 3-pass split-TF32, 2 = tcgen05 1-pass TF32, 1 = SIMT fp32.  Call before _mutual. */
 int  mcb_cgraph_debug_cor(mcb_cgraph* g, int impl, int64_t a_rows, int64_t b_rows, float* host_c);
+
+/* scm_gene_stat's per-gene statistics (reference R/gstats.r:65-205, up to but excluding the rolling-median
+ * trends of :153-190, which are O(genes) and stay with the caller).  m: raw matrix; ds: the result of
+ * mcb_csc_downsample(m, n, seed, add_non_dsamp = 0), or NULL (the ds_* columns are then NaN); sub_cells / n_sub:
+ * the cells sz_cor is computed on (R draws 50,000 when there are more, :143-146; host-supplied index set, 0-based,
+ * distinct), NULL = all cells.  out is [12][ngenes] doubles, unrounded, one row per statistic in this order:
+ * tot, var, niche_stat, n_mean, is_on_count, sz_cor, ds_top1, ds_top2, ds_top3, ds_mean, ds_var, ds_is_on_count
+ * (definitions: R/gstats.r:83-87 quant_mean with k_reg = 10, :113-127).  All genes are reported; the caller
+ * applies f_g = tot > 10 (:95).                                                                     */
+int  mcb_gene_stats(mcb_ctx* ctx, const mcb_csc* m, const mcb_csc* ds, double niche_quantile, double k_std_n,
+                    const int32_t* sub_cells, int64_t n_sub, double* out);
 
 /* tgs_cor_knn(x, y, knn) with y != x (reference call sites R/atlas.r:164-166,277,475-478,584): for every
  * cell of x (nx cells, one contiguous vector of G doubles each) the knn cells of y with the highest

@@ -20,7 +20,7 @@ SYMBOLS = [
     "mcb_cgraph_valid_cells", "mcb_cgraph_features", "mcb_cgraph_knn", "mcb_cgraph_knn_begin", "mcb_cgraph_knn_thr_buffer",
     "mcb_cgraph_knn_filter", "mcb_cgraph_knn_recv_buffer", "mcb_cgraph_knn_finish", "mcb_cgraph_knn_buffer",
     "mcb_cgraph_download_knn", "mcb_cgraph_knn_stats", "mcb_cgraph_mutual", "mcb_cgraph_thr_buffer",
-    "mcb_cgraph_prune", "mcb_cgraph_edges", "mcb_cgraph_debug_cor", "mcb_cor_knn_xy", "mcb_cgraph_bknn", "mcb_free",
+    "mcb_cgraph_prune", "mcb_cgraph_edges", "mcb_cgraph_debug_cor", "mcb_cor_knn_xy", "mcb_gene_stats", "mcb_cgraph_bknn", "mcb_free",
     "mcb_coclust_run", "mcb_graph_cover", "mcb_coclust_destroy", "mcb_coclust_buffers", "mcb_coclust_assignments",
     "mcb_coclust_extract", "mcb_coclust_pairs",
 ]
@@ -340,6 +340,20 @@ def cgraph_bknn_oneshot(ctx, ngenes, indptr, indices, data, feat_rows, K, k_expa
         lib().mcb_free(pd)
         lib().mcb_free(pw)
     return src, dst, w, int(nv.value)
+
+
+GENE_STAT_COLUMNS = ("tot", "var", "niche_stat", "n_mean", "is_on_count", "sz_cor", "ds_top1", "ds_top2", "ds_top3",
+                     "ds_mean", "ds_var", "ds_is_on_count")
+
+
+def gene_stats(ctx, csc, ds=None, niche_quantile=0.2, k_std_n=1000.0, sub_cells=None):
+    """mcb_gene_stats: dict of per-gene arrays (all genes, unrounded); ds = csc.downsample(n, seed, add_non_dsamp=False)."""
+    out = np.empty((len(GENE_STAT_COLUMNS), csc.ngenes), dtype=np.float64)
+    sub = None if sub_cells is None else as_c(sub_cells, np.int32)
+    check(lib().mcb_gene_stats(ctx.h, csc.h, ds.h if ds is not None else None, C.c_double(niche_quantile), C.c_double(k_std_n),
+                               ptr(sub, C.c_int32) if sub is not None else None, C.c_int64(0 if sub is None else sub.size),
+                               ptr(out, C.c_double)))
+    return {k: out[q] for q, k in enumerate(GENE_STAT_COLUMNS)}
 
 
 def cor_knn_xy(ctx, x_cells, y_cells, knn):

@@ -252,6 +252,98 @@ def gset_get_feat_mat(gset_id, mat_id, downsamp=False, add_non_dsamp=False, down
 
 
 # ------------------------------------------------------------------------------------------------
+# scm_gene_stat (reference R/gstats.r:65-205)
+# ------------------------------------------------------------------------------------------------
+def _rollmedian(x, k, left, right):
+    """zoo::rollmedian(x, k, fill = c(left, NA, right)), k odd (R/gstats.r:157,168,182)"""
+    h = k // 2
+    out = np.empty(x.size, dtype=np.float64)
+    out[:h] = left
+    out[x.size - h:] = right
+    if x.size > 2 * h:
+        out[h:x.size - h] = np.median(np.lib.stride_tricks.sliding_window_view(x, k), axis=1)
+    return out
+
+
+def _trend_norm(values, order):
+    """values[order] - rolling median (window 101) of values[order], ends filled with the medians of the first 101 /
+    last 102 entries exactly as R/gstats.r:153-161 index them."""
+    v = values[order]
+    cmin = np.median(v[:101])
+    cmax = np.median(v[v.size - 102:])
+    out = np.empty_like(values)
+    out[order] = v - _rollmedian(v, 101, cmin, cmax)
+    return out
+
+
+def scm_gene_stat(mat_id, niche_quantile=0.2, downsample_n=None, K_std_n=1000, ctx=None):
+    """reference R/gstats.r:65-205.  Returns a dict of equal-length columns (the R data frame), one entry per gene with
+    more than 10 UMIs (:95).  The per-gene sums, the downsampling and the niche selection run on the GPU
+    (mcb_gene_stats); the O(genes) rolling-median trends are host work as in the reference.  Like the reference the
+    `downsample_n` argument is overwritten by scm_which_downsamp_n (:97)."""
+    mat = scdb_mat(mat_id)
+    if mat is None:
+        raise McbError(f"MC-ERR: missing mat {mat_id} when computing gene statistics")
+    if niche_quantile > 1 or niche_quantile < 0:
+        raise McbError(f"niche_quantile must be between 0 and 1, got {niche_quantile}")
+    ctx = _ctx(ctx)
+    _message("Calculating gene statistics... ")
+    csc = _upload(mat, ctx)
+    ds = None
+    try:
+        csum = csc.col_sums()
+        f_oversize = (csum > np.quantile(csum, 0.95) * 2) | (csum < 100)                 # :82-83
+        N = int((~f_oversize).sum())
+        downsample_n = _lib.downsamp_depth(csum) if get_param("scm_n_downsamp_gstat") is None else get_param("scm_n_downsamp_gstat")
+        _message("will downsamp")
+        ds = csc.downsample(float(downsample_n), get_param("mc_rseed"), add_non_dsamp=False)
+        _message("done downsamp")
+        sub = None
+        if mat.ncells > 50000:                                                            # :143-146 (host-supplied index set)
+            sub = np.sort(np.random.default_rng(int(get_param("mc_rseed"))).choice(mat.ncells, 50000, replace=False)).astype(np.int32)
+        st = _lib.gene_stats(ctx, csc, ds, float(niche_quantile), float(K_std_n), sub)
+    finally:
+        if ds is not None:
+            ds.free()
+        csc.free()
+    f_g = st["tot"] > 10                                                                  # :95
+    if int(f_g.sum()) < 102:
+        raise McbError("MC-ERR: fewer than 102 genes with more than 10 UMIs, cannot compute gene statistic trends")
+    g = {k: v[f_g] for k, v in st.items()}
+    res = {"name": [mat.genes[i] for i in np.nonzero(f_g)[0]]}
+    res["tot"] = g["tot"]
+    res["var"] = np.round(g["var"], 7)
+    res["is_on_count"] = g["is_on_count"]
+    res["sz_cor"] = np.round(g["sz_cor"], 3)
+    tot_ord = np.argsort(res["tot"], kind="stable")
+    res["sz_cor_norm"] = _trend_norm(res["sz_cor"], tot_ord)
+    res["niche_stat"] = g["niche_stat"]
+    res["niche_norm"] = _trend_norm(res["niche_stat"], tot_ord)
+    res["n_mean"] = np.round(g["n_mean"], 7)
+    for k in ("ds_top1", "ds_top2", "ds_top3"):
+        res[k] = g[k]
+    res["ds_mean"] = np.round(g["ds_mean"], 7)
+    res["ds_var"] = np.round(g["ds_var"], 7)
+    m_reg = 10.0 / N                                                                      # :176
+    res["ds_log_varmean"] = np.log2((m_reg + res["ds_var"]) / (m_reg + res["ds_mean"]))
+    ds_ord = np.argsort(res["ds_mean"], kind="stable")
+    res["ds_vm_norm"] = _trend_norm(res["ds_log_varmean"], ds_ord)
+    res["ds_is_on_count"] = g["ds_is_on_count"]
+    res["downsample_n"] = np.full(res["tot"].size, float(downsample_n))
+    _message("..done")
+    return res
+
+
+def mcell_add_gene_stat(mat_id, gstat_id, force=False, ctx=None):
+    """reference R/gstats.r:19-27: compute and store the gene statistics table in scdb."""
+    if not force and _scdb_get("gstat", gstat_id) is not None:
+        return _scdb_get("gstat", gstat_id)
+    gs = scm_gene_stat(mat_id, ctx=ctx)
+    _scdb_add("gstat", gstat_id, gs)
+    return gs
+
+
+# ------------------------------------------------------------------------------------------------
 # A5 / A6: the tgstat trio
 # ------------------------------------------------------------------------------------------------
 def tgs_cor_knn(x, y=None, knn=None, ctx=None):

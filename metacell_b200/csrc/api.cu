@@ -323,6 +323,109 @@ extern "C" int mcb_csc_download(mcb_ctx* ctx, const mcb_csc* m, double* host_x, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// per-gene statistics (scm_gene_stat, reference R/gstats.r:65-205)
+// ---------------------------------------------------------------------------------------------
+static long double u128_ld(unsigned long long lo, unsigned long long hi) { return (long double)hi * 18446744073709551616.0L + (long double)lo; }
+
+extern "C" int mcb_gene_stats(mcb_ctx* ctx, const mcb_csc* m, const mcb_csc* ds, double niche_quantile, double k_std_n,
+                              const int32_t* sub_cells, int64_t n_sub, double* out)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && m && out, "mcb_gene_stats: null argument");
+    MCB_CHECK(niche_quantile >= 0.0 && niche_quantile <= 1.0, "niche_quantile must be between 0 and 1");      // R/gstats.r:78-80
+    MCB_CHECK(!ds || (ds->ncells == m->ncells && ds->nnz == m->nnz && ds->ngenes == m->ngenes),
+              "mcb_gene_stats: the downsampled matrix must share the raw matrix's structure");
+    MCB_CHECK(m->nnz < ((int64_t)1 << 32), "mcb_gene_stats: more than 2^32 stored entries");
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const int32_t ng = m->ngenes;
+    const int64_t n = m->ncells;
+    const double nan = std::nan("");
+    for (int64_t q = 0; q < (int64_t)12 * ng; ++q) out[q] = nan;
+    if (ng == 0 || n == 0) return 0;
+    // cell totals over all genes (R/gstats.r:102 colSums(mat)) and the per-cell scale K_std_n / total
+    DevBuf<int64_t> ctot(ctx, (size_t)n);
+    { StageTimer t(ctx, "col_sums"); launch_col_sums(ctx, n, m->p, m->x, ctot.p); }
+    std::vector<int64_t> htot((size_t)n);
+    MCB_CUDA(cudaMemcpyAsync(htot.data(), ctot.p, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<uint8_t> hkept;
+    if (ds) {
+        hkept.resize((size_t)n, 1);
+        if (ds->kept.p) MCB_CUDA(cudaMemcpyAsync(hkept.data(), ds->kept.p, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<double> hscale((size_t)n);
+    for (int64_t c = 0; c < n; ++c) hscale[c] = htot[c] > 0 ? k_std_n / (double)htot[c] : 0.0;
+    std::vector<uint8_t> hmask;
+    int64_t ns = n;
+    if (sub_cells) {
+        hmask.assign((size_t)n, 0);
+        for (int64_t q = 0; q < n_sub; ++q) {
+            MCB_CHECK(sub_cells[q] >= 0 && sub_cells[q] < n, "mcb_gene_stats: sz_cor cell index out of range");
+            MCB_CHECK(!hmask[sub_cells[q]], "mcb_gene_stats: duplicate sz_cor cell index");
+            hmask[sub_cells[q]] = 1;
+        }
+        ns = n_sub;
+    }
+    long double T = 0.0L, TT = 0.0L;                                  // sum and sum of squares of the totals over the sz_cor cells
+    for (int64_t c = 0; c < n; ++c)
+        if (!sub_cells || hmask[c]) { T += (long double)htot[c]; TT += (long double)htot[c] * (long double)htot[c]; }
+    int64_t n_ds = 0;
+    if (ds) for (int64_t c = 0; c < n; ++c) n_ds += hkept[c] ? 1 : 0;
+    DevBuf<double> scale(ctx, (size_t)n);
+    DevBuf<uint8_t> mask(ctx, sub_cells ? (size_t)n : 0);
+    MCB_CUDA(cudaMemcpyAsync(scale.p, hscale.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (sub_cells) MCB_CUDA(cudaMemcpyAsync(mask.p, hmask.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    // gene-major buckets
+    DevBuf<uint32_t> cnt(ctx, (size_t)ng), tx(ctx, (size_t)std::max<int64_t>(m->nnz, 1)), tds(ctx, ds ? (size_t)std::max<int64_t>(m->nnz, 1) : 0);
+    DevBuf<int32_t> tc(ctx, (size_t)std::max<int64_t>(m->nnz, 1));
+    DevBuf<int64_t> start(ctx, (size_t)ng + 1);
+    {
+        StageTimer t(ctx, "gene_bucket", 3);
+        launch_gene_bucket(ctx, ng, n, m->nnz, m->p, m->i, m->x, ds ? ds->x : nullptr, cnt.p, start.p, tx.p, tc.p, ds ? tds.p : nullptr);
+    }
+    const long long niche_r = (long long)std::nearbyint((double)n * niche_quantile);      // R round(): half to even
+    DevBuf<GeneRaw> raw(ctx, (size_t)ng);
+    {
+        StageTimer t(ctx, "gene_stats");
+        launch_gene_stats(ctx, ng, start.p, tx.p, tc.p, ds ? tds.p : nullptr, scale.p, ctot.p, sub_cells ? mask.p : nullptr, niche_r, raw.p);
+    }
+    std::vector<GeneRaw> h((size_t)ng);
+    MCB_CUDA(cudaMemcpyAsync(h.data(), raw.p, sizeof(GeneRaw) * (size_t)ng, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    double* o_tot = out; double* o_var = out + ng; double* o_niche = out + 2 * (int64_t)ng; double* o_nmean = out + 3 * (int64_t)ng;
+    double* o_on = out + 4 * (int64_t)ng; double* o_szcor = out + 5 * (int64_t)ng; double* o_t1 = out + 6 * (int64_t)ng;
+    double* o_t2 = out + 7 * (int64_t)ng; double* o_t3 = out + 8 * (int64_t)ng; double* o_dmean = out + 9 * (int64_t)ng;
+    double* o_dvar = out + 10 * (int64_t)ng; double* o_don = out + 11 * (int64_t)ng;
+    const long double nl = (long double)n, nsl = (long double)ns, ndl = (long double)n_ds;
+    const long double vart = ns > 1 ? TT - T * T / nsl : 0.0L;
+    for (int32_t g = 0; g < ng; ++g) {
+        const GeneRaw& r = h[g];
+        const long double tot = (long double)r.tot;
+        o_tot[g] = (double)r.tot;
+        o_var[g] = n > 1 ? (double)((u128_ld(r.sumsq_lo, r.sumsq_hi) - tot * tot / nl) / (nl - 1.0L)) : nan;
+        o_niche[g] = (double)((10.0L + (long double)r.up) / (10.0L + tot));
+        o_nmean[g] = r.nmean_sum / (double)n;
+        o_on[g] = (double)r.on;
+        {
+            const long double sx = (long double)r.sx_s;
+            const long double varx = u128_ld(r.sxx_lo, r.sxx_hi) - sx * sx / nsl;
+            const long double cov = u128_ld(r.sxt_lo, r.sxt_hi) - sx * T / nsl;
+            o_szcor[g] = (ns > 1 && varx > 0.0L && vart > 0.0L) ? (double)(cov / sqrtl(varx * vart)) : nan;
+        }
+        if (ds) {
+            o_t1[g] = n_ds >= 1 ? (double)r.top[0] : nan;
+            o_t2[g] = n_ds >= 2 ? (double)r.top[1] : nan;
+            o_t3[g] = n_ds >= 3 ? (double)r.top[2] : nan;
+            const long double dt = (long double)r.dtot;
+            o_dmean[g] = n_ds >= 1 ? (double)(dt / ndl) : nan;
+            o_dvar[g] = n_ds > 1 ? (double)((u128_ld(r.dsumsq_lo, r.dsumsq_hi) - dt * dt / ndl) / (ndl - 1.0L)) : nan;
+            o_don[g] = (double)r.d_on;
+        }
+    }
+    MCB_API_END
+}
+
+// ---------------------------------------------------------------------------------------------
 // balanced K-nn cell graph
 // ---------------------------------------------------------------------------------------------
 

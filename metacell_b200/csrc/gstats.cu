@@ -1,0 +1,272 @@
+// gstats.cu -- per-gene statistics of scm_gene_stat (reference R/gstats.r:65-205): the step
+// right before the hot path (it selects the feature genes) and already a client of scm_downsamp (:99).
+//
+// What the reference computes per gene over the raw matrix (all n cells) and the downsampled one (n_ds kept
+// cells), restated from R/gstats.r:108-131:
+//   tot = rowSums, var = rowVars (n-1 denominator, zeros included), is_on_count = #(x > 0),
+//   niche_stat = (10 + sum of the round(n*q) largest values) / (10 + tot)            (quant_mean, :83-87)
+//   n_mean = rowMeans of x * K_std_n / colSums(mat)                                   (:102, :120)
+//   ds_top1/2/3 = three largest downsampled values, ds_mean, ds_var, ds_is_on_count  (:121-127)
+//   sz_cor = cor(x[g, subs], colSums[subs])                                           (:143-151)
+// The rolling-median trends after that (:153-190) are O(genes) host work and stay with the caller.
+//
+// Layout: the CSC is cell-major, the statistics are per gene, so the entries are first bucketed by gene
+// (count, scan, scatter: values, cell ids and the downsampled values of the same entry land in gene-major
+// arrays), then one CTA per gene streams its contiguous segment.  Integer sums are exact (64/128-bit); only
+// n_mean is a floating-point sum.  HBM-bound: 12 B per entry read by the scatter, 12 B written, 12 B read by
+// the per-gene pass, plus the radix passes of the niche selection over the gene's (L2-resident) segment.
+#include "internal.h"
+
+namespace mcb {
+
+typedef unsigned __int128 u128;
+
+__global__ void gene_count_kernel(int64_t nnz, const int32_t* __restrict__ gi, uint32_t* __restrict__ cnt)
+{
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&cnt[gi[e]], 1u);
+}
+
+// single block: start[g] = exclusive prefix of cnt (int64), start[ngenes] = total
+__global__ void __launch_bounds__(1024) gene_scan_kernel(int32_t ngenes, const uint32_t* __restrict__ cnt, int64_t* __restrict__ start)
+{
+    __shared__ long long warp_tot[33];
+    __shared__ long long s_run;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < ngenes; base += 1024) {
+        const int g = base + threadIdx.x;
+        const long long v = g < ngenes ? (long long)cnt[g] : 0;
+        long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        long long pre = 0, all = 0;
+        for (int q = 0; q < 32; ++q) { const long long t = warp_tot[q]; if (q < w) pre += t; all += t; }
+        const long long run = s_run;
+        if (g < ngenes) start[g] = run + pre + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_run = run + all;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) start[ngenes] = s_run;
+}
+
+// one warp per cell: entries go to their gene's segment (order inside a segment is arbitrary)
+__global__ void gene_scatter_kernel(int64_t ncells, const int64_t* __restrict__ p, const int32_t* __restrict__ gi,
+                                    const uint32_t* __restrict__ x, const uint32_t* __restrict__ dsx,
+                                    const int64_t* __restrict__ start, uint32_t* __restrict__ cursor,
+                                    uint32_t* __restrict__ tx, int32_t* __restrict__ tc, uint32_t* __restrict__ tds)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = warp; c < ncells; c += nwarps) {
+        for (int64_t e = p[c] + lane; e < p[c + 1]; e += 32) {
+            const int32_t g = gi[e];
+            const int64_t pos = start[g] + (int64_t)atomicAdd(&cursor[g], 1u);
+            tx[pos] = x[e];
+            tc[pos] = (int32_t)c;
+            if (tds) tds[pos] = dsx[e];
+        }
+    }
+}
+
+constexpr int GS_THREADS = 256;
+
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* sm /* [8] */)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long t = 0;
+#pragma unroll
+    for (int q = 0; q < GS_THREADS / 32; ++q) t += sm[q];
+    return t;
+}
+__device__ __forceinline__ u128 block_sum_u128(u128 v, unsigned long long* sm /* [16] */)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long lo = __shfl_xor_sync(0xffffffffu, (unsigned long long)v, o);
+        const unsigned long long hi = __shfl_xor_sync(0xffffffffu, (unsigned long long)(v >> 64), o);
+        v += ((u128)hi << 64) | lo;
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { sm[2 * (threadIdx.x >> 5)] = (unsigned long long)v; sm[2 * (threadIdx.x >> 5) + 1] = (unsigned long long)(v >> 64); }
+    __syncthreads();
+    u128 t = 0;
+#pragma unroll
+    for (int q = 0; q < GS_THREADS / 32; ++q) t += ((u128)sm[2 * q + 1] << 64) | sm[2 * q];
+    return t;
+}
+__device__ __forceinline__ double block_sum_f64(double v, double* sm /* [8] */)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < GS_THREADS / 32; ++q) t += sm[q];
+    return t;
+}
+__device__ __forceinline__ void top3_push(uint32_t t[3], uint32_t v)
+{
+    if (v > t[0]) { t[2] = t[1]; t[1] = t[0]; t[0] = v; }
+    else if (v > t[1]) { t[2] = t[1]; t[1] = v; }
+    else if (v > t[2]) t[2] = v;
+}
+
+// one CTA per gene (grid-stride).  niche_r = round(n * niche_quantile) (host, R rounding).
+__global__ void __launch_bounds__(GS_THREADS)
+gene_stats_kernel(int32_t ngenes, const int64_t* __restrict__ start, const uint32_t* __restrict__ tx,
+                  const int32_t* __restrict__ tc, const uint32_t* __restrict__ tds, const double* __restrict__ scale,
+                  const int64_t* __restrict__ ctot, const uint8_t* __restrict__ sub_mask, long long niche_r,
+                  GeneRaw* __restrict__ out)
+{
+    __shared__ unsigned long long sm64[16];
+    __shared__ double smd[8];
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_top[GS_THREADS / 32][3];
+    __shared__ unsigned long long s_prefix;
+    __shared__ long long s_k;
+    for (int g = blockIdx.x; g < ngenes; g += gridDim.x) {
+        const int64_t s = start[g], e = start[g + 1];
+        unsigned long long tot = 0, sx_s = 0, dtot = 0;
+        u128 sumsq = 0, sxx = 0, sxt = 0, dsumsq = 0;
+        double nm = 0.0;
+        unsigned long long on = 0, d_on = 0;
+        uint32_t vmax = 0;
+        uint32_t t3[3] = {0u, 0u, 0u};
+        for (int64_t q = s + threadIdx.x; q < e; q += GS_THREADS) {
+            const unsigned long long v = tx[q];
+            const int32_t c = tc[q];
+            tot += v; sumsq += (u128)(v * v); on += v > 0;
+            nm += (double)v * scale[c];
+            vmax = max(vmax, (uint32_t)v);
+            if (!sub_mask || sub_mask[c]) { sx_s += v; sxx += (u128)(v * v); sxt += (u128)v * (u128)(unsigned long long)ctot[c]; }
+            if (tds) {
+                const unsigned long long d = tds[q];
+                dtot += d; dsumsq += (u128)(d * d); d_on += d > 0;
+                top3_push(t3, (uint32_t)d);
+            }
+        }
+        GeneRaw r;
+        r.tot = block_sum_u64(tot, sm64);
+        { const u128 t = block_sum_u128(sumsq, sm64); r.sumsq_lo = (unsigned long long)t; r.sumsq_hi = (unsigned long long)(t >> 64); }
+        r.on = (uint32_t)block_sum_u64(on, sm64);
+        r.nmean_sum = block_sum_f64(nm, smd);
+        r.sx_s = block_sum_u64(sx_s, sm64);
+        { const u128 t = block_sum_u128(sxx, sm64); r.sxx_lo = (unsigned long long)t; r.sxx_hi = (unsigned long long)(t >> 64); }
+        { const u128 t = block_sum_u128(sxt, sm64); r.sxt_lo = (unsigned long long)t; r.sxt_hi = (unsigned long long)(t >> 64); }
+        r.dtot = block_sum_u64(dtot, sm64);
+        { const u128 t = block_sum_u128(dsumsq, sm64); r.dsumsq_lo = (unsigned long long)t; r.dsumsq_hi = (unsigned long long)(t >> 64); }
+        r.d_on = (uint32_t)block_sum_u64(d_on, sm64);
+        // top-3 downsampled values: warp merge, then warp leaders through shared memory
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const uint32_t a = __shfl_xor_sync(0xffffffffu, t3[0], o), b = __shfl_xor_sync(0xffffffffu, t3[1], o),
+                           c3 = __shfl_xor_sync(0xffffffffu, t3[2], o);
+            top3_push(t3, a); top3_push(t3, b); top3_push(t3, c3);
+        }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { s_top[threadIdx.x >> 5][0] = t3[0]; s_top[threadIdx.x >> 5][1] = t3[1]; s_top[threadIdx.x >> 5][2] = t3[2]; }
+        __syncthreads();
+        r.top[0] = r.top[1] = r.top[2] = 0u;
+        for (int q = 0; q < GS_THREADS / 32; ++q) { top3_push(r.top, s_top[q][0]); top3_push(r.top, s_top[q][1]); top3_push(r.top, s_top[q][2]); }
+        // niche: sum of the niche_r largest values (zeros of the other cells included, so at most all of tot)
+        {
+            uint32_t m = vmax;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) sm64[threadIdx.x >> 5] = m;
+            __syncthreads();
+            for (int q = 0; q < GS_THREADS / 32; ++q) m = max(m, (uint32_t)sm64[q]);
+            vmax = m;
+        }
+        const long long L = (long long)(e - s);
+        unsigned long long up;
+        if (niche_r <= 0) up = 0;
+        else if (niche_r >= (long long)r.on) up = r.tot;
+        else {
+            // radix select of the niche_r-th largest = (L - niche_r)-th smallest (0-based) 32-bit value
+            int top_byte = 3;
+            while (top_byte > 0 && (vmax >> (8 * top_byte)) == 0) --top_byte;
+            if (threadIdx.x == 0) { s_prefix = 0ull; s_k = L - niche_r; }
+            __syncthreads();
+            for (int b = top_byte; b >= 0; --b) {
+                const int shift = 8 * b;
+                const uint32_t decided = b == 3 ? 0u : (0xffffffffu << (shift + 8));
+                const uint32_t prefix = (uint32_t)s_prefix;
+                hist[threadIdx.x] = 0;
+                __syncthreads();
+                for (int64_t q = s + threadIdx.x; q < e; q += GS_THREADS) {
+                    const uint32_t v = tx[q];
+                    if ((v & decided) == prefix) atomicAdd(&hist[(v >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                if (threadIdx.x < 32) {
+                    int dg; long long cum;
+                    const long long k = s_k;
+                    warp_find_bucket<8>(hist, k, dg, cum);
+                    __syncwarp();
+                    if (threadIdx.x == 0) { s_prefix = (unsigned long long)(prefix | ((uint32_t)dg << shift)); s_k = k - cum; }
+                }
+                __syncthreads();
+            }
+            const uint32_t thr = (uint32_t)s_prefix;          // the niche_r-th largest value
+            unsigned long long gsum = 0, gcnt = 0;
+            for (int64_t q = s + threadIdx.x; q < e; q += GS_THREADS) {
+                const uint32_t v = tx[q];
+                if (v > thr) { gsum += v; ++gcnt; }
+            }
+            gsum = block_sum_u64(gsum, sm64);
+            gcnt = block_sum_u64(gcnt, sm64);
+            up = gsum + ((unsigned long long)niche_r - gcnt) * (unsigned long long)thr;
+        }
+        r.up = up;
+        r.pad = 0;
+        if (threadIdx.x == 0) out[g] = r;
+        __syncthreads();
+    }
+}
+
+void launch_gene_bucket(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, int64_t nnz, const int64_t* p, const int32_t* gi,
+                        const uint32_t* x, const uint32_t* dsx, uint32_t* cnt, int64_t* start, uint32_t* tx, int32_t* tc,
+                        uint32_t* tds)
+{
+    MCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * (size_t)std::max(ngenes, 1), ctx->stream));
+    if (nnz > 0) {
+        const int grid = (int)std::min<int64_t>(ceil_div(nnz, 256), (int64_t)ctx->num_sms * 16);
+        gene_count_kernel<<<grid, 256, 0, ctx->stream>>>(nnz, gi, cnt);
+        MCB_LAUNCH_CHECK();
+    }
+    gene_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ngenes, cnt, start);
+    MCB_LAUNCH_CHECK();
+    MCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * (size_t)std::max(ngenes, 1), ctx->stream));    // reused as cursor
+    if (nnz > 0) {
+        const int grid = (int)std::min<int64_t>(ceil_div(ncells, 8), (int64_t)ctx->num_sms * 16);
+        gene_scatter_kernel<<<grid, 256, 0, ctx->stream>>>(ncells, p, gi, x, dsx, start, cnt, tx, tc, tds);
+        MCB_LAUNCH_CHECK();
+    }
+}
+
+void launch_gene_stats(mcb_ctx* ctx, int32_t ngenes, const int64_t* start, const uint32_t* tx, const int32_t* tc,
+                       const uint32_t* tds, const double* scale, const int64_t* ctot, const uint8_t* sub_mask, int64_t niche_r,
+                       void* out_raw)
+{
+    if (ngenes == 0) return;
+    const int grid = std::min(ngenes, ctx->num_sms * 8);
+    gene_stats_kernel<<<grid, GS_THREADS, 0, ctx->stream>>>(ngenes, start, tx, tc, tds, scale, ctot, sub_mask, (long long)niche_r,
+                                                            (GeneRaw*)out_raw);
+    MCB_LAUNCH_CHECK();
+}
+
+}  // namespace mcb

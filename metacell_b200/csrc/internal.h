@@ -150,6 +150,21 @@ void launch_topk_big(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t M, const
                      int64_t row0, int32_t kc_out, int32_t Kc, const float* thr_rows /* [own rows] or null */,
                      int32_t* knn_col, float* knn_cor, bool with_self = true);
 
+// gstats.cu: per-gene statistics (scm_gene_stat, reference R/gstats.r:65-205)
+struct GeneRaw {            // exact per-gene sums, finished on the host
+    unsigned long long tot, sumsq_lo, sumsq_hi, up, sx_s, sxx_lo, sxx_hi, sxt_lo, sxt_hi;
+    unsigned long long dtot, dsumsq_lo, dsumsq_hi;
+    double nmean_sum;
+    uint32_t on, d_on, top[3], pad;
+};
+static_assert(sizeof(GeneRaw) == 128, "GeneRaw layout");
+void launch_gene_bucket(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, int64_t nnz, const int64_t* p, const int32_t* gi,
+                        const uint32_t* x, const uint32_t* dsx, uint32_t* cnt, int64_t* start, uint32_t* tx, int32_t* tc,
+                        uint32_t* tds);
+void launch_gene_stats(mcb_ctx* ctx, int32_t ngenes, const int64_t* start, const uint32_t* tx, const int32_t* tc,
+                       const uint32_t* tds, const double* scale, const int64_t* ctot, const uint8_t* sub_mask, int64_t niche_r,
+                       void* out_raw);
+
 // balance.cu
 void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t Kc, int32_t H, int32_t rank_bits,
                        uint32_t* table);

@@ -64,3 +64,58 @@ def cor_knn_xy(X, Y, knn):
     col[vx, :kk] = yi[order[vx]]
     cor[vx, :kk] = np.take_along_axis(C, order, axis=1)[vx]
     return col, cor
+
+
+def r_round_half_even(v):
+    return float(np.rint(v))          # R's round(): IEC 60559 half-to-even, which is numpy's rint
+
+
+def gene_stats_dense(raw, ds, niche_quantile=0.2, k_std_n=1000.0, sub_cells=None):
+    """Literal dense restatement of the per-gene block of scm_gene_stat (reference R/gstats.r:83-87, :102, :113-127,
+    :143-151) -- small inputs only.  raw: [genes][cells] counts (all cells); ds: [genes][kept cells] downsampled
+    counts (or None).  Returns a dict of unrounded per-gene arrays, one per data-frame column."""
+    raw = np.asarray(raw, dtype=np.float64)
+    ng, n = raw.shape
+    r = int(r_round_half_even(n * niche_quantile))
+    out = {}
+    out["tot"] = raw.sum(axis=1)
+    out["var"] = raw.var(axis=1, ddof=1)
+    srt = np.sort(raw, axis=1)
+    up = srt[:, n - r:].sum(axis=1) if r > 0 else np.zeros(ng)          # sum(tail(sort(x), n = round(n * q)))
+    out["niche_stat"] = (10.0 + up) / (10.0 + out["tot"])
+    csum = raw.sum(axis=0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        scale = np.where(csum > 0, k_std_n / csum, 0.0)
+    out["n_mean"] = (raw * scale[None, :]).mean(axis=1)
+    out["is_on_count"] = (raw > 0).sum(axis=1).astype(np.float64)
+    cells = np.arange(n) if sub_cells is None else np.asarray(sub_cells)
+    ct = csum[cells]
+    sz = np.full(ng, np.nan)
+    for g in range(ng):
+        x = raw[g, cells]
+        if x.std() > 0 and ct.std() > 0:
+            sz[g] = np.corrcoef(x, ct)[0, 1]
+    out["sz_cor"] = sz
+    if ds is not None:
+        ds = np.asarray(ds, dtype=np.float64)
+        n_ds = ds.shape[1]
+        dsrt = np.sort(ds, axis=1)
+        out["ds_top1"] = dsrt[:, n_ds - 1]
+        out["ds_top2"] = dsrt[:, n_ds - 2]                                # rowOrderStats(which = n_ds - 1)
+        out["ds_top3"] = dsrt[:, n_ds - 3]
+        out["ds_mean"] = ds.mean(axis=1)
+        out["ds_var"] = ds.var(axis=1, ddof=1)
+        out["ds_is_on_count"] = (ds > 0).sum(axis=1).astype(np.float64)
+    return out
+
+
+def rollmedian_fill(x, k, left, right):
+    """zoo::rollmedian(x, k, fill = c(left, NA, right)) for odd k: centred running median, ends filled."""
+    x = np.asarray(x, dtype=np.float64)
+    h = k // 2
+    out = np.empty_like(x)
+    out[:h] = left
+    out[x.size - h:] = right
+    for i in range(h, x.size - h):
+        out[i] = np.median(x[i - h:i + h + 1])
+    return out

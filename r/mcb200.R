@@ -24,6 +24,17 @@ tgs_cor_graph = function(x, knn, k_expand, k_alpha, k_beta)
 	data.frame(col1 = factor(nms[r$mc1], levels = nms), col2 = factor(nms[r$mc2], levels = nms), weight = r$w)
 }
 
+# replaces the stat_on_genes / doMC block of scm_gene_stat (R/gstats.r:95-151): one call returns the per-gene
+# columns for every gene; the caller keeps f_g = tot > 10, the rounding, and the rollmedian trends (:153-190) in R
+mcb_gene_stat_block = function(mat, downsample_n, niche_quantile = 0.2, K_std_n = 1000, subs = NULL)
+{
+	r = .Call("mcbr_gene_stats", mat@p, mat@i, mat@x, nrow(mat), as.numeric(downsample_n), as.numeric(get_param("mc_rseed")),
+	          as.numeric(niche_quantile), as.numeric(K_std_n), if (is.null(subs)) NULL else as.integer(subs), PACKAGE = "mcb200")
+	colnames(r) = c("tot", "var", "niche_stat", "n_mean", "is_on_count", "sz_cor", "ds_top1", "ds_top2", "ds_top3",
+	                "ds_mean", "ds_var", "ds_is_on_count")
+	data.frame(name = rownames(mat), r, stringsAsFactors = F)
+}
+
 # tgs_cor_knn for the y != x call sites (atlas projection, R/atlas.r:164-166,277,475-478,584); x == y keeps
 # going through tgs_cor_graph / mcell_add_cgraph_from_mat_bknn.  Same data.frame schema as tgstat's.
 tgs_cor_knn = function(x, y, knn, ...)

@@ -128,6 +128,30 @@ SEXP mcbr_cor_graph_dense(SEXP x, SEXP K, SEXP k_expand, SEXP k_beta)
     return edges_to_list(ne, src, dst, w, nvalid);
 }
 
+/* per-gene block of scm_gene_stat (reference R/gstats.r:95-131, :143-151): raw dgCMatrix slots, depth n, seed,
+ * niche quantile, K_std_n and the (1-based) cells sz_cor is computed on (NULL = all).  Returns a 12 x ngenes matrix,
+ * rows in the order documented at mcb_gene_stats (include/mcb200.h). */
+SEXP mcbr_gene_stats(SEXP p, SEXP i, SEXP x, SEXP ngenes, SEXP n, SEXP seed, SEXP niche_quantile, SEXP k_std_n, SEXP sub_cells)
+{
+    R_xlen_t ncells;
+    int64_t* p64 = widen_p(p, &ncells);
+    mcb_csc *m = NULL, *ds = NULL;
+    CHECK(mcb_csc_upload(ctx(), asInteger(ngenes), ncells, p64, INTEGER(i), REAL(x), &m));
+    if (mcb_csc_downsample(ctx(), m, asReal(n), (uint64_t)asReal(seed), 0, &ds) != 0) { mcb_csc_free(m); Rf_error("%s", mcb_last_error()); }
+    int32_t* sub = NULL; int64_t nsub = 0;
+    if (!isNull(sub_cells)) {
+        nsub = XLENGTH(sub_cells);
+        sub = (int32_t*)R_alloc((size_t)(nsub ? nsub : 1), sizeof(int32_t));
+        for (int64_t q = 0; q < nsub; ++q) sub[q] = INTEGER(sub_cells)[q] - 1;
+    }
+    SEXP out = PROTECT(allocMatrix(REALSXP, asInteger(ngenes), 12));          /* column-major: one column per statistic */
+    int rc = mcb_gene_stats(ctx(), m, ds, asReal(niche_quantile), asReal(k_std_n), sub, nsub, REAL(out));
+    mcb_csc_free(ds); mcb_csc_free(m);
+    UNPROTECT(1);
+    if (rc) Rf_error("%s", mcb_last_error());
+    return out;
+}
+
 /* tgs_cor_knn(x, y, knn) with y != x (reference R/atlas.r:164-166,277,475-478,584): x, y dense genes x cells */
 SEXP mcbr_cor_knn_xy(SEXP x, SEXP y, SEXP knn)
 {

@@ -98,3 +98,67 @@ def test_raw_knn_graph_and_confusion(ctx, oracle, tmp_path):
     assert np.array_equal(confu, want)
     with pytest.raises(api.McbError, match="MC-ERR"):
         api.mcell_mc_confusion_mat("nope", "graw", K)
+
+
+def _dense(m, data=None):
+    d = np.zeros((m.ngenes, m.ncells))
+    x = m.data if data is None else data
+    for c in range(m.ncells):
+        s, e = m.indptr[c], m.indptr[c + 1]
+        d[m.indices[s:e], c] = x[s:e]
+    return d
+
+
+@pytest.mark.parametrize("ncells,ngenes,q,use_sub", [(400, 300, 0.2, False), (777, 150, 0.1, True), (64, 40, 0.5, False)])
+def test_gene_stats_match_dense_restatement(ctx, ncells, ngenes, q, use_sub):
+    """mcb_gene_stats against the literal dense restatement of R/gstats.r:83-151: integer statistics exact, floating
+    point ones to 1e-10 relative (the reference rounds them to 3-7 decimals)"""
+    from metacell_b200 import _lib, synth
+    from oracle import oracle_np
+    m = synth.make_umi_matrix(ncells, ngenes, n_types=4, median_umis=900.0, seed=ncells)
+    csc = _lib.Csc.upload(ctx, m.ngenes, m.indptr, m.indices, m.data.astype(np.float64))
+    csum = csc.col_sums()
+    n = float(np.quantile(csum, 0.3))                               # fractional depth, drops ~30 % of the cells
+    ds = csc.downsample(n, 19, add_non_dsamp=False)
+    dsx, kept = ds.download()
+    sub = np.sort(np.random.default_rng(3).choice(ncells, ncells // 2, replace=False)).astype(np.int32) if use_sub else None
+    got = _lib.gene_stats(ctx, csc, ds, q, 1000.0, sub)
+    want = oracle_np.gene_stats_dense(_dense(m), _dense(m, dsx)[:, kept], q, 1000.0, sub)
+    for k in ("tot", "is_on_count", "ds_top1", "ds_top2", "ds_top3", "ds_is_on_count"):
+        assert np.array_equal(got[k], want[k]), k
+    for k in ("var", "niche_stat", "n_mean", "ds_mean", "ds_var", "sz_cor"):
+        a, b = got[k], want[k]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), k
+        ok = ~np.isnan(a)
+        assert np.allclose(a[ok], b[ok], rtol=1e-10, atol=1e-12), (k, np.abs(a[ok] - b[ok]).max())
+    # without a downsampled matrix the ds_* columns are NA
+    got2 = _lib.gene_stats(ctx, csc, None, q, 1000.0, sub)
+    assert np.all(np.isnan(got2["ds_mean"])) and np.array_equal(got2["tot"], got["tot"])
+    ds.free(); csc.free()
+
+
+def test_scm_gene_stat_mirror(ctx, tmp_path):
+    """scm_gene_stat through the R-named mirror: schema (R/gstats.r:195-199), gene filter, rounding and the
+    rolling-median trends against oracle_np.rollmedian_fill"""
+    from metacell_b200 import api, synth
+    from oracle import oracle_np
+    m = synth.make_umi_matrix(1500, 400, n_types=6, median_umis=1500.0, seed=8)
+    api.scdb_init(str(tmp_path), force_reinit=True)
+    api.scdb_add_mat("m", api.tgScMat(m.indptr, m.indices, m.data, ngenes=m.ngenes))
+    gs = api.mcell_add_gene_stat("m", "gs", ctx=ctx)
+    cols = ["name", "tot", "var", "is_on_count", "sz_cor", "sz_cor_norm", "niche_stat", "niche_norm", "n_mean", "ds_top1",
+            "ds_top2", "ds_top3", "ds_mean", "ds_var", "ds_log_varmean", "ds_vm_norm", "ds_is_on_count", "downsample_n"]
+    assert list(gs.keys()) == cols
+    ng = len(gs["name"])
+    assert all(len(gs[k]) == ng for k in cols) and ng >= 102
+    assert np.all(gs["tot"] > 10)
+    assert np.all(gs["ds_top1"] >= gs["ds_top2"]) and np.all(gs["ds_top2"] >= gs["ds_top3"])
+    assert np.all(gs["niche_stat"] > 0) and np.all(gs["niche_stat"] <= 1)
+    assert np.allclose(gs["var"], np.round(gs["var"], 7)) and np.allclose(gs["sz_cor"], np.round(gs["sz_cor"], 3))
+    order = np.argsort(gs["tot"], kind="stable")
+    v = gs["niche_stat"][order]
+    trend = oracle_np.rollmedian_fill(v, 101, np.median(v[:101]), np.median(v[-102:]))
+    assert np.allclose(gs["niche_norm"][order], v - trend, atol=1e-12)
+    assert api._scdb_get("gstat", "gs") is gs
+    with pytest.raises(api.McbError):
+        api.scm_gene_stat("m", niche_quantile=1.5, ctx=ctx)

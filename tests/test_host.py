@@ -111,3 +111,22 @@ def test_coclust_filt_by_k_deg_matches_r_logic(tmp_path):
     assert np.array_equal(got, exp)
     with pytest.raises(api.McbError, match="MC-ERR"):
         api.mcell_coclust_filt_by_k_deg("nope", K, alpha)
+
+
+def test_rollmedian_matches_oracle_and_gene_stat_oracle_on_tiny_case():
+    """host logic of scm_gene_stat: the running-median helper against the loop restatement, and the dense oracle
+    against hand-computed values on a 2 x 5 matrix (reference R/gstats.r:83-87, :113-120)"""
+    from metacell_b200 import api
+    from oracle import oracle_np
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=400)
+    assert np.array_equal(api._rollmedian(x, 101, -1.0, 2.0), oracle_np.rollmedian_fill(x, 101, -1.0, 2.0))
+    raw = np.array([[0, 3, 1, 0, 6], [2, 2, 2, 2, 2]], dtype=np.float64)
+    st = oracle_np.gene_stats_dense(raw, None, niche_quantile=0.4)       # round(5 * 0.4) = 2 cells
+    assert np.array_equal(st["tot"], [10, 10])
+    assert np.allclose(st["niche_stat"], [(10 + 9) / (10 + 10), (10 + 4) / (10 + 10)])
+    assert np.allclose(st["var"], [np.var([0, 3, 1, 0, 6], ddof=1), 0.0])
+    assert np.array_equal(st["is_on_count"], [3, 5])
+    csum = raw.sum(axis=0)
+    assert np.allclose(st["n_mean"], (raw * (1000.0 / csum)).mean(axis=1))
+    assert np.isnan(st["sz_cor"][1]) and abs(st["sz_cor"][0] - np.corrcoef(raw[0], csum)[0, 1]) < 1e-15
