@@ -371,10 +371,10 @@ extern "C" int mcb_gene_stats(mcb_ctx* ctx, const mcb_csc* m, const mcb_csc* ds,
         if (!sub_cells || hmask[c]) { T += (long double)htot[c]; TT += (long double)htot[c] * (long double)htot[c]; }
     int64_t n_ds = 0;
     if (ds) for (int64_t c = 0; c < n; ++c) n_ds += hkept[c] ? 1 : 0;
-    DevBuf<double> scale(ctx, (size_t)n);
-    DevBuf<uint8_t> mask(ctx, sub_cells ? (size_t)n : 0);
-    MCB_CUDA(cudaMemcpyAsync(scale.p, hscale.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-    if (sub_cells) MCB_CUDA(cudaMemcpyAsync(mask.p, hmask.data(), (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<CellInfo> hinfo((size_t)n);
+    for (int64_t c = 0; c < n; ++c) { hinfo[c].scale = hscale[c]; hinfo[c].tot = (!sub_cells || hmask[c]) ? (long long)htot[c] : -1 - (long long)htot[c]; }
+    DevBuf<CellInfo> cinfo(ctx, (size_t)n);
+    MCB_CUDA(cudaMemcpyAsync(cinfo.p, hinfo.data(), sizeof(CellInfo) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     // gene-major buckets
     DevBuf<uint32_t> cnt(ctx, (size_t)ng), tx(ctx, (size_t)std::max<int64_t>(m->nnz, 1)), tds(ctx, ds ? (size_t)std::max<int64_t>(m->nnz, 1) : 0);
     DevBuf<int32_t> tc(ctx, (size_t)std::max<int64_t>(m->nnz, 1));
@@ -387,7 +387,7 @@ extern "C" int mcb_gene_stats(mcb_ctx* ctx, const mcb_csc* m, const mcb_csc* ds,
     DevBuf<GeneRaw> raw(ctx, (size_t)ng);
     {
         StageTimer t(ctx, "gene_stats");
-        launch_gene_stats(ctx, ng, start.p, tx.p, tc.p, ds ? tds.p : nullptr, scale.p, ctot.p, sub_cells ? mask.p : nullptr, niche_r, raw.p);
+        launch_gene_stats(ctx, ng, start.p, tx.p, tc.p, ds ? tds.p : nullptr, cinfo.p, niche_r, raw.p);
     }
     std::vector<GeneRaw> h((size_t)ng);
     MCB_CUDA(cudaMemcpyAsync(h.data(), raw.p, sizeof(GeneRaw) * (size_t)ng, cudaMemcpyDeviceToHost, ctx->stream));

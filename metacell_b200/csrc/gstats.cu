@@ -21,10 +21,24 @@ namespace mcb {
 
 typedef unsigned __int128 u128;
 
-__global__ void gene_count_kernel(int64_t nnz, const int32_t* __restrict__ gi, uint32_t* __restrict__ cnt)
+// Entries per gene.  Hot genes receive one update per cell, so the counters are privatised per CTA in shared
+// memory (ngenes * 4 B) and flushed once; gene_count_global_kernel is the fallback for very long gene lists.
+__global__ void gene_count_global_kernel(int64_t nnz, const int32_t* __restrict__ gi, uint32_t* __restrict__ cnt)
 {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += (int64_t)gridDim.x * blockDim.x)
         atomicAdd(&cnt[gi[e]], 1u);
+}
+__global__ void __launch_bounds__(512)
+gene_count_kernel(int32_t ngenes, int64_t nnz, const int32_t* __restrict__ gi, uint32_t* __restrict__ cnt)
+{
+    extern __shared__ uint32_t sh[];
+    for (int g = threadIdx.x; g < ngenes; g += blockDim.x) sh[g] = 0;
+    __syncthreads();
+    const int64_t per = (nnz + gridDim.x - 1) / gridDim.x;
+    const int64_t e0 = (int64_t)blockIdx.x * per, e1 = min(nnz, e0 + per);
+    for (int64_t e = e0 + threadIdx.x; e < e1; e += blockDim.x) atomicAdd(&sh[gi[e]], 1u);
+    __syncthreads();
+    for (int g = threadIdx.x; g < ngenes; g += blockDim.x) { const uint32_t v = sh[g]; if (v) atomicAdd(&cnt[g], v); }
 }
 
 // single block: start[g] = exclusive prefix of cnt (int64), start[ngenes] = total
@@ -54,11 +68,14 @@ __global__ void __launch_bounds__(1024) gene_scan_kernel(int32_t ngenes, const u
     if (threadIdx.x == 0) start[ngenes] = s_run;
 }
 
-// one warp per cell: entries go to their gene's segment (order inside a segment is arbitrary)
+// Scatter into the gene segments: one warp per cell, positions handed out by a global cursor per gene.  Because
+// the cursors advance in global time order, the write frontier is one or two sectors per gene and array (a few MB
+// in total), stays L2-resident and the 4-byte stores merge there.  (A per-CTA run reservation was tried: it removes
+// the atomic hot spots but multiplies the frontier by the CTA count, thrashes L2 and ran 3x slower.)
 __global__ void gene_scatter_kernel(int64_t ncells, const int64_t* __restrict__ p, const int32_t* __restrict__ gi,
-                                    const uint32_t* __restrict__ x, const uint32_t* __restrict__ dsx,
-                                    const int64_t* __restrict__ start, uint32_t* __restrict__ cursor,
-                                    uint32_t* __restrict__ tx, int32_t* __restrict__ tc, uint32_t* __restrict__ tds)
+                                           const uint32_t* __restrict__ x, const uint32_t* __restrict__ dsx,
+                                           const int64_t* __restrict__ start, uint32_t* __restrict__ cursor,
+                                           uint32_t* __restrict__ tx, int32_t* __restrict__ tc, uint32_t* __restrict__ tds)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -73,7 +90,6 @@ __global__ void gene_scatter_kernel(int64_t ncells, const int64_t* __restrict__ 
         }
     }
 }
-
 constexpr int GS_THREADS = 256;
 
 __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* sm /* [8] */)
@@ -126,8 +142,8 @@ __device__ __forceinline__ void top3_push(uint32_t t[3], uint32_t v)
 // one CTA per gene (grid-stride).  niche_r = round(n * niche_quantile) (host, R rounding).
 __global__ void __launch_bounds__(GS_THREADS)
 gene_stats_kernel(int32_t ngenes, const int64_t* __restrict__ start, const uint32_t* __restrict__ tx,
-                  const int32_t* __restrict__ tc, const uint32_t* __restrict__ tds, const double* __restrict__ scale,
-                  const int64_t* __restrict__ ctot, const uint8_t* __restrict__ sub_mask, long long niche_r,
+                  const int32_t* __restrict__ tc, const uint32_t* __restrict__ tds, const CellInfo* __restrict__ cinfo,
+                  long long niche_r,
                   GeneRaw* __restrict__ out)
 {
     __shared__ unsigned long long sm64[16];
@@ -148,9 +164,10 @@ gene_stats_kernel(int32_t ngenes, const int64_t* __restrict__ start, const uint3
             const unsigned long long v = tx[q];
             const int32_t c = tc[q];
             tot += v; sumsq += (u128)(v * v); on += v > 0;
-            nm += (double)v * scale[c];
+            const CellInfo ci = cinfo[c];                // one 16-byte gather: K_std_n / total and total (negated if outside subs)
+            nm += (double)v * ci.scale;
             vmax = max(vmax, (uint32_t)v);
-            if (!sub_mask || sub_mask[c]) { sx_s += v; sxx += (u128)(v * v); sxt += (u128)v * (u128)(unsigned long long)ctot[c]; }
+            if (ci.tot >= 0) { sx_s += v; sxx += (u128)(v * v); sxt += (u128)v * (u128)(unsigned long long)ci.tot; }
             if (tds) {
                 const unsigned long long d = tds[q];
                 dtot += d; dsumsq += (u128)(d * d); d_on += d > 0;
@@ -242,10 +259,25 @@ void launch_gene_bucket(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, int64_t nn
                         const uint32_t* x, const uint32_t* dsx, uint32_t* cnt, int64_t* start, uint32_t* tx, int32_t* tc,
                         uint32_t* tds)
 {
+    const size_t smem = (size_t)ngenes * sizeof(uint32_t);
+    const bool priv = smem <= 200 * 1024;              // per-CTA counters fit in shared memory
+    if (priv) {
+        static size_t configured = 0;
+        if (smem > configured) {
+            MCB_CUDA(cudaFuncSetAttribute(gene_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+    }
+    const int per_sm = priv ? (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem, 1))) : 16;
     MCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * (size_t)std::max(ngenes, 1), ctx->stream));
     if (nnz > 0) {
-        const int grid = (int)std::min<int64_t>(ceil_div(nnz, 256), (int64_t)ctx->num_sms * 16);
-        gene_count_kernel<<<grid, 256, 0, ctx->stream>>>(nnz, gi, cnt);
+        if (priv) {
+            const int grid = (int)std::min<int64_t>(ceil_div(nnz, 4096), (int64_t)ctx->num_sms * per_sm);
+            gene_count_kernel<<<grid, 512, smem, ctx->stream>>>(ngenes, nnz, gi, cnt);
+        } else {
+            const int grid = (int)std::min<int64_t>(ceil_div(nnz, 256), (int64_t)ctx->num_sms * 16);
+            gene_count_global_kernel<<<grid, 256, 0, ctx->stream>>>(nnz, gi, cnt);
+        }
         MCB_LAUNCH_CHECK();
     }
     gene_scan_kernel<<<1, 1024, 0, ctx->stream>>>(ngenes, cnt, start);
@@ -259,12 +291,11 @@ void launch_gene_bucket(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, int64_t nn
 }
 
 void launch_gene_stats(mcb_ctx* ctx, int32_t ngenes, const int64_t* start, const uint32_t* tx, const int32_t* tc,
-                       const uint32_t* tds, const double* scale, const int64_t* ctot, const uint8_t* sub_mask, int64_t niche_r,
-                       void* out_raw)
+                       const uint32_t* tds, const CellInfo* cinfo, int64_t niche_r, void* out_raw)
 {
     if (ngenes == 0) return;
     const int grid = std::min(ngenes, ctx->num_sms * 8);
-    gene_stats_kernel<<<grid, GS_THREADS, 0, ctx->stream>>>(ngenes, start, tx, tc, tds, scale, ctot, sub_mask, (long long)niche_r,
+    gene_stats_kernel<<<grid, GS_THREADS, 0, ctx->stream>>>(ngenes, start, tx, tc, tds, cinfo, (long long)niche_r,
                                                             (GeneRaw*)out_raw);
     MCB_LAUNCH_CHECK();
 }

@@ -161,9 +161,9 @@ static_assert(sizeof(GeneRaw) == 128, "GeneRaw layout");
 void launch_gene_bucket(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, int64_t nnz, const int64_t* p, const int32_t* gi,
                         const uint32_t* x, const uint32_t* dsx, uint32_t* cnt, int64_t* start, uint32_t* tx, int32_t* tc,
                         uint32_t* tds);
+struct alignas(16) CellInfo { double scale; long long tot; };      // K_std_n / total; total, or -1 - total for cells outside the sz_cor subset
 void launch_gene_stats(mcb_ctx* ctx, int32_t ngenes, const int64_t* start, const uint32_t* tx, const int32_t* tc,
-                       const uint32_t* tds, const double* scale, const int64_t* ctot, const uint8_t* sub_mask, int64_t niche_r,
-                       void* out_raw);
+                       const uint32_t* tds, const CellInfo* cinfo, int64_t niche_r, void* out_raw);
 
 // balance.cu
 void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t Kc, int32_t H, int32_t rank_bits,
