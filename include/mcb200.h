@@ -14,6 +14,7 @@
  *     R/cgraph_knn.r:10-25 mcell_add_cgraph_from_mat_bknn                 -> mcb_cgraph_bknn (one shot)
  *     R/atlas.r:164-166   tgs_cor_knn(x, y, knn), y != x                     -> mcb_cor_knn_xy
  *     R/gstats.r:65-205   scm_gene_stat per-gene statistics                  -> mcb_gene_stats
+ *     R/mc.r:164-241      mc_compute_fp / e_gc / cov_gc (tgs_matrix_tapply)  -> mcb_mc_gene_tapply
  *     R/coclust_graph_cov.r:41 tgs_graph_cover_resample(method = "full")  -> mcb_coclust_*
  *
  * Conventions
@@ -135,6 +136,14 @@ int  mcb_cgraph_debug_cor(mcb_cgraph* g, int impl, int64_t a_rows, int64_t b_row
  * applies f_g = tot > 10 (:95).                                                                     */
 int  mcb_gene_stats(mcb_ctx* ctx, const mcb_csc* m, const mcb_csc* ds, double niche_quantile, double k_std_n,
                     const int32_t* sub_cells, int64_t n_sub, double* out);
+
+/* tgs_matrix_tapply(us, mc@mc, f) for the two reductions mc_compute_fp / mc_compute_e_gc / mc_compute_cov_gc use
+ * (reference R/mc.r:185-186, :222, :240): geomean[k][g] = exp(mean(log(1 + u[g, cells of k]))) - 1 and
+ * frac_on[k][g] = mean(u[g, cells of k] > 0), both [n_mc][ngenes]; mc_size[k] = cells in metacell k and
+ * mc_meansize[k] = mean cell total (tapply(colSums(us), mc@mc, mean), R/mc.r:194).  mc_of_cell: 0-based metacell
+ * per cell, -1 = outside the cover.  The gene filter rowSums(us) > 10 and the normalisations stay with the caller. */
+int  mcb_mc_gene_tapply(mcb_ctx* ctx, const mcb_csc* m, const int32_t* mc_of_cell, int32_t n_mc, double* geomean,
+                        double* frac_on, int64_t* mc_size, double* mc_meansize);
 
 /* tgs_cor_knn(x, y, knn) with y != x (reference call sites R/atlas.r:164-166,277,475-478,584): for every
  * cell of x (nx cells, one contiguous vector of G doubles each) the knn cells of y with the highest

@@ -20,7 +20,7 @@ SYMBOLS = [
     "mcb_cgraph_valid_cells", "mcb_cgraph_features", "mcb_cgraph_knn", "mcb_cgraph_knn_begin", "mcb_cgraph_knn_thr_buffer",
     "mcb_cgraph_knn_filter", "mcb_cgraph_knn_recv_buffer", "mcb_cgraph_knn_finish", "mcb_cgraph_knn_buffer",
     "mcb_cgraph_download_knn", "mcb_cgraph_knn_stats", "mcb_cgraph_mutual", "mcb_cgraph_thr_buffer",
-    "mcb_cgraph_prune", "mcb_cgraph_edges", "mcb_cgraph_debug_cor", "mcb_cor_knn_xy", "mcb_gene_stats", "mcb_cgraph_bknn", "mcb_free",
+    "mcb_cgraph_prune", "mcb_cgraph_edges", "mcb_cgraph_debug_cor", "mcb_cor_knn_xy", "mcb_gene_stats", "mcb_mc_gene_tapply", "mcb_cgraph_bknn", "mcb_free",
     "mcb_coclust_run", "mcb_graph_cover", "mcb_coclust_destroy", "mcb_coclust_buffers", "mcb_coclust_assignments",
     "mcb_coclust_extract", "mcb_coclust_pairs",
 ]
@@ -354,6 +354,20 @@ def gene_stats(ctx, csc, ds=None, niche_quantile=0.2, k_std_n=1000.0, sub_cells=
                                ptr(sub, C.c_int32) if sub is not None else None, C.c_int64(0 if sub is None else sub.size),
                                ptr(out, C.c_double)))
     return {k: out[q] for q, k in enumerate(GENE_STAT_COLUMNS)}
+
+
+def mc_gene_tapply(ctx, csc, mc_of_cell, n_mc):
+    """mcb_mc_gene_tapply: (geomean [n_mc][ngenes], frac_on [n_mc][ngenes], mc_size [n_mc], mc_meansize [n_mc])."""
+    mc = as_c(mc_of_cell, np.int32)
+    if mc.size != csc.ncells:
+        raise McbError("MC-ERR: one metacell id per cell is required")
+    geo = np.empty((int(n_mc), csc.ngenes), dtype=np.float64)
+    frac = np.empty((int(n_mc), csc.ngenes), dtype=np.float64)
+    size = np.empty(int(n_mc), dtype=np.int64)
+    mean = np.empty(int(n_mc), dtype=np.float64)
+    check(lib().mcb_mc_gene_tapply(ctx.h, csc.h, ptr(mc, C.c_int32), C.c_int32(int(n_mc)), ptr(geo, C.c_double), ptr(frac, C.c_double),
+                                   ptr(size, C.c_int64), ptr(mean, C.c_double)))
+    return geo, frac, size, mean
 
 
 def cor_knn_xy(ctx, x_cells, y_cells, knn):

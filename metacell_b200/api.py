@@ -252,6 +252,72 @@ def gset_get_feat_mat(gset_id, mat_id, downsamp=False, add_non_dsamp=False, down
 
 
 # ------------------------------------------------------------------------------------------------
+# mc_compute_fp / mc_compute_e_gc / mc_compute_cov_gc / mc_update_stats (reference R/mc.r:92-241)
+# ------------------------------------------------------------------------------------------------
+def _mc_tapply(mc, mat, ctx):
+    """one GPU pass shared by the three summaries: us = mat[, names(mc@mc)] (R/mc.r:94) is expressed as a per-cell
+    metacell id with -1 for cells outside the cover"""
+    index = {nm: q for q, nm in enumerate(mat.cells)}
+    ids = np.full(mat.ncells, -1, dtype=np.int32)
+    for nm, k in mc["mc"].items():
+        q = index.get(nm)
+        if q is None:
+            raise McbError(f"MC-ERR: cell {nm} of the metacell cover is missing from the matrix")
+        ids[q] = int(k) - 1
+    n_mc = int(ids.max()) + 1
+    csc = _upload(mat, ctx)
+    try:
+        geo, frac, size, meansize = _lib.mc_gene_tapply(ctx, csc, ids, n_mc)
+        covered = ids >= 0
+        # rowSums(us): gene totals over the covered cells only
+        tot = np.bincount(mat.indices[np.repeat(covered, np.diff(mat.indptr))],
+                          weights=mat.data[np.repeat(covered, np.diff(mat.indptr))], minlength=mat.ngenes)
+    finally:
+        csc.free()
+    return geo, frac, size, meansize, tot
+
+
+def mc_compute_fp(mc, mat, norm_by_mc_size=True, min_total_umi=10, ctx=None, _pre=None):
+    """reference R/mc.r:164-207: regularised, per-gene median-normalised geometric-mean footprint, genes x metacells."""
+    geo, _, _, meansize, tot = _pre if _pre is not None else _mc_tapply(mc, mat, _ctx(ctx))
+    f_g = tot > min_total_umi
+    g = geo[:, f_g].T                                                     # genes x metacells (t(tgs_matrix_tapply(...)))
+    if norm_by_mc_size:
+        ideal = min(1000.0, float(np.median(meansize)))
+        g = ideal * g / meansize[None, :]
+    fp_reg = 0.1
+    g = (fp_reg + g) / np.median(fp_reg + g, axis=1, keepdims=True)
+    return g, [mat.genes[i] for i in np.nonzero(f_g)[0]]
+
+
+def mc_compute_e_gc(mc, mat, norm_by_mc_meansize=True, ctx=None, _pre=None):
+    """reference R/mc.r:218-229"""
+    geo, _, _, meansize, tot = _pre if _pre is not None else _mc_tapply(mc, mat, _ctx(ctx))
+    f_g = tot > 10
+    e = geo[:, f_g].T
+    if norm_by_mc_meansize:
+        e = e / meansize[None, :]
+    return e, [mat.genes[i] for i in np.nonzero(f_g)[0]]
+
+
+def mc_compute_cov_gc(mc, mat, ctx=None, _pre=None):
+    """reference R/mc.r:237-243"""
+    _, frac, _, _, tot = _pre if _pre is not None else _mc_tapply(mc, mat, _ctx(ctx))
+    f_g = tot > 10
+    return frac[:, f_g].T, [mat.genes[i] for i in np.nonzero(f_g)[0]]
+
+
+def mc_update_stats(mc, mat, ctx=None):
+    """reference R/mc.r:92-105 (batch counts excluded): footprints, absolute expression and coverage from one pass"""
+    pre = _mc_tapply(mc, mat, _ctx(ctx))
+    mc = dict(mc)
+    mc["mc_fp"], mc["genes"] = mc_compute_fp(mc, mat, _pre=pre)
+    mc["e_gc"], _ = mc_compute_e_gc(mc, mat, _pre=pre)
+    mc["cov_gc"], _ = mc_compute_cov_gc(mc, mat, _pre=pre)
+    return mc
+
+
+# ------------------------------------------------------------------------------------------------
 # scm_gene_stat (reference R/gstats.r:65-205)
 # ------------------------------------------------------------------------------------------------
 def _rollmedian(x, k, left, right):

@@ -425,6 +425,46 @@ extern "C" int mcb_gene_stats(mcb_ctx* ctx, const mcb_csc* m, const mcb_csc* ds,
     MCB_API_END
 }
 
+// tgs_matrix_tapply(us, mc@mc, f) for the two functions metacell uses (reference R/mc.r:185-186, :222, :240):
+// geomean[k][g] = exp(mean(log(1 + u[g, cells of k]))) - 1 and frac_on[k][g] = mean(u > 0); plus, per metacell, the
+// number of cells and the mean cell total (tapply(colSums(us), mc@mc, mean), R/mc.r:194).  mc_of_cell: 0-based
+// metacell of every cell, -1 for cells outside the cover (outliers).  Outputs are [n_mc][ngenes] (row per metacell).
+extern "C" int mcb_mc_gene_tapply(mcb_ctx* ctx, const mcb_csc* m, const int32_t* mc_of_cell, int32_t n_mc, double* geomean,
+                                  double* frac_on, int64_t* mc_size, double* mc_meansize)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && m && mc_of_cell && geomean && frac_on && mc_size && mc_meansize, "mcb_mc_gene_tapply: null argument");
+    MCB_CHECK(n_mc >= 1, "MC-ERR: no metacells to summarise");
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const int64_t n = m->ncells, cells = (int64_t)n_mc * m->ngenes;
+    std::vector<int64_t> hsize((size_t)n_mc, 0);
+    for (int64_t c = 0; c < n; ++c) {
+        MCB_CHECK(mc_of_cell[c] >= -1 && mc_of_cell[c] < n_mc, "MC-ERR: metacell id out of range");
+        if (mc_of_cell[c] >= 0) ++hsize[mc_of_cell[c]];
+    }
+    DevBuf<int32_t> dmc(ctx, (size_t)std::max<int64_t>(n, 1));
+    DevBuf<int64_t> dsize(ctx, (size_t)n_mc);
+    DevBuf<unsigned long long> logsum(ctx, (size_t)std::max<int64_t>(cells, 1)), mtot(ctx, (size_t)n_mc);
+    DevBuf<uint32_t> on(ctx, (size_t)std::max<int64_t>(cells, 1));
+    DevBuf<double> dgeo(ctx, (size_t)std::max<int64_t>(cells, 1)), dfrac(ctx, (size_t)std::max<int64_t>(cells, 1));
+    MCB_CUDA(cudaMemcpyAsync(dmc.p, mc_of_cell, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    MCB_CUDA(cudaMemcpyAsync(dsize.p, hsize.data(), sizeof(int64_t) * (size_t)n_mc, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        StageTimer t(ctx, "mc_tapply", 2);
+        launch_mc_tapply(ctx, n, m->ngenes, m->p, m->i, m->x, dmc.p, n_mc, dsize.p, logsum.p, on.p, mtot.p, dgeo.p, dfrac.p);
+    }
+    std::vector<unsigned long long> htot((size_t)n_mc);
+    MCB_CUDA(cudaMemcpyAsync(geomean, dgeo.p, sizeof(double) * (size_t)cells, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaMemcpyAsync(frac_on, dfrac.p, sizeof(double) * (size_t)cells, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaMemcpyAsync(htot.data(), mtot.p, sizeof(unsigned long long) * (size_t)n_mc, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int32_t k = 0; k < n_mc; ++k) {
+        mc_size[k] = hsize[k];
+        mc_meansize[k] = hsize[k] > 0 ? (double)htot[k] / (double)hsize[k] : std::nan("");
+    }
+    MCB_API_END
+}
+
 // ---------------------------------------------------------------------------------------------
 // balanced K-nn cell graph
 // ---------------------------------------------------------------------------------------------

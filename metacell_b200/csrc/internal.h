@@ -165,6 +165,10 @@ struct alignas(16) CellInfo { double scale; long long tot; };      // K_std_n / 
 void launch_gene_stats(mcb_ctx* ctx, int32_t ngenes, const int64_t* start, const uint32_t* tx, const int32_t* tc,
                        const uint32_t* tds, const CellInfo* cinfo, int64_t niche_r, void* out_raw);
 
+void launch_mc_tapply(mcb_ctx* ctx, int64_t ncells, int32_t ngenes, const int64_t* p, const int32_t* gi, const uint32_t* x,
+                      const int32_t* mc_of_cell, int32_t n_mc, const int64_t* mc_size, unsigned long long* logsum, uint32_t* on,
+                      unsigned long long* mc_tot, double* geomean, double* frac_on);
+
 // balance.cu
 void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t Kc, int32_t H, int32_t rank_bits,
                        uint32_t* table);

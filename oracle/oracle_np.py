@@ -119,3 +119,21 @@ def rollmedian_fill(x, k, left, right):
     for i in range(h, x.size - h):
         out[i] = np.median(x[i - h:i + h + 1])
     return out
+
+
+def mc_tapply_dense(us, mc_ids):
+    """tgs_matrix_tapply(us, mc, f) for f = exp(mean(log(1+y)))-1 and mean(x>0) (reference R/mc.r:185-186, :240), dense
+    and literal.  us: [genes][cells] over the covered cells, mc_ids: 0-based metacell per cell.
+    Returns (geomean [genes][n_mc], frac_on [genes][n_mc], mc_meansize [n_mc])."""
+    us = np.asarray(us, dtype=np.float64)
+    n_mc = int(mc_ids.max()) + 1
+    geo = np.empty((us.shape[0], n_mc))
+    frac = np.empty((us.shape[0], n_mc))
+    msz = np.empty(n_mc)
+    csum = us.sum(axis=0)
+    for k in range(n_mc):
+        y = us[:, mc_ids == k]
+        geo[:, k] = np.exp(np.log(1.0 + y).mean(axis=1)) - 1.0
+        frac[:, k] = (y > 0).mean(axis=1)
+        msz[k] = csum[mc_ids == k].mean()
+    return geo, frac, msz

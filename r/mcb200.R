@@ -35,6 +35,16 @@ mcb_gene_stat_block = function(mat, downsample_n, niche_quantile = 0.2, K_std_n 
 	data.frame(name = rownames(mat), r, stringsAsFactors = F)
 }
 
+# the two tgs_matrix_tapply reductions of mc_compute_fp / mc_compute_e_gc / mc_compute_cov_gc (R/mc.r:185-186, :222, :240)
+# in one pass; e.g. in mc_compute_e_gc:  e_gc = mcb_mc_tapply(us, mc@mc)$geomean[f_g_cov, ]
+mcb_mc_tapply = function(us, mc_of_cell)
+{
+	ids = as.integer(mc_of_cell[colnames(us)])
+	r = .Call("mcbr_mc_gene_tapply", us@p, us@i, us@x, nrow(us), ids, max(ids, na.rm = T), PACKAGE = "mcb200")
+	rownames(r$geomean) = rownames(us); rownames(r$frac_on) = rownames(us)
+	r
+}
+
 # tgs_cor_knn for the y != x call sites (atlas projection, R/atlas.r:164-166,277,475-478,584); x == y keeps
 # going through tgs_cor_graph / mcell_add_cgraph_from_mat_bknn.  Same data.frame schema as tgstat's.
 tgs_cor_knn = function(x, y, knn, ...)

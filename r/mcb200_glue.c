@@ -152,6 +152,31 @@ SEXP mcbr_gene_stats(SEXP p, SEXP i, SEXP x, SEXP ngenes, SEXP n, SEXP seed, SEX
     return out;
 }
 
+/* tgs_matrix_tapply(us, mc@mc, f) for f = geometric mean of 1+y minus 1 and f = mean(x > 0) (reference R/mc.r:185-186, :222, :240).
+ * mc: integer metacell id per column of the matrix (1-based, NA for cells outside the cover).  Returns
+ * list(geomean, frac_on) as ngenes x n_mc matrices, mc_size and mc_meansize. */
+SEXP mcbr_mc_gene_tapply(SEXP p, SEXP i, SEXP x, SEXP ngenes, SEXP mc, SEXP n_mc)
+{
+    R_xlen_t ncells;
+    int64_t* p64 = widen_p(p, &ncells);
+    const int32_t ng = asInteger(ngenes), nm = asInteger(n_mc);
+    int32_t* ids = (int32_t*)R_alloc((size_t)(ncells ? ncells : 1), sizeof(int32_t));
+    for (R_xlen_t c = 0; c < ncells; ++c) ids[c] = INTEGER(mc)[c] == NA_INTEGER ? -1 : INTEGER(mc)[c] - 1;
+    mcb_csc* m = NULL;
+    CHECK(mcb_csc_upload(ctx(), ng, ncells, p64, INTEGER(i), REAL(x), &m));
+    SEXP geo = PROTECT(allocMatrix(REALSXP, ng, nm)), frac = PROTECT(allocMatrix(REALSXP, ng, nm));     /* column-major == [n_mc][ngenes] */
+    SEXP msz = PROTECT(allocVector(REALSXP, nm)), mmean = PROTECT(allocVector(REALSXP, nm));
+    int64_t* sz = (int64_t*)R_alloc((size_t)nm, sizeof(int64_t));
+    int rc = mcb_mc_gene_tapply(ctx(), m, ids, nm, REAL(geo), REAL(frac), sz, REAL(mmean));
+    mcb_csc_free(m);
+    if (rc) { UNPROTECT(4); Rf_error("%s", mcb_last_error()); }
+    for (int32_t k = 0; k < nm; ++k) REAL(msz)[k] = (double)sz[k];
+    SEXP res = PROTECT(mkNamed(VECSXP, (const char*[]){"geomean", "frac_on", "mc_size", "mc_meansize", ""}));
+    SET_VECTOR_ELT(res, 0, geo); SET_VECTOR_ELT(res, 1, frac); SET_VECTOR_ELT(res, 2, msz); SET_VECTOR_ELT(res, 3, mmean);
+    UNPROTECT(5);
+    return res;
+}
+
 /* tgs_cor_knn(x, y, knn) with y != x (reference R/atlas.r:164-166,277,475-478,584): x, y dense genes x cells */
 SEXP mcbr_cor_knn_xy(SEXP x, SEXP y, SEXP knn)
 {

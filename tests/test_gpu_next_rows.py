@@ -162,3 +162,37 @@ def test_scm_gene_stat_mirror(ctx, tmp_path):
     assert api._scdb_get("gstat", "gs") is gs
     with pytest.raises(api.McbError):
         api.scm_gene_stat("m", niche_quantile=1.5, ctx=ctx)
+
+
+def test_mc_footprints_match_dense_restatement(ctx, tmp_path):
+    """mc_compute_fp / e_gc / cov_gc (R/mc.r:164-241) through the mirror against the literal dense restatement;
+    a few cells are outliers (outside the cover) and one count is large enough to leave the kernel's lookup table"""
+    from metacell_b200 import api, synth
+    from oracle import oracle_np
+    m = synth.make_umi_matrix(900, 250, n_types=5, median_umis=1200.0, seed=31)
+    data = m.data.copy()
+    data[5] = 5000.0
+    rng = np.random.default_rng(2)
+    ids = rng.integers(0, 7, m.ncells)
+    ids[::13] = -1
+    cells = [f"c{i}" for i in range(m.ncells)]
+    mat = api.tgScMat(m.indptr, m.indices, data, cells=cells, ngenes=m.ngenes)
+    mc = {"mc": {cells[i]: int(ids[i]) + 1 for i in range(m.ncells) if ids[i] >= 0}, "outliers": [cells[i] for i in range(0, m.ncells, 13)]}
+    dense = _dense(m, data)
+    cov = ids >= 0
+    geo, frac, msz = oracle_np.mc_tapply_dense(dense[:, cov], ids[cov])
+    f_g = dense[:, cov].sum(axis=1) > 10
+    e, genes = api.mc_compute_e_gc(mc, mat, ctx=ctx)
+    assert genes == [mat.genes[i] for i in np.nonzero(f_g)[0]]
+    assert np.allclose(e, geo[f_g] / msz[None, :], rtol=1e-11, atol=1e-14)
+    c, _ = api.mc_compute_cov_gc(mc, mat, ctx=ctx)
+    assert np.array_equal(c, frac[f_g])
+    fp, _ = api.mc_compute_fp(mc, mat, ctx=ctx)
+    g = min(1000.0, np.median(msz)) * geo[f_g] / msz[None, :]
+    want = (0.1 + g) / np.median(0.1 + g, axis=1, keepdims=True)
+    assert np.allclose(fp, want, rtol=1e-10)
+    upd = api.mc_update_stats(mc, mat, ctx=ctx)
+    assert np.array_equal(upd["mc_fp"], fp) and np.array_equal(upd["cov_gc"], c)      # deterministic: fixed-point sums
+    bad = dict(mc); bad["mc"] = dict(mc["mc"]); bad["mc"]["nope"] = 1
+    with pytest.raises(api.McbError, match="MC-ERR"):
+        api.mc_compute_fp(bad, mat, ctx=ctx)
