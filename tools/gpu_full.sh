@@ -6,5 +6,5 @@ timeout 900 python -m pytest tests -m gpu -q --timeout=300 > gpurun_out/${TAG}_p
 timeout 300 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke exit $?" | tee -a gpurun_out/${TAG}_smoke.log
 timeout 1200 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.log 2>&1; echo "bench exit $?"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.log 2>&1; echo "ref exit $?"
-bash tools/gpu_profile.sh ${TAG}
+bash tools/gpu_profile.sh ${TAG} list
 tail -3 gpurun_out/${TAG}_pytest_gpu.log; tail -2 gpurun_out/${TAG}_smoke.log
