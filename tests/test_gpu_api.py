@@ -73,5 +73,9 @@ def test_tgs_cor_knn_schema(db, ctx, oracle):
     assert np.array_equal(r["col1"][first], r["col2"][first]) and np.allclose(r["cor"][first], 1.0)   # self at rank 1, R/atlas.r:475-476
     ref = np.corrcoef(x.T)
     assert np.abs(r["cor"] - ref[r["col1"], r["col2"]]).max() < 1e-5
+    # y != x (atlas projection, R/atlas.r:164-166): the 5 best of the 10 y cells per x cell, no forced self
+    r2 = api.tgs_cor_knn(x, x[:, :10].copy(), 5, ctx=ctx)
+    assert r2["col1"].size == 400 * 5 and r2["col2"].max() < 10
+    assert np.abs(r2["cor"] - ref[r2["col1"], r2["col2"]]).max() < 1e-5
     with pytest.raises(api.McbError, match="MC-ERR"):
-        api.tgs_cor_knn(x, x[:, :10], 5, ctx=ctx)
+        api.tgs_cor_knn(x, x[:50, :10].copy(), 5, ctx=ctx)                 # different number of genes
