@@ -286,6 +286,29 @@ __device__ __forceinline__ NodeEdges<IN_SLOTS> load_edges(const FastGraph& g, co
     return e;
 }
 
+template <int OUT_SLOTS, int IN_SLOTS> struct BatchEdges { int v; int uo[OUT_SLOTS]; uint32_t wo[OUT_SLOTS]; int ui[IN_SLOTS]; uint32_t wi[IN_SLOTS]; };
+template <int FT, int OUT_SLOTS, int IN_SLOTS>
+__device__ __forceinline__ BatchEdges<OUT_SLOTS, IN_SLOTS> load_batch_edges(const FastGraph& g, const NodeOffs<IN_SLOTS>& o, int tid)
+{
+    BatchEdges<OUT_SLOTS, IN_SLOTS> e;
+    e.v = o.v;
+#pragma unroll
+    for (int s = 0; s < OUT_SLOTS; ++s) {
+        const int eo = o.o0 + s * FT + tid;
+        const bool ho = eo < o.o1;                  // o.v < 0 has o0 == o1 == 0
+        e.uo[s] = ho ? g.odst[eo] : -1;
+        e.wo[s] = ho ? g.ow[eo] : 0u;
+    }
+#pragma unroll
+    for (int s = 0; s < IN_SLOTS; ++s) {
+        const int ei = o.i0 + s * FT + tid;
+        const bool hi = ei < o.i1;
+        e.ui[s] = hi ? g.isrc[ei] : -1;
+        e.wi[s] = hi ? g.iw[ei] : 0u;
+    }
+    return e;
+}
+
 // requires (checked on the host): out-degree <= FT and in-degree <= IN_SLOTS * FT for every node
 template <int FT, int IN_SLOTS>
 __global__ void __launch_bounds__(FT)
@@ -500,8 +523,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int B, int IN_SLOTS>
-__global__ void __launch_bounds__(128 * B, 8 / B)
+template <int B, int OUT_SLOTS, int IN_SLOTS>
+__global__ void __launch_bounds__(128 * B, (OUT_SLOTS == 1 && IN_SLOTS <= 3) ? 8 / B : 1)
 graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict__ resamp_ids, int32_t n_s,
                          const int32_t* __restrict__ samples, const uint64_t* __restrict__ seeds, int32_t min_size,
                          double cooling, int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap, int32_t out_warps,
@@ -636,18 +659,18 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
             int moved = 0;
             int t = 0;
             int cur_t = -1, nxt_t = -1;
-            NodeEdges<IN_SLOTS> cur;
+            BatchEdges<OUT_SLOTS, IN_SLOTS> cur;
             NodeOffs<IN_SLOTS> nxt;
             cur.v = -1; nxt.v = -1;
             while (t < n_s) {
                 const int my_t = t + sb;
                 if (cur_t != my_t) {              // start of sweep, or the previous batch ended on a move: reload
-                    cur = load_edges<FT, IN_SLOTS>(g, load_offs<IN_SLOTS>(g, vlist, my_t, n_s), ltid);
+                    cur = load_batch_edges<FT, OUT_SLOTS, IN_SLOTS>(g, load_offs<IN_SLOTS>(g, vlist, my_t, n_s), ltid);
                     cur_t = my_t;
                     nxt_t = my_t + B;
                     nxt = load_offs<IN_SLOTS>(g, vlist, nxt_t, n_s);
                 }
-                const NodeEdges<IN_SLOTS> pre = load_edges<FT, IN_SLOTS>(g, nxt, ltid);   // node my_t + B, in flight
+                const BatchEdges<OUT_SLOTS, IN_SLOTS> pre = load_batch_edges<FT, OUT_SLOTS, IN_SLOTS>(g, nxt, ltid);   // node my_t + B, in flight
                 const NodeOffs<IN_SLOTS> nxt2 = load_offs<IN_SLOTS>(g, vlist, nxt_t + B, n_s);
                 uint32_t* wo_b = wout + (size_t)(2 * sb + (parity & 1)) * ncl_cap;
                 uint32_t* wi_b = win + (size_t)(2 * sb + (parity & 1)) * ncl_cap;
@@ -657,8 +680,12 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
                 int rcur = -3;
                 if (lane < 4 * B && (lane >> 2) < nb) rcur = (int)mc_s[vlist[t + (lane >> 2)]];
                 // [A] association of this sub-block's node towards its neighbouring clusters
-                int ko = -1, ki[IN_SLOTS];
-                if (cur.uo >= 0) { ko = (int)mc_s[cur.uo]; if (ko >= 0) atomicAdd(&wo_b[ko], cur.wo); }
+                int ko[OUT_SLOTS], ki[IN_SLOTS];
+#pragma unroll
+                for (int s = 0; s < OUT_SLOTS; ++s) {
+                    ko[s] = -1;
+                    if (cur.uo[s] >= 0) { ko[s] = (int)mc_s[cur.uo[s]]; if (ko[s] >= 0) atomicAdd(&wo_b[ko[s]], cur.wo[s]); }
+                }
 #pragma unroll
                 for (int s = 0; s < IN_SLOTS; ++s) {
                     ki[s] = -1;
@@ -666,28 +693,33 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
                 }
                 named_bar_sync(1 + sb, FT);
                 // [B] best cluster among those reached by an out edge: per-warp partial (score bits, cluster)
-                if (lwid < out_warps) {
-                    unsigned long long bits = 0ull;
-                    if (ko >= 0) {
-                        const uint32_t wo = wo_b[ko], wi = wi_b[ko];
-                        if (wo != 0 && wi != 0) {
-                            const int curk = (int)mc_s[v];
-                            const double sz = (double)size[ko];
-                            double sc = (double)((unsigned long long)wo * (unsigned long long)wi) / (sz * sz);
-                            if (ko == curk) sc = sc * factor;
-                            bits = (unsigned long long)__double_as_longlong(sc);
+                if (OUT_SLOTS > 1 || lwid < out_warps) {
+                    unsigned long long bits = 0ull; int bko = 0x7fffffff;
+#pragma unroll
+                    for (int s = 0; s < OUT_SLOTS; ++s) {
+                        if (ko[s] >= 0) {
+                            const uint32_t wo = wo_b[ko[s]], wi = wi_b[ko[s]];
+                            if (wo != 0 && wi != 0) {
+                                const int curk = (int)mc_s[v];
+                                const double sz = (double)size[ko[s]];
+                                double sc = (double)((unsigned long long)wo * (unsigned long long)wi) / (sz * sz);
+                                if (ko[s] == curk) sc = sc * factor;
+                                const unsigned long long b2 = (unsigned long long)__double_as_longlong(sc);
+                                if (b2 > bits || (b2 == bits && ko[s] < bko)) { bits = b2; bko = ko[s]; }
+                            }
                         }
                     }
                     const uint32_t hi = (uint32_t)(bits >> 32), lo = (uint32_t)bits;
                     const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
                     const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
                     const bool top = bits != 0ull && hi == mh && lo == ml;
-                    const uint32_t mk = __reduce_min_sync(0xffffffffu, top ? (uint32_t)ko : 0x7fffffffu);
+                    const uint32_t mk = __reduce_min_sync(0xffffffffu, top ? (uint32_t)bko : 0x7fffffffu);
                     if (lane == 0) { s_pbits[parity & 1][sb * 4 + lwid] = ((unsigned long long)mh << 32) | ml; s_pk[parity & 1][sb * 4 + lwid] = (int)mk; }
                 }
                 __syncthreads();
                 // [C] clear this batch's accumulators (next used two batches from now)
-                if (ko >= 0) wo_b[ko] = 0;
+#pragma unroll
+                for (int s = 0; s < OUT_SLOTS; ++s) if (ko[s] >= 0) wo_b[ko[s]] = 0;
 #pragma unroll
                 for (int s = 0; s < IN_SLOTS; ++s) if (ki[s] >= 0) wi_b[ki[s]] = 0;
                 // [D] resolve: every warp finds the first node of the batch that moves
@@ -1094,7 +1126,7 @@ static void launch_cover_fast(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local
     MCB_LAUNCH_CHECK();
 }
 
-template <int B, int IN_SLOTS>
+template <int B, int OUT_SLOTS, int IN_SLOTS>
 static void launch_cover_batch(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
                                const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling, int32_t burn_in,
                                int32_t max_sweeps, int32_t ncl_cap, int32_t max_out, size_t smem, int32_t* mc, int32_t* f_ws,
@@ -1102,11 +1134,11 @@ static void launch_cover_batch(mcb_ctx* ctx, const FastGraph& fg, int32_t n_loca
 {
     static size_t configured = 0;
     if (smem > configured) {
-        MCB_CUDA(cudaFuncSetAttribute(graph_cover_batch_kernel<B, IN_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MCB_CUDA(cudaFuncSetAttribute(graph_cover_batch_kernel<B, OUT_SLOTS, IN_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const int32_t out_warps = std::max(1, (int)ceil_div(max_out, 32));
-    graph_cover_batch_kernel<B, IN_SLOTS><<<n_local, 128 * B, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds,
+    graph_cover_batch_kernel<B, OUT_SLOTS, IN_SLOTS><<<n_local, 128 * B, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds,
                                                                                     min_size, cooling, burn_in, max_sweeps,
                                                                                     ncl_cap, out_warps, mc, f_ws, sweeps, status);
     MCB_LAUNCH_CHECK();
@@ -1147,16 +1179,17 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
     if (small_state && want != "slow") {
         const FastGraph fg{g.N, optr32, g.odst, g.ow, iptr32, g.isrc, g.iw};
         const bool auto_ = want == "auto";
-#define BATCH(BB)                                                                                                         \
+#define BATCH(BB, OS, IS)                                                                                                 \
     if ((auto_ && BB == 4) || want == "batch" #BB) {                                                                      \
         const size_t bsmem = ((size_t)(1 + 4 * BB) * ncl_cap + (size_t)n_s) * sizeof(uint32_t) + (size_t)g.N * sizeof(int16_t) + 16; \
-        if (max_out <= 128 && max_in <= 3 * 128 && bsmem <= 200 * 1024) {                                                 \
-            launch_cover_batch<BB, 3>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,      \
-                                      max_sweeps, ncl_cap, max_out, bsmem, mc, f_ws, sweeps, status);                     \
+        if (max_out <= OS * 128 && max_in <= IS * 128 && bsmem <= 200 * 1024) {                                           \
+            launch_cover_batch<BB, OS, IS>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in, \
+                                           max_sweeps, ncl_cap, max_out, bsmem, mc, f_ws, sweeps, status);                \
             return;                                                                                                       \
         }                                                                                                                 \
     }
-        BATCH(4) BATCH(2) BATCH(8)
+        BATCH(4, 1, 3) BATCH(2, 1, 3) BATCH(8, 1, 3)
+        BATCH(4, 2, 4)                  // K = 150 graphs: out-degree <= 256, in-degree <= 512 (one CTA per SM)
 #undef BATCH
         const int32_t kin_stride = (int32_t)round_up((int64_t)std::max(std::min(max_in, ncl_cap), 1), 32) + 2;
 #define WARPK(BB, OS)                                                                                                    \

@@ -127,3 +127,23 @@ def test_graph_cover_kernel_variants_bit_exact(ctx, oracle, kernel, monkeypatch)
         omc, osw = oracle.graph_cover(ncells, csr, sets[r], min_size, 1.05, 10, int(seeds[r]))
         assert sweeps[r] == osw, (kernel, r, sweeps[r], osw)
         assert np.array_equal(mc[r], omc), (kernel, r)
+
+
+@pytest.mark.parametrize("kernel", ["auto", "batch4", "warp16", "warp8", "fast", "slow"])
+def test_graph_cover_high_degree_graph(ctx, oracle, kernel, monkeypatch):
+    """K = 140 graph (out-degree > 128, in-degree up to 3K as at K = 150 in C4/C5): the wider-slot instantiations
+    of the speculative kernels and the 256-thread sequential kernel against the oracle"""
+    from metacell_b200 import _lib, synth
+    ncells, min_size = 1500, 25
+    src, dst, w = _graph(oracle, ncells, 140, seed=13)
+    assert np.bincount(src).max() > 128
+    monkeypatch.setenv("MCB_COVER_KERNEL", kernel)
+    sets, seeds = synth.resample_sets(ncells, 0.75, 3, 99)
+    cc = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, min_size, 1.05, 10)
+    mc, sweeps = cc.assignments()
+    cc.destroy()
+    csr = oracle.graph_to_csr(ncells, src, dst, w)
+    for r in range(sets.shape[0]):
+        omc, osw = oracle.graph_cover(ncells, csr, sets[r], min_size, 1.05, 10, int(seeds[r]))
+        assert sweeps[r] == osw, (kernel, r, sweeps[r], osw)
+        assert np.array_equal(mc[r], omc), (kernel, r)
