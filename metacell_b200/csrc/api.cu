@@ -703,23 +703,26 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
         if (ctx->gemm_impl != 1) launch_gather_rows(ctx, g->Zh.p, (int64_t)Gpad * sizeof(__half), d_samp.p, (int32_t)Spad, Zs.p);
         else launch_gather_rows(ctx, g->Zf.p, (int64_t)Gpad * sizeof(float), d_samp.p, (int32_t)Spad, Zsf.p);
     }
-    int64_t chunk = std::max<int64_t>(128, ((int64_t)2 << 30) / (Spad * 4) / 128 * 128);
+    int64_t chunk = std::max<int64_t>(128, ((int64_t)2 << 30) / (Spad * (ctx->gemm_impl != 1 ? 2 : 4)) / 128 * 128);
     chunk = std::min(chunk, round_up(rows, 128));
-    DevBuf<float> Cs(ctx, (size_t)chunk * Spad);
+    const bool tc = ctx->gemm_impl != 1;              // tensor-core path keeps the sampled correlations in fp16
+    DevBuf<float> Cs(ctx, tc ? 0 : (size_t)chunk * Spad);
+    DevBuf<__half> Cs16(ctx, tc ? (size_t)chunk * Spad : 0);
     const float eps = 1.0f / 512.0f;      // covers the 1-pass error of the sampled correlations
     for (int64_t c0 = 0; c0 < rows; c0 += chunk) {
         const int64_t nr = std::min(chunk, rows - c0);
         {
             StageTimer t(ctx, "cor_sample_gemm");
             if (ctx->gemm_impl != 1)
-                launch_tc_store(ctx, g->Zh.p + (size_t)(row0 + c0) * Gpad, g->Mpad - (row0 + c0), Zs.p, Spad, Gpad,
-                                Cs.p, Spad, nr, S);
+                launch_tc_store16(ctx, g->Zh.p + (size_t)(row0 + c0) * Gpad, g->Mpad - (row0 + c0), Zs.p, Spad, Gpad,
+                                  Cs16.p, Spad, nr, S);
             else
                 launch_simt_store(ctx, g->Zf.p + (size_t)(row0 + c0) * Gpad, nr, Zsf.p, S, Gpad, Cs.p, Spad);
         }
         {
             StageTimer t(ctx, "sample_threshold");
-            launch_sample_threshold(ctx, Cs.p, Spad, nr, (int32_t)S, r_sel, eps, thr + c0);
+            if (tc) launch_sample_threshold16(ctx, Cs16.p, Spad, nr, (int32_t)S, r_sel, eps, thr + c0);
+            else launch_sample_threshold(ctx, Cs.p, Spad, nr, (int32_t)S, r_sel, eps, thr + c0);
         }
     }
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));        // samp / temporaries die here

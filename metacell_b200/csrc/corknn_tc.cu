@@ -39,6 +39,7 @@
 // group (GROUP_M x 1 MB) stays L2 resident and each B tile is fetched from HBM once per group.
 #include "internal.h"
 #include "ptx.cuh"
+#include <cuda_fp16.h>
 #include <cstdlib>
 
 namespace mcb {
@@ -65,7 +66,10 @@ template <int NPASS> struct TcCfg {
     static constexpr int B_BYTES = BN * BK * ELT;                      // 32 KB per plane
     static constexpr int STAGE_BYTES = A_PLANES * (A_BYTES + B_BYTES);
     static constexpr int NSTAGE = NPASS == 3 ? 2 : 4;
-    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * (BN / 2) * 4;
+    // per-epilogue-warp scratch: column thresholds (symmetric filter) or, in the 1-pass kernel, the 32 x 32 fp16
+    // transpose buffer of the coalesced STORE16 epilogue (32 rows x (16 + 1 pad) words)
+    static constexpr int EPI_SCRATCH_WORDS = NPASS == 1 ? 32 * 17 : BN / 2;
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * EPI_SCRATCH_WORDS * 4;
 };
 
 struct TcParams {
@@ -78,8 +82,9 @@ struct TcParams {
     // tiles whose run index is congruent to `part` modulo `nparts`; local_tiles = how many that is
     int32_t part_block, nparts, part, local_tiles;
     int32_t dbg;         // diagnostics (MCB_TC_DEBUG): 1 = epilogue only waits, 2 = epilogue only reads TMEM
-    // STORE
+    // STORE (fp32) or, when C16 is set, STORE16: fp16 output of the 1-pass kernel (sampled correlations)
     float* C; int64_t ldc;
+    __half* C16; int64_t ldc16;
     // FILTER: per-row thresholds in, candidate records out (chunk pool)
     const float* thr;
     uint4* pool; uint32_t* pool_cursor; uint32_t* chunk_fill; uint32_t pool_chunks; uint32_t* overflow;
@@ -178,7 +183,28 @@ __device__ __forceinline__ void epilogue_tile(const TcParams& prm, uint32_t tmem
         }
         const int64_t col0 = n0 + c * 32;
         if (prm.dbg == 2) { if (__uint_as_float(v[lane & 31]) == 123.456f) prm.overflow[0] = 2u; continue; }
-        if (MODE == 0) {
+        if (MODE == 0 && NPASS == 1 && prm.C16) {
+            // fp16 output, transposed through the warp's scratch so that each store instruction writes two 64-byte
+            // row segments (the direct path writes 16 bytes to 32 different rows per instruction and was store-bound)
+            uint32_t* sc = reinterpret_cast<uint32_t*>(tcol);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const __half2 h = __floats2half2_rn(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+                sc[lane * 17 + k] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            __syncwarp();
+            const int sub = lane >> 4, w = lane & 15;
+            const int64_t col = col0 + 2 * w;
+            const int64_t row_base = (int64_t)m_blk * BM + quarter * 32;
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+                const int r = 2 * rr + sub;
+                const uint32_t val = sc[r * 17 + w];
+                if (row_base + r < prm.a_rows && col < prm.b_rows)
+                    *reinterpret_cast<uint32_t*>(prm.C16 + (row_base + r) * prm.ldc16 + col) = val;
+            }
+        } else if (MODE == 0) {
             if (row_ok && col0 < prm.b_rows) {
                 float* dst = prm.C + lrow * prm.ldc + col0;
                 if (col0 + 32 <= prm.b_rows) {
@@ -515,7 +541,7 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
         const int half = (warp - EPI_WARP0) >> 2;
         int it = 0;
         TileIter iter = iter0;
-        float* tcol = reinterpret_cast<float*>(tmem_slot + 4) + (warp - EPI_WARP0) * (BN / 2);    // per-warp column thresholds (MODE 2)
+        float* tcol = reinterpret_cast<float*>(tmem_slot + 4) + (warp - EPI_WARP0) * Cfg::EPI_SCRATCH_WORDS;    // per-warp scratch (column thresholds / transpose)
         uint32_t chunk_id = 0, fill = 0;          // this warp's open record chunk (warp-uniform)
         bool have_chunk = false;
         for (int l = unit0; l < prm.local_tiles; l += unit_stride) {
@@ -766,6 +792,23 @@ static void launch_tc(mcb_ctx* ctx, const CUtensorMap& ah, const CUtensorMap& al
     cfg.attrs = attr; cfg.numAttrs = 1;
     MCB_CUDA(cudaLaunchKernelEx(&cfg, tc_cor_kernel<NPASS, MODE, CM>, ah, al, bh, bl, p2));
     MCB_LAUNCH_CHECK();
+}
+
+// 1-pass product with fp16 output (the sampled correlations of the threshold stage): ldc16 even, >= b_rows rounded up to 2
+void launch_tc_store16(mcb_ctx* ctx, const void* Ahi, int64_t a_rows_alloc, const void* Bhi, int64_t b_rows_alloc,
+                       int32_t Gpad, void* C16, int64_t ldc16, int64_t a_rows, int64_t b_rows)
+{
+    if (a_rows == 0 || b_rows == 0) return;
+    tc_init();
+    MCB_CHECK(Gpad % BK == 0, "Gpad must be a multiple of 64");
+    MCB_CHECK(ldc16 % 2 == 0 && ldc16 >= ((b_rows + 1) & ~(int64_t)1), "tc store16: ldc must be even and cover the columns");
+    const CUtensorMap ah = make_map(Ahi, a_rows_alloc, Gpad, BM);
+    const CUtensorMap bh = make_map(Bhi, b_rows_alloc, Gpad, BN);
+    TcParams prm{};
+    prm.a_row0 = 0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK;
+    prm.m_tiles = (int32_t)ceil_div(a_rows, BM); prm.n_tiles = (int32_t)ceil_div(b_rows, BN);
+    prm.C16 = reinterpret_cast<__half*>(C16); prm.ldc16 = ldc16;
+    launch_tc<1, 0, 1>(ctx, ah, ah, bh, bh, prm);
 }
 
 void launch_tc_store(mcb_ctx* ctx, const void* Ahi, int64_t a_rows_alloc, const void* Bhi, int64_t b_rows_alloc,

@@ -127,6 +127,8 @@ struct CandPool {
 };
 uint32_t tc_pool_chunk_records();
 uint32_t tc_pool_min_chunks(mcb_ctx* ctx);
+void launch_tc_store16(mcb_ctx* ctx, const void* Ahi, int64_t a_rows_alloc, const void* Bhi, int64_t b_rows_alloc,
+                       int32_t Gpad, void* C16, int64_t ldc16, int64_t a_rows, int64_t b_rows);
 void launch_tc_store3_ab(mcb_ctx* ctx, const void* Ahi, const void* Alo, int64_t a_rows_alloc, const void* Bhi, const void* Blo,
                          int64_t b_rows_alloc, int64_t a_rows, int64_t b_rows, int32_t Gpad, float* C, int64_t ldc);
 void launch_tc_filter(mcb_ctx* ctx, const void* Zh, const void* Zl, int64_t rows_alloc, int64_t a_row0,
@@ -143,6 +145,8 @@ void launch_scatter_candidates(mcb_ctx* ctx, const CandPool& pool, uint64_t* can
 // select.cu
 void launch_sample_threshold(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t rows, int32_t S, int32_t r,
                              float eps, float* thr);
+void launch_sample_threshold16(mcb_ctx* ctx, const void* C16, int64_t ldc, int64_t rows, int32_t S, int32_t r,
+                               float eps, float* thr);
 void launch_topk_rows(mcb_ctx* ctx, const uint64_t* cand, const uint32_t* cnt, int32_t cap, int64_t row0,
                       int64_t rows, int32_t kc_out, int32_t Kc, int32_t* knn_col, float* knn_cor, int32_t* fail_flag);
 void launch_compact_flags(mcb_ctx* ctx, const int32_t* flag, int64_t n, int32_t* list, int32_t* n_out);

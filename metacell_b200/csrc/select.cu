@@ -9,6 +9,7 @@
 // All three are shared-memory radix-select / bitonic-sort kernels, one CTA per row; their HBM
 // traffic is one read of the candidates and one write of the list.
 #include "internal.h"
+#include <cuda_fp16.h>
 
 namespace mcb {
 
@@ -104,26 +105,60 @@ __device__ uint32_t bin_select(const uint32_t* keys, int n, int r, uint32_t* bin
 // (linear interpolation inside the bin; the rank error is far below the rule's 4 sigma slack, and rows that still
 // miss their window are redone exactly).  One streaming pass and 16 KB of shared memory
 // (8 CTAs per SM), and replaced an exact two-level select that kept the row's keys in shared memory (4.8 ms at C2).
-__global__ void __launch_bounds__(SEL_THREADS)
-sample_threshold_kernel(const float* __restrict__ C, int64_t ldc, int64_t rows, int32_t S, int32_t r, float eps,
+// T = float (CUDA-core validation path) or __half (tensor-core path, STORE16).  Instruction-issue bound at ~0.9
+// instructions per sampled value (ncu: 11 K warp instructions per row of 12,800 values, 51 % issue-active); the
+// shared-memory atomics compile to ATOMS.POPC.INC, which aggregates same-bin lanes, and are not the limiter: three
+// variants that pre-filtered the values against mean + sd before binning all ran slower than binning everything.
+template <typename T>
+__global__ void __launch_bounds__(SEL_THREADS, 8)
+sample_threshold_kernel(const T* __restrict__ C, int64_t ldc, int64_t rows, int32_t S, int32_t r, float eps,
                         float* __restrict__ thr)
 {
     __shared__ uint32_t bins[THR_BINS];
     __shared__ uint32_t part[SEL_THREADS];
     __shared__ uint32_t chunk[32];
     constexpr int BPT = THR_BINS / SEL_THREADS;     // bins per thread
-    static_assert(BPT <= 32, "one lane per bin of a chunk");
+    static_assert(BPT <= 32 && (BPT & (BPT - 1)) == 0, "one lane per bin of a chunk; power of two for the rotated read");
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
         if (r > S) { if (threadIdx.x == 0) thr[row] = -2.0f; continue; }
-        const float* c = C + row * ldc;
+        const T* c = C + row * ldc;
 #pragma unroll
         for (int q = 0; q < BPT; ++q) bins[q * SEL_THREADS + threadIdx.x] = 0;
         __syncthreads();
-        for (int j = threadIdx.x; j < S; j += SEL_THREADS) atomicAdd(&bins[lin_bin(c[j])], 1u);
+        if constexpr (sizeof(T) == 2) {
+            // rows are 16-byte aligned (ldc % 8 == 0): 8 values per load, the loads of a batch issued together
+            const uint4* c8 = reinterpret_cast<const uint4*>(c);
+            const int nv = S / 8;
+            constexpr int NLD = 4;
+            for (int j0 = 0; j0 < nv; j0 += NLD * SEL_THREADS) {
+                uint4 v[NLD];
+#pragma unroll
+                for (int q = 0; q < NLD; ++q) {
+                    const int j = j0 + q * SEL_THREADS + threadIdx.x;
+                    v[q] = j < nv ? c8[j] : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int q = 0; q < NLD; ++q) {
+                    if (j0 + q * SEL_THREADS + threadIdx.x >= nv) continue;
+                    const uint32_t w[4] = {v[q].x, v[q].y, v[q].z, v[q].w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 p = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+                        atomicAdd(&bins[lin_bin(p.x)], 1u);
+                        atomicAdd(&bins[lin_bin(p.y)], 1u);
+                    }
+                }
+            }
+            for (int j = nv * 8 + threadIdx.x; j < S; j += SEL_THREADS) atomicAdd(&bins[lin_bin(__half2float(c[j]))], 1u);
+        } else {
+            for (int j = threadIdx.x; j < S; j += SEL_THREADS) atomicAdd(&bins[lin_bin((float)c[j])], 1u);
+        }
         __syncthreads();
+        // part[t] = count of the thread's BPT consecutive bins; the read order is rotated per thread so that a warp
+        // touches 16 banks at a time instead of 2 (the straight loop was a 16-way bank conflict)
         uint32_t mine = 0;
 #pragma unroll
-        for (int q = 0; q < BPT; ++q) mine += bins[threadIdx.x * BPT + q];
+        for (int q = 0; q < BPT; ++q) mine += bins[threadIdx.x * BPT + ((q + threadIdx.x) & (BPT - 1))];
         part[threadIdx.x] = mine;
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -134,10 +169,10 @@ sample_threshold_kernel(const float* __restrict__ C, int64_t ldc, int64_t rows, 
             __syncwarp();
             warp_find_bucket<1>(chunk, (long long)(S - r) - before_t, b, before_b);
             if (threadIdx.x == 0) {
-                // linear interpolation inside the bin: the value at ascending position `below` of its `cnt` members
-                const float below = (float)((long long)(S - r) - before_t - before_b);
+                // linear interpolation inside the bin: the value at ascending position `pos` of its `cnt` members
+                const float pos = (float)((long long)(S - r) - before_t - before_b);
                 const float cnt = (float)chunk[b];
-                const float frac = cnt > 0.f ? (below + 0.5f) / cnt : 0.f;
+                const float frac = cnt > 0.f ? (pos + 0.5f) / cnt : 0.f;
                 thr[row] = ((float)(t * BPT + b) + frac) * (2.0f / THR_BINS) - 1.0f - eps;
             }
         }
@@ -391,7 +426,18 @@ void launch_sample_threshold(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t 
 {
     if (rows == 0) return;
     int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
-    sample_threshold_kernel<<<grid, SEL_THREADS, 0, ctx->stream>>>(C, ldc, rows, S, r, eps, thr);
+    sample_threshold_kernel<float><<<grid, SEL_THREADS, 0, ctx->stream>>>(C, ldc, rows, S, r, eps, thr);
+    MCB_LAUNCH_CHECK();
+}
+void launch_sample_threshold16(mcb_ctx* ctx, const void* C16, int64_t ldc, int64_t rows, int32_t S, int32_t r,
+                               float eps, float* thr)
+{
+    if (rows == 0) return;
+    MCB_CHECK(ldc % 8 == 0, "sample threshold: fp16 rows must be 16-byte aligned");
+    static int per_sm = 0;            // resident CTAs per SM: one full wave, the kernel strides over the rows
+    if (!per_sm) MCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sample_threshold_kernel<__half>, SEL_THREADS, 0));
+    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * std::max(per_sm, 1));
+    sample_threshold_kernel<__half><<<grid, SEL_THREADS, 0, ctx->stream>>>(reinterpret_cast<const __half*>(C16), ldc, rows, S, r, eps, thr);
     MCB_LAUNCH_CHECK();
 }
 
