@@ -190,11 +190,13 @@ __device__ __forceinline__ void bitonic_sort_regs_u64(uint64_t (&key)[IPT], uint
 template <int PER>
 __device__ __forceinline__ void warp_find_bucket(const uint32_t* counts, long long k, int& d, long long& before)
 {
+    static_assert((PER & (PER - 1)) == 0, "PER must be a power of two");
     const int lane = threadIdx.x & 31;
-    uint32_t c[PER];
+    // level 1: sum of each lane's PER consecutive counts.  The read order is rotated by the lane index: reading
+    // counts[lane * PER + q] straight is a PER-way (up to 32-way) shared-memory bank conflict.
     long long s = 0;
 #pragma unroll
-    for (int q = 0; q < PER; ++q) { c[q] = counts[lane * PER + q]; s += c[q]; }
+    for (int q = 0; q < PER; ++q) s += counts[lane * PER + ((q + lane) & (PER - 1))];
     long long incl = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -203,20 +205,46 @@ __device__ __forceinline__ void warp_find_bucket(const uint32_t* counts, long lo
     }
     const long long excl = incl - s;
     const unsigned owner_mask = __ballot_sync(0xffffffffu, excl <= k && k < incl);
-    const int owner = owner_mask ? __ffs(owner_mask) - 1 : 31;
-    int dd = lane * PER + PER - 1;
-    long long bb = excl;
-    if (lane == owner) {
-        long long run = excl;
+    if (owner_mask == 0u) {                      // k is past the total: last bucket, everything before it
+        d = 32 * PER - 1;
+        before = __shfl_sync(0xffffffffu, incl, 31);
+        return;
+    }
+    const int owner = __ffs(owner_mask) - 1;
+    const long long base = __shfl_sync(0xffffffffu, excl, owner);
+    // level 2: the warp scans the owner's PER counts together (conflict-free, no serial dependent loads)
+    constexpr int E = PER >= 32 ? PER / 32 : 1;
+    uint32_t c2[E];
+    long long s2 = 0;
 #pragma unroll
-        for (int q = 0; q < PER; ++q) {
-            if (run + c[q] > k) { dd = lane * PER + q; bb = run; break; }
-            run += c[q];
-            bb = run;
+    for (int e = 0; e < E; ++e) {
+        const int idx = lane * E + e;
+        c2[e] = idx < PER ? counts[owner * PER + idx] : 0u;
+        s2 += c2[e];
+    }
+    long long incl2 = s2;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long up = __shfl_up_sync(0xffffffffu, incl2, o);
+        if (lane >= o) incl2 += up;
+    }
+    const long long excl2 = incl2 - s2;
+    const long long kk = k - base;
+    const unsigned m2 = __ballot_sync(0xffffffffu, excl2 <= kk && kk < incl2);
+    const int owner2 = m2 ? __ffs(m2) - 1 : 31;
+    int dd = owner * PER + PER - 1;
+    long long bb = base + excl2;
+    if (lane == owner2) {
+        long long run = excl2;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            if (run + c2[e] > kk) { dd = owner * PER + lane * E + e; bb = base + run; break; }
+            run += c2[e];
+            bb = base + run;
         }
     }
-    d = __shfl_sync(0xffffffffu, dd, owner);
-    before = __shfl_sync(0xffffffffu, bb, owner);
+    d = __shfl_sync(0xffffffffu, dd, owner2);
+    before = __shfl_sync(0xffffffffu, bb, owner2);
 }
 
 __device__ __forceinline__ int next_pow2(int n)
