@@ -456,8 +456,9 @@ topk_select_rows_kernel(const uint64_t* __restrict__ cand, const uint32_t* __res
                         int32_t* __restrict__ fail_flag)
 {
     extern __shared__ uint64_t sk[];        // [256 * IPT_IN]
-    __shared__ uint32_t hist[TOPK_BINS];
-    __shared__ uint32_t s_min[SEL_THREADS / 32], s_max[SEL_THREADS / 32];
+    __shared__ __align__(16) uint32_t hist[TOPK_BINS];
+    __shared__ __align__(16) uint32_t pfx[TOPK_BINS + 4];
+    __shared__ uint32_t s_min[SEL_THREADS / 32], s_max[SEL_THREADS / 32], s_wsum[SEL_THREADS / 32];
     __shared__ int s_bin, s_total, s_n;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
@@ -502,8 +503,59 @@ topk_select_rows_kernel(const uint64_t* __restrict__ cand, const uint32_t* __res
         }
         __syncthreads();
         const int bsel = s_bin, total = s_total;
-        if (total <= 256 * IPT_OUT) {
-            // compact the keys of the bins up to bsel (warp-aggregated positions), pad, sort the short list
+        // exclusive prefix of the histogram (thread t owns bins [8t, 8t + 8)), and the largest selected bin
+        constexpr int BPT = TOPK_BINS / SEL_THREADS;
+        static_assert(BPT == 8, "two 16-byte loads per thread");
+        uint32_t hv[BPT];
+        {
+            const uint4 a = *reinterpret_cast<const uint4*>(&hist[threadIdx.x * BPT]);
+            const uint4 b = *reinterpret_cast<const uint4*>(&hist[threadIdx.x * BPT + 4]);
+            hv[0] = a.x; hv[1] = a.y; hv[2] = a.z; hv[3] = a.w; hv[4] = b.x; hv[5] = b.y; hv[6] = b.z; hv[7] = b.w;
+        }
+        uint32_t loc = 0, mx = 0;
+#pragma unroll
+        for (int q = 0; q < BPT; ++q) { loc += hv[q]; if ((int)threadIdx.x * BPT + q <= bsel) mx = max(mx, hv[q]); }
+        uint32_t incl = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += up; }
+        if (lane == 31) s_wsum[wid] = incl;
+        __syncthreads();
+        uint32_t run = incl - loc;
+#pragma unroll
+        for (int w = 0; w < SEL_THREADS / 32; ++w) if (w < wid) run += s_wsum[w];
+        {
+            uint32_t p[BPT];
+#pragma unroll
+            for (int q = 0; q < BPT; ++q) { p[q] = run; run += hv[q]; }
+            *reinterpret_cast<uint4*>(&pfx[threadIdx.x * BPT]) = make_uint4(p[0], p[1], p[2], p[3]);
+            *reinterpret_cast<uint4*>(&pfx[threadIdx.x * BPT + 4]) = make_uint4(p[4], p[5], p[6], p[7]);
+            if (threadIdx.x == SEL_THREADS - 1) pfx[TOPK_BINS] = run;
+        }
+        const int crowded = __syncthreads_or(mx > 32u);
+        const uint64_t* res = sk;
+        if (total <= 256 * IPT_OUT && !crowded) {
+            // counting sort: the histogram already groups the keys by their leading bits (~0.5 keys per bin), so each
+            // selected key goes to its bin's segment and is then ranked among the few keys of the same bin --
+            // O(n) work instead of the n log^2 n of a sorting network (which took ~70 % of this kernel's instructions)
+#pragma unroll
+            for (int r = 0; r < IPT_IN; ++r) {
+                if (key[r] == ~0ull) continue;
+                const int bin = (int)((((uint32_t)(key[r] >> 32) - kmin) >> shift));
+                if (bin <= bsel) sk[pfx[bin] + (atomicSub(&hist[bin], 1u) - 1u)] = key[r];
+            }
+            __syncthreads();
+            uint64_t* sorted = sk + 256 * IPT_OUT;          // total <= 256 * IPT_OUT <= half of sk
+            for (int p = threadIdx.x; p < total; p += SEL_THREADS) {
+                const uint64_t k = sk[p];
+                const int bin = (int)((((uint32_t)(k >> 32) - kmin) >> shift));
+                const int a = (int)pfx[bin], b = (int)pfx[bin + 1];
+                int rank = 0;
+                for (int q = a; q < b; ++q) rank += sk[q] < k ? 1 : 0;
+                sorted[a + rank] = k;
+            }
+            res = sorted;
+        } else if (total <= 256 * IPT_OUT) {
+            // crowded bins (many near-ties): compact the keys of the bins up to bsel, pad, sort the short list
 #pragma unroll
             for (int r = 0; r < IPT_IN; ++r) {
                 const bool in = key[r] != ~0ull && (int)((((uint32_t)(key[r] >> 32) - kmin) >> shift)) <= bsel;
@@ -533,7 +585,7 @@ topk_select_rows_kernel(const uint64_t* __restrict__ cand, const uint32_t* __res
         __syncthreads();
         for (int q = threadIdx.x; q < Kc; q += SEL_THREADS) {
             if (q == 0) { oc[0] = (int32_t)(row0 + row); ov[0] = 1.0f; }
-            else if (q < kc_out) { const uint64_t k = sk[q - 1]; oc[q] = (int32_t)cand_key_col(k); ov[q] = cand_key_cor(k); }
+            else if (q < kc_out) { const uint64_t k = res[q - 1]; oc[q] = (int32_t)cand_key_col(k); ov[q] = cand_key_cor(k); }
             else { oc[q] = -1; ov[q] = 0.0f; }
         }
         __syncthreads();
@@ -550,7 +602,9 @@ static void launch_topk_select_t(mcb_ctx* ctx, const uint64_t* cand, const uint3
         MCB_CUDA(cudaFuncSetAttribute(topk_select_rows_kernel<IPT_IN, IPT_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
+    static int per_sm = 0;            // resident CTAs per SM: whole waves only, the kernel strides over the rows
+    if (!per_sm) MCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, topk_select_rows_kernel<IPT_IN, IPT_OUT>, SEL_THREADS, smem));
+    int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * std::max(per_sm, 1));
     topk_select_rows_kernel<IPT_IN, IPT_OUT><<<grid, SEL_THREADS, smem, ctx->stream>>>(cand, cnt, cap, row0, rows, kc_out, Kc,
                                                                                         knn_col, knn_cor, fail_flag);
     MCB_LAUNCH_CHECK();
