@@ -608,7 +608,7 @@ static void launch_topk_select_t(mcb_ctx* ctx, const uint64_t* cand, const uint3
 {
     const size_t smem = (size_t)IPT_IN * 256 * sizeof(uint64_t);
     static bool configured = false;
-    if (!configured && smem > 40 * 1024) {
+    if (!configured) {      // static (histogram + prefix, 16.5 KB) + dynamic shared memory can exceed the 48 KB default
         MCB_CUDA(cudaFuncSetAttribute(topk_select_rows_kernel<IPT_IN, IPT_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }

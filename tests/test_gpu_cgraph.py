@@ -156,6 +156,35 @@ def test_cor_knn_parity(ctx, oracle, impl, ncells, K, kx):
     g.destroy()
 
 
+@pytest.mark.parametrize("ncells,K,kx", [(6000, 70, 10), (9000, 150, 10)])
+def test_cor_knn_parity_large_lists(ctx, oracle, ncells, K, kx):
+    """candidate capacities above 1,024 and 2,048 keys: the histogram-select + counting-sort ranking kernels
+    (topk_select_rows_kernel<8,4> and <16,8>) that the C2 / C4 configurations use, and the balancing kernels at
+    Kc = 1,500"""
+    from metacell_b200 import _lib
+    m = _small(ncells=ncells)
+    feats = np.arange(0, 500, 2, dtype=np.int32)
+    csc = _upload(ctx, m)
+    g = _lib.CGraph.from_csc(ctx, csc, feats, 7.0)
+    g.knn(K, kx)
+    col, cor = g.download_knn()
+    stats = g.knn_stats()
+    assert stats["cap"] > (2048 if K * kx > 1024 else 1024), stats
+    Z, valid = oracle.features(m.indptr, m.indices, m.data, feat_map_of(m.ngenes, feats), feats.size)
+    ocol, ocor = oracle.cor_knn(Z[valid], K * kx + 8)
+    agree = _knn_parity(col, cor, ocol, ocor)
+    print(f"N={ncells} Kc={K * kx}: agreement {agree:.6f} stats {stats}")
+    # balancing on the GPU's own lists must equal the oracle's balancing of the same lists, bit for bit
+    g.mutual(3)
+    g.prune()
+    src, dst, w = g.edges()
+    deg, odst, _ = oracle.balance(col, K, kx, 3)
+    osrc, odst2, ow = oracle.edges_from_balance(deg, odst, K)
+    cells = g.valid_cells()
+    assert np.array_equal(src, cells[osrc]) and np.array_equal(dst, cells[odst2]) and np.array_equal(w, ow)
+    g.destroy()
+
+
 @pytest.mark.parametrize("impl", [0, 1])
 def test_cor_knn_exact_row_path(ctx, oracle, impl):
     """rows whose candidate count misses the window are redone exactly: force it for most rows"""
