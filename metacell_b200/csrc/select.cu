@@ -16,10 +16,8 @@ namespace mcb {
 constexpr int SEL_THREADS = 256;
 
 // ---------------------------------------------------------------------------------------------
-// thr[row] = (r-th largest of C[row][0..S)) - eps ; -2 if r > S
-// Two levels: a 4096-bin linear histogram of the correlations over [-1, 1] (well spread, so the
-// shared-memory atomics do not pile onto a few exponent bins) locates the bin holding the answer;
-// only that bin's few values go through the exact 4 x 8-bit radix select.
+// thr[row] = (r-th largest of C[row][0..S)) - eps ; -2 if r > S, from a 4096-bin linear histogram of the
+// correlations over [-1, 1] (well spread, so the shared-memory atomics do not pile onto a few exponent bins)
 // ---------------------------------------------------------------------------------------------
 constexpr int THR_BINS = 4096;
 
@@ -27,77 +25,6 @@ __device__ __forceinline__ int lin_bin(float c)
 {
     int b = (int)((c + 1.0f) * (THR_BINS / 2));
     return b < 0 ? 0 : (b >= THR_BINS ? THR_BINS - 1 : b);
-}
-
-// exact k-th smallest (0-based) of keys[0..n) held in shared memory; all SEL_THREADS threads call it
-__device__ uint32_t radix_kth_smallest(const uint32_t* keys, int n, int k, uint32_t* hist /*[256]*/, uint32_t* s_prefix, int* s_k)
-{
-    if (threadIdx.x == 0) { *s_prefix = 0u; *s_k = k; }
-    __syncthreads();
-    for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        const uint32_t decided = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-        const uint32_t prefix = *s_prefix;
-        hist[threadIdx.x] = 0;
-        __syncthreads();
-        for (int j = threadIdx.x; j < n; j += SEL_THREADS) {
-            const uint32_t key = keys[j];
-            if ((key & decided) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-        }
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            int dg; long long before;
-            warp_find_bucket<8>(hist, (long long)*s_k, dg, before);
-            __syncwarp();
-            if (threadIdx.x == 0) { *s_prefix = prefix | ((uint32_t)dg << shift); *s_k = *s_k - (int)before; }
-        }
-        __syncthreads();
-    }
-    return *s_prefix;
-}
-
-// exact r-th largest (1-based) of keys[0..n) in shared memory through the two-level scheme; all threads call it.
-// bins: [THR_BINS] scratch; returns the key.  n >= r >= 1.
-struct SelScratch { uint32_t hist[256]; uint32_t part[SEL_THREADS]; uint32_t chunk[32]; uint32_t prefix; int k, bin, rank, n; };
-
-__device__ uint32_t bin_select(const uint32_t* keys, int n, int r, uint32_t* bins, SelScratch& sc)
-{
-    constexpr int BPT = THR_BINS / SEL_THREADS;     // bins per thread
-    static_assert(BPT <= 32, "one lane per bin of a chunk");
-    for (int b = threadIdx.x; b < THR_BINS; b += SEL_THREADS) bins[b] = 0;
-    if (threadIdx.x == 0) sc.n = 0;
-    __syncthreads();
-    for (int j = threadIdx.x; j < n; j += SEL_THREADS) atomicAdd(&bins[lin_bin(ordered_to_float(keys[j]))], 1u);
-    __syncthreads();
-    uint32_t mine = 0;
-#pragma unroll
-    for (int q = 0; q < BPT; ++q) mine += bins[threadIdx.x * BPT + q];
-    sc.part[threadIdx.x] = mine;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        // the r-th largest is the (n - r)-th smallest (0-based): chunk of BPT bins, then the bin inside it
-        int t, b; long long before_t, before_b;
-        warp_find_bucket<SEL_THREADS / 32>(sc.part, (long long)(n - r), t, before_t);
-        sc.chunk[threadIdx.x] = threadIdx.x < BPT ? bins[t * BPT + threadIdx.x] : 0u;
-        __syncwarp();
-        warp_find_bucket<1>(sc.chunk, (long long)(n - r) - before_t, b, before_b);
-        if (threadIdx.x == 0) {
-            sc.bin = t * BPT + b;
-            const int below = (int)((long long)(n - r) - before_t - before_b);   // position from the bottom inside the bin
-            sc.rank = (int)bins[t * BPT + b] - below;                            // 1-based rank from the top inside it
-        }
-    }
-    __syncthreads();
-    const int bsel = sc.bin;
-    const int n_in = (int)bins[bsel];
-    __syncthreads();
-    if (n_in > THR_BINS) return radix_kth_smallest(keys, n, n - r, sc.hist, &sc.prefix, &sc.k);   // degenerate: one huge bin
-    for (int j = threadIdx.x; j < n; j += SEL_THREADS) {
-        const uint32_t k = keys[j];
-        if (lin_bin(ordered_to_float(k)) == bsel) bins[atomicAdd(&sc.n, 1)] = k;
-    }
-    __syncthreads();
-    return radix_kth_smallest(bins, n_in, n_in - sc.rank, sc.hist, &sc.prefix, &sc.k);
 }
 
 // The filter threshold is a statistical estimate with slack (api.cu::sample_rule), so the selection does not have
