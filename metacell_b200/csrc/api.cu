@@ -1189,32 +1189,7 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
     MCB_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
     MCB_CHECK((int64_t)N * N < ((int64_t)1 << 36), "MC-ERR: method=\"full\" needs an N x N counter matrix; N is too large");
     MCB_CUDA(cudaSetDevice(ctx->device));
-    // CSR (out and in) with 16-bit fixed-point weights: host-side counting sort of the R edge table
-    std::vector<int64_t> optr((size_t)N + 1, 0), iptr((size_t)N + 1, 0);
-    for (int64_t e = 0; e < n_edges; ++e) {
-        MCB_CHECK(src[e] >= 0 && src[e] < N && dst[e] >= 0 && dst[e] < N, "MC-ERR: edge endpoint out of range");
-        optr[(size_t)src[e] + 1]++; iptr[(size_t)dst[e] + 1]++;
-    }
-    for (int32_t v = 0; v < N; ++v) { optr[v + 1] += optr[v]; iptr[v + 1] += iptr[v]; }
-    std::vector<int32_t> odst((size_t)n_edges), isrc((size_t)n_edges);
-    std::vector<uint32_t> ow((size_t)n_edges), iw((size_t)n_edges);
-    {
-        std::vector<int64_t> oc(optr.begin(), optr.end() - 1), ic(iptr.begin(), iptr.end() - 1);
-        for (int64_t e = 0; e < n_edges; ++e) {
-            const double wf = std::nearbyint(w[e] * 65536.0);
-            const uint32_t wi = wf < 1.0 ? 1u : (uint32_t)wf;
-            const int64_t po = oc[src[e]]++, pi = ic[dst[e]]++;
-            odst[po] = dst[e]; ow[po] = wi;
-            isrc[pi] = src[e]; iw[pi] = wi;
-        }
-    }
-    for (int32_t r = 0; r < n_resamp; ++r) {
-        const int32_t* S = samples + (size_t)r * n_s;
-        for (int32_t q = 0; q < n_s; ++q) {
-            MCB_CHECK(S[q] >= 0 && S[q] < N, "MC-ERR: sampled node out of range");
-            MCB_CHECK(q == 0 || S[q] > S[q - 1], "MC-ERR: each resample index set must be strictly ascending");
-        }
-    }
+    MCB_CHECK(n_edges < ((int64_t)1 << 31), "MC-ERR: too many edges");
     std::vector<int32_t> ids;
     for (int32_t r = rank; r < n_resamp; r += nranks) ids.push_back(r);
     std::unique_ptr<mcb_coclust> c(new mcb_coclust());
@@ -1222,33 +1197,24 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
     c->ncl_cap = n_s / (min_mc_size > 0 ? min_mc_size + 1 : 1) + 2;
     const int32_t nl = c->n_local;
 
-    int32_t max_out = 0, max_in = 0;
-    for (int32_t v = 0; v < N; ++v) {
-        max_out = std::max<int32_t>(max_out, (int32_t)(optr[v + 1] - optr[v]));
-        max_in = std::max<int32_t>(max_in, (int32_t)(iptr[v + 1] - iptr[v]));
-    }
-    const bool small = n_edges < ((int64_t)1 << 31);
-    std::vector<int32_t> optr32(small ? optr.begin() : optr.begin(), small ? optr.end() : optr.begin());
-    std::vector<int32_t> iptr32(small ? iptr.begin() : iptr.begin(), small ? iptr.end() : iptr.begin());
-    DevBuf<int32_t> d_optr32(ctx, optr32.size()), d_iptr32(ctx, iptr32.size());
-    DevBuf<int64_t> d_optr(ctx, optr.size()), d_iptr(ctx, iptr.size());
-    DevBuf<int32_t> d_odst(ctx, odst.size()), d_isrc(ctx, isrc.size());
-    DevBuf<uint32_t> d_ow(ctx, ow.size()), d_iw(ctx, iw.size());
-    DevBuf<int32_t> d_samples(ctx, (size_t)n_resamp * n_s), d_ids(ctx, (size_t)std::max(nl, 1));
+    // the host's edge table and sample sets go up as they are; CSR (out and in, 16-bit fixed-point weights) and the
+    // input validation run on the device
+    const size_t ne1 = (size_t)std::max<int64_t>(n_edges, 1);
+    DevBuf<int32_t> d_src(ctx, ne1), d_dst(ctx, ne1);
+    DevBuf<double> d_w(ctx, ne1);
+    DevBuf<int32_t> d_odeg(ctx, (size_t)N + 1), d_ideg(ctx, (size_t)N + 1), d_optr32(ctx, (size_t)N + 1), d_iptr32(ctx, (size_t)N + 1);
+    DevBuf<int64_t> d_optr(ctx, (size_t)N + 1), d_iptr(ctx, (size_t)N + 1);
+    DevBuf<int32_t> d_odst(ctx, ne1), d_isrc(ctx, ne1), scratch(ctx, 4);
+    DevBuf<uint32_t> d_ow(ctx, ne1), d_iw(ctx, ne1);
+    DevBuf<int32_t> d_samples(ctx, (size_t)std::max<int64_t>((int64_t)n_resamp * n_s, 1)), d_ids(ctx, (size_t)std::max(nl, 1));
     DevBuf<uint64_t> d_seeds(ctx, (size_t)std::max(n_resamp, 1));
+    int32_t hs[4] = {0, 0, 0, 0};
     {
         StageTimer t(ctx, "h2d_graph");
-        MCB_CUDA(cudaMemcpyAsync(d_optr.p, optr.data(), optr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-        MCB_CUDA(cudaMemcpyAsync(d_iptr.p, iptr.data(), iptr.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-        if (small) {
-            MCB_CUDA(cudaMemcpyAsync(d_optr32.p, optr32.data(), optr32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-            MCB_CUDA(cudaMemcpyAsync(d_iptr32.p, iptr32.data(), iptr32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-        }
         if (n_edges) {
-            MCB_CUDA(cudaMemcpyAsync(d_odst.p, odst.data(), odst.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-            MCB_CUDA(cudaMemcpyAsync(d_isrc.p, isrc.data(), isrc.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-            MCB_CUDA(cudaMemcpyAsync(d_ow.p, ow.data(), ow.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-            MCB_CUDA(cudaMemcpyAsync(d_iw.p, iw.data(), iw.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            MCB_CUDA(cudaMemcpyAsync(d_src.p, src, (size_t)n_edges * 4, cudaMemcpyHostToDevice, ctx->stream));
+            MCB_CUDA(cudaMemcpyAsync(d_dst.p, dst, (size_t)n_edges * 4, cudaMemcpyHostToDevice, ctx->stream));
+            MCB_CUDA(cudaMemcpyAsync(d_w.p, w, (size_t)n_edges * 8, cudaMemcpyHostToDevice, ctx->stream));
         }
         if (n_resamp) {
             MCB_CUDA(cudaMemcpyAsync(d_samples.p, samples, (size_t)n_resamp * n_s * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1256,6 +1222,22 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
         }
         if (nl) MCB_CUDA(cudaMemcpyAsync(d_ids.p, ids.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
+    {
+        StageTimer t(ctx, "graph_csr", 8);
+        d_odeg.zero(); d_ideg.zero(); scratch.zero();
+        launch_build_cover_csr(ctx, N, n_edges, d_src.p, d_dst.p, d_w.p, d_odeg.p, d_ideg.p, d_optr32.p, d_iptr32.p, d_odst.p, d_ow.p,
+                               d_isrc.p, d_iw.p, scratch.p);
+        launch_sample_check(ctx, (int64_t)n_resamp * n_s, n_s, d_samples.p, N, scratch.p + 1);
+        launch_widen_i32(ctx, d_optr32.p, d_optr.p, (int64_t)N + 1);
+        launch_widen_i32(ctx, d_iptr32.p, d_iptr.p, (int64_t)N + 1);
+    }
+    MCB_CUDA(cudaMemcpyAsync(hs, scratch.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MCB_CHECK(!(hs[1] & 1), "MC-ERR: edge endpoint out of range");
+    MCB_CHECK(!(hs[1] & 2), "MC-ERR: sampled node out of range");
+    MCB_CHECK(!(hs[1] & 4), "MC-ERR: each resample index set must be strictly ascending");
+    const int32_t max_out = hs[2], max_in = hs[3];
+    const bool small = true;
     c->cnt.alloc(ctx, (size_t)N * N); c->cnt.zero();
     c->nsamp.alloc(ctx, (size_t)N); c->nsamp.zero();
     c->mc.alloc(ctx, (size_t)std::max(nl, 1) * N);

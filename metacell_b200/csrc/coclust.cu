@@ -1023,6 +1023,77 @@ graph_cover_warp_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// CSR (out and in) of the host's edge table, built on the device: degree count, scan, fill.  The order of a node's
+// edges inside its segment is arbitrary (atomic cursors); every consumer only sums integer weights or counts over a
+// segment, so the cover does not depend on it.  Also validates what the host loops used to validate.
+// err bits: 1 = edge endpoint out of range, 2 = sampled node out of range, 4 = sample set not strictly ascending.
+// ---------------------------------------------------------------------------------------------
+__global__ void edge_degree_kernel(int64_t ne, const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int32_t N,
+                                   int32_t* __restrict__ odeg, int32_t* __restrict__ ideg, int32_t* __restrict__ err)
+{
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t a = src[e], b = dst[e];
+        if (a < 0 || a >= N || b < 0 || b >= N) { atomicOr(err, 1); continue; }
+        atomicAdd(&odeg[a], 1); atomicAdd(&ideg[b], 1);
+    }
+}
+__global__ void edge_fill_kernel(int64_t ne, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                 const double* __restrict__ w, int32_t N, const int32_t* __restrict__ optr,
+                                 const int32_t* __restrict__ iptr, int32_t* __restrict__ ocur, int32_t* __restrict__ icur,
+                                 int32_t* __restrict__ odst, uint32_t* __restrict__ ow, int32_t* __restrict__ isrc,
+                                 uint32_t* __restrict__ iw)
+{
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t a = src[e], b = dst[e];
+        if (a < 0 || a >= N || b < 0 || b >= N) continue;
+        const double wf = rint(w[e] * 65536.0);                 // 16-bit fixed point, at least one unit (as orc_graph_to_csr)
+        const uint32_t wi = wf < 1.0 ? 1u : (uint32_t)wf;
+        const int po = optr[a] + atomicAdd(&ocur[a], 1), pi = iptr[b] + atomicAdd(&icur[b], 1);
+        odst[po] = b; ow[po] = wi;
+        isrc[pi] = a; iw[pi] = wi;
+    }
+}
+__global__ void max_degree_kernel(int32_t N, const int32_t* __restrict__ odeg, const int32_t* __restrict__ ideg, int32_t* __restrict__ out2)
+{
+    int mo = 0, mi = 0;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < N; v += gridDim.x * blockDim.x) { mo = max(mo, odeg[v]); mi = max(mi, ideg[v]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { mo = max(mo, __shfl_xor_sync(0xffffffffu, mo, o)); mi = max(mi, __shfl_xor_sync(0xffffffffu, mi, o)); }
+    if ((threadIdx.x & 31) == 0) { atomicMax(&out2[0], mo); atomicMax(&out2[1], mi); }
+}
+__global__ void sample_check_kernel(int64_t total, int32_t n_s, const int32_t* __restrict__ samples, int32_t N, int32_t* __restrict__ err)
+{
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = samples[q];
+        if (v < 0 || v >= N) atomicOr(err, 2);
+        if (q % n_s != 0 && v <= samples[q - 1]) atomicOr(err, 4);
+    }
+}
+
+void launch_build_cover_csr(mcb_ctx* ctx, int32_t N, int64_t ne, const int32_t* src, const int32_t* dst, const double* w,
+                            int32_t* odeg /*[N+1] zeroed*/, int32_t* ideg /*[N+1] zeroed*/, int32_t* optr /*[N+1]*/,
+                            int32_t* iptr /*[N+1]*/, int32_t* odst, uint32_t* ow, int32_t* isrc, uint32_t* iw,
+                            int32_t* scratch4 /* [0] total, [1] err, [2] max out, [3] max in; zeroed */)
+{
+    const int grid = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(ne, 256), 1), (int64_t)ctx->num_sms * 8);
+    if (ne > 0) { edge_degree_kernel<<<grid, 256, 0, ctx->stream>>>(ne, src, dst, N, odeg, ideg, scratch4 + 1); MCB_LAUNCH_CHECK(); }
+    max_degree_kernel<<<std::min(ctx->num_sms, (int)ceil_div(N, 256)), 256, 0, ctx->stream>>>(N, odeg, ideg, scratch4 + 2);
+    MCB_LAUNCH_CHECK();
+    launch_exclusive_scan_i32(ctx, odeg, optr, (int64_t)N + 1, scratch4);
+    launch_exclusive_scan_i32(ctx, ideg, iptr, (int64_t)N + 1, scratch4);
+    MCB_CUDA(cudaMemsetAsync(odeg, 0, sizeof(int32_t) * ((size_t)N + 1), ctx->stream));     // reused as fill cursors
+    MCB_CUDA(cudaMemsetAsync(ideg, 0, sizeof(int32_t) * ((size_t)N + 1), ctx->stream));
+    if (ne > 0) { edge_fill_kernel<<<grid, 256, 0, ctx->stream>>>(ne, src, dst, w, N, optr, iptr, odeg, ideg, odst, ow, isrc, iw); MCB_LAUNCH_CHECK(); }
+}
+void launch_sample_check(mcb_ctx* ctx, int64_t total, int32_t n_s, const int32_t* samples, int32_t N, int32_t* err)
+{
+    if (total == 0) return;
+    const int grid = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)ctx->num_sms * 8);
+    sample_check_kernel<<<grid, 256, 0, ctx->stream>>>(total, n_s, samples, N, err);
+    MCB_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
 // co-occurrence: for every cluster of every local resample, cnt[min(a,b)][max(a,b)] += 1 for all
 // member pairs; nsamp[a] += 1 for every sampled node (mc[a] != -2).
 // One CTA per resample; members are grouped by a counting sort in global workspace.
@@ -1179,8 +1250,12 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
     if (small_state && want != "slow") {
         const FastGraph fg{g.N, optr32, g.odst, g.ow, iptr32, g.isrc, g.iw};
         const bool auto_ = want == "auto";
-#define BATCH(BB, OS, IS)                                                                                                 \
-    if ((auto_ && BB == 4) || want == "batch" #BB) {                                                                      \
+        // batches of 4 visits minimise one resample's latency (37.7 ms at C3, two 512-thread CTAs per SM); once more
+        // resamples are queued than those 2 x num_sms slots the machine is issue-bound and batches of 2 (less
+        // speculative waste, four 256-thread CTAs per SM) give more throughput: 500 resamples 99 ms vs 112 ms
+        const int auto_b = n_local > 2 * ctx->num_sms ? 2 : 4;
+#define BATCH(BB, OS, IS, AUTO)                                                                                               \
+    if ((auto_ && (AUTO)) || want == "batch" #BB) {                                                                      \
         const size_t bsmem = ((size_t)(1 + 4 * BB) * ncl_cap + (size_t)n_s) * sizeof(uint32_t) + (size_t)g.N * sizeof(int16_t) + 16; \
         if (max_out <= OS * 128 && max_in <= IS * 128 && bsmem <= 200 * 1024) {                                           \
             launch_cover_batch<BB, OS, IS>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in, \
@@ -1188,8 +1263,9 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
             return;                                                                                                       \
         }                                                                                                                 \
     }
-        BATCH(4, 1, 3) BATCH(2, 1, 3) BATCH(8, 1, 3)
-        BATCH(4, 2, 4)                  // K = 150 graphs: out-degree <= 256, in-degree <= 512 (one CTA per SM)
+        BATCH(4, 1, 3, auto_b == 4) BATCH(2, 1, 3, auto_b == 2) BATCH(8, 1, 3, false)
+        BATCH(4, 2, 4, true)                  // K = 150 graphs: out-degree <= 256, in-degree <= 512 (one CTA per SM)
+        BATCH(2, 1, 3, true)                  // batches of 4 did not fit in shared memory
 #undef BATCH
         const int32_t kin_stride = (int32_t)round_up((int64_t)std::max(std::min(max_in, ncl_cap), 1), 32) + 2;
 #define WARPK(BB, OS)                                                                                                    \

@@ -173,6 +173,12 @@ void launch_mc_tapply(mcb_ctx* ctx, int64_t ncells, int32_t ngenes, const int64_
                       const int32_t* mc_of_cell, int32_t n_mc, const int64_t* mc_size, unsigned long long* logsum, uint32_t* on,
                       unsigned long long* mc_tot, double* geomean, double* frac_on);
 
+// coclust.cu: device-side CSR build of the host edge table + input validation
+void launch_build_cover_csr(mcb_ctx* ctx, int32_t N, int64_t ne, const int32_t* src, const int32_t* dst, const double* w,
+                            int32_t* odeg, int32_t* ideg, int32_t* optr, int32_t* iptr, int32_t* odst, uint32_t* ow,
+                            int32_t* isrc, uint32_t* iw, int32_t* scratch4);
+void launch_sample_check(mcb_ctx* ctx, int64_t total, int32_t n_s, const int32_t* samples, int32_t N, int32_t* err);
+
 // balance.cu
 void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t Kc, int32_t H, int32_t rank_bits,
                        uint32_t* table);
