@@ -1206,6 +1206,8 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
     DevBuf<int64_t> d_optr(ctx, (size_t)N + 1), d_iptr(ctx, (size_t)N + 1);
     DevBuf<int32_t> d_odst(ctx, ne1), d_isrc(ctx, ne1), scratch(ctx, 4);
     DevBuf<uint32_t> d_ow(ctx, ne1), d_iw(ctx, ne1);
+    DevBuf<int2> d_oe(ctx, ne1), d_ie(ctx, ne1);
+    DevBuf<int4> d_nd(ctx, (size_t)N);
     DevBuf<int32_t> d_samples(ctx, (size_t)std::max<int64_t>((int64_t)n_resamp * n_s, 1)), d_ids(ctx, (size_t)std::max(nl, 1));
     DevBuf<uint64_t> d_seeds(ctx, (size_t)std::max(n_resamp, 1));
     int32_t hs[4] = {0, 0, 0, 0};
@@ -1226,7 +1228,7 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
         StageTimer t(ctx, "graph_csr", 8);
         d_odeg.zero(); d_ideg.zero(); scratch.zero();
         launch_build_cover_csr(ctx, N, n_edges, d_src.p, d_dst.p, d_w.p, d_odeg.p, d_ideg.p, d_optr32.p, d_iptr32.p, d_odst.p, d_ow.p,
-                               d_isrc.p, d_iw.p, scratch.p);
+                               d_isrc.p, d_iw.p, d_oe.p, d_ie.p, d_nd.p, scratch.p);
         launch_sample_check(ctx, (int64_t)n_resamp * n_s, n_s, d_samples.p, N, scratch.p + 1);
         launch_widen_i32(ctx, d_optr32.p, d_optr.p, (int64_t)N + 1);
         launch_widen_i32(ctx, d_iptr32.p, d_iptr.p, (int64_t)N + 1);
@@ -1237,7 +1239,6 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
     MCB_CHECK(!(hs[1] & 2), "MC-ERR: sampled node out of range");
     MCB_CHECK(!(hs[1] & 4), "MC-ERR: each resample index set must be strictly ascending");
     const int32_t max_out = hs[2], max_in = hs[3];
-    const bool small = true;
     c->cnt.alloc(ctx, (size_t)N * N); c->cnt.zero();
     c->nsamp.alloc(ctx, (size_t)N); c->nsamp.zero();
     c->mc.alloc(ctx, (size_t)std::max(nl, 1) * N);
@@ -1247,7 +1248,7 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
     CoverGraph cg{N, d_optr.p, d_odst.p, d_ow.p, d_iptr.p, d_isrc.p, d_iw.p};
     {
         StageTimer t(ctx, "graph_cover");
-        launch_graph_cover(ctx, cg, small ? d_optr32.p : nullptr, small ? d_iptr32.p : nullptr, max_out, max_in, nl, d_ids.p, n_s, d_samples.p, d_seeds.p, min_mc_size, cooling, burn_in, max_sweeps,
+        launch_graph_cover(ctx, cg, d_optr32.p, d_iptr32.p, d_nd.p, d_oe.p, d_ie.p, max_out, max_in, nl, d_ids.p, n_s, d_samples.p, d_seeds.p, min_mc_size, cooling, burn_in, max_sweeps,
                            c->ncl_cap, c->mc.p, f_ws.p, c->sweeps.p, status.p);
     }
     {

@@ -251,6 +251,10 @@ graph_cover_kernel(CoverGraph g, int32_t n_local, const int32_t* __restrict__ re
 struct FastGraph {      // CoverGraph with 32-bit CSR offsets (n_edges < 2^31), fewer integer instructions per visit
     int32_t N; const int32_t* optr; const int32_t* odst; const uint32_t* ow;
     const int32_t* iptr; const int32_t* isrc; const uint32_t* iw;
+    // packed copies for the speculative batch kernel: one 16-byte descriptor {o0, o1, i0, i1} per node and one 8-byte
+    // {neighbour, weight} per edge, so a visit's prefetch is 1 + OUT_SLOTS + IN_SLOTS loads instead of twice as many
+    // 4-byte loads with their own address arithmetic (the prefetch was 23 % of the kernel's instructions)
+    const int4* nd; const int2* oe; const int2* ie;
 };
 template <int IN_SLOTS> struct NodeOffs { int v, o0, o1, i0, i1; };
 template <int IN_SLOTS> struct NodeEdges { int v; int uo; uint32_t wo; int ui[IN_SLOTS]; uint32_t wi[IN_SLOTS]; };
@@ -287,6 +291,18 @@ __device__ __forceinline__ NodeEdges<IN_SLOTS> load_edges(const FastGraph& g, co
 }
 
 template <int OUT_SLOTS, int IN_SLOTS> struct BatchEdges { int v; int uo[OUT_SLOTS]; uint32_t wo[OUT_SLOTS]; int ui[IN_SLOTS]; uint32_t wi[IN_SLOTS]; };
+template <int IN_SLOTS>
+__device__ __forceinline__ NodeOffs<IN_SLOTS> load_batch_offs(const FastGraph& g, const int32_t* vlist, int t, int n_s)
+{
+    NodeOffs<IN_SLOTS> o;
+    o.v = -1; o.o0 = o.o1 = o.i0 = o.i1 = 0;
+    if (t < n_s) {
+        o.v = vlist[t];
+        const int4 d = __ldg(g.nd + o.v);
+        o.o0 = d.x; o.o1 = d.y; o.i0 = d.z; o.i1 = d.w;
+    }
+    return o;
+}
 template <int FT, int OUT_SLOTS, int IN_SLOTS>
 __device__ __forceinline__ BatchEdges<OUT_SLOTS, IN_SLOTS> load_batch_edges(const FastGraph& g, const NodeOffs<IN_SLOTS>& o, int tid)
 {
@@ -295,16 +311,16 @@ __device__ __forceinline__ BatchEdges<OUT_SLOTS, IN_SLOTS> load_batch_edges(cons
 #pragma unroll
     for (int s = 0; s < OUT_SLOTS; ++s) {
         const int eo = o.o0 + s * FT + tid;
-        const bool ho = eo < o.o1;                  // o.v < 0 has o0 == o1 == 0
-        e.uo[s] = ho ? g.odst[eo] : -1;
-        e.wo[s] = ho ? g.ow[eo] : 0u;
+        int2 p = make_int2(-1, 0);
+        if (eo < o.o1) p = __ldg(g.oe + eo);          // o.v < 0 has o0 == o1 == 0
+        e.uo[s] = p.x; e.wo[s] = (uint32_t)p.y;
     }
 #pragma unroll
     for (int s = 0; s < IN_SLOTS; ++s) {
         const int ei = o.i0 + s * FT + tid;
-        const bool hi = ei < o.i1;
-        e.ui[s] = hi ? g.isrc[ei] : -1;
-        e.wi[s] = hi ? g.iw[ei] : 0u;
+        int2 p = make_int2(-1, 0);
+        if (ei < o.i1) p = __ldg(g.ie + ei);
+        e.ui[s] = p.x; e.wi[s] = (uint32_t)p.y;
     }
     return e;
 }
@@ -665,13 +681,13 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
             while (t < n_s) {
                 const int my_t = t + sb;
                 if (cur_t != my_t) {              // start of sweep, or the previous batch ended on a move: reload
-                    cur = load_batch_edges<FT, OUT_SLOTS, IN_SLOTS>(g, load_offs<IN_SLOTS>(g, vlist, my_t, n_s), ltid);
+                    cur = load_batch_edges<FT, OUT_SLOTS, IN_SLOTS>(g, load_batch_offs<IN_SLOTS>(g, vlist, my_t, n_s), ltid);
                     cur_t = my_t;
                     nxt_t = my_t + B;
-                    nxt = load_offs<IN_SLOTS>(g, vlist, nxt_t, n_s);
+                    nxt = load_batch_offs<IN_SLOTS>(g, vlist, nxt_t, n_s);
                 }
                 const BatchEdges<OUT_SLOTS, IN_SLOTS> pre = load_batch_edges<FT, OUT_SLOTS, IN_SLOTS>(g, nxt, ltid);   // node my_t + B, in flight
-                const NodeOffs<IN_SLOTS> nxt2 = load_offs<IN_SLOTS>(g, vlist, nxt_t + B, n_s);
+                const NodeOffs<IN_SLOTS> nxt2 = load_batch_offs<IN_SLOTS>(g, vlist, nxt_t + B, n_s);
                 uint32_t* wo_b = wout + (size_t)(2 * sb + (parity & 1)) * ncl_cap;
                 uint32_t* wi_b = win + (size_t)(2 * sb + (parity & 1)) * ncl_cap;
                 const int v = cur.v;               // -1 beyond the end of the sweep
@@ -1041,7 +1057,7 @@ __global__ void edge_fill_kernel(int64_t ne, const int32_t* __restrict__ src, co
                                  const double* __restrict__ w, int32_t N, const int32_t* __restrict__ optr,
                                  const int32_t* __restrict__ iptr, int32_t* __restrict__ ocur, int32_t* __restrict__ icur,
                                  int32_t* __restrict__ odst, uint32_t* __restrict__ ow, int32_t* __restrict__ isrc,
-                                 uint32_t* __restrict__ iw)
+                                 uint32_t* __restrict__ iw, int2* __restrict__ oe, int2* __restrict__ ie)
 {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
         const int32_t a = src[e], b = dst[e];
@@ -1049,9 +1065,14 @@ __global__ void edge_fill_kernel(int64_t ne, const int32_t* __restrict__ src, co
         const double wf = rint(w[e] * 65536.0);                 // 16-bit fixed point, at least one unit (as orc_graph_to_csr)
         const uint32_t wi = wf < 1.0 ? 1u : (uint32_t)wf;
         const int po = optr[a] + atomicAdd(&ocur[a], 1), pi = iptr[b] + atomicAdd(&icur[b], 1);
-        odst[po] = b; ow[po] = wi;
-        isrc[pi] = a; iw[pi] = wi;
+        odst[po] = b; ow[po] = wi; oe[po] = make_int2(b, (int)wi);
+        isrc[pi] = a; iw[pi] = wi; ie[pi] = make_int2(a, (int)wi);
     }
+}
+__global__ void node_desc_kernel(int32_t N, const int32_t* __restrict__ optr, const int32_t* __restrict__ iptr, int4* __restrict__ nd)
+{
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < N; v += gridDim.x * blockDim.x)
+        nd[v] = make_int4(optr[v], optr[v + 1], iptr[v], iptr[v + 1]);
 }
 __global__ void max_degree_kernel(int32_t N, const int32_t* __restrict__ odeg, const int32_t* __restrict__ ideg, int32_t* __restrict__ out2)
 {
@@ -1073,6 +1094,7 @@ __global__ void sample_check_kernel(int64_t total, int32_t n_s, const int32_t* _
 void launch_build_cover_csr(mcb_ctx* ctx, int32_t N, int64_t ne, const int32_t* src, const int32_t* dst, const double* w,
                             int32_t* odeg /*[N+1] zeroed*/, int32_t* ideg /*[N+1] zeroed*/, int32_t* optr /*[N+1]*/,
                             int32_t* iptr /*[N+1]*/, int32_t* odst, uint32_t* ow, int32_t* isrc, uint32_t* iw,
+                            void* oe /* int2[ne] */, void* ie /* int2[ne] */, void* nd /* int4[N] */,
                             int32_t* scratch4 /* [0] total, [1] err, [2] max out, [3] max in; zeroed */)
 {
     const int grid = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(ne, 256), 1), (int64_t)ctx->num_sms * 8);
@@ -1083,7 +1105,9 @@ void launch_build_cover_csr(mcb_ctx* ctx, int32_t N, int64_t ne, const int32_t* 
     launch_exclusive_scan_i32(ctx, ideg, iptr, (int64_t)N + 1, scratch4);
     MCB_CUDA(cudaMemsetAsync(odeg, 0, sizeof(int32_t) * ((size_t)N + 1), ctx->stream));     // reused as fill cursors
     MCB_CUDA(cudaMemsetAsync(ideg, 0, sizeof(int32_t) * ((size_t)N + 1), ctx->stream));
-    if (ne > 0) { edge_fill_kernel<<<grid, 256, 0, ctx->stream>>>(ne, src, dst, w, N, optr, iptr, odeg, ideg, odst, ow, isrc, iw); MCB_LAUNCH_CHECK(); }
+    if (ne > 0) { edge_fill_kernel<<<grid, 256, 0, ctx->stream>>>(ne, src, dst, w, N, optr, iptr, odeg, ideg, odst, ow, isrc, iw, (int2*)oe, (int2*)ie); MCB_LAUNCH_CHECK(); }
+    node_desc_kernel<<<std::min(ctx->num_sms, (int)ceil_div(N, 256)), 256, 0, ctx->stream>>>(N, optr, iptr, (int4*)nd);
+    MCB_LAUNCH_CHECK();
 }
 void launch_sample_check(mcb_ctx* ctx, int64_t total, int32_t n_s, const int32_t* samples, int32_t N, int32_t* err)
 {
@@ -1232,8 +1256,8 @@ static void launch_cover_warp(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local
     MCB_LAUNCH_CHECK();
 }
 
-void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32, const int32_t* iptr32, int32_t max_out,
-                        int32_t max_in, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
+void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32, const int32_t* iptr32, const void* nd,
+                        const void* oe, const void* ie, int32_t max_out, int32_t max_in, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
                         const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling,
                         int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap, int32_t* mc, int32_t* f_ws,
                         int32_t* sweeps, int32_t* status)
@@ -1246,9 +1270,9 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
     //   slow    sequential visits, mc[] in global memory (any size)
     const char* ksel = getenv("MCB_COVER_KERNEL");
     const std::string want = ksel ? ksel : (getenv("MCB_COVER_SLOW") ? "slow" : "auto");
-    const bool small_state = optr32 && ncl_cap < 32000;
+    const bool small_state = optr32 && nd && oe && ie && ncl_cap < 32000;
     if (small_state && want != "slow") {
-        const FastGraph fg{g.N, optr32, g.odst, g.ow, iptr32, g.isrc, g.iw};
+        const FastGraph fg{g.N, optr32, g.odst, g.ow, iptr32, g.isrc, g.iw, (const int4*)nd, (const int2*)oe, (const int2*)ie};
         const bool auto_ = want == "auto";
         // batches of 4 visits minimise one resample's latency (37.7 ms at C3, two 512-thread CTAs per SM); once more
         // resamples are queued than those 2 x num_sms slots the machine is issue-bound and batches of 2 (less

@@ -176,7 +176,7 @@ void launch_mc_tapply(mcb_ctx* ctx, int64_t ncells, int32_t ngenes, const int64_
 // coclust.cu: device-side CSR build of the host edge table + input validation
 void launch_build_cover_csr(mcb_ctx* ctx, int32_t N, int64_t ne, const int32_t* src, const int32_t* dst, const double* w,
                             int32_t* odeg, int32_t* ideg, int32_t* optr, int32_t* iptr, int32_t* odst, uint32_t* ow,
-                            int32_t* isrc, uint32_t* iw, int32_t* scratch4);
+                            int32_t* isrc, uint32_t* iw, void* oe, void* ie, void* nd, int32_t* scratch4);
 void launch_sample_check(mcb_ctx* ctx, int64_t total, int32_t n_s, const int32_t* samples, int32_t N, int32_t* err);
 
 // balance.cu
@@ -197,9 +197,10 @@ struct CoverGraph {
     int32_t N; const int64_t* optr; const int32_t* odst; const uint32_t* ow;
     const int64_t* iptr; const int32_t* isrc; const uint32_t* iw;
 };
-// optr32 / iptr32: 32-bit copies of the CSR offsets (null when n_edges >= 2^31); max_out / max_in: largest degrees
-void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32, const int32_t* iptr32, int32_t max_out,
-                        int32_t max_in, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
+// optr32 / iptr32: 32-bit CSR offsets; nd / oe / ie: packed node descriptors (int4) and edges (int2) of the same CSR;
+// max_out / max_in: largest degrees
+void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32, const int32_t* iptr32, const void* nd,
+                        const void* oe, const void* ie, int32_t max_out, int32_t max_in, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
                         const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling,
                         int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap, int32_t* mc /* [n_local][N] */,
                         int32_t* f_ws /* [n_local][N] */, int32_t* sweeps, int32_t* status);
