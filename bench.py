@@ -122,7 +122,7 @@ class ClockSampler:
     thread (an `nvidia-smi -lms` loop was measured to stall the driver and triple the step time)."""
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, dev, period=float(os.environ.get("MCB_BENCH_CLOCK_PERIOD", "0.2"))):
+    def __init__(self, dev, period=float(os.environ.get("MCB_BENCH_CLOCK_PERIOD", "0.05"))):
         self.dev, self.period, self.sm, self.bits, self.mx, self.ok = dev, period, [], 0, None, False
         self.stop_flag = threading.Event()
 
