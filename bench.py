@@ -291,7 +291,8 @@ def run_ours(a):
         bf16 = peaks.get("bf16_tflops_sustained")
         peak = bf16 if bf16 else 1400.0
         roof = {"bound": "tensor", "kernel": "tc_cor2_kernel<SYM> (tcgen05 cta_group::2 kind::f16, 3-pass hi/lo split of z*2^12, fp32 accumulate, fused top-Kc filter)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": _ncu_traffic(a, M),
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": (_ncu_traffic(a, M) or {}).get("bytes"), "traffic_unit": "bytes of DRAM read + written per launch (ncu --set full)",
+                "traffic_source": (_ncu_traffic(a, M) or {}).get("source"),
                 "issued_tflops": 3.0 * achieved * (-(-a.genes // 64) * 64) / a.genes * 0.5 * (1.0 + 256.0 / max(M, 256)),
                 "ms_per_launch": gemm_ms, "share_of_step": gemm_ms / ms_step,
                 "peak_source": ("bf16_tflops_sustained of MEASURED_PEAKS.json (kind::f16 runs at the bf16 rate; kernel timed inside a long step)"
