@@ -72,7 +72,7 @@ __device__ __forceinline__ uint32_t hash_lookup(const uint32_t* __restrict__ tab
 
 // mutual scores s(i, r) and the in-degree threshold of every owned row
 template <int IPT>      // 256 * IPT >= Kc keys sorted per row, register resident
-__global__ void __launch_bounds__(BAL_THREADS)
+__global__ void __launch_bounds__(BAL_THREADS, IPT <= 4 ? 4 : 1)
 mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ table, int64_t row0, int64_t rows,
               int32_t Kc, int32_t H, int32_t log2H, int32_t rank_bits, long long smax, int strict, int keep_self,
               int32_t kin, uint32_t* __restrict__ sym, uint64_t* __restrict__ thr_in)
@@ -152,7 +152,7 @@ mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ 
 
 // out-degree prune: survivors of the target's in-degree cut, best K by (s, target)
 template <int IPT>
-__global__ void __launch_bounds__(BAL_THREADS)
+__global__ void __launch_bounds__(BAL_THREADS, IPT <= 4 ? 4 : 1)
 prune_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ sym, const uint64_t* __restrict__ thr_in,
              int64_t row0, int64_t rows, int32_t Kc, int32_t K, long long smax, int32_t* __restrict__ out_deg,
              int32_t* __restrict__ out_dst, int32_t* __restrict__ out_s)
