@@ -291,13 +291,13 @@ __device__ __forceinline__ NodeEdges<IN_SLOTS> load_edges(const FastGraph& g, co
 }
 
 template <int OUT_SLOTS, int IN_SLOTS> struct BatchEdges { int v; int uo[OUT_SLOTS]; uint32_t wo[OUT_SLOTS]; int ui[IN_SLOTS]; uint32_t wi[IN_SLOTS]; };
-template <int IN_SLOTS>
-__device__ __forceinline__ NodeOffs<IN_SLOTS> load_batch_offs(const FastGraph& g, const int32_t* vlist, int t, int n_s)
+template <int IN_SLOTS, typename VT>
+__device__ __forceinline__ NodeOffs<IN_SLOTS> load_batch_offs(const FastGraph& g, const VT* vlist, int t, int n_s)
 {
     NodeOffs<IN_SLOTS> o;
     o.v = -1; o.o0 = o.o1 = o.i0 = o.i1 = 0;
     if (t < n_s) {
-        o.v = vlist[t];
+        o.v = (int)vlist[t];
         const int4 d = __ldg(g.nd + o.v);
         o.o0 = d.x; o.o1 = d.y; o.i0 = d.z; o.i1 = d.w;
     }
@@ -539,8 +539,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int B, int OUT_SLOTS, int IN_SLOTS>
-__global__ void __launch_bounds__(128 * B, (OUT_SLOTS == 1 && IN_SLOTS <= 3) ? 8 / B : 1)
+// VT: element type of the shared-memory visit order (uint16_t when N < 65536: at the C5 shape this is what lets two
+// CTAs of the wide-slot instantiation share an SM)
+template <int B, int OUT_SLOTS, int IN_SLOTS, typename VT>
+__global__ void __launch_bounds__(128 * B, (OUT_SLOTS == 1 && IN_SLOTS <= 3) ? 8 / B : (sizeof(VT) == 2 ? 4 / B : 1))
 graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict__ resamp_ids, int32_t n_s,
                          const int32_t* __restrict__ samples, const uint64_t* __restrict__ seeds, int32_t min_size,
                          double cooling, int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap, int32_t out_warps,
@@ -555,8 +557,8 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
     int32_t* size = (int32_t*)dsm;                               // [ncl_cap]
     uint32_t* wout = dsm + ncl_cap;                              // [B][2][ncl_cap]
     uint32_t* win = wout + (size_t)2 * B * ncl_cap;              // [B][2][ncl_cap]
-    int32_t* vlist = (int32_t*)(win + (size_t)2 * B * ncl_cap);  // [n_s]
-    int16_t* mc_s = (int16_t*)(vlist + n_s);                     // [N]
+    VT* vlist = (VT*)(win + (size_t)2 * B * ncl_cap);            // [n_s]
+    int16_t* mc_s = (int16_t*)(vlist + ((n_s + 1) & ~1));        // [N]
     __shared__ unsigned long long s_part[NT];
     __shared__ unsigned long long s_pbits[2][B * 4];   // per-(node, warp) partial arg-max, double buffered by batch parity
     __shared__ int s_pk[2][B * 4];
@@ -670,7 +672,7 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
                 rk[0] = (uint32_t)w0; rk[1] = (uint32_t)(w0 >> 32); rk[2] = (uint32_t)w1; rk[3] = (uint32_t)(w1 >> 32);
             }
             __syncthreads();
-            for (int t = tid; t < n_s; t += NT) vlist[t] = S[perm_index((uint32_t)t, (uint32_t)n_s, hb, rk)];
+            for (int t = tid; t < n_s; t += NT) vlist[t] = (VT)S[perm_index((uint32_t)t, (uint32_t)n_s, hb, rk)];
             __syncthreads();
             int moved = 0;
             int t = 0;
@@ -1221,7 +1223,7 @@ static void launch_cover_fast(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local
     MCB_LAUNCH_CHECK();
 }
 
-template <int B, int OUT_SLOTS, int IN_SLOTS>
+template <int B, int OUT_SLOTS, int IN_SLOTS, typename VT>
 static void launch_cover_batch(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
                                const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling, int32_t burn_in,
                                int32_t max_sweeps, int32_t ncl_cap, int32_t max_out, size_t smem, int32_t* mc, int32_t* f_ws,
@@ -1229,11 +1231,11 @@ static void launch_cover_batch(mcb_ctx* ctx, const FastGraph& fg, int32_t n_loca
 {
     static size_t configured = 0;
     if (smem > configured) {
-        MCB_CUDA(cudaFuncSetAttribute(graph_cover_batch_kernel<B, OUT_SLOTS, IN_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MCB_CUDA(cudaFuncSetAttribute(graph_cover_batch_kernel<B, OUT_SLOTS, IN_SLOTS, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const int32_t out_warps = std::max(1, (int)ceil_div(max_out, 32));
-    graph_cover_batch_kernel<B, OUT_SLOTS, IN_SLOTS><<<n_local, 128 * B, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds,
+    graph_cover_batch_kernel<B, OUT_SLOTS, IN_SLOTS, VT><<<n_local, 128 * B, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds,
                                                                                     min_size, cooling, burn_in, max_sweeps,
                                                                                     ncl_cap, out_warps, mc, f_ws, sweeps, status);
     MCB_LAUNCH_CHECK();
@@ -1278,18 +1280,22 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
         // resamples are queued than those 2 x num_sms slots the machine is issue-bound and batches of 2 (less
         // speculative waste, four 256-thread CTAs per SM) give more throughput: 500 resamples 99 ms vs 112 ms
         const int auto_b = n_local > 2 * ctx->num_sms ? 2 : 4;
-#define BATCH(BB, OS, IS, AUTO)                                                                                               \
+#define BATCH(BB, OS, IS, VT, AUTO)                                                                                       \
     if ((auto_ && (AUTO)) || want == "batch" #BB) {                                                                      \
-        const size_t bsmem = ((size_t)(1 + 4 * BB) * ncl_cap + (size_t)n_s) * sizeof(uint32_t) + (size_t)g.N * sizeof(int16_t) + 16; \
-        if (max_out <= OS * 128 && max_in <= IS * 128 && bsmem <= 200 * 1024) {                                           \
-            launch_cover_batch<BB, OS, IS>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in, \
-                                           max_sweeps, ncl_cap, max_out, bsmem, mc, f_ws, sweeps, status);                \
+        const size_t bsmem = (size_t)(1 + 4 * BB) * ncl_cap * sizeof(uint32_t) + (size_t)((n_s + 1) & ~1) * sizeof(VT) +  \
+                             (size_t)g.N * sizeof(int16_t) + 16;                                                          \
+        if (max_out <= OS * 128 && max_in <= IS * 128 && bsmem <= 200 * 1024 && (sizeof(VT) == 4 || g.N < 65536)) {       \
+            launch_cover_batch<BB, OS, IS, VT>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling,      \
+                                               burn_in, max_sweeps, ncl_cap, max_out, bsmem, mc, f_ws, sweeps, status);   \
             return;                                                                                                       \
         }                                                                                                                 \
     }
-        BATCH(4, 1, 3, auto_b == 4) BATCH(2, 1, 3, auto_b == 2) BATCH(8, 1, 3, false)
-        BATCH(4, 2, 4, true)                  // K = 150 graphs: out-degree <= 256, in-degree <= 512 (one CTA per SM)
-        BATCH(2, 1, 3, true)                  // batches of 4 did not fit in shared memory
+        BATCH(4, 1, 3, int32_t, auto_b == 4) BATCH(2, 1, 3, int32_t, auto_b == 2) BATCH(8, 1, 3, int32_t, false)
+        // K = 150 graphs: out-degree <= 256, in-degree <= 512.  With a 16-bit visit order two CTAs of the 2-visit
+        // instantiation fit an SM (C5: 96 KB each); otherwise one CTA of the 4-visit one
+        BATCH(2, 2, 4, uint16_t, n_local > ctx->num_sms)
+        BATCH(4, 2, 4, int32_t, true)
+        BATCH(2, 1, 3, int32_t, true)             // batches of 4 did not fit in shared memory
 #undef BATCH
         const int32_t kin_stride = (int32_t)round_up((int64_t)std::max(std::min(max_in, ncl_cap), 1), 32) + 2;
 #define WARPK(BB, OS)                                                                                                    \

@@ -129,7 +129,7 @@ def test_graph_cover_kernel_variants_bit_exact(ctx, oracle, kernel, monkeypatch)
         assert np.array_equal(mc[r], omc), (kernel, r)
 
 
-@pytest.mark.parametrize("kernel", ["auto", "batch4", "warp16", "warp8", "fast", "slow"])
+@pytest.mark.parametrize("kernel", ["auto", "batch2", "batch4", "warp16", "warp8", "fast", "slow"])
 def test_graph_cover_high_degree_graph(ctx, oracle, kernel, monkeypatch):
     """K = 140 graph (out-degree > 128, in-degree up to 3K as at K = 150 in C4/C5): the wider-slot instantiations
     of the speculative kernels and the 256-thread sequential kernel against the oracle"""
