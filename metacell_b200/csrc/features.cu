@@ -17,12 +17,19 @@
 
 namespace mcb {
 
+constexpr uint32_t FEAT_LUT = 256;
+
 // one warp per cell: sum / sum of squares of the transformed feature entries in fp64
 __global__ void feat_stats_kernel(int64_t ncells, const int64_t* __restrict__ p, const int32_t* __restrict__ ridx,
                                   const uint32_t* __restrict__ x, const int32_t* __restrict__ feat_map, int32_t G,
                                   double k_nonz, double* __restrict__ mu_out, double* __restrict__ inv_out,
                                   int32_t* __restrict__ valid)
 {
+    // UMI counts are small integers: the transform of u < 256 comes from a table built with the same expression
+    // (bit-identical), which removes three fp64 log2 evaluations per stored entry from the feature stage
+    __shared__ double lut[FEAT_LUT];
+    for (int u = threadIdx.x; u < FEAT_LUT; u += blockDim.x) lut[u] = log2(1.0 + k_nonz * (double)u);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -33,7 +40,7 @@ __global__ void feat_stats_kernel(int64_t ncells, const int64_t* __restrict__ p,
             const uint32_t u = x[e];
             if (u == 0) continue;
             if (feat_map[ridx[e]] < 0) continue;
-            s += log2(1.0 + k_nonz * (double)u);
+            s += u < FEAT_LUT ? lut[u] : log2(1.0 + k_nonz * (double)u);
             ++cnt;
         }
         s = warp_reduce_sum(s);
@@ -45,7 +52,7 @@ __global__ void feat_stats_kernel(int64_t ncells, const int64_t* __restrict__ p,
             const uint32_t u = x[e];
             if (u == 0) continue;
             if (feat_map[ridx[e]] < 0) continue;
-            const double dlt = log2(1.0 + k_nonz * (double)u) - mu;
+            const double dlt = (u < FEAT_LUT ? lut[u] : log2(1.0 + k_nonz * (double)u)) - mu;
             s2 += dlt * dlt;
         }
         s2 = warp_reduce_sum(s2);
@@ -111,6 +118,9 @@ feat_rows_kernel(int64_t ncells, const int64_t* __restrict__ p, const int32_t* _
                  __half* __restrict__ Zh, __half* __restrict__ Zl, int32_t* __restrict__ cell_of_row)
 {
     extern __shared__ float srow[];        // [Gpad]
+    __shared__ double lut[FEAT_LUT];
+    for (int u = threadIdx.x; u < FEAT_LUT; u += FR_THREADS) lut[u] = log2(1.0 + k_nonz * (double)u);
+    __syncthreads();
     for (int64_t c = blockIdx.x; c < ncells; c += gridDim.x) {
         if (!valid[c]) continue;           // uniform per block
         const double mu = mu_in[c], inv = inv_in[c];
@@ -122,7 +132,7 @@ feat_rows_kernel(int64_t ncells, const int64_t* __restrict__ p, const int32_t* _
             if (u == 0) continue;
             const int32_t f = feat_map[ridx[e]];
             if (f < 0) continue;
-            const double v = log2(1.0 + k_nonz * (double)u);
+            const double v = u < FEAT_LUT ? lut[u] : log2(1.0 + k_nonz * (double)u);
             srow[f] = (float)((v - mu) * inv);
         }
         __syncthreads();
