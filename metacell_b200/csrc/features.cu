@@ -67,7 +67,9 @@ __global__ void feat_stats_kernel(int64_t ncells, const int64_t* __restrict__ p,
     }
 }
 
-// single-block exclusive scan (n up to a few million; negligible next to the GEMM)
+// single-block exclusive scan (n up to a few million).  Each thread owns SCAN_VPT consecutive elements per sweep, so a
+// 100,000-element scan is 25 sweeps of three barriers instead of 98.
+constexpr int SCAN_VPT = 4;
 template <typename T>
 __global__ void __launch_bounds__(1024) excl_scan_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t n,
                                                           T* __restrict__ total)
@@ -77,10 +79,13 @@ __global__ void __launch_bounds__(1024) excl_scan_kernel(const T* __restrict__ i
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        const T v = i < n ? in[i] : (T)0;
-        T inc = v;
+    for (int64_t base = 0; base < n; base += 1024 * SCAN_VPT) {
+        const int64_t i0 = base + (int64_t)threadIdx.x * SCAN_VPT;
+        T v[SCAN_VPT];
+        T mine = 0;
+#pragma unroll
+        for (int q = 0; q < SCAN_VPT; ++q) { v[q] = i0 + q < n ? in[i0 + q] : (T)0; mine += v[q]; }
+        T inc = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             T u = __shfl_up_sync(0xffffffffu, inc, o);
@@ -91,7 +96,9 @@ __global__ void __launch_bounds__(1024) excl_scan_kernel(const T* __restrict__ i
         T wbase = 0, all = 0;
         for (int q = 0; q < 32; ++q) { T t = warp_tot[q]; if (q < w) wbase += t; all += t; }
         const T carry = carry_s;
-        if (i < n) out[i] = carry + wbase + inc - v;
+        T run = carry + wbase + inc - mine;
+#pragma unroll
+        for (int q = 0; q < SCAN_VPT; ++q) { if (i0 + q < n) out[i0 + q] = run; run += v[q]; }
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + all;
         __syncthreads();
