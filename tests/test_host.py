@@ -130,3 +130,21 @@ def test_rollmedian_matches_oracle_and_gene_stat_oracle_on_tiny_case():
     csum = raw.sum(axis=0)
     assert np.allclose(st["n_mean"], (raw * (1000.0 / csum)).mean(axis=1))
     assert np.isnan(st["sz_cor"][1]) and abs(st["sz_cor"][0] - np.corrcoef(raw[0], csum)[0, 1]) < 1e-15
+
+
+def test_mc_confusion_mat_host_logic(tmp_path):
+    """mcell_mc_confusion_mat is host tabulation (reference R/mc_confusion.r:10-45): edges between covered cells are
+    counted per (metacell of source, metacell of target); cells outside the cover contribute nothing"""
+    from metacell_b200 import api
+    api.scdb_init(str(tmp_path), force_reinit=True)
+    cells = [f"c{i}" for i in range(6)]
+    edges = {"mc1": np.array([0, 0, 1, 2, 3, 4, 5]), "mc2": np.array([1, 2, 0, 3, 2, 5, 0]), "w": np.ones(7)}
+    api.scdb_add_cgraph("g", api.tgCellGraph(edges, cells))
+    api._scdb_add("mc", "m", {"mc": {"c0": 1, "c1": 1, "c2": 2, "c3": 2, "c4": 2}, "outliers": ["c5"]})
+    confu = api.mcell_mc_confusion_mat("m", "g", 2)
+    # c0->c1 (1,1) c0->c2 (1,2) c1->c0 (1,1) c2->c3 (2,2) c3->c2 (2,2); c4->c5 and c5->c0 touch the outlier
+    assert np.array_equal(confu, np.array([[2, 1], [0, 2]]))
+    api._scdb_add("mc", "bad", {"mc": {"zz": 1}, "outliers": []})
+    with pytest.raises(api.McbError, match="MC-ERR"):
+        api.mcell_mc_confusion_mat("bad", "g", 2)
+    assert api.mcell_mc_confusion_mat("bad", "g", 2, ignore_mismatch=True).size == 0
