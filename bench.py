@@ -26,6 +26,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv or os.environ.get("MCB_BENCH_ALL_CORES"):
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to every rank; the CPU arm must use all host cores, and the
+    # BLAS / OpenMP pools read these when numpy and the oracle are first loaded
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count())
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -47,6 +53,8 @@ def parse():
     ap.add_argument("--seed", type=int, default=1234)
     ap.add_argument("--no-coclust", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-bench parity check against the fp64 oracle")
+    ap.add_argument("--parity-rows", type=int, default=256)
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto ~15 s)")
     return ap.parse_args()
 
@@ -65,7 +73,8 @@ def make_input(a):
 # CPU port (baseline + reference arm)
 # ------------------------------------------------------------------------------------------------
 def cpu_port(a, m, feats, rows=0, target_s=15.0):
-    """A3+A4 on all cells, then A5 (the >95% stage) on a bounded row sample with all host cores."""
+    """A3+A4 on all cells, then A5 (the >95% stage) on a bounded row sample with all host cores: OpenBLAS fp64 dgemm in
+    row blocks + OpenMP per-row partial selection (oracle/mc_oracle.c orc_select_rows)."""
     from oracle import oracle as O, oracle_np as P
     fm = np.full(m.ngenes, -1, np.int32)
     fm[feats] = np.arange(feats.size)
@@ -77,16 +86,19 @@ def cpu_port(a, m, feats, rows=0, target_s=15.0):
     Kc = a.K * 10
     if rows <= 0:           # calibrate: one block, then size the sample for ~15 s
         t0 = time.perf_counter()
-        P.cor_knn_blas(Zv, Kc, 0, min(256, M))
-        per_row = (time.perf_counter() - t0) / min(256, M)
-        rows = int(max(256, min(M, target_s / max(per_row, 1e-9)) // 256 * 256))
+        P.cor_knn_blas(Zv, Kc, 0, min(1024, M))
+        per_row = (time.perf_counter() - t0) / min(1024, M)
+        rows = int(max(1024, min(M, target_s / max(per_row, 1e-9)) // 1024 * 1024))
     rows = min(rows, M)
+    split = {}
     t0 = time.perf_counter()
-    P.cor_knn_blas(Zv, Kc, 0, rows)
+    P.cor_knn_blas(Zv, Kc, 0, rows, timing=split)
     t_knn = time.perf_counter() - t0
     cells_per_s = rows / (t_knn + t_feat * rows / M)
-    return dict(value=cells_per_s, unit=UNIT, cores=os.cpu_count(), kind="port",
-                sample=f"features on all {M} cells + correlation/top-{Kc} (OpenBLAS fp64 dgemm + argpartition) for "
+    return dict(value=cells_per_s, unit=UNIT, cores=os.cpu_count(), omp_threads=O.num_threads(), kind="port",
+                phases_s={"features_all_cells": round(t_feat, 3), "dgemm": round(split.get("dgemm", 0.0), 3),
+                          "select": round(split.get("select", 0.0), 3)},
+                sample=f"features on all {M} cells + correlation/top-{Kc} (OpenBLAS fp64 dgemm + OpenMP per-row select) for "
                        f"{rows} of {M} rows against all columns; balancing (<3% of CPU time) excluded; "
                        f"{t_knn:.1f} s measured"), rows, t_knn
 
@@ -112,6 +124,46 @@ def run_reference(a):
             "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "CPU port of the tgstat path (tgstat itself cannot run here: no R); each step is a bounded row sample"}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# in-bench parity: the bench workload's own result against the fp64 oracle (untimed, after the timed region)
+# ------------------------------------------------------------------------------------------------
+def parity_block(a, m, feats, cells, col, cor, src, dst, w, row0=0):
+    """`col` / `cor`: the GPU's kNN lists of rows [row0, row0 + col.shape[0]) of the valid cells; (src, dst, w) the
+    balanced edges of the same rows.  Checks a random row sample against orc_select_rows on fp64 correlations
+    (north_star: correlations within 1e-5, lists equal except inside runs tied within that tolerance) and, when the
+    lists cover every row, the balanced edges bit for bit against orc_balance of the GPU's own lists."""
+    from oracle import oracle as O, oracle_np as P
+    t0 = time.perf_counter()
+    fm = np.full(m.ngenes, -1, np.int32)
+    fm[feats] = np.arange(feats.size)
+    Z, valid = O.features(m.indptr, m.indices, m.data, fm, feats.size)
+    Zv = Z[valid]
+    M, Kc = Zv.shape[0], a.K * 10
+    ok_cells = bool(np.array_equal(cells, np.nonzero(valid)[0]))
+    n = min(a.parity_rows, col.shape[0])
+    pick = np.sort(np.random.default_rng(a.seed + 99).choice(col.shape[0], n, replace=False))
+    ocol, ocor = P.cor_knn_blas(Zv, Kc + 8, rows=pick + row0)
+    gc, gr = col[pick], cor[pick].astype(np.float64)
+    dcor = float(np.abs(gr - ocor[:, :Kc]).max())
+    diff = gc != ocol[:, :Kc]
+    off_tie = 0                       # disagreeing positions whose oracle neighbours are NOT tied within 2e-5
+    for i, j in zip(*np.nonzero(diff)):
+        nb = [abs(ocor[i, j] - ocor[i, jj]) for jj in (j - 1, j + 1) if 0 < jj < ocor.shape[1]]
+        if not nb or min(nb) >= 2e-5:
+            off_tie += 1
+    out = {"rows": int(n), "of_rows": int(M), "max_abs_dcor": dcor, "list_agreement": float((~diff).mean()),
+           "disagreements_off_ties": int(off_tie), "valid_cells_equal": ok_cells, "tolerance": 1e-5}
+    if col.shape[0] == M:
+        deg, odst, _ = O.balance(col, a.K, 10, 3)
+        osrc, odst2, ow = O.edges_from_balance(deg, odst, a.K)
+        out["edges_bit_exact_on_gpu_lists"] = bool(np.array_equal(src, cells[osrc]) and np.array_equal(dst, cells[odst2])
+                                                   and np.array_equal(w, ow))
+        out["edges"] = int(src.size)
+    out["ok"] = bool(ok_cells and dcor < 1e-5 and off_tie == 0 and out.get("edges_bit_exact_on_gpu_lists", True))
+    out["seconds"] = round(time.perf_counter() - t0, 1)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -311,6 +363,17 @@ def run_ours(a):
         if world == 1 and not a.no_cpu:
             cb, _, _ = cpu_port(a, m, feats, a.cpu_rows)
             line["cpu_baseline"] = cb
+        if world == 1 and not a.no_parity:
+            g = _lib.CGraph.from_csc(ctx, csc_dev, feats, 7.0)
+            cells = g.valid_cells()
+            g.knn(a.K, 10)
+            col, cor = g.download_knn()
+            g.mutual(3)
+            g.prune()
+            src, dst, w = g.edges()
+            g.destroy()
+            line["parity"] = parity_block(a, m, feats, cells, col, cor, src, dst, w)
+            del col, cor
     coc = None if a.no_coclust else bench_coclust(ctx, a, rank, world)
     if rank == 0:
         if coc is not None:

@@ -305,6 +305,43 @@ int orc_cor_knn(int64_t M, int32_t G, const double* Z, int32_t Kc, int64_t row_b
 }
 
 /* ------------------------------------------------------------------------------------------
+ * A5 (selection half), for the multi-core CPU baseline: the dense correlation block C[nrows][ldc]
+ * (fp64, e.g. an OpenBLAS dgemm of Z[rows] . Z^T) -> per row the min(Kc, M) best columns by
+ * (cor desc, col asc), the row's own column self_col[r] forced to rank 1 with cor = 1 -- the same
+ * rule as orc_cor_knn above, one OpenMP thread per row.  tgstat's tgs_cor_knn (call site
+ * R/utils.r:119) can run its correlation through BLAS (tgs_use.blas), so dgemm + this select is
+ * the fair all-cores restatement of that stage.
+ * ---------------------------------------------------------------------------------------- */
+int orc_select_rows(int64_t nrows, int64_t M, const double* C, int64_t ldc, const int64_t* self_col, int32_t Kc,
+                    int32_t* knn_col, double* knn_cor)
+{
+    if (Kc <= 0 || M <= 0) return 1;
+    const int64_t kk = Kc < M ? Kc : M;
+    int err = 0;
+#pragma omp parallel
+    {
+        cand_t* cd = (cand_t*)malloc(sizeof(cand_t) * (size_t)M);
+        if (!cd) err = 2;
+#pragma omp for schedule(dynamic, 4)
+        for (int64_t r = 0; r < nrows; ++r) {
+            if (err) continue;
+            const double* ci = C + (size_t)r * (size_t)ldc;
+            const int64_t self = self_col ? self_col[r] : -1;
+            for (int64_t j = 0; j < M; ++j) { cd[j].c = ci[j]; cd[j].j = (int32_t)j; }
+            if (self >= 0 && self < M) cd[self].c = 2.0;
+            select_best(cd, M, kk);
+            qsort(cd, (size_t)kk, sizeof(cand_t), cmp_cand);
+            int32_t* oc = knn_col + (size_t)r * (size_t)Kc;
+            double*  ov = knn_cor + (size_t)r * (size_t)Kc;
+            for (int64_t q = 0; q < kk; ++q) { oc[q] = cd[q].j; ov[q] = (cd[q].j == self) ? 1.0 : cd[q].c; }
+            for (int64_t q = kk; q < Kc; ++q) { oc[q] = -1; ov[q] = 0.0; }
+        }
+        free(cd);
+    }
+    return err;
+}
+
+/* ------------------------------------------------------------------------------------------
  * A6. tgs_graph(x_knn, knn = K, k_expand, k_beta)  (call site R/utils.r:120).  The only in-tree
  * statement of the rule is cormat_to_balanced_knn, R/cgraph_knn_mcnorm.r:48-81:
  *   keep pair iff  K*K*k_expand - rank(i,j)*rank(j,i) > 0            (:66-68, strict)

@@ -101,6 +101,21 @@ def cor_knn(Z, Kc, row_begin=0, row_end=None):
     return col, cor
 
 
+def select_rows(Cblock, self_cols, Kc):
+    """orc_select_rows: per row of a dense fp64 correlation block the best min(Kc, M) columns, (cor desc, col asc),
+    self forced to rank 1; all host cores (OpenMP)."""
+    Cblock = np.ascontiguousarray(Cblock, dtype=np.float64)
+    nr, M = Cblock.shape
+    sc = np.ascontiguousarray(self_cols, dtype=np.int64)
+    col = np.empty((nr, Kc), dtype=np.int32)
+    cor = np.empty((nr, Kc), dtype=np.float64)
+    rc = lib().orc_select_rows(C.c_int64(nr), C.c_int64(M), _p(Cblock, C.c_double), C.c_int64(M), _p(sc, C.c_int64),
+                               C.c_int32(Kc), _p(col, C.c_int32), _p(cor, C.c_double))
+    if rc:
+        raise RuntimeError(f"orc_select_rows rc={rc}")
+    return col, cor
+
+
 def balance(knn_col, K, k_expand=10, k_beta=3, thresh_strict=True, keep_self=False):
     knn_col = np.ascontiguousarray(knn_col, dtype=np.int32)
     M, Kc = knn_col.shape

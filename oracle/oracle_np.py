@@ -2,14 +2,46 @@
 
 tgstat can run its correlation through BLAS (`options(tgs_use.blas = TRUE)`), so the
 fair multi-core CPU baseline for tgs_cor_knn (reference call site R/utils.r:119) is an fp64 dgemm in
-row blocks followed by a per-row partial selection.  Semantics are those of mc_oracle.c orc_cor_knn:
+row blocks followed by a per-row partial selection (OpenMP, mc_oracle.c orc_select_rows).  Semantics are those of mc_oracle.c orc_cor_knn:
 self forced to rank 1, ties to the lower column index.  Only bench.py's cpu_baseline / --impl
 reference legs and tests/ may import this module.  PARITY UNPINNED (see mc_oracle.c).
 """
 import numpy as np
 
 
-def cor_knn_blas(Z, Kc, row_begin=0, row_end=None, block=512):
+def cor_knn_blas(Z, Kc, row_begin=0, row_end=None, block=1024, rows=None, timing=None):
+    """rows [row_begin, row_end) (or the explicit index list `rows`) against all columns: OpenBLAS dgemm in row
+    blocks (all cores) + the OpenMP per-row select of mc_oracle.c (all cores).  `timing` (dict) accumulates the
+    seconds spent in each half under "dgemm" / "select"."""
+    import time
+    from . import oracle as O
+    Z = np.ascontiguousarray(Z, dtype=np.float64)
+    M = Z.shape[0]
+    if rows is None:
+        row_end = M if row_end is None else row_end
+        rows = np.arange(row_begin, row_end, dtype=np.int64)
+    else:
+        rows = np.asarray(rows, dtype=np.int64)
+    col = np.full((rows.size, Kc), -1, dtype=np.int32)
+    cor = np.zeros((rows.size, Kc), dtype=np.float64)
+    for b0 in range(0, rows.size, block):
+        rb = rows[b0:b0 + block]
+        t0 = time.perf_counter()
+        contiguous = rb.size > 0 and rb[-1] - rb[0] + 1 == rb.size
+        A = Z[rb[0]:rb[-1] + 1] if contiguous else Z[rb]
+        C = A @ Z.T                                         # dgemm on all cores
+        t1 = time.perf_counter()
+        col[b0:b0 + rb.size], cor[b0:b0 + rb.size] = O.select_rows(C, rb, Kc)
+        t2 = time.perf_counter()
+        if timing is not None:
+            timing["dgemm"] = timing.get("dgemm", 0.0) + (t1 - t0)
+            timing["select"] = timing.get("select", 0.0) + (t2 - t1)
+    return col, cor
+
+
+def cor_knn_numpy(Z, Kc, row_begin=0, row_end=None, block=512):
+    """the same stage with numpy only (argpartition + lexsort; single-threaded selection) -- kept as an independent
+    check of orc_select_rows"""
     Z = np.ascontiguousarray(Z, dtype=np.float64)
     M = Z.shape[0]
     row_end = M if row_end is None else row_end
@@ -18,7 +50,7 @@ def cor_knn_blas(Z, Kc, row_begin=0, row_end=None, block=512):
     cor = np.zeros((row_end - row_begin, Kc), dtype=np.float64)
     for i0 in range(row_begin, row_end, block):
         i1 = min(row_end, i0 + block)
-        C = Z[i0:i1] @ Z.T                                  # dgemm on all cores
+        C = Z[i0:i1] @ Z.T
         rows = np.arange(i0, i1)
         C[np.arange(i1 - i0), rows] = 2.0                   # self sentinel: always rank 1
         if kk < M:

@@ -6,7 +6,7 @@ edge sets bit-exact except at correlation ties within that tolerance; down-sampl
 import numpy as np
 import pytest
 
-from conftest import feat_map_of
+from conftest import feat_map_of, knn_parity as _knn_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -116,24 +116,6 @@ def test_correlation_kernels_vs_fp64(ctx, oracle, G):
 
 
 # ---- A5 ------------------------------------------------------------------------------------------
-def _knn_parity(col, cor, ocol_x, ocor_x, tol=COR_TOL):
-    """ocol_x / ocor_x: oracle lists computed a few ranks deeper than `col`, so that the tie partner of
-    the last rank is visible.  Disagreements are only allowed inside runs of correlations tied within tol."""
-    kc = col.shape[1]
-    ocol, ocor = ocol_x[:, :kc], ocor_x[:, :kc]
-    assert np.abs(cor - ocor).max() < tol
-    assert np.array_equal(col[:, 0], ocol[:, 0])                      # self is rank 1 (R/atlas.r:475-476)
-    diff = col != ocol
-    if diff.any():
-        r, q = np.nonzero(diff)
-        for i, j in zip(r, q):
-            nb = [abs(ocor_x[i, j] - ocor_x[i, jj]) for jj in (j - 1, j + 1) if 0 < jj < ocor_x.shape[1] and ocol_x[i, jj] >= 0]
-            assert nb and min(nb) < 2 * tol, (i, j, ocor_x[i, max(j - 1, 0):j + 2], cor[i, max(j - 1, 0):j + 2])
-        for i in np.unique(r):
-            assert len(set(col[i]) ^ set(ocol[i])) <= 2 * int(diff[i].sum())
-    return float((~diff).mean())
-
-
 @pytest.mark.parametrize("impl", [0, 1])
 @pytest.mark.parametrize("ncells,K,kx", [(1200, 20, 10), (900, 100, 10), (3000, 30, 10)])
 def test_cor_knn_parity(ctx, oracle, impl, ncells, K, kx):

@@ -121,8 +121,13 @@ def test_cor_knn_vs_bruteforce(oracle):
         assert np.array_equal(col[i], order)
     assert np.all(col[:, 0] == np.arange(Zv.shape[0])) and np.all(cor[:, 0] == 1.0)      # R/atlas.r:475-476
     assert np.all(np.diff(cor[:, 1:], axis=1) <= 1e-15)
-    c2, r2 = oracle_np.cor_knn_blas(Zv, 40)
+    c2, r2 = oracle_np.cor_knn_blas(Zv, 40)                       # dgemm + orc_select_rows (OpenMP)
     assert np.array_equal(col, c2) and np.abs(cor - r2).max() < 1e-12
+    c3, r3 = oracle_np.cor_knn_numpy(Zv, 40)                      # numpy-only selection
+    assert np.array_equal(col, c3) and np.abs(cor - r3).max() < 1e-12
+    pick = np.array([7, 3, 50, 51, 52, 11], dtype=np.int64)       # explicit row lists (the bench's parity sample)
+    c4, r4 = oracle_np.cor_knn_blas(Zv, 40, rows=pick)
+    assert np.array_equal(c4, col[pick]) and np.abs(r4 - cor[pick]).max() < 1e-12
     # Kc > M pads with -1; row ranges agree with the full call
     colp, _ = oracle.cor_knn(Zv[:30], 40)
     assert np.all(colp[:, 30:] == -1) and np.all(colp[:, :30] >= 0)
