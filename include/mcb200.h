@@ -39,6 +39,8 @@ typedef struct mcb_ctx     mcb_ctx;      /* device + stream + memory pool       
 typedef struct mcb_csc     mcb_csc;      /* device-resident genes x cells CSC count matrix   */
 typedef struct mcb_cgraph  mcb_cgraph;   /* one balanced-graph build (features .. edges)     */
 typedef struct mcb_coclust mcb_coclust;  /* one resampled co-clustering run                  */
+typedef struct mcb_comm    mcb_comm;     /* one rank of a multi-GPU communicator (context + NCCL)    */
+typedef struct mcb_multi   mcb_multi;    /* one process driving several devices (contexts + NCCL + threads) */
 
 int         mcb_version(void);
 const char* mcb_last_error(void);
@@ -55,7 +57,8 @@ void* mcb_ctx_stream(mcb_ctx* ctx);                   /* cudaStream_t all kernel
  *          "thresh_strict" 1 = s < K*K*k_expand (default), 0 = s <= ...;
  *          "trim"      release the context's cache of device blocks back to the driver;
  *          "cap_override" n > 0: test hook, caps the per-row candidate capacity so rows take the
- *                      exact-row path                                                           */
+ *                      exact-row path;
+ *          "host_threads" staging threads of this context (0 = min(16, cores / 2))              */
 int   mcb_ctx_set_option(mcb_ctx* ctx, const char* key, int64_t value);
 /* stage timings of the calls since the last mcb_ctx_timings_reset (needs option profile=1).
  * Writes up to cap entries; *n receives the number available.  names[i] are static strings.  */
@@ -68,6 +71,13 @@ int mcb_downsamp_depth(const int64_t* col_sums, int64_t ncells, double* depth);
 /* ---- CSC matrix (the dgCMatrix slots of tgScMat@mat: @p, @i, @x, @Dim) --------------------- */
 int  mcb_csc_upload(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* p, const int32_t* i,
                     const double* x, mcb_csc** out);                       /* host -> device      */
+/* the cell range [cell0, cell0 + ncells) of a larger host matrix: p points at p_full[cell0] and keeps its ABSOLUTE
+ * offsets, i and x are the full arrays.  What each rank of a multi-GPU build uploads.
+ * Both upload entry points stage through pinned memory with host threads (ordinary pageable R vectors reach PCIe speed),
+ * narrow the values on the way (counts to 16 bits with escapes, row indices to 16 bits when ngenes <= 65536), and
+ * validate the matrix: x integral, >= 0 and < 2^32; p non-decreasing; 0 <= i < ngenes, strictly ascending per column. */
+int  mcb_csc_upload_range(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* p, const int32_t* i,
+                          const double* x, mcb_csc** out);
 int  mcb_csc_wrap_device(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* dev_p,
                          const int32_t* dev_i, const uint32_t* dev_x, mcb_csc** out); /* no copy  */
 void mcb_csc_free(mcb_csc* m);
@@ -122,6 +132,9 @@ int  mcb_cgraph_prune(mcb_cgraph* g, int64_t* n_edges);
 /* edges of the owned rows as (mc1, mc2, w) (R/cgraph_knn.r:22), original 0-based cell ids,
  * ordered by (source, place).                                                                  */
 int  mcb_cgraph_edges(mcb_cgraph* g, int32_t* host_src, int32_t* host_dst, double* host_w);
+/* the same table left on the device; pointers stay valid until the handle is destroyed                    */
+int  mcb_cgraph_edges_device(mcb_cgraph* g, int64_t* n_edges, const int32_t** dev_src, const int32_t** dev_dst,
+                             const double** dev_w);
 /* test hook: dense correlation block C[a_rows][b_rows] of the first rows of Z through one kernel:
  * impl 0 = tcgen05 3-pass split-TF32, 2 = tcgen05 1-pass TF32, 1 = SIMT fp32.  Call before _mutual. */
 int  mcb_cgraph_debug_cor(mcb_cgraph* g, int impl, int64_t a_rows, int64_t b_rows, float* host_c);
@@ -162,6 +175,48 @@ int  mcb_cgraph_bknn(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t
                      int32_t** src, int32_t** dst, double** w, int64_t* n_valid_cells);
 void mcb_free(void* host_ptr);
 
+/* ---- multi-GPU.  NCCL is used inside the library (resolved with dlopen at the first call):
+ * correlation tiles and rows shard over ranks; exchanges = all-gather of the feature planes, all-gather of the filter
+ * thresholds, all-to-all of candidate records, all-gather of the kNN lists and of the in-degree cuts; co-clustering
+ * resamples stride over ranks with one reduce(sum) of the counters.  Two deployments share the same rank-level code:
+ *
+ * (1) ONE PROCESS, several devices -- what the single R process calls (R/cgraph_knn.r:10-25,
+ *     R/coclust_graph_cov.r:13-58).  A session owns a context + communicator + host thread per device; every device
+ *     uploads its own cell range straight from the caller's dgCMatrix slots and writes its own edge rows straight
+ *     into the result table.  devices == NULL: devices 0 .. ndev-1.                                                */
+int      mcb_multi_create(const int32_t* devices, int32_t ndev, mcb_multi** out);
+void     mcb_multi_destroy(mcb_multi* m);
+int      mcb_multi_size(const mcb_multi* m);
+mcb_ctx* mcb_multi_ctx(mcb_multi* m, int32_t rank);                       /* borrowed: timings / options of one device */
+int      mcb_multi_set_option(mcb_multi* m, const char* key, int64_t value);
+/* arguments and outputs exactly as mcb_cgraph_bknn */
+int  mcb_cgraph_bknn_multi(mcb_multi* m, int32_t ngenes, int64_t ncells, const int64_t* p, const int32_t* i,
+                           const double* x, const int32_t* feat_rows, int32_t G, int32_t K, int32_t k_expand,
+                           int32_t k_beta, double k_nonz, int dsamp, uint64_t seed, int64_t* n_edges,
+                           int32_t** src, int32_t** dst, double** w, int64_t* n_valid_cells);
+/* tgs_graph_cover_resample(edges, knn, min_mc_size, cooling, burn_in, p_resamp, n_resamp, method = "full")
+ * (R/coclust_graph_cov.r:41) on all devices; outputs library-allocated (mcb_free): co_cluster rows + samples[N]     */
+int  mcb_coclust_multi(mcb_multi* m, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst, const double* w,
+                       int32_t n_resamp, int32_t n_s, const int32_t* samples, const uint64_t* seeds, int32_t min_mc_size,
+                       double cooling, int32_t burn_in, int32_t max_sweeps, int32_t knn, int64_t* n_pairs, int32_t** node1,
+                       int32_t** node2, int32_t** cnt, int32_t** samples_per_node);
+/* (2) ONE PROCESS PER DEVICE (e.g. under torchrun / mpirun): rank 0 makes a unique id, the launcher's own channel
+ *     carries its 128 bytes to the other ranks, every rank creates its communicator; then the rank-collective calls.  */
+int  mcb_comm_unique_id(uint8_t* id128);
+int  mcb_comm_create(mcb_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t* id128, mcb_comm** out);
+void mcb_comm_destroy(mcb_comm* c);
+int  mcb_comm_rank(const mcb_comm* c, int32_t* rank, int32_t* nranks);
+/* collective.  local = this rank's cells [cell_base, cell_base + ncells_local) (ascending contiguous ranges in rank
+ * order).  A1..A7; afterwards the handle holds the edges of this rank's share of the valid rows.                   */
+int  mcb_cgraph_build_sharded(mcb_comm* comm, const mcb_csc* local, int64_t cell_base, const int32_t* feat_rows, int32_t G,
+                              double k_nonz, int32_t K, int32_t k_expand, int32_t k_beta, int dsamp, uint64_t seed,
+                              mcb_cgraph** out, int64_t* n_edges_local);
+/* collective.  All ranks' edges to root's host in source order; outputs library-allocated on root, NULL elsewhere   */
+int  mcb_cgraph_gather_edges(mcb_comm* comm, mcb_cgraph* g, int32_t root, int64_t* n_edges_total, int32_t** src,
+                             int32_t** dst, double** w);
+/* collective.  reduce(sum) of cnt[N][N] and samples[N] into root                                                    */
+int  mcb_coclust_reduce(mcb_comm* comm, mcb_coclust* c, int32_t root);
+
 /* ---- A8: tgs_graph_cover_resample(..., method = "full") ------------------------------------ */
 /* Graph = directed weighted edges (0-based).  samples: [n_resamp][n_s] node ids and one uint64
  * seed per resample, both host-supplied.  Runs the resamples r with r % nranks == rank and
@@ -170,6 +225,13 @@ int  mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* sr
                      const double* w, int32_t n_resamp, int32_t n_s, const int32_t* samples,
                      const uint64_t* seeds, int32_t min_mc_size, double cooling, int32_t burn_in,
                      int32_t max_sweeps, int32_t rank, int32_t nranks, mcb_coclust** out);
+/* the same with tgs_graph_cover_resample's `knn` argument (R/coclust_graph_cov.r:39-41: K = round(nrow(edges)/ncells)):
+ * the most out-edges a node may use inside one resample, 0 = no limit.  A resample in which some node has more than
+ * knn sampled out-neighbours is rejected (MC-ERR) rather than silently covered without the limit.                  */
+int  mcb_coclust_run2(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst,
+                      const double* w, int32_t n_resamp, int32_t n_s, const int32_t* samples,
+                      const uint64_t* seeds, int32_t min_mc_size, double cooling, int32_t burn_in,
+                      int32_t max_sweeps, int32_t knn, int32_t rank, int32_t nranks, mcb_coclust** out);
 void mcb_coclust_destroy(mcb_coclust* c);
 /* tgs_graph_cover(edges, min_mc_size, cooling, burn_in) (R/mc_graphcov.r:27, R/mc_from_coclust.r:247): one cover over
  * all N nodes.  host_cluster[v] = 0 for outliers (R/mc_graphcov.r:28), otherwise a cluster id >= 1.            */

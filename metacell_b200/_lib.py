@@ -23,6 +23,10 @@ SYMBOLS = [
     "mcb_cgraph_prune", "mcb_cgraph_edges", "mcb_cgraph_debug_cor", "mcb_cor_knn_xy", "mcb_gene_stats", "mcb_mc_gene_tapply", "mcb_cgraph_bknn", "mcb_free",
     "mcb_coclust_run", "mcb_graph_cover", "mcb_coclust_destroy", "mcb_coclust_buffers", "mcb_coclust_assignments",
     "mcb_coclust_extract", "mcb_coclust_pairs",
+    "mcb_csc_upload_range", "mcb_cgraph_edges_device", "mcb_multi_create", "mcb_multi_destroy", "mcb_multi_size", "mcb_multi_ctx",
+    "mcb_multi_set_option", "mcb_cgraph_bknn_multi", "mcb_coclust_multi", "mcb_comm_unique_id", "mcb_comm_create",
+    "mcb_comm_destroy", "mcb_comm_rank", "mcb_cgraph_build_sharded", "mcb_cgraph_gather_edges", "mcb_coclust_reduce",
+    "mcb_coclust_run2",
 ]
 
 
@@ -43,7 +47,9 @@ def lib():
         L.mcb_last_error.restype = C.c_char_p
         L.mcb_ctx_stream.restype = C.c_void_p
         L.mcb_launch_count.restype = C.c_int64
-        for name in ("mcb_ctx_destroy", "mcb_csc_free", "mcb_cgraph_destroy", "mcb_coclust_destroy", "mcb_free"):
+        L.mcb_multi_ctx.restype = C.c_void_p
+        for name in ("mcb_ctx_destroy", "mcb_csc_free", "mcb_cgraph_destroy", "mcb_coclust_destroy", "mcb_free", "mcb_comm_destroy",
+                     "mcb_multi_destroy"):
             getattr(L, name).restype = None
         _lib = L
     return _lib
@@ -69,15 +75,19 @@ def as_c(a, dtype):
 class Context:
     """mcb_ctx: one device + stream + memory pool."""
 
-    def __init__(self, device=0):
-        self.h = C.c_void_p()
-        check(lib().mcb_ctx_create(C.c_int(device), C.byref(self.h)))
+    def __init__(self, device=0, borrowed=None):
+        self.owned = borrowed is None
+        if borrowed is None:
+            self.h = C.c_void_p()
+            check(lib().mcb_ctx_create(C.c_int(device), C.byref(self.h)))
+        else:
+            self.h = C.c_void_p(borrowed)           # e.g. a device context of a Multi session
         self.device = device
 
     def close(self):
-        if self.h:
+        if self.h and self.owned:
             lib().mcb_ctx_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
 
     def __del__(self):
         try:
@@ -141,6 +151,18 @@ class Csc:
         check(lib().mcb_csc_upload(ctx.h, C.c_int32(ngenes), C.c_int64(p.size - 1), ptr(p, C.c_int64),
                                    ptr(i, C.c_int32), ptr(x, C.c_double), C.byref(h)))
         return cls(ctx, h, ngenes, p.size - 1, int(p[-1]))
+
+    @classmethod
+    def upload_range(cls, ctx, ngenes, indptr, indices, data, cell0, cell1):
+        """cells [cell0, cell1) of the host matrix: what one rank of a sharded build uploads (mcb_csc_upload_range)"""
+        p = as_c(indptr, np.int64)
+        i = as_c(indices, np.int32)
+        x = as_c(data, np.float64)
+        h = C.c_void_p()
+        pp = C.cast(C.c_void_p(p.ctypes.data + 8 * int(cell0)), C.POINTER(C.c_int64))
+        check(lib().mcb_csc_upload_range(ctx.h, C.c_int32(ngenes), C.c_int64(int(cell1) - int(cell0)), pp, ptr(i, C.c_int32),
+                                         ptr(x, C.c_double), C.byref(h)))
+        return cls(ctx, h, ngenes, int(cell1) - int(cell0), int(p[cell1] - p[cell0]))
 
     @classmethod
     def upload_ptrs(cls, ctx, ngenes, ncells, nnz, p_ptr, i_ptr, x_ptr, keep=None):
@@ -317,29 +339,140 @@ class CGraph:
         return src[:self.n_edges], dst[:self.n_edges], w[:self.n_edges]
 
 
+def _take(pointer, n, copy=True):
+    """library-allocated host array -> numpy (copied, then released with mcb_free)"""
+    try:
+        a = np.ctypeslib.as_array(pointer, shape=(max(n, 1),))[:n]
+        return a.copy() if copy else a
+    finally:
+        if copy:
+            lib().mcb_free(pointer)
+
+
 def cgraph_bknn_oneshot(ctx, ngenes, indptr, indices, data, feat_rows, K, k_expand=10, k_beta=3, k_nonz=7.0,
-                        dsamp=False, seed=42):
-    """mcb_cgraph_bknn: the single call the R glue makes (host in, host out)."""
+                        dsamp=False, seed=42, raw=False):
+    """mcb_cgraph_bknn (ctx = Context) or mcb_cgraph_bknn_multi (ctx = Multi): the single call the R glue makes, ordinary
+    host arrays in, host edge table out.  raw=True skips the numpy copies and frees the library's arrays at once
+    (timing the call itself): returns (n_edges, n_valid)."""
     p = as_c(indptr, np.int64)
     i = as_c(indices, np.int32)
     x = as_c(data, np.float64)
     fr = as_c(feat_rows, np.int32)
     ne, nv = C.c_int64(0), C.c_int64(0)
     ps, pd, pw = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_double)()
-    check(lib().mcb_cgraph_bknn(ctx.h, C.c_int32(ngenes), C.c_int64(p.size - 1), ptr(p, C.c_int64), ptr(i, C.c_int32),
-                                ptr(x, C.c_double), ptr(fr, C.c_int32), C.c_int32(fr.size), C.c_int32(K),
-                                C.c_int32(k_expand), C.c_int32(k_beta), C.c_double(k_nonz), C.c_int(int(dsamp)),
-                                C.c_uint64(int(seed)), C.byref(ne), C.byref(ps), C.byref(pd), C.byref(pw), C.byref(nv)))
+    fn = lib().mcb_cgraph_bknn_multi if isinstance(ctx, Multi) else lib().mcb_cgraph_bknn
+    check(fn(ctx.h, C.c_int32(ngenes), C.c_int64(p.size - 1), ptr(p, C.c_int64), ptr(i, C.c_int32),
+             ptr(x, C.c_double), ptr(fr, C.c_int32), C.c_int32(fr.size), C.c_int32(K),
+             C.c_int32(k_expand), C.c_int32(k_beta), C.c_double(k_nonz), C.c_int(int(dsamp)),
+             C.c_uint64(int(seed)), C.byref(ne), C.byref(ps), C.byref(pd), C.byref(pw), C.byref(nv)))
     n = int(ne.value)
-    try:
-        src = np.ctypeslib.as_array(ps, shape=(max(n, 1),))[:n].copy()
-        dst = np.ctypeslib.as_array(pd, shape=(max(n, 1),))[:n].copy()
-        w = np.ctypeslib.as_array(pw, shape=(max(n, 1),))[:n].copy()
-    finally:
-        lib().mcb_free(ps)
-        lib().mcb_free(pd)
-        lib().mcb_free(pw)
-    return src, dst, w, int(nv.value)
+    if raw:
+        for q in (ps, pd, pw):
+            lib().mcb_free(q)
+        return n, int(nv.value)
+    return _take(ps, n), _take(pd, n), _take(pw, n), int(nv.value)
+
+
+class Multi:
+    """mcb_multi: one process driving several devices (contexts + NCCL communicators + one host thread each)."""
+
+    def __init__(self, devices):
+        dev = as_c(list(devices), np.int32)
+        self.h = C.c_void_p()
+        check(lib().mcb_multi_create(ptr(dev, C.c_int32), C.c_int32(dev.size), C.byref(self.h)))
+        self.devices = [int(d) for d in dev]
+
+    def close(self):
+        if self.h:
+            lib().mcb_multi_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self):
+        return int(lib().mcb_multi_size(self.h))
+
+    def ctx(self, rank):
+        return Context(self.devices[rank], borrowed=lib().mcb_multi_ctx(self.h, C.c_int32(rank)))
+
+    def set_option(self, key, value):
+        check(lib().mcb_multi_set_option(self.h, key.encode(), C.c_int64(int(value))))
+
+    def coclust(self, N, src, dst, w, samples, seeds, min_mc_size, cooling, burn_in, max_sweeps=1000, knn=0):
+        """mcb_coclust_multi: (node1, node2, cnt, samples_per_node)"""
+        src, dst, w = as_c(src, np.int32), as_c(dst, np.int32), as_c(w, np.float64)
+        samples, seeds = as_c(samples, np.int32), as_c(seeds, np.uint64)
+        n_resamp, n_s = samples.shape
+        npairs = C.c_int64(0)
+        p1, p2, pc, pn = (C.POINTER(C.c_int32)() for _ in range(4))
+        check(lib().mcb_coclust_multi(self.h, C.c_int32(N), C.c_int64(src.size), ptr(src, C.c_int32), ptr(dst, C.c_int32),
+                                      ptr(w, C.c_double), C.c_int32(n_resamp), C.c_int32(n_s), ptr(samples, C.c_int32),
+                                      ptr(seeds, C.c_uint64), C.c_int32(min_mc_size), C.c_double(cooling), C.c_int32(burn_in),
+                                      C.c_int32(max_sweeps), C.c_int32(knn), C.byref(npairs), C.byref(p1), C.byref(p2),
+                                      C.byref(pc), C.byref(pn)))
+        n = int(npairs.value)
+        return _take(p1, n), _take(p2, n), _take(pc, n), _take(pn, N)
+
+
+class Comm:
+    """mcb_comm: this process's rank of a multi-process communicator (one process per device)."""
+
+    def __init__(self, ctx, nranks, rank, unique_id):
+        self.ctx, self.rank, self.nranks = ctx, rank, nranks
+        self.h = C.c_void_p()
+        idb = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id)) if unique_id is not None else None
+        check(lib().mcb_comm_create(ctx.h, C.c_int32(nranks), C.c_int32(rank), idb, C.byref(self.h)))
+
+    @staticmethod
+    def unique_id():
+        b = (C.c_uint8 * 128)()
+        check(lib().mcb_comm_unique_id(b))
+        return bytes(b)
+
+    def close(self):
+        if self.h:
+            lib().mcb_comm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def build_sharded(self, local_csc, cell_base, feat_rows, K, k_expand=10, k_beta=3, k_nonz=7.0, dsamp=False, seed=42):
+        """mcb_cgraph_build_sharded: rank-collective A1..A7; returns a CGraph holding this rank's edges"""
+        fr = as_c(feat_rows, np.int32)
+        h = C.c_void_p()
+        ne = C.c_int64(0)
+        check(lib().mcb_cgraph_build_sharded(self.h, local_csc.h, C.c_int64(int(cell_base)), ptr(fr, C.c_int32), C.c_int32(fr.size),
+                                             C.c_double(k_nonz), C.c_int32(K), C.c_int32(k_expand), C.c_int32(k_beta),
+                                             C.c_int(int(dsamp)), C.c_uint64(int(seed)), C.byref(h), C.byref(ne)))
+        g = CGraph(self.ctx, h, keep=local_csc)
+        g._set_split(K, k_expand, self.rank, self.nranks)
+        g.n_edges = int(ne.value)
+        return g
+
+    def gather_edges(self, g, root=0, raw=False):
+        """mcb_cgraph_gather_edges: (src, dst, w) on root, None elsewhere"""
+        ne = C.c_int64(0)
+        ps, pd, pw = C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_double)()
+        check(lib().mcb_cgraph_gather_edges(self.h, g.h, C.c_int32(root), C.byref(ne), C.byref(ps), C.byref(pd), C.byref(pw)))
+        n = int(ne.value)
+        if self.rank != root:
+            return None
+        if raw:
+            for q in (ps, pd, pw):
+                lib().mcb_free(q)
+            return n
+        return _take(ps, n), _take(pd, n), _take(pw, n)
+
+    def coclust_reduce(self, cc, root=0):
+        check(lib().mcb_coclust_reduce(self.h, cc.h, C.c_int32(root)))
 
 
 GENE_STAT_COLUMNS = ("tot", "var", "niche_stat", "n_mean", "is_on_count", "sz_cor", "ds_top1", "ds_top2", "ds_top3",
@@ -387,7 +520,7 @@ class CoClust:
     """mcb_coclust: one resampled co-clustering run (this rank's share of the resamples)."""
 
     def __init__(self, ctx, N, src, dst, w, samples, seeds, min_mc_size, cooling, burn_in, max_sweeps=1000,
-                 rank=0, nranks=1):
+                 rank=0, nranks=1, knn=0):
         src = as_c(src, np.int32)
         dst = as_c(dst, np.int32)
         w = as_c(w, np.float64)
@@ -396,11 +529,11 @@ class CoClust:
         n_resamp, n_s = samples.shape
         self.ctx, self.N, self.n_resamp = ctx, N, n_resamp
         self.h = C.c_void_p()
-        check(lib().mcb_coclust_run(ctx.h, C.c_int32(N), C.c_int64(src.size), ptr(src, C.c_int32), ptr(dst, C.c_int32),
-                                    ptr(w, C.c_double), C.c_int32(n_resamp), C.c_int32(n_s), ptr(samples, C.c_int32),
-                                    ptr(seeds, C.c_uint64), C.c_int32(min_mc_size), C.c_double(cooling),
-                                    C.c_int32(burn_in), C.c_int32(max_sweeps), C.c_int32(rank), C.c_int32(nranks),
-                                    C.byref(self.h)))
+        check(lib().mcb_coclust_run2(ctx.h, C.c_int32(N), C.c_int64(src.size), ptr(src, C.c_int32), ptr(dst, C.c_int32),
+                                     ptr(w, C.c_double), C.c_int32(n_resamp), C.c_int32(n_s), ptr(samples, C.c_int32),
+                                     ptr(seeds, C.c_uint64), C.c_int32(min_mc_size), C.c_double(cooling),
+                                     C.c_int32(burn_in), C.c_int32(max_sweeps), C.c_int32(knn), C.c_int32(rank), C.c_int32(nranks),
+                                     C.byref(self.h)))
         self.n_local = len(range(rank, n_resamp, nranks))
 
     def destroy(self):

@@ -593,14 +593,16 @@ def resample_index_sets(ncells, p_resamp, n_resamp, seed):
 def tgs_graph_cover_resample(edges, knn, min_cluster_size, cooling, burn_in, p_resamp, n_resamp, method="full",
                              n_nodes=None, seed=None, ctx=None, max_sweeps=1000):
     """tgstat call of reference R/coclust_graph_cov.r:41.  edges: dict col1, col2, weight (0-based codes).
-    Returns dict(co_cluster = dict(node1, node2, cnt), samples = int[N])."""
+    `knn` (R passes K = round(nrow(edges) / ncells), R/coclust_graph_cov.r:39) caps the out-edges a node may use inside
+    one resample; 0 = no cap.  Returns dict(co_cluster = dict(node1, node2, cnt), samples = int[N])."""
     if method != "full":
         raise McbError("MC-ERR: only method = \"full\" is supported (what metacell calls)")
     ctx = _ctx(ctx)
     src, dst, w = edges["col1"], edges["col2"], edges["weight"]
     N = int(n_nodes if n_nodes is not None else max(int(np.max(src)), int(np.max(dst))) + 1)
     sets, seeds = resample_index_sets(N, p_resamp, n_resamp, get_param("mc_rseed") if seed is None else seed)
-    cc = _lib.CoClust(ctx, N, src, dst, w, sets, seeds, int(min_cluster_size), float(cooling), int(burn_in), max_sweeps)
+    cc = _lib.CoClust(ctx, N, src, dst, w, sets, seeds, int(min_cluster_size), float(cooling), int(burn_in), max_sweeps,
+                      knn=int(knn or 0))
     try:
         n1, n2, cnt, samples = cc.pairs()
     finally:

@@ -3,6 +3,7 @@
 // buffers, derives scalar parameters and moves bytes.
 #include "../../include/mcb200.h"
 #include "internal.h"
+#include "handles.h"
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -144,6 +145,8 @@ void mcb::ctx_release(mcb_ctx* ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     resolve_timers(ctx);
+    mcb::ctx_staging_destroy(ctx);
+    if (ctx->samp_dev) { cudaFree(ctx->samp_dev); ctx->samp_dev = nullptr; }
     ctx->trim();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -170,6 +173,12 @@ extern "C" int mcb_ctx_set_option(mcb_ctx* ctx, const char* key, int64_t value)
     else if (!strcmp(key, "keep_self")) ctx->keep_self = (int)value;
     else if (!strcmp(key, "thresh_strict")) ctx->thresh_strict = (int)value;
     else if (!strcmp(key, "cap_override")) ctx->cap_override = (int)value;
+    else if (!strcmp(key, "host_threads")) {
+        MCB_CHECK(value >= 0 && value <= 64, "host_threads must be between 0 and 64");
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        mcb::ctx_staging_destroy(ctx);                 // rebuilt with the new thread count on next use
+        ctx->host_threads = (int)value;
+    }
     else if (!strcmp(key, "trim")) { MCB_CUDA(cudaStreamSynchronize(ctx->stream)); ctx->trim(); }
     else throw Error(1, std::string("unknown option: ") + key);
     MCB_API_END
@@ -223,40 +232,55 @@ extern "C" int mcb_downsamp_depth(const int64_t* col_sums, int64_t ncells, doubl
 // ---------------------------------------------------------------------------------------------
 // CSC matrix
 // ---------------------------------------------------------------------------------------------
-struct mcb_csc {
-    CtxRef ref;
-    mcb_ctx* ctx = nullptr;
-    int32_t ngenes = 0;
-    int64_t ncells = 0, nnz = 0;
-    const int64_t* p = nullptr; const int32_t* i = nullptr; const uint32_t* x = nullptr;   // device views
-    DevBuf<int64_t> own_p; DevBuf<int32_t> own_i; DevBuf<uint32_t> own_x; DevBuf<uint8_t> kept;
-};
+// Host CSC -> device (pinned-ring staging with narrowing, staging.cu) + structure validation on the device.
+// p holds absolute offsets into i / x (p[0] is the first entry of this column range).
+mcb_csc* mcb::csc_upload_impl(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* p, const int32_t* i, const double* x)
+{
+    MCB_CHECK(ngenes >= 0 && ncells >= 0, "mcb_csc_upload: negative dimension");
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const int64_t nnz = p[ncells] - p[0];
+    MCB_CHECK(p[0] >= 0 && nnz >= 0, "MC-ERR: mcb_csc_upload: malformed column pointer");
+    MCB_CHECK(nnz == 0 || (i && x), "mcb_csc_upload: null index/value array");
+    std::unique_ptr<mcb_csc> m(new mcb_csc());
+    m->ref.set(ctx); m->ctx = ctx; m->ngenes = ngenes; m->ncells = ncells; m->nnz = nnz;
+    m->own_p.alloc(ctx, (size_t)ncells + 1);
+    m->own_i.alloc(ctx, (size_t)nnz);
+    m->own_x.alloc(ctx, (size_t)nnz);
+    DevBuf<int32_t> flags(ctx, 1);
+    flags.zero();
+    {
+        StageTimer t(ctx, "h2d_csc");
+        staged_upload_csc(ctx, ngenes, ncells, p, i, x, m->own_p.p, m->own_i.p, m->own_x.p);
+    }
+    // a malformed matrix would send the feature / statistics kernels out of bounds: check the structure once, here
+    launch_csc_validate(ctx, ngenes, ncells, nnz, m->own_p.p, m->own_i.p, flags.p);
+    int32_t hf = 0;
+    MCB_CUDA(cudaMemcpyAsync(&hf, flags.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MCB_CHECK(!(hf & 1), "MC-ERR: mcb_csc_upload: column pointers must be non-decreasing and end at nnz");
+    MCB_CHECK(!(hf & 2), "MC-ERR: mcb_csc_upload: gene row index out of range (is ngenes smaller than max(i) + 1?)");
+    MCB_CHECK(!(hf & 4), "MC-ERR: mcb_csc_upload: row indices must be strictly ascending within a column");
+    m->p = m->own_p.p; m->i = m->own_i.p; m->x = m->own_x.p;
+    return m.release();
+}
 
 extern "C" int mcb_csc_upload(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* p, const int32_t* i,
                               const double* x, mcb_csc** out)
 {
     MCB_API_BEGIN
     MCB_CHECK(ctx && p && out, "mcb_csc_upload: null argument");
-    MCB_CHECK(ngenes >= 0 && ncells >= 0, "mcb_csc_upload: negative dimension");
-    MCB_CUDA(cudaSetDevice(ctx->device));
-    const int64_t nnz = p[ncells];
-    MCB_CHECK(p[0] == 0 && nnz >= 0, "mcb_csc_upload: malformed column pointer");
-    MCB_CHECK(nnz == 0 || (i && x), "mcb_csc_upload: null index/value array");
-    std::unique_ptr<mcb_csc> m(new mcb_csc());
-    m->ref.set(ctx); m->ctx = ctx; m->ngenes = ngenes; m->ncells = ncells; m->nnz = nnz;
-    StageTimer t(ctx, "h2d_csc");
-    m->own_p.alloc(ctx, (size_t)ncells + 1);
-    m->own_i.alloc(ctx, (size_t)nnz);
-    m->own_x.alloc(ctx, (size_t)nnz);
-    MCB_CUDA(cudaMemcpyAsync(m->own_p.p, p, sizeof(int64_t) * ((size_t)ncells + 1), cudaMemcpyHostToDevice, ctx->stream));
-    if (nnz) {
-        DevBuf<double> xd(ctx, (size_t)nnz);
-        MCB_CUDA(cudaMemcpyAsync(m->own_i.p, i, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
-        MCB_CUDA(cudaMemcpyAsync(xd.p, x, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, ctx->stream));
-        launch_convert_x(ctx, xd.p, m->own_x.p, nnz);
-    }
-    m->p = m->own_p.p; m->i = m->own_i.p; m->x = m->own_x.p;
-    *out = m.release();
+    MCB_CHECK(ncells < 0 || p[0] == 0, "MC-ERR: mcb_csc_upload: malformed column pointer (p[0] must be 0)");
+    *out = csc_upload_impl(ctx, ngenes, ncells, p, i, x);
+    MCB_API_END
+}
+// the cell range [cell0, cell0 + ncells) of a larger host matrix: p points at p_full[cell0] (absolute offsets), i and x
+// are the full arrays.  What each rank of a multi-GPU build uploads.
+extern "C" int mcb_csc_upload_range(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* p, const int32_t* i,
+                                    const double* x, mcb_csc** out)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && p && out, "mcb_csc_upload_range: null argument");
+    *out = csc_upload_impl(ctx, ngenes, ncells, p, i, x);
     MCB_API_END
 }
 extern "C" int mcb_csc_wrap_device(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* dev_p,
@@ -286,11 +310,8 @@ extern "C" int mcb_csc_col_sums(mcb_ctx* ctx, const mcb_csc* m, int64_t* host_to
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
     MCB_API_END
 }
-extern "C" int mcb_csc_downsample(mcb_ctx* ctx, const mcb_csc* m, double n, uint64_t seed, int add_non_dsamp,
-                                  mcb_csc** out)
+static mcb_csc* csc_downsample_impl(mcb_ctx* ctx, const mcb_csc* m, double n, uint64_t seed, int add_non_dsamp, int64_t cell_base)
 {
-    MCB_API_BEGIN
-    MCB_CHECK(ctx && m && out, "mcb_csc_downsample: null argument");
     MCB_CHECK(n >= 1.0, "MC-ERR: downsample depth must be >= 1");
     MCB_CUDA(cudaSetDevice(ctx->device));
     std::unique_ptr<mcb_csc> d(new mcb_csc());
@@ -298,10 +319,47 @@ extern "C" int mcb_csc_downsample(mcb_ctx* ctx, const mcb_csc* m, double n, uint
     d->p = m->p; d->i = m->i;                      // shares structure with the input (caller keeps it alive)
     d->own_x.alloc(ctx, (size_t)m->nnz);
     d->kept.alloc(ctx, (size_t)m->ncells);
-    { StageTimer t(ctx, "downsample"); launch_downsample(ctx, m->ncells, m->p, m->x, n, seed, add_non_dsamp, d->own_x.p, d->kept.p); }
+    { StageTimer t(ctx, "downsample"); launch_downsample(ctx, m->ncells, m->p, m->x, n, seed, add_non_dsamp, d->own_x.p, d->kept.p, cell_base); }
     d->x = d->own_x.p;
-    *out = d.release();
+    return d.release();
+}
+extern "C" int mcb_csc_downsample(mcb_ctx* ctx, const mcb_csc* m, double n, uint64_t seed, int add_non_dsamp,
+                                  mcb_csc** out)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && m && out, "mcb_csc_downsample: null argument");
+    *out = csc_downsample_impl(ctx, m, n, seed, add_non_dsamp, 0);
     MCB_API_END
+}
+// gset_get_feat_mat(downsamp = T, add_non_dsamp = T) on a cell shard (R/gset.r:173-187): the depth rule
+// (R/scmat.r:399-407) needs the totals of ALL cells, so the shards' column sums are gathered over the communicator and
+// every rank derives the same depth; the Philox keys name cells by their index in the whole matrix.
+mcb_csc* mcb::csc_downsample_auto(mcb_ctx* ctx, mcb_comm* comm, const mcb_csc* m, int64_t cell_base, uint64_t seed, double* depth_out)
+{
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const bool multi = comm && comm->nranks > 1;
+    int64_t n_all = m->ncells;
+    std::vector<int64_t> range;
+    if (multi) {
+        const int64_t mine[2] = {cell_base, m->ncells};
+        range = comm_allgather_i64v(comm, mine, 2);
+        n_all = 0;
+        for (int r = 0; r < comm->nranks; ++r) n_all = std::max(n_all, range[2 * r] + range[2 * r + 1]);
+    }
+    DevBuf<int64_t> tot(ctx, (size_t)std::max<int64_t>(n_all, 1));
+    { StageTimer t(ctx, "col_sums"); launch_col_sums(ctx, m->ncells, m->p, m->x, tot.p + (multi ? cell_base : 0)); }
+    if (multi) {
+        std::vector<size_t> offs((size_t)comm->nranks), cnts((size_t)comm->nranks);
+        for (int r = 0; r < comm->nranks; ++r) { offs[r] = (size_t)range[2 * r] * 8; cnts[r] = (size_t)range[2 * r + 1] * 8; }
+        comm_allgatherv_inplace(comm, tot.p, offs.data(), cnts.data());
+    }
+    std::vector<int64_t> htot((size_t)n_all);
+    if (n_all) MCB_CUDA(cudaMemcpyAsync(htot.data(), tot.p, sizeof(int64_t) * (size_t)n_all, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    double depth = 0.0;
+    if (mcb_downsamp_depth(htot.data(), n_all, &depth)) throw Error(1, mcb_last_error());
+    if (depth_out) *depth_out = depth;
+    return csc_downsample_impl(ctx, m, depth, seed, /*add_non_dsamp=*/1, multi ? cell_base : 0);
 }
 extern "C" int mcb_csc_download(mcb_ctx* ctx, const mcb_csc* m, double* host_x, uint8_t* host_kept)
 {
@@ -469,51 +527,29 @@ extern "C" int mcb_mc_gene_tapply(mcb_ctx* ctx, const mcb_csc* m, const int32_t*
 // balanced K-nn cell graph
 // ---------------------------------------------------------------------------------------------
 
-struct mcb_cgraph {
-    CtxRef ref;
-    mcb_ctx* ctx = nullptr;
-    int64_t ncells = 0; int32_t G = 0, Gpad = 0;
-    int64_t M = 0, Mpad = 0;
-    DevBuf<float> Zf;              // fp32 plane (CUDA-core kernels)
-    DevBuf<__half> Zh, Zl;         // fp16 hi / lo planes of z * 2^12 (tensor-core kernels)
-    DevBuf<int32_t> cell_of_row;
-    // knn
-    int32_t K = 0, k_expand = 0, Kc = 0, kc_out = 0, rank = 0, nranks = 1;
-    int64_t rows_per_rank = 0, row0 = 0, rows = 0;
-    DevBuf<int32_t> knn_col; DevBuf<float> knn_cor;
-    int64_t n_fallback = 0, n_candidates = 0; int32_t cap = 0, n_sample = 0;
-    double expect_per_row = 0.0; int exchange = 0;
-    DevBuf<float> thr_all;                               // filter thresholds, [nranks * rows_per_rank]
-    DevBuf<uint64_t> cand; DevBuf<uint32_t> cnt;         // per-row candidate lists of the owned rows
-    DevBuf<uint4> pool_records; DevBuf<uint32_t> pool_fill, pool_ctl; uint32_t pool_chunks = 0;
-    DevBuf<uint4> send, recv; std::vector<int64_t> send_counts;   // symmetric multi-GPU record exchange
-    // balance
-    int32_t H = 0, rank_bits = 0, k_beta = 0;
-    DevBuf<uint32_t> sym; DevBuf<uint64_t> thr_in;
-    DevBuf<int32_t> out_deg, out_dst, out_s;
-    int64_t n_edges = 0;
-    DevBuf<int32_t> e_src, e_dst; DevBuf<double> e_w;
-};
-
-static void alloc_planes(mcb_cgraph* g, int64_t M)
+static void alloc_planes(mcb_cgraph* g, int64_t M, bool with_f32)
 {
     mcb_ctx* ctx = g->ctx;
     const size_t n = (size_t)g->Mpad * g->Gpad;
-    g->Zf.alloc(ctx, n); g->Zh.alloc(ctx, n); g->Zl.alloc(ctx, n);
+    if (with_f32) g->Zf.alloc(ctx, n);
+    g->Zh.alloc(ctx, n); g->Zl.alloc(ctx, n);
     g->cell_of_row.alloc(ctx, (size_t)std::max<int64_t>(M, 1));
     if (g->Mpad > M) {     // zero the padding rows
         const size_t off = (size_t)M * g->Gpad, cnt = (size_t)(g->Mpad - M) * g->Gpad;
-        MCB_CUDA(cudaMemsetAsync(g->Zf.p + off, 0, cnt * sizeof(float), ctx->stream));
+        if (with_f32) MCB_CUDA(cudaMemsetAsync(g->Zf.p + off, 0, cnt * sizeof(float), ctx->stream));
         MCB_CUDA(cudaMemsetAsync(g->Zh.p + off, 0, cnt * sizeof(__half), ctx->stream));
         MCB_CUDA(cudaMemsetAsync(g->Zl.p + off, 0, cnt * sizeof(__half), ctx->stream));
     }
 }
 
-extern "C" int mcb_cgraph_create(mcb_ctx* ctx, const mcb_csc* m, const int32_t* feat_rows, int32_t G, double k_nonz,
-                                 mcb_cgraph** out)
+// A3 + A4.  `m` holds this rank's cells (all cells when comm is null); cell_base = index of its first cell in the whole
+// matrix.  Every rank builds the rows of its own valid cells directly at their place in the full planes and the rest
+// arrives by an in-place all-gather of variable-size blocks -- the fp16 planes only: the fp32 plane
+// serves the CUDA-core validation kernels and exists on single-rank builds alone.  Ranks must hold ascending,
+// contiguous cell ranges in rank order, so that valid-row order == cell order.
+mcb_cgraph* mcb::cgraph_features_csc(mcb_ctx* ctx, mcb_comm* comm, const mcb_csc* m, int64_t cell_base, const int32_t* feat_rows,
+                                     int32_t G, double k_nonz)
 {
-    MCB_API_BEGIN
-    MCB_CHECK(ctx && m && feat_rows && out, "mcb_cgraph_create: null argument");
     MCB_CHECK(G >= 2, "MC-ERR: need at least 2 feature genes");
     MCB_CUDA(cudaSetDevice(ctx->device));
     std::vector<int32_t> fmap((size_t)m->ngenes, -1);
@@ -522,29 +558,55 @@ extern "C" int mcb_cgraph_create(mcb_ctx* ctx, const mcb_csc* m, const int32_t* 
         MCB_CHECK(fmap[feat_rows[g]] < 0, "MC-ERR: duplicate feature gene row");
         fmap[feat_rows[g]] = g;
     }
+    const bool multi = comm && comm->nranks > 1;
     std::unique_ptr<mcb_cgraph> g(new mcb_cgraph());
-    g->ref.set(ctx); g->ctx = ctx; g->ncells = m->ncells; g->G = G; g->Gpad = (int32_t)round_up(G, 64);
-    DevBuf<int32_t> d_fmap(ctx, fmap.size());
+    g->ref.set(ctx); g->ctx = ctx; g->comm = multi ? comm : nullptr; g->ncells = m->ncells; g->G = G; g->Gpad = (int32_t)round_up(G, 64);
+    const size_t nc1 = (size_t)std::max<int64_t>(m->ncells, 1);
+    DevBuf<int32_t> d_fmap(ctx, std::max<size_t>(fmap.size(), 1));
     MCB_CUDA(cudaMemcpyAsync(d_fmap.p, fmap.data(), fmap.size() * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    DevBuf<double> mu(ctx, (size_t)m->ncells), inv(ctx, (size_t)m->ncells);
-    DevBuf<int32_t> valid(ctx, (size_t)m->ncells), rowpos(ctx, (size_t)m->ncells), total(ctx, 1);
+    DevBuf<double> mu(ctx, nc1), inv(ctx, nc1);
+    DevBuf<int32_t> valid(ctx, nc1), rowpos(ctx, nc1), total(ctx, 1);
+    total.zero();
     {
         StageTimer t(ctx, "feat_stats", 2);
         launch_feat_stats(ctx, m->ncells, m->p, m->i, m->x, d_fmap.p, G, k_nonz, mu.p, inv.p, valid.p);
-        launch_exclusive_scan_i32(ctx, valid.p, rowpos.p, m->ncells, total.p);
+        if (m->ncells) launch_exclusive_scan_i32(ctx, valid.p, rowpos.p, m->ncells, total.p);
     }
-    int32_t M = 0;
-    MCB_CUDA(cudaMemcpyAsync(&M, total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    int32_t Mloc = 0;
+    MCB_CUDA(cudaMemcpyAsync(&Mloc, total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::vector<int64_t> counts(1, Mloc);
+    if (multi) counts = comm_allgather_i64(comm, Mloc);
+    int64_t M = 0, before = 0;
+    for (size_t r = 0; r < counts.size(); ++r) { if (multi && (int)r < comm->rank) before += counts[r]; M += counts[r]; }
     g->M = M; g->Mpad = round_up(std::max<int64_t>(M, 1), 256);
-    alloc_planes(g.get(), M);
+    alloc_planes(g.get(), M, !multi);
     {
         StageTimer t(ctx, "feat_rows");
+        const size_t off = (size_t)before * g->Gpad;
         launch_feat_rows(ctx, m->ncells, m->p, m->i, m->x, d_fmap.p, G, g->Gpad, k_nonz, mu.p, inv.p, valid.p, rowpos.p,
-                         g->Zf.p, g->Zh.p, g->Zl.p, g->cell_of_row.p);
+                         multi ? nullptr : g->Zf.p, g->Zh.p + off, g->Zl.p + off, g->cell_of_row.p + before, multi ? cell_base : 0);
     }
-    MCB_CUDA(cudaStreamSynchronize(ctx->stream));     // temporaries die here
-    *out = g.release();
+    if (multi) {
+        StageTimer t(ctx, "allgather_features", 0);
+        std::vector<size_t> offs(counts.size()), cnts(counts.size());
+        size_t run = 0;
+        for (size_t r = 0; r < counts.size(); ++r) { offs[r] = run * g->Gpad * sizeof(__half); cnts[r] = (size_t)counts[r] * g->Gpad * sizeof(__half); run += (size_t)counts[r]; }
+        comm_allgatherv_inplace(comm, g->Zh.p, offs.data(), cnts.data());
+        comm_allgatherv_inplace(comm, g->Zl.p, offs.data(), cnts.data());
+        run = 0;
+        for (size_t r = 0; r < counts.size(); ++r) { offs[r] = run * sizeof(int32_t); cnts[r] = (size_t)counts[r] * sizeof(int32_t); run += (size_t)counts[r]; }
+        comm_allgatherv_inplace(comm, g->cell_of_row.p, offs.data(), cnts.data());
+    }
+    return g.release();          // temporaries are released in stream order (the block cache reuses on this stream only)
+}
+
+extern "C" int mcb_cgraph_create(mcb_ctx* ctx, const mcb_csc* m, const int32_t* feat_rows, int32_t G, double k_nonz,
+                                 mcb_cgraph** out)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && m && feat_rows && out, "mcb_cgraph_create: null argument");
+    *out = cgraph_features_csc(ctx, nullptr, m, 0, feat_rows, G, k_nonz);
     MCB_API_END
 }
 // tgs_cor_graph(x = feat, ...) entry (reference R/utils.r:115): x is the dense genes x cells matrix
@@ -573,7 +635,7 @@ extern "C" int mcb_cgraph_create_dense(mcb_ctx* ctx, const double* x, int32_t G,
     MCB_CUDA(cudaMemcpyAsync(&M, total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
     g->M = M; g->Mpad = round_up(std::max<int64_t>(M, 1), 256);
-    alloc_planes(g.get(), M);
+    alloc_planes(g.get(), M, true);
     {
         StageTimer t(ctx, "feat_rows");
         launch_dense_rows(ctx, ncells, dx.p, G, g->Gpad, mu.p, inv.p, valid.p, rowpos.p, g->Zf.p, g->Zh.p, g->Zl.p, g->cell_of_row.p);
@@ -649,7 +711,8 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
     MCB_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
     MCB_CHECK((int64_t)K * k_expand <= 4096, "MC-ERR: K * k_expand above 4096 is not supported");
     MCB_CHECK(g->M >= 2, "MC-ERR: fewer than 2 cells with non-constant features");
-    MCB_CHECK(g->Zf.p, "mcb_cgraph_knn: the feature planes were released (call before mcb_cgraph_mutual)");
+    MCB_CHECK(g->Zh.p, "mcb_cgraph_knn: the feature planes were released (call before mcb_cgraph_mutual)");
+    MCB_CHECK(g->ctx->gemm_impl != 1 || g->Zf.p, "gemm_impl = 1 (CUDA-core validation kernels) is a single-rank path");
     mcb_ctx* ctx = g->ctx;
     const int64_t M = g->M;
     const int32_t Gpad = g->Gpad;
@@ -663,11 +726,8 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
     g->knn_col.alloc(ctx, (size_t)nranks * g->rows_per_rank * Kc);
     g->knn_cor.alloc(ctx, (size_t)std::max<int64_t>(rows, 1) * Kc);
     g->thr_all.alloc(ctx, (size_t)nranks * g->rows_per_rank);
-    {   // rows past M (padding of the last rank's block) never pass
-        std::vector<float> inf((size_t)nranks * g->rows_per_rank, INFINITY);
-        MCB_CUDA(cudaMemcpyAsync(g->thr_all.p, inf.data(), inf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
+    // rows past M (padding of the last rank's block) never pass: +inf
+    launch_fill_u32(ctx, g->thr_all.p, (int64_t)nranks * g->rows_per_rank, 0x7f800000u);
     // ---- sampling pass: per-row filter threshold from a random column sample -----------------
     int64_t S = std::min<int64_t>(262144, round_up(ceil_div(128 * M, kc_out), 256));     // ~128 sampled columns above the true cut
     if (S >= M) S = M;
@@ -679,10 +739,12 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
     g->cap = cap; g->n_sample = (int32_t)S;
     g->expect_per_row = r_sel > S ? (double)M : (double)r_sel * (double)M / (double)S;
     if (rows == 0) return;
-    std::vector<int32_t> samp((size_t)Spad, -1);
-    {
+    // the sampled columns (fixed seed: the sample only steers the filter, never the result) are cached on the device
+    // per (M, S): a repeated build of the same shape draws nothing on the host
+    if (ctx->samp_M != M || ctx->samp_S != S || !ctx->samp_dev) {
+        std::vector<int32_t> samp((size_t)Spad, -1);
         if (S >= M) { for (int64_t q = 0; q < M; ++q) samp[q] = (int32_t)q; }
-        else {   // partial Fisher-Yates with a fixed seed: the sample only steers the filter, not the result
+        else {   // partial Fisher-Yates
             std::vector<int32_t> perm((size_t)M);
             for (int64_t q = 0; q < M; ++q) perm[q] = (int32_t)q;
             std::mt19937_64 gen(0x6d63623230300aull);
@@ -692,9 +754,18 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
                 samp[q] = perm[q];
             }
         }
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));            // nothing queued may still read the old sample
+        if (ctx->samp_bytes < sizeof(int32_t) * (size_t)Spad) {
+            if (ctx->samp_dev) MCB_CUDA(cudaFree(ctx->samp_dev));
+            ctx->samp_dev = nullptr; ctx->samp_bytes = 0; ctx->samp_M = ctx->samp_S = 0;
+            MCB_CUDA(cudaMalloc(&ctx->samp_dev, sizeof(int32_t) * (size_t)Spad));
+            ctx->samp_bytes = sizeof(int32_t) * (size_t)Spad;
+        }
+        MCB_CUDA(cudaMemcpyAsync(ctx->samp_dev, samp.data(), sizeof(int32_t) * (size_t)Spad, cudaMemcpyHostToDevice, ctx->stream));
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->samp_M = M; ctx->samp_S = S;
     }
-    DevBuf<int32_t> d_samp(ctx, (size_t)Spad);
-    MCB_CUDA(cudaMemcpyAsync(d_samp.p, samp.data(), sizeof(int32_t) * (size_t)Spad, cudaMemcpyHostToDevice, ctx->stream));
+    struct { int32_t* p; } d_samp{(int32_t*)ctx->samp_dev};
     DevBuf<__half> Zs(ctx, ctx->gemm_impl != 1 ? (size_t)Spad * Gpad : 0);
     DevBuf<float> Zsf(ctx, ctx->gemm_impl != 1 ? 0 : (size_t)Spad * Gpad);
     float* thr = g->thr_all.p + row0;
@@ -725,7 +796,7 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
             else launch_sample_threshold(ctx, Cs.p, Spad, nr, (int32_t)S, r_sel, eps, thr + c0);
         }
     }
-    MCB_CUDA(cudaStreamSynchronize(ctx->stream));        // samp / temporaries die here
+    // temporaries are released in stream order: no host synchronisation here
 }
 
 static void knn_filter(mcb_cgraph* g, int exchange)
@@ -785,8 +856,7 @@ static void knn_filter(mcb_cgraph* g, int exchange)
         MCB_CUDA(cudaMemcpyAsync(base.p, hb.data(), sizeof(uint64_t) * (size_t)nranks, cudaMemcpyHostToDevice, ctx->stream));
         g->send.alloc(ctx, (size_t)std::max<uint64_t>(tot, 1));
         launch_partition_records(ctx, pool, g->rows_per_rank, nranks, base.p, cur.p, g->send.p);
-        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-        g->pool_records.release();
+        g->pool_records.release();              // stream ordered
     }
 }
 
@@ -795,7 +865,7 @@ static void knn_finish(mcb_cgraph* g, int64_t n_recv)
     mcb_ctx* ctx = g->ctx;
     const int64_t M = g->M, rows = g->rows, row0 = g->row0;
     const int32_t Gpad = g->Gpad, cap = g->cap, Kc = g->Kc, kc_out = g->kc_out;
-    if (rows == 0) { MCB_CUDA(cudaStreamSynchronize(ctx->stream)); return; }
+    if (rows == 0) return;
     if (ctx->gemm_impl != 1) {
         StageTimer t(ctx, "cand_scatter");
         if (g->exchange) launch_scatter_flat(ctx, g->recv.p, n_recv, row0, g->cand.p, g->cnt.p, cap);
@@ -812,9 +882,14 @@ static void knn_finish(mcb_cgraph* g, int64_t n_recv)
         launch_topk_rows(ctx, g->cand.p, g->cnt.p, cap, row0, rows, kc_out, Kc, own_col, g->knn_cor.p, fail.p);
     }
     launch_compact_flags(ctx, fail.p, rows, fail_list.p, n_fail_d.p);
+    DevBuf<uint64_t> cand_total(ctx, 1);
+    launch_sum_u32(ctx, g->cnt.p, rows, cand_total.p);              // statistics for DESIGN / bench: how selective the filter was
     int32_t n_fail = 0;
+    uint64_t h_total = 0;
     MCB_CUDA(cudaMemcpyAsync(&n_fail, n_fail_d.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaMemcpyAsync(&h_total, cand_total.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    g->n_candidates = (int64_t)h_total;
     g->n_fallback = n_fail;
     if (n_fail > 0) {
         // rows whose candidate count missed [kc_out-1, cap]: their full correlation rows through the 3-pass
@@ -846,25 +921,45 @@ static void knn_finish(mcb_cgraph* g, int64_t n_recv)
             MCB_CUDA(cudaStreamSynchronize(ctx->stream));      // gl is reused
         }
     }
-    {   // statistics for DESIGN / bench: how selective the filter was
-        std::vector<uint32_t> hc((size_t)rows);
-        MCB_CUDA(cudaMemcpyAsync(hc.data(), g->cnt.p, sizeof(uint32_t) * (size_t)rows, cudaMemcpyDeviceToHost, ctx->stream));
-        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-        int64_t tot = 0;
-        for (auto v : hc) tot += v;
-        g->n_candidates = tot;
-    }
     g->cand.release(); g->cnt.release(); g->pool_records.release(); g->pool_fill.release(); g->send.release(); g->recv.release();
+}
+
+// A5 for this rank's rows.  With a communicator (rank-collective build) the exchanges of the symmetric schedule run
+// here, on the context's stream: all-gather of the filter thresholds, all-to-all of the candidate records (sizes
+// through one small all-gather), all-gather of the ranked kNN columns.
+void mcb::cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks)
+{
+    MCB_CUDA(cudaSetDevice(g->ctx->device));
+    mcb_comm* comm = g->comm;
+    if (comm) MCB_CHECK(comm->rank == rank && comm->nranks == nranks, "mcb_cgraph_knn: rank / nranks differ from the communicator's");
+    knn_begin(g, K, k_expand, rank, nranks);
+    if (!comm) {
+        knn_filter(g, 0);
+        knn_finish(g, 0);
+        return;
+    }
+    mcb_ctx* ctx = g->ctx;
+    { StageTimer t(ctx, "allgather_thresholds", 0); comm_allgather_inplace(comm, g->thr_all.p, (size_t)g->rows_per_rank * sizeof(float)); }
+    knn_filter(g, 1);
+    const std::vector<int64_t> all = comm_allgather_i64v(comm, g->send_counts.data(), nranks);      // [sender][owner]
+    std::vector<size_t> soff((size_t)nranks), scnt((size_t)nranks), roff((size_t)nranks), rcnt((size_t)nranks);
+    size_t srun = 0, rrun = 0;
+    for (int r = 0; r < nranks; ++r) {
+        soff[r] = srun * sizeof(uint4); scnt[r] = (size_t)g->send_counts[r] * sizeof(uint4); srun += (size_t)g->send_counts[r];
+        const size_t from_r = (size_t)all[(size_t)r * nranks + rank];
+        roff[r] = rrun * sizeof(uint4); rcnt[r] = from_r * sizeof(uint4); rrun += from_r;
+    }
+    g->recv.alloc(ctx, std::max<size_t>(rrun, 1));
+    { StageTimer t(ctx, "alltoall_records", 0); comm_alltoallv(comm, g->send.p, soff.data(), scnt.data(), g->recv.p, roff.data(), rcnt.data()); }
+    knn_finish(g, (int64_t)rrun);
+    { StageTimer t(ctx, "allgather_knn", 0); comm_allgather_inplace(comm, g->knn_col.p, (size_t)g->rows_per_rank * g->Kc * sizeof(int32_t)); }
 }
 
 extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks)
 {
     MCB_API_BEGIN
     MCB_CHECK(g, "null argument");
-    MCB_CUDA(cudaSetDevice(g->ctx->device));
-    knn_begin(g, K, k_expand, rank, nranks);
-    knn_filter(g, 0);
-    knn_finish(g, 0);
+    cgraph_knn(g, K, k_expand, rank, nranks);
     MCB_API_END
 }
 // ---- staged form for the symmetric multi-GPU schedule (metacell_b200/dist.py shows the sequence) ------------------
@@ -948,10 +1043,10 @@ extern "C" int mcb_cgraph_knn_stats(mcb_cgraph* g, int64_t* n_fallback_rows, int
 
 static int ilog2_ceil(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) ++l; return l; }
 
-extern "C" int mcb_cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
+// A6 step 1 for the owned rows; with a communicator the in-degree cuts of every row are all-gathered here
+void mcb::cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
 {
-    MCB_API_BEGIN
-    MCB_CHECK(g && g->knn_col.p, "mcb_cgraph_mutual: run mcb_cgraph_knn first");
+    MCB_CHECK(g->knn_col.p, "mcb_cgraph_mutual: run mcb_cgraph_knn first");
     MCB_CHECK(k_beta >= 1, "MC-ERR: k_beta must be >= 1");
     mcb_ctx* ctx = g->ctx;
     MCB_CUDA(cudaSetDevice(ctx->device));
@@ -976,7 +1071,14 @@ extern "C" int mcb_cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
         launch_mutual(ctx, g->knn_col.p, table.p, g->row0, g->rows, Kc, H, g->rank_bits,
                       (int64_t)g->K * g->K * g->k_expand, ctx->thresh_strict, ctx->keep_self, g->K * k_beta, g->sym.p, g->thr_in.p);
     }
-    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (g->comm) { StageTimer t(ctx, "allgather_cuts", 0); comm_allgather_inplace(g->comm, g->thr_in.p, (size_t)g->rows_per_rank * sizeof(uint64_t)); }
+    // the table is released in stream order
+}
+extern "C" int mcb_cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g, "null argument");
+    cgraph_mutual(g, k_beta);
     MCB_API_END
 }
 extern "C" int mcb_cgraph_thr_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank)
@@ -987,10 +1089,9 @@ extern "C" int mcb_cgraph_thr_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* row
     if (rows_per_rank) *rows_per_rank = g->rows_per_rank;
     MCB_API_END
 }
-extern "C" int mcb_cgraph_prune(mcb_cgraph* g, int64_t* n_edges)
+int64_t mcb::cgraph_prune(mcb_cgraph* g)
 {
-    MCB_API_BEGIN
-    MCB_CHECK(g && g->sym.p, "mcb_cgraph_prune: run mcb_cgraph_mutual first");
+    MCB_CHECK(g->sym.p, "mcb_cgraph_prune: run mcb_cgraph_mutual first");
     mcb_ctx* ctx = g->ctx;
     MCB_CUDA(cudaSetDevice(ctx->device));
     const int64_t rows = g->rows;
@@ -1020,24 +1121,43 @@ extern "C" int mcb_cgraph_prune(mcb_cgraph* g, int64_t* n_edges)
         StageTimer t(ctx, "edge_emit");
         launch_emit_edges(ctx, g->out_deg.p, g->out_dst.p, offs.p, g->cell_of_row.p, g->row0, rows, K, g->e_src.p, g->e_dst.p, g->e_w.p);
     }
-    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ne;
+}
+extern "C" int mcb_cgraph_prune(mcb_cgraph* g, int64_t* n_edges)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g, "null argument");
+    const int64_t ne = cgraph_prune(g);
+    MCB_CUDA(cudaStreamSynchronize(g->ctx->stream));
     if (n_edges) *n_edges = ne;
     MCB_API_END
+}
+// The edge table of the owned rows -> host.  The device sends the targets and the out-degrees; the host threads of the
+// staging ring rebuild mc1 and w = 1 - place/K while the targets are in flight (staging.cu).
+void mcb::cgraph_edges_to_host(mcb_cgraph* g, int32_t* host_src, int32_t* host_dst, double* host_w)
+{
+    MCB_CHECK(g->e_src.p, "mcb_cgraph_edges: run mcb_cgraph_prune first");
+    mcb_ctx* ctx = g->ctx;
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    StageTimer t(ctx, "d2h_edges", 0);
+    staged_download_edges(ctx, g->rows, g->K, g->n_edges, g->out_deg.p, g->cell_of_row.p + g->row0, g->e_dst.p, host_src, host_dst, host_w);
 }
 extern "C" int mcb_cgraph_edges(mcb_cgraph* g, int32_t* host_src, int32_t* host_dst, double* host_w)
 {
     MCB_API_BEGIN
-    MCB_CHECK(g && g->e_src.p, "mcb_cgraph_edges: run mcb_cgraph_prune first");
-    mcb_ctx* ctx = g->ctx;
-    MCB_CUDA(cudaSetDevice(ctx->device));
-    const size_t ne = (size_t)g->n_edges;
-    StageTimer t(ctx, "d2h_edges");
-    if (ne) {
-        if (host_src) MCB_CUDA(cudaMemcpyAsync(host_src, g->e_src.p, ne * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        if (host_dst) MCB_CUDA(cudaMemcpyAsync(host_dst, g->e_dst.p, ne * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        if (host_w) MCB_CUDA(cudaMemcpyAsync(host_w, g->e_w.p, ne * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    MCB_CHECK(g, "null argument");
+    cgraph_edges_to_host(g, host_src, host_dst, host_w);
+    MCB_API_END
+}
+// the same table left on the device (e.g. for a caller that keeps working there): pointers valid until the handle dies
+extern "C" int mcb_cgraph_edges_device(mcb_cgraph* g, int64_t* n_edges, const int32_t** dev_src, const int32_t** dev_dst, const double** dev_w)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(g && g->e_src.p, "mcb_cgraph_edges_device: run mcb_cgraph_prune first");
+    if (n_edges) *n_edges = g->n_edges;
+    if (dev_src) *dev_src = g->e_src.p;
+    if (dev_dst) *dev_dst = g->e_dst.p;
+    if (dev_w) *dev_w = g->e_w.p;
     MCB_API_END
 }
 
@@ -1122,72 +1242,197 @@ extern "C" int mcb_cor_knn_xy(mcb_ctx* ctx, const double* x, int64_t nx, const d
     MCB_API_END
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// the whole body of mcell_add_cgraph_from_mat_bknn (R/cgraph_knn.r:10-25) for ONE rank: upload of the rank's cell range,
+// [depth rule + downsample + add-back], features, kNN, balancing.  comm == null: the only rank.
+// ---------------------------------------------------------------------------------------------------------------
+mcb_cgraph* mcb::bknn_rank(mcb_ctx* ctx, mcb_comm* comm, const BknnJob& j)
+{
+    MCB_CHECK(j.p && j.feat_rows, "mcb_cgraph_bknn: null argument");
+    MCB_CHECK(j.cell0 >= 0 && j.cell0 <= j.cell1 && j.cell1 <= j.ncells, "mcb_cgraph_bknn: bad cell range");
+    std::unique_ptr<mcb_csc> m(csc_upload_impl(ctx, j.ngenes, j.cell1 - j.cell0, j.p + j.cell0, j.i, j.x));
+    return bknn_rank_uploaded(ctx, comm, j, m.get());
+}
+// the same with the rank's cell range already on the device (`m` is only read; the caller frees it after the return)
+mcb_cgraph* mcb::bknn_rank_uploaded(mcb_ctx* ctx, mcb_comm* comm, const BknnJob& j, const mcb_csc* m)
+{
+    const int rank = comm ? comm->rank : 0, nranks = comm ? comm->nranks : 1;
+    std::unique_ptr<mcb_csc> d;
+    const mcb_csc* use = m;
+    if (j.dsamp) { d.reset(csc_downsample_auto(ctx, comm, m, j.cell0, j.seed, nullptr)); use = d.get(); }
+    std::unique_ptr<mcb_cgraph, void (*)(mcb_cgraph*)> g(cgraph_features_csc(ctx, comm, use, j.cell0, j.feat_rows, j.G, j.k_nonz),
+                                                          [](mcb_cgraph* q) { mcb_cgraph_destroy(q); });
+    cgraph_knn(g.get(), j.K, j.k_expand, rank, nranks);
+    cgraph_mutual(g.get(), j.k_beta);
+    cgraph_prune(g.get());
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));       // the CSC handles die here
+    return g.release();
+}
+
+// one shot, single GPU, host in / host out: what mcell_add_cgraph_from_mat_bknn's body becomes
 extern "C" int mcb_cgraph_bknn(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* p, const int32_t* i,
                                const double* x, const int32_t* feat_rows, int32_t G, int32_t K, int32_t k_expand,
                                int32_t k_beta, double k_nonz, int dsamp, uint64_t seed, int64_t* n_edges,
                                int32_t** src, int32_t** dst, double** w, int64_t* n_valid_cells)
 {
-    mcb_csc* m = nullptr; mcb_csc* d = nullptr; mcb_cgraph* g = nullptr;
+    mcb_cgraph* g = nullptr;
     int32_t* hs = nullptr; int32_t* hd = nullptr; double* hw = nullptr;
     int rc = 0;
-    do {
-        if (!n_edges || !src || !dst || !w) { mcb::set_error("mcb_cgraph_bknn: null output"); rc = 1; break; }
-        if ((rc = mcb_csc_upload(ctx, ngenes, ncells, p, i, x, &m))) break;
-        const mcb_csc* use = m;
-        if (dsamp) {
-            std::vector<int64_t> tot((size_t)ncells);
-            if ((rc = mcb_csc_col_sums(ctx, m, tot.data()))) break;
-            double depth = 0.0;
-            if ((rc = mcb_downsamp_depth(tot.data(), ncells, &depth))) break;
-            if ((rc = mcb_csc_downsample(ctx, m, depth, seed, /*add_non_dsamp=*/1, &d))) break;
-            use = d;
-        }
-        if ((rc = mcb_cgraph_create(ctx, use, feat_rows, G, k_nonz, &g))) break;
-        if ((rc = mcb_cgraph_knn(g, K, k_expand, 0, 1))) break;
-        if ((rc = mcb_cgraph_mutual(g, k_beta))) break;
-        int64_t ne = 0;
-        if ((rc = mcb_cgraph_prune(g, &ne))) break;
+    try {
+        MCB_CHECK(ctx && n_edges && src && dst && w, "mcb_cgraph_bknn: null argument");
+        MCB_CHECK(p && p[0] == 0, "MC-ERR: mcb_cgraph_bknn: malformed column pointer");
+        BknnJob j{ngenes, ncells, 0, ncells, p, i, x, feat_rows, G, K, k_expand, k_beta, k_nonz, dsamp, seed};
+        g = bknn_rank(ctx, nullptr, j);
+        const int64_t ne = g->n_edges;
         hs = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
         hd = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
         hw = (double*)malloc(sizeof(double) * (size_t)std::max<int64_t>(ne, 1));
-        if (!hs || !hd || !hw) { mcb::set_error("host out of memory"); rc = 3; break; }
-        if ((rc = mcb_cgraph_edges(g, hs, hd, hw))) break;
+        if (!hs || !hd || !hw) throw std::bad_alloc();
+        cgraph_edges_to_host(g, hs, hd, hw);
         *n_edges = ne; *src = hs; *dst = hd; *w = hw;
         if (n_valid_cells) *n_valid_cells = g->M;
         hs = nullptr; hd = nullptr; hw = nullptr;
-    } while (0);
+    }
+    catch (const mcb::Error& e) { mcb::set_error(e.what()); rc = e.code; }
+    catch (const std::bad_alloc&) { mcb::set_error("host out of memory"); rc = 3; }
+    catch (const std::exception& e) { mcb::set_error(e.what()); rc = 4; }
+    catch (...) { mcb::set_error("unknown error"); rc = 5; }
     free(hs); free(hd); free(hw);
     mcb_cgraph_destroy(g);
-    mcb_csc_free(d);
-    mcb_csc_free(m);
+    return rc;
+}
+
+// ---- rank-collective form: every rank of the communicator calls these with its own cell range ---------------------
+// `local` = this rank's cells [cell_base, cell_base + local->ncells) of the whole matrix (ranks hold ascending contiguous
+// ranges in rank order).  Runs A1..A7; on return this rank holds the edges of its share of the valid rows.
+extern "C" int mcb_cgraph_build_sharded(mcb_comm* comm, const mcb_csc* local, int64_t cell_base, const int32_t* feat_rows, int32_t G,
+                                        double k_nonz, int32_t K, int32_t k_expand, int32_t k_beta, int dsamp, uint64_t seed,
+                                        mcb_cgraph** out, int64_t* n_edges_local)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(comm && local && feat_rows && out, "mcb_cgraph_build_sharded: null argument");
+    MCB_CHECK(local->ctx == comm->ctx, "mcb_cgraph_build_sharded: matrix and communicator live on different contexts");
+    mcb_ctx* ctx = comm->ctx;
+    std::unique_ptr<mcb_csc> d;
+    const mcb_csc* use = local;
+    if (dsamp) { d.reset(csc_downsample_auto(ctx, comm, local, cell_base, seed, nullptr)); use = d.get(); }
+    std::unique_ptr<mcb_cgraph, void (*)(mcb_cgraph*)> g(cgraph_features_csc(ctx, comm, use, cell_base, feat_rows, G, k_nonz),
+                                                          [](mcb_cgraph* q) { mcb_cgraph_destroy(q); });
+    cgraph_knn(g.get(), K, k_expand, comm->rank, comm->nranks);
+    cgraph_mutual(g.get(), k_beta);
+    const int64_t ne = cgraph_prune(g.get());
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_edges_local) *n_edges_local = ne;
+    *out = g.release();
+    MCB_API_END
+}
+// every rank's edges on `root`'s host, in rank (= source) order.  Collective.  The compact form (targets + out-degrees +
+// source ids) travels over NVLink and PCIe; root's staging threads rebuild (mc1, mc2, w).  Outputs are library-allocated
+// on root (mcb_free) and null elsewhere; *n_edges_total is set on every rank.
+extern "C" int mcb_cgraph_gather_edges(mcb_comm* comm, mcb_cgraph* g, int32_t root, int64_t* n_edges_total, int32_t** src,
+                                       int32_t** dst, double** w)
+{
+    int32_t* hs = nullptr; int32_t* hd = nullptr; double* hw = nullptr;
+    int rc = 0;
+    try {
+        MCB_CHECK(comm && g && g->e_src.p, "mcb_cgraph_gather_edges: run the build first");
+        MCB_CHECK(root >= 0 && root < comm->nranks, "mcb_cgraph_gather_edges: bad root");
+        mcb_ctx* ctx = g->ctx;
+        MCB_CUDA(cudaSetDevice(ctx->device));
+        const int P = comm->nranks;
+        const int64_t mine[2] = {g->n_edges, g->rows};
+        const std::vector<int64_t> all = comm_allgather_i64v(comm, mine, 2);
+        int64_t ne = 0, nr = 0;
+        std::vector<size_t> eoff((size_t)P), ecnt((size_t)P), roff((size_t)P), rcnt((size_t)P);
+        for (int r = 0; r < P; ++r) {
+            eoff[r] = (size_t)ne * 4; ecnt[r] = (size_t)all[2 * r] * 4; ne += all[2 * r];
+            roff[r] = (size_t)nr * 4; rcnt[r] = (size_t)all[2 * r + 1] * 4; nr += all[2 * r + 1];
+        }
+        const bool is_root = comm->rank == root;
+        DevBuf<int32_t> dst_all(ctx, is_root ? (size_t)std::max<int64_t>(ne, 1) : 0), deg_all(ctx, is_root ? (size_t)std::max<int64_t>(nr, 1) : 0),
+            cell_all(ctx, is_root ? (size_t)std::max<int64_t>(nr, 1) : 0);
+        {
+            StageTimer t(ctx, "gather_edges", 0);
+            comm_gatherv(comm, g->e_dst.p, (size_t)g->n_edges * 4, dst_all.p, eoff.data(), ecnt.data(), root);
+            comm_gatherv(comm, g->out_deg.p, (size_t)g->rows * 4, deg_all.p, roff.data(), rcnt.data(), root);
+            comm_gatherv(comm, g->cell_of_row.p + g->row0, (size_t)g->rows * 4, cell_all.p, roff.data(), rcnt.data(), root);
+        }
+        if (n_edges_total) *n_edges_total = ne;
+        if (is_root) {
+            MCB_CHECK(src && dst && w, "mcb_cgraph_gather_edges: null output on root");
+            hs = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
+            hd = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
+            hw = (double*)malloc(sizeof(double) * (size_t)std::max<int64_t>(ne, 1));
+            if (!hs || !hd || !hw) throw std::bad_alloc();
+            StageTimer t(ctx, "d2h_edges", 0);
+            staged_download_edges(ctx, nr, g->K, ne, deg_all.p, cell_all.p, dst_all.p, hs, hd, hw);
+            *src = hs; *dst = hd; *w = hw;
+            hs = nullptr; hd = nullptr; hw = nullptr;
+        } else {
+            if (src) *src = nullptr;
+            if (dst) *dst = nullptr;
+            if (w) *w = nullptr;
+        }
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    catch (const mcb::Error& e) { mcb::set_error(e.what()); rc = e.code; }
+    catch (const std::bad_alloc&) { mcb::set_error("host out of memory"); rc = 3; }
+    catch (const std::exception& e) { mcb::set_error(e.what()); rc = 4; }
+    catch (...) { mcb::set_error("unknown error"); rc = 5; }
+    free(hs); free(hd); free(hw);
     return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
 // resampled co-clustering
 // ---------------------------------------------------------------------------------------------
-struct mcb_coclust {
-    CtxRef ref;
-    mcb_ctx* ctx = nullptr;
-    int32_t N = 0, n_local = 0, ncl_cap = 0;
-    DevBuf<uint32_t> cnt; DevBuf<int32_t> nsamp;
-    DevBuf<int32_t> mc, sweeps;
-    int64_t n_pairs = -1;
-    DevBuf<int32_t> p1, p2, pc;
+// the host's edge table -> device CSR (out and in, 16-bit fixed-point weights, packed node / edge descriptors) + endpoint
+// validation; shared by the resampled co-clustering and the single cover
+struct CoverCsr {
+    DevBuf<int32_t> src, dst; DevBuf<double> w;
+    DevBuf<int32_t> odeg, ideg, optr32, iptr32; DevBuf<int64_t> optr, iptr;
+    DevBuf<int32_t> odst, isrc, scratch; DevBuf<uint32_t> ow, iw; DevBuf<int2> oe, ie; DevBuf<int4> nd;
+    int32_t max_out = 0, max_in = 0;
 };
-
-extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst,
-                               const double* w, int32_t n_resamp, int32_t n_s, const int32_t* samples,
-                               const uint64_t* seeds, int32_t min_mc_size, double cooling, int32_t burn_in,
-                               int32_t max_sweeps, int32_t rank, int32_t nranks, mcb_coclust** out)
+static void cover_csr_build(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst, const double* w, CoverCsr& c)
 {
-    MCB_API_BEGIN
-    MCB_CHECK(ctx && out, "mcb_coclust_run: null argument");
+    const size_t ne1 = (size_t)std::max<int64_t>(n_edges, 1);
+    c.src.alloc(ctx, ne1); c.dst.alloc(ctx, ne1); c.w.alloc(ctx, ne1);
+    c.odeg.alloc(ctx, (size_t)N + 1); c.ideg.alloc(ctx, (size_t)N + 1); c.optr32.alloc(ctx, (size_t)N + 1); c.iptr32.alloc(ctx, (size_t)N + 1);
+    c.optr.alloc(ctx, (size_t)N + 1); c.iptr.alloc(ctx, (size_t)N + 1);
+    c.odst.alloc(ctx, ne1); c.isrc.alloc(ctx, ne1); c.scratch.alloc(ctx, 4);
+    c.ow.alloc(ctx, ne1); c.iw.alloc(ctx, ne1); c.oe.alloc(ctx, ne1); c.ie.alloc(ctx, ne1); c.nd.alloc(ctx, (size_t)N);
+    {
+        StageTimer t(ctx, "h2d_graph");
+        if (n_edges) {
+            MCB_CUDA(cudaMemcpyAsync(c.src.p, src, (size_t)n_edges * 4, cudaMemcpyHostToDevice, ctx->stream));
+            MCB_CUDA(cudaMemcpyAsync(c.dst.p, dst, (size_t)n_edges * 4, cudaMemcpyHostToDevice, ctx->stream));
+            MCB_CUDA(cudaMemcpyAsync(c.w.p, w, (size_t)n_edges * 8, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    {
+        StageTimer t(ctx, "graph_csr", 8);
+        c.odeg.zero(); c.ideg.zero(); c.scratch.zero();
+        launch_build_cover_csr(ctx, N, n_edges, c.src.p, c.dst.p, c.w.p, c.odeg.p, c.ideg.p, c.optr32.p, c.iptr32.p, c.odst.p, c.ow.p,
+                               c.isrc.p, c.iw.p, c.oe.p, c.ie.p, c.nd.p, c.scratch.p);
+        launch_widen_i32(ctx, c.optr32.p, c.optr.p, (int64_t)N + 1);
+        launch_widen_i32(ctx, c.iptr32.p, c.iptr.p, (int64_t)N + 1);
+    }
+}
+
+// n_resamp covers on host-supplied node samples.  with_counts: accumulate the N x N co-occurrence counters
+// (tgs_graph_cover_resample, method = "full"); without: assignments only (tgs_graph_cover).
+static mcb_coclust* coclust_run_impl(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst, const double* w,
+                                     int32_t n_resamp, int32_t n_s, const int32_t* samples, const uint64_t* seeds, int32_t min_mc_size,
+                                     double cooling, int32_t burn_in, int32_t max_sweeps, int32_t knn, int32_t rank, int32_t nranks,
+                                     bool with_counts)
+{
     MCB_CHECK(N >= 1 && n_edges >= 0 && n_resamp >= 0 && n_s >= 1 && n_s <= N, "MC-ERR: bad co-clustering dimensions");
     MCB_CHECK(n_edges == 0 || (src && dst && w), "mcb_coclust_run: null edge arrays");
-    MCB_CHECK(n_resamp == 0 || (samples && seeds), "mcb_coclust_run: null sample arrays");
+    MCB_CHECK(n_resamp == 0 || seeds, "mcb_coclust_run: null seed array");
     MCB_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
-    MCB_CHECK((int64_t)N * N < ((int64_t)1 << 36), "MC-ERR: method=\"full\" needs an N x N counter matrix; N is too large");
+    MCB_CHECK(knn >= 0, "MC-ERR: knn must be >= 0 (0 = no per-node edge limit)");
+    MCB_CHECK(!with_counts || (int64_t)N * N < ((int64_t)1 << 36), "MC-ERR: method=\"full\" needs an N x N counter matrix; N is too large");
     MCB_CUDA(cudaSetDevice(ctx->device));
     MCB_CHECK(n_edges < ((int64_t)1 << 31), "MC-ERR: too many edges");
     std::vector<int32_t> ids;
@@ -1197,61 +1442,52 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
     c->ncl_cap = n_s / (min_mc_size > 0 ? min_mc_size + 1 : 1) + 2;
     const int32_t nl = c->n_local;
 
-    // the host's edge table and sample sets go up as they are; CSR (out and in, 16-bit fixed-point weights) and the
-    // input validation run on the device
-    const size_t ne1 = (size_t)std::max<int64_t>(n_edges, 1);
-    DevBuf<int32_t> d_src(ctx, ne1), d_dst(ctx, ne1);
-    DevBuf<double> d_w(ctx, ne1);
-    DevBuf<int32_t> d_odeg(ctx, (size_t)N + 1), d_ideg(ctx, (size_t)N + 1), d_optr32(ctx, (size_t)N + 1), d_iptr32(ctx, (size_t)N + 1);
-    DevBuf<int64_t> d_optr(ctx, (size_t)N + 1), d_iptr(ctx, (size_t)N + 1);
-    DevBuf<int32_t> d_odst(ctx, ne1), d_isrc(ctx, ne1), scratch(ctx, 4);
-    DevBuf<uint32_t> d_ow(ctx, ne1), d_iw(ctx, ne1);
-    DevBuf<int2> d_oe(ctx, ne1), d_ie(ctx, ne1);
-    DevBuf<int4> d_nd(ctx, (size_t)N);
+    CoverCsr csr;
+    cover_csr_build(ctx, N, n_edges, src, dst, w, csr);
     DevBuf<int32_t> d_samples(ctx, (size_t)std::max<int64_t>((int64_t)n_resamp * n_s, 1)), d_ids(ctx, (size_t)std::max(nl, 1));
     DevBuf<uint64_t> d_seeds(ctx, (size_t)std::max(n_resamp, 1));
+    if (n_resamp) {
+        if (samples) MCB_CUDA(cudaMemcpyAsync(d_samples.p, samples, (size_t)n_resamp * n_s * 4, cudaMemcpyHostToDevice, ctx->stream));
+        else { MCB_CHECK(n_s == N && n_resamp == 1, "mcb_coclust_run: null sample array"); launch_iota_i32(ctx, d_samples.p, N); }   // all nodes
+        MCB_CUDA(cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n_resamp * 8, cudaMemcpyHostToDevice, ctx->stream));
+        launch_sample_check(ctx, (int64_t)n_resamp * n_s, n_s, d_samples.p, N, csr.scratch.p + 1);
+    }
+    if (nl) MCB_CUDA(cudaMemcpyAsync(d_ids.p, ids.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, ctx->stream));
     int32_t hs[4] = {0, 0, 0, 0};
-    {
-        StageTimer t(ctx, "h2d_graph");
-        if (n_edges) {
-            MCB_CUDA(cudaMemcpyAsync(d_src.p, src, (size_t)n_edges * 4, cudaMemcpyHostToDevice, ctx->stream));
-            MCB_CUDA(cudaMemcpyAsync(d_dst.p, dst, (size_t)n_edges * 4, cudaMemcpyHostToDevice, ctx->stream));
-            MCB_CUDA(cudaMemcpyAsync(d_w.p, w, (size_t)n_edges * 8, cudaMemcpyHostToDevice, ctx->stream));
-        }
-        if (n_resamp) {
-            MCB_CUDA(cudaMemcpyAsync(d_samples.p, samples, (size_t)n_resamp * n_s * 4, cudaMemcpyHostToDevice, ctx->stream));
-            MCB_CUDA(cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n_resamp * 8, cudaMemcpyHostToDevice, ctx->stream));
-        }
-        if (nl) MCB_CUDA(cudaMemcpyAsync(d_ids.p, ids.data(), (size_t)nl * 4, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    {
-        StageTimer t(ctx, "graph_csr", 8);
-        d_odeg.zero(); d_ideg.zero(); scratch.zero();
-        launch_build_cover_csr(ctx, N, n_edges, d_src.p, d_dst.p, d_w.p, d_odeg.p, d_ideg.p, d_optr32.p, d_iptr32.p, d_odst.p, d_ow.p,
-                               d_isrc.p, d_iw.p, d_oe.p, d_ie.p, d_nd.p, scratch.p);
-        launch_sample_check(ctx, (int64_t)n_resamp * n_s, n_s, d_samples.p, N, scratch.p + 1);
-        launch_widen_i32(ctx, d_optr32.p, d_optr.p, (int64_t)N + 1);
-        launch_widen_i32(ctx, d_iptr32.p, d_iptr.p, (int64_t)N + 1);
-    }
-    MCB_CUDA(cudaMemcpyAsync(hs, scratch.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaMemcpyAsync(hs, csr.scratch.p, sizeof(hs), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
     MCB_CHECK(!(hs[1] & 1), "MC-ERR: edge endpoint out of range");
     MCB_CHECK(!(hs[1] & 2), "MC-ERR: sampled node out of range");
     MCB_CHECK(!(hs[1] & 4), "MC-ERR: each resample index set must be strictly ascending");
     const int32_t max_out = hs[2], max_in = hs[3];
-    c->cnt.alloc(ctx, (size_t)N * N); c->cnt.zero();
-    c->nsamp.alloc(ctx, (size_t)N); c->nsamp.zero();
+    if (knn > 0 && knn < max_out && nl) {
+        // `knn` = the most out-edges a node may use inside one resample (R/coclust_graph_cov.r:39-41 passes the graph's
+        // average out-degree).  A sampled node only exceeds it when more than knn of its targets were sampled too;
+        // count how often that happens (at p = 0.75 and knn = 0.92 * max out-degree: practically never)
+        DevBuf<int32_t> over(ctx, 1);
+        over.zero();
+        launch_knn_trunc_check(ctx, N, nl, d_ids.p, n_s, d_samples.p, csr.optr32.p, csr.odst.p, knn, over.p);
+        int32_t h_over = 0;
+        MCB_CUDA(cudaMemcpyAsync(&h_over, over.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        MCB_CHECK(h_over == 0, "MC-ERR: tgs_graph_cover_resample: some sampled nodes have more than `knn` sampled out-neighbours; "
+                               "per-node edge truncation is not implemented -- pass knn = 0 (no limit) or knn >= the maximum out-degree");
+    }
+    if (with_counts) {
+        c->cnt.alloc(ctx, (size_t)N * N); c->cnt.zero();
+        c->nsamp.alloc(ctx, (size_t)N); c->nsamp.zero();
+    }
     c->mc.alloc(ctx, (size_t)std::max(nl, 1) * N);
     c->sweeps.alloc(ctx, (size_t)std::max(nl, 1));
     DevBuf<int32_t> f_ws(ctx, (size_t)std::max(nl, 1) * N), status(ctx, (size_t)std::max(nl, 1));
-    DevBuf<int32_t> ws_order(ctx, (size_t)std::max(nl, 1) * N), ws_start(ctx, (size_t)std::max(nl, 1) * (c->ncl_cap + 1));
-    CoverGraph cg{N, d_optr.p, d_odst.p, d_ow.p, d_iptr.p, d_isrc.p, d_iw.p};
+    CoverGraph cg{N, csr.optr.p, csr.odst.p, csr.ow.p, csr.iptr.p, csr.isrc.p, csr.iw.p};
     {
         StageTimer t(ctx, "graph_cover");
-        launch_graph_cover(ctx, cg, d_optr32.p, d_iptr32.p, d_nd.p, d_oe.p, d_ie.p, max_out, max_in, nl, d_ids.p, n_s, d_samples.p, d_seeds.p, min_mc_size, cooling, burn_in, max_sweeps,
-                           c->ncl_cap, c->mc.p, f_ws.p, c->sweeps.p, status.p);
+        launch_graph_cover(ctx, cg, csr.optr32.p, csr.iptr32.p, csr.nd.p, csr.oe.p, csr.ie.p, max_out, max_in, nl, d_ids.p, n_s, d_samples.p, d_seeds.p,
+                           min_mc_size, cooling, burn_in, max_sweeps, c->ncl_cap, c->mc.p, f_ws.p, c->sweeps.p, status.p);
     }
-    {
+    if (with_counts) {
+        DevBuf<int32_t> ws_order(ctx, (size_t)std::max(nl, 1) * N), ws_start(ctx, (size_t)std::max(nl, 1) * (c->ncl_cap + 1));
         StageTimer t(ctx, "cooccur");
         launch_cooccur(ctx, N, nl, c->mc.p, c->ncl_cap, c->cnt.p, c->nsamp.p, ws_order.p, ws_start.p);
     }
@@ -1259,25 +1495,63 @@ extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
     if (nl) MCB_CUDA(cudaMemcpyAsync(hst.data(), status.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int32_t q = 0; q < nl; ++q) MCB_CHECK(hst[q] == 0, "MC-ERR: graph cover ran out of cluster slots");
-    *out = c.release();
+    return c.release();
+}
+
+extern "C" int mcb_coclust_run2(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst,
+                                const double* w, int32_t n_resamp, int32_t n_s, const int32_t* samples,
+                                const uint64_t* seeds, int32_t min_mc_size, double cooling, int32_t burn_in,
+                                int32_t max_sweeps, int32_t knn, int32_t rank, int32_t nranks, mcb_coclust** out)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && out, "mcb_coclust_run: null argument");
+    MCB_CHECK(n_resamp == 0 || samples, "mcb_coclust_run: null sample arrays");
+    *out = coclust_run_impl(ctx, N, n_edges, src, dst, w, n_resamp, n_s, samples, seeds, min_mc_size, cooling, burn_in, max_sweeps,
+                            knn, rank, nranks, true);
+    MCB_API_END
+}
+extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst,
+                               const double* w, int32_t n_resamp, int32_t n_s, const int32_t* samples,
+                               const uint64_t* seeds, int32_t min_mc_size, double cooling, int32_t burn_in,
+                               int32_t max_sweeps, int32_t rank, int32_t nranks, mcb_coclust** out)
+{
+    return mcb_coclust_run2(ctx, N, n_edges, src, dst, w, n_resamp, n_s, samples, seeds, min_mc_size, cooling, burn_in, max_sweeps,
+                            /*knn=*/0, rank, nranks, out);
+}
+// NCCL reduce(sum) of the co-occurrence counters and of samples[N] into `root`; collective
+extern "C" int mcb_coclust_reduce(mcb_comm* comm, mcb_coclust* c, int32_t root)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(comm && c && c->cnt.p, "mcb_coclust_reduce: null argument");
+    MCB_CHECK(root >= 0 && root < comm->nranks, "mcb_coclust_reduce: bad root");
+    mcb_ctx* ctx = c->ctx;
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    {
+        StageTimer t(ctx, "reduce_counts", 0);
+        comm_reduce_sum_u32(comm, c->cnt.p, (size_t)c->N * c->N, root);
+        comm_reduce_sum_u32(comm, c->nsamp.p, (size_t)c->N, root);
+    }
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
     MCB_API_END
 }
 // tgs_graph_cover(edges, min_mc_size, cooling, burn_in) (reference call sites R/mc_graphcov.r:27,
-// R/mc_from_coclust.r:247): ONE cover over all nodes.  cluster[v] = 0 for outliers (R/mc_graphcov.r:28),
-// 1..n for covered nodes (ids are the cover's seeding order, not compacted).
+// R/mc_from_coclust.r:247): ONE cover over all nodes, no co-occurrence counters (so no N x N memory: the cover of a
+// million-node graph is fine).  cluster[v] = 0 for outliers (R/mc_graphcov.r:28), 1..n for covered nodes (ids are the
+// cover's seeding order, not compacted).
 extern "C" int mcb_graph_cover(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst,
                                const double* w, int32_t min_mc_size, double cooling, int32_t burn_in, int32_t max_sweeps,
                                uint64_t seed, int32_t* host_cluster, int32_t* n_sweeps)
 {
     mcb_coclust* c = nullptr;
     int rc = 0;
-    {
-        if (!host_cluster || N < 1) { mcb::set_error("mcb_graph_cover: bad argument"); return 1; }
-        std::vector<int32_t> all((size_t)N);
-        for (int32_t v = 0; v < N; ++v) all[v] = v;
-        rc = mcb_coclust_run(ctx, N, n_edges, src, dst, w, 1, N, all.data(), &seed, min_mc_size, cooling, burn_in, max_sweeps,
-                             0, 1, &c);
+    try {
+        MCB_CHECK(ctx && host_cluster && N >= 1, "mcb_graph_cover: bad argument");
+        c = coclust_run_impl(ctx, N, n_edges, src, dst, w, 1, N, /*samples = all nodes*/ nullptr, &seed, min_mc_size, cooling, burn_in,
+                             max_sweeps, 0, 0, 1, false);
     }
+    catch (const mcb::Error& e) { mcb::set_error(e.what()); rc = e.code; }
+    catch (const std::bad_alloc&) { mcb::set_error("host out of memory"); rc = 3; }
+    catch (const std::exception& e) { mcb::set_error(e.what()); rc = 4; }
     if (rc) return rc;
     int32_t nl = 0, sw = 0;
     rc = mcb_coclust_assignments(c, host_cluster, &sw, &nl);
@@ -1297,7 +1571,7 @@ extern "C" void mcb_coclust_destroy(mcb_coclust* c)
 extern "C" int mcb_coclust_buffers(mcb_coclust* c, void** dev_cnt, void** dev_nsamp)
 {
     MCB_API_BEGIN
-    MCB_CHECK(c, "null argument");
+    MCB_CHECK(c && c->cnt.p, "mcb_coclust_buffers: no counters on this handle");
     if (dev_cnt) *dev_cnt = c->cnt.p;
     if (dev_nsamp) *dev_nsamp = c->nsamp.p;
     MCB_API_END
@@ -1317,7 +1591,7 @@ extern "C" int mcb_coclust_assignments(mcb_coclust* c, int32_t* host_mc, int32_t
 extern "C" int mcb_coclust_extract(mcb_coclust* c, int64_t* n_pairs)
 {
     MCB_API_BEGIN
-    MCB_CHECK(c && n_pairs, "null argument");
+    MCB_CHECK(c && n_pairs && c->cnt.p, "null argument");
     mcb_ctx* ctx = c->ctx;
     MCB_CUDA(cudaSetDevice(ctx->device));
     const int32_t N = c->N;

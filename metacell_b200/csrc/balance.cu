@@ -262,22 +262,19 @@ __global__ void widen_i32_kernel(const int32_t* __restrict__ in, int64_t* __rest
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 template <typename F>
-static void ensure_smem(F* kernel, size_t smem, size_t& configured)
+static void ensure_smem(mcb_ctx* ctx, F* kernel, size_t smem, SmemOptIn& optin)
 {
     MCB_CHECK(smem <= 200 * 1024, "balance: K*k_expand too large for shared memory");
-    if (smem > configured) {
-        MCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    ensure_dyn_smem(optin, ctx, kernel, smem);
 }
 
 void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t Kc, int32_t H, int32_t rank_bits,
                        uint32_t* table)
 {
     if (M == 0) return;
-    static size_t configured = 0;
+    static SmemOptIn optin;
     const size_t smem = (size_t)H * sizeof(uint32_t);
-    ensure_smem(build_hash_kernel, smem, configured);
+    ensure_smem(ctx, build_hash_kernel, smem, optin);
     const int grid = wave_grid(ctx, build_hash_kernel, smem, M);
     build_hash_kernel<<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, M, Kc, H, ilog2(H), rank_bits, table);
     MCB_LAUNCH_CHECK();
@@ -288,9 +285,9 @@ static void launch_mutual_t(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t
                             int32_t Kc, int32_t H, int32_t rank_bits, int64_t smax, int strict, int keep_self, int32_t kin,
                             uint32_t* sym, uint64_t* thr_in)
 {
-    static size_t configured = 0;
+    static SmemOptIn optin;
     const size_t smem = (size_t)IPT * 256 * sizeof(uint64_t);
-    ensure_smem(mutual_kernel<IPT>, smem, configured);
+    ensure_smem(ctx, mutual_kernel<IPT>, smem, optin);
     const int grid = wave_grid(ctx, mutual_kernel<IPT>, smem, rows);
     mutual_kernel<IPT><<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, table, row0, rows, Kc, H, ilog2(H), rank_bits,
                                                                   (long long)smax, strict, keep_self, kin, sym, thr_in);
@@ -300,9 +297,9 @@ template <int IPT>
 static void launch_prune_t(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* sym, const uint64_t* thr_in, int64_t row0,
                            int64_t rows, int32_t Kc, int32_t K, int64_t smax, int32_t* out_deg, int32_t* out_dst, int32_t* out_s)
 {
-    static size_t configured = 0;
+    static SmemOptIn optin;
     const size_t smem = (size_t)IPT * 256 * sizeof(uint64_t);
-    ensure_smem(prune_kernel<IPT>, smem, configured);
+    ensure_smem(ctx, prune_kernel<IPT>, smem, optin);
     const int grid = wave_grid(ctx, prune_kernel<IPT>, smem, rows);
     prune_kernel<IPT><<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, sym, thr_in, row0, rows, Kc, K, (long long)smax, out_deg, out_dst, out_s);
     MCB_LAUNCH_CHECK();

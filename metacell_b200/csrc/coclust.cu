@@ -1111,6 +1111,54 @@ void launch_build_cover_csr(mcb_ctx* ctx, int32_t N, int64_t ne, const int32_t* 
     node_desc_kernel<<<std::min(ctx->num_sms, (int)ceil_div(N, 256)), 256, 0, ctx->stream>>>(N, optr, iptr, (int4*)nd);
     MCB_LAUNCH_CHECK();
 }
+__global__ void iota_i32_kernel(int32_t* __restrict__ v, int32_t n)
+{
+    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = i;
+}
+void launch_iota_i32(mcb_ctx* ctx, int32_t* v, int32_t n)
+{
+    if (n == 0) return;
+    iota_i32_kernel<<<std::min(ctx->num_sms * 4, (int)ceil_div(n, 256)), 256, 0, ctx->stream>>>(v, n);
+    MCB_LAUNCH_CHECK();
+}
+
+// `knn` of tgs_graph_cover_resample = the most out-edges a node may use inside one resample.  One CTA per local resample:
+// a bitmap of the sampled nodes (global workspace, N bits), then per sampled node the number of sampled out-neighbours;
+// *over += number of (resample, node) pairs above knn.
+__global__ void __launch_bounds__(256)
+knn_trunc_check_kernel(int32_t N, int32_t n_local, const int32_t* __restrict__ resamp_ids, int32_t n_s,
+                       const int32_t* __restrict__ samples, const int32_t* __restrict__ optr, const int32_t* __restrict__ odst,
+                       int32_t knn, uint32_t* __restrict__ bitmap_ws, int32_t* __restrict__ over)
+{
+    const int32_t words = (N + 31) / 32;
+    for (int lr = blockIdx.x; lr < n_local; lr += gridDim.x) {
+        uint32_t* bm = bitmap_ws + (int64_t)blockIdx.x * words;
+        const int32_t* S = samples + (int64_t)resamp_ids[lr] * n_s;
+        for (int q = threadIdx.x; q < words; q += blockDim.x) bm[q] = 0u;
+        __syncthreads();
+        for (int q = threadIdx.x; q < n_s; q += blockDim.x) atomicOr(&bm[S[q] >> 5], 1u << (S[q] & 31));
+        __syncthreads();
+        int bad = 0;
+        for (int q = threadIdx.x; q < n_s; q += blockDim.x) {
+            const int32_t v = S[q];
+            int c = 0;
+            for (int32_t e = optr[v]; e < optr[v + 1]; ++e) { const int32_t u = odst[e]; c += (bm[u >> 5] >> (u & 31)) & 1u; }
+            bad += c > knn;
+        }
+        if (bad) atomicAdd(over, bad);
+        __syncthreads();
+    }
+}
+void launch_knn_trunc_check(mcb_ctx* ctx, int32_t N, int32_t n_local, const int32_t* resamp_ids, int32_t n_s, const int32_t* samples,
+                            const int32_t* optr32, const int32_t* odst, int32_t knn, int32_t* over)
+{
+    if (n_local == 0) return;
+    const int grid = std::min(n_local, ctx->num_sms * 4);
+    DevBuf<uint32_t> ws(ctx, (size_t)grid * ((N + 31) / 32));
+    knn_trunc_check_kernel<<<grid, 256, 0, ctx->stream>>>(N, n_local, resamp_ids, n_s, samples, optr32, odst, knn, ws.p, over);
+    MCB_LAUNCH_CHECK();
+}
+
 void launch_sample_check(mcb_ctx* ctx, int64_t total, int32_t n_s, const int32_t* samples, int32_t N, int32_t* err)
 {
     if (total == 0) return;
@@ -1211,11 +1259,8 @@ static void launch_cover_fast(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local
                               int32_t max_sweeps, int32_t ncl_cap, int32_t max_out, size_t smem, int32_t* mc, int32_t* f_ws,
                               int32_t* sweeps, int32_t* status)
 {
-    static size_t configured = 0;
-    if (smem > configured) {
-        MCB_CUDA(cudaFuncSetAttribute(graph_cover_fast_kernel<FT, IN_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    ensure_dyn_smem(optin, ctx, graph_cover_fast_kernel<FT, IN_SLOTS>, smem);
     const int32_t out_warps = std::max(1, (int)ceil_div(max_out, 32));
     graph_cover_fast_kernel<FT, IN_SLOTS><<<n_local, FT, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds,
                                                                                min_size, cooling, burn_in, max_sweeps, ncl_cap,
@@ -1229,11 +1274,8 @@ static void launch_cover_batch(mcb_ctx* ctx, const FastGraph& fg, int32_t n_loca
                                int32_t max_sweeps, int32_t ncl_cap, int32_t max_out, size_t smem, int32_t* mc, int32_t* f_ws,
                                int32_t* sweeps, int32_t* status)
 {
-    static size_t configured = 0;
-    if (smem > configured) {
-        MCB_CUDA(cudaFuncSetAttribute(graph_cover_batch_kernel<B, OUT_SLOTS, IN_SLOTS, VT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    ensure_dyn_smem(optin, ctx, graph_cover_batch_kernel<B, OUT_SLOTS, IN_SLOTS, VT>, smem);
     const int32_t out_warps = std::max(1, (int)ceil_div(max_out, 32));
     graph_cover_batch_kernel<B, OUT_SLOTS, IN_SLOTS, VT><<<n_local, 128 * B, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds,
                                                                                     min_size, cooling, burn_in, max_sweeps,
@@ -1247,11 +1289,8 @@ static void launch_cover_warp(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local
                               int32_t max_sweeps, int32_t ncl_cap, int32_t kin_stride, size_t smem, int32_t* mc, int32_t* f_ws,
                               int32_t* sweeps, int32_t* status)
 {
-    static size_t configured = 0;
-    if (smem > configured) {
-        MCB_CUDA(cudaFuncSetAttribute(graph_cover_warp_kernel<B, OUT_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    ensure_dyn_smem(optin, ctx, graph_cover_warp_kernel<B, OUT_SLOTS>, smem);
     graph_cover_warp_kernel<B, OUT_SLOTS><<<n_local, 32 * B, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds,
                                                                                    min_size, cooling, burn_in, max_sweeps, ncl_cap,
                                                                                    kin_stride, mc, f_ws, sweeps, status);
@@ -1324,11 +1363,8 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
     }
     const size_t smem = (size_t)ncl_cap * 3 * sizeof(uint32_t);
     MCB_CHECK(smem <= 200 * 1024, "MC-ERR: graph cover: too many potential clusters for shared memory");
-    static size_t configured = 0;
-    if (smem > configured) {
-        MCB_CUDA(cudaFuncSetAttribute(graph_cover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    ensure_dyn_smem(optin, ctx, graph_cover_kernel, smem);
     graph_cover_kernel<<<n_local, CC_THREADS, smem, ctx->stream>>>(g, n_local, resamp_ids, n_s, samples, seeds, min_size,
                                                                     cooling, burn_in, max_sweeps, ncl_cap, mc, f_ws,
                                                                     sweeps, status);
@@ -1340,11 +1376,8 @@ void launch_cooccur(mcb_ctx* ctx, int32_t N, int32_t n_local, const int32_t* mc,
 {
     if (n_local == 0) return;
     const size_t smem = (size_t)(ncl_cap + 1) * sizeof(int32_t);
-    static size_t configured = 0;
-    if (smem > configured && smem > 48 * 1024) {
-        MCB_CUDA(cudaFuncSetAttribute(cooccur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemOptIn optin;
+    ensure_dyn_smem(optin, ctx, cooccur_kernel, smem);
     cooccur_kernel<<<n_local, 256, smem, ctx->stream>>>(N, n_local, mc, ncl_cap, cnt, nsamp, ws_order, ws_start);
     MCB_LAUNCH_CHECK();
 }

@@ -768,11 +768,8 @@ static void launch_tc(mcb_ctx* ctx, const CUtensorMap& ah, const CUtensorMap& al
                       const CUtensorMap& bl, const TcParams& prm)
 {
     using Cfg = TcCfg<NPASS>;
-    static bool configured = false;
-    if (!configured) {
-        MCB_CUDA(cudaFuncSetAttribute(tc_cor_kernel<NPASS, MODE, CM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    ensure_dyn_smem(optin, ctx, tc_cor_kernel<NPASS, MODE, CM>, (size_t)Cfg::SMEM_BYTES);
     TcParams p2 = prm;
     p2.dbg = (MODE != 0 && getenv("MCB_TC_DEBUG")) ? atoi(getenv("MCB_TC_DEBUG")) : 0;
     p2.total_tiles = TileIter((int)ceil_div(prm.m_tiles, CM), prm.n_tiles, MODE == 2 ? 1 : 0, CM * BM).total();
@@ -829,11 +826,8 @@ void launch_tc_store(mcb_ctx* ctx, const void* Ahi, int64_t a_rows_alloc, const 
 template <int MODE>
 static void launch_tc2(mcb_ctx* ctx, const CUtensorMap& mh, const CUtensorMap& ml, const TcParams& prm)
 {
-    static bool configured = false;
-    if (!configured) {
-        MCB_CUDA(cudaFuncSetAttribute(tc_cor2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::SMEM_BYTES));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    ensure_dyn_smem(optin, ctx, tc_cor2_kernel<MODE>, (size_t)Tc2Cfg::SMEM_BYTES);
     TcParams p2 = prm;
     p2.dbg = getenv("MCB_TC_DEBUG") ? atoi(getenv("MCB_TC_DEBUG")) : 0;
     p2.total_tiles = TileIter((int)ceil_div(prm.m_tiles, 2), prm.n_tiles, MODE == 2 ? 1 : 0, 2 * BM).total();

@@ -70,7 +70,7 @@ __device__ __forceinline__ long long block_excl_scan(long long v, long long* war
 __global__ void __launch_bounds__(DS_THREADS)
 downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t* __restrict__ x, double n,
                   uint32_t seed_lo, uint32_t seed_hi, int add_non_dsamp, uint32_t* __restrict__ out_x,
-                  uint8_t* __restrict__ kept)
+                  uint8_t* __restrict__ kept, int64_t cell_base)
 {
     __shared__ uint32_t hist[256];
     __shared__ long long warp_tot[DS_THREADS / 32 + 1];
@@ -99,7 +99,8 @@ downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t*
         // 2. radix select of the d-th smallest 64-bit key (index d-1), 8 bits per pass from the top
         if (threadIdx.x == 0) { s_prefix = 0ull; s_krem = d - 1; s_done = 0; s_thr = ~0ull; }
         __syncthreads();
-        const uint32_t c_lo = (uint32_t)c, c_hi = (uint32_t)((uint64_t)c >> 32);
+        // the key of a UMI names its cell by the index in the WHOLE matrix, so a cell shard draws the same subset
+        const uint32_t c_lo = (uint32_t)(c + cell_base), c_hi = (uint32_t)((uint64_t)(c + cell_base) >> 32);
         const long long ngroups = (tot + 3) >> 2;
         for (int pass = 0; pass < 8; ++pass) {
             const int shift = 56 - 8 * pass;
@@ -186,13 +187,13 @@ void launch_col_sums(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const uint3
     MCB_LAUNCH_CHECK();
 }
 void launch_downsample(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const uint32_t* x, double n, uint64_t seed,
-                       int add_non_dsamp, uint32_t* out_x, uint8_t* kept)
+                       int add_non_dsamp, uint32_t* out_x, uint8_t* kept, int64_t cell_base)
 {
     if (ncells == 0) return;
     MCB_CHECK(n >= 1.0, "MC-ERR: downsample depth must be >= 1");
     int grid = (int)std::min<int64_t>(ncells, (int64_t)ctx->num_sms * 8);
     downsample_kernel<<<grid, DS_THREADS, 0, ctx->stream>>>(ncells, p, x, n, (uint32_t)seed, (uint32_t)(seed >> 32),
-                                                             add_non_dsamp, out_x, kept);
+                                                             add_non_dsamp, out_x, kept, cell_base);
     MCB_LAUNCH_CHECK();
 }
 

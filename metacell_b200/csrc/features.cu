@@ -122,7 +122,7 @@ feat_rows_kernel(int64_t ncells, const int64_t* __restrict__ p, const int32_t* _
                  const uint32_t* __restrict__ x, const int32_t* __restrict__ feat_map, int32_t G, int32_t Gpad,
                  double k_nonz, const double* __restrict__ mu_in, const double* __restrict__ inv_in,
                  const int32_t* __restrict__ valid, const int32_t* __restrict__ rowpos, float* __restrict__ Zf,
-                 __half* __restrict__ Zh, __half* __restrict__ Zl, int32_t* __restrict__ cell_of_row)
+                 __half* __restrict__ Zh, __half* __restrict__ Zl, int32_t* __restrict__ cell_of_row, int64_t cell_base)
 {
     extern __shared__ float srow[];        // [Gpad]
     __shared__ double lut[FEAT_LUT];
@@ -146,10 +146,10 @@ feat_rows_kernel(int64_t ncells, const int64_t* __restrict__ p, const int32_t* _
         const int64_t r = rowpos[c];
         for (int g = threadIdx.x; g < Gpad; g += FR_THREADS) {
             const float z = srow[g];
-            Zf[r * (int64_t)Gpad + g] = z;
+            if (Zf) Zf[r * (int64_t)Gpad + g] = z;          // the fp32 plane only exists on single-rank builds
             split_store(z, Zh + r * (int64_t)Gpad + g, Zl + r * (int64_t)Gpad + g);
         }
-        if (threadIdx.x == 0) cell_of_row[r] = (int32_t)c;
+        if (threadIdx.x == 0) cell_of_row[r] = (int32_t)(cell_base + c);
         __syncthreads();
     }
 }
@@ -256,12 +256,12 @@ void launch_exclusive_scan_i64(mcb_ctx* ctx, const int64_t* in, int64_t* out, in
 void launch_feat_rows(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const int32_t* ridx, const uint32_t* x,
                       const int32_t* feat_map, int32_t G, int32_t Gpad, double k_nonz, const double* mu,
                       const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zf, void* Zh, void* Zl,
-                      int32_t* cell_of_row)
+                      int32_t* cell_of_row, int64_t cell_base)
 {
     if (ncells == 0) return;
     int grid = (int)std::min<int64_t>(ncells, (int64_t)ctx->num_sms * 16);
     feat_rows_kernel<<<grid, FR_THREADS, (size_t)Gpad * sizeof(float), ctx->stream>>>(
-        ncells, p, ridx, x, feat_map, G, Gpad, k_nonz, mu, inv, valid, rowpos, Zf, (__half*)Zh, (__half*)Zl, cell_of_row);
+        ncells, p, ridx, x, feat_map, G, Gpad, k_nonz, mu, inv, valid, rowpos, Zf, (__half*)Zh, (__half*)Zl, cell_of_row, cell_base);
     MCB_LAUNCH_CHECK();
 }
 void launch_gather_rows(mcb_ctx* ctx, const void* Z, int64_t row_bytes, const int32_t* rows, int32_t nrows, void* out)

@@ -262,11 +262,8 @@ void launch_gene_bucket(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, int64_t nn
     const size_t smem = (size_t)ngenes * sizeof(uint32_t);
     const bool priv = smem <= 200 * 1024;              // per-CTA counters fit in shared memory
     if (priv) {
-        static size_t configured = 0;
-        if (smem > configured) {
-            MCB_CUDA(cudaFuncSetAttribute(gene_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
-        }
+        static SmemOptIn optin;
+        ensure_dyn_smem(optin, ctx, gene_count_kernel, smem);
     }
     const int per_sm = priv ? (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(smem, 1))) : 16;
     MCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(uint32_t) * (size_t)std::max(ngenes, 1), ctx->stream));

@@ -10,6 +10,8 @@
 #include <map>
 #include <mutex>
 
+namespace mcb { struct Staging; }
+
 struct mcb_ctx {
     std::atomic<int> refs{1};   // the creator + every live handle; destroyed when it drops to 0
     int device = 0;
@@ -30,6 +32,10 @@ struct mcb_ctx {
     int keep_self = 0;
     int thresh_strict = 1;
     int cap_override = 0;    // test hook: shrink the candidate capacity so rows take the exact-row path
+    int host_threads = 0;    // staging threads per context (0 = min(16, cores / 2), env MCB_HOST_THREADS)
+    mcb::Staging* staging = nullptr;     // pinned ring + copy stream + host threads, created on first use (staging.cu)
+    // cached sample of column indices for the kNN threshold pass, keyed by (M, S): the sample only steers the filter
+    int64_t samp_M = 0, samp_S = 0; void* samp_dev = nullptr; size_t samp_bytes = 0;
     // stage timers
     struct Stage { const char* name; cudaEvent_t a, b; int64_t launches; };
     std::vector<Stage> stages;
@@ -68,6 +74,20 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// cudaFuncSetAttribute applies to the CURRENT device only, and one process can hold contexts on several devices
+// (mcb_ctx_create(device), mcb_multi): the opt-in to large dynamic shared memory is tracked per (kernel, device).
+struct SmemOptIn { std::mutex mu; size_t done[64] = {}; };
+template <typename F>
+inline void ensure_dyn_smem(SmemOptIn& st, mcb_ctx* ctx, F* kernel, size_t smem)
+{
+    std::lock_guard<std::mutex> lk(st.mu);
+    size_t& d = st.done[ctx->device & 63];
+    if (smem > d) {
+        MCB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        d = smem;
+    }
+}
+
 // declared FIRST in every handle struct so it is destroyed LAST (after the DevBufs that use the ctx)
 void ctx_retain(mcb_ctx* c);
 void ctx_release(mcb_ctx* c);
@@ -86,13 +106,22 @@ struct StageTimer {
     ~StageTimer();
 };
 
+// staging.cu: pinned-ring transfers of the large host objects (see the header comment there)
+Staging* ctx_staging(mcb_ctx* ctx);
+void ctx_staging_destroy(mcb_ctx* ctx);
+void staged_upload_csc(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64_t* p, const int32_t* i, const double* x,
+                       int64_t* d_p, int32_t* d_i, uint32_t* d_x);
+void staged_download_edges(mcb_ctx* ctx, int64_t rows, int32_t K, int64_t ne, const int32_t* d_out_deg, const int32_t* d_src_cell,
+                           const int32_t* d_e_dst, int32_t* host_src, int32_t* host_dst, double* host_w);
+void launch_csc_validate(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, int64_t nnz, const int64_t* p, const int32_t* ridx, int32_t* flags);
+
 // ---- launchers (each enqueues on ctx->stream; no host sync unless stated) -------------------
 
 // downsample.cu
 void launch_convert_x(mcb_ctx* ctx, const double* d_xd, uint32_t* d_x, int64_t nnz);
 void launch_col_sums(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const uint32_t* x, int64_t* tot);
 void launch_downsample(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const uint32_t* x, double n, uint64_t seed,
-                       int add_non_dsamp, uint32_t* out_x, uint8_t* kept);
+                       int add_non_dsamp, uint32_t* out_x, uint8_t* kept, int64_t cell_base = 0);
 void launch_x_to_double(mcb_ctx* ctx, const uint32_t* d_x, double* d_xd, int64_t nnz);
 
 // features.cu
@@ -102,7 +131,7 @@ void launch_exclusive_scan_i32(mcb_ctx* ctx, const int32_t* in, int32_t* out, in
 void launch_feat_rows(mcb_ctx* ctx, int64_t ncells, const int64_t* p, const int32_t* ridx, const uint32_t* x,
                       const int32_t* feat_map, int32_t G, int32_t Gpad, double k_nonz, const double* mu,
                       const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zf, void* Zh, void* Zl,
-                      int32_t* cell_of_row);
+                      int32_t* cell_of_row, int64_t cell_base = 0);
 void launch_dense_stats(mcb_ctx* ctx, int64_t ncells, const double* x, int32_t G, double* mu, double* inv, int32_t* valid);
 void launch_dense_rows(mcb_ctx* ctx, int64_t ncells, const double* x, int32_t G, int32_t Gpad, const double* mu,
                        const double* inv, const int32_t* valid, const int32_t* rowpos, float* Zf, void* Zh, void* Zl,
@@ -150,6 +179,8 @@ void launch_sample_threshold16(mcb_ctx* ctx, const void* C16, int64_t ldc, int64
 void launch_topk_rows(mcb_ctx* ctx, const uint64_t* cand, const uint32_t* cnt, int32_t cap, int64_t row0,
                       int64_t rows, int32_t kc_out, int32_t Kc, int32_t* knn_col, float* knn_cor, int32_t* fail_flag);
 void launch_compact_flags(mcb_ctx* ctx, const int32_t* flag, int64_t n, int32_t* list, int32_t* n_out);
+void launch_sum_u32(mcb_ctx* ctx, const uint32_t* v, int64_t n, uint64_t* out);
+void launch_fill_u32(mcb_ctx* ctx, void* v, int64_t n, uint32_t value);
 void launch_topk_big(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t M, const int32_t* rows, int32_t nrows,
                      int64_t row0, int32_t kc_out, int32_t Kc, const float* thr_rows /* [own rows] or null */,
                      int32_t* knn_col, float* knn_cor, bool with_self = true);
@@ -178,6 +209,9 @@ void launch_build_cover_csr(mcb_ctx* ctx, int32_t N, int64_t ne, const int32_t* 
                             int32_t* odeg, int32_t* ideg, int32_t* optr, int32_t* iptr, int32_t* odst, uint32_t* ow,
                             int32_t* isrc, uint32_t* iw, void* oe, void* ie, void* nd, int32_t* scratch4);
 void launch_sample_check(mcb_ctx* ctx, int64_t total, int32_t n_s, const int32_t* samples, int32_t N, int32_t* err);
+void launch_iota_i32(mcb_ctx* ctx, int32_t* v, int32_t n);
+void launch_knn_trunc_check(mcb_ctx* ctx, int32_t N, int32_t n_local, const int32_t* resamp_ids, int32_t n_s, const int32_t* samples,
+                            const int32_t* optr32, const int32_t* odst, int32_t knn, int32_t* over);
 
 // balance.cu
 void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t Kc, int32_t H, int32_t rank_bits,

@@ -534,11 +534,8 @@ static void launch_topk_select_t(mcb_ctx* ctx, const uint64_t* cand, const uint3
                                  int64_t rows, int32_t kc_out, int32_t Kc, int32_t* knn_col, float* knn_cor, int32_t* fail_flag)
 {
     const size_t smem = (size_t)IPT_IN * 256 * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured) {      // static (histogram + prefix, 16.5 KB) + dynamic shared memory can exceed the 48 KB default
-        MCB_CUDA(cudaFuncSetAttribute(topk_select_rows_kernel<IPT_IN, IPT_OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static SmemOptIn optin;   // static (histogram + prefix, 16.5 KB) + dynamic shared memory can exceed the 48 KB default
+    ensure_dyn_smem(optin, ctx, topk_select_rows_kernel<IPT_IN, IPT_OUT>, smem);
     static int per_sm = 0;            // resident CTAs per SM: whole waves only, the kernel strides over the rows
     if (!per_sm) MCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, topk_select_rows_kernel<IPT_IN, IPT_OUT>, SEL_THREADS, smem));
     int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * std::max(per_sm, 1));
@@ -552,11 +549,8 @@ static void launch_topk_rows_t(mcb_ctx* ctx, const uint64_t* cand, const uint32_
                                int64_t rows, int32_t kc_out, int32_t Kc, int32_t* knn_col, float* knn_cor, int32_t* fail_flag)
 {
     const size_t smem = (size_t)IPT * 256 * sizeof(uint64_t);
-    static bool configured = false;
-    if (!configured && smem > 48 * 1024) {
-        MCB_CUDA(cudaFuncSetAttribute(topk_rows_kernel<IPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static SmemOptIn optin;
+    ensure_dyn_smem(optin, ctx, topk_rows_kernel<IPT>, smem);
     int grid = (int)std::min<int64_t>(rows, (int64_t)ctx->num_sms * 8);
     topk_rows_kernel<IPT><<<grid, SEL_THREADS, smem, ctx->stream>>>(cand, cnt, cap, row0, rows, kc_out, Kc, knn_col,
                                                                      knn_cor, fail_flag);
@@ -613,6 +607,35 @@ void launch_scatter_flat(mcb_ctx* ctx, const void* records, int64_t n, int64_t r
     MCB_LAUNCH_CHECK();
 }
 
+__global__ void sum_u32_kernel(const uint32_t* __restrict__ v, int64_t n, unsigned long long* __restrict__ out)
+{
+    unsigned long long s = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(out, s);
+}
+__global__ void fill_u32_kernel(uint32_t* __restrict__ v, int64_t n, uint32_t value)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = value;
+}
+// *out (pre-zeroed by this launcher) = sum of v[0..n)
+void launch_sum_u32(mcb_ctx* ctx, const uint32_t* v, int64_t n, uint64_t* out)
+{
+    MCB_CUDA(cudaMemsetAsync(out, 0, sizeof(uint64_t), ctx->stream));
+    if (n == 0) return;
+    int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->num_sms * 4);
+    sum_u32_kernel<<<grid, 256, 0, ctx->stream>>>(v, n, (unsigned long long*)out);
+    MCB_LAUNCH_CHECK();
+}
+void launch_fill_u32(mcb_ctx* ctx, void* v, int64_t n, uint32_t value)
+{
+    if (n == 0) return;
+    int grid = (int)std::min<int64_t>(ceil_div(n, 256), (int64_t)ctx->num_sms * 4);
+    fill_u32_kernel<<<grid, 256, 0, ctx->stream>>>((uint32_t*)v, n, value);
+    MCB_LAUNCH_CHECK();
+}
+
 void launch_compact_flags(mcb_ctx* ctx, const int32_t* flag, int64_t n, int32_t* list, int32_t* n_out)
 {
     MCB_CUDA(cudaMemsetAsync(n_out, 0, sizeof(int32_t), ctx->stream));
@@ -631,12 +654,9 @@ void launch_topk_big(mcb_ctx* ctx, const float* C, int64_t ldc, int64_t M, const
     if (thr_rows) np2 = std::max(np2, 4096);
     const size_t smem = (size_t)np2 * sizeof(uint64_t);
     MCB_CHECK(smem <= 200 * 1024, "topk_big: Kc too large for shared memory");
-    static size_t configured = 0;
-    if (smem > configured) {
-        MCB_CUDA(cudaFuncSetAttribute(topk_big_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MCB_CUDA(cudaFuncSetAttribute(topk_big_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemOptIn optin_t, optin_f;
+    ensure_dyn_smem(optin_t, ctx, topk_big_kernel<true>, smem);
+    ensure_dyn_smem(optin_f, ctx, topk_big_kernel<false>, smem);
     if (with_self)
         topk_big_kernel<true><<<nrows, SEL_THREADS, smem, ctx->stream>>>(C, ldc, M, rows, nrows, row0, kc_out, Kc, thr_rows, np2, knn_col, knn_cor);
     else
