@@ -5,16 +5,17 @@ Metric (BASELINE.json): cells/sec for the balanced K=100 cgraph build.  One "ste
 of the hot path (features -> correlation + top-Kc -> rank balancing -> edge table) over the C2
 workload: 100,000 cells x 1,000 feature genes, K = 100 (k_expand 10, k_beta 3), synthetic
 negative-binomial UMIs.  At N > 1 the same workload is sharded over N ranks (strong scaling): every rank
-contracts 1/N of the symmetric tile list, candidate records reach their row owners in one NCCL all-to-all, and
-the kNN lists / in-degree cuts are all-gathered.
+ingests 1/N of the cells and contracts 1/N of the symmetric tile list; NCCL runs inside libmcb200.so (feature planes,
+thresholds, kNN lists and in-degree cuts all-gathered; candidate records all-to-all).
 
   value : cells / s with the CSC matrix already resident in HBM (device-timed, max over ranks)
-  e2e   : cells / s through the C ABI with host (pinned) buffers: H2D of the CSC + the whole path +
-          D2H of the (mc1, mc2, w) edge table inside the timed region
+  e2e   : cells / s through the one-shot C-ABI call the R glue makes (mcb_cgraph_bknn) with ordinary pageable host
+          vectors: H2D of the dgCMatrix slots + the whole path + D2H of the (mc1, mc2, w) edge table in the timed region
   roofline     : the dominant kernel (tcgen05 correlation + fused filter), CUDA-event timed
   cpu_baseline : CPU port of the dominant stage (OpenBLAS fp64 dgemm + partial selection) on a bounded
                  row sample, all host cores
-  coclust      : second metric, co-clustering resamples / s on the C3 workload (N = 1 only)
+  parity       : the bench workload's own result checked against the fp64 oracle after the timed region
+  C1 / C3 / C5 : the other BASELINE configs as named sub-records (C3 = the metric's second half, resamples / s)
 
 `--impl reference` times the CPU port alone (the reference's tgstat cannot run here: no R).
 """
@@ -235,35 +236,40 @@ def _ncu_traffic(a, M):
     return best
 
 
+def _stage_dict(st):
+    return {k: round(v[0], 3) for k, v in st.items()}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
     from metacell_b200 import _lib
-    from metacell_b200 import dist as mdist
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = _lib.Context(local)
+    comm = None
+    if world > 1:
+        # the launcher's process group only carries the 128-byte NCCL id, the barriers and the max over ranks of the
+        # timings; every exchange of the path runs inside libmcb200.so on its own communicator
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(_lib.Comm.unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        comm = _lib.Comm(ctx, world, rank, idt.cpu().numpy().tobytes())
     stream = torch.cuda.ExternalStream(ctx.stream(), device=local)
 
     m, feats = make_input(a)
-    nnz = m.nnz
-    # pinned host copies of the dgCMatrix slots (what R would hand over) + device-resident copy
-    hp = torch.from_numpy(m.indptr.astype(np.int64)).pin_memory()
-    hi = torch.from_numpy(m.indices.astype(np.int32)).pin_memory()
-    hx = torch.from_numpy(m.data.astype(np.float64)).pin_memory()
-    dp, di = hp.cuda(), hi.cuda()
-    dx = torch.from_numpy(m.data.astype(np.int64)).cuda().to(torch.int32)      # uint32 counts on device
-    csc_dev = _lib.Csc.wrap_device(ctx, m.ngenes, m.ncells, nnz, dp.data_ptr(), di.data_ptr(), dx.data_ptr(), keep=(dp, di, dx))
-    max_edges = m.ncells * a.K
-    out_src = torch.empty(max_edges, dtype=torch.int32).pin_memory()
-    out_dst = torch.empty(max_edges, dtype=torch.int32).pin_memory()
-    out_w = torch.empty(max_edges, dtype=torch.float64).pin_memory()
-    out_np = (out_src.numpy(), out_dst.numpy(), out_w.numpy())
+    # the dgCMatrix slots as R hands them over: ordinary pageable vectors (@p widened to int64 by the glue)
+    hp = np.ascontiguousarray(m.indptr, dtype=np.int64)
+    hi = np.ascontiguousarray(m.indices, dtype=np.int32)
+    hx = np.ascontiguousarray(m.data, dtype=np.float64)
+    cut = [m.ncells * r // world for r in range(world + 1)]
+    c0, c1 = cut[rank], cut[rank + 1]
+    csc_dev = _lib.Csc.upload_range(ctx, m.ngenes, hp, hi, hx, c0, c1)         # this rank's cells, resident in HBM
 
     def barrier():
         ctx.sync()
@@ -274,59 +280,78 @@ def run_ours(a):
 
     info = {}
 
-    def step(csc, d2h):
-        t_dbg = time.perf_counter()
-        g = _lib.CGraph.from_csc(ctx, csc, feats, 7.0)
-        eng = mdist.CudaCGraphEngine(g)
-        mdist.cgraph_sharded(eng, a.K, 10, 3, rank, world, fetch_edges=False)
-        if d2h:
-            g.edges(out_np)
-        info["edges"] = g.n_edges
-        info["stats"] = g.knn_stats()
-        info["rows"] = g.rows
-        info["M"] = g.M
-        g.destroy()
-        if os.environ.get("MCB_BENCH_DEBUG"):
-            print(f"[debug] step wall {1e3 * (time.perf_counter() - t_dbg):.1f} ms", file=sys.stderr, flush=True)
+    def build(csc):
+        """device-resident matrix -> device-resident edge table of this rank's rows"""
+        if comm is None:
+            g = _lib.CGraph.from_csc(ctx, csc, feats, 7.0)
+            g.knn(a.K, 10)
+            g.mutual(3)
+            g.prune()
+        else:
+            g = comm.build_sharded(csc, c0, feats, a.K, 10, 3, 7.0)
+        info.update(edges_local=g.n_edges, stats=g.knn_stats(), rows=g.rows, M=g.M)
+        return g
 
-    def timed(n_steps, e2e):
+    def step_device():
+        build(csc_dev).destroy()
+
+    def step_e2e():
+        """host in -> host out through the call the R glue makes: mcb_cgraph_bknn (one device) or, one process per
+        device, upload of the rank's cell range + mcb_cgraph_build_sharded + mcb_cgraph_gather_edges to rank 0"""
+        if comm is None:
+            ne, _ = _lib.cgraph_bknn_oneshot(ctx, m.ngenes, hp, hi, hx, feats, a.K, 10, 3, 7.0, raw=True)
+            info["edges"] = ne
+        else:
+            csc = _lib.Csc.upload_range(ctx, m.ngenes, hp, hi, hx, c0, c1)
+            g = build(csc)
+            ne = comm.gather_edges(g, 0, raw=True)
+            if rank == 0:
+                info["edges"] = ne
+            g.destroy()
+            csc.free()
+
+    def timed(n_steps, fn):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
+        t0 = time.perf_counter()
         e0.record(stream)
         for _ in range(n_steps):
-            if e2e:
-                csc = _lib.Csc.upload_ptrs(ctx, m.ngenes, m.ncells, nnz, hp.data_ptr(), hi.data_ptr(), hx.data_ptr())
-                step(csc, True)
-                csc.free()
-            else:
-                step(csc_dev, False)
+            fn()
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        wall = (time.perf_counter() - t0) * 1e3
+        t = torch.tensor([e0.elapsed_time(e1), wall], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), _lib.launch_count() - l0
+        return float(t[0].item()), float(t[1].item()), _lib.launch_count() - l0
 
     for _ in range(a.warmup):
-        step(csc_dev, False)
+        step_device()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_total, launches = timed(a.steps, False)
+    ms_total, _, launches = timed(a.steps, step_device)
     clocks = sampler.stop() if rank == 0 else None
     # per-stage CUDA-event timings of one more (untimed) step, for the roofline of the dominant kernel
     ctx.set_option("profile", 1)
     ctx.timings_reset()
-    step(csc_dev, False)
+    step_device()
     stages = ctx.timings()
+    ctx.timings_reset()
     ctx.set_option("profile", 0)
-    # end to end through host buffers
-    timed(1, True)
-    ms_e2e, _ = timed(max(1, a.steps), True)
+    # end to end through host buffers (the one-shot call; the host wall clock is reported beside the device time because
+    # the staging threads work before the first and after the last device operation)
+    for _ in range(2):
+        step_e2e()
     n_e2e = max(1, a.steps)
+    ms_e2e_dev, ms_e2e_wall, _ = timed(n_e2e, step_e2e)
+    ctx.set_option("profile", 1)
+    step_e2e()
+    stages_e2e = ctx.timings()
+    ctx.set_option("profile", 0)
 
+    line = None
     if rank == 0:
         peaks = {}
         try:
@@ -335,104 +360,190 @@ def run_ours(a):
             pass
         ms_step = ms_total / a.steps
         value = a.cells / (ms_step * 1e-3)
-        e2e_v = a.cells / (ms_e2e / n_e2e * 1e-3)
+        ms_e2e = max(ms_e2e_dev, ms_e2e_wall) / n_e2e
+        e2e_v = a.cells / (ms_e2e * 1e-3)
         gemm_ms, _ = stages.get("cor_filter_gemm", (float("nan"), 0))
         M, rows = info["M"], info["rows"]
         flop = 2.0 * rows * M * a.genes                      # algorithmic: fp32-equivalent, unpadded G, this rank's rows
         achieved = flop / (gemm_ms * 1e-3) / 1e12
         bf16 = peaks.get("bf16_tflops_sustained")
         peak = bf16 if bf16 else 1400.0
+        tr = _ncu_traffic(a, M) or {}
         roof = {"bound": "tensor", "kernel": "tc_cor2_kernel<SYM> (tcgen05 cta_group::2 kind::f16, 3-pass hi/lo split of z*2^12, fp32 accumulate, fused top-Kc filter)",
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": (_ncu_traffic(a, M) or {}).get("bytes"), "traffic_unit": "bytes of DRAM read + written per launch (ncu --set full)",
-                "traffic_source": (_ncu_traffic(a, M) or {}).get("source"),
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": tr.get("bytes"),
+                "traffic_unit": "bytes of DRAM read + written per launch (ncu --set full)", "traffic_source": tr.get("source"),
                 "issued_tflops": 3.0 * achieved * (-(-a.genes // 64) * 64) / a.genes * 0.5 * (1.0 + 256.0 / max(M, 256)),
                 "ms_per_launch": gemm_ms, "share_of_step": gemm_ms / ms_step,
                 "peak_source": ("bf16_tflops_sustained of MEASURED_PEAKS.json (kind::f16 runs at the bf16 rate; kernel timed inside a long step)"
                                 if bf16 else "1400 TFLOP/s sustained fallback (B200_PROFILING.md)"),
                 "note": "algorithmic flop = 2*rows*M*G (full square, fp32-equivalent); 3 passes are issued per pair and the symmetric schedule contracts each unordered pair once (across all ranks), so issued = 1.5x algorithmic"}
+        h2d = int(hp.nbytes + hi.nbytes + hx.nbytes)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f16x3 split (fp32-equivalent, fp32 accumulate); int32/uint64 index work", "data": "synthetic",
                 "config": {"workload": workload_name(a), "l2": "inputs larger than L2 (Z planes 0.8 GB, candidate buffers 1.6 GB)",
-                           "parallelism": f"symmetric tile list and rows sharded over {world} rank(s); exchanges: thresholds + kNN lists + in-degree cuts (all-gather), candidate records (all-to-all)", "valid_cells": M, "edges": info["edges"],
-                           "knn_filter": info["stats"]},
-                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(hp.numel() * 8 + hi.numel() * 4 + hx.numel() * 8),
-                        "d2h_bytes_per_step": int(info["edges"] * 16), "ms_per_step": ms_e2e / n_e2e},
+                           "parallelism": (f"one process per GPU, NCCL inside libmcb200.so: cells (ingest), symmetric tile list and rows sharded over {world} rank(s); "
+                                           "exchanges: feature planes + thresholds + kNN lists + in-degree cuts (all-gather), candidate records (all-to-all), edges (gather to rank 0 in e2e)"),
+                           "valid_cells": M, "edges": info.get("edges"), "knn_filter": info["stats"]},
+                "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int((info.get("edges") or 0) * 16),
+                        "ms_per_step": ms_e2e, "ms_per_step_device_events": ms_e2e_dev / n_e2e, "ms_per_step_host_wall": ms_e2e_wall / n_e2e,
+                        "call": ("mcb_cgraph_bknn(host dgCMatrix slots, pageable) -> host (mc1, mc2, w)" if world == 1 else
+                                 "per rank: mcb_csc_upload_range(pageable) + mcb_cgraph_build_sharded + mcb_cgraph_gather_edges -> host table on rank 0"),
+                        "bytes_note": "h2d / d2h are the caller-side bytes (dgCMatrix slots in, 16 B per edge out); the library narrows them on the way "
+                                      "(staging.cu): ~4 B per stored entry up, ~4 B per edge down",
+                        "stages_ms": _stage_dict(stages_e2e)},
                 "gpu_launches": launches, "clocks": clocks,
-                "stages_ms": {k: round(v[0], 3) for k, v in stages.items()}, "roofline": roof}
+                "stages_ms": _stage_dict(stages), "roofline": roof}
         if world == 1 and not a.no_cpu:
             cb, _, _ = cpu_port(a, m, feats, a.cpu_rows)
             line["cpu_baseline"] = cb
-        if world == 1 and not a.no_parity:
-            g = _lib.CGraph.from_csc(ctx, csc_dev, feats, 7.0)
+    # in-bench parity of this very workload (untimed): rank 0's rows against the fp64 oracle
+    if not a.no_parity:
+        g = build(csc_dev)
+        if rank == 0:
             cells = g.valid_cells()
-            g.knn(a.K, 10)
             col, cor = g.download_knn()
-            g.mutual(3)
-            g.prune()
             src, dst, w = g.edges()
-            g.destroy()
-            line["parity"] = parity_block(a, m, feats, cells, col, cor, src, dst, w)
+            line["parity"] = parity_block(a, m, feats, cells, col, cor, src, dst, w, row0=0)
             del col, cor
-    coc = None if a.no_coclust else bench_coclust(ctx, a, rank, world)
+        g.destroy()
+    csc_dev.free()
+    if not a.no_coclust:
+        subs = bench_sub_records(ctx, comm, a, rank, world, peaks if rank == 0 else {})
+        if rank == 0:
+            line.update(subs)
     if rank == 0:
-        if coc is not None:
-            line["coclust"] = coc
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        comm.close()
         dist.destroy_process_group()
 
 
-def bench_coclust(ctx, a, rank=0, world=1):
-    """C3: PBMC8k-shaped graph (8,000 cells, K=100), 500 resamples at p=0.75, min_mc_size=20.  At world > 1 the
-    resamples are strided over the ranks and the counters are reduced to rank 0 over NCCL."""
+def _timed_call(ctx, fn, rank, world):
+    """one call, device events on the context's stream + host wall, max over ranks"""
     import torch
     import torch.distributed as dist
-    from metacell_b200 import _lib, synth
-    from metacell_b200 import dist as mdist
-    m = synth.make_umi_matrix(8000, 600, n_types=12, median_umis=3000.0, seed=a.seed + 5)
-    csc = _lib.Csc.upload(ctx, m.ngenes, m.indptr, m.indices, m.data.astype(np.float64))
-    g = _lib.CGraph.from_csc(ctx, csc, np.arange(600, dtype=np.int32), 7.0)
-    g.knn(100, 10); g.mutual(3); g.prune()
-    src, dst, w = g.edges()
-    g.destroy(); csc.free()
-    sets, seeds = synth.resample_sets(m.ncells, 0.75, 500, 77)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=ctx.device)
-
-    def run():
-        cc = _lib.CoClust(ctx, m.ncells, src, dst, w, sets, seeds, 20, 1.05, 10, rank=rank, nranks=world)
-        out = mdist.coclust_sharded(cc, rank, world)
-        return cc, out
-
-    warm, _ = run()                      # warm-up at the timed shape (block cache, NCCL buffers)
-    warm.destroy()
-    if rank == 0:
-        ctx.set_option("profile", 1); ctx.timings_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ctx.sync(); torch.cuda.synchronize()
     if world > 1:
         dist.barrier(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
     e0.record(stream)
-    cc, out = run()
+    out = fn()
     e1.record(stream); ctx.sync(); torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier(); torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    wall = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e0.elapsed_time(e1), wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    res = None
+    return out, max(float(t[0].item()), float(t[1].item()))
+
+
+def _coclust_call(ctx, comm, N, src, dst, w, sets, seeds, min_size, rank, world, knn=0):
+    from metacell_b200 import _lib
+    cc = _lib.CoClust(ctx, N, src, dst, w, sets, seeds, min_size, 1.05, 10, rank=rank, nranks=world, knn=knn)
+    if comm is not None:
+        comm.coclust_reduce(cc, 0)
+    out = cc.pairs() if rank == 0 else None
+    return cc, out
+
+
+def bench_sub_records(ctx, comm, a, rank, world, peaks):
+    """The other BASELINE configs as named sub-records (host in -> host out, each with its own roofline statement):
+      C1  PBMC8k-shaped cgraph with down-sampling (8,000 cells x 4,000 genes, 600 feature genes, K = 100), N = 1 only
+      C3  500 co-clustering resamples of the C1 graph, p = 0.75, min_mc_size = 20 (resamples strided over the ranks)
+      C5  Amphimedon-shaped: 20,000 low-UMI cells, K = 150 cgraph + 1,000 resamples end to end"""
+    import torch.distributed as dist
+    from metacell_b200 import _lib, synth
+    hbm = peaks.get("hbm_gbs") or 6650.0
+    out = {}
+
+    def graph_of(name):
+        m, feats, prm = synth.config(name)
+        x = m.data.astype(np.float64)
+        call = lambda: _lib.cgraph_bknn_oneshot(ctx, m.ngenes, m.indptr, m.indices, x, feats, prm["K"], 10, 3, 7.0, dsamp=prm["dsamp"], seed=42)
+        call()                                           # warm-up at the timed shape
+        ctx.set_option("profile", 1); ctx.timings_reset()
+        (src, dst, w, nv), ms = _timed_call(ctx, call, 0, 1)
+        st = ctx.timings(); ctx.timings_reset(); ctx.set_option("profile", 0)
+        return m, prm, (src, dst, w), nv, ms, st
+
+    def bcast_graph(N, g):
+        """rank 0's edge table to every rank (launcher channel; untimed input distribution)"""
+        import torch
+        if world == 1:
+            return g
+        n = torch.tensor([g[0].size if rank == 0 else 0], device="cuda")
+        dist.broadcast(n, 0)
+        ts = [torch.zeros(int(n), dtype=t, device="cuda") for t in (torch.int32, torch.int32, torch.float64)]
+        if rank == 0:
+            ts = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in g]
+        for t in ts:
+            dist.broadcast(t, 0)
+        return tuple(t.cpu().numpy() for t in ts)
+
+    def coclust_record(name, N, g, n_resamp, min_size, K):
+        sets, seeds = synth.resample_sets(N, 0.75, n_resamp, 77)
+        warm, _ = _coclust_call(ctx, comm, N, *g, sets, seeds, min_size, rank, world)
+        warm.destroy()
+        if rank == 0:
+            ctx.set_option("profile", 1); ctx.timings_reset()
+        (cc, res), ms = _timed_call(ctx, lambda: _coclust_call(ctx, comm, N, *g, sets, seeds, min_size, rank, world), rank, world)
+        rec = None
+        if rank == 0:
+            st = ctx.timings(); ctx.timings_reset(); ctx.set_option("profile", 0)
+            _, sweeps = cc.assignments()
+            cover_ms = st.get("graph_cover", (float("nan"), 0))[0]
+            visits = float(np.sum(sweeps)) * sets.shape[1] * world          # rank 0's resamples stand for all (strided)
+            edge_bytes = visits * (K + 3 * K) * 8.0 / max(world, 1)           # packed int2 edges of every visited node, this rank
+            rec = {"metric": "coclust resamples/sec", "value": n_resamp / (ms * 1e-3), "unit": "resamples/s", "ms": ms, "n_gpus": world,
+                   "config": {"workload": name, "edges": int(g[0].size), "pairs": int(res[0].size), "mean_sweeps_rank0": float(np.mean(sweeps))},
+                   "stages_ms_rank0": _stage_dict(st),
+                   "roofline": {"bound": "latency (neither HBM nor tensor roofline binds: sequential Gauss-Seidel sweeps, SURVEY 8d)",
+                                "node_visits_per_s": visits / (ms * 1e-3), "achieved": edge_bytes / (cover_ms * 1e-3) / 1e9, "peak": hbm,
+                                "unit": "GB/s", "frac": edge_bytes / (cover_ms * 1e-3) / 1e9 / hbm,
+                                "note": "achieved = edge bytes touched by this rank's node visits / graph_cover kernel time (served from L2, not HBM)"},
+                   "note": "host edge table in, host (node1, node2, cnt) out on rank 0; counters reduced with NCCL inside the library"}
+        cc.destroy()
+        return rec
+
+    # ---- C1 + C3
+    g1 = None
     if rank == 0:
-        st = ctx.timings(); ctx.set_option("profile", 0)
-        _, sweeps = cc.assignments()
-        res = {"metric": "coclust resamples/sec", "value": 500.0 / (ms * 1e-3), "unit": "resamples/s", "ms": ms, "n_gpus": world,
-               "config": {"workload": "C3: 8,000 cells, balanced K=100 graph, 500 resamples, p=0.75, min_mc_size=20",
-                          "edges": int(src.size), "pairs": int(out[0].size), "mean_sweeps_rank0": float(np.mean(sweeps))},
-               "stages_ms_rank0": {k: round(v[0], 3) for k, v in st.items()},
-               "note": "host edge table in, host (node1,node2,cnt) out on rank 0; graph cover is latency-bound (DESIGN.md)"}
-    cc.destroy()
-    return res
+        m1, prm1, g1, nv1, ms1, st1 = graph_of("C1")
+        ds_ms = st1.get("downsample", (float("nan"), 0))[0]
+        out["C1"] = {"metric": METRIC, "value": m1.ncells / (ms1 * 1e-3), "unit": UNIT, "ms": ms1, "n_gpus": 1,
+                     "config": {"workload": "C1: 8,000 cells x 4,000 gene rows, 600 feature genes, downsample + bknn cgraph K=100 (mcb_cgraph_bknn, host in -> host out)",
+                                "nnz": m1.nnz, "valid_cells": nv1, "edges": int(g1[0].size)},
+                     "stages_ms": _stage_dict(st1),
+                     "roofline": {"bound": "hbm", "kernel": "downsample_kernel", "achieved": m1.nnz * 24.0 / (ds_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                  "frac": m1.nnz * 24.0 / (ds_ms * 1e-3) / 1e9 / hbm, "ms_per_launch": ds_ms,
+                                  "note": "algorithmic bytes = nnz_in*12 + nnz_out*12 (SURVEY 8d); the kernel regenerates Philox keys per radix pass and is ALU-bound at this size"}}
+    g1 = bcast_graph(8000, g1)
+    rec = coclust_record("C3: 8,000 cells, balanced K=100 graph, 500 resamples, p=0.75, min_mc_size=20", 8000, g1, 500, 20, 100)
+    if rank == 0:
+        out["C3"] = rec
+        out["coclust"] = rec                                  # the key round 1 used
+    # ---- C5
+    g5 = None
+    if rank == 0:
+        m5, prm5, g5, nv5, ms5, st5 = graph_of("C5")
+        gemm5 = st5.get("cor_filter_gemm", (float("nan"), 0))[0]
+        flop5 = 2.0 * nv5 * nv5 * 800
+        tf = peaks.get("bf16_tflops_sustained") or 1400.0
+        out["C5"] = {"cgraph": {"metric": "cells/sec for balanced K=150 cgraph build", "value": m5.ncells / (ms5 * 1e-3), "unit": UNIT, "ms": ms5, "n_gpus": 1,
+                                "config": {"workload": "C5: 20,000 low-UMI cells x 3,000 gene rows, 800 feature genes, bknn cgraph K=150, no downsampling (host in -> host out)",
+                                           "valid_cells": nv5, "edges": int(g5[0].size)},
+                                "stages_ms": _stage_dict(st5),
+                                "roofline": {"bound": "tensor", "kernel": "tc_cor2_kernel<SYM>", "achieved": flop5 / (gemm5 * 1e-3) / 1e12, "peak": tf, "unit": "TFLOP/s",
+                                             "frac": flop5 / (gemm5 * 1e-3) / 1e12 / tf, "ms_per_launch": gemm5}}}
+    g5 = bcast_graph(20000, g5)
+    rec = coclust_record("C5: 20,000 cells, balanced K=150 graph, 1,000 resamples, p=0.75, min_mc_size=20", 20000, g5, 1000, 20, 150)
+    if rank == 0:
+        out["C5"]["coclust"] = rec
+        out["C5"]["end_to_end_ms"] = out["C5"]["cgraph"]["ms"] + rec["ms"]
+    return out
 
 
 if __name__ == "__main__":
