@@ -201,7 +201,46 @@ extern "C" int mcb_ctx_timings_reset(mcb_ctx* ctx)
     ctx->agg.clear();
     MCB_API_END
 }
-extern "C" void mcb_free(void* p) { free(p); }
+// ---- host result blocks: malloc + a bounded cache of freed blocks ------------------------------------------------
+namespace {
+struct HostPool {
+    std::mutex mu;
+    std::map<void*, size_t> live;                 // blocks handed out by host_alloc
+    std::multimap<size_t, void*> idle;            // freed blocks, by size
+    size_t idle_bytes = 0;
+    static constexpr size_t CAP = (size_t)4 << 30;
+    ~HostPool() { for (auto& kv : idle) free(kv.second); }
+};
+HostPool g_host_pool;
+}  // namespace
+void* mcb::host_alloc(size_t bytes)
+{
+    const size_t sz = (std::max<size_t>(bytes, 1) + 4095) & ~(size_t)4095;
+    std::lock_guard<std::mutex> lk(g_host_pool.mu);
+    auto it = g_host_pool.idle.lower_bound(sz);
+    void* p = nullptr;
+    size_t got = sz;
+    if (it != g_host_pool.idle.end() && it->first <= sz + sz / 4) {       // close enough in size: reuse (pages already mapped)
+        p = it->second; got = it->first;
+        g_host_pool.idle_bytes -= got;
+        g_host_pool.idle.erase(it);
+    } else if (posix_memalign(&p, 4096, sz) != 0) p = nullptr;
+    if (!p) throw std::bad_alloc();
+    g_host_pool.live[p] = got;
+    return p;
+}
+extern "C" void mcb_free(void* p)
+{
+    if (!p) return;
+    std::unique_lock<std::mutex> lk(g_host_pool.mu);
+    auto it = g_host_pool.live.find(p);
+    if (it == g_host_pool.live.end()) { lk.unlock(); free(p); return; }
+    const size_t sz = it->second;
+    g_host_pool.live.erase(it);
+    if (g_host_pool.idle_bytes + sz <= HostPool::CAP) { g_host_pool.idle.emplace(sz, p); g_host_pool.idle_bytes += sz; return; }
+    lk.unlock();
+    free(p);
+}
 
 // ---------------------------------------------------------------------------------------------
 // A1: scm_which_downsamp_n (reference R/scmat.r:399-407): R quantile type 7 + round-half-even
@@ -1284,10 +1323,9 @@ extern "C" int mcb_cgraph_bknn(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, con
         BknnJob j{ngenes, ncells, 0, ncells, p, i, x, feat_rows, G, K, k_expand, k_beta, k_nonz, dsamp, seed};
         g = bknn_rank(ctx, nullptr, j);
         const int64_t ne = g->n_edges;
-        hs = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
-        hd = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
-        hw = (double*)malloc(sizeof(double) * (size_t)std::max<int64_t>(ne, 1));
-        if (!hs || !hd || !hw) throw std::bad_alloc();
+        hs = (int32_t*)host_alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
+        hd = (int32_t*)host_alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
+        hw = (double*)host_alloc(sizeof(double) * (size_t)std::max<int64_t>(ne, 1));
         cgraph_edges_to_host(g, hs, hd, hw);
         *n_edges = ne; *src = hs; *dst = hd; *w = hw;
         if (n_valid_cells) *n_valid_cells = g->M;
@@ -1297,7 +1335,7 @@ extern "C" int mcb_cgraph_bknn(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, con
     catch (const std::bad_alloc&) { mcb::set_error("host out of memory"); rc = 3; }
     catch (const std::exception& e) { mcb::set_error(e.what()); rc = 4; }
     catch (...) { mcb::set_error("unknown error"); rc = 5; }
-    free(hs); free(hd); free(hw);
+    mcb_free(hs); mcb_free(hd); mcb_free(hw);
     mcb_cgraph_destroy(g);
     return rc;
 }
@@ -1360,11 +1398,10 @@ extern "C" int mcb_cgraph_gather_edges(mcb_comm* comm, mcb_cgraph* g, int32_t ro
         if (n_edges_total) *n_edges_total = ne;
         if (is_root) {
             MCB_CHECK(src && dst && w, "mcb_cgraph_gather_edges: null output on root");
-            hs = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
-            hd = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
-            hw = (double*)malloc(sizeof(double) * (size_t)std::max<int64_t>(ne, 1));
-            if (!hs || !hd || !hw) throw std::bad_alloc();
-            StageTimer t(ctx, "d2h_edges", 0);
+            hs = (int32_t*)host_alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
+            hd = (int32_t*)host_alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(ne, 1));
+            hw = (double*)host_alloc(sizeof(double) * (size_t)std::max<int64_t>(ne, 1));
+                StageTimer t(ctx, "d2h_edges", 0);
             staged_download_edges(ctx, nr, g->K, ne, deg_all.p, cell_all.p, dst_all.p, hs, hd, hw);
             *src = hs; *dst = hd; *w = hw;
             hs = nullptr; hd = nullptr; hw = nullptr;
@@ -1379,7 +1416,7 @@ extern "C" int mcb_cgraph_gather_edges(mcb_comm* comm, mcb_cgraph* g, int32_t ro
     catch (const std::bad_alloc&) { mcb::set_error("host out of memory"); rc = 3; }
     catch (const std::exception& e) { mcb::set_error(e.what()); rc = 4; }
     catch (...) { mcb::set_error("unknown error"); rc = 5; }
-    free(hs); free(hd); free(hw);
+    mcb_free(hs); mcb_free(hd); mcb_free(hw);
     return rc;
 }
 

@@ -106,6 +106,11 @@ struct StageTimer {
     ~StageTimer();
 };
 
+// api.cu: library-allocated host results (released by the caller with mcb_free).  Freed blocks are kept in a small
+// process-wide cache, so a caller that repeats a call gets pages that are already mapped (first-touch page faults of a
+// fresh 150 MB result cost more than its PCIe transfer).
+void* host_alloc(size_t bytes);
+
 // staging.cu: pinned-ring transfers of the large host objects (see the header comment there)
 Staging* ctx_staging(mcb_ctx* ctx);
 void ctx_staging_destroy(mcb_ctx* ctx);

@@ -136,8 +136,13 @@ extern "C" int mcb_multi_create(const int32_t* devices, int32_t ndev, mcb_multi*
         m->comm.assign((size_t)ndev, nullptr);
         m->err.assign((size_t)ndev, std::string());
         m->err_code.assign((size_t)ndev, 0);
-        for (int r = 0; r < ndev; ++r)
+        for (int r = 0; r < ndev; ++r) {
             if (mcb_ctx_create(m->devices[r], &m->ctx[r])) throw Error(2, mcb_last_error());
+            if (!getenv("MCB_HOST_THREADS")) {                        // the devices of a session share the host's cores
+                const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+                m->ctx[r]->host_threads = (int)std::max(2u, std::min(16u, hw / (unsigned)ndev));
+            }
+        }
         std::vector<void*> raw((size_t)ndev, nullptr);
         if (ndev > 1) comm_init_all(ndev, m->devices.data(), raw.data());
         for (int r = 0; r < ndev; ++r) {
@@ -216,10 +221,9 @@ extern "C" int mcb_cgraph_bknn_multi(mcb_multi* m, int32_t ngenes, int64_t ncell
                 if (!hs) {
                     total = 0;
                     for (int q = 0; q < P; ++q) total += ne[q];
-                    hs = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(total, 1));
-                    hd = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(total, 1));
-                    hw = (double*)malloc(sizeof(double) * (size_t)std::max<int64_t>(total, 1));
-                    if (!hs || !hd || !hw) throw std::bad_alloc();
+                    hs = (int32_t*)host_alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(total, 1));
+                    hd = (int32_t*)host_alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(total, 1));
+                    hw = (double*)host_alloc(sizeof(double) * (size_t)std::max<int64_t>(total, 1));
                 }
             }
             int64_t off = 0;
@@ -234,7 +238,7 @@ extern "C" int mcb_cgraph_bknn_multi(mcb_multi* m, int32_t ngenes, int64_t ncell
     catch (const std::bad_alloc&) { mcb::set_error("host out of memory"); rc = 3; }
     catch (const std::exception& e) { mcb::set_error(e.what()); rc = 4; }
     catch (...) { mcb::set_error("unknown error"); rc = 5; }
-    free(hs); free(hd); free(hw);
+    mcb_free(hs); mcb_free(hd); mcb_free(hw);
     return rc;
 }
 
@@ -264,11 +268,10 @@ extern "C" int mcb_coclust_multi(mcb_multi* m, int32_t N, int64_t n_edges, const
             if (r == 0) {
                 int64_t np = 0;
                 if (mcb_coclust_extract(c[0], &np)) throw Error(2, mcb_last_error());
-                h1 = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(np, 1));
-                h2 = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(np, 1));
-                hc = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int64_t>(np, 1));
-                hn = (int32_t*)malloc(sizeof(int32_t) * (size_t)std::max<int32_t>(N, 1));
-                if (!h1 || !h2 || !hc || !hn) throw std::bad_alloc();
+                h1 = (int32_t*)host_alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(np, 1));
+                h2 = (int32_t*)host_alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(np, 1));
+                hc = (int32_t*)host_alloc(sizeof(int32_t) * (size_t)std::max<int64_t>(np, 1));
+                hn = (int32_t*)host_alloc(sizeof(int32_t) * (size_t)std::max<int32_t>(N, 1));
                 if (mcb_coclust_pairs(c[0], h1, h2, hc, hn)) throw Error(2, mcb_last_error());
                 *n_pairs = np;
             }
@@ -280,6 +283,6 @@ extern "C" int mcb_coclust_multi(mcb_multi* m, int32_t N, int64_t n_edges, const
     catch (const std::bad_alloc&) { mcb::set_error("host out of memory"); rc = 3; }
     catch (const std::exception& e) { mcb::set_error(e.what()); rc = 4; }
     catch (...) { mcb::set_error("unknown error"); rc = 5; }
-    free(h1); free(h2); free(hc); free(hn);
+    mcb_free(h1); mcb_free(h2); mcb_free(hc); mcb_free(hn);
     return rc;
 }

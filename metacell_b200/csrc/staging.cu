@@ -12,6 +12,7 @@
 //       mc1 (runs of the source id) and w = 1 - place/K (a function of the position in the run)   16 B -> ~4 B per edge
 // A small kernel widens the narrowed arrays on the device (HBM-bound, ~0.1 ms at C2).
 #include "internal.h"
+#include "narrow.h"
 #include <condition_variable>
 #include <cstring>
 #include <functional>
@@ -110,8 +111,11 @@ struct Staging {
 static int default_host_threads()
 {
     if (const char* e = getenv("MCB_HOST_THREADS")) { const int v = atoi(e); if (v >= 1) return std::min(v, 64); }
-    const unsigned hw = std::thread::hardware_concurrency();
-    return (int)std::max(2u, std::min(16u, hw ? hw / 2 : 4u));
+    unsigned hw = std::thread::hardware_concurrency();
+    if (!hw) hw = 4;
+    // one process per device on the same host (torchrun, mpirun): share the cores
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) { const int v = atoi(e); if (v > 1) hw = std::max(2u, hw / (unsigned)v); }
+    return (int)std::max(2u, std::min(16u, hw));
 }
 
 Staging* ctx_staging(mcb_ctx* ctx)
@@ -140,32 +144,32 @@ void ctx_staging_destroy(mcb_ctx* ctx)
     ctx->staging = nullptr;
 }
 
-// Generic staged host -> device pipeline.  The job is cut into chunks; fill(chunk, slot_ptr) writes the chunk's
-// narrowed bytes into a pinned slot and returns their count; dst(chunk) is where they go on the device.  Waves of
-// `wave` chunks are filled in parallel while the copy engine drains the previous wave.  The copies run on the
-// staging stream; on return the context's stream has been made to wait for them.
-static void staged_h2d(mcb_ctx* ctx, int64_t nchunks, const std::function<size_t(int64_t, char*)>& fill,
-                       const std::function<char*(int64_t)>& dst)
+// Generic staged host -> device pipeline.  The job is cut into chunks handed out dynamically; every host thread owns
+// two pinned slots and alternates between them: while the copy engine drains one, the thread fills the other.
+// work(chunk, slot_ptr, copy_stream) fills the slot and enqueues its own cudaMemcpyAsync calls on the copy stream.
+// On return the context's stream has been made to wait for every copy.
+static void staged_h2d(mcb_ctx* ctx, int64_t nchunks, const std::function<void(int64_t, char*, cudaStream_t)>& work)
 {
     Staging* st = ctx_staging(ctx);
     // the destinations come from the context's block cache, whose reuse is ordered on ctx->stream only: the copy
     // stream must not run ahead of work already queued there
     MCB_CUDA(cudaEventRecord(st->done, ctx->stream));
     MCB_CUDA(cudaStreamWaitEvent(st->copy, st->done, 0));
-    std::vector<size_t> bytes((size_t)st->wave);
-    int half = 0;
-    for (int64_t c0 = 0; c0 < nchunks; c0 += st->wave, half ^= 1) {
-        const int n = (int)std::min<int64_t>(st->wave, nchunks - c0);
-        const int s0 = half * st->wave;
-        st->workers->parallel_for(n, [&](int q) {
-            MCB_CUDA(cudaEventSynchronize(st->ev[s0 + q]));           // the slot's previous copy has left
-            bytes[q] = fill(c0 + q, st->slot[s0 + q]);
-        });
-        for (int q = 0; q < n; ++q) {
-            if (bytes[q]) MCB_CUDA(cudaMemcpyAsync(dst(c0 + q), st->slot[s0 + q], bytes[q], cudaMemcpyHostToDevice, st->copy));
-            MCB_CUDA(cudaEventRecord(st->ev[s0 + q], st->copy));
+    std::atomic<int64_t> next{0};
+    const int nt = (int)std::min<int64_t>(st->wave, nchunks);
+    st->workers->parallel_for(nt, [&](int t) {
+        MCB_CUDA(cudaSetDevice(ctx->device));
+        int flip = 0;
+        for (;;) {
+            const int64_t c = next.fetch_add(1);
+            if (c >= nchunks) break;
+            const int s = 2 * t + flip;
+            flip ^= 1;
+            MCB_CUDA(cudaEventSynchronize(st->ev[s]));           // the slot's previous copy has left
+            work(c, st->slot[s], st->copy);
+            MCB_CUDA(cudaEventRecord(st->ev[s], st->copy));
         }
-    }
+    });
     MCB_CUDA(cudaEventRecord(st->done, st->copy));
     MCB_CUDA(cudaStreamWaitEvent(ctx->stream, st->done, 0));
 }
@@ -234,87 +238,64 @@ void staged_upload_csc(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64
                        int64_t* d_p, int32_t* d_i, uint32_t* d_x)
 {
     const int64_t base = p[0], nnz = p[ncells] - base;
+    Staging* st = ctx_staging(ctx);
     // ---- @p: as is (8 B per cell), rebased on the device
     {
-        const int64_t per = (int64_t)(Staging::SLOT / sizeof(int64_t)), n = ncells + 1;
-        staged_h2d(ctx, ceil_div(n, per),
-                   [&](int64_t c, char* s) { const int64_t a = c * per, b = std::min(n, a + per); memcpy(s, p + a, (size_t)(b - a) * 8); return (size_t)(b - a) * 8; },
-                   [&](int64_t c) { return (char*)(d_p + c * per); });
+        const int64_t n = ncells + 1;
+        MCB_CUDA(cudaEventRecord(st->done, ctx->stream));
+        MCB_CUDA(cudaStreamWaitEvent(st->copy, st->done, 0));
+        MCB_CUDA(cudaMemcpyAsync(d_p, p, (size_t)n * 8, cudaMemcpyHostToDevice, st->copy));    // small: the driver's own staging
+        MCB_CUDA(cudaEventRecord(st->done, st->copy));
+        MCB_CUDA(cudaStreamWaitEvent(ctx->stream, st->done, 0));
         if (base) {
             rebase_p_kernel<<<(int)std::min<int64_t>(ceil_div(n, 256), 1024), 256, 0, ctx->stream>>>(d_p, n, base);
             MCB_LAUNCH_CHECK();
         }
     }
     if (nnz == 0) return;
-    const int64_t per = (int64_t)(Staging::SLOT / sizeof(uint16_t));        // entries per chunk (2 B each)
+    // ---- @i and @x in one pass over the stored entries.  A slot holds, for E entries, the narrowed counts (2 B each)
+    // followed by the narrowed (2 B) or plain (4 B) row indices.
+    const bool rows16 = ngenes <= 65536;
+    const int64_t per = (int64_t)(Staging::SLOT / (rows16 ? 4 : 6)) & ~(int64_t)63;
     const int64_t nchunks = ceil_div(nnz, per);
-    // ---- @i
-    if (ngenes <= 65536) {
-        DevBuf<uint16_t> n16(ctx, (size_t)nnz);
-        staged_h2d(ctx, nchunks,
-                   [&](int64_t c, char* s) {
-                       const int64_t a = c * per, b = std::min(nnz, a + per);
-                       const int32_t* src = i + base + a;
-                       uint16_t* o = (uint16_t*)s;
-                       int bad = 0;
-                       for (int64_t q = 0; q < b - a; ++q) { const int32_t v = src[q]; bad |= (v < 0) | (v > 65535); o[q] = (uint16_t)v; }
-                       if (bad) throw Error(1, "MC-ERR: mcb_csc_upload: gene row index out of range");
-                       return (size_t)(b - a) * 2;
-                   },
-                   [&](int64_t c) { return (char*)(n16.p + c * per); });
-        widen_u16_kernel<<<(int)std::min<int64_t>(ceil_div(nnz, 2048), (int64_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(n16.p, (uint32_t*)d_i, nnz);
-        MCB_LAUNCH_CHECK();
-    } else {
-        const int64_t per4 = (int64_t)(Staging::SLOT / sizeof(int32_t));
-        staged_h2d(ctx, ceil_div(nnz, per4),
-                   [&](int64_t c, char* s) { const int64_t a = c * per4, b = std::min(nnz, a + per4); memcpy(s, i + base + a, (size_t)(b - a) * 4); return (size_t)(b - a) * 4; },
-                   [&](int64_t c) { return (char*)(d_i + c * per4); });
-    }
-    // ---- @x: double -> uint16 with escapes, validated on the way
-    {
-        DevBuf<uint16_t> n16(ctx, (size_t)nnz);
-        std::mutex esc_mu;
-        std::vector<int64_t> esc_pos;
-        std::vector<uint32_t> esc_val;
-        staged_h2d(ctx, nchunks,
-                   [&](int64_t c, char* s) {
-                       const int64_t a = c * per, b = std::min(nnz, a + per);
-                       const double* src = x + base + a;
-                       uint16_t* o = (uint16_t*)s;
-                       // fast pass: branch-free narrowing; `big` collects every bit seen, `ok` the round-trip test
-                       uint64_t big = 0;
-                       bool ok = true;
-                       for (int64_t q = 0; q < b - a; ++q) {
-                           const double v = src[q];
-                           const int64_t t = (int64_t)v;                           // out-of-range / NaN -> INT64_MIN
-                           ok &= ((double)t == v);
-                           big |= (uint64_t)t;
-                           o[q] = (uint16_t)((uint64_t)t < 65535u ? t : 65535);
-                       }
-                       if (!ok || big >= 4294967296ull)                           // non-integral, NaN, negative or >= 2^32
-                           throw Error(1, "MC-ERR: mcb_csc_upload: counts must be non-negative integers below 2^32");
-                       if (big >= 65535u) {                                        // rare: escape the large counts
-                           for (int64_t q = 0; q < b - a; ++q) {
-                               if (o[q] != 65535u) continue;
-                               std::lock_guard<std::mutex> lk(esc_mu);
-                               esc_pos.push_back(a + q); esc_val.push_back((uint32_t)(int64_t)src[q]);
-                           }
-                       }
-                       return (size_t)(b - a) * 2;
-                   },
-                   [&](int64_t c) { return (char*)(n16.p + c * per); });
-        widen_u16_kernel<<<(int)std::min<int64_t>(ceil_div(nnz, 2048), (int64_t)ctx->num_sms * 8), 256, 0, ctx->stream>>>(n16.p, d_x, nnz);
-        MCB_LAUNCH_CHECK();
-        if (!esc_pos.empty()) {
-            const int64_t ne = (int64_t)esc_pos.size();
-            DevBuf<int64_t> dp(ctx, (size_t)ne);
-            DevBuf<uint32_t> dv(ctx, (size_t)ne);
-            MCB_CUDA(cudaMemcpyAsync(dp.p, esc_pos.data(), (size_t)ne * 8, cudaMemcpyHostToDevice, ctx->stream));
-            MCB_CUDA(cudaMemcpyAsync(dv.p, esc_val.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, ctx->stream));
-            patch_u32_kernel<<<(int)std::min<int64_t>(ceil_div(ne, 256), 1024), 256, 0, ctx->stream>>>(dp.p, dv.p, ne, d_x);
-            MCB_LAUNCH_CHECK();
-            MCB_CUDA(cudaStreamSynchronize(ctx->stream));                         // esc_* are pageable host vectors
+    DevBuf<uint16_t> x16(ctx, (size_t)nnz), i16(ctx, rows16 ? (size_t)nnz : 0);
+    std::mutex esc_mu;
+    std::vector<int64_t> esc_pos;
+    std::vector<uint32_t> esc_val;
+    staged_h2d(ctx, nchunks, [&](int64_t c, char* slot, cudaStream_t cs) {
+        const int64_t a = c * per, b = std::min(nnz, a + per), n = b - a;
+        uint16_t* ox = (uint16_t*)slot;
+        char* oi = slot + (size_t)per * 2;
+        const double* sx = x + base + a;
+        const int rc = narrow_counts_u16(sx, (size_t)n, ox);
+        if (rc == 2) throw Error(1, "MC-ERR: mcb_csc_upload: counts must be non-negative integers below 2^32");
+        if (rc == 1) {                                       // rare: counts >= 65535 travel in a patch list
+            std::lock_guard<std::mutex> lk(esc_mu);
+            for (int64_t q = 0; q < n; ++q)
+                if (ox[q] == 65535u) { esc_pos.push_back(a + q); esc_val.push_back((uint32_t)sx[q]); }
         }
+        MCB_CUDA(cudaMemcpyAsync(x16.p + a, ox, (size_t)n * 2, cudaMemcpyHostToDevice, cs));
+        if (rows16) {
+            if (narrow_rows_u16(i + base + a, (size_t)n, (uint16_t*)oi)) throw Error(1, "MC-ERR: mcb_csc_upload: gene row index out of range");
+            MCB_CUDA(cudaMemcpyAsync(i16.p + a, oi, (size_t)n * 2, cudaMemcpyHostToDevice, cs));
+        } else {
+            memcpy(oi, i + base + a, (size_t)n * 4);
+            MCB_CUDA(cudaMemcpyAsync(d_i + a, oi, (size_t)n * 4, cudaMemcpyHostToDevice, cs));
+        }
+    });
+    const int wgrid = (int)std::min<int64_t>(ceil_div(nnz, 2048), (int64_t)ctx->num_sms * 8);
+    widen_u16_kernel<<<wgrid, 256, 0, ctx->stream>>>(x16.p, d_x, nnz);
+    MCB_LAUNCH_CHECK();
+    if (rows16) { widen_u16_kernel<<<wgrid, 256, 0, ctx->stream>>>(i16.p, (uint32_t*)d_i, nnz); MCB_LAUNCH_CHECK(); }
+    if (!esc_pos.empty()) {
+        const int64_t ne = (int64_t)esc_pos.size();
+        DevBuf<int64_t> dp(ctx, (size_t)ne);
+        DevBuf<uint32_t> dv(ctx, (size_t)ne);
+        MCB_CUDA(cudaMemcpyAsync(dp.p, esc_pos.data(), (size_t)ne * 8, cudaMemcpyHostToDevice, ctx->stream));
+        MCB_CUDA(cudaMemcpyAsync(dv.p, esc_val.data(), (size_t)ne * 4, cudaMemcpyHostToDevice, ctx->stream));
+        patch_u32_kernel<<<(int)std::min<int64_t>(ceil_div(ne, 256), 1024), 256, 0, ctx->stream>>>(dp.p, dv.p, ne, d_x);
+        MCB_LAUNCH_CHECK();
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));                         // esc_* are pageable host vectors
     }
 }
 
@@ -338,45 +319,44 @@ void staged_download_edges(mcb_ctx* ctx, int64_t rows, int32_t K, int64_t ne, co
     std::vector<int64_t> offs((size_t)rows + 1, 0);
     for (int64_t r = 0; r < rows; ++r) offs[r + 1] = offs[r] + deg[r];
     MCB_CHECK(offs[rows] == ne, "edge table: degree sum does not match the edge count");
-    // mc1 and w depend on the degrees only: rebuilt by the host threads while the targets are in flight
-    const int nt = st->workers->size();
-    auto fill_src_w = [&](int part) {
-        const int64_t r0 = rows * part / nt, r1 = rows * (part + 1) / nt;
-        for (int64_t r = r0; r < r1; ++r) {
-            const int64_t o = offs[r];
-            const int32_t c = cell[r];
-            for (int32_t q = 0; q < deg[r]; ++q) {
-                if (host_src) host_src[o + q] = c;
-                if (host_w) host_w[o + q] = 1.0 - (double)q / (double)K;
+    const int64_t per = (int64_t)(Staging::SLOT / sizeof(int32_t));
+    const int64_t nchunks = (host_dst && ne) ? ceil_div(ne, per) : 0;
+    const int nt = st->wave;
+    std::atomic<int64_t> next{0};
+    st->workers->parallel_for(nt, [&](int t) {
+        MCB_CUDA(cudaSetDevice(ctx->device));
+        // every thread keeps up to two target chunks in flight (its two slots) ...
+        int64_t pend[2] = {-1, -1};
+        auto issue = [&](int sl) {
+            const int64_t c = next.fetch_add(1);
+            if (c >= nchunks) { pend[sl] = -1; return; }
+            const int64_t a = c * per, b = std::min(ne, a + per);
+            MCB_CUDA(cudaMemcpyAsync(st->slot[2 * t + sl], d_e_dst + a, (size_t)(b - a) * 4, cudaMemcpyDeviceToHost, st->copy));
+            MCB_CUDA(cudaEventRecord(st->ev[2 * t + sl], st->copy));
+            pend[sl] = c;
+        };
+        issue(0);
+        issue(1);
+        // ... and meanwhile rebuilds mc1 and w for its share of the rows: they depend on the degrees only
+        {
+            const int64_t r0 = rows * t / nt, r1 = rows * (t + 1) / nt;
+            for (int64_t r = r0; r < r1; ++r) {
+                const int64_t o = offs[r];
+                const int32_t c = cell[r];
+                const int32_t d = deg[r];
+                if (host_src) for (int32_t q = 0; q < d; ++q) host_src[o + q] = c;
+                if (host_w) for (int32_t q = 0; q < d; ++q) host_w[o + q] = 1.0 - (double)q / (double)K;
             }
         }
-    };
-    if (!host_dst || ne == 0) { st->workers->parallel_for(nt, fill_src_w); return; }
-    const int64_t per = (int64_t)(Staging::SLOT / sizeof(int32_t));
-    const int64_t nchunks = ceil_div(ne, per);
-    // issue the D2H copies in waves; drain wave w (memcpy into the caller's array) while wave w+1 is in flight
-    auto issue = [&](int64_t c0, int half) {
-        const int n = (int)std::min<int64_t>(st->wave, nchunks - c0);
-        for (int q = 0; q < n; ++q) {
-            const int64_t a = (c0 + q) * per, b = std::min(ne, a + per);
-            MCB_CUDA(cudaMemcpyAsync(st->slot[half * st->wave + q], d_e_dst + a, (size_t)(b - a) * 4, cudaMemcpyDeviceToHost, st->copy));
-            MCB_CUDA(cudaEventRecord(st->ev[half * st->wave + q], st->copy));
+        for (int sl = 0; pend[0] >= 0 || pend[1] >= 0; sl ^= 1) {
+            if (pend[sl] < 0) continue;
+            const int64_t a = pend[sl] * per, b = std::min(ne, a + per);
+            MCB_CUDA(cudaEventSynchronize(st->ev[2 * t + sl]));
+            memcpy(host_dst + a, st->slot[2 * t + sl], (size_t)(b - a) * 4);
+            issue(sl);
         }
-    };
-    issue(0, 0);
-    bool src_done = false;
-    int half = 0;
-    for (int64_t c0 = 0; c0 < nchunks; c0 += st->wave, half ^= 1) {
-        if (c0 + st->wave < nchunks) issue(c0 + st->wave, half ^ 1);
-        if (!src_done) { st->workers->parallel_for(nt, fill_src_w); src_done = true; }
-        const int n = (int)std::min<int64_t>(st->wave, nchunks - c0);
-        st->workers->parallel_for(n, [&](int q) {
-            const int64_t a = (c0 + q) * per, b = std::min(ne, a + per);
-            MCB_CUDA(cudaEventSynchronize(st->ev[half * st->wave + q]));
-            memcpy(host_dst + a, st->slot[half * st->wave + q], (size_t)(b - a) * 4);
-        });
-    }
-    // leave the ring's events signalled for the next user (they are: every recorded event was synchronised above)
+    });
+    // every recorded slot event was synchronised above: the ring is free for the next user
 }
 
 }  // namespace mcb

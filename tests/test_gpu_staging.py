@@ -91,9 +91,9 @@ def test_staged_edge_download_equals_device_table(ctx):
     _lib.check(_lib.lib().mcb_cgraph_edges_device(g.h, C.byref(n), C.byref(ps), C.byref(pd), C.byref(pw)))
     assert n.value == ne
     import torch
-    dev = [torch.empty(ne, dtype=t, device="cuda") for t in (torch.int32, torch.int32, torch.float64)]
-    for t, p, sz in zip(dev, (ps, pd, pw), (4, 4, 8)):
-        torch.cuda.cudart().cudaMemcpy(t.data_ptr(), p.value, ne * sz, 3)
+    from metacell_b200.dist import device_view
+    ctx.sync()
+    dev = [device_view(p.value, ne * sz, t, ctx.device) for t, p, sz in zip((torch.int32, torch.int32, torch.float64), (ps, pd, pw), (4, 4, 8))]
     assert np.array_equal(src, dev[0].cpu().numpy()) and np.array_equal(dst, dev[1].cpu().numpy()) and np.array_equal(w, dev[2].cpu().numpy())
     g.destroy()
 
