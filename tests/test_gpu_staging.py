@@ -134,17 +134,17 @@ def test_two_contexts_on_one_device_from_two_threads(oracle):
 
 
 def test_graph_cover_of_a_large_sparse_graph_needs_no_counter_matrix(ctx, oracle):
-    """tgs_graph_cover on 300,000 nodes (N*N counters would be 360 GB): a ring of small cliques"""
+    """tgs_graph_cover on 300,000 nodes (N*N counters would be 360 GB): disjoint cliques of 25 nodes"""
     from metacell_b200 import _lib
-    N, c = 300000, 6
+    N, c = 300000, 25
     base = (np.arange(N) // c) * c
     src = np.repeat(np.arange(N, dtype=np.int32), c - 1)
     offs = np.tile(np.arange(1, c), N)
     dst = (base.repeat(c - 1) + (np.arange(N).repeat(c - 1) % c + offs) % c).astype(np.int32)
-    w = np.tile(1.0 - np.arange(c - 1) / 8.0, N)
-    cluster, sweeps = _lib.graph_cover(ctx, N, src, dst, w, 3, 1.05, 10, 99)
+    w = np.tile(1.0 - np.arange(c - 1) / 32.0, N)
+    cluster, sweeps = _lib.graph_cover(ctx, N, src, dst, w, 20, 1.05, 10, 99)
     csr = oracle.graph_to_csr(N, src, dst, w)
-    omc, osw = oracle.graph_cover(N, csr, np.arange(N, dtype=np.int32), 3, 1.05, 10, 99)
+    omc, osw = oracle.graph_cover(N, csr, np.arange(N, dtype=np.int32), 20, 1.05, 10, 99)
     assert sweeps == osw and np.array_equal(cluster, np.where(omc < 0, 0, omc + 1))
     assert (cluster > 0).mean() > 0.99
     # every clique lands in one cluster
