@@ -88,9 +88,23 @@ tgs_graph_cover_resample = function(edges, knn, min_mc_size, cooling, burn_in, p
 	n_s = round(p_resamp * N)
 	samples = sapply(1:n_resamp, function(i) sort(sample.int(N, n_s)))            # n_s x n_resamp, ascending
 	seeds = floor(runif(n_resamp) * 2^52)
-	r = .Call("mcbr_coclust", N, as.integer(edges$col1), as.integer(edges$col2), as.numeric(edges$weight),
+	r = .Call("mcbr_coclust", N, as.integer(edges$col1), as.integer(edges$col2), as.numeric(edges$weight), as.integer(knn),
 	          samples, seeds, as.integer(min_mc_size), as.numeric(cooling), as.integer(burn_in), PACKAGE = "mcb200")
 	list(co_cluster = data.frame(node1 = factor(nodes[r$node1], levels = nodes),
 	                             node2 = factor(nodes[r$node2], levels = nodes), cnt = r$cnt),
 	     samples = r$samples)
 }
+
+# replaces tgstat's tgs_graph_cover at its two call sites, mcell_add_mc_from_graph (R/mc_graphcov.r:27) and
+# mcell_mc_from_coclust_balanced (R/mc_from_coclust.r:247): data.frame(node, cluster), cluster 0 = outlier (R/mc_graphcov.r:28)
+tgs_graph_cover = function(edges, min_mc_size, cooling, burn_in)
+{
+	nodes = levels(edges$col1)
+	cl = .Call("mcbr_graph_cover", length(nodes), as.integer(edges$col1), as.integer(edges$col2), as.numeric(edges$weight),
+	           as.integer(min_mc_size), as.numeric(cooling), as.integer(burn_in), floor(runif(1) * 2^52), PACKAGE = "mcb200")
+	data.frame(node = nodes, cluster = cl, stringsAsFactors = F)
+}
+
+# several B200s in the box: options(mcb200.devices = 0:7) before the first call; mcell_add_cgraph_from_mat_bknn and
+# tgs_graph_cover_resample then run on all of them (mcb_cgraph_bknn_multi / mcb_coclust_multi), nothing else changes
+.onUnload = function(libpath) .Call("mcbr_shutdown", PACKAGE = "mcb200")

@@ -17,14 +17,31 @@
 #include <stdlib.h>
 #include "mcb200.h"
 
-static mcb_ctx* g_ctx = NULL;
+/* One session per R process: a context + NCCL communicator + host thread for every device named by
+ * options(mcb200.devices = c(0, 1, ...)) (default: device 0 alone).  The R process stays single-threaded; the
+ * session's threads live inside the library and are joined before every call returns (SURVEY 8b "Threading"). */
+static mcb_multi* g_multi = NULL;
 
-static mcb_ctx* ctx(void)
+static mcb_multi* session(void)
 {
-    if (!g_ctx && mcb_ctx_create(0, &g_ctx) != 0) Rf_error("%s", mcb_last_error());
-    return g_ctx;
+    if (!g_multi) {
+        SEXP opt = GetOption1(install("mcb200.devices"));
+        int32_t dev[64] = {0}, n = 1;
+        if (!isNull(opt)) {
+            SEXP iv = PROTECT(coerceVector(opt, INTSXP));
+            n = 0;
+            for (R_xlen_t k = 0; k < XLENGTH(iv) && n < 64; ++k) dev[n++] = INTEGER(iv)[k];
+            UNPROTECT(1);
+        }
+        if (mcb_multi_create(dev, n, &g_multi) != 0) Rf_error("%s", mcb_last_error());
+    }
+    return g_multi;
 }
+static mcb_ctx* ctx(void) { return mcb_multi_ctx(session(), 0); }       /* single-device calls run on the first device */
 #define CHECK(call) do { if ((call) != 0) Rf_error("%s", mcb_last_error()); } while (0)
+
+/* called from .onUnload */
+SEXP mcbr_shutdown(void) { mcb_multi_destroy(g_multi); g_multi = NULL; return R_NilValue; }
 
 /* dgCMatrix@p is int32 in R; the ABI takes int64 column pointers */
 static int64_t* widen_p(SEXP p, R_xlen_t* ncells)
@@ -97,9 +114,10 @@ SEXP mcbr_cgraph_bknn(SEXP p, SEXP i, SEXP x, SEXP ngenes, SEXP feat_rows, SEXP 
     int64_t ne = 0, nvalid = 0;
     int32_t *src = NULL, *dst = NULL;
     double* w = NULL;
-    CHECK(mcb_cgraph_bknn(ctx(), asInteger(ngenes), (int64_t)ncells, p64, INTEGER(i), REAL(x), fr, (int32_t)G, asInteger(K),
-                          asInteger(k_expand), asInteger(k_beta), asReal(k_nonz), asLogical(dsamp), (uint64_t)asReal(seed),
-                          &ne, &src, &dst, &w, &nvalid));
+    /* every device of the session takes a cell range of the dgCMatrix and writes its own rows of the edge table */
+    CHECK(mcb_cgraph_bknn_multi(session(), asInteger(ngenes), (int64_t)ncells, p64, INTEGER(i), REAL(x), fr, (int32_t)G, asInteger(K),
+                                asInteger(k_expand), asInteger(k_beta), asReal(k_nonz), asLogical(dsamp), (uint64_t)asReal(seed),
+                                &ne, &src, &dst, &w, &nvalid));
     SEXP res = edges_to_list(ne, src, dst, w, nvalid);
     mcb_free(src); mcb_free(dst); mcb_free(w);
     return res;
@@ -197,9 +215,10 @@ SEXP mcbr_cor_knn_xy(SEXP x, SEXP y, SEXP knn)
     return res;
 }
 
-/* tgs_graph_cover_resample(..., method = "full") (reference R/coclust_graph_cov.r:41).
- * samples: integer matrix n_s x n_resamp (one resample per COLUMN, 1-based, ascending); seeds: numeric */
-SEXP mcbr_coclust(SEXP n_nodes, SEXP col1, SEXP col2, SEXP weight, SEXP samples, SEXP seeds, SEXP min_mc_size,
+/* tgs_graph_cover_resample(edges, knn, ..., method = "full") (reference R/coclust_graph_cov.r:41).
+ * samples: integer matrix n_s x n_resamp (one resample per COLUMN, 1-based, ascending); seeds: numeric.
+ * The resamples are strided over the session's devices and the counters reduced inside the library. */
+SEXP mcbr_coclust(SEXP n_nodes, SEXP col1, SEXP col2, SEXP weight, SEXP knn, SEXP samples, SEXP seeds, SEXP min_mc_size,
                   SEXP cooling, SEXP burn_in)
 {
     const int32_t N = asInteger(n_nodes);
@@ -213,19 +232,34 @@ SEXP mcbr_coclust(SEXP n_nodes, SEXP col1, SEXP col2, SEXP weight, SEXP samples,
     for (int64_t q = 0; q < (int64_t)n_s * n_resamp; ++q) smp[q] = INTEGER(samples)[q] - 1;     /* column-major == [n_resamp][n_s] */
     uint64_t* sd = (uint64_t*)R_alloc((size_t)n_resamp, sizeof(uint64_t));
     for (int32_t r = 0; r < n_resamp; ++r) sd[r] = (uint64_t)REAL(seeds)[r];
-    mcb_coclust* c = NULL;
-    CHECK(mcb_coclust_run(ctx(), N, ne, src, dst, REAL(weight), n_resamp, n_s, smp, sd, asInteger(min_mc_size), asReal(cooling),
-                          asInteger(burn_in), 1000, 0, 1, &c));
     int64_t np = 0;
-    if (mcb_coclust_extract(c, &np) != 0) { mcb_coclust_destroy(c); Rf_error("%s", mcb_last_error()); }
+    int32_t *h1 = NULL, *h2 = NULL, *hc = NULL, *hn = NULL;
+    CHECK(mcb_coclust_multi(session(), N, ne, src, dst, REAL(weight), n_resamp, n_s, smp, sd, asInteger(min_mc_size), asReal(cooling),
+                            asInteger(burn_in), 1000, asInteger(knn), &np, &h1, &h2, &hc, &hn));
     SEXP n1 = PROTECT(allocVector(INTSXP, np)), n2 = PROTECT(allocVector(INTSXP, np)), cnt = PROTECT(allocVector(INTSXP, np));
     SEXP ns = PROTECT(allocVector(INTSXP, N));
-    int rc = mcb_coclust_pairs(c, INTEGER(n1), INTEGER(n2), INTEGER(cnt), INTEGER(ns));
-    mcb_coclust_destroy(c);
-    if (rc) { UNPROTECT(4); Rf_error("%s", mcb_last_error()); }
-    for (int64_t q = 0; q < np; ++q) { INTEGER(n1)[q] += 1; INTEGER(n2)[q] += 1; }
+    for (int64_t q = 0; q < np; ++q) { INTEGER(n1)[q] = h1[q] + 1; INTEGER(n2)[q] = h2[q] + 1; INTEGER(cnt)[q] = hc[q]; }
+    for (int32_t v = 0; v < N; ++v) INTEGER(ns)[v] = hn[v];
+    mcb_free(h1); mcb_free(h2); mcb_free(hc); mcb_free(hn);
     SEXP res = PROTECT(mkNamed(VECSXP, (const char*[]){"node1", "node2", "cnt", "samples", ""}));
     SET_VECTOR_ELT(res, 0, n1); SET_VECTOR_ELT(res, 1, n2); SET_VECTOR_ELT(res, 2, cnt); SET_VECTOR_ELT(res, 3, ns);
     UNPROTECT(5);
     return res;
+}
+
+/* tgs_graph_cover(edges, min_mc_size, cooling, burn_in) (reference R/mc_graphcov.r:27, R/mc_from_coclust.r:247):
+ * one cover over all nodes; returns integer cluster per node, 0 = outlier (R/mc_graphcov.r:28) */
+SEXP mcbr_graph_cover(SEXP n_nodes, SEXP col1, SEXP col2, SEXP weight, SEXP min_mc_size, SEXP cooling, SEXP burn_in, SEXP seed)
+{
+    const int32_t N = asInteger(n_nodes);
+    const int64_t ne = XLENGTH(col1);
+    int32_t* src = (int32_t*)R_alloc((size_t)(ne ? ne : 1), sizeof(int32_t));
+    int32_t* dst = (int32_t*)R_alloc((size_t)(ne ? ne : 1), sizeof(int32_t));
+    for (int64_t e = 0; e < ne; ++e) { src[e] = INTEGER(col1)[e] - 1; dst[e] = INTEGER(col2)[e] - 1; }
+    SEXP cl = PROTECT(allocVector(INTSXP, N));
+    int32_t sweeps = 0;
+    if (mcb_graph_cover(ctx(), N, ne, src, dst, REAL(weight), asInteger(min_mc_size), asReal(cooling), asInteger(burn_in), 1000,
+                        (uint64_t)asReal(seed), INTEGER(cl), &sweeps) != 0) { UNPROTECT(1); Rf_error("%s", mcb_last_error()); }
+    UNPROTECT(1);
+    return cl;
 }

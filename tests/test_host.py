@@ -148,3 +148,19 @@ def test_mc_confusion_mat_host_logic(tmp_path):
     with pytest.raises(api.McbError, match="MC-ERR"):
         api.mcell_mc_confusion_mat("bad", "g", 2)
     assert api.mcell_mc_confusion_mat("bad", "g", 2, ignore_mismatch=True).size == 0
+
+
+def test_r_glue_type_checks_against_the_abi():
+    """r/mcb200_glue.c cannot be built here (no R headers), but every mcb_* call in it is type-checked against
+    include/mcb200.h by compiling it (-fsyntax-only) with declarations-only stubs of the R C API (tests/r_stub/)."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I" + os.path.join(root, "tests", "r_stub"),
+                        "-I" + os.path.join(root, "include"), os.path.join(root, "r", "mcb200_glue.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # every .Call target named in r/mcb200.R exists in the glue
+    glue = open(os.path.join(root, "r", "mcb200_glue.c")).read()
+    for name in set(re.findall(r'\.Call\("(mcbr_[a-z_]+)"', open(os.path.join(root, "r", "mcb200.R")).read())):
+        assert re.search(r"\bSEXP " + name + r"\(", glue), name
