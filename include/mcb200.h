@@ -102,31 +102,17 @@ void mcb_cgraph_destroy(mcb_cgraph* g);
 int  mcb_cgraph_num_valid(const mcb_cgraph* g, int64_t* M);
 int  mcb_cgraph_valid_cells(mcb_cgraph* g, int32_t* host_cell_of_row /* [M] */);
 int  mcb_cgraph_features(mcb_cgraph* g, float* host_z /* [M][G] */);      /* test / debug export */
-/* A5: tgs_cor_knn(x, y = x, knn = K*k_expand) for the rows owned by `rank` of `nranks`
- * (contiguous split of the M valid cells).  Self is rank 1 (R/atlas.r:475-476).                */
+/* A5: tgs_cor_knn(x, y = x, knn = K*k_expand).  Self is rank 1 (R/atlas.r:475-476).  rank / nranks: the contiguous
+ * split of the M valid cells whose rows this call ranks; a handle made by mcb_cgraph_create is a single-rank build
+ * (rank 0 of 1 -- or a row block against all columns, for the kNN lists alone); row-sharded graphs go through
+ * mcb_cgraph_build_sharded / mcb_cgraph_bknn_multi, which run the exchanges inside the library.              */
 int  mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks);
-/* Symmetric multi-GPU form of the same stage (every unordered cell pair is contracted once across all ranks):
- *   knn_begin        sampling pass, thresholds of the owned rows
- *   knn_thr_buffer   float [nranks * rows_per_rank] threshold buffer: all-gather it in place
- *   knn_filter       this rank's share of the symmetric tile list -> candidate records for rows of EVERY rank,
- *                    grouped by owner rank: *dev_send = uint4 records, send_counts[nranks] = records per owner
- *   knn_recv_buffer  room for the records this rank receives in the all-to-all
- *   knn_finish       bin the received records, rank them, exact rows; then continue as after mcb_cgraph_knn  */
-int  mcb_cgraph_knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks);
-int  mcb_cgraph_knn_thr_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank);
-int  mcb_cgraph_knn_filter(mcb_cgraph* g, void** dev_send, int64_t* send_counts /* [nranks] */);
-int  mcb_cgraph_knn_recv_buffer(mcb_cgraph* g, int64_t n_records, void** dev_recv);
-int  mcb_cgraph_knn_finish(mcb_cgraph* g, int64_t n_records);
-/* the full [nranks * rows_per_rank][Kc] int32 kNN column buffer on the device; this rank's block
- * starts at row rank * rows_per_rank.  The host plumbing all-gathers it in place (NCCL).       */
-int  mcb_cgraph_knn_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank, int32_t* Kc);
 int  mcb_cgraph_download_knn(mcb_cgraph* g, int32_t* host_col /* [rows][Kc] */, float* host_cor);
 int  mcb_cgraph_knn_stats(mcb_cgraph* g, int64_t* n_fallback_rows, int64_t* n_candidates, int32_t* cap,
                           int32_t* n_sample_cols);
-/* A6 step 1: mutual rank products + per-target in-degree cut (K*k_beta) for the owned rows.   */
+/* A6 step 1: mutual rank products + per-target in-degree cut (K*k_beta) for the owned rows.
+ * context option "join_impl": 0 = routed, L2-blocked join (default) | 1 = direct probing join (cross-check)   */
 int  mcb_cgraph_mutual(mcb_cgraph* g, int32_t k_beta);
-/* the full [nranks * rows_per_rank] uint64 in-degree threshold buffer (all-gathered in place)  */
-int  mcb_cgraph_thr_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank);
 /* A6 steps 2-4: out-degree cut (K) and weights 1 - (place-1)/K for the owned rows.             */
 int  mcb_cgraph_prune(mcb_cgraph* g, int64_t* n_edges);
 /* edges of the owned rows as (mc1, mc2, w) (R/cgraph_knn.r:22), original 0-based cell ids,

@@ -17,9 +17,9 @@ SYMBOLS = [
     "mcb_ctx_set_option", "mcb_ctx_timings", "mcb_ctx_timings_reset", "mcb_downsamp_depth", "mcb_csc_upload",
     "mcb_csc_wrap_device", "mcb_csc_free", "mcb_csc_col_sums", "mcb_csc_downsample", "mcb_csc_download",
     "mcb_cgraph_create", "mcb_cgraph_create_dense", "mcb_cgraph_destroy", "mcb_cgraph_num_valid",
-    "mcb_cgraph_valid_cells", "mcb_cgraph_features", "mcb_cgraph_knn", "mcb_cgraph_knn_begin", "mcb_cgraph_knn_thr_buffer",
-    "mcb_cgraph_knn_filter", "mcb_cgraph_knn_recv_buffer", "mcb_cgraph_knn_finish", "mcb_cgraph_knn_buffer",
-    "mcb_cgraph_download_knn", "mcb_cgraph_knn_stats", "mcb_cgraph_mutual", "mcb_cgraph_thr_buffer",
+    "mcb_cgraph_valid_cells", "mcb_cgraph_features", "mcb_cgraph_knn", 
+    
+    "mcb_cgraph_download_knn", "mcb_cgraph_knn_stats", "mcb_cgraph_mutual", 
     "mcb_cgraph_prune", "mcb_cgraph_edges", "mcb_cgraph_debug_cor", "mcb_cor_knn_xy", "mcb_gene_stats", "mcb_mc_gene_tapply", "mcb_cgraph_bknn", "mcb_free",
     "mcb_coclust_run", "mcb_graph_cover", "mcb_coclust_destroy", "mcb_coclust_buffers", "mcb_coclust_assignments",
     "mcb_coclust_extract", "mcb_coclust_pairs",
@@ -272,38 +272,6 @@ class CGraph:
         self.row0 = min(self.M, rank * self.rows_per_rank)
         self.rows = min(self.M, self.row0 + self.rows_per_rank) - self.row0
 
-    # staged form for the symmetric multi-GPU schedule (see metacell_b200/dist.py)
-    def knn_begin(self, K, k_expand=10, rank=0, nranks=1):
-        check(lib().mcb_cgraph_knn_begin(self.h, C.c_int32(K), C.c_int32(k_expand), C.c_int32(rank), C.c_int32(nranks)))
-        self._set_split(K, k_expand, rank, nranks)
-
-    def knn_thr_buffer(self):
-        p = C.c_void_p()
-        rpr = C.c_int64(0)
-        check(lib().mcb_cgraph_knn_thr_buffer(self.h, C.byref(p), C.byref(rpr)))
-        return p.value, int(rpr.value)
-
-    def knn_filter(self):
-        p = C.c_void_p()
-        counts = (C.c_int64 * self.nranks)()
-        check(lib().mcb_cgraph_knn_filter(self.h, C.byref(p), counts))
-        return p.value, [int(c) for c in counts]
-
-    def knn_recv_buffer(self, n):
-        p = C.c_void_p()
-        check(lib().mcb_cgraph_knn_recv_buffer(self.h, C.c_int64(n), C.byref(p)))
-        return p.value
-
-    def knn_finish(self, n):
-        check(lib().mcb_cgraph_knn_finish(self.h, C.c_int64(n)))
-
-    def knn_buffer(self):
-        p = C.c_void_p()
-        rpr = C.c_int64(0)
-        kc = C.c_int32(0)
-        check(lib().mcb_cgraph_knn_buffer(self.h, C.byref(p), C.byref(rpr), C.byref(kc)))
-        return p.value, int(rpr.value), int(kc.value)
-
     def download_knn(self):
         col = np.zeros((self.rows, self.Kc), dtype=np.int32)
         cor = np.zeros((self.rows, self.Kc), dtype=np.float32)
@@ -317,12 +285,6 @@ class CGraph:
 
     def mutual(self, k_beta=3):
         check(lib().mcb_cgraph_mutual(self.h, C.c_int32(k_beta)))
-
-    def thr_buffer(self):
-        p = C.c_void_p()
-        rpr = C.c_int64(0)
-        check(lib().mcb_cgraph_thr_buffer(self.h, C.byref(p), C.byref(rpr)))
-        return p.value, int(rpr.value)
 
     def prune(self):
         ne = C.c_int64(0)

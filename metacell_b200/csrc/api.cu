@@ -173,6 +173,7 @@ extern "C" int mcb_ctx_set_option(mcb_ctx* ctx, const char* key, int64_t value)
     else if (!strcmp(key, "keep_self")) ctx->keep_self = (int)value;
     else if (!strcmp(key, "thresh_strict")) ctx->thresh_strict = (int)value;
     else if (!strcmp(key, "cap_override")) ctx->cap_override = (int)value;
+    else if (!strcmp(key, "join_impl")) ctx->join_impl = (int)value;
     else if (!strcmp(key, "host_threads")) {
         MCB_CHECK(value >= 0 && value <= 64, "host_threads must be between 0 and 64");
         MCB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -762,7 +763,7 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
     g->rows = std::min<int64_t>(M, g->row0 + g->rows_per_rank) - g->row0;
     const int64_t rows = g->rows, row0 = g->row0;
     const int32_t Kc = g->Kc, kc_out = g->kc_out;
-    g->knn_col.alloc(ctx, (size_t)nranks * g->rows_per_rank * Kc);
+    g->knn_col.alloc(ctx, (size_t)std::max<int64_t>(rows, 1) * Kc);              // the rank's own rows
     g->knn_cor.alloc(ctx, (size_t)std::max<int64_t>(rows, 1) * Kc);
     g->thr_all.alloc(ctx, (size_t)nranks * g->rows_per_rank);
     // rows past M (padding of the last rank's block) never pass: +inf
@@ -915,7 +916,7 @@ static void knn_finish(mcb_cgraph* g, int64_t n_recv)
     }
     // ---- ranked lists -------------------------------------------------------------------------
     DevBuf<int32_t> fail(ctx, (size_t)rows), fail_list(ctx, (size_t)rows), n_fail_d(ctx, 1);
-    int32_t* own_col = g->knn_col.p + (size_t)row0 * Kc;
+    int32_t* own_col = g->knn_col.p;
     {
         StageTimer t(ctx, "topk_rows");
         launch_topk_rows(ctx, g->cand.p, g->cnt.p, cap, row0, rows, kc_out, Kc, own_col, g->knn_cor.p, fail.p);
@@ -991,7 +992,7 @@ void mcb::cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, i
     g->recv.alloc(ctx, std::max<size_t>(rrun, 1));
     { StageTimer t(ctx, "alltoall_records", 0); comm_alltoallv(comm, g->send.p, soff.data(), scnt.data(), g->recv.p, roff.data(), rcnt.data()); }
     knn_finish(g, (int64_t)rrun);
-    { StageTimer t(ctx, "allgather_knn", 0); comm_allgather_inplace(comm, g->knn_col.p, (size_t)g->rows_per_rank * g->Kc * sizeof(int32_t)); }
+    // the ranked lists stay with their owner: the balancing join routes records, not lists (cgraph_mutual)
 }
 
 extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks)
@@ -1001,61 +1002,6 @@ extern "C" int mcb_cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_
     cgraph_knn(g, K, k_expand, rank, nranks);
     MCB_API_END
 }
-// ---- staged form for the symmetric multi-GPU schedule (metacell_b200/dist.py shows the sequence) ------------------
-extern "C" int mcb_cgraph_knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, int32_t nranks)
-{
-    MCB_API_BEGIN
-    MCB_CHECK(g, "null argument");
-    MCB_CUDA(cudaSetDevice(g->ctx->device));
-    knn_begin(g, K, k_expand, rank, nranks);
-    MCB_API_END
-}
-extern "C" int mcb_cgraph_knn_thr_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank)
-{
-    MCB_API_BEGIN
-    MCB_CHECK(g && g->thr_all.p, "mcb_cgraph_knn_thr_buffer: run mcb_cgraph_knn_begin first");
-    if (dev_ptr) *dev_ptr = g->thr_all.p;
-    if (rows_per_rank) *rows_per_rank = g->rows_per_rank;
-    MCB_API_END
-}
-extern "C" int mcb_cgraph_knn_filter(mcb_cgraph* g, void** dev_send, int64_t* send_counts)
-{
-    MCB_API_BEGIN
-    MCB_CHECK(g && g->thr_all.p, "mcb_cgraph_knn_filter: run mcb_cgraph_knn_begin first");
-    MCB_CUDA(cudaSetDevice(g->ctx->device));
-    knn_filter(g, 1);
-    if (dev_send) *dev_send = g->send.p;
-    if (send_counts) for (int32_t r = 0; r < g->nranks; ++r) send_counts[r] = g->send_counts[r];
-    MCB_API_END
-}
-extern "C" int mcb_cgraph_knn_recv_buffer(mcb_cgraph* g, int64_t n_records, void** dev_recv)
-{
-    MCB_API_BEGIN
-    MCB_CHECK(g && dev_recv && n_records >= 0, "mcb_cgraph_knn_recv_buffer: bad argument");
-    MCB_CUDA(cudaSetDevice(g->ctx->device));
-    g->recv.alloc(g->ctx, (size_t)std::max<int64_t>(n_records, 1));
-    MCB_CUDA(cudaStreamSynchronize(g->ctx->stream));
-    *dev_recv = g->recv.p;
-    MCB_API_END
-}
-extern "C" int mcb_cgraph_knn_finish(mcb_cgraph* g, int64_t n_records)
-{
-    MCB_API_BEGIN
-    MCB_CHECK(g && g->cand.p, "mcb_cgraph_knn_finish: run mcb_cgraph_knn_filter first");
-    MCB_CUDA(cudaSetDevice(g->ctx->device));
-    knn_finish(g, n_records);
-    MCB_API_END
-}
-
-extern "C" int mcb_cgraph_knn_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank, int32_t* Kc)
-{
-    MCB_API_BEGIN
-    MCB_CHECK(g && g->knn_col.p, "mcb_cgraph_knn_buffer: run mcb_cgraph_knn first");
-    if (dev_ptr) *dev_ptr = g->knn_col.p;
-    if (rows_per_rank) *rows_per_rank = g->rows_per_rank;
-    if (Kc) *Kc = g->Kc;
-    MCB_API_END
-}
 extern "C" int mcb_cgraph_download_knn(mcb_cgraph* g, int32_t* host_col, float* host_cor)
 {
     MCB_API_BEGIN
@@ -1063,7 +1009,7 @@ extern "C" int mcb_cgraph_download_knn(mcb_cgraph* g, int32_t* host_col, float* 
     mcb_ctx* ctx = g->ctx;
     MCB_CUDA(cudaSetDevice(ctx->device));
     const size_t n = (size_t)g->rows * g->Kc;
-    if (host_col && n) MCB_CUDA(cudaMemcpyAsync(host_col, g->knn_col.p + (size_t)g->row0 * g->Kc, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (host_col && n) MCB_CUDA(cudaMemcpyAsync(host_col, g->knn_col.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (host_cor && n) MCB_CUDA(cudaMemcpyAsync(host_cor, g->knn_cor.p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
     MCB_API_END
@@ -1082,50 +1028,122 @@ extern "C" int mcb_cgraph_knn_stats(mcb_cgraph* g, int64_t* n_fallback_rows, int
 
 static int ilog2_ceil(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) ++l; return l; }
 
-// A6 step 1 for the owned rows; with a communicator the in-degree cuts of every row are all-gathered here
+// A6 step 1 for the owned rows: mutual scores s(i,j) = rank(i,j) * rank(j,i) and the per-target in-degree cut.
+// Routed join (balance.cu): every list entry becomes a record bucketed by (owner rank, row block) of its target; with a
+// communicator the buckets of other ranks travel in one all-to-all (the kNN lists themselves never leave their owner and
+// a rank builds rank tables for its own rows only); the probe pass then walks this rank's blocks one by one.  The
+// in-degree cuts (8 bytes per row) are all-gathered at the end.  Option "join_impl" = 1 selects the direct join (every
+// entry probes the table of its target row wherever it lies in memory), single rank only: the cross-check of the routed one.
 void mcb::cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
 {
     MCB_CHECK(g->knn_col.p, "mcb_cgraph_mutual: run mcb_cgraph_knn first");
     MCB_CHECK(k_beta >= 1, "MC-ERR: k_beta must be >= 1");
     mcb_ctx* ctx = g->ctx;
     MCB_CUDA(cudaSetDevice(ctx->device));
-    const int64_t M = g->M;
-    const int32_t Kc = g->Kc;
+    mcb_comm* comm = g->comm;
+    MCB_CHECK(comm || g->nranks == 1, "mcb_cgraph_mutual: a row-sharded build needs a communicator (mcb_cgraph_build_sharded)");
+    const int64_t M = g->M, rows = g->rows, row0 = g->row0;
+    const int32_t Kc = g->Kc, P = g->nranks;
     g->k_beta = k_beta;
     g->rank_bits = std::max(1, ilog2_ceil(Kc));
     int32_t H = 2; while (H < 2 * Kc) H <<= 1;
     g->H = H;
     MCB_CHECK(M < ((int64_t)1 << (32 - g->rank_bits)) - 1, "MC-ERR: too many cells for the packed rank table at this K * k_expand");
-    // drop the feature planes: they are not needed after the kNN stage and the table is large
+    const int64_t smax = (int64_t)g->K * g->K * g->k_expand;
+    // drop the feature planes: they are not needed after the kNN stage and the tables are large
     g->Zf.release(); g->Zh.release(); g->Zl.release();
-    DevBuf<uint32_t> table(ctx, (size_t)M * H);
-    g->sym.alloc(ctx, (size_t)std::max<int64_t>(g->rows, 1) * Kc);
-    g->thr_in.alloc(ctx, (size_t)g->nranks * g->rows_per_rank);
+    const size_t rows1 = (size_t)std::max<int64_t>(rows, 1);
+    g->sym.alloc(ctx, rows1 * Kc);
+    g->thr_in.alloc(ctx, (size_t)P * g->rows_per_rank);
+    DevBuf<uint32_t> table(ctx, rows1 * H);
     {
         StageTimer t(ctx, "balance_hash");
-        launch_build_hash(ctx, g->knn_col.p, M, Kc, H, g->rank_bits, table.p);
+        launch_build_hash(ctx, g->knn_col.p, rows, Kc, H, g->rank_bits, table.p);        // own rows only
+    }
+    if (ctx->join_impl == 1 && P == 1) {
+        StageTimer t(ctx, "balance_mutual");
+        launch_mutual(ctx, g->knn_col.p, table.p, row0, rows, Kc, H, g->rank_bits, smax, ctx->thresh_strict, ctx->keep_self,
+                      g->K * k_beta, g->sym.p, g->thr_in.p, /*have_scores=*/0);
+        return;
+    }
+    const RouteShape rs = route_shape(ctx, g->rows_per_rank, P, H, g->rank_bits);
+    DevBuf<uint32_t> counts(ctx, (size_t)rs.grid * rs.nbuckets);
+    DevBuf<int64_t> btotal(ctx, (size_t)rs.nbuckets), bstart(ctx, (size_t)rs.nbuckets + 1);
+    DevBuf<uint64_t> records(ctx, rows1 * Kc);
+    {
+        StageTimer t(ctx, "balance_route", 4);
+        launch_route_records(ctx, g->knn_col.p, row0, rows, Kc, g->rows_per_rank, rs, g->rank_bits, ctx->keep_self, counts.p, btotal.p,
+                             bstart.p, records.p);
+    }
+    g->sym.zero();
+    const int32_t nbr = rs.nbr;
+    if (!comm) {
+        // one rank: the buckets are the blocks, already in visiting order
+        DevBuf<int32_t> seg_block(ctx, (size_t)nbr);
+        launch_iota_i32(ctx, seg_block.p, nbr);
+        StageTimer t(ctx, "balance_probe");
+        launch_probe(ctx, records.p, (int64_t)rows * Kc, bstart.p, bstart.p, seg_block.p, nbr, rs.blk_shift, table.p, H, g->rank_bits, Kc,
+                     smax, ctx->thresh_strict, g->sym.p);
+        // (n_records is an upper bound: the prefix ends at the true count, positions past it fall in no segment)
+    } else {
+        // bucket totals of every rank -> who sends how much to whom, and where each (sender, block) piece lands here
+        std::vector<int64_t> mine((size_t)rs.nbuckets);
+        MCB_CUDA(cudaMemcpyAsync(mine.data(), btotal.p, sizeof(int64_t) * mine.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        const std::vector<int64_t> all = comm_allgather_i64v(comm, mine.data(), rs.nbuckets);          // [sender][bucket]
+        const int me = comm->rank;
+        std::vector<size_t> soff((size_t)P), scnt((size_t)P), roff((size_t)P), rcnt((size_t)P);
+        size_t srun = 0, rrun = 0;
+        for (int r = 0; r < P; ++r) {
+            size_t to_r = 0, from_r = 0;
+            for (int b = 0; b < nbr; ++b) { to_r += (size_t)mine[(size_t)r * nbr + b]; from_r += (size_t)all[(size_t)r * rs.nbuckets + (size_t)me * nbr + b]; }
+            soff[r] = srun * 8; scnt[r] = to_r * 8; srun += to_r;
+            roff[r] = rrun * 8; rcnt[r] = from_r * 8; rrun += from_r;
+        }
+        DevBuf<uint64_t> recv(ctx, std::max<size_t>(rrun, 1));
+        { StageTimer t(ctx, "alltoall_join_records", 0); comm_alltoallv(comm, records.p, soff.data(), scnt.data(), recv.p, roff.data(), rcnt.data()); }
+        records.release();
+        // visiting order: block-major, the P senders' pieces of a block one after the other
+        const int32_t nseg = nbr * P;
+        std::vector<int64_t> h_prefix((size_t)nseg + 1), h_src((size_t)nseg);
+        std::vector<int32_t> h_blk((size_t)nseg);
+        std::vector<size_t> piece((size_t)P);
+        for (int r = 0; r < P; ++r) piece[r] = roff[r] / 8;
+        int64_t run = 0;
+        // pieces of sender r are laid out by ascending block inside its contribution: walk the blocks and advance each sender's cursor
+        for (int b = 0; b < nbr; ++b)
+            for (int r = 0; r < P; ++r) {
+                const int q = b * P + r;
+                const int64_t c = all[(size_t)r * rs.nbuckets + (size_t)me * nbr + b];
+                h_prefix[q] = run; h_src[q] = (int64_t)piece[r]; h_blk[q] = b;
+                run += c; piece[r] += (size_t)c;
+            }
+        h_prefix[nseg] = run;
+        DevBuf<int64_t> seg_prefix(ctx, (size_t)nseg + 1), seg_src(ctx, (size_t)nseg);
+        DevBuf<int32_t> seg_block(ctx, (size_t)nseg);
+        MCB_CUDA(cudaMemcpyAsync(seg_prefix.p, h_prefix.data(), sizeof(int64_t) * h_prefix.size(), cudaMemcpyHostToDevice, ctx->stream));
+        MCB_CUDA(cudaMemcpyAsync(seg_src.p, h_src.data(), sizeof(int64_t) * h_src.size(), cudaMemcpyHostToDevice, ctx->stream));
+        MCB_CUDA(cudaMemcpyAsync(seg_block.p, h_blk.data(), sizeof(int32_t) * h_blk.size(), cudaMemcpyHostToDevice, ctx->stream));
+        {
+            StageTimer t(ctx, "balance_probe");
+            launch_probe(ctx, recv.p, run, seg_prefix.p, seg_src.p, seg_block.p, nseg, rs.blk_shift, table.p, H, g->rank_bits, Kc, smax,
+                         ctx->thresh_strict, g->sym.p);
+        }
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));          // the segment tables above are pageable host vectors
     }
     {
-        StageTimer t(ctx, "balance_mutual");
-        launch_mutual(ctx, g->knn_col.p, table.p, g->row0, g->rows, Kc, H, g->rank_bits,
-                      (int64_t)g->K * g->K * g->k_expand, ctx->thresh_strict, ctx->keep_self, g->K * k_beta, g->sym.p, g->thr_in.p);
+        StageTimer t(ctx, "balance_cut");
+        launch_mutual(ctx, g->knn_col.p, table.p, row0, rows, Kc, H, g->rank_bits, smax, ctx->thresh_strict, ctx->keep_self, g->K * k_beta,
+                      g->sym.p, g->thr_in.p, /*have_scores=*/1);
     }
-    if (g->comm) { StageTimer t(ctx, "allgather_cuts", 0); comm_allgather_inplace(g->comm, g->thr_in.p, (size_t)g->rows_per_rank * sizeof(uint64_t)); }
-    // the table is released in stream order
+    if (comm) { StageTimer t(ctx, "allgather_cuts", 0); comm_allgather_inplace(comm, g->thr_in.p, (size_t)g->rows_per_rank * sizeof(uint64_t)); }
+    // temporaries are released in stream order
 }
 extern "C" int mcb_cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
 {
     MCB_API_BEGIN
     MCB_CHECK(g, "null argument");
     cgraph_mutual(g, k_beta);
-    MCB_API_END
-}
-extern "C" int mcb_cgraph_thr_buffer(mcb_cgraph* g, void** dev_ptr, int64_t* rows_per_rank)
-{
-    MCB_API_BEGIN
-    MCB_CHECK(g && g->thr_in.p, "mcb_cgraph_thr_buffer: run mcb_cgraph_mutual first");
-    if (dev_ptr) *dev_ptr = g->thr_in.p;
-    if (rows_per_rank) *rows_per_rank = g->rows_per_rank;
     MCB_API_END
 }
 int64_t mcb::cgraph_prune(mcb_cgraph* g)

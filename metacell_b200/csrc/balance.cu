@@ -10,8 +10,15 @@
 //
 // Data layout: the reverse rank rank(j,i) is found through a per-row open-addressing hash table
 // (H = 2^k >= 2*Kc slots of u32 = (column << rank_bits) | rank0) instead of a binary search or a
-// global sort, so the join costs ~1.5 random 32-byte sectors per edge.  All kernels are one CTA per
-// row with the row's keys sorted in shared memory; HBM-bound integer work.
+// global sort.  The join is ROUTED (route_* / probe_kernel below): every list entry (i -> j, rank r) becomes an
+// 8-byte record that is bucketed by the block of ~2K rows that holds j; the probe pass then walks the records
+// block by block, so the 16 MB slice of tables it probes -- and the slice of the score array it writes -- stay in
+// L2 and every table atom is read from HBM once (the direct join read one 64-byte DRAM atom per probe: 11.5 GB for
+// 10^8 probes at C2, profiles/r2a_ncu_stages.csv).  The score is symmetric, s(i,j) = s(j,i), so the probe of row j's
+// table by the record of (i -> j) is recorded in ROW j's score array at position rank(j,i): results land at the
+// owner of the probed table and nothing travels back.  Across ranks the same bucketing is the exchange: a rank
+// only ever needs the tables of its own rows, and the records (not the whole kNN lists) cross NVLink once.
+// Selection kernels are one CTA per row with the row's keys in registers; HBM-bound integer work.
 #include "internal.h"
 
 namespace mcb {
@@ -70,13 +77,132 @@ __device__ __forceinline__ uint32_t hash_lookup(const uint32_t* __restrict__ tab
     return 0u;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// routed join
+// ---------------------------------------------------------------------------------------------------------------
+// Bucket of a target row j: (owner rank, block of `blk` rows inside the owner's row range).
+struct RouteGeom {
+    int64_t rows_per_rank;      // contiguous row split of the M valid rows over the ranks
+    int32_t blk_shift;          // block = 2^blk_shift rows
+    int32_t nbr;                // blocks per rank = ceil(rows_per_rank / blk)
+    int32_t nbuckets;           // nranks * nbr
+    int32_t rank_bits;
+};
+__device__ __forceinline__ int32_t route_bucket(const RouteGeom& g, int32_t j, uint32_t& jl)
+{
+    const int32_t owner = (int32_t)(j / g.rows_per_rank);
+    const int32_t lrow = (int32_t)(j - owner * g.rows_per_rank);
+    jl = (uint32_t)lrow & ((1u << g.blk_shift) - 1u);
+    return owner * g.nbr + (lrow >> g.blk_shift);
+}
+constexpr int ROUTE_THREADS = 256;
+
+// pass 1: counts[cta][bucket] = entries of the CTA's rows that go to `bucket`.  Every CTA owns a contiguous chunk of
+// the rank's rows (the same chunk in pass 2); the histogram lives in shared memory.
+__global__ void __launch_bounds__(ROUTE_THREADS)
+route_count_kernel(const int32_t* __restrict__ knn_col, int64_t row0, int64_t rows, int32_t Kc, RouteGeom geo, int keep_self,
+                   uint32_t* __restrict__ counts)
+{
+    extern __shared__ uint32_t hist[];      // [nbuckets]
+    for (int q = threadIdx.x; q < geo.nbuckets; q += ROUTE_THREADS) hist[q] = 0;
+    __syncthreads();
+    const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(rows, r0 + per);
+    for (int64_t e = r0 * Kc + threadIdx.x; e < r1 * Kc; e += ROUTE_THREADS) {
+        const int32_t j = knn_col[e];
+        if (j < 0) continue;
+        if (!keep_self && j == (int32_t)(row0 + e / Kc)) continue;
+        uint32_t jl;
+        atomicAdd(&hist[route_bucket(geo, j, jl)], 1u);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < geo.nbuckets; q += ROUTE_THREADS) counts[(int64_t)blockIdx.x * geo.nbuckets + q] = hist[q];
+}
+// per bucket: exclusive prefix of the CTAs' counts (in place) and the bucket total
+__global__ void route_offsets_kernel(uint32_t* __restrict__ counts, int32_t nctas, int32_t nbuckets, int64_t* __restrict__ total)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbuckets) return;
+    uint32_t run = 0;
+    for (int c = 0; c < nctas; ++c) { const uint32_t v = counts[(int64_t)c * nbuckets + b]; counts[(int64_t)c * nbuckets + b] = run; run += v; }
+    total[b] = run;
+}
+// pass 2: records[bucket_start[b] + within[cta][b] + k] = (source row i : 32 | row of j inside its block : * | rank0 : rank_bits)
+__global__ void __launch_bounds__(ROUTE_THREADS)
+route_scatter_kernel(const int32_t* __restrict__ knn_col, int64_t row0, int64_t rows, int32_t Kc, RouteGeom geo, int keep_self,
+                     const uint32_t* __restrict__ within, const int64_t* __restrict__ bucket_start, uint64_t* __restrict__ records)
+{
+    extern __shared__ long long rbase[];                // [nbuckets] first slot of this CTA in each bucket's stream
+    uint32_t* cursor = reinterpret_cast<uint32_t*>(rbase + geo.nbuckets);      // [nbuckets] entries written so far
+    for (int q = threadIdx.x; q < geo.nbuckets; q += ROUTE_THREADS) {
+        rbase[q] = bucket_start[q] + (long long)within[(int64_t)blockIdx.x * geo.nbuckets + q];
+        cursor[q] = 0;
+    }
+    __syncthreads();
+    const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+    const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(rows, r0 + per);
+    for (int64_t e = r0 * Kc + threadIdx.x; e < r1 * Kc; e += ROUTE_THREADS) {
+        const int32_t j = knn_col[e];
+        if (j < 0) continue;
+        const int64_t lrow = e / Kc;
+        const uint32_t r = (uint32_t)(e - lrow * Kc);
+        const uint32_t i = (uint32_t)(row0 + lrow);
+        if (!keep_self && j == (int32_t)i) continue;
+        uint32_t jl;
+        const int32_t b = route_bucket(geo, j, jl);
+        const long long pos = rbase[b] + (long long)atomicAdd(&cursor[b], 1u);
+        records[pos] = ((uint64_t)i << 32) | (uint64_t)((jl << geo.rank_bits) | r);
+    }
+}
+
+// probe pass.  The records of this rank's blocks are visited block by block: segment q covers positions
+// [seg_prefix[q], seg_prefix[q+1]) of the visiting order, lives at records + seg_src[q] and belongs to local block
+// seg_block[q].  For record (i -> j, r): if i sits at rank r' of j's list and s = (r+1)(r'+1) passes the threshold,
+// sym[j][r'] = s  (the score of j's own entry for i -- s is symmetric).
+__global__ void __launch_bounds__(256)
+probe_kernel(const uint64_t* __restrict__ records, int64_t n_records, const int64_t* __restrict__ seg_prefix,
+             const int64_t* __restrict__ seg_src, const int32_t* __restrict__ seg_block, int32_t nseg, int32_t blk_shift,
+             const uint32_t* __restrict__ table, int32_t H, int32_t log2H, int32_t rank_bits, int32_t Kc, long long smax, int strict,
+             uint32_t* __restrict__ sym)
+{
+    extern __shared__ long long sp[];      // [nseg + 1] prefix, then seg_src [nseg], then seg_block as long long [nseg]
+    long long* ssrc = sp + nseg + 1;
+    long long* sblk = ssrc + nseg;
+    for (int q = threadIdx.x; q <= nseg; q += 256) sp[q] = seg_prefix[q];
+    for (int q = threadIdx.x; q < nseg; q += 256) { ssrc[q] = seg_src[q]; sblk[q] = seg_block[q]; }
+    __syncthreads();
+    const uint32_t rmask = (1u << rank_bits) - 1u;
+    if (sp[nseg] < n_records) n_records = sp[nseg];          // the prefix ends at the true record count
+    int lo = 0;                             // segment of the thread's current position: positions only move forward
+    {
+        const int64_t v0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+        int hi = nseg;
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sp[mid] <= v0) lo = mid; else hi = mid; }
+    }
+    for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < n_records; v += (int64_t)gridDim.x * 256) {
+        while (lo + 1 < nseg && sp[lo + 1] <= v) ++lo;
+        const uint64_t rec = records[ssrc[lo] + (v - sp[lo])];
+        const uint32_t i = (uint32_t)(rec >> 32), w = (uint32_t)rec;
+        const int64_t jrow = ((int64_t)sblk[lo] << blk_shift) + (w >> rank_bits);          // row of j among the rank's own rows
+        const uint32_t rji = hash_lookup(table + jrow * H, H, log2H, rank_bits, i);          // 1-based, 0 = absent
+        if (rji) {
+            const long long s = (long long)((w & rmask) + 1u) * (long long)rji;
+            if (strict ? (s < smax) : (s <= smax)) sym[jrow * Kc + (rji - 1u)] = (uint32_t)s;
+        }
+    }
+}
+
 // mutual scores s(i, r) and the in-degree threshold of every owned row
 template <int IPT>      // 256 * IPT >= Kc keys sorted per row, register resident
 __global__ void __launch_bounds__(BAL_THREADS, IPT <= 4 ? 4 : 1)
 mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ table, int64_t row0, int64_t rows,
               int32_t Kc, int32_t H, int32_t log2H, int32_t rank_bits, long long smax, int strict, int keep_self,
-              int32_t kin, uint32_t* __restrict__ sym, uint64_t* __restrict__ thr_in)
+              int32_t kin, uint32_t* __restrict__ sym, uint64_t* __restrict__ thr_in, int have_scores)
 {
+    // have_scores: sym already holds the scores (routed join); otherwise they are computed here by probing the
+    // tables of ALL rows (direct join, single rank only; kept as the cross-check of the routed one).
+    // knn_col holds the rank's own rows (row lrow of the buffer = global row row0 + lrow).
     extern __shared__ uint64_t sk[];        // [256 * IPT]
     __shared__ uint32_t hist[BAL_BINS];
     __shared__ int s_n, s_sel, s_bin, s_before;
@@ -84,7 +210,7 @@ mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ 
     while ((smax >> bin_shift) >= BAL_BINS) ++bin_shift;
     for (int64_t lrow = blockIdx.x; lrow < rows; lrow += gridDim.x) {
         const int64_t i = row0 + lrow;
-        const int32_t* kc = knn_col + i * (int64_t)Kc;
+        const int32_t* kc = knn_col + lrow * (int64_t)Kc;
         uint32_t* so = sym + lrow * (int64_t)Kc;
         uint64_t key[IPT];
 #pragma unroll
@@ -94,15 +220,20 @@ mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ 
             if (r < Kc) {
                 const int32_t j = kc[r];
                 uint32_t sv = 0;
-                if (j >= 0 && (j != (int32_t)i || keep_self)) {
-                    const uint32_t rji = (j == (int32_t)i) ? (uint32_t)(r + 1)
-                                                           : hash_lookup(table + (int64_t)j * H, H, log2H, rank_bits, (uint32_t)i);
-                    if (rji) {
-                        const long long s = (long long)(r + 1) * (long long)rji;
-                        if (strict ? (s < smax) : (s <= smax)) { sv = (uint32_t)s; kv = ((uint64_t)s << 32) | (uint32_t)j; }
+                if (have_scores) {
+                    sv = so[r];
+                    if (sv) kv = ((uint64_t)sv << 32) | (uint32_t)j;
+                } else {
+                    if (j >= 0 && (j != (int32_t)i || keep_self)) {
+                        const uint32_t rji = (j == (int32_t)i) ? (uint32_t)(r + 1)
+                                                               : hash_lookup(table + (int64_t)j * H, H, log2H, rank_bits, (uint32_t)i);
+                        if (rji) {
+                            const long long s = (long long)(r + 1) * (long long)rji;
+                            if (strict ? (s < smax) : (s <= smax)) { sv = (uint32_t)s; kv = ((uint64_t)s << 32) | (uint32_t)j; }
+                        }
                     }
+                    so[r] = sv;
                 }
-                so[r] = sv;
             }
             key[q] = kv;
         }
@@ -164,7 +295,7 @@ prune_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ s
     while ((smax >> bin_shift) >= BAL_BINS) ++bin_shift;
     for (int64_t lrow = blockIdx.x; lrow < rows; lrow += gridDim.x) {
         const int64_t i = row0 + lrow;
-        const int32_t* kc = knn_col + i * (int64_t)Kc;
+        const int32_t* kc = knn_col + lrow * (int64_t)Kc;          // own rows only
         const uint32_t* so = sym + lrow * (int64_t)Kc;
         if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
@@ -283,14 +414,14 @@ void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t 
 template <int IPT>
 static void launch_mutual_t(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* table, int64_t row0, int64_t rows,
                             int32_t Kc, int32_t H, int32_t rank_bits, int64_t smax, int strict, int keep_self, int32_t kin,
-                            uint32_t* sym, uint64_t* thr_in)
+                            uint32_t* sym, uint64_t* thr_in, int have_scores)
 {
     static SmemOptIn optin;
     const size_t smem = (size_t)IPT * 256 * sizeof(uint64_t);
     ensure_smem(ctx, mutual_kernel<IPT>, smem, optin);
     const int grid = wave_grid(ctx, mutual_kernel<IPT>, smem, rows);
     mutual_kernel<IPT><<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, table, row0, rows, Kc, H, ilog2(H), rank_bits,
-                                                                  (long long)smax, strict, keep_self, kin, sym, thr_in);
+                                                                  (long long)smax, strict, keep_self, kin, sym, thr_in, have_scores);
     MCB_LAUNCH_CHECK();
 }
 template <int IPT>
@@ -313,13 +444,61 @@ static void launch_prune_t(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t*
         else { CALL(16); }                                            \
     } while (0)
 
+
+// ---- routed join launchers ------------------------------------------------------------------------------------------
+RouteShape route_shape(mcb_ctx* ctx, int64_t rows_per_rank, int32_t nranks, int32_t H, int32_t rank_bits)
+{
+    RouteShape rs;
+    // block of rows whose tables take <= 16 MB (a quarter of one L2 partition, with the score rows beside them)
+    int32_t shift = 13;
+    while (shift > 6 && ((int64_t)H * 4 << shift) > ((int64_t)16 << 20)) --shift;
+    int32_t nbr = (int32_t)std::max<int64_t>(1, ceil_div(rows_per_rank, (int64_t)1 << shift));
+    while ((int64_t)nbr * nranks > 4096) { ++shift; nbr = (int32_t)std::max<int64_t>(1, ceil_div(rows_per_rank, (int64_t)1 << shift)); }
+    MCB_CHECK(shift + rank_bits <= 32, "balance: block too large for the packed record");
+    rs.blk_shift = shift; rs.nbr = nbr; rs.nbuckets = nbr * nranks;
+    rs.grid = ctx->num_sms * 4;
+    return rs;
+}
+void launch_route_records(mcb_ctx* ctx, const int32_t* knn_col_own, int64_t row0, int64_t rows, int32_t Kc, int64_t rows_per_rank,
+                          const RouteShape& rs, int32_t rank_bits, int keep_self, uint32_t* counts /* [grid][nbuckets] */,
+                          int64_t* bucket_total /* [nbuckets] */, int64_t* bucket_start /* [nbuckets + 1] */, uint64_t* records)
+{
+    RouteGeom geo{rows_per_rank, rs.blk_shift, rs.nbr, rs.nbuckets, rank_bits};
+    const size_t smem1 = (size_t)rs.nbuckets * sizeof(uint32_t), smem2 = (size_t)rs.nbuckets * (sizeof(long long) + sizeof(uint32_t));
+    static SmemOptIn o1, o2;
+    ensure_dyn_smem(o1, ctx, route_count_kernel, smem1);
+    ensure_dyn_smem(o2, ctx, route_scatter_kernel, smem2);
+    route_count_kernel<<<rs.grid, ROUTE_THREADS, smem1, ctx->stream>>>(knn_col_own, row0, rows, Kc, geo, keep_self, counts);
+    MCB_LAUNCH_CHECK();
+    route_offsets_kernel<<<(int)ceil_div(rs.nbuckets, 128), 128, 0, ctx->stream>>>(counts, rs.grid, rs.nbuckets, bucket_total);
+    MCB_LAUNCH_CHECK();
+    launch_exclusive_scan_i64(ctx, bucket_total, bucket_start, rs.nbuckets, bucket_start + rs.nbuckets);
+    route_scatter_kernel<<<rs.grid, ROUTE_THREADS, smem2, ctx->stream>>>(knn_col_own, row0, rows, Kc, geo, keep_self, counts, bucket_start, records);
+    MCB_LAUNCH_CHECK();
+}
+void launch_probe(mcb_ctx* ctx, const uint64_t* records, int64_t n_records, const int64_t* seg_prefix, const int64_t* seg_src,
+                  const int32_t* seg_block, int32_t nseg, int32_t blk_shift, const uint32_t* table_own, int32_t H, int32_t rank_bits,
+                  int32_t Kc, int64_t smax, int strict, uint32_t* sym_own)
+{
+    if (n_records == 0 || nseg == 0) return;
+    const size_t smem = (size_t)(3 * nseg + 1) * sizeof(long long);
+    static SmemOptIn optin;
+    ensure_dyn_smem(optin, ctx, probe_kernel, smem);
+    int per_sm = 0;
+    MCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_kernel, 256, smem));
+    const int grid = (int)std::min<int64_t>(ceil_div(n_records, 256), (int64_t)ctx->num_sms * std::max(per_sm, 1));
+    probe_kernel<<<grid, 256, smem, ctx->stream>>>(records, n_records, seg_prefix, seg_src, seg_block, nseg, blk_shift, table_own, H,
+                                                   ilog2(H), rank_bits, Kc, (long long)smax, strict, sym_own);
+    MCB_LAUNCH_CHECK();
+}
+
 void launch_mutual(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* table, int64_t row0, int64_t rows,
                    int32_t Kc, int32_t H, int32_t rank_bits, int64_t smax, int strict, int keep_self, int32_t kin,
-                   uint32_t* sym, uint64_t* thr_in)
+                   uint32_t* sym, uint64_t* thr_in, int have_scores)
 {
     if (rows == 0) return;
     MCB_CHECK(Kc <= 4096, "MC-ERR: K * k_expand above 4096 is not supported");
-#define CALL(I) launch_mutual_t<I>(ctx, knn_col, table, row0, rows, Kc, H, rank_bits, smax, strict, keep_self, kin, sym, thr_in)
+#define CALL(I) launch_mutual_t<I>(ctx, knn_col, table, row0, rows, Kc, H, rank_bits, smax, strict, keep_self, kin, sym, thr_in, have_scores)
     MCB_DISPATCH_IPT(Kc, CALL);
 #undef CALL
 }

@@ -32,6 +32,7 @@ struct mcb_ctx {
     int keep_self = 0;
     int thresh_strict = 1;
     int cap_override = 0;    // test hook: shrink the candidate capacity so rows take the exact-row path
+    int join_impl = 0;       // balancing join: 0 = routed / L2-blocked (default), 1 = direct probing (single rank; cross-check)
     int host_threads = 0;    // staging threads per context (0 = min(16, cores / 2), env MCB_HOST_THREADS)
     mcb::Staging* staging = nullptr;     // pinned ring + copy stream + host threads, created on first use (staging.cu)
     // cached sample of column indices for the kNN threshold pass, keyed by (M, S): the sample only steers the filter
@@ -221,9 +222,19 @@ void launch_knn_trunc_check(mcb_ctx* ctx, int32_t N, int32_t n_local, const int3
 // balance.cu
 void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t Kc, int32_t H, int32_t rank_bits,
                        uint32_t* table);
+// knn_col of launch_mutual / launch_prune / launch_route_records: the rank's OWN rows ([rows][Kc], row 0 = global row row0)
 void launch_mutual(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* table, int64_t row0, int64_t rows,
                    int32_t Kc, int32_t H, int32_t rank_bits, int64_t smax, int strict, int keep_self, int32_t kin,
-                   uint32_t* sym, uint64_t* thr_in);
+                   uint32_t* sym, uint64_t* thr_in, int have_scores);
+// routed join (balance.cu): entries bucketed by (owner rank, block of rows) of their target, then probed block by block
+struct RouteShape { int32_t blk_shift, nbr, nbuckets, grid; };
+RouteShape route_shape(mcb_ctx* ctx, int64_t rows_per_rank, int32_t nranks, int32_t H, int32_t rank_bits);
+void launch_route_records(mcb_ctx* ctx, const int32_t* knn_col_own, int64_t row0, int64_t rows, int32_t Kc, int64_t rows_per_rank,
+                          const RouteShape& rs, int32_t rank_bits, int keep_self, uint32_t* counts, int64_t* bucket_total,
+                          int64_t* bucket_start, uint64_t* records);
+void launch_probe(mcb_ctx* ctx, const uint64_t* records, int64_t n_records, const int64_t* seg_prefix, const int64_t* seg_src,
+                  const int32_t* seg_block, int32_t nseg, int32_t blk_shift, const uint32_t* table_own, int32_t H, int32_t rank_bits,
+                  int32_t Kc, int64_t smax, int strict, uint32_t* sym_own);
 void launch_prune(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* sym, const uint64_t* thr_in, int64_t row0,
                   int64_t rows, int32_t Kc, int32_t K, int64_t smax, int32_t* out_deg, int32_t* out_dst, int32_t* out_s);
 void launch_widen_i32(mcb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n);

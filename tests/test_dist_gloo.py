@@ -1,74 +1,46 @@
-"""World-size-2 gloo test of the multi-rank plumbing (metacell_b200/dist.py) on CPU.
-
-No GPU here, so the stage engine is built on the CPU oracle (test infrastructure); what is under test
-is the sharding + exchange logic the GPU path shares: contiguous row blocks, in-place all-gather of
-the kNN lists and of the in-degree thresholds, gather of the edge rows, and that the sharded result
-equals the single-rank one bit for bit."""
+"""World-size-2 (and 3) gloo tests of the multi-rank PROTOCOL on CPU (metacell_b200/dist.py: the numpy mirror of what
+libmcb200.so runs over NCCL).  No GPU here, so every stage's compute comes from the CPU oracle (test infrastructure);
+what is under test is the rank-level logic the GPU path shares: contiguous cell / row splits, variable-block
+all-gathers, the routed balancing join with its symmetry trick, the all-gather of the in-degree cuts, the gather of the
+edge rows, the strided resamples + reduce -- and that the sharded result equals the single-rank oracle bit for bit."""
 import os
 import sys
 
 import numpy as np
 import pytest
-import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+K, KX, KB = 6, 5, 3
+
+
+def _matrix():
+    from metacell_b200 import synth
+    m = synth.make_umi_matrix(333, 150, n_types=5, median_umis=900.0, seed=21)       # odd size: ragged last block
+    data = m.data.copy()
+    for c in (0, 170, 332):                                                            # degenerate cells on both ranks
+        data[m.indptr[c]:m.indptr[c + 1]] = 0
+    return m, data
 
 
 class OracleEngine:
-    """Same interface as metacell_b200.dist.CudaCGraphEngine, stages computed by the oracle."""
-
-    def __init__(self, Z):
+    def __init__(self):
         from oracle import oracle as O
-        self.O, self.Z, self.M = O, Z, Z.shape[0]
+        self.O = O
+        self.m, self.data = _matrix()
 
-    def knn(self, K, k_expand, rank, world):
-        self.K, self.kx, self.Kc = K, k_expand, K * k_expand
-        self.rank, self.world = rank, world
-        self.rpr = -(-self.M // world)
-        self.row0 = min(self.M, rank * self.rpr)
-        self.row1 = min(self.M, self.row0 + self.rpr)
-        self.knn_buf = torch.full((world * self.rpr * self.Kc,), -1, dtype=torch.int32)
-        col, _ = self.O.cor_knn(self.Z, self.Kc, self.row0, self.row1)
-        self.knn_buf.view(world * self.rpr, self.Kc)[self.row0:self.row1] = torch.from_numpy(col)
+    def features(self, cells):
+        c0, c1 = cells
+        m = self.m
+        p = m.indptr[c0:c1 + 1] - m.indptr[c0]
+        sl = slice(m.indptr[c0], m.indptr[c1])
+        Z, valid = self.O.features(p, m.indices[sl], self.data[sl], np.arange(150, dtype=np.int32), 150)
+        return Z[valid], np.arange(c0, c1)[valid]
 
-    def knn_full(self, world):
-        return self.knn_buf
-
-    def mutual(self, k_beta):
-        self.kb = k_beta
-        self.thr_buf = torch.zeros(self.world * self.rpr, dtype=torch.int64)
-        # the oracle has no separate threshold export; mark the block so the exchange is exercised
-        self.thr_buf[self.row0:self.row1] = torch.arange(self.row0, self.row1)
-
-    def thr_full(self, world):
-        return self.thr_buf
-
-    def prune(self):
-        col = self.knn_buf.view(self.world * self.rpr, self.Kc)[:self.M].numpy()
-        assert (col[:, 0] == np.arange(self.M)).all(), "kNN all-gather left holes"
-        assert (self.thr_buf[:self.M].numpy() == np.arange(self.M)).all(), "threshold all-gather left holes"
-        deg, dst, _ = self.O.balance(col, self.K, self.kx, self.kb)
-        src, d, w = self.O.edges_from_balance(deg, dst, self.K)
-        own = (src >= self.row0) & (src < self.row1)
-        self._edges = (src[own], d[own], w[own])
-        return int(own.sum())
-
-    def edges(self):
-        return self._edges
-
-    def sync(self):
-        pass
-
-
-def _features():
-    from metacell_b200 import synth
-    from oracle import oracle as O
-    m = synth.make_umi_matrix(333, 150, n_types=5, median_umis=900.0, seed=21)       # odd size: ragged last block
-    fm = np.arange(150, dtype=np.int32)
-    Z, valid = O.features(m.indptr, m.indices, m.data, fm, 150)
-    return Z[valid]
+    def knn(self, Z, row0, row1, Kc):
+        col, _ = self.O.cor_knn(Z, Kc, row0, row1)
+        return col
 
 
 def _worker(rank, world, port, out_dir):
@@ -76,26 +48,48 @@ def _worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from metacell_b200 import dist as mdist
-    eng = OracleEngine(_features())
-    src, dst, w = mdist.cgraph_sharded(eng, 6, 5, 3, rank, world)
-    res = mdist.gather_edges(src, dst, w, rank, world)
+    from metacell_b200 import synth
+    from oracle import oracle as O
+    eng = OracleEngine()
+    n = eng.m.ncells
+    cells = (n * rank // world, n * (rank + 1) // world)
+    src, dst, w = mdist.cgraph_sharded(eng, cells, K, KX, KB)
+    res = mdist.gather_edges(src, dst, w)
+    # co-clustering: resamples strided over the ranks on the gathered graph (broadcast from rank 0), counters reduced
+    obj = [res]
+    dist.broadcast_object_list(obj, src=0)
+    es, ed, ew = obj[0]
+    sets, seeds = synth.resample_sets(n, 0.75, 7, 5)
+    mine = list(range(rank, 7, world))
+    csr = O.graph_to_csr(n, es, ed, ew)
+    cnt, ns, _ = O.coclust(n, csr, sets[mine], seeds[mine], 8, 1.05, 10) if mine else (np.zeros((n, n), np.uint32), np.zeros(n, np.int32), None)
+    red = mdist.coclust_sharded(cnt, ns)
     if rank == 0:
-        np.savez(os.path.join(out_dir, "edges.npz"), src=res[0], dst=res[1], w=res[2])
+        np.savez(os.path.join(out_dir, "out.npz"), src=res[0], dst=res[1], w=res[2], cnt=red[0], ns=red[1])
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.timeout(300)
-def test_sharded_cgraph_equals_single_rank(tmp_path):
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_protocol_equals_single_rank(tmp_path, world):
+    from metacell_b200 import synth
     from oracle import oracle as O
-    port = 29500 + (os.getpid() % 1000)
-    mp.start_processes(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True, start_method="spawn")
-    got = np.load(tmp_path / "edges.npz")
-    Z = _features()
-    col, _ = O.cor_knn(Z, 30)
-    deg, dst, _ = O.balance(col, 6, 5, 3)
-    src, d, w = O.edges_from_balance(deg, dst, 6)
-    assert np.array_equal(got["src"], src) and np.array_equal(got["dst"], d) and np.array_equal(got["w"], w)
+    port = 29500 + (os.getpid() % 1000) + world
+    mp.start_processes(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True, start_method="spawn")
+    got = np.load(tmp_path / "out.npz")
+    m, data = _matrix()
+    Z, valid = O.features(m.indptr, m.indices, data, np.arange(150, dtype=np.int32), 150)
+    assert not valid[[0, 170, 332]].any()
+    cells = np.nonzero(valid)[0]
+    col, _ = O.cor_knn(Z[valid], K * KX)
+    deg, dst, _ = O.balance(col, K, KX, KB)
+    src, d, w = O.edges_from_balance(deg, dst, K)
+    assert np.array_equal(got["src"], cells[src]) and np.array_equal(got["dst"], cells[d]) and np.array_equal(got["w"], w)
+    sets, seeds = synth.resample_sets(m.ncells, 0.75, 7, 5)
+    csr = O.graph_to_csr(m.ncells, got["src"], got["dst"], got["w"])
+    cnt, ns, _ = O.coclust(m.ncells, csr, sets, seeds, 8, 1.05, 10)
+    assert np.array_equal(got["cnt"], cnt) and np.array_equal(got["ns"], ns)
 
 
 def test_resample_striding_partitions_the_work():
@@ -103,3 +97,13 @@ def test_resample_striding_partitions_the_work():
     for world in (1, 2, 3, 8):
         seen = sorted(r for rank in range(world) for r in range(rank, 500, world))
         assert seen == list(range(500))
+
+
+def test_row_split_covers_every_row_once():
+    from metacell_b200.dist import row_split
+    for M, world in ((10, 3), (333, 2), (7, 8), (100000, 8)):
+        rpr, split = row_split(M, world)
+        rows = [r for a, b in split for r in range(a, b)] if M < 1000 else None
+        assert split[0][0] == 0 and split[-1][1] == M and all(split[q][1] == split[q + 1][0] for q in range(world - 1))
+        if rows is not None:
+            assert rows == list(range(M))

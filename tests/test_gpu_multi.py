@@ -2,8 +2,7 @@
 library (SURVEY 8b "Threading", 8e): (1) one process driving several devices (mcb_multi: mcb_cgraph_bknn_multi,
 mcb_coclust_multi), (2) one process per device (mcb_comm: mcb_cgraph_build_sharded, mcb_cgraph_gather_edges,
 mcb_coclust_reduce).  Both must reproduce the single-device result: edges identical up to correlation ties, co-occurrence
-counts bit-exact.  tools/multi_check.py is the worker; tools/mgpu_check.py keeps the older torch.distributed harness
-(metacell_b200/dist.py) alive as a second opinion."""
+counts bit-exact.  tools/multi_check.py is the worker (the launcher's gloo group only carries the NCCL id)."""
 import os
 import subprocess
 import sys
@@ -38,13 +37,3 @@ def test_process_per_device_matches_single_device():
     r = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
               "--master-port", str(port), os.path.join(ROOT, "tools", "multi_check.py")])
     assert r.returncode == 0 and "MULTI_CHECK PASS" in r.stdout
-
-
-def test_torch_distributed_harness_still_agrees():
-    if _gpus() < 2:
-        pytest.skip("needs 2 GPUs")
-    port = 29900 + os.getpid() % 90
-    r = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-              "--master-port", str(port), os.path.join(ROOT, "tools", "mgpu_check.py")])
-    assert r.returncode == 0
-    assert "coclust: sharded" in r.stdout and "identical True" in r.stdout
