@@ -83,7 +83,7 @@ __device__ __forceinline__ uint32_t hash_lookup(const uint32_t* __restrict__ tab
 // ---------------------------------------------------------------------------------------------------------------
 // Bucket of a target row j: (owner rank, block of `blk` rows inside the owner's row range).
 struct RouteGeom {
-    int64_t rows_per_rank;      // contiguous row split of the M valid rows over the ranks
+    uint32_t rows_per_rank;     // contiguous row split of the M valid rows over the ranks (1 rank: every row is rank 0's)
     int32_t blk_shift;          // block = 2^blk_shift rows
     int32_t nbr;                // blocks per rank = ceil(rows_per_rank / blk)
     int32_t nbuckets;           // nranks * nbr
@@ -91,15 +91,16 @@ struct RouteGeom {
 };
 __device__ __forceinline__ int32_t route_bucket(const RouteGeom& g, int32_t j, uint32_t& jl)
 {
-    const int32_t owner = (int32_t)(j / g.rows_per_rank);
-    const int32_t lrow = (int32_t)(j - owner * g.rows_per_rank);
+    const uint32_t owner = g.nbuckets == g.nbr ? 0u : (uint32_t)j / g.rows_per_rank;          // 32-bit division, none on one rank
+    const uint32_t lrow = (uint32_t)j - owner * g.rows_per_rank;
     jl = (uint32_t)lrow & ((1u << g.blk_shift) - 1u);
-    return owner * g.nbr + (lrow >> g.blk_shift);
+    return (int32_t)(owner * (uint32_t)g.nbr + (lrow >> g.blk_shift));
 }
 constexpr int ROUTE_THREADS = 256;
 
 // pass 1: counts[cta][bucket] = entries of the CTA's rows that go to `bucket`.  Every CTA owns a contiguous chunk of
-// the rank's rows (the same chunk in pass 2); the histogram lives in shared memory.
+// the rank's rows (the same chunk in pass 2) and walks it row by row; the histogram lives in shared memory (+1 atomics
+// without a return value: the hardware aggregates the lanes of a warp that hit the same bin).
 __global__ void __launch_bounds__(ROUTE_THREADS)
 route_count_kernel(const int32_t* __restrict__ knn_col, int64_t row0, int64_t rows, int32_t Kc, RouteGeom geo, int keep_self,
                    uint32_t* __restrict__ counts)
@@ -109,12 +110,15 @@ route_count_kernel(const int32_t* __restrict__ knn_col, int64_t row0, int64_t ro
     __syncthreads();
     const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
     const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(rows, r0 + per);
-    for (int64_t e = r0 * Kc + threadIdx.x; e < r1 * Kc; e += ROUTE_THREADS) {
-        const int32_t j = knn_col[e];
-        if (j < 0) continue;
-        if (!keep_self && j == (int32_t)(row0 + e / Kc)) continue;
-        uint32_t jl;
-        atomicAdd(&hist[route_bucket(geo, j, jl)], 1u);
+    for (int64_t lrow = r0; lrow < r1; ++lrow) {
+        const int32_t* kc = knn_col + lrow * Kc;
+        const int32_t self = keep_self ? -1 : (int32_t)(row0 + lrow);
+        for (int r = threadIdx.x; r < Kc; r += ROUTE_THREADS) {
+            const int32_t j = kc[r];
+            if (j < 0 || j == self) continue;
+            uint32_t jl;
+            atomicAdd(&hist[route_bucket(geo, j, jl)], 1u);
+        }
     }
     __syncthreads();
     for (int q = threadIdx.x; q < geo.nbuckets; q += ROUTE_THREADS) counts[(int64_t)blockIdx.x * geo.nbuckets + q] = hist[q];
@@ -128,7 +132,8 @@ __global__ void route_offsets_kernel(uint32_t* __restrict__ counts, int32_t ncta
     for (int c = 0; c < nctas; ++c) { const uint32_t v = counts[(int64_t)c * nbuckets + b]; counts[(int64_t)c * nbuckets + b] = run; run += v; }
     total[b] = run;
 }
-// pass 2: records[bucket_start[b] + within[cta][b] + k] = (source row i : 32 | row of j inside its block : * | rank0 : rank_bits)
+// pass 2: records[bucket_start[b] + within[cta][b] + k] = (source row i : 32 | row of j inside its block : * | rank0 : rank_bits).
+// The lanes of a warp that target the same bucket take their slots with ONE shared-memory atomic (match_any + popc).
 __global__ void __launch_bounds__(ROUTE_THREADS)
 route_scatter_kernel(const int32_t* __restrict__ knn_col, int64_t row0, int64_t rows, int32_t Kc, RouteGeom geo, int keep_self,
                      const uint32_t* __restrict__ within, const int64_t* __restrict__ bucket_start, uint64_t* __restrict__ records)
@@ -140,19 +145,29 @@ route_scatter_kernel(const int32_t* __restrict__ knn_col, int64_t row0, int64_t 
         cursor[q] = 0;
     }
     __syncthreads();
+    const int lane = threadIdx.x & 31;
     const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
     const int64_t r0 = (int64_t)blockIdx.x * per, r1 = min(rows, r0 + per);
-    for (int64_t e = r0 * Kc + threadIdx.x; e < r1 * Kc; e += ROUTE_THREADS) {
-        const int32_t j = knn_col[e];
-        if (j < 0) continue;
-        const int64_t lrow = e / Kc;
-        const uint32_t r = (uint32_t)(e - lrow * Kc);
+    const int Kc_pad = (Kc + 31) & ~31;                 // whole warps stay converged for the match
+    for (int64_t lrow = r0; lrow < r1; ++lrow) {
+        const int32_t* kc = knn_col + lrow * Kc;
         const uint32_t i = (uint32_t)(row0 + lrow);
-        if (!keep_self && j == (int32_t)i) continue;
-        uint32_t jl;
-        const int32_t b = route_bucket(geo, j, jl);
-        const long long pos = rbase[b] + (long long)atomicAdd(&cursor[b], 1u);
-        records[pos] = ((uint64_t)i << 32) | (uint64_t)((jl << geo.rank_bits) | r);
+        const int32_t self = keep_self ? -1 : (int32_t)i;
+        for (int r = threadIdx.x; r < Kc_pad; r += ROUTE_THREADS) {
+            const int32_t j = r < Kc ? kc[r] : -1;
+            const bool live = j >= 0 && j != self;
+            uint32_t jl = 0;
+            const int32_t b = live ? route_bucket(geo, j, jl) : -1 - lane;          // dead lanes match nobody
+            const unsigned peers = __match_any_sync(0xffffffffu, b);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (live && lane == leader) base = atomicAdd(&cursor[b], (uint32_t)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (live) {
+                const long long pos = rbase[b] + (long long)(base + (uint32_t)__popc(peers & ((1u << lane) - 1u)));
+                records[pos] = ((uint64_t)i << 32) | (uint64_t)((jl << geo.rank_bits) | (uint32_t)r);
+            }
+        }
     }
 }
 
@@ -463,7 +478,7 @@ void launch_route_records(mcb_ctx* ctx, const int32_t* knn_col_own, int64_t row0
                           const RouteShape& rs, int32_t rank_bits, int keep_self, uint32_t* counts /* [grid][nbuckets] */,
                           int64_t* bucket_total /* [nbuckets] */, int64_t* bucket_start /* [nbuckets + 1] */, uint64_t* records)
 {
-    RouteGeom geo{rows_per_rank, rs.blk_shift, rs.nbr, rs.nbuckets, rank_bits};
+    RouteGeom geo{(uint32_t)rows_per_rank, rs.blk_shift, rs.nbr, rs.nbuckets, rank_bits};
     const size_t smem1 = (size_t)rs.nbuckets * sizeof(uint32_t), smem2 = (size_t)rs.nbuckets * (sizeof(long long) + sizeof(uint32_t));
     static SmemOptIn o1, o2;
     ensure_dyn_smem(o1, ctx, route_count_kernel, smem1);

@@ -91,10 +91,15 @@ def test_staged_edge_download_equals_device_table(ctx):
     _lib.check(_lib.lib().mcb_cgraph_edges_device(g.h, C.byref(n), C.byref(ps), C.byref(pd), C.byref(pw)))
     assert n.value == ne
     import torch
-    from metacell_b200.dist import device_view
+
+    class _DevMem:
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
     ctx.sync()
-    dev = [device_view(p.value, ne * sz, t, ctx.device) for t, p, sz in zip((torch.int32, torch.int32, torch.float64), (ps, pd, pw), (4, 4, 8))]
-    assert np.array_equal(src, dev[0].cpu().numpy()) and np.array_equal(dst, dev[1].cpu().numpy()) and np.array_equal(w, dev[2].cpu().numpy())
+    dev = [torch.as_tensor(_DevMem(p.value, ne * sz), device=torch.device("cuda", ctx.device)).view(t).cpu().numpy()
+           for t, p, sz in zip((torch.int32, torch.int32, torch.float64), (ps, pd, pw), (4, 4, 8))]
+    assert np.array_equal(src, dev[0]) and np.array_equal(dst, dev[1]) and np.array_equal(w, dev[2])
     g.destroy()
 
 
