@@ -174,6 +174,7 @@ extern "C" int mcb_ctx_set_option(mcb_ctx* ctx, const char* key, int64_t value)
     else if (!strcmp(key, "thresh_strict")) ctx->thresh_strict = (int)value;
     else if (!strcmp(key, "cap_override")) ctx->cap_override = (int)value;
     else if (!strcmp(key, "join_impl")) ctx->join_impl = (int)value;
+    else if (!strcmp(key, "sample_factor")) { MCB_CHECK(value >= 16 && value <= 1024, "sample_factor must be between 16 and 1024"); ctx->sample_factor = (int)value; }
     else if (!strcmp(key, "host_threads")) {
         MCB_CHECK(value >= 0 && value <= 64, "host_threads must be between 0 and 64");
         MCB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -769,7 +770,7 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
     // rows past M (padding of the last rank's block) never pass: +inf
     launch_fill_u32(ctx, g->thr_all.p, (int64_t)nranks * g->rows_per_rank, 0x7f800000u);
     // ---- sampling pass: per-row filter threshold from a random column sample -----------------
-    int64_t S = std::min<int64_t>(262144, round_up(ceil_div(128 * M, kc_out), 256));     // ~128 sampled columns above the true cut
+    int64_t S = std::min<int64_t>(262144, round_up(ceil_div((int64_t)ctx->sample_factor * M, kc_out), 256));     // ~sample_factor sampled columns above the true cut
     if (S >= M) S = M;
     const int64_t Spad = round_up(S, 256);
     int32_t r_sel = 0, cap = 0;

@@ -123,14 +123,24 @@ route_count_kernel(const int32_t* __restrict__ knn_col, int64_t row0, int64_t ro
     __syncthreads();
     for (int q = threadIdx.x; q < geo.nbuckets; q += ROUTE_THREADS) counts[(int64_t)blockIdx.x * geo.nbuckets + q] = hist[q];
 }
-// per bucket: exclusive prefix of the CTAs' counts (in place) and the bucket total
-__global__ void route_offsets_kernel(uint32_t* __restrict__ counts, int32_t nctas, int32_t nbuckets, int64_t* __restrict__ total)
+// per bucket: exclusive prefix of the CTAs' counts (in place) and the bucket total.  One warp per bucket, 32 CTAs per step.
+__global__ void __launch_bounds__(128)
+route_offsets_kernel(uint32_t* __restrict__ counts, int32_t nctas, int32_t nbuckets, int64_t* __restrict__ total)
 {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (b >= nbuckets) return;
-    uint32_t run = 0;
-    for (int c = 0; c < nctas; ++c) { const uint32_t v = counts[(int64_t)c * nbuckets + b]; counts[(int64_t)c * nbuckets + b] = run; run += v; }
-    total[b] = run;
+    uint32_t carry = 0;
+    for (int c0 = 0; c0 < nctas; c0 += 32) {
+        const int c = c0 + lane;
+        const uint32_t v = c < nctas ? counts[(int64_t)c * nbuckets + b] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (c < nctas) counts[(int64_t)c * nbuckets + b] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) total[b] = carry;
 }
 // pass 2: records[bucket_start[b] + within[cta][b] + k] = (source row i : 32 | row of j inside its block : * | rank0 : rank_bits).
 // The lanes of a warp that target the same bucket take their slots with ONE shared-memory atomic (match_any + popc).
@@ -485,7 +495,7 @@ void launch_route_records(mcb_ctx* ctx, const int32_t* knn_col_own, int64_t row0
     ensure_dyn_smem(o2, ctx, route_scatter_kernel, smem2);
     route_count_kernel<<<rs.grid, ROUTE_THREADS, smem1, ctx->stream>>>(knn_col_own, row0, rows, Kc, geo, keep_self, counts);
     MCB_LAUNCH_CHECK();
-    route_offsets_kernel<<<(int)ceil_div(rs.nbuckets, 128), 128, 0, ctx->stream>>>(counts, rs.grid, rs.nbuckets, bucket_total);
+    route_offsets_kernel<<<(int)ceil_div(rs.nbuckets, 4), 128, 0, ctx->stream>>>(counts, rs.grid, rs.nbuckets, bucket_total);
     MCB_LAUNCH_CHECK();
     launch_exclusive_scan_i64(ctx, bucket_total, bucket_start, rs.nbuckets, bucket_start + rs.nbuckets);
     route_scatter_kernel<<<rs.grid, ROUTE_THREADS, smem2, ctx->stream>>>(knn_col_own, row0, rows, Kc, geo, keep_self, counts, bucket_start, records);

@@ -67,12 +67,25 @@ __device__ __forceinline__ long long block_excl_scan(long long v, long long* war
     return base + inc - v;
 }
 
-__global__ void __launch_bounds__(DS_THREADS)
+// radix passes over the 64-bit key, most significant bits first: 11 bits, then 8 at a time (53 = 6 * 8 + 5).  With 2,048
+// bins the first pass leaves ~1 key in the bucket of the d-th smallest for cells up to a few thousand UMIs, so the select is
+// usually one or two passes over the cell's UMIs instead of three or four.
+constexpr int DS_BINS = 2048;
+__device__ __forceinline__ void ds_pass(int pass, int& shift, int& width)
+{
+    if (pass == 0) { shift = 53; width = 11; }
+    else if (pass <= 6) { shift = 53 - 8 * pass; width = 8; }
+    else { shift = 0; width = 5; }
+}
+constexpr int DS_BITMAP_WORDS = 8192;      // kept-UMI bitmap in shared memory: cells up to 262,144 UMIs take the fast final pass
+
+__global__ void __launch_bounds__(DS_THREADS, 4)
 downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t* __restrict__ x, double n,
                   uint32_t seed_lo, uint32_t seed_hi, int add_non_dsamp, uint32_t* __restrict__ out_x,
                   uint8_t* __restrict__ kept, int64_t cell_base)
 {
-    __shared__ uint32_t hist[256];
+    __shared__ uint32_t hist[DS_BINS];
+    __shared__ uint32_t bitmap[DS_BITMAP_WORDS];
     __shared__ long long warp_tot[DS_THREADS / 32 + 1];
     __shared__ unsigned long long s_prefix, s_thr;
     __shared__ long long s_krem;
@@ -96,17 +109,19 @@ downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t*
             for (int64_t e = e0 + threadIdx.x; e < e1; e += DS_THREADS) out_x[e] = x[e];
             continue;
         }
-        // 2. radix select of the d-th smallest 64-bit key (index d-1), 8 bits per pass from the top
+        // 2. radix select of the d-th smallest 64-bit key (index d-1)
         if (threadIdx.x == 0) { s_prefix = 0ull; s_krem = d - 1; s_done = 0; s_thr = ~0ull; }
         __syncthreads();
         // the key of a UMI names its cell by the index in the WHOLE matrix, so a cell shard draws the same subset
         const uint32_t c_lo = (uint32_t)(c + cell_base), c_hi = (uint32_t)((uint64_t)(c + cell_base) >> 32);
         const long long ngroups = (tot + 3) >> 2;
         for (int pass = 0; pass < 8; ++pass) {
-            const int shift = 56 - 8 * pass;
-            const unsigned long long decided = pass == 0 ? 0ull : (~0ull << (shift + 8));
+            int shift, width;
+            ds_pass(pass, shift, width);
+            const uint32_t bmask = (1u << width) - 1u;
+            const unsigned long long decided = pass == 0 ? 0ull : (~0ull << (shift + width));
             const unsigned long long prefix = s_prefix;
-            hist[threadIdx.x] = 0;         // DS_THREADS == 256
+            for (int q = threadIdx.x; q < (1 << width); q += DS_THREADS) hist[q] = 0;
             __syncthreads();
             for (long long g = threadIdx.x; g < ngroups; g += DS_THREADS) {
                 uint32_t o[4];
@@ -116,7 +131,7 @@ downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t*
                     const long long t = (g << 2) + q;
                     if (t < tot) {
                         const uint64_t key = ds_key(o[q], (uint32_t)t);
-                        if ((key & decided) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 255u], 1u);
+                        if ((key & decided) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & bmask], 1u);
                     }
                 }
             }
@@ -124,7 +139,9 @@ downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t*
             if (threadIdx.x < 32) {
                 int dg; long long cum;
                 const long long k = s_krem;
-                warp_find_bucket<8>(hist, k, dg, cum);
+                if (width == 11) warp_find_bucket<64>(hist, k, dg, cum);
+                else if (width == 8) warp_find_bucket<8>(hist, k, dg, cum);
+                else warp_find_bucket<1>(hist, k, dg, cum);
                 __syncwarp();
                 if (threadIdx.x == 0) {
                     const unsigned long long np = prefix | ((unsigned long long)dg << shift);
@@ -142,6 +159,53 @@ downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t*
         }
         const uint64_t thr = s_thr;
         // 3. per stored entry: how many of its UMIs have key <= thr
+        if (tot <= (long long)DS_BITMAP_WORDS * 32) {
+            // one more uniform pass over the UMIs: thread -> one bitmap word = 8 Philox blocks = 32 UMIs (no atomics),
+            // then every entry counts the bits of its own UMI range.  (The per-entry loop below makes a warp wait for
+            // its most expressed gene.)
+            const int nwords = (int)((tot + 31) >> 5);
+            for (int wq = threadIdx.x; wq < nwords; wq += DS_THREADS) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int b8 = 0; b8 < 8; ++b8) {
+                    const long long g = ((long long)wq << 3) + b8;
+                    if ((g << 2) >= tot) break;
+                    uint32_t o[4];
+                    philox4x32_10((uint32_t)g, c_lo, c_hi, TAG_DOWNSAMP, seed_lo, seed_hi, o);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const long long t = (g << 2) + q;
+                        if (t < tot && ds_key(o[q], (uint32_t)t) <= thr) word |= 1u << (b8 * 4 + q);
+                    }
+                }
+                bitmap[wq] = word;
+            }
+            __syncthreads();
+            long long run = 0;
+            for (int64_t base = e0; base < e1; base += DS_THREADS) {
+                const int64_t e = base + threadIdx.x;
+                const long long xe = e < e1 ? (long long)x[e] : 0;
+                long long chunk_tot;
+                const long long start = run + block_excl_scan(xe, warp_tot, &chunk_tot);
+                run += chunk_tot;
+                if (e < e1) {
+                    uint32_t cnt = 0;
+                    if (xe) {
+                        const long long last = start + xe - 1;
+                        const int w0 = (int)(start >> 5), w1 = (int)(last >> 5);
+                        const uint32_t m0 = ~0u << (start & 31), m1 = ~0u >> (31 - (last & 31));
+                        if (w0 == w1) cnt = __popc(bitmap[w0] & m0 & m1);
+                        else {
+                            cnt = __popc(bitmap[w0] & m0) + __popc(bitmap[w1] & m1);
+                            for (int wq = w0 + 1; wq < w1; ++wq) cnt += __popc(bitmap[wq]);
+                        }
+                    }
+                    out_x[e] = cnt;
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         long long run = 0;
         for (int64_t base = e0; base < e1; base += DS_THREADS) {
             const int64_t e = base + threadIdx.x;

@@ -32,6 +32,7 @@ struct mcb_ctx {
     int keep_self = 0;
     int thresh_strict = 1;
     int cap_override = 0;    // test hook: shrink the candidate capacity so rows take the exact-row path
+    int sample_factor = 128; // kNN threshold pass: sampled columns expected above a row's true cut (more = tighter filter, longer pass)
     int join_impl = 0;       // balancing join: 0 = routed / L2-blocked (default), 1 = direct probing (single rank; cross-check)
     int host_threads = 0;    // staging threads per context (0 = min(16, cores / 2), env MCB_HOST_THREADS)
     mcb::Staging* staging = nullptr;     // pinned ring + copy stream + host threads, created on first use (staging.cu)
