@@ -111,7 +111,8 @@ int  mcb_cgraph_download_knn(mcb_cgraph* g, int32_t* host_col /* [rows][Kc] */, 
 int  mcb_cgraph_knn_stats(mcb_cgraph* g, int64_t* n_fallback_rows, int64_t* n_candidates, int32_t* cap,
                           int32_t* n_sample_cols);
 /* A6 step 1: mutual rank products + per-target in-degree cut (K*k_beta) for the owned rows.
- * context option "join_impl": 0 = routed, L2-blocked join (default) | 1 = direct probing join (cross-check)   */
+ * context option "join_impl": 0 = routed, L2-blocked join | 1 = direct probing join (single rank) | -1 = auto (default:
+ * direct on one rank, routed across ranks); both give identical results                                        */
 int  mcb_cgraph_mutual(mcb_cgraph* g, int32_t k_beta);
 /* A6 steps 2-4: out-degree cut (K) and weights 1 - (place-1)/K for the owned rows.             */
 int  mcb_cgraph_prune(mcb_cgraph* g, int64_t* n_edges);

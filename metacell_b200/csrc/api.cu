@@ -1033,8 +1033,9 @@ static int ilog2_ceil(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) ++l;
 // Routed join (balance.cu): every list entry becomes a record bucketed by (owner rank, row block) of its target; with a
 // communicator the buckets of other ranks travel in one all-to-all (the kNN lists themselves never leave their owner and
 // a rank builds rank tables for its own rows only); the probe pass then walks this rank's blocks one by one.  The
-// in-degree cuts (8 bytes per row) are all-gathered at the end.  Option "join_impl" = 1 selects the direct join (every
-// entry probes the table of its target row wherever it lies in memory), single rank only: the cross-check of the routed one.
+// in-degree cuts (8 bytes per row) are all-gathered at the end.  Option "join_impl": 1 = direct join (every entry probes
+// the table of its target row wherever it lies in memory; single rank only), 0 = routed join, -1 (default) = direct on a
+// single rank, routed across ranks.  The two are bit-identical (tests/test_gpu_cgraph.py::test_routed_join_equals_direct_join).
 void mcb::cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
 {
     MCB_CHECK(g->knn_col.p, "mcb_cgraph_mutual: run mcb_cgraph_knn first");
@@ -1061,7 +1062,7 @@ void mcb::cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
         StageTimer t(ctx, "balance_hash");
         launch_build_hash(ctx, g->knn_col.p, rows, Kc, H, g->rank_bits, table.p);        // own rows only
     }
-    if (ctx->join_impl == 1 && P == 1) {
+    if (P == 1 && ctx->join_impl != 0) {
         StageTimer t(ctx, "balance_mutual");
         launch_mutual(ctx, g->knn_col.p, table.p, row0, rows, Kc, H, g->rank_bits, smax, ctx->thresh_strict, ctx->keep_self,
                       g->K * k_beta, g->sym.p, g->thr_in.p, /*have_scores=*/0);

@@ -33,7 +33,8 @@ struct mcb_ctx {
     int thresh_strict = 1;
     int cap_override = 0;    // test hook: shrink the candidate capacity so rows take the exact-row path
     int sample_factor = 128; // kNN threshold pass: sampled columns expected above a row's true cut (more = tighter filter, longer pass)
-    int join_impl = 0;       // balancing join: 0 = routed / L2-blocked (default), 1 = direct probing (single rank; cross-check)
+    int join_impl = -1;      // balancing join: 0 = routed / L2-blocked, 1 = direct probing (single rank only), -1 = auto: direct on one
+                             // rank (measured 2.9 ms vs 4.7 ms at C2), routed across ranks (no list all-gather, no replicated tables)
     int host_threads = 0;    // staging threads per context (0 = min(16, cores / 2), env MCB_HOST_THREADS)
     mcb::Staging* staging = nullptr;     // pinned ring + copy stream + host threads, created on first use (staging.cu)
     // cached sample of column indices for the kNN threshold pass, keyed by (M, S): the sample only steers the filter
