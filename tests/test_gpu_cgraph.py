@@ -327,7 +327,7 @@ def test_routed_join_equals_direct_join(ctx, oracle, ncells, K, kx, kb):
                 out[impl] = g.edges()
                 g.destroy()
             finally:
-                ctx.set_option("join_impl", 0)
+                ctx.set_option("join_impl", -1)
                 ctx.set_option("keep_self", 0)
         assert all(np.array_equal(a, b) for a, b in zip(out[0], out[1])), keep_self
         deg, odst, _ = oracle.balance(col, K, kx, kb, keep_self=bool(keep_self))
