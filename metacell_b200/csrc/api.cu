@@ -174,6 +174,7 @@ extern "C" int mcb_ctx_set_option(mcb_ctx* ctx, const char* key, int64_t value)
     else if (!strcmp(key, "thresh_strict")) ctx->thresh_strict = (int)value;
     else if (!strcmp(key, "cap_override")) ctx->cap_override = (int)value;
     else if (!strcmp(key, "join_impl")) ctx->join_impl = (int)value;
+    else if (!strcmp(key, "sample_impl")) { MCB_CHECK(value >= -1 && value <= 2, "sample_impl must be -1, 0, 1 or 2"); ctx->sample_impl = (int)value; }
     else if (!strcmp(key, "sample_factor")) { MCB_CHECK(value >= 16 && value <= 1024, "sample_factor must be between 16 and 1024"); ctx->sample_factor = (int)value; }
     else if (!strcmp(key, "host_threads")) {
         MCB_CHECK(value >= 0 && value <= 64, "host_threads must be between 0 and 64");
@@ -735,7 +736,7 @@ static void sample_rule(int64_t M, int64_t S, int32_t kc_out, int32_t& r_out, in
     if (r < 0) { r_out = (int32_t)S + 1; cap_out = (int32_t)round_up(M, 64); return; }    // keep everything
     const double sd = std::sqrt((double)r * (1.0 - (double)r / (double)S)) * fpc;
     const double upper = ((double)r + z * sd) * scale;
-    int64_t cap = round_up((int64_t)(upper * 1.08) + 64, 64);
+    int64_t cap = round_up((int64_t)(upper * 1.05) + 64, 64);       // slack for eps and the threshold's bin resolution
     cap = std::min<int64_t>(cap, round_up(M, 64));
     r_out = r; cap_out = (int32_t)cap;
 }
@@ -774,11 +775,38 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
     if (S >= M) S = M;
     const int64_t Spad = round_up(S, 256);
     int32_t r_sel = 0, cap = 0;
-    sample_rule(M, S, kc_out, r_sel, cap);
+    // fused path (corsample.cu): e4m3 operands, per-row histograms in the epilogue, nothing stored.  The first
+    // ~5/32 of the sampled columns only bracket each row's quantile; the rank is located among the rest (S_fine).
+    bool fused = ctx->gemm_impl == 0 && ctx->sample_impl != 1 && S >= 4096 && S < M;
+    int32_t n_tiles1 = 0, c_hi = 0, c_lo = 0;
+    int64_t S_fine = S;
+    if (fused) {
+        const int32_t n_tiles = (int32_t)(Spad / 256);
+        n_tiles1 = std::max<int32_t>(2, std::min<int32_t>(n_tiles / 2, (int32_t)((S * 5 / 32 + 128) / 256)));
+        S_fine = S - (int64_t)n_tiles1 * 256;
+        sample_rule(M, S_fine, kc_out, r_sel, cap);
+        if (r_sel > S_fine) fused = false;
+        else {
+            // bracket ranks in the coarse sample: Poisson tails of the coarse count above the row's fine-sample quantile,
+            // each side below ~1e-7 (an escaped row costs a batch of the exact path)
+            const double m1 = (double)r_sel / (double)S_fine * (double)n_tiles1 * 256.0;
+            const double m_lo = 0.8 * m1, m_hi = 1.25 * m1;
+            double term = std::exp(-m_lo), cdf = term;
+            c_hi = -1;
+            for (int c = 0; cdf <= 1e-7 && c < 100000; ++c) { c_hi = c; term *= m_lo / (double)(c + 1); cdf += term; }
+            term = std::exp(-m_hi); cdf = term;               // P(X <= c)
+            int c = 0;
+            while (1.0 - cdf > 1e-7 && c < 100000) { ++c; term *= m_hi / (double)c; cdf += term; }
+            c_lo = c + 1;
+            if (c_hi < 0) c_hi = 0;
+            if (c_lo <= c_hi) c_lo = c_hi + 1;
+        }
+    }
+    if (!fused) { S_fine = S; sample_rule(M, S, kc_out, r_sel, cap); }
     MCB_CHECK(cap <= 4096, "MC-ERR: K * k_expand is too large relative to the number of cells for this build");
     if (ctx->cap_override > 0) cap = std::min(cap, ctx->cap_override);
     g->cap = cap; g->n_sample = (int32_t)S;
-    g->expect_per_row = r_sel > S ? (double)M : (double)r_sel * (double)M / (double)S;
+    g->expect_per_row = r_sel > S_fine ? (double)M : (double)r_sel * (double)M / (double)S_fine;
     if (rows == 0) return;
     // the sampled columns (fixed seed: the sample only steers the filter, never the result) are cached on the device
     // per (M, S): a repeated build of the same shape draws nothing on the host
@@ -807,9 +835,33 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
         ctx->samp_M = M; ctx->samp_S = S;
     }
     struct { int32_t* p; } d_samp{(int32_t*)ctx->samp_dev};
+    float* thr = g->thr_all.p + row0;
+    const float eps = 1.0f / 2048.0f;     // covers the 1-pass error of the sampled correlations (hi plane only: ~1e-5 rms, < 5e-4 worst case)
+    if (fused && ctx->sample_impl == 2) {            // e4m3 operands: measured dead end, kept for the record (corsample.cu)
+        const int32_t G8pad = (int32_t)round_up(Gpad, 128);
+        DevBuf<uint8_t> A8(ctx, (size_t)rows * G8pad), B8(ctx, (size_t)Spad * G8pad);
+        {
+            StageTimer t(ctx, "sample_gather", 2);
+            launch_z8_rows(ctx, g->Zh.p, Gpad, nullptr, row0, rows, G8pad, A8.p);
+            launch_z8_rows(ctx, g->Zh.p, Gpad, d_samp.p, 0, Spad, G8pad, B8.p);
+        }
+        StageTimer t(ctx, "cor_sample_hist");
+        launch_sample_thresholds_fused(ctx, 1, A8.p, rows, B8.p, Spad, G8pad, (int32_t)S, n_tiles1, r_sel, c_hi, c_lo, eps, thr, nullptr);
+        return;                 // temporaries are released in stream order
+    }
+    if (fused) {
+        DevBuf<__half> Zs(ctx, (size_t)Spad * Gpad);
+        {
+            StageTimer t(ctx, "sample_gather");
+            launch_gather_rows(ctx, g->Zh.p, (int64_t)Gpad * sizeof(__half), d_samp.p, (int32_t)Spad, Zs.p);
+        }
+        StageTimer t(ctx, "cor_sample_hist");
+        launch_sample_thresholds_fused(ctx, 0, g->Zh.p + (size_t)row0 * Gpad, rows, Zs.p, Spad, Gpad * (int32_t)sizeof(__half), (int32_t)S,
+                                       n_tiles1, r_sel, c_hi, c_lo, eps, thr, nullptr);
+        return;
+    }
     DevBuf<__half> Zs(ctx, ctx->gemm_impl != 1 ? (size_t)Spad * Gpad : 0);
     DevBuf<float> Zsf(ctx, ctx->gemm_impl != 1 ? 0 : (size_t)Spad * Gpad);
-    float* thr = g->thr_all.p + row0;
     {
         StageTimer t(ctx, "sample_gather");
         if (ctx->gemm_impl != 1) launch_gather_rows(ctx, g->Zh.p, (int64_t)Gpad * sizeof(__half), d_samp.p, (int32_t)Spad, Zs.p);
@@ -820,7 +872,6 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
     const bool tc = ctx->gemm_impl != 1;              // tensor-core path keeps the sampled correlations in fp16
     DevBuf<float> Cs(ctx, tc ? 0 : (size_t)chunk * Spad);
     DevBuf<__half> Cs16(ctx, tc ? (size_t)chunk * Spad : 0);
-    const float eps = 1.0f / 512.0f;      // covers the 1-pass error of the sampled correlations
     for (int64_t c0 = 0; c0 < rows; c0 += chunk) {
         const int64_t nr = std::min(chunk, rows - c0);
         {

@@ -32,6 +32,8 @@ struct mcb_ctx {
     int keep_self = 0;
     int thresh_strict = 1;
     int cap_override = 0;    // test hook: shrink the candidate capacity so rows take the exact-row path
+    int sample_impl = -1;    // kNN threshold pass: -1 / 0 = fused histogram kernel when the shape allows (corsample.cu), 1 = stored fp16 block +
+                             // threshold kernel, 2 = fused kernel on e4m3 operands (measured dead end, see corsample.cu)
     int sample_factor = 128; // kNN threshold pass: sampled columns expected above a row's true cut (more = tighter filter, longer pass)
     int join_impl = -1;      // balancing join: 0 = routed / L2-blocked, 1 = direct probing (single rank only), -1 = auto: direct on one
                              // rank (measured 2.9 ms vs 4.7 ms at C2), routed across ranks (no list all-gather, no replicated tables)
@@ -171,6 +173,11 @@ void launch_tc_store3_ab(mcb_ctx* ctx, const void* Ahi, const void* Alo, int64_t
 void launch_tc_filter(mcb_ctx* ctx, const void* Zh, const void* Zl, int64_t rows_alloc, int64_t a_row0,
                       int64_t a_rows, int64_t b_rows, int32_t Gpad, const float* thr, const CandPool& pool, int32_t part = 0,
                       int32_t nparts = 1);
+// corsample.cu: fused sampling pass (e4m3 operands, per-row histograms in the epilogue)
+void launch_z8_rows(mcb_ctx* ctx, const void* Zh, int32_t Gpad, const int32_t* rows, int64_t row0, int64_t nrows, int32_t G8pad, void* out);
+void launch_sample_thresholds_fused(mcb_ctx* ctx, int f8, const void* A, int64_t a_rows, const void* B, int64_t Spad, int32_t row_bytes,
+                                    int32_t S, int32_t n_tiles1, int32_t r_sel, int32_t c_hi, int32_t c_lo, float eps, float* thr,
+                                    uint32_t* n_escaped);
 // select.cu: symmetric multi-GPU record exchange helpers
 void launch_count_records_by_dest(mcb_ctx* ctx, const CandPool& pool, int64_t rows_per_rank, int32_t nranks, uint64_t* counts);
 void launch_partition_records(mcb_ctx* ctx, const CandPool& pool, int64_t rows_per_rank, int32_t nranks, const uint64_t* base,

@@ -218,6 +218,32 @@ def test_cor_knn_duplicate_cells_and_ties(ctx, oracle):
     g.destroy()
 
 
+@pytest.mark.parametrize("ncells,ngenes,K", [(20000, 300, 20), (33000, 520, 30), (12900, 200, 40)])
+def test_fused_sampling_pass_equals_stored_block_path(ctx, ncells, ngenes, K):
+    """The sampling pass only steers the filter: the fused e4m3 histogram kernel (corsample.cu) and the stored fp16 block +
+    threshold kernel must give identical ranked lists, a similar number of candidates, and (next to) no exact-row fallbacks."""
+    from metacell_b200 import _lib, synth
+    m = synth.make_umi_matrix(ncells, ngenes, n_types=12, median_umis=1500.0, seed=5)
+    feats = np.arange(ngenes, dtype=np.int32)
+    csc = _upload(ctx, m)
+    res = {}
+    try:
+        for impl in (1, -1):
+            ctx.set_option("sample_impl", impl)
+            g = _lib.CGraph.from_csc(ctx, csc, feats, 7.0)
+            g.knn(K, 10)
+            res[impl] = (g.download_knn(), g.knn_stats())
+            g.destroy()
+    finally:
+        ctx.set_option("sample_impl", -1)
+    (c1, v1), s1 = res[1]
+    (c2, v2), s2 = res[-1]
+    assert s1["sample_cols"] >= 4096, "shape too small to reach the fused path"
+    assert np.array_equal(c1, c2) and np.allclose(v1, v2, rtol=0, atol=1e-6)     # exact-row fallbacks sum in another order
+    assert s2["fallback_rows"] <= max(2, ncells // 5000), s2
+    assert 0.85 * s1["candidates"] <= s2["candidates"] <= 1.15 * s1["candidates"], (s1, s2)
+
+
 # ---- A6 / A7 ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("ncells,K,kx,kb", [(1200, 20, 10, 3), (900, 100, 10, 3), (2500, 15, 4, 2)])
 def test_balance_bit_exact_on_same_lists(ctx, oracle, ncells, K, kx, kb):
