@@ -1085,8 +1085,10 @@ static int ilog2_ceil(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) ++l;
 // communicator the buckets of other ranks travel in one all-to-all (the kNN lists themselves never leave their owner and
 // a rank builds rank tables for its own rows only); the probe pass then walks this rank's blocks one by one.  The
 // in-degree cuts (8 bytes per row) are all-gathered at the end.  Option "join_impl": 1 = direct join (every entry probes
-// the table of its target row wherever it lies in memory; single rank only), 0 = routed join, -1 (default) = direct on a
-// single rank, routed across ranks.  The two are bit-identical (tests/test_gpu_cgraph.py::test_routed_join_equals_direct_join).
+// the table of its target row wherever it lies in memory; single rank only), 0 = routed join, 2 = blocked-list join
+// (single rank: the lists are bucketed by target block while the tables are built, probed block-major, mutual keys kept
+// in compact lists), -1 (default) = blocked on a single rank, routed across ranks.  All three are bit-identical
+// (tests/test_gpu_cgraph.py::test_routed_join_equals_direct_join).
 void mcb::cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
 {
     MCB_CHECK(g->knn_col.p, "mcb_cgraph_mutual: run mcb_cgraph_knn first");
@@ -1106,14 +1108,38 @@ void mcb::cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
     // drop the feature planes: they are not needed after the kNN stage and the tables are large
     g->Zf.release(); g->Zh.release(); g->Zl.release();
     const size_t rows1 = (size_t)std::max<int64_t>(rows, 1);
-    g->sym.alloc(ctx, rows1 * Kc);
     g->thr_in.alloc(ctx, (size_t)P * g->rows_per_rank);
     DevBuf<uint32_t> table(ctx, rows1 * H);
+    const int join = P > 1 ? 0 : (ctx->join_impl < 0 ? 2 : ctx->join_impl);
+    g->mut.release(); g->n_mut.release(); g->sym.release();
+    if (join == 2) {
+        // blocked join: lists bucketed by target block in the same pass that builds the tables, block-major probe into
+        // compact lists of mutual keys, in-degree cut on the compact lists
+        const BlockedShape bs = blocked_shape(rows, H);
+        DevBuf<uint32_t> blist(ctx, rows1 * Kc);
+        DevBuf<uint16_t> off(ctx, rows1 * (size_t)(bs.nb + 1));
+        g->mut.alloc(ctx, rows1 * Kc);
+        g->n_mut.alloc(ctx, rows1);
+        g->n_mut.zero();
+        {
+            StageTimer t(ctx, "balance_hash");
+            launch_prepare_blocked(ctx, g->knn_col.p, rows, Kc, H, g->rank_bits, bs, ctx->keep_self, table.p, blist.p, off.p);
+        }
+        {
+            StageTimer t(ctx, "balance_probe");
+            launch_probe_blocked(ctx, blist.p, off.p, rows, Kc, bs, table.p, H, g->rank_bits, smax, ctx->thresh_strict, g->mut.p, g->n_mut.p);
+        }
+        StageTimer t(ctx, "balance_cut");
+        launch_mutual(ctx, g->knn_col.p, table.p, row0, rows, Kc, H, g->rank_bits, smax, ctx->thresh_strict, ctx->keep_self, g->K * k_beta,
+                      nullptr, g->thr_in.p, /*have_scores=*/2, g->mut.p, g->n_mut.p);
+        return;
+    }
+    g->sym.alloc(ctx, rows1 * Kc);
     {
         StageTimer t(ctx, "balance_hash");
         launch_build_hash(ctx, g->knn_col.p, rows, Kc, H, g->rank_bits, table.p);        // own rows only
     }
-    if (P == 1 && ctx->join_impl != 0) {
+    if (join == 1) {
         StageTimer t(ctx, "balance_mutual");
         launch_mutual(ctx, g->knn_col.p, table.p, row0, rows, Kc, H, g->rank_bits, smax, ctx->thresh_strict, ctx->keep_self,
                       g->K * k_beta, g->sym.p, g->thr_in.p, /*have_scores=*/0);
@@ -1201,7 +1227,7 @@ extern "C" int mcb_cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
 }
 int64_t mcb::cgraph_prune(mcb_cgraph* g)
 {
-    MCB_CHECK(g->sym.p, "mcb_cgraph_prune: run mcb_cgraph_mutual first");
+    MCB_CHECK(g->sym.p || g->mut.p, "mcb_cgraph_prune: run mcb_cgraph_mutual first");
     mcb_ctx* ctx = g->ctx;
     MCB_CUDA(cudaSetDevice(ctx->device));
     const int64_t rows = g->rows;
@@ -1212,7 +1238,8 @@ int64_t mcb::cgraph_prune(mcb_cgraph* g)
     g->out_s.alloc(ctx, rk);
     {
         StageTimer t(ctx, "balance_prune");
-        launch_prune(ctx, g->knn_col.p, g->sym.p, g->thr_in.p, g->row0, rows, g->Kc, K, (int64_t)g->K * g->K * g->k_expand, g->out_deg.p, g->out_dst.p, g->out_s.p);
+        launch_prune(ctx, g->knn_col.p, g->sym.p, g->thr_in.p, g->row0, rows, g->Kc, K, (int64_t)g->K * g->K * g->k_expand, g->out_deg.p, g->out_dst.p, g->out_s.p,
+                     g->mut.p, g->n_mut.p);
     }
     DevBuf<int64_t> deg64(ctx, (size_t)std::max<int64_t>(rows, 1)), offs(ctx, (size_t)std::max<int64_t>(rows, 1)), total(ctx, 1);
     int64_t ne = 0;

@@ -20,6 +20,7 @@
 // only ever needs the tables of its own rows, and the records (not the whole kNN lists) cross NVLink once.
 // Selection kernels are one CTA per row with the row's keys in registers; HBM-bound integer work.
 #include "internal.h"
+#include <cstdlib>
 
 namespace mcb {
 
@@ -218,14 +219,156 @@ probe_kernel(const uint64_t* __restrict__ records, int64_t n_records, const int6
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// blocked join (single rank): the lists themselves are bucketed, no record stream
+// ---------------------------------------------------------------------------------------------------------------
+// prepare: one CTA per row builds the row's rank table (as build_hash_kernel) AND writes the row's list grouped by the
+// block of 2^blk_shift rows that holds each target: blist[row][off[row][b] .. off[row][b+1]) = (j << rank_bits) | rank0
+// for the targets j of block b (self dropped unless keep_self).  The probe pass then walks (block, row) segments
+// block-major: the slice of tables it probes (<= 32 MB) stays in L2, every table atom comes from HBM once, and the
+// list is read in contiguous segments -- no count pass, no scatter pass, no 8-byte records.
+constexpr int MAX_JOIN_BLOCKS = 128;
+__global__ void __launch_bounds__(BAL_THREADS)
+prepare_blocked_kernel(const int32_t* __restrict__ knn_col, int64_t M, int32_t Kc, int32_t H, int32_t log2H, int32_t rank_bits,
+                       int32_t blk_shift, int32_t nb, int keep_self, uint32_t* __restrict__ table, uint32_t* __restrict__ blist,
+                       uint16_t* __restrict__ off)
+{
+    extern __shared__ uint32_t stab[];      // [H]
+    __shared__ uint32_t bcount[MAX_JOIN_BLOCKS + 1], bcur[MAX_JOIN_BLOCKS];
+    for (int64_t row = blockIdx.x; row < M; row += gridDim.x) {
+        for (int q = threadIdx.x; q < H; q += BAL_THREADS) stab[q] = HASH_EMPTY;
+        for (int q = threadIdx.x; q <= nb; q += BAL_THREADS) bcount[q] = 0;
+        __syncthreads();
+        const int32_t* kc = knn_col + row * (int64_t)Kc;
+        for (int r = threadIdx.x; r < Kc; r += BAL_THREADS) {
+            const int32_t j = kc[r];
+            if (j < 0) continue;
+            const uint32_t val = ((uint32_t)j << rank_bits) | (uint32_t)r;
+            uint32_t slot = hash_slot((uint32_t)j, log2H);
+            while (atomicCAS(&stab[slot], HASH_EMPTY, val) != HASH_EMPTY) slot = (slot + 1) & (uint32_t)(H - 1);
+            if (j != (int32_t)row || keep_self) atomicAdd(&bcount[j >> blk_shift], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {             // exclusive prefix of the block counts (nb <= 128: four per lane)
+            uint32_t v[MAX_JOIN_BLOCKS / 32], loc = 0;
+#pragma unroll
+            for (int q = 0; q < MAX_JOIN_BLOCKS / 32; ++q) {
+                const int b = (int)threadIdx.x * (MAX_JOIN_BLOCKS / 32) + q;
+                v[q] = b < nb ? bcount[b] : 0u;
+                loc += v[q];
+            }
+            uint32_t incl = loc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += u; }
+            uint32_t run = incl - loc;
+#pragma unroll
+            for (int q = 0; q < MAX_JOIN_BLOCKS / 32; ++q) {
+                const int b = (int)threadIdx.x * (MAX_JOIN_BLOCKS / 32) + q;
+                if (b < nb) { bcur[b] = run; off[row * (int64_t)(nb + 1) + b] = (uint16_t)run; }
+                run += v[q];
+            }
+            if (threadIdx.x == 31) off[row * (int64_t)(nb + 1) + nb] = (uint16_t)run;
+        }
+        __syncthreads();
+        uint32_t* bl = blist + row * (int64_t)Kc;
+        for (int r = threadIdx.x; r < Kc; r += BAL_THREADS) {
+            const int32_t j = kc[r];
+            if (j < 0 || (j == (int32_t)row && !keep_self)) continue;
+            bl[atomicAdd(&bcur[j >> blk_shift], 1u)] = ((uint32_t)j << rank_bits) | (uint32_t)r;
+        }
+        uint32_t* out = table + row * (int64_t)H;
+        for (int q = threadIdx.x; q < H; q += BAL_THREADS) out[q] = stab[q];
+        __syncthreads();
+    }
+}
+
+// probe, block-major: item = b * M + i, one warp per item.  For every entry (i -> j, rank r) of the segment whose
+// reverse rank r' exists and whose score s = (r + 1) * r' passes the threshold, the key (s << 32) | j is appended to
+// row i's COMPACT list of mutual edges (one returning atomic per warp and segment; the order inside a row's list is
+// arbitrary, every later step selects by key).  Most of a row's Kc entries are not mutual or fail the threshold, so
+// the later steps read a fraction of the list.
+// L2 cache policies: the block's tables should stay resident while the one-pass streams (list entries in, mutual keys out)
+// go through
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint32_t ld_hint(const uint32_t* p, uint64_t pol)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+__global__ void __launch_bounds__(256)
+probe_blocked_kernel(const uint32_t* __restrict__ blist, const uint16_t* __restrict__ off, int64_t M, int32_t Kc, int32_t nb,
+                     const uint32_t* __restrict__ table, int32_t H, int32_t log2H, int32_t rank_bits, long long smax, int strict,
+                     uint64_t* __restrict__ mut, uint32_t* __restrict__ n_mut)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp0 = ((uint32_t)blockIdx.x * 256u + threadIdx.x) >> 5, nwarps = ((uint32_t)gridDim.x * 256u) >> 5;
+    const uint32_t rmask = (1u << rank_bits) - 1u;
+    const uint32_t Mu = (uint32_t)M;
+    const uint64_t keep = l2_policy_evict_last(), stream = l2_policy_evict_first();
+    // scores are products of two ranks <= 4096; strict: s < smax  <=>  s <= smax - 1
+    const uint32_t slim = (uint32_t)(smax > 0x7fffffffll ? 0x7fffffffll : smax) - (strict ? 1u : 0u);
+    // item = b * M + i, visited block-major; (b, i) advance without a division
+    const uint32_t step_b = nwarps / Mu, step_i = nwarps - step_b * Mu;
+    uint32_t b = warp0 / Mu, i = warp0 - b * Mu;
+    for (; b < (uint32_t)nb; ) {
+        const uint16_t* o = off + (size_t)i * (uint32_t)(nb + 1) + b;
+        const int o0 = o[0], o1 = o[1];
+        const uint32_t* bl = blist + (size_t)i * (uint32_t)Kc;
+        // two entries per lane and pass: their list loads, then their first table probes, are in flight together
+        // (a segment holds ~Kc / nb entries; the latency chain offsets -> entries -> probes -> slot bounds this kernel)
+        for (int e0 = o0; e0 < o1; e0 += 64) {
+            const int ea = e0 + lane, eb = e0 + 32 + lane;
+            const uint32_t wa = ea < o1 ? ld_hint(bl + ea, stream) : 0u, wb = eb < o1 ? ld_hint(bl + eb, stream) : 0u;
+            const uint32_t ja = wa >> rank_bits, jb = wb >> rank_bits;
+            const uint32_t* ta = table + (size_t)ja * (uint32_t)H;
+            const uint32_t* tb = table + (size_t)jb * (uint32_t)H;
+            uint32_t sa = hash_slot(i, log2H), sb = sa;
+            uint32_t va = ea < o1 ? ld_hint(ta + sa, keep) : HASH_EMPTY, vb = eb < o1 ? ld_hint(tb + sb, keep) : HASH_EMPTY;
+            while (va != HASH_EMPTY && (va >> rank_bits) != i) { sa = (sa + 1) & (uint32_t)(H - 1); va = ld_hint(ta + sa, keep); }
+            while (vb != HASH_EMPTY && (vb >> rank_bits) != i) { sb = (sb + 1) & (uint32_t)(H - 1); vb = ld_hint(tb + sb, keep); }
+            uint32_t ra = va != HASH_EMPTY ? (va & rmask) + 1u : 0u, rb = vb != HASH_EMPTY ? (vb & rmask) + 1u : 0u;
+            if (ea < o1 && ja == i) ra = (wa & rmask) + 1u;            // self (keep_self): its own rank
+            if (eb < o1 && jb == i) rb = (wb & rmask) + 1u;
+            const uint32_t sca = ((wa & rmask) + 1u) * ra, scb = ((wb & rmask) + 1u) * rb;
+            const bool oka = ra != 0u && sca <= slim, okb = rb != 0u && scb <= slim;
+            const unsigned ma = __ballot_sync(0xffffffffu, oka), mb = __ballot_sync(0xffffffffu, okb);
+            if (ma | mb) {
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&n_mut[i], (uint32_t)(__popc(ma) + __popc(mb)));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                uint64_t* dst = mut + (size_t)i * (uint32_t)Kc + base;
+                const unsigned below = (1u << lane) - 1u;
+                if (oka) __stcs(reinterpret_cast<unsigned long long*>(dst + __popc(ma & below)), ((unsigned long long)sca << 32) | ja);
+                if (okb) __stcs(reinterpret_cast<unsigned long long*>(dst + __popc(ma) + __popc(mb & below)), ((unsigned long long)scb << 32) | jb);
+            }
+        }
+        i += step_i; b += step_b;
+        if (i >= Mu) { i -= Mu; ++b; }
+    }
+}
+
 // mutual scores s(i, r) and the in-degree threshold of every owned row
 template <int IPT>      // 256 * IPT >= Kc keys sorted per row, register resident
 __global__ void __launch_bounds__(BAL_THREADS, IPT <= 4 ? 4 : 1)
 mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ table, int64_t row0, int64_t rows,
               int32_t Kc, int32_t H, int32_t log2H, int32_t rank_bits, long long smax, int strict, int keep_self,
-              int32_t kin, uint32_t* __restrict__ sym, uint64_t* __restrict__ thr_in, int have_scores)
+              int32_t kin, uint32_t* __restrict__ sym, uint64_t* __restrict__ thr_in, int have_scores,
+              const uint64_t* __restrict__ mut, const uint32_t* __restrict__ n_mut)
 {
-    // have_scores: sym already holds the scores (routed join); otherwise they are computed here by probing the
+    // have_scores = 2: the row's mutual keys are the compact list mut / n_mut (blocked join);
+    // have_scores = 1: sym already holds the scores (routed join); otherwise they are computed here by probing the
     // tables of ALL rows (direct join, single rank only; kept as the cross-check of the routed one).
     // knn_col holds the rank's own rows (row lrow of the buffer = global row row0 + lrow).
     extern __shared__ uint64_t sk[];        // [256 * IPT]
@@ -243,9 +386,11 @@ mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ 
             const int r = q * BAL_THREADS + threadIdx.x;          // coalesced over the rank list (any order sorts)
             uint64_t kv = ~0ull;
             if (r < Kc) {
-                const int32_t j = kc[r];
+                const int32_t j = have_scores == 2 ? 0 : kc[r];
                 uint32_t sv = 0;
-                if (have_scores) {
+                if (have_scores == 2) {          // compact list of mutual keys (blocked join): n_mut[lrow] keys at mut
+                    if (r < (int)n_mut[lrow]) kv = mut[lrow * (int64_t)Kc + r];
+                } else if (have_scores) {
                     sv = so[r];
                     if (sv) kv = ((uint64_t)sv << 32) | (uint32_t)j;
                 } else {
@@ -290,10 +435,13 @@ mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ 
                 for (int q = 0; q < IPT; ++q)
                     if (key[q] != ~0ull && (int)((uint32_t)(key[q] >> 32) >> bin_shift) == bsel) sk[atomicAdd(&s_sel, 1)] = key[q];
                 __syncthreads();
-                uint64_t k1[1] = {threadIdx.x < m ? sk[threadIdx.x] : ~0ull};
-                __syncthreads();
-                bitonic_sort_regs_u64<1>(k1, sk);
-                if (threadIdx.x == idx) thr_in[i] = k1[0];
+                // the bin holds a handful of keys: each finds its rank by counting (keys are distinct), no sorting network
+                if ((int)threadIdx.x < m) {
+                    const uint64_t k = sk[threadIdx.x];
+                    int rank = 0;
+                    for (int q = 0; q < m; ++q) rank += sk[q] < k ? 1 : 0;
+                    if (rank == idx) thr_in[i] = k;
+                }
             } else {
                 bitonic_sort_regs_u64<IPT>(key, sk);
 #pragma unroll
@@ -311,7 +459,8 @@ template <int IPT>
 __global__ void __launch_bounds__(BAL_THREADS, IPT <= 4 ? 4 : 1)
 prune_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ sym, const uint64_t* __restrict__ thr_in,
              int64_t row0, int64_t rows, int32_t Kc, int32_t K, long long smax, int32_t* __restrict__ out_deg,
-             int32_t* __restrict__ out_dst, int32_t* __restrict__ out_s)
+             int32_t* __restrict__ out_dst, int32_t* __restrict__ out_s, const uint64_t* __restrict__ mut,
+             const uint32_t* __restrict__ n_mut)
 {
     extern __shared__ uint64_t sk[];        // [256 * IPT]
     __shared__ uint32_t hist[BAL_BINS];
@@ -330,7 +479,13 @@ prune_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ s
         for (int q = 0; q < IPT; ++q) {
             const int r = q * BAL_THREADS + threadIdx.x;
             uint64_t kv = ~0ull;
-            if (r < Kc) {
+            if (mut) {                       // compact list of mutual keys (blocked join)
+                if (r < (int)n_mut[lrow]) {
+                    const uint64_t k = mut[lrow * (int64_t)Kc + r];
+                    const uint64_t inkey = (k & 0xffffffff00000000ull) | (uint32_t)i;   // edge i -> j seen from target j
+                    if (inkey <= thr_in[(uint32_t)k]) { kv = k; ++local; }
+                }
+            } else if (r < Kc) {
                 const uint32_t s = so[r];
                 if (s) {
                     const int32_t j = kc[r];
@@ -365,11 +520,15 @@ prune_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ s
             for (int q = 0; q < IPT; ++q)
                 if (key[q] != ~0ull && (int)((uint32_t)(key[q] >> 32) >> bin_shift) <= bsel) sk[atomicAdd(&s_sel, 1)] = key[q];
             __syncthreads();
-            uint64_t k1[1] = {threadIdx.x < total ? sk[threadIdx.x] : ~0ull};
+            // ~K + a few keys: rank by counting (keys are distinct) instead of a 256-key sorting network with its barriers
+            uint64_t k = ~0ull;
+            int rank = 0;
+            if ((int)threadIdx.x < total) {
+                k = sk[threadIdx.x];
+                for (int q = 0; q < total; ++q) rank += sk[q] < k ? 1 : 0;
+            }
             __syncthreads();
-            bitonic_sort_regs_u64<1>(k1, sk);
-            __syncthreads();
-            sk[threadIdx.x] = k1[0];
+            if ((int)threadIdx.x < total) sk[rank] = k;
         } else {
             bitonic_sort_regs_u64<IPT>(key, sk);
             __syncthreads();
@@ -439,25 +598,27 @@ void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t 
 template <int IPT>
 static void launch_mutual_t(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* table, int64_t row0, int64_t rows,
                             int32_t Kc, int32_t H, int32_t rank_bits, int64_t smax, int strict, int keep_self, int32_t kin,
-                            uint32_t* sym, uint64_t* thr_in, int have_scores)
+                            uint32_t* sym, uint64_t* thr_in, int have_scores, const uint64_t* mut, const uint32_t* n_mut)
 {
     static SmemOptIn optin;
     const size_t smem = (size_t)IPT * 256 * sizeof(uint64_t);
     ensure_smem(ctx, mutual_kernel<IPT>, smem, optin);
     const int grid = wave_grid(ctx, mutual_kernel<IPT>, smem, rows);
     mutual_kernel<IPT><<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, table, row0, rows, Kc, H, ilog2(H), rank_bits,
-                                                                  (long long)smax, strict, keep_self, kin, sym, thr_in, have_scores);
+                                                                  (long long)smax, strict, keep_self, kin, sym, thr_in, have_scores, mut, n_mut);
     MCB_LAUNCH_CHECK();
 }
 template <int IPT>
 static void launch_prune_t(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* sym, const uint64_t* thr_in, int64_t row0,
-                           int64_t rows, int32_t Kc, int32_t K, int64_t smax, int32_t* out_deg, int32_t* out_dst, int32_t* out_s)
+                           int64_t rows, int32_t Kc, int32_t K, int64_t smax, int32_t* out_deg, int32_t* out_dst, int32_t* out_s,
+                           const uint64_t* mut, const uint32_t* n_mut)
 {
     static SmemOptIn optin;
     const size_t smem = (size_t)IPT * 256 * sizeof(uint64_t);
     ensure_smem(ctx, prune_kernel<IPT>, smem, optin);
     const int grid = wave_grid(ctx, prune_kernel<IPT>, smem, rows);
-    prune_kernel<IPT><<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, sym, thr_in, row0, rows, Kc, K, (long long)smax, out_deg, out_dst, out_s);
+    prune_kernel<IPT><<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, sym, thr_in, row0, rows, Kc, K, (long long)smax, out_deg, out_dst, out_s,
+                                                                 mut, n_mut);
     MCB_LAUNCH_CHECK();
 }
 
@@ -517,23 +678,60 @@ void launch_probe(mcb_ctx* ctx, const uint64_t* records, int64_t n_records, cons
     MCB_LAUNCH_CHECK();
 }
 
+// blocked join (single rank).  Block = the largest power of two of rows whose tables fit 32 MB, at most MAX_JOIN_BLOCKS blocks
+BlockedShape blocked_shape(int64_t M, int32_t H)
+{
+    BlockedShape bs;
+    static const int64_t block_mb = getenv("MCB_JOIN_BLOCK_MB") ? std::max(1, atoi(getenv("MCB_JOIN_BLOCK_MB"))) : 32;     // tuning hook
+    int32_t shift = 6;
+    while (((int64_t)H * 4 << (shift + 1)) <= (block_mb << 20)) ++shift;
+    while (ceil_div(std::max<int64_t>(M, 1), (int64_t)1 << shift) > MAX_JOIN_BLOCKS) ++shift;
+    bs.blk_shift = shift; bs.nb = (int32_t)ceil_div(std::max<int64_t>(M, 1), (int64_t)1 << shift);
+    return bs;
+}
+void launch_prepare_blocked(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t Kc, int32_t H, int32_t rank_bits, const BlockedShape& bs,
+                            int keep_self, uint32_t* table, uint32_t* blist, uint16_t* off)
+{
+    if (M == 0) return;
+    MCB_CHECK(Kc < 65536 && bs.nb <= MAX_JOIN_BLOCKS, "balance: blocked join shape out of range");
+    static SmemOptIn optin;
+    const size_t smem = (size_t)H * sizeof(uint32_t);
+    ensure_smem(ctx, prepare_blocked_kernel, smem, optin);
+    const int grid = wave_grid(ctx, prepare_blocked_kernel, smem, M);
+    prepare_blocked_kernel<<<grid, BAL_THREADS, smem, ctx->stream>>>(knn_col, M, Kc, H, ilog2(H), rank_bits, bs.blk_shift, bs.nb, keep_self,
+                                                                      table, blist, off);
+    MCB_LAUNCH_CHECK();
+}
+void launch_probe_blocked(mcb_ctx* ctx, const uint32_t* blist, const uint16_t* off, int64_t M, int32_t Kc, const BlockedShape& bs,
+                          const uint32_t* table, int32_t H, int32_t rank_bits, int64_t smax, int strict, uint64_t* mut, uint32_t* n_mut)
+{
+    if (M == 0) return;
+    int per_sm = 0;
+    MCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, probe_blocked_kernel, 256, 0));
+    const int grid = (int)std::min<int64_t>(ceil_div((int64_t)bs.nb * M, 8), (int64_t)ctx->num_sms * std::max(per_sm, 1));
+    probe_blocked_kernel<<<grid, 256, 0, ctx->stream>>>(blist, off, M, Kc, bs.nb, table, H, ilog2(H), rank_bits, (long long)smax, strict, mut, n_mut);
+    MCB_LAUNCH_CHECK();
+}
+
 void launch_mutual(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* table, int64_t row0, int64_t rows,
                    int32_t Kc, int32_t H, int32_t rank_bits, int64_t smax, int strict, int keep_self, int32_t kin,
-                   uint32_t* sym, uint64_t* thr_in, int have_scores)
+                   uint32_t* sym, uint64_t* thr_in, int have_scores, const uint64_t* mut, const uint32_t* n_mut)
 {
     if (rows == 0) return;
     MCB_CHECK(Kc <= 4096, "MC-ERR: K * k_expand above 4096 is not supported");
-#define CALL(I) launch_mutual_t<I>(ctx, knn_col, table, row0, rows, Kc, H, rank_bits, smax, strict, keep_self, kin, sym, thr_in, have_scores)
+    MCB_CHECK(have_scores != 2 || (mut && n_mut), "balance: compact lists missing");
+#define CALL(I) launch_mutual_t<I>(ctx, knn_col, table, row0, rows, Kc, H, rank_bits, smax, strict, keep_self, kin, sym, thr_in, have_scores, mut, n_mut)
     MCB_DISPATCH_IPT(Kc, CALL);
 #undef CALL
 }
 
 void launch_prune(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* sym, const uint64_t* thr_in, int64_t row0,
-                  int64_t rows, int32_t Kc, int32_t K, int64_t smax, int32_t* out_deg, int32_t* out_dst, int32_t* out_s)
+                  int64_t rows, int32_t Kc, int32_t K, int64_t smax, int32_t* out_deg, int32_t* out_dst, int32_t* out_s,
+                  const uint64_t* mut, const uint32_t* n_mut)
 {
     if (rows == 0) return;
     MCB_CHECK(Kc <= 4096, "MC-ERR: K * k_expand above 4096 is not supported");
-#define CALL(I) launch_prune_t<I>(ctx, knn_col, sym, thr_in, row0, rows, Kc, K, smax, out_deg, out_dst, out_s)
+#define CALL(I) launch_prune_t<I>(ctx, knn_col, sym, thr_in, row0, rows, Kc, K, smax, out_deg, out_dst, out_s, mut, n_mut)
     MCB_DISPATCH_IPT(Kc, CALL);
 #undef CALL
 }

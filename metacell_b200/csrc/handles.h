@@ -37,6 +37,7 @@ struct mcb_cgraph {
     // balance
     int32_t H = 0, rank_bits = 0, k_beta = 0;
     mcb::DevBuf<uint32_t> sym; mcb::DevBuf<uint64_t> thr_in;
+    mcb::DevBuf<uint64_t> mut; mcb::DevBuf<uint32_t> n_mut;   // blocked join: compact per-row lists of mutual keys (replace sym)
     mcb::DevBuf<int32_t> out_deg, out_dst, out_s;
     int64_t n_edges = 0;
     mcb::DevBuf<int32_t> e_src, e_dst; mcb::DevBuf<double> e_w;

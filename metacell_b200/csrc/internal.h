@@ -35,8 +35,8 @@ struct mcb_ctx {
     int sample_impl = -1;    // kNN threshold pass: -1 / 0 = fused histogram kernel when the shape allows (corsample.cu), 1 = stored fp16 block +
                              // threshold kernel, 2 = fused kernel on e4m3 operands (measured dead end, see corsample.cu)
     int sample_factor = 128; // kNN threshold pass: sampled columns expected above a row's true cut (more = tighter filter, longer pass)
-    int join_impl = -1;      // balancing join: 0 = routed / L2-blocked, 1 = direct probing (single rank only), -1 = auto: direct on one
-                             // rank (measured 2.9 ms vs 4.7 ms at C2), routed across ranks (no list all-gather, no replicated tables)
+    int join_impl = -1;      // balancing join: 0 = routed records, 1 = direct probing (single rank only), 2 = blocked lists (single rank
+                             // only), -1 = auto: blocked on one rank, routed across ranks (no list all-gather, no replicated tables)
     int host_threads = 0;    // staging threads per context (0 = min(16, cores / 2), env MCB_HOST_THREADS)
     mcb::Staging* staging = nullptr;     // pinned ring + copy stream + host threads, created on first use (staging.cu)
     // cached sample of column indices for the kNN threshold pass, keyed by (M, S): the sample only steers the filter
@@ -234,7 +234,15 @@ void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t 
 // knn_col of launch_mutual / launch_prune / launch_route_records: the rank's OWN rows ([rows][Kc], row 0 = global row row0)
 void launch_mutual(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* table, int64_t row0, int64_t rows,
                    int32_t Kc, int32_t H, int32_t rank_bits, int64_t smax, int strict, int keep_self, int32_t kin,
-                   uint32_t* sym, uint64_t* thr_in, int have_scores);
+                   uint32_t* sym, uint64_t* thr_in, int have_scores, const uint64_t* mut = nullptr, const uint32_t* n_mut = nullptr);
+// blocked join (balance.cu, single rank): lists bucketed by the block of rows of their target, probed block-major, mutual
+// keys appended to compact per-row lists (mut [rows][Kc] u64 (s << 32 | j), n_mut [rows])
+struct BlockedShape { int32_t blk_shift, nb; };
+BlockedShape blocked_shape(int64_t M, int32_t H);
+void launch_prepare_blocked(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t Kc, int32_t H, int32_t rank_bits, const BlockedShape& bs,
+                            int keep_self, uint32_t* table, uint32_t* blist, uint16_t* off);
+void launch_probe_blocked(mcb_ctx* ctx, const uint32_t* blist, const uint16_t* off, int64_t M, int32_t Kc, const BlockedShape& bs,
+                          const uint32_t* table, int32_t H, int32_t rank_bits, int64_t smax, int strict, uint64_t* mut, uint32_t* n_mut);
 // routed join (balance.cu): entries bucketed by (owner rank, block of rows) of their target, then probed block by block
 struct RouteShape { int32_t blk_shift, nbr, nbuckets, grid; };
 RouteShape route_shape(mcb_ctx* ctx, int64_t rows_per_rank, int32_t nranks, int32_t H, int32_t rank_bits);
@@ -245,7 +253,8 @@ void launch_probe(mcb_ctx* ctx, const uint64_t* records, int64_t n_records, cons
                   const int32_t* seg_block, int32_t nseg, int32_t blk_shift, const uint32_t* table_own, int32_t H, int32_t rank_bits,
                   int32_t Kc, int64_t smax, int strict, uint32_t* sym_own);
 void launch_prune(mcb_ctx* ctx, const int32_t* knn_col, const uint32_t* sym, const uint64_t* thr_in, int64_t row0,
-                  int64_t rows, int32_t Kc, int32_t K, int64_t smax, int32_t* out_deg, int32_t* out_dst, int32_t* out_s);
+                  int64_t rows, int32_t Kc, int32_t K, int64_t smax, int32_t* out_deg, int32_t* out_dst, int32_t* out_s,
+                  const uint64_t* mut = nullptr, const uint32_t* n_mut = nullptr);
 void launch_widen_i32(mcb_ctx* ctx, const int32_t* in, int64_t* out, int64_t n);
 void launch_emit_edges(mcb_ctx* ctx, const int32_t* out_deg, const int32_t* out_dst, const int64_t* offs,
                        const int32_t* cell_of_row, int64_t row0, int64_t rows, int32_t K, int32_t* src, int32_t* dst,

@@ -333,15 +333,15 @@ def test_errors_are_reported_not_thrown(ctx):
 
 @pytest.mark.parametrize("ncells,K,kx,kb", [(1200, 20, 10, 3), (5000, 100, 10, 3), (9000, 150, 10, 3), (300, 40, 10, 3)])
 def test_routed_join_equals_direct_join(ctx, oracle, ncells, K, kx, kb):
-    """the L2-blocked routed join (default) and the direct probing join give bit-identical balanced graphs; several
-    row blocks, Kc above and below the number of cells, self edges kept and dropped"""
+    """the routed join (multi-rank default), the direct probing join and the blocked-list join (single-rank default) give
+    bit-identical balanced graphs; several row blocks, Kc above and below the number of cells, self edges kept and dropped"""
     from metacell_b200 import _lib
     m = _small(ncells=ncells)
     feats = np.arange(0, 500, 2, dtype=np.int32)
     csc = _upload(ctx, m)
     out = {}
     for keep_self in (0, 1):
-        for impl in (0, 1):
+        for impl in (0, 1, 2):
             ctx.set_option("join_impl", impl)
             ctx.set_option("keep_self", keep_self)
             try:
@@ -356,6 +356,7 @@ def test_routed_join_equals_direct_join(ctx, oracle, ncells, K, kx, kb):
                 ctx.set_option("join_impl", -1)
                 ctx.set_option("keep_self", 0)
         assert all(np.array_equal(a, b) for a, b in zip(out[0], out[1])), keep_self
+        assert all(np.array_equal(a, b) for a, b in zip(out[2], out[1])), keep_self
         deg, odst, _ = oracle.balance(col, K, kx, kb, keep_self=bool(keep_self))
         osrc, odst2, ow = oracle.edges_from_balance(deg, odst, K)
         assert np.array_equal(out[0][0], osrc) and np.array_equal(out[0][1], odst2) and np.array_equal(out[0][2], ow)
