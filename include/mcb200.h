@@ -212,9 +212,10 @@ int  mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* sr
                      const double* w, int32_t n_resamp, int32_t n_s, const int32_t* samples,
                      const uint64_t* seeds, int32_t min_mc_size, double cooling, int32_t burn_in,
                      int32_t max_sweeps, int32_t rank, int32_t nranks, mcb_coclust** out);
-/* the same with tgs_graph_cover_resample's `knn` argument (R/coclust_graph_cov.r:39-41: K = round(nrow(edges)/ncells)):
- * the most out-edges a node may use inside one resample, 0 = no limit.  A resample in which some node has more than
- * knn sampled out-neighbours is rejected (MC-ERR) rather than silently covered without the limit.                  */
+/* the same with tgs_graph_cover_resample's `knn` argument (R/coclust_graph_cov.r:39-41: K = round(nrow(edges)/ncells), the
+ * graph's AVERAGE out-degree): the most out edges a node may use inside one resample, 0 = no limit.  Among a sampled node's
+ * out edges whose target is sampled too, the knn of highest weight (ties: lower target index) exist in that resample; the
+ * others are dropped for it, in both directions (oracle/oracle.py truncate_edges states the rule).                  */
 int  mcb_coclust_run2(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst,
                       const double* w, int32_t n_resamp, int32_t n_s, const int32_t* samples,
                       const uint64_t* seeds, int32_t min_mc_size, double cooling, int32_t burn_in,

@@ -593,8 +593,8 @@ def resample_index_sets(ncells, p_resamp, n_resamp, seed):
 def tgs_graph_cover_resample(edges, knn, min_cluster_size, cooling, burn_in, p_resamp, n_resamp, method="full",
                              n_nodes=None, seed=None, ctx=None, max_sweeps=1000):
     """tgstat call of reference R/coclust_graph_cov.r:41.  edges: dict col1, col2, weight (0-based codes).
-    `knn` (R passes K = round(nrow(edges) / ncells), R/coclust_graph_cov.r:39) caps the out-edges a node may use inside
-    one resample; 0 = no cap.  Returns dict(co_cluster = dict(node1, node2, cnt), samples = int[N])."""
+    `knn` (R passes K = round(nrow(edges) / ncells), the average out-degree, R/coclust_graph_cov.r:39) caps the out edges a
+    node may use inside one resample: its knn heaviest edges among those whose target was sampled too; 0 = no cap.  Returns dict(co_cluster = dict(node1, node2, cnt), samples = int[N])."""
     if method != "full":
         raise McbError("MC-ERR: only method = \"full\" is supported (what metacell calls)")
     ctx = _ctx(ctx)

@@ -1527,16 +1527,18 @@ struct CoverCsr {
     DevBuf<int32_t> src, dst; DevBuf<double> w;
     DevBuf<int32_t> odeg, ideg, optr32, iptr32; DevBuf<int64_t> optr, iptr;
     DevBuf<int32_t> odst, isrc, scratch; DevBuf<uint32_t> ow, iw; DevBuf<int2> oe, ie; DevBuf<int4> nd;
+    DevBuf<uint16_t> ipos;          // position of every in edge inside its source's out segment (edge truncation, `knn`)
     int32_t max_out = 0, max_in = 0;
 };
-static void cover_csr_build(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst, const double* w, CoverCsr& c)
+static void cover_csr_build(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst, const double* w, bool sort_out,
+                            CoverCsr& c)
 {
     const size_t ne1 = (size_t)std::max<int64_t>(n_edges, 1);
     c.src.alloc(ctx, ne1); c.dst.alloc(ctx, ne1); c.w.alloc(ctx, ne1);
     c.odeg.alloc(ctx, (size_t)N + 1); c.ideg.alloc(ctx, (size_t)N + 1); c.optr32.alloc(ctx, (size_t)N + 1); c.iptr32.alloc(ctx, (size_t)N + 1);
     c.optr.alloc(ctx, (size_t)N + 1); c.iptr.alloc(ctx, (size_t)N + 1);
     c.odst.alloc(ctx, ne1); c.isrc.alloc(ctx, ne1); c.scratch.alloc(ctx, 4);
-    c.ow.alloc(ctx, ne1); c.iw.alloc(ctx, ne1); c.oe.alloc(ctx, ne1); c.ie.alloc(ctx, ne1); c.nd.alloc(ctx, (size_t)N);
+    c.ow.alloc(ctx, ne1); c.iw.alloc(ctx, ne1); c.oe.alloc(ctx, ne1); c.ie.alloc(ctx, ne1); c.nd.alloc(ctx, (size_t)N); c.ipos.alloc(ctx, ne1);
     {
         StageTimer t(ctx, "h2d_graph");
         if (n_edges) {
@@ -1549,7 +1551,7 @@ static void cover_csr_build(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int3
         StageTimer t(ctx, "graph_csr", 8);
         c.odeg.zero(); c.ideg.zero(); c.scratch.zero();
         launch_build_cover_csr(ctx, N, n_edges, c.src.p, c.dst.p, c.w.p, c.odeg.p, c.ideg.p, c.optr32.p, c.iptr32.p, c.odst.p, c.ow.p,
-                               c.isrc.p, c.iw.p, c.oe.p, c.ie.p, c.nd.p, c.scratch.p);
+                               c.isrc.p, c.iw.p, c.oe.p, c.ie.p, c.nd.p, c.ipos.p, sort_out, c.scratch.p);
         launch_widen_i32(ctx, c.optr32.p, c.optr.p, (int64_t)N + 1);
         launch_widen_i32(ctx, c.iptr32.p, c.iptr.p, (int64_t)N + 1);
     }
@@ -1578,7 +1580,7 @@ static mcb_coclust* coclust_run_impl(mcb_ctx* ctx, int32_t N, int64_t n_edges, c
     const int32_t nl = c->n_local;
 
     CoverCsr csr;
-    cover_csr_build(ctx, N, n_edges, src, dst, w, csr);
+    cover_csr_build(ctx, N, n_edges, src, dst, w, /*sort_out=*/knn > 0, csr);
     DevBuf<int32_t> d_samples(ctx, (size_t)std::max<int64_t>((int64_t)n_resamp * n_s, 1)), d_ids(ctx, (size_t)std::max(nl, 1));
     DevBuf<uint64_t> d_seeds(ctx, (size_t)std::max(n_resamp, 1));
     if (n_resamp) {
@@ -1594,20 +1596,13 @@ static mcb_coclust* coclust_run_impl(mcb_ctx* ctx, int32_t N, int64_t n_edges, c
     MCB_CHECK(!(hs[1] & 1), "MC-ERR: edge endpoint out of range");
     MCB_CHECK(!(hs[1] & 2), "MC-ERR: sampled node out of range");
     MCB_CHECK(!(hs[1] & 4), "MC-ERR: each resample index set must be strictly ascending");
+    MCB_CHECK(!(hs[1] & 8), "MC-ERR: tgs_graph_cover_resample: per-node edge truncation (knn) supports out-degrees up to 1024");
     const int32_t max_out = hs[2], max_in = hs[3];
-    if (knn > 0 && knn < max_out && nl) {
-        // `knn` = the most out-edges a node may use inside one resample (R/coclust_graph_cov.r:39-41 passes the graph's
-        // average out-degree).  A sampled node only exceeds it when more than knn of its targets were sampled too;
-        // count how often that happens (at p = 0.75 and knn = 0.92 * max out-degree: practically never)
-        DevBuf<int32_t> over(ctx, 1);
-        over.zero();
-        launch_knn_trunc_check(ctx, N, nl, d_ids.p, n_s, d_samples.p, csr.optr32.p, csr.odst.p, knn, over.p);
-        int32_t h_over = 0;
-        MCB_CUDA(cudaMemcpyAsync(&h_over, over.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-        MCB_CHECK(h_over == 0, "MC-ERR: tgs_graph_cover_resample: some sampled nodes have more than `knn` sampled out-neighbours; "
-                               "per-node edge truncation is not implemented -- pass knn = 0 (no limit) or knn >= the maximum out-degree");
-    }
+    // `knn` = the most out edges a node may use inside one resample (R/coclust_graph_cov.r:39-41 passes the graph's AVERAGE
+    // out-degree, so well-connected nodes lose their weakest sampled edges).  It can only bind below the largest out-degree.
+    const int32_t knn_eff = (knn > 0 && knn < max_out) ? knn : 0;
+    MCB_CHECK(knn_eff == 0 || max_out < 65536, "MC-ERR: out-degree too large for per-node edge truncation");
+    DevBuf<uint16_t> ocut(ctx, knn_eff ? (size_t)std::max(nl, 1) * N : 0);
     if (with_counts) {
         c->cnt.alloc(ctx, (size_t)N * N); c->cnt.zero();
         c->nsamp.alloc(ctx, (size_t)N); c->nsamp.zero();
@@ -1619,7 +1614,7 @@ static mcb_coclust* coclust_run_impl(mcb_ctx* ctx, int32_t N, int64_t n_edges, c
     {
         StageTimer t(ctx, "graph_cover");
         launch_graph_cover(ctx, cg, csr.optr32.p, csr.iptr32.p, csr.nd.p, csr.oe.p, csr.ie.p, max_out, max_in, nl, d_ids.p, n_s, d_samples.p, d_seeds.p,
-                           min_mc_size, cooling, burn_in, max_sweeps, c->ncl_cap, c->mc.p, f_ws.p, c->sweeps.p, status.p);
+                           min_mc_size, cooling, burn_in, max_sweeps, c->ncl_cap, c->mc.p, f_ws.p, c->sweeps.p, status.p, knn_eff, csr.ipos.p, ocut.p);
     }
     if (with_counts) {
         DevBuf<int32_t> ws_order(ctx, (size_t)std::max(nl, 1) * N), ws_start(ctx, (size_t)std::max(nl, 1) * (c->ncl_cap + 1));

@@ -55,8 +55,13 @@ __global__ void __launch_bounds__(CC_THREADS)
 graph_cover_kernel(CoverGraph g, int32_t n_local, const int32_t* __restrict__ resamp_ids, int32_t n_s,
                    const int32_t* __restrict__ samples, const uint64_t* __restrict__ seeds, int32_t min_size,
                    double cooling, int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap, int32_t* __restrict__ mc_all,
-                   int32_t* __restrict__ f_all, int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status)
+                   int32_t* __restrict__ f_all, int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status,
+                   int32_t knn, const uint16_t* __restrict__ ipos, uint16_t* __restrict__ ocut_all)
 {
+    // knn > 0 (`knn` of tgs_graph_cover_resample): a node uses only its first knn out edges, in (weight descending,
+    // target ascending) order, among those whose target is sampled.  Out segments are stored in that order, so the
+    // usable part of node v's segment is its first ocut[v] positions; the in edge u -> v is usable iff its position in
+    // u's out segment, ipos[e], is below ocut[u].
     extern __shared__ uint32_t dsm[];
     int32_t* size = (int32_t*)dsm;                  // [ncl_cap]
     uint32_t* wout = dsm + ncl_cap;                 // [ncl_cap]
@@ -76,6 +81,7 @@ graph_cover_kernel(CoverGraph g, int32_t n_local, const int32_t* __restrict__ re
         const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
         int32_t* mc = mc_all + (int64_t)lr * N;
         int32_t* f = f_all + (int64_t)lr * N;
+        uint16_t* ocut = knn > 0 ? ocut_all + (int64_t)lr * N : nullptr;
 
         for (int v = tid; v < N; v += CC_THREADS) { mc[v] = -2; f[v] = 0; }
         for (int k = tid; k < ncl_cap; k += CC_THREADS) { size[k] = 0; wout[k] = 0; win[k] = 0; }
@@ -85,8 +91,12 @@ graph_cover_kernel(CoverGraph g, int32_t n_local, const int32_t* __restrict__ re
         for (int q = tid; q < n_s; q += CC_THREADS) {
             const int v = S[q];
             int c = 0;
-            for (int64_t e = g.optr[v]; e < g.optr[v + 1]; ++e) c += (mc[g.odst[e]] == -1);
+            int64_t e = g.optr[v];
+            for (; e < g.optr[v + 1]; ++e) {
+                if (mc[g.odst[e]] == -1) { if (knn > 0 && c == knn) break; ++c; }
+            }
             f[v] = c;
+            if (knn > 0) ocut[v] = (uint16_t)(e - g.optr[v]);
         }
         __syncthreads();
 
@@ -134,7 +144,7 @@ graph_cover_kernel(CoverGraph g, int32_t n_local, const int32_t* __restrict__ re
             if (tid == 0) { mc[pick] = k; s_flag = 1; }
             __syncthreads();
             // claim the uncovered sampled out-neighbours (edges are unique per (src, dst))
-            const int64_t oe0 = g.optr[pick], oe1 = g.optr[pick + 1];
+            const int64_t oe0 = g.optr[pick], oe1 = knn > 0 ? oe0 + ocut[pick] : g.optr[pick + 1];
             for (int64_t e = oe0 + tid; e < oe1; e += CC_THREADS) {
                 const int u = g.odst[e];
                 if (mc[u] == -1) { mc[u] = k; atomicAdd(&s_flag, 1); }
@@ -147,7 +157,11 @@ graph_cover_kernel(CoverGraph g, int32_t n_local, const int32_t* __restrict__ re
                 // u was claimed in this iteration iff mc[u] == k; the seed itself is handled at e = oe0-1.
                 // A self edge pick -> pick must not be counted twice.
                 if (mc[u] != k || (e >= oe0 && u == pick)) continue;
-                for (int64_t e2 = g.iptr[u] + lane; e2 < g.iptr[u + 1]; e2 += 32) atomicSub(&f[g.isrc[e2]], 1);
+                for (int64_t e2 = g.iptr[u] + lane; e2 < g.iptr[u + 1]; e2 += 32) {
+                    const int sn = g.isrc[e2];
+                    if (knn > 0 && ipos[e2] >= ocut[sn]) continue;
+                    atomicSub(&f[sn], 1);
+                }
             }
             __syncthreads();
         }
@@ -175,7 +189,7 @@ graph_cover_kernel(CoverGraph g, int32_t n_local, const int32_t* __restrict__ re
             for (int t = 0; t < n_s; ++t) {
                 const int v = S[perm_index((uint32_t)t, (uint32_t)n_s, hb, rk)];
                 const int cur = (v == pend_v) ? pend_k : mc[v];
-                const int64_t oe0 = g.optr[v], oe1 = g.optr[v + 1];
+                const int64_t oe0 = g.optr[v], oe1 = knn > 0 ? oe0 + ocut[v] : g.optr[v + 1];
                 const int64_t ie0 = g.iptr[v], ie1 = g.iptr[v + 1];
                 // [A] accumulate association towards every neighbouring cluster
                 for (int64_t e = oe0 + tid; e < oe1; e += CC_THREADS) {
@@ -185,6 +199,7 @@ graph_cover_kernel(CoverGraph g, int32_t n_local, const int32_t* __restrict__ re
                 }
                 for (int64_t e = ie0 + tid; e < ie1; e += CC_THREADS) {
                     const int u = g.isrc[e];
+                    if (knn > 0 && ipos[e] >= ocut[u]) continue;
                     const int k = (u == pend_v) ? pend_k : mc[u];
                     if (k >= 0) atomicAdd(&win[k], g.iw[e]);
                 }
@@ -217,7 +232,7 @@ graph_cover_kernel(CoverGraph g, int32_t n_local, const int32_t* __restrict__ re
                 }
                 // [C] clear the touched accumulators
                 for (int64_t e = oe0 + tid; e < oe1; e += CC_THREADS) { const int k = mc[g.odst[e]]; if (k >= 0) wout[k] = 0; }
-                for (int64_t e = ie0 + tid; e < ie1; e += CC_THREADS) { const int k = mc[g.isrc[e]]; if (k >= 0) win[k] = 0; }
+                for (int64_t e = ie0 + tid; e < ie1; e += CC_THREADS) { const int k = mc[g.isrc[e]]; if (k >= 0) win[k] = 0; }   // (clearing an untouched slot is harmless)
                 __syncthreads();
                 // [D] apply the move; other threads see it through (pend_v, pend_k) until the next barrier
                 pend_v = -1;
@@ -291,20 +306,23 @@ __device__ __forceinline__ NodeEdges<IN_SLOTS> load_edges(const FastGraph& g, co
 }
 
 template <int OUT_SLOTS, int IN_SLOTS> struct BatchEdges { int v; int uo[OUT_SLOTS]; uint32_t wo[OUT_SLOTS]; int ui[IN_SLOTS]; uint32_t wi[IN_SLOTS]; };
-template <int IN_SLOTS, typename VT>
-__device__ __forceinline__ NodeOffs<IN_SLOTS> load_batch_offs(const FastGraph& g, const VT* vlist, int t, int n_s)
+// TRUNC (per-node edge truncation, `knn`): ocut[v] = usable leading positions of v's out segment in this resample;
+// an in edge is usable iff its position in its source's out segment (ipos) is below the source's ocut
+template <int IN_SLOTS, typename VT, bool TRUNC = false>
+__device__ __forceinline__ NodeOffs<IN_SLOTS> load_batch_offs(const FastGraph& g, const VT* vlist, int t, int n_s, const uint16_t* ocut = nullptr)
 {
     NodeOffs<IN_SLOTS> o;
     o.v = -1; o.o0 = o.o1 = o.i0 = o.i1 = 0;
     if (t < n_s) {
         o.v = (int)vlist[t];
         const int4 d = __ldg(g.nd + o.v);
-        o.o0 = d.x; o.o1 = d.y; o.i0 = d.z; o.i1 = d.w;
+        o.o0 = d.x; o.o1 = TRUNC ? d.x + (int)ocut[o.v] : d.y; o.i0 = d.z; o.i1 = d.w;
     }
     return o;
 }
-template <int FT, int OUT_SLOTS, int IN_SLOTS>
-__device__ __forceinline__ BatchEdges<OUT_SLOTS, IN_SLOTS> load_batch_edges(const FastGraph& g, const NodeOffs<IN_SLOTS>& o, int tid)
+template <int FT, int OUT_SLOTS, int IN_SLOTS, bool TRUNC = false>
+__device__ __forceinline__ BatchEdges<OUT_SLOTS, IN_SLOTS> load_batch_edges(const FastGraph& g, const NodeOffs<IN_SLOTS>& o, int tid,
+                                                                            const uint16_t* ipos = nullptr, const uint16_t* ocut = nullptr)
 {
     BatchEdges<OUT_SLOTS, IN_SLOTS> e;
     e.v = o.v;
@@ -319,7 +337,10 @@ __device__ __forceinline__ BatchEdges<OUT_SLOTS, IN_SLOTS> load_batch_edges(cons
     for (int s = 0; s < IN_SLOTS; ++s) {
         const int ei = o.i0 + s * FT + tid;
         int2 p = make_int2(-1, 0);
-        if (ei < o.i1) p = __ldg(g.ie + ei);
+        if (ei < o.i1) {
+            p = __ldg(g.ie + ei);
+            if (TRUNC && ipos[ei] >= ocut[p.x]) p.x = -1;
+        }
         e.ui[s] = p.x; e.wi[s] = (uint32_t)p.y;
     }
     return e;
@@ -541,13 +562,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 
 // VT: element type of the shared-memory visit order (uint16_t when N < 65536: at the C5 shape this is what lets two
 // CTAs of the wide-slot instantiation share an SM)
-template <int B, int OUT_SLOTS, int IN_SLOTS, typename VT>
+template <int B, int OUT_SLOTS, int IN_SLOTS, typename VT, bool TRUNC>
 __global__ void __launch_bounds__(128 * B, (OUT_SLOTS == 1 && IN_SLOTS <= 3) ? 8 / B : (sizeof(VT) == 2 ? 4 / B : 1))
 graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict__ resamp_ids, int32_t n_s,
                          const int32_t* __restrict__ samples, const uint64_t* __restrict__ seeds, int32_t min_size,
                          double cooling, int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap, int32_t out_warps,
                          int32_t* __restrict__ mc_all, int32_t* __restrict__ f_all, int32_t* __restrict__ sweeps_out,
-                         int32_t* __restrict__ status)
+                         int32_t* __restrict__ status, int32_t knn, const uint16_t* __restrict__ ipos, uint16_t* __restrict__ ocut_all)
 {
     constexpr int FT = 128;            // threads per sub-block (one visited node each)
     constexpr int NT = FT * B;
@@ -574,6 +595,7 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
         const uint64_t seed = seeds[rid];
         const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
         int32_t* f = f_all + (int64_t)lr * N;
+        uint16_t* ocut = TRUNC ? ocut_all + (int64_t)lr * N : nullptr;
 
         for (int v = tid; v < N; v += NT) { mc_s[v] = -2; f[v] = 0; }
         for (int k = tid; k < ncl_cap; k += NT) size[k] = 0;
@@ -585,8 +607,12 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
         for (int q = tid; q < n_s; q += NT) {
             const int v = S[q];
             int c = 0;
-            for (int e = g.optr[v]; e < g.optr[v + 1]; ++e) c += (mc_s[g.odst[e]] == -1);
+            int e = g.optr[v];
+            for (; e < g.optr[v + 1]; ++e) {
+                if (mc_s[g.odst[e]] == -1) { if (TRUNC && c == knn) break; ++c; }
+            }
             f[v] = c;
+            if (TRUNC) ocut[v] = (uint16_t)(e - g.optr[v]);
         }
         __syncthreads();
 
@@ -636,7 +662,7 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
             const int k = ncl++;
             if (tid == 0) { mc_s[pick] = (int16_t)k; s_flag = 1; }
             __syncthreads();
-            const int oe0 = g.optr[pick], oe1 = g.optr[pick + 1];
+            const int oe0 = g.optr[pick], oe1 = TRUNC ? oe0 + (int)ocut[pick] : g.optr[pick + 1];
             for (int e = oe0 + tid; e < oe1; e += NT) {
                 const int u = g.odst[e];
                 if (mc_s[u] == -1) { mc_s[u] = (int16_t)k; atomicAdd(&s_flag, 1); }
@@ -646,7 +672,11 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
             for (int e = oe0 - 1 + wid; e < oe1; e += NW) {
                 const int u = (e < oe0) ? pick : g.odst[e];
                 if (mc_s[u] != k || (e >= oe0 && u == pick)) continue;
-                for (int e2 = g.iptr[u] + lane; e2 < g.iptr[u + 1]; e2 += 32) atomicSub(&f[g.isrc[e2]], 1);
+                for (int e2 = g.iptr[u] + lane; e2 < g.iptr[u + 1]; e2 += 32) {
+                    const int sn = g.isrc[e2];
+                    if (TRUNC && ipos[e2] >= ocut[sn]) continue;
+                    atomicSub(&f[sn], 1);
+                }
             }
             __syncthreads();
         }
@@ -683,13 +713,13 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
             while (t < n_s) {
                 const int my_t = t + sb;
                 if (cur_t != my_t) {              // start of sweep, or the previous batch ended on a move: reload
-                    cur = load_batch_edges<FT, OUT_SLOTS, IN_SLOTS>(g, load_batch_offs<IN_SLOTS>(g, vlist, my_t, n_s), ltid);
+                    cur = load_batch_edges<FT, OUT_SLOTS, IN_SLOTS, TRUNC>(g, load_batch_offs<IN_SLOTS, VT, TRUNC>(g, vlist, my_t, n_s, ocut), ltid, ipos, ocut);
                     cur_t = my_t;
                     nxt_t = my_t + B;
-                    nxt = load_batch_offs<IN_SLOTS>(g, vlist, nxt_t, n_s);
+                    nxt = load_batch_offs<IN_SLOTS, VT, TRUNC>(g, vlist, nxt_t, n_s, ocut);
                 }
-                const BatchEdges<OUT_SLOTS, IN_SLOTS> pre = load_batch_edges<FT, OUT_SLOTS, IN_SLOTS>(g, nxt, ltid);   // node my_t + B, in flight
-                const NodeOffs<IN_SLOTS> nxt2 = load_batch_offs<IN_SLOTS>(g, vlist, nxt_t + B, n_s);
+                const BatchEdges<OUT_SLOTS, IN_SLOTS> pre = load_batch_edges<FT, OUT_SLOTS, IN_SLOTS, TRUNC>(g, nxt, ltid, ipos, ocut);   // node my_t + B, in flight
+                const NodeOffs<IN_SLOTS> nxt2 = load_batch_offs<IN_SLOTS, VT, TRUNC>(g, vlist, nxt_t + B, n_s, ocut);
                 uint32_t* wo_b = wout + (size_t)(2 * sb + (parity & 1)) * ncl_cap;
                 uint32_t* wi_b = win + (size_t)(2 * sb + (parity & 1)) * ncl_cap;
                 const int v = cur.v;               // -1 beyond the end of the sweep
@@ -1042,9 +1072,11 @@ graph_cover_warp_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict_
 
 // ---------------------------------------------------------------------------------------------
 // CSR (out and in) of the host's edge table, built on the device: degree count, scan, fill.  The order of a node's
-// edges inside its segment is arbitrary (atomic cursors); every consumer only sums integer weights or counts over a
-// segment, so the cover does not depend on it.  Also validates what the host loops used to validate.
-// err bits: 1 = edge endpoint out of range, 2 = sampled node out of range, 4 = sample set not strictly ascending.
+// edges inside its IN segment is arbitrary (atomic cursors); every consumer only sums integer weights or counts over a
+// segment, so the cover does not depend on it.  OUT segments are ordered by (weight descending, target ascending) when
+// per-node edge truncation (`knn`) is requested.  Also validates what the host loops used to validate.
+// err bits: 1 = edge endpoint out of range, 2 = sampled node out of range, 4 = sample set not strictly ascending,
+// 8 = out segment too long to order.
 // ---------------------------------------------------------------------------------------------
 __global__ void edge_degree_kernel(int64_t ne, const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int32_t N,
                                    int32_t* __restrict__ odeg, int32_t* __restrict__ ideg, int32_t* __restrict__ err)
@@ -1055,20 +1087,55 @@ __global__ void edge_degree_kernel(int64_t ne, const int32_t* __restrict__ src, 
         atomicAdd(&odeg[a], 1); atomicAdd(&ideg[b], 1);
     }
 }
-__global__ void edge_fill_kernel(int64_t ne, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
-                                 const double* __restrict__ w, int32_t N, const int32_t* __restrict__ optr,
-                                 const int32_t* __restrict__ iptr, int32_t* __restrict__ ocur, int32_t* __restrict__ icur,
-                                 int32_t* __restrict__ odst, uint32_t* __restrict__ ow, int32_t* __restrict__ isrc,
-                                 uint32_t* __restrict__ iw, int2* __restrict__ oe, int2* __restrict__ ie)
+__global__ void edge_fill_out_kernel(int64_t ne, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                     const double* __restrict__ w, int32_t N, const int32_t* __restrict__ optr,
+                                     int32_t* __restrict__ ocur, int32_t* __restrict__ odst, uint32_t* __restrict__ ow)
 {
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
         const int32_t a = src[e], b = dst[e];
         if (a < 0 || a >= N || b < 0 || b >= N) continue;
         const double wf = rint(w[e] * 65536.0);                 // 16-bit fixed point, at least one unit (as orc_graph_to_csr)
         const uint32_t wi = wf < 1.0 ? 1u : (uint32_t)wf;
-        const int po = optr[a] + atomicAdd(&ocur[a], 1), pi = iptr[b] + atomicAdd(&icur[b], 1);
-        odst[po] = b; ow[po] = wi; oe[po] = make_int2(b, (int)wi);
-        isrc[pi] = a; iw[pi] = wi; ie[pi] = make_int2(a, (int)wi);
+        const int po = optr[a] + atomicAdd(&ocur[a], 1);
+        odst[po] = b; ow[po] = wi;
+    }
+}
+// One warp per node: (SORT) order the node's out segment by (weight descending, target ascending) -- the order in which
+// tgs_graph_cover_resample's `knn` keeps a node's edges -- then write the packed out edges and scatter the node's edges
+// into the in-CSR of their targets, each with its POSITION in the source's out segment (ipos).  err bit 8: a segment
+// longer than COVER_SORT_MAX could not be ordered.
+constexpr int COVER_SORT_MAX = 1024;
+template <bool SORT>
+__global__ void __launch_bounds__(128)
+finish_csr_kernel(int32_t N, const int32_t* __restrict__ optr, const int32_t* __restrict__ iptr, int32_t* __restrict__ icur,
+                  int32_t* __restrict__ odst, uint32_t* __restrict__ ow, int2* __restrict__ oe, int32_t* __restrict__ isrc,
+                  uint32_t* __restrict__ iw, int2* __restrict__ ie, uint16_t* __restrict__ ipos, int32_t* __restrict__ err)
+{
+    __shared__ int32_t sd[SORT ? 4 : 1][SORT ? COVER_SORT_MAX : 1];
+    __shared__ uint32_t sw[SORT ? 4 : 1][SORT ? COVER_SORT_MAX : 1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int v = blockIdx.x * 4 + wid; v < N; v += gridDim.x * 4) {
+        const int o0 = optr[v], d = optr[v + 1] - o0;
+        if (SORT && d > 1) {
+            if (d <= COVER_SORT_MAX) {
+                for (int q = lane; q < d; q += 32) { sd[wid][q] = odst[o0 + q]; sw[wid][q] = ow[o0 + q]; }
+                __syncwarp();
+                for (int q = lane; q < d; q += 32) {
+                    const int32_t t = sd[wid][q]; const uint32_t x = sw[wid][q];
+                    int rank = 0;
+                    for (int r = 0; r < d; ++r) rank += (sw[wid][r] > x || (sw[wid][r] == x && sd[wid][r] < t)) ? 1 : 0;
+                    odst[o0 + rank] = t; ow[o0 + rank] = x;          // (src, dst) pairs are unique: ranks are a permutation
+                }
+                __syncwarp();
+            } else if (lane == 0) atomicOr(err, 8);
+        }
+        for (int q = lane; q < d; q += 32) {
+            const int32_t t = odst[o0 + q]; const uint32_t x = ow[o0 + q];
+            oe[o0 + q] = make_int2(t, (int)x);
+            const int pi = iptr[t] + atomicAdd(&icur[t], 1);
+            isrc[pi] = v; iw[pi] = x; ie[pi] = make_int2(v, (int)x); ipos[pi] = (uint16_t)min(q, 65535);
+        }
+        __syncwarp();
     }
 }
 __global__ void node_desc_kernel(int32_t N, const int32_t* __restrict__ optr, const int32_t* __restrict__ iptr, int4* __restrict__ nd)
@@ -1096,8 +1163,8 @@ __global__ void sample_check_kernel(int64_t total, int32_t n_s, const int32_t* _
 void launch_build_cover_csr(mcb_ctx* ctx, int32_t N, int64_t ne, const int32_t* src, const int32_t* dst, const double* w,
                             int32_t* odeg /*[N+1] zeroed*/, int32_t* ideg /*[N+1] zeroed*/, int32_t* optr /*[N+1]*/,
                             int32_t* iptr /*[N+1]*/, int32_t* odst, uint32_t* ow, int32_t* isrc, uint32_t* iw,
-                            void* oe /* int2[ne] */, void* ie /* int2[ne] */, void* nd /* int4[N] */,
-                            int32_t* scratch4 /* [0] total, [1] err, [2] max out, [3] max in; zeroed */)
+                            void* oe /* int2[ne] */, void* ie /* int2[ne] */, void* nd /* int4[N] */, uint16_t* ipos /* [ne] */,
+                            bool sort_out, int32_t* scratch4 /* [0] total, [1] err, [2] max out, [3] max in; zeroed */)
 {
     const int grid = (int)std::min<int64_t>(std::max<int64_t>(ceil_div(ne, 256), 1), (int64_t)ctx->num_sms * 8);
     if (ne > 0) { edge_degree_kernel<<<grid, 256, 0, ctx->stream>>>(ne, src, dst, N, odeg, ideg, scratch4 + 1); MCB_LAUNCH_CHECK(); }
@@ -1107,7 +1174,14 @@ void launch_build_cover_csr(mcb_ctx* ctx, int32_t N, int64_t ne, const int32_t* 
     launch_exclusive_scan_i32(ctx, ideg, iptr, (int64_t)N + 1, scratch4);
     MCB_CUDA(cudaMemsetAsync(odeg, 0, sizeof(int32_t) * ((size_t)N + 1), ctx->stream));     // reused as fill cursors
     MCB_CUDA(cudaMemsetAsync(ideg, 0, sizeof(int32_t) * ((size_t)N + 1), ctx->stream));
-    if (ne > 0) { edge_fill_kernel<<<grid, 256, 0, ctx->stream>>>(ne, src, dst, w, N, optr, iptr, odeg, ideg, odst, ow, isrc, iw, (int2*)oe, (int2*)ie); MCB_LAUNCH_CHECK(); }
+    if (ne > 0) {
+        edge_fill_out_kernel<<<grid, 256, 0, ctx->stream>>>(ne, src, dst, w, N, optr, odeg, odst, ow);
+        MCB_LAUNCH_CHECK();
+        const int fgrid = (int)std::min<int64_t>(ceil_div(N, 4), (int64_t)ctx->num_sms * 16);
+        if (sort_out) finish_csr_kernel<true><<<fgrid, 128, 0, ctx->stream>>>(N, optr, iptr, ideg, odst, ow, (int2*)oe, isrc, iw, (int2*)ie, ipos, scratch4 + 1);
+        else finish_csr_kernel<false><<<fgrid, 128, 0, ctx->stream>>>(N, optr, iptr, ideg, odst, ow, (int2*)oe, isrc, iw, (int2*)ie, ipos, scratch4 + 1);
+        MCB_LAUNCH_CHECK();
+    }
     node_desc_kernel<<<std::min(ctx->num_sms, (int)ceil_div(N, 256)), 256, 0, ctx->stream>>>(N, optr, iptr, (int4*)nd);
     MCB_LAUNCH_CHECK();
 }
@@ -1119,43 +1193,6 @@ void launch_iota_i32(mcb_ctx* ctx, int32_t* v, int32_t n)
 {
     if (n == 0) return;
     iota_i32_kernel<<<std::min(ctx->num_sms * 4, (int)ceil_div(n, 256)), 256, 0, ctx->stream>>>(v, n);
-    MCB_LAUNCH_CHECK();
-}
-
-// `knn` of tgs_graph_cover_resample = the most out-edges a node may use inside one resample.  One CTA per local resample:
-// a bitmap of the sampled nodes (global workspace, N bits), then per sampled node the number of sampled out-neighbours;
-// *over += number of (resample, node) pairs above knn.
-__global__ void __launch_bounds__(256)
-knn_trunc_check_kernel(int32_t N, int32_t n_local, const int32_t* __restrict__ resamp_ids, int32_t n_s,
-                       const int32_t* __restrict__ samples, const int32_t* __restrict__ optr, const int32_t* __restrict__ odst,
-                       int32_t knn, uint32_t* __restrict__ bitmap_ws, int32_t* __restrict__ over)
-{
-    const int32_t words = (N + 31) / 32;
-    for (int lr = blockIdx.x; lr < n_local; lr += gridDim.x) {
-        uint32_t* bm = bitmap_ws + (int64_t)blockIdx.x * words;
-        const int32_t* S = samples + (int64_t)resamp_ids[lr] * n_s;
-        for (int q = threadIdx.x; q < words; q += blockDim.x) bm[q] = 0u;
-        __syncthreads();
-        for (int q = threadIdx.x; q < n_s; q += blockDim.x) atomicOr(&bm[S[q] >> 5], 1u << (S[q] & 31));
-        __syncthreads();
-        int bad = 0;
-        for (int q = threadIdx.x; q < n_s; q += blockDim.x) {
-            const int32_t v = S[q];
-            int c = 0;
-            for (int32_t e = optr[v]; e < optr[v + 1]; ++e) { const int32_t u = odst[e]; c += (bm[u >> 5] >> (u & 31)) & 1u; }
-            bad += c > knn;
-        }
-        if (bad) atomicAdd(over, bad);
-        __syncthreads();
-    }
-}
-void launch_knn_trunc_check(mcb_ctx* ctx, int32_t N, int32_t n_local, const int32_t* resamp_ids, int32_t n_s, const int32_t* samples,
-                            const int32_t* optr32, const int32_t* odst, int32_t knn, int32_t* over)
-{
-    if (n_local == 0) return;
-    const int grid = std::min(n_local, ctx->num_sms * 4);
-    DevBuf<uint32_t> ws(ctx, (size_t)grid * ((N + 31) / 32));
-    knn_trunc_check_kernel<<<grid, 256, 0, ctx->stream>>>(N, n_local, resamp_ids, n_s, samples, optr32, odst, knn, ws.p, over);
     MCB_LAUNCH_CHECK();
 }
 
@@ -1268,19 +1305,30 @@ static void launch_cover_fast(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local
     MCB_LAUNCH_CHECK();
 }
 
+template <int B, int OUT_SLOTS, int IN_SLOTS, typename VT, bool TRUNC>
+static void launch_cover_batch_t(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
+                                 const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling, int32_t burn_in,
+                                 int32_t max_sweeps, int32_t ncl_cap, int32_t max_out, size_t smem, int32_t* mc, int32_t* f_ws,
+                                 int32_t* sweeps, int32_t* status, int32_t knn, const uint16_t* ipos, uint16_t* ocut)
+{
+    static SmemOptIn optin;
+    ensure_dyn_smem(optin, ctx, graph_cover_batch_kernel<B, OUT_SLOTS, IN_SLOTS, VT, TRUNC>, smem);
+    const int32_t out_warps = std::max(1, (int)ceil_div(max_out, 32));
+    graph_cover_batch_kernel<B, OUT_SLOTS, IN_SLOTS, VT, TRUNC><<<n_local, 128 * B, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds,
+                                                                                    min_size, cooling, burn_in, max_sweeps,
+                                                                                    ncl_cap, out_warps, mc, f_ws, sweeps, status, knn, ipos, ocut);
+    MCB_LAUNCH_CHECK();
+}
 template <int B, int OUT_SLOTS, int IN_SLOTS, typename VT>
 static void launch_cover_batch(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
                                const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling, int32_t burn_in,
                                int32_t max_sweeps, int32_t ncl_cap, int32_t max_out, size_t smem, int32_t* mc, int32_t* f_ws,
-                               int32_t* sweeps, int32_t* status)
+                               int32_t* sweeps, int32_t* status, int32_t knn, const uint16_t* ipos, uint16_t* ocut)
 {
-    static SmemOptIn optin;
-    ensure_dyn_smem(optin, ctx, graph_cover_batch_kernel<B, OUT_SLOTS, IN_SLOTS, VT>, smem);
-    const int32_t out_warps = std::max(1, (int)ceil_div(max_out, 32));
-    graph_cover_batch_kernel<B, OUT_SLOTS, IN_SLOTS, VT><<<n_local, 128 * B, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds,
-                                                                                    min_size, cooling, burn_in, max_sweeps,
-                                                                                    ncl_cap, out_warps, mc, f_ws, sweeps, status);
-    MCB_LAUNCH_CHECK();
+    if (knn > 0) launch_cover_batch_t<B, OUT_SLOTS, IN_SLOTS, VT, true>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,
+                                                                        max_sweeps, ncl_cap, max_out, smem, mc, f_ws, sweeps, status, knn, ipos, ocut);
+    else launch_cover_batch_t<B, OUT_SLOTS, IN_SLOTS, VT, false>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,
+                                                                 max_sweeps, ncl_cap, max_out, smem, mc, f_ws, sweeps, status, 0, nullptr, nullptr);
 }
 
 template <int B, int OUT_SLOTS>
@@ -1301,8 +1349,10 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
                         const void* oe, const void* ie, int32_t max_out, int32_t max_in, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
                         const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling,
                         int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap, int32_t* mc, int32_t* f_ws,
-                        int32_t* sweeps, int32_t* status)
+                        int32_t* sweeps, int32_t* status, int32_t knn, const uint16_t* ipos, uint16_t* ocut_ws)
 {
+    // knn > 0: per-node edge truncation is active (the caller passes 0 when knn >= the largest out-degree, where it can never
+    // bind).  Only the speculative batch kernels and the general kernel implement it.
     if (n_local == 0) return;
     // Kernel choice (MCB_COVER_KERNEL overrides for tests/diagnostics: batch2|batch4|batch8|warp8|warp16|warp32|fast|slow):
     //   batch4  speculative batches of 4 visits, 4 warps per node  (out-degree <= 128, in-degree <= 384)
@@ -1325,7 +1375,8 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
                              (size_t)g.N * sizeof(int16_t) + 16;                                                          \
         if (max_out <= OS * 128 && max_in <= IS * 128 && bsmem <= 200 * 1024 && (sizeof(VT) == 4 || g.N < 65536)) {       \
             launch_cover_batch<BB, OS, IS, VT>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling,      \
-                                               burn_in, max_sweeps, ncl_cap, max_out, bsmem, mc, f_ws, sweeps, status);   \
+                                               burn_in, max_sweeps, ncl_cap, max_out, bsmem, mc, f_ws, sweeps, status,    \
+                                               knn, ipos, ocut_ws);                                                       \
             return;                                                                                                       \
         }                                                                                                                 \
     }
@@ -1347,12 +1398,14 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
             return;                                                                                                       \
         }                                                                                                                 \
     }
-        if (max_out <= 128) { WARPK(16, 4) WARPK(8, 4) WARPK(32, 4) }
-        else { WARPK(16, 8) WARPK(8, 8) }
+        if (knn == 0) {
+            if (max_out <= 128) { WARPK(16, 4) WARPK(8, 4) WARPK(32, 4) }
+            else { WARPK(16, 8) WARPK(8, 8) }
+        }
 #undef WARPK
         // fast kernels: size + 2 x (wout, win) + visit order + int16 mc[] in shared memory, edges of a node in registers
         const size_t fast_smem = ((size_t)5 * ncl_cap + (size_t)n_s) * sizeof(uint32_t) + (size_t)g.N * sizeof(int16_t) + 16;
-        if (fast_smem <= 200 * 1024) {
+        if (fast_smem <= 200 * 1024 && knn == 0) {
 #define FAST(FT, SL) launch_cover_fast<FT, SL>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in, \
                                                max_sweeps, ncl_cap, max_out, fast_smem, mc, f_ws, sweeps, status)
             if (max_out <= 128 && max_in <= 3 * 128) { FAST(128, 3); return; }
@@ -1367,7 +1420,7 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
     ensure_dyn_smem(optin, ctx, graph_cover_kernel, smem);
     graph_cover_kernel<<<n_local, CC_THREADS, smem, ctx->stream>>>(g, n_local, resamp_ids, n_s, samples, seeds, min_size,
                                                                     cooling, burn_in, max_sweeps, ncl_cap, mc, f_ws,
-                                                                    sweeps, status);
+                                                                    sweeps, status, knn, ipos, ocut_ws);
     MCB_LAUNCH_CHECK();
 }
 

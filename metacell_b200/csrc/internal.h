@@ -222,11 +222,9 @@ void launch_mc_tapply(mcb_ctx* ctx, int64_t ncells, int32_t ngenes, const int64_
 // coclust.cu: device-side CSR build of the host edge table + input validation
 void launch_build_cover_csr(mcb_ctx* ctx, int32_t N, int64_t ne, const int32_t* src, const int32_t* dst, const double* w,
                             int32_t* odeg, int32_t* ideg, int32_t* optr, int32_t* iptr, int32_t* odst, uint32_t* ow,
-                            int32_t* isrc, uint32_t* iw, void* oe, void* ie, void* nd, int32_t* scratch4);
+                            int32_t* isrc, uint32_t* iw, void* oe, void* ie, void* nd, uint16_t* ipos, bool sort_out, int32_t* scratch4);
 void launch_sample_check(mcb_ctx* ctx, int64_t total, int32_t n_s, const int32_t* samples, int32_t N, int32_t* err);
 void launch_iota_i32(mcb_ctx* ctx, int32_t* v, int32_t n);
-void launch_knn_trunc_check(mcb_ctx* ctx, int32_t N, int32_t n_local, const int32_t* resamp_ids, int32_t n_s, const int32_t* samples,
-                            const int32_t* optr32, const int32_t* odst, int32_t knn, int32_t* over);
 
 // balance.cu
 void launch_build_hash(mcb_ctx* ctx, const int32_t* knn_col, int64_t M, int32_t Kc, int32_t H, int32_t rank_bits,
@@ -271,7 +269,8 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
                         const void* oe, const void* ie, int32_t max_out, int32_t max_in, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
                         const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling,
                         int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap, int32_t* mc /* [n_local][N] */,
-                        int32_t* f_ws /* [n_local][N] */, int32_t* sweeps, int32_t* status);
+                        int32_t* f_ws /* [n_local][N] */, int32_t* sweeps, int32_t* status, int32_t knn = 0,
+                        const uint16_t* ipos = nullptr, uint16_t* ocut_ws /* [n_local][N] when knn > 0 */ = nullptr);
 void launch_cooccur(mcb_ctx* ctx, int32_t N, int32_t n_local, const int32_t* mc, int32_t ncl_cap, uint32_t* cnt,
                     int32_t* nsamp, int32_t* ws_order /* [n_local][N] */, int32_t* ws_start /* [n_local][ncl_cap+1] */);
 void launch_count_pairs(mcb_ctx* ctx, int32_t N, const uint32_t* cnt, int64_t* row_counts);

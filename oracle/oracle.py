@@ -156,6 +156,33 @@ def graph_to_csr(N, src, dst, w):
     return (optr, dst[o].astype(np.int32), wf[o], iptr, src[i].astype(np.int32), wf[i])
 
 
+def truncate_edges(N, src, dst, w, sample, knn):
+    """`knn` of tgs_graph_cover_resample (reference call site R/coclust_graph_cov.r:39-41, which passes the graph's average
+    out-degree): inside one resample a node uses at most `knn` out edges.  DECISION `knn_rule` (tgstat is absent): among a
+    sampled node's out edges whose target is sampled too, keep the `knn` with the highest weight (16-bit fixed point as in
+    graph_to_csr; ties go to the lower target index); the dropped edges do not exist for that resample, in either
+    direction.  Returns the edge table of the resample's graph (edges with an unsampled endpoint are removed as well;
+    orc_graph_cover ignores them anyway).  knn <= 0: no limit."""
+    src = np.asarray(src, dtype=np.int64)
+    dst = np.asarray(dst, dtype=np.int64)
+    w = np.asarray(w, dtype=np.float64)
+    inside = np.zeros(N, dtype=bool)
+    inside[np.asarray(sample)] = True
+    keep = inside[src] & inside[dst]
+    src, dst, w = src[keep], dst[keep], w[keep]
+    if knn is None or knn <= 0 or src.size == 0:
+        return src.astype(np.int32), dst.astype(np.int32), w
+    wf = np.maximum(1, np.rint(w * 65536.0)).astype(np.int64)
+    order = np.lexsort((dst, -wf, src))                          # by source, weight descending, target ascending
+    s_o = src[order]
+    first = np.r_[0, np.flatnonzero(np.diff(s_o)) + 1]
+    start = np.repeat(first, np.diff(np.r_[first, s_o.size]))
+    place = np.arange(s_o.size) - start                           # position among the node's sampled out edges
+    sel = order[place < knn]
+    sel.sort()
+    return src[sel].astype(np.int32), dst[sel].astype(np.int32), w[sel]
+
+
 def graph_cover(N, csr, sample, min_size, cooling, burn_in, seed, max_sweeps=1000):
     optr, odst, ow, iptr, isrc, iw = csr
     sample = np.ascontiguousarray(sample, dtype=np.int32)

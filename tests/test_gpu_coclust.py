@@ -45,6 +45,53 @@ def test_cover_assignments_and_counts_bit_exact(ctx, oracle, ncells, K, min_size
     cc.destroy()
 
 
+@pytest.mark.parametrize("kernel", ["auto", "batch2", "batch4", "slow"])
+@pytest.mark.parametrize("ncells,K,knn,min_size", [(900, 15, 9, 8), (1400, 30, 20, 15)])
+def test_knn_edge_truncation_bit_exact(ctx, oracle, monkeypatch, ncells, K, knn, min_size, kernel):
+    """`knn` of tgs_graph_cover_resample (R/coclust_graph_cov.r:39-41): every resample's cover must equal the oracle's cover
+    of the resample's truncated graph (oracle.truncate_edges: at most knn highest-weight sampled out edges per node)."""
+    from metacell_b200 import _lib, synth
+    monkeypatch.setenv("MCB_COVER_KERNEL", kernel)
+    src, dst, w = _graph(oracle, ncells, K)
+    n_resamp = 4
+    sets, seeds = synth.resample_sets(ncells, 0.75, n_resamp, 23)
+    cc = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, min_size, 1.05, 10, knn=knn)
+    mc, sweeps = cc.assignments()
+    free = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, min_size, 1.05, 10, knn=0)
+    mc_free, _ = free.assignments()
+    free.destroy()
+    dense_o = np.zeros((ncells, ncells), np.uint32)
+    n_trunc = 0
+    for r in range(n_resamp):
+        ts, td, tw = oracle.truncate_edges(ncells, src, dst, w, sets[r], knn)
+        inside = np.zeros(ncells, bool); inside[sets[r]] = True
+        n_trunc += int((inside[src] & inside[dst]).sum()) - ts.size
+        omc, osw = oracle.graph_cover(ncells, oracle.graph_to_csr(ncells, ts, td, tw), sets[r], min_size, 1.05, 10, int(seeds[r]))
+        assert sweeps[r] == osw, (r, sweeps[r], osw)
+        assert np.array_equal(mc[r], omc), r
+        for k in range(omc.max() + 1):
+            mem = np.flatnonzero(omc == k)
+            dense_o[np.ix_(mem, mem)] += 1
+    assert n_trunc > 0, "the case must actually truncate"
+    assert not np.array_equal(mc, mc_free), "truncation changed nothing: the case does not exercise it"
+    n1, n2, cnt, ns = cc.pairs()
+    dense = np.zeros((ncells, ncells), np.uint32)
+    dense[n1, n2] = cnt
+    assert np.array_equal(dense, np.triu(dense_o, 1))
+    cc.destroy()
+
+
+def test_knn_at_or_above_max_out_degree_is_no_limit(ctx, oracle):
+    from metacell_b200 import _lib, synth
+    ncells, K = 700, 12
+    src, dst, w = _graph(oracle, ncells, K)
+    sets, seeds = synth.resample_sets(ncells, 0.75, 3, 4)
+    a = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, 8, 1.05, 10, knn=0)
+    b = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, 8, 1.05, 10, knn=K)
+    assert all(np.array_equal(x, y) for x, y in zip(a.assignments(), b.assignments()))
+    a.destroy(); b.destroy()
+
+
 def test_rank_sharding_sums_to_whole(ctx, oracle):
     """resamples strided over 3 emulated ranks: counters add up to the single-rank result"""
     from metacell_b200 import _lib, synth

@@ -277,3 +277,25 @@ def test_golden_vectors(oracle):
     for r in range(3):
         mc, _ = oracle.graph_cover(M, csr, g["sets"][r], 5, 1.05, 10, int(g["seeds"][r]))
         assert np.array_equal(mc, g["mcs"][r])
+
+
+def test_truncate_edges_keeps_the_knn_heaviest_sampled_out_edges():
+    """oracle.truncate_edges (`knn` of tgs_graph_cover_resample, R/coclust_graph_cov.r:39-41) against a literal loop"""
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    N, knn = 60, 4
+    src, dst = np.nonzero(rng.random((N, N)) < 0.2)
+    keep = src != dst
+    src, dst = src[keep].astype(np.int32), dst[keep].astype(np.int32)
+    w = np.round(rng.random(src.size) * 8) / 8 + 1.0 / 65536                   # many tied weights
+    sample = np.sort(rng.choice(N, 45, replace=False)).astype(np.int32)
+    ts, td, tw = O.truncate_edges(N, src, dst, w, sample, knn)
+    inside = set(sample.tolist())
+    want = set()
+    for v in inside:
+        cand = [(-(max(1, int(np.rint(w[e] * 65536.0)))), int(dst[e])) for e in np.flatnonzero(src == v) if int(dst[e]) in inside]
+        for _, u in sorted(cand)[:knn]:
+            want.add((v, u))
+    assert set(zip(ts.tolist(), td.tolist())) == want
+    a, b, c = O.truncate_edges(N, src, dst, w, sample, 0)
+    assert a.size == sum(1 for s_, d_ in zip(src.tolist(), dst.tolist()) if s_ in inside and d_ in inside)
