@@ -340,6 +340,10 @@ def run_ours(a):
     stages = ctx.timings()
     ctx.timings_reset()
     ctx.set_option("profile", 0)
+    if os.environ.get("MCB_BENCH_DUMP_STAGES"):           # diagnosis of rank skew: every rank's own stage timings
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", f"{os.environ['MCB_BENCH_DUMP_STAGES']}_rank{rank}.json"), "w") as fh:
+            json.dump(_stage_dict(stages), fh)
     # end to end through host buffers (the one-shot call; the host wall clock is reported beside the device time because
     # the staging threads work before the first and after the last device operation)
     for _ in range(2):

@@ -1147,12 +1147,12 @@ void mcb::cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
     }
     const RouteShape rs = route_shape(ctx, g->rows_per_rank, P, H, g->rank_bits);
     DevBuf<uint32_t> counts(ctx, (size_t)rs.grid * rs.nbuckets);
-    DevBuf<int64_t> btotal(ctx, (size_t)rs.nbuckets), bstart(ctx, (size_t)rs.nbuckets + 1);
-    DevBuf<uint64_t> records(ctx, rows1 * Kc);
+    DevBuf<int64_t> btotal(ctx, (size_t)rs.nbuckets), bpad(ctx, (size_t)rs.nbuckets), bstart(ctx, (size_t)rs.nbuckets + 1);
+    DevBuf<uint64_t> records(ctx, rows1 * Kc + (size_t)rs.nbuckets);          // every bucket padded to an even number of records
     {
-        StageTimer t(ctx, "balance_route", 4);
+        StageTimer t(ctx, "balance_route", 5);
         launch_route_records(ctx, g->knn_col.p, row0, rows, Kc, g->rows_per_rank, rs, g->rank_bits, ctx->keep_self, counts.p, btotal.p,
-                             bstart.p, records.p);
+                             bpad.p, bstart.p, records.p);
     }
     g->sym.zero();
     const int32_t nbr = rs.nbr;
@@ -1161,7 +1161,7 @@ void mcb::cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
         DevBuf<int32_t> seg_block(ctx, (size_t)nbr);
         launch_iota_i32(ctx, seg_block.p, nbr);
         StageTimer t(ctx, "balance_probe");
-        launch_probe(ctx, records.p, (int64_t)rows * Kc, bstart.p, bstart.p, seg_block.p, nbr, rs.blk_shift, table.p, H, g->rank_bits, Kc,
+        launch_probe(ctx, records.p, (int64_t)rows * Kc + rs.nbuckets, bstart.p, bstart.p, seg_block.p, nbr, rs.blk_shift, table.p, H, g->rank_bits, Kc,
                      smax, ctx->thresh_strict, g->sym.p);
         // (n_records is an upper bound: the prefix ends at the true count, positions past it fall in no segment)
     } else {
@@ -1173,9 +1173,10 @@ void mcb::cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
         const int me = comm->rank;
         std::vector<size_t> soff((size_t)P), scnt((size_t)P), roff((size_t)P), rcnt((size_t)P);
         size_t srun = 0, rrun = 0;
+        auto even = [](int64_t c) { return (size_t)((c + 1) & ~(int64_t)1); };            // bucket strides (launch_route_records)
         for (int r = 0; r < P; ++r) {
             size_t to_r = 0, from_r = 0;
-            for (int b = 0; b < nbr; ++b) { to_r += (size_t)mine[(size_t)r * nbr + b]; from_r += (size_t)all[(size_t)r * rs.nbuckets + (size_t)me * nbr + b]; }
+            for (int b = 0; b < nbr; ++b) { to_r += even(mine[(size_t)r * nbr + b]); from_r += even(all[(size_t)r * rs.nbuckets + (size_t)me * nbr + b]); }
             soff[r] = srun * 8; scnt[r] = to_r * 8; srun += to_r;
             roff[r] = rrun * 8; rcnt[r] = from_r * 8; rrun += from_r;
         }
@@ -1195,7 +1196,7 @@ void mcb::cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
                 const int q = b * P + r;
                 const int64_t c = all[(size_t)r * rs.nbuckets + (size_t)me * nbr + b];
                 h_prefix[q] = run; h_src[q] = (int64_t)piece[r]; h_blk[q] = b;
-                run += c; piece[r] += (size_t)c;
+                run += c; piece[r] += even(c);
             }
         h_prefix[nseg] = run;
         DevBuf<int64_t> seg_prefix(ctx, (size_t)nseg + 1), seg_src(ctx, (size_t)nseg);

@@ -126,7 +126,8 @@ route_count_kernel(const int32_t* __restrict__ knn_col, int64_t row0, int64_t ro
 }
 // per bucket: exclusive prefix of the CTAs' counts (in place) and the bucket total.  One warp per bucket, 32 CTAs per step.
 __global__ void __launch_bounds__(128)
-route_offsets_kernel(uint32_t* __restrict__ counts, int32_t nctas, int32_t nbuckets, int64_t* __restrict__ total)
+route_offsets_kernel(uint32_t* __restrict__ counts, int32_t nctas, int32_t nbuckets, int64_t* __restrict__ total,
+                     int64_t* __restrict__ padded)
 {
     const int lane = threadIdx.x & 31;
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -141,7 +142,17 @@ route_offsets_kernel(uint32_t* __restrict__ counts, int32_t nctas, int32_t nbuck
         if (c < nctas) counts[(int64_t)c * nbuckets + b] = carry + inc - v;
         carry += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) total[b] = carry;
+    if (lane == 0) { total[b] = carry; padded[b] = ((int64_t)carry + 1) & ~(int64_t)1; }
+}
+// Buckets start on 16-byte boundaries (an even number of 8-byte records): NCCL's send / recv moves 16-byte vectors only when
+// source and destination are aligned alike, and the unaligned path was measured at a third of the bandwidth (0.2 GB in
+// 1.7 ms instead of 0.65 ms on two ranks).  The pad slot of an odd bucket holds a record no table answers.
+constexpr uint64_t ROUTE_PAD_RECORD = 0xffffffff00000000ull;
+__global__ void route_pad_kernel(int32_t nbuckets, const int64_t* __restrict__ total, const int64_t* __restrict__ bucket_start,
+                                 uint64_t* __restrict__ records)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbuckets && (total[b] & 1)) records[bucket_start[b] + total[b]] = ROUTE_PAD_RECORD;
 }
 // pass 2: records[bucket_start[b] + within[cta][b] + k] = (source row i : 32 | row of j inside its block : * | rank0 : rank_bits).
 // The lanes of a warp that target the same bucket take their slots with ONE shared-memory atomic (match_any + popc).
@@ -647,7 +658,8 @@ RouteShape route_shape(mcb_ctx* ctx, int64_t rows_per_rank, int32_t nranks, int3
 }
 void launch_route_records(mcb_ctx* ctx, const int32_t* knn_col_own, int64_t row0, int64_t rows, int32_t Kc, int64_t rows_per_rank,
                           const RouteShape& rs, int32_t rank_bits, int keep_self, uint32_t* counts /* [grid][nbuckets] */,
-                          int64_t* bucket_total /* [nbuckets] */, int64_t* bucket_start /* [nbuckets + 1] */, uint64_t* records)
+                          int64_t* bucket_total /* [nbuckets] true counts */, int64_t* bucket_padded /* [nbuckets] rounded up to even */,
+                          int64_t* bucket_start /* [nbuckets + 1] prefix of the padded counts */, uint64_t* records /* rows * Kc + nbuckets */)
 {
     RouteGeom geo{(uint32_t)rows_per_rank, rs.blk_shift, rs.nbr, rs.nbuckets, rank_bits};
     const size_t smem1 = (size_t)rs.nbuckets * sizeof(uint32_t), smem2 = (size_t)rs.nbuckets * (sizeof(long long) + sizeof(uint32_t));
@@ -656,10 +668,12 @@ void launch_route_records(mcb_ctx* ctx, const int32_t* knn_col_own, int64_t row0
     ensure_dyn_smem(o2, ctx, route_scatter_kernel, smem2);
     route_count_kernel<<<rs.grid, ROUTE_THREADS, smem1, ctx->stream>>>(knn_col_own, row0, rows, Kc, geo, keep_self, counts);
     MCB_LAUNCH_CHECK();
-    route_offsets_kernel<<<(int)ceil_div(rs.nbuckets, 4), 128, 0, ctx->stream>>>(counts, rs.grid, rs.nbuckets, bucket_total);
+    route_offsets_kernel<<<(int)ceil_div(rs.nbuckets, 4), 128, 0, ctx->stream>>>(counts, rs.grid, rs.nbuckets, bucket_total, bucket_padded);
     MCB_LAUNCH_CHECK();
-    launch_exclusive_scan_i64(ctx, bucket_total, bucket_start, rs.nbuckets, bucket_start + rs.nbuckets);
+    launch_exclusive_scan_i64(ctx, bucket_padded, bucket_start, rs.nbuckets, bucket_start + rs.nbuckets);
     route_scatter_kernel<<<rs.grid, ROUTE_THREADS, smem2, ctx->stream>>>(knn_col_own, row0, rows, Kc, geo, keep_self, counts, bucket_start, records);
+    MCB_LAUNCH_CHECK();
+    route_pad_kernel<<<(int)ceil_div(rs.nbuckets, 256), 256, 0, ctx->stream>>>(rs.nbuckets, bucket_total, bucket_start, records);
     MCB_LAUNCH_CHECK();
 }
 void launch_probe(mcb_ctx* ctx, const uint64_t* records, int64_t n_records, const int64_t* seg_prefix, const int64_t* seg_src,

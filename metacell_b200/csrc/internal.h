@@ -246,7 +246,7 @@ struct RouteShape { int32_t blk_shift, nbr, nbuckets, grid; };
 RouteShape route_shape(mcb_ctx* ctx, int64_t rows_per_rank, int32_t nranks, int32_t H, int32_t rank_bits);
 void launch_route_records(mcb_ctx* ctx, const int32_t* knn_col_own, int64_t row0, int64_t rows, int32_t Kc, int64_t rows_per_rank,
                           const RouteShape& rs, int32_t rank_bits, int keep_self, uint32_t* counts, int64_t* bucket_total,
-                          int64_t* bucket_start, uint64_t* records);
+                          int64_t* bucket_padded, int64_t* bucket_start, uint64_t* records);
 void launch_probe(mcb_ctx* ctx, const uint64_t* records, int64_t n_records, const int64_t* seg_prefix, const int64_t* seg_src,
                   const int32_t* seg_block, int32_t nseg, int32_t blk_shift, const uint32_t* table_own, int32_t H, int32_t rank_bits,
                   int32_t Kc, int64_t smax, int strict, uint32_t* sym_own);
