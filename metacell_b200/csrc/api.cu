@@ -138,6 +138,23 @@ extern "C" int mcb_ctx_create(int device, mcb_ctx** out)
     *out = c;
     MCB_API_END
 }
+cudaStream_t mcb_ctx::side()
+{
+    if (!side_stream) MCB_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    return side_stream;
+}
+void mcb_cgraph::wait_planes()
+{
+    if (!planes_pending) return;
+    planes_pending = false;
+    MCB_CUDA(cudaStreamWaitEvent(ctx->stream, planes_ready, 0));
+}
+mcb_cgraph::~mcb_cgraph()
+{
+    // the buffers go back to the stream-ordered pool: the context's stream must be behind the side stream's writes
+    if (planes_pending) cudaStreamWaitEvent(ctx->stream, planes_ready, 0);
+    if (planes_ready) cudaEventDestroy(planes_ready);
+}
 void mcb::ctx_retain(mcb_ctx* c) { c->refs.fetch_add(1); }
 void mcb::ctx_release(mcb_ctx* ctx)
 {
@@ -148,6 +165,7 @@ void mcb::ctx_release(mcb_ctx* ctx)
     mcb::ctx_staging_destroy(ctx);
     if (ctx->samp_dev) { cudaFree(ctx->samp_dev); ctx->samp_dev = nullptr; }
     ctx->trim();
+    if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -614,11 +632,17 @@ mcb_cgraph* mcb::cgraph_features_csc(mcb_ctx* ctx, mcb_comm* comm, const mcb_csc
         launch_feat_stats(ctx, m->ncells, m->p, m->i, m->x, d_fmap.p, G, k_nonz, mu.p, inv.p, valid.p);
         if (m->ncells) launch_exclusive_scan_i32(ctx, valid.p, rowpos.p, m->ncells, total.p);
     }
-    int32_t Mloc = 0;
-    MCB_CUDA(cudaMemcpyAsync(&Mloc, total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-    std::vector<int64_t> counts(1, Mloc);
-    if (multi) counts = comm_allgather_i64(comm, Mloc);
+    std::vector<int64_t> counts(1, 0);
+    if (multi) {            // every rank's count of valid cells: widened and all-gathered on the device, one host synchronisation
+        DevBuf<int64_t> tot64(ctx, 1);
+        launch_widen_i32(ctx, total.p, tot64.p, 1);
+        counts = comm_allgather_dev_i64v(comm, tot64.p, 1);
+    } else {
+        int32_t Mloc = 0;
+        MCB_CUDA(cudaMemcpyAsync(&Mloc, total.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        counts[0] = Mloc;
+    }
     int64_t M = 0, before = 0;
     for (size_t r = 0; r < counts.size(); ++r) { if (multi && (int)r < comm->rank) before += counts[r]; M += counts[r]; }
     g->M = M; g->Mpad = round_up(std::max<int64_t>(M, 1), 256);
@@ -630,15 +654,22 @@ mcb_cgraph* mcb::cgraph_features_csc(mcb_ctx* ctx, mcb_comm* comm, const mcb_csc
                          multi ? nullptr : g->Zf.p, g->Zh.p + off, g->Zl.p + off, g->cell_of_row.p + before, multi ? cell_base : 0);
     }
     if (multi) {
-        StageTimer t(ctx, "allgather_features", 0);
+        // the hi plane (all the sampling pass needs) on the context's stream; the lo plane and the row -> cell map on the
+        // side stream, under the sampling pass (cgraph_knn waits for them before the filter pass)
         std::vector<size_t> offs(counts.size()), cnts(counts.size());
         size_t run = 0;
         for (size_t r = 0; r < counts.size(); ++r) { offs[r] = run * g->Gpad * sizeof(__half); cnts[r] = (size_t)counts[r] * g->Gpad * sizeof(__half); run += (size_t)counts[r]; }
-        comm_allgatherv_inplace(comm, g->Zh.p, offs.data(), cnts.data());
-        comm_allgatherv_inplace(comm, g->Zl.p, offs.data(), cnts.data());
-        run = 0;
-        for (size_t r = 0; r < counts.size(); ++r) { offs[r] = run * sizeof(int32_t); cnts[r] = (size_t)counts[r] * sizeof(int32_t); run += (size_t)counts[r]; }
-        comm_allgatherv_inplace(comm, g->cell_of_row.p, offs.data(), cnts.data());
+        cudaStream_t side = ctx->side();
+        if (!g->planes_ready) MCB_CUDA(cudaEventCreateWithFlags(&g->planes_ready, cudaEventDisableTiming));
+        MCB_CUDA(cudaEventRecord(g->planes_ready, ctx->stream));                 // feat_rows done
+        MCB_CUDA(cudaStreamWaitEvent(side, g->planes_ready, 0));
+        { StageTimer t(ctx, "allgather_features", 0); comm_allgatherv_inplace(comm, g->Zh.p, offs.data(), cnts.data()); }
+        comm_allgatherv_inplace(comm, g->Zl.p, offs.data(), cnts.data(), side);
+        // row -> cell map: 4-byte items, so a rank's block may start off a 16-byte boundary; it is small, broadcast per rank
+        for (size_t r = 0, at = 0; r < counts.size(); at += (size_t)counts[r], ++r)
+            if (counts[r]) comm_broadcast_on(comm, g->cell_of_row.p + at, (size_t)counts[r] * sizeof(int32_t), (int)r, side);
+        MCB_CUDA(cudaEventRecord(g->planes_ready, side));
+        g->planes_pending = true;
     }
     return g.release();          // temporaries are released in stream order (the block cache reuses on this stream only)
 }
@@ -704,6 +735,7 @@ extern "C" int mcb_cgraph_valid_cells(mcb_cgraph* g, int32_t* host)
     MCB_API_BEGIN
     MCB_CHECK(g && host, "null argument");
     MCB_CUDA(cudaSetDevice(g->ctx->device));
+    g->wait_planes();
     if (g->M) MCB_CUDA(cudaMemcpyAsync(host, g->cell_of_row.p, sizeof(int32_t) * (size_t)g->M, cudaMemcpyDeviceToHost, g->ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(g->ctx->stream));
     MCB_API_END
@@ -894,6 +926,7 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
 static void knn_filter(mcb_cgraph* g, int exchange)
 {
     mcb_ctx* ctx = g->ctx;
+    g->wait_planes();              // multi-rank: the lo plane arrives on the side stream
     const int64_t M = g->M, rows = g->rows, row0 = g->row0;
     const int32_t Gpad = g->Gpad, cap = g->cap, nranks = g->nranks;
     g->exchange = exchange;
@@ -926,29 +959,42 @@ static void knn_filter(mcb_cgraph* g, int exchange)
             if (exchange) launch_tc_filter(ctx, g->Zh.p, g->Zl.p, g->Mpad, 0, M, M, Gpad, g->thr_all.p, pool, g->rank, nranks);
             else if (rows) launch_tc_filter(ctx, g->Zh.p, g->Zl.p, g->Mpad, row0, rows, M, Gpad, g->thr_all.p + row0, pool);
         }
-        uint32_t hctl[2] = {0, 0};
-        MCB_CUDA(cudaMemcpyAsync(hctl, g->pool_ctl.p, sizeof(hctl), cudaMemcpyDeviceToHost, ctx->stream));
-        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (!hctl[1]) break;
+        if (!exchange) {
+            uint32_t hctl[2] = {0, 0};
+            MCB_CUDA(cudaMemcpyAsync(hctl, g->pool_ctl.p, sizeof(hctl), cudaMemcpyDeviceToHost, ctx->stream));
+            MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (!hctl[1]) break;
+        } else {
+            // records per owner rank + this rank's overflow flag, all-gathered on the device: ONE host synchronisation tells
+            // every rank what it sends, what it receives, and whether anyone's pool ran out (then all repeat the pass together)
+            DevBuf<uint64_t> cnt_ov(ctx, (size_t)nranks + 1), cur(ctx, (size_t)nranks);
+            cnt_ov.zero(); cur.zero();
+            std::vector<int64_t> all;
+            {
+                StageTimer t(ctx, "records_partition", 1);
+                launch_count_records_by_dest(ctx, pool, g->rows_per_rank, nranks, cnt_ov.p);
+                MCB_CUDA(cudaMemcpyAsync(cnt_ov.p + nranks, g->pool_ctl.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+                all = comm_allgather_dev_i64v(g->comm, reinterpret_cast<const int64_t*>(cnt_ov.p), nranks + 1);
+            }
+            bool overflow = false;
+            for (int r = 0; r < nranks; ++r) overflow |= all[(size_t)r * (nranks + 1) + nranks] != 0;
+            if (!overflow) {
+                g->recv_counts.assign((size_t)nranks, 0);
+                int64_t tot = 0;
+                for (int r = 0; r < nranks; ++r) {
+                    g->send_counts[r] = all[(size_t)g->rank * (nranks + 1) + r];
+                    g->recv_counts[r] = all[(size_t)r * (nranks + 1) + g->rank];
+                    tot += g->send_counts[r];
+                }
+                StageTimer t(ctx, "records_partition", 1);
+                g->send.alloc(ctx, (size_t)std::max<int64_t>(tot, 1));
+                launch_partition_records(ctx, pool, g->rows_per_rank, nranks, cnt_ov.p, cur.p, g->send.p);
+                g->pool_records.release();              // stream ordered
+                break;
+            }
+        }
         MCB_CHECK(attempt < 3, "MC-ERR: candidate pool overflow (correlation structure far from the sampled estimate)");
         expect *= 2.0;          // the pool ran out: repeat the pass with twice the room
-    }
-    if (exchange) {
-        // group the records by owner rank for the all-to-all
-        StageTimer t(ctx, "records_partition", 2);
-        CandPool pool{g->pool_records.p, g->pool_ctl.p, g->pool_fill.p, g->pool_chunks, g->pool_ctl.p + 1};
-        DevBuf<uint64_t> counts(ctx, (size_t)nranks), base(ctx, (size_t)nranks), cur(ctx, (size_t)nranks);
-        counts.zero(); cur.zero();
-        launch_count_records_by_dest(ctx, pool, g->rows_per_rank, nranks, counts.p);
-        std::vector<uint64_t> hc((size_t)nranks), hb((size_t)nranks);
-        MCB_CUDA(cudaMemcpyAsync(hc.data(), counts.p, sizeof(uint64_t) * (size_t)nranks, cudaMemcpyDeviceToHost, ctx->stream));
-        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-        uint64_t tot = 0;
-        for (int32_t r = 0; r < nranks; ++r) { hb[r] = tot; tot += hc[r]; g->send_counts[r] = (int64_t)hc[r]; }
-        MCB_CUDA(cudaMemcpyAsync(base.p, hb.data(), sizeof(uint64_t) * (size_t)nranks, cudaMemcpyHostToDevice, ctx->stream));
-        g->send.alloc(ctx, (size_t)std::max<uint64_t>(tot, 1));
-        launch_partition_records(ctx, pool, g->rows_per_rank, nranks, base.p, cur.p, g->send.p);
-        g->pool_records.release();              // stream ordered
     }
 }
 
@@ -1033,12 +1079,11 @@ void mcb::cgraph_knn(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, i
     mcb_ctx* ctx = g->ctx;
     { StageTimer t(ctx, "allgather_thresholds", 0); comm_allgather_inplace(comm, g->thr_all.p, (size_t)g->rows_per_rank * sizeof(float)); }
     knn_filter(g, 1);
-    const std::vector<int64_t> all = comm_allgather_i64v(comm, g->send_counts.data(), nranks);      // [sender][owner]
     std::vector<size_t> soff((size_t)nranks), scnt((size_t)nranks), roff((size_t)nranks), rcnt((size_t)nranks);
     size_t srun = 0, rrun = 0;
     for (int r = 0; r < nranks; ++r) {
         soff[r] = srun * sizeof(uint4); scnt[r] = (size_t)g->send_counts[r] * sizeof(uint4); srun += (size_t)g->send_counts[r];
-        const size_t from_r = (size_t)all[(size_t)r * nranks + rank];
+        const size_t from_r = (size_t)g->recv_counts[r];            // exchanged in knn_filter
         roff[r] = rrun * sizeof(uint4); rcnt[r] = from_r * sizeof(uint4); rrun += from_r;
     }
     g->recv.alloc(ctx, std::max<size_t>(rrun, 1));
@@ -1166,11 +1211,9 @@ void mcb::cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
         // (n_records is an upper bound: the prefix ends at the true count, positions past it fall in no segment)
     } else {
         // bucket totals of every rank -> who sends how much to whom, and where each (sender, block) piece lands here
-        std::vector<int64_t> mine((size_t)rs.nbuckets);
-        MCB_CUDA(cudaMemcpyAsync(mine.data(), btotal.p, sizeof(int64_t) * mine.size(), cudaMemcpyDeviceToHost, ctx->stream));
-        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
-        const std::vector<int64_t> all = comm_allgather_i64v(comm, mine.data(), rs.nbuckets);          // [sender][bucket]
+        const std::vector<int64_t> all = comm_allgather_dev_i64v(comm, btotal.p, rs.nbuckets);         // [sender][bucket], one host sync
         const int me = comm->rank;
+        const int64_t* mine = all.data() + (size_t)me * rs.nbuckets;
         std::vector<size_t> soff((size_t)P), scnt((size_t)P), roff((size_t)P), rcnt((size_t)P);
         size_t srun = 0, rrun = 0;
         auto even = [](int64_t c) { return (size_t)((c + 1) & ~(int64_t)1); };            // bucket strides (launch_route_records)
@@ -1209,7 +1252,7 @@ void mcb::cgraph_mutual(mcb_cgraph* g, int32_t k_beta)
             launch_probe(ctx, recv.p, run, seg_prefix.p, seg_src.p, seg_block.p, nseg, rs.blk_shift, table.p, H, g->rank_bits, Kc, smax,
                          ctx->thresh_strict, g->sym.p);
         }
-        MCB_CUDA(cudaStreamSynchronize(ctx->stream));          // the segment tables above are pageable host vectors
+        // (the copies above come from pageable host vectors: cudaMemcpyAsync stages such a source before it returns)
     }
     {
         StageTimer t(ctx, "balance_cut");

@@ -90,15 +90,19 @@ void comm_allgather_inplace(mcb_comm* c, void* buf, size_t bytes_per_rank)
     MCB_NCCL(nccl().AllGather((const char*)buf + (size_t)c->rank * bytes_per_rank, buf, bytes_per_rank, ncclInt8,
                               (ncclComm_t)c->comm, c->ctx->stream));
 }
-// blocks of different sizes: rank r owns [offs[r], offs[r] + counts[r]) bytes of buf, in place
-void comm_allgatherv_inplace(mcb_comm* c, void* buf, const size_t* offs, const size_t* counts)
+// blocks of different sizes: rank r owns [offs[r], offs[r] + counts[r]) bytes of buf, in place.  Every rank sends its
+// block straight to every peer (NVSwitch: all pairs at full bandwidth) -- grouped broadcasts ran at half this rate on 8
+// ranks.  `stream` = 0: the context's stream.  Blocks should start on 16-byte boundaries (see comm_alltoallv's callers).
+void comm_allgatherv_inplace(mcb_comm* c, void* buf, const size_t* offs, const size_t* counts, cudaStream_t stream)
 {
     if (c->nranks == 1) return;
+    if (!stream) stream = c->ctx->stream;
+    const char* mine = (const char*)buf + offs[c->rank];
     MCB_NCCL(nccl().GroupStart());
     for (int r = 0; r < c->nranks; ++r) {
-        if (counts[r] == 0) continue;
-        char* p = (char*)buf + offs[r];
-        MCB_NCCL(nccl().Broadcast(p, p, counts[r], ncclInt8, r, (ncclComm_t)c->comm, c->ctx->stream));
+        if (r == c->rank) continue;
+        if (counts[c->rank]) MCB_NCCL(nccl().Send(mine, counts[c->rank], ncclInt8, r, (ncclComm_t)c->comm, stream));
+        if (counts[r]) MCB_NCCL(nccl().Recv((char*)buf + offs[r], counts[r], ncclInt8, r, (ncclComm_t)c->comm, stream));
     }
     MCB_NCCL(nccl().GroupEnd());
 }
@@ -139,6 +143,11 @@ void comm_reduce_sum_u32(mcb_comm* c, void* buf, size_t count, int root)
     if (c->nranks == 1 || count == 0) return;
     MCB_NCCL(nccl().Reduce(buf, buf, count, ncclUint32, ncclSum, root, (ncclComm_t)c->comm, c->ctx->stream));
 }
+void comm_broadcast_on(mcb_comm* c, void* buf, size_t bytes, int root, cudaStream_t stream)
+{
+    if (c->nranks == 1 || bytes == 0) return;
+    MCB_NCCL(nccl().Broadcast(buf, buf, bytes, ncclInt8, root, (ncclComm_t)c->comm, stream));
+}
 void comm_broadcast(mcb_comm* c, void* buf, size_t bytes, int root)
 {
     if (c->nranks == 1 || bytes == 0) return;
@@ -154,6 +163,25 @@ std::vector<int64_t> comm_allgather_i64(mcb_comm* c, int64_t mine)
     DevBuf<int64_t> d(ctx, (size_t)c->nranks);
     MCB_CUDA(cudaMemcpyAsync(d.p + c->rank, &mine, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     comm_allgather_inplace(c, d.p, sizeof(int64_t));
+    MCB_CUDA(cudaMemcpyAsync(out.data(), d.p, sizeof(int64_t) * out.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return out;
+}
+// `n` int64 per rank that are already ON THE DEVICE (dev_mine), all ranks' blocks back on the host: [nranks][n].  One host
+// synchronisation for the device -> host hop and the exchange together (the host-in variant below costs the caller a
+// second one for its own device -> host copy).
+std::vector<int64_t> comm_allgather_dev_i64v(mcb_comm* c, const int64_t* dev_mine, int n)
+{
+    std::vector<int64_t> out((size_t)c->nranks * n);
+    mcb_ctx* ctx = c->ctx;
+    if (c->nranks == 1) {
+        MCB_CUDA(cudaMemcpyAsync(out.data(), dev_mine, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        MCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return out;
+    }
+    DevBuf<int64_t> d(ctx, out.size());
+    MCB_CUDA(cudaMemcpyAsync(d.p + (size_t)c->rank * n, dev_mine, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
+    comm_allgather_inplace(c, d.p, sizeof(int64_t) * (size_t)n);
     MCB_CUDA(cudaMemcpyAsync(out.data(), d.p, sizeof(int64_t) * out.size(), cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
     return out;

@@ -24,6 +24,10 @@ struct mcb_cgraph {
     mcb::DevBuf<float> Zf;              // fp32 plane (CUDA-core kernels; single-rank builds only)
     mcb::DevBuf<__half> Zh, Zl;         // fp16 hi / lo planes of z * 2^12 (tensor-core kernels)
     mcb::DevBuf<int32_t> cell_of_row;
+    cudaEvent_t planes_ready = nullptr;  // multi-rank: the lo plane's all-gather runs on the side stream under the sampling pass
+    bool planes_pending = false;
+    void wait_planes();                  // orders the context's stream behind that all-gather (idempotent)
+    ~mcb_cgraph();
     // knn
     int32_t K = 0, k_expand = 0, Kc = 0, kc_out = 0, rank = 0, nranks = 1;
     int64_t rows_per_rank = 0, row0 = 0, rows = 0;
@@ -33,7 +37,7 @@ struct mcb_cgraph {
     mcb::DevBuf<float> thr_all;                               // filter thresholds, [nranks * rows_per_rank]
     mcb::DevBuf<uint64_t> cand; mcb::DevBuf<uint32_t> cnt;    // per-row candidate lists of the owned rows
     mcb::DevBuf<uint4> pool_records; mcb::DevBuf<uint32_t> pool_fill, pool_ctl; uint32_t pool_chunks = 0;
-    mcb::DevBuf<uint4> send, recv; std::vector<int64_t> send_counts;   // symmetric multi-GPU record exchange
+    mcb::DevBuf<uint4> send, recv; std::vector<int64_t> send_counts, recv_counts;   // symmetric multi-GPU record exchange
     // balance
     int32_t H = 0, rank_bits = 0, k_beta = 0;
     mcb::DevBuf<uint32_t> sym; mcb::DevBuf<uint64_t> thr_in;

@@ -17,6 +17,8 @@ struct mcb_ctx {
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t side_stream = nullptr;   // second stream for an exchange that overlaps compute (created on first use)
+    cudaStream_t side();
     // size-keyed cache of device blocks: a step repeats the same allocation sizes, so after the first
     // step no allocation reaches the driver (driver allocation calls were measured to stall for tens of
     // ms under a busy host).  Reuse is safe because every user of a block is ordered on `stream`.
@@ -180,7 +182,7 @@ void launch_sample_thresholds_fused(mcb_ctx* ctx, int f8, const void* A, int64_t
                                     uint32_t* n_escaped);
 // select.cu: symmetric multi-GPU record exchange helpers
 void launch_count_records_by_dest(mcb_ctx* ctx, const CandPool& pool, int64_t rows_per_rank, int32_t nranks, uint64_t* counts);
-void launch_partition_records(mcb_ctx* ctx, const CandPool& pool, int64_t rows_per_rank, int32_t nranks, const uint64_t* base,
+void launch_partition_records(mcb_ctx* ctx, const CandPool& pool, int64_t rows_per_rank, int32_t nranks, const uint64_t* counts,
                               uint64_t* cursor, void* send);
 void launch_scatter_flat(mcb_ctx* ctx, const void* records, int64_t n, int64_t row0, uint64_t* cand, uint32_t* cnt, int32_t cap);
 // select.cu: bin the pool's records into the per-row candidate lists (cnt counts every record, also past cap)

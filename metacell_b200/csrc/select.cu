@@ -313,11 +313,15 @@ count_records_by_dest_kernel(const uint4* __restrict__ records, const uint32_t* 
 __global__ void __launch_bounds__(256)
 partition_records_kernel(const uint4* __restrict__ records, const uint32_t* __restrict__ cursor,
                          const uint32_t* __restrict__ chunk_fill, uint32_t pool_chunks, uint32_t chunk_records,
-                         uint32_t rows_per_rank, int nranks, const unsigned long long* __restrict__ base,
+                         uint32_t rows_per_rank, int nranks, const unsigned long long* __restrict__ counts,
                          unsigned long long* __restrict__ cur, uint4* __restrict__ send)
 {
+    // counts[d] = records for destination d (count_records_by_dest_kernel); a destination's segment of `send` starts at the
+    // sum of the counts before it -- derived here, so the host never has to hand the prefix back
     __shared__ uint32_t sc[MAX_RANKS];
-    __shared__ unsigned long long sb[MAX_RANKS];
+    __shared__ unsigned long long sb[MAX_RANKS], base[MAX_RANKS];
+    if (threadIdx.x == 0) { unsigned long long run = 0; for (int d = 0; d < nranks; ++d) { base[d] = run; run += counts[d]; } }
+    __syncthreads();
     const uint32_t used = min(*cursor, pool_chunks);
     for (uint32_t ch = blockIdx.x; ch < used; ch += gridDim.x) {
         if (threadIdx.x < MAX_RANKS) sc[threadIdx.x] = 0;
@@ -590,13 +594,13 @@ void launch_count_records_by_dest(mcb_ctx* ctx, const CandPool& pool, int64_t ro
                                                                 (unsigned long long*)counts);
     MCB_LAUNCH_CHECK();
 }
-void launch_partition_records(mcb_ctx* ctx, const CandPool& pool, int64_t rows_per_rank, int32_t nranks, const uint64_t* base,
+void launch_partition_records(mcb_ctx* ctx, const CandPool& pool, int64_t rows_per_rank, int32_t nranks, const uint64_t* counts,
                               uint64_t* cursor, void* send)
 {
     int grid = (int)std::min<int64_t>(pool.n_chunks, (int64_t)ctx->num_sms * 8);
     partition_records_kernel<<<grid, 256, 0, ctx->stream>>>((const uint4*)pool.records, pool.cursor, pool.chunk_fill, pool.n_chunks,
                                                             tc_pool_chunk_records(), (uint32_t)rows_per_rank, nranks,
-                                                            (const unsigned long long*)base, (unsigned long long*)cursor, (uint4*)send);
+                                                            (const unsigned long long*)counts, (unsigned long long*)cursor, (uint4*)send);
     MCB_LAUNCH_CHECK();
 }
 void launch_scatter_flat(mcb_ctx* ctx, const void* records, int64_t n, int64_t row0, uint64_t* cand, uint32_t* cnt, int32_t cap)
