@@ -573,7 +573,7 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
     constexpr int FT = 128;            // threads per sub-block (one visited node each)
     constexpr int NT = FT * B;
     constexpr int NW = NT / 32;
-    static_assert(4 * B <= 32, "one lane per (node, warp) partial");
+    static_assert(B <= 32, "one lane per node of a batch");
     extern __shared__ uint32_t dsm[];
     int32_t* size = (int32_t*)dsm;                               // [ncl_cap]
     uint32_t* wout = dsm + ncl_cap;                              // [B][2][ncl_cap]
@@ -581,14 +581,21 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
     VT* vlist = (VT*)(win + (size_t)2 * B * ncl_cap);            // [n_s]
     int16_t* mc_s = (int16_t*)(vlist + ((n_s + 1) & ~1));        // [N]
     __shared__ unsigned long long s_part[NT];
-    __shared__ unsigned long long s_pbits[2][B * 4];   // per-(node, warp) partial arg-max, double buffered by batch parity
-    __shared__ int s_pk[2][B * 4];
+    __shared__ unsigned long long s_pbits[2][B];       // per-node arg-max (score bits, cluster), double buffered by batch parity
+    __shared__ int s_pk[2][B];
+    // distinct clusters reached by the visited node's out edges (its ~100 edges point into a handful of clusters): the
+    // first edge that adds to a cluster's accumulator lists it, and ONE warp scores the list -- the fp64 division of
+    // the score used to be issued by all four warps of the node, a dozen times per cluster
+    constexpr int CL_MAX = 128 * OUT_SLOTS;
+    __shared__ int16_t s_clist[2][B][CL_MAX];
+    __shared__ int s_ccount[2][B];
     __shared__ int s_pick, s_flag;
     __shared__ unsigned long long s_total;
 
     const int N = g.N;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int sb = tid >> 7, ltid = tid & (FT - 1), lwid = ltid >> 5;
+    if (tid < 2 * B) s_ccount[tid / B][tid % B] = 0;
     for (int lr = blockIdx.x; lr < n_local; lr += gridDim.x) {
         const int rid = resamp_ids[lr];
         const int32_t* S = samples + (int64_t)rid * n_s;
@@ -600,7 +607,7 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
         for (int v = tid; v < N; v += NT) { mc_s[v] = -2; f[v] = 0; }
         for (int k = tid; k < ncl_cap; k += NT) size[k] = 0;
         for (int k = tid; k < 2 * B * ncl_cap; k += NT) { wout[k] = 0; win[k] = 0; }
-        if (tid < 4 * B) { s_pbits[0][tid] = s_pbits[1][tid] = 0ull; s_pk[0][tid] = s_pk[1][tid] = 0x7fffffff; }
+        if (tid < B) { s_pbits[0][tid] = s_pbits[1][tid] = 0ull; s_pk[0][tid] = s_pk[1][tid] = 0x7fffffff; }
         __syncthreads();
         for (int q = tid; q < n_s; q += NT) mc_s[S[q]] = -1;
         __syncthreads();
@@ -710,6 +717,8 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
             BatchEdges<OUT_SLOTS, IN_SLOTS> cur;
             NodeOffs<IN_SLOTS> nxt;
             cur.v = -1; nxt.v = -1;
+            uint32_t* const wo_b0 = wout + (size_t)(2 * sb) * ncl_cap; uint32_t* const wo_b1 = wo_b0 + ncl_cap;
+            uint32_t* const wi_b0 = win + (size_t)(2 * sb) * ncl_cap;  uint32_t* const wi_b1 = wi_b0 + ncl_cap;
             while (t < n_s) {
                 const int my_t = t + sb;
                 if (cur_t != my_t) {              // start of sweep, or the previous batch ended on a move: reload
@@ -720,19 +729,24 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
                 }
                 const BatchEdges<OUT_SLOTS, IN_SLOTS> pre = load_batch_edges<FT, OUT_SLOTS, IN_SLOTS, TRUNC>(g, nxt, ltid, ipos, ocut);   // node my_t + B, in flight
                 const NodeOffs<IN_SLOTS> nxt2 = load_batch_offs<IN_SLOTS, VT, TRUNC>(g, vlist, nxt_t + B, n_s, ocut);
-                uint32_t* wo_b = wout + (size_t)(2 * sb + (parity & 1)) * ncl_cap;
-                uint32_t* wi_b = win + (size_t)(2 * sb + (parity & 1)) * ncl_cap;
+                uint32_t* wo_b = (parity & 1) ? wo_b1 : wo_b0;
+                uint32_t* wi_b = (parity & 1) ? wi_b1 : wi_b0;
                 const int v = cur.v;               // -1 beyond the end of the sweep
                 const int nb = min(B, n_s - t);
                 // current cluster of the batch's nodes, read before anything in this batch can move
                 int rcur = -3;
-                if (lane < 4 * B && (lane >> 2) < nb) rcur = (int)mc_s[vlist[t + (lane >> 2)]];
+                if (lane < nb) rcur = (int)mc_s[vlist[t + lane]];
                 // [A] association of this sub-block's node towards its neighbouring clusters
                 int ko[OUT_SLOTS], ki[IN_SLOTS];
 #pragma unroll
                 for (int s = 0; s < OUT_SLOTS; ++s) {
                     ko[s] = -1;
-                    if (cur.uo[s] >= 0) { ko[s] = (int)mc_s[cur.uo[s]]; if (ko[s] >= 0) atomicAdd(&wo_b[ko[s]], cur.wo[s]); }
+                    if (cur.uo[s] >= 0) {
+                        ko[s] = (int)mc_s[cur.uo[s]];
+                        // weights are at least one unit: a zero accumulator means this edge is the cluster's first
+                        if (ko[s] >= 0 && atomicAdd(&wo_b[ko[s]], cur.wo[s]) == 0u)
+                            s_clist[parity & 1][sb][atomicAdd(&s_ccount[parity & 1][sb], 1)] = (int16_t)ko[s];
+                    }
                 }
 #pragma unroll
                 for (int s = 0; s < IN_SLOTS; ++s) {
@@ -740,21 +754,20 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
                     if (cur.ui[s] >= 0) { ki[s] = (int)mc_s[cur.ui[s]]; if (ki[s] >= 0) atomicAdd(&wi_b[ki[s]], cur.wi[s]); }
                 }
                 named_bar_sync(1 + sb, FT);
-                // [B] best cluster among those reached by an out edge: per-warp partial (score bits, cluster)
-                if (OUT_SLOTS > 1 || lwid < out_warps) {
+                // [B] best cluster among those reached by an out edge: the node's first warp scores the distinct clusters
+                if (lwid == 0) {
                     unsigned long long bits = 0ull; int bko = 0x7fffffff;
-#pragma unroll
-                    for (int s = 0; s < OUT_SLOTS; ++s) {
-                        if (ko[s] >= 0) {
-                            const uint32_t wo = wo_b[ko[s]], wi = wi_b[ko[s]];
-                            if (wo != 0 && wi != 0) {
-                                const int curk = (int)mc_s[v];
-                                const double sz = (double)size[ko[s]];
-                                double sc = (double)((unsigned long long)wo * (unsigned long long)wi) / (sz * sz);
-                                if (ko[s] == curk) sc = sc * factor;
-                                const unsigned long long b2 = (unsigned long long)__double_as_longlong(sc);
-                                if (b2 > bits || (b2 == bits && ko[s] < bko)) { bits = b2; bko = ko[s]; }
-                            }
+                    const int ncand = s_ccount[parity & 1][sb];
+                    const int curk = v >= 0 ? (int)mc_s[v] : -1;
+                    for (int c = lane; c < ncand; c += 32) {
+                        const int k = (int)s_clist[parity & 1][sb][c];
+                        const uint32_t wo = wo_b[k], wi = wi_b[k];
+                        if (wi != 0) {
+                            const double sz = (double)size[k];
+                            double sc = (double)((unsigned long long)wo * (unsigned long long)wi) / (sz * sz);
+                            if (k == curk) sc = sc * factor;
+                            const unsigned long long b2 = (unsigned long long)__double_as_longlong(sc);
+                            if (b2 > bits || (b2 == bits && k < bko)) { bits = b2; bko = k; }
                         }
                     }
                     const uint32_t hi = (uint32_t)(bits >> 32), lo = (uint32_t)bits;
@@ -762,7 +775,10 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
                     const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
                     const bool top = bits != 0ull && hi == mh && lo == ml;
                     const uint32_t mk = __reduce_min_sync(0xffffffffu, top ? (uint32_t)bko : 0x7fffffffu);
-                    if (lane == 0) { s_pbits[parity & 1][sb * 4 + lwid] = ((unsigned long long)mh << 32) | ml; s_pk[parity & 1][sb * 4 + lwid] = (int)mk; }
+                    if (lane == 0) {
+                        s_pbits[parity & 1][sb] = ((unsigned long long)mh << 32) | ml; s_pk[parity & 1][sb] = (int)mk;
+                        s_ccount[parity & 1][sb] = 0;              // next used two batches from now
+                    }
                 }
                 __syncthreads();
                 // [C] clear this batch's accumulators (next used two batches from now)
@@ -770,29 +786,19 @@ graph_cover_batch_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict
                 for (int s = 0; s < OUT_SLOTS; ++s) if (ko[s] >= 0) wo_b[ko[s]] = 0;
 #pragma unroll
                 for (int s = 0; s < IN_SLOTS; ++s) if (ki[s] >= 0) wi_b[ki[s]] = 0;
-                // [D] resolve: every warp finds the first node of the batch that moves
+                // [D] resolve: every warp finds the first node of the batch that moves (lane j <-> node j)
                 unsigned long long rb = 0ull; int rk_ = 0x7fffffff;
-                if (lane < 4 * B) {
-                    const int j = lane >> 2, w = lane & 3;
-                    if (w < out_warps && j < nb) { rb = s_pbits[parity & 1][lane]; rk_ = s_pk[parity & 1][lane]; }
-                }
-#pragma unroll
-                for (int o = 1; o <= 2; o <<= 1) {
-                    const unsigned long long ob = __shfl_xor_sync(0xffffffffu, rb, o);
-                    const int ok = __shfl_xor_sync(0xffffffffu, rk_, o);
-                    if (ob > rb || (ob == rb && ok < rk_)) { rb = ob; rk_ = ok; }
-                }
-                const bool mv = (lane < 4 * B) && ((lane >> 2) < nb) && rb != 0ull && rk_ != rcur;
+                if (lane < nb) { rb = s_pbits[parity & 1][lane]; rk_ = s_pk[parity & 1][lane]; }
+                const bool mv = lane < nb && rb != 0ull && rk_ != rcur;
                 const unsigned mvmask = __ballot_sync(0xffffffffu, mv);
                 parity ^= 1u;
                 cur = pre; cur_t = nxt_t; nxt = nxt2; nxt_t += B;
                 if (mvmask == 0u) {
                     t += nb;
                 } else {
-                    const int jl = __ffs(mvmask) - 1;          // first lane of the first moving node
-                    const int bk = __shfl_sync(0xffffffffu, rk_, jl);
-                    const int curk = __shfl_sync(0xffffffffu, rcur, jl);
-                    const int js = jl >> 2;
+                    const int js = __ffs(mvmask) - 1;          // the first moving node
+                    const int bk = __shfl_sync(0xffffffffu, rk_, js);
+                    const int curk = __shfl_sync(0xffffffffu, rcur, js);
                     if (tid == 0) {
                         if (curk >= 0) size[curk]--;
                         size[bk]++;
