@@ -220,6 +220,16 @@ int  mcb_coclust_run2(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* s
                       const double* w, int32_t n_resamp, int32_t n_s, const int32_t* samples,
                       const uint64_t* seeds, int32_t min_mc_size, double cooling, int32_t burn_in,
                       int32_t max_sweeps, int32_t knn, int32_t rank, int32_t nranks, mcb_coclust** out);
+/* method = "edges" ([RECALL] tgstat's tgs_graph_cover_resample offers method = "hash" | "full" | "edges"; metacell calls
+ * "full", R/coclust_graph_cov.r:41): the same covers, but co-occurrence is counted only for pairs that are edges of the
+ * graph -- O(edges) memory instead of the N x N matrix, which cannot exist at 10^6 cells (4 TB).  Read the result with
+ * mcb_coclust_edge_counts: one row per edge, ordered by (source, weight descending, target ascending); cnt may be 0.   */
+int  mcb_coclust_run_edges(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst,
+                           const double* w, int32_t n_resamp, int32_t n_s, const int32_t* samples,
+                           const uint64_t* seeds, int32_t min_mc_size, double cooling, int32_t burn_in,
+                           int32_t max_sweeps, int32_t knn, int32_t rank, int32_t nranks, mcb_coclust** out);
+int  mcb_coclust_edge_counts(mcb_coclust* c, int32_t* host_node1 /* [n_edges] */, int32_t* host_node2, int32_t* host_cnt,
+                             int32_t* host_samples /* [N] */);
 void mcb_coclust_destroy(mcb_coclust* c);
 /* tgs_graph_cover(edges, min_mc_size, cooling, burn_in) (R/mc_graphcov.r:27, R/mc_from_coclust.r:247): one cover over
  * all N nodes.  host_cluster[v] = 0 for outliers (R/mc_graphcov.r:28), otherwise a cluster id >= 1.            */

@@ -26,7 +26,7 @@ SYMBOLS = [
     "mcb_csc_upload_range", "mcb_cgraph_edges_device", "mcb_multi_create", "mcb_multi_destroy", "mcb_multi_size", "mcb_multi_ctx",
     "mcb_multi_set_option", "mcb_cgraph_bknn_multi", "mcb_coclust_multi", "mcb_comm_unique_id", "mcb_comm_create",
     "mcb_comm_destroy", "mcb_comm_rank", "mcb_cgraph_build_sharded", "mcb_cgraph_gather_edges", "mcb_coclust_reduce",
-    "mcb_coclust_run2",
+    "mcb_coclust_run2", "mcb_coclust_run_edges", "mcb_coclust_edge_counts",
 ]
 
 
@@ -482,7 +482,7 @@ class CoClust:
     """mcb_coclust: one resampled co-clustering run (this rank's share of the resamples)."""
 
     def __init__(self, ctx, N, src, dst, w, samples, seeds, min_mc_size, cooling, burn_in, max_sweeps=1000,
-                 rank=0, nranks=1, knn=0):
+                 rank=0, nranks=1, knn=0, method="full"):
         src = as_c(src, np.int32)
         dst = as_c(dst, np.int32)
         w = as_c(w, np.float64)
@@ -491,7 +491,9 @@ class CoClust:
         n_resamp, n_s = samples.shape
         self.ctx, self.N, self.n_resamp = ctx, N, n_resamp
         self.h = C.c_void_p()
-        check(lib().mcb_coclust_run2(ctx.h, C.c_int32(N), C.c_int64(src.size), ptr(src, C.c_int32), ptr(dst, C.c_int32),
+        self.method, self.n_edges = method, int(src.size)
+        run = {"full": lib().mcb_coclust_run2, "edges": lib().mcb_coclust_run_edges}[method]
+        check(run(ctx.h, C.c_int32(N), C.c_int64(src.size), ptr(src, C.c_int32), ptr(dst, C.c_int32),
                                      ptr(w, C.c_double), C.c_int32(n_resamp), C.c_int32(n_s), ptr(samples, C.c_int32),
                                      ptr(seeds, C.c_uint64), C.c_int32(min_mc_size), C.c_double(cooling),
                                      C.c_int32(burn_in), C.c_int32(max_sweeps), C.c_int32(knn), C.c_int32(rank), C.c_int32(nranks),
@@ -520,6 +522,14 @@ class CoClust:
         nl = C.c_int32(0)
         check(lib().mcb_coclust_assignments(self.h, ptr(mc, C.c_int32), ptr(sw, C.c_int32), C.byref(nl)))
         return mc[:nl.value], sw[:nl.value]
+
+    def edge_counts(self):
+        """method = "edges": (node1, node2, cnt) for every edge of the graph (cnt may be 0) + samples[N]"""
+        n1, n2, cnt = (np.zeros(max(self.n_edges, 1), np.int32) for _ in range(3))
+        samples = np.zeros(self.N, np.int32)
+        check(lib().mcb_coclust_edge_counts(self.h, ptr(n1, C.c_int32), ptr(n2, C.c_int32), ptr(cnt, C.c_int32), ptr(samples, C.c_int32)))
+        n = self.n_edges
+        return n1[:n], n2[:n], cnt[:n], samples
 
     def pairs(self):
         npairs = C.c_int64(0)

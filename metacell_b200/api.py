@@ -595,16 +595,21 @@ def tgs_graph_cover_resample(edges, knn, min_cluster_size, cooling, burn_in, p_r
     """tgstat call of reference R/coclust_graph_cov.r:41.  edges: dict col1, col2, weight (0-based codes).
     `knn` (R passes K = round(nrow(edges) / ncells), the average out-degree, R/coclust_graph_cov.r:39) caps the out edges a
     node may use inside one resample: its knn heaviest edges among those whose target was sampled too; 0 = no cap.  Returns dict(co_cluster = dict(node1, node2, cnt), samples = int[N])."""
-    if method != "full":
-        raise McbError("MC-ERR: only method = \"full\" is supported (what metacell calls)")
+    if method not in ("full", "edges"):
+        raise McbError("MC-ERR: method must be \"full\" (what metacell calls) or \"edges\" (co-occurrence of graph edges only)")
     ctx = _ctx(ctx)
     src, dst, w = edges["col1"], edges["col2"], edges["weight"]
     N = int(n_nodes if n_nodes is not None else max(int(np.max(src)), int(np.max(dst))) + 1)
     sets, seeds = resample_index_sets(N, p_resamp, n_resamp, get_param("mc_rseed") if seed is None else seed)
     cc = _lib.CoClust(ctx, N, src, dst, w, sets, seeds, int(min_cluster_size), float(cooling), int(burn_in), max_sweeps,
-                      knn=int(knn or 0))
+                      knn=int(knn or 0), method=method)
     try:
-        n1, n2, cnt, samples = cc.pairs()
+        if method == "full":
+            n1, n2, cnt, samples = cc.pairs()
+        else:                                   # O(edges) memory: the variant for cell counts whose N x N matrix cannot exist
+            n1, n2, cnt, samples = cc.edge_counts()
+            keep = cnt > 0
+            n1, n2, cnt = n1[keep], n2[keep], cnt[keep]
     finally:
         cc.destroy()
     return {"co_cluster": {"node1": n1.copy(), "node2": n2.copy(), "cnt": cnt.copy()}, "samples": samples}

@@ -1606,8 +1606,9 @@ static void cover_csr_build(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int3
 static mcb_coclust* coclust_run_impl(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst, const double* w,
                                      int32_t n_resamp, int32_t n_s, const int32_t* samples, const uint64_t* seeds, int32_t min_mc_size,
                                      double cooling, int32_t burn_in, int32_t max_sweeps, int32_t knn, int32_t rank, int32_t nranks,
-                                     bool with_counts)
+                                     int count_mode /* 0 none (single cover), 1 method "full", 2 method "edges" */)
 {
+    const bool with_counts = count_mode == 1;
     MCB_CHECK(N >= 1 && n_edges >= 0 && n_resamp >= 0 && n_s >= 1 && n_s <= N, "MC-ERR: bad co-clustering dimensions");
     MCB_CHECK(n_edges == 0 || (src && dst && w), "mcb_coclust_run: null edge arrays");
     MCB_CHECK(n_resamp == 0 || seeds, "mcb_coclust_run: null seed array");
@@ -1624,7 +1625,7 @@ static mcb_coclust* coclust_run_impl(mcb_ctx* ctx, int32_t N, int64_t n_edges, c
     const int32_t nl = c->n_local;
 
     CoverCsr csr;
-    cover_csr_build(ctx, N, n_edges, src, dst, w, /*sort_out=*/knn > 0, csr);
+    cover_csr_build(ctx, N, n_edges, src, dst, w, /*sort_out=*/knn > 0 || count_mode == 2, csr);
     DevBuf<int32_t> d_samples(ctx, (size_t)std::max<int64_t>((int64_t)n_resamp * n_s, 1)), d_ids(ctx, (size_t)std::max(nl, 1));
     DevBuf<uint64_t> d_seeds(ctx, (size_t)std::max(n_resamp, 1));
     if (n_resamp) {
@@ -1640,7 +1641,7 @@ static mcb_coclust* coclust_run_impl(mcb_ctx* ctx, int32_t N, int64_t n_edges, c
     MCB_CHECK(!(hs[1] & 1), "MC-ERR: edge endpoint out of range");
     MCB_CHECK(!(hs[1] & 2), "MC-ERR: sampled node out of range");
     MCB_CHECK(!(hs[1] & 4), "MC-ERR: each resample index set must be strictly ascending");
-    MCB_CHECK(!(hs[1] & 8), "MC-ERR: tgs_graph_cover_resample: per-node edge truncation (knn) supports out-degrees up to 1024");
+    MCB_CHECK(!(hs[1] & 8), "MC-ERR: tgs_graph_cover_resample: knn and method = \"edges\" order every node's out edges, which supports out-degrees up to 1024");
     const int32_t max_out = hs[2], max_in = hs[3];
     // `knn` = the most out edges a node may use inside one resample (R/coclust_graph_cov.r:39-41 passes the graph's AVERAGE
     // out-degree, so well-connected nodes lose their weakest sampled edges).  It can only bind below the largest out-degree.
@@ -1665,6 +1666,19 @@ static mcb_coclust* coclust_run_impl(mcb_ctx* ctx, int32_t N, int64_t n_edges, c
         StageTimer t(ctx, "cooccur");
         launch_cooccur(ctx, N, nl, c->mc.p, c->ncl_cap, c->cnt.p, c->nsamp.p, ws_order.p, ws_start.p);
     }
+    if (count_mode == 2) {
+        // one counter per edge (out-CSR order) + the edge behind it; O(edges) memory
+        MCB_CHECK(!(hs[1] & 8), "MC-ERR: method = \"edges\" supports out-degrees up to 1024");
+        c->mode = 1; c->n_edges = n_edges;
+        const size_t ne1 = (size_t)std::max<int64_t>(n_edges, 1);
+        c->cnt.alloc(ctx, ne1); c->cnt.zero();
+        c->nsamp.alloc(ctx, (size_t)N); c->nsamp.zero();
+        c->e_src.alloc(ctx, ne1); c->e_dst.alloc(ctx, ne1);
+        StageTimer t(ctx, "cooccur", 2);
+        launch_expand_src(ctx, N, csr.optr32.p, c->e_src.p);
+        if (n_edges) MCB_CUDA(cudaMemcpyAsync(c->e_dst.p, csr.odst.p, (size_t)n_edges * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        launch_cooccur_edges(ctx, N, nl, c->mc.p, csr.optr32.p, csr.odst.p, c->cnt.p, c->nsamp.p);
+    }
     std::vector<int32_t> hst((size_t)std::max(nl, 1), 0);
     if (nl) MCB_CUDA(cudaMemcpyAsync(hst.data(), status.p, (size_t)nl * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1681,7 +1695,38 @@ extern "C" int mcb_coclust_run2(mcb_ctx* ctx, int32_t N, int64_t n_edges, const 
     MCB_CHECK(ctx && out, "mcb_coclust_run: null argument");
     MCB_CHECK(n_resamp == 0 || samples, "mcb_coclust_run: null sample arrays");
     *out = coclust_run_impl(ctx, N, n_edges, src, dst, w, n_resamp, n_s, samples, seeds, min_mc_size, cooling, burn_in, max_sweeps,
-                            knn, rank, nranks, true);
+                            knn, rank, nranks, 1);
+    MCB_API_END
+}
+// method = "edges" of tgs_graph_cover_resample: the same covers, co-occurrence counted for graph edges only
+extern "C" int mcb_coclust_run_edges(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst,
+                                     const double* w, int32_t n_resamp, int32_t n_s, const int32_t* samples,
+                                     const uint64_t* seeds, int32_t min_mc_size, double cooling, int32_t burn_in,
+                                     int32_t max_sweeps, int32_t knn, int32_t rank, int32_t nranks, mcb_coclust** out)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(ctx && out, "mcb_coclust_run_edges: null argument");
+    MCB_CHECK(n_resamp == 0 || samples, "mcb_coclust_run_edges: null sample arrays");
+    *out = coclust_run_impl(ctx, N, n_edges, src, dst, w, n_resamp, n_s, samples, seeds, min_mc_size, cooling, burn_in, max_sweeps,
+                            knn, rank, nranks, 2);
+    MCB_API_END
+}
+// one row per edge of the graph, ordered by (source, weight descending, target): (node1, node2, cnt) + samples[N]
+extern "C" int mcb_coclust_edge_counts(mcb_coclust* c, int32_t* host_node1, int32_t* host_node2, int32_t* host_cnt,
+                                       int32_t* host_samples)
+{
+    MCB_API_BEGIN
+    MCB_CHECK(c && c->mode == 1, "mcb_coclust_edge_counts: not a method = \"edges\" run");
+    mcb_ctx* ctx = c->ctx;
+    MCB_CUDA(cudaSetDevice(ctx->device));
+    const size_t ne = (size_t)c->n_edges;
+    if (ne) {
+        if (host_node1) MCB_CUDA(cudaMemcpyAsync(host_node1, c->e_src.p, ne * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (host_node2) MCB_CUDA(cudaMemcpyAsync(host_node2, c->e_dst.p, ne * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (host_cnt) MCB_CUDA(cudaMemcpyAsync(host_cnt, c->cnt.p, ne * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (host_samples) MCB_CUDA(cudaMemcpyAsync(host_samples, c->nsamp.p, (size_t)c->N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MCB_CUDA(cudaStreamSynchronize(ctx->stream));
     MCB_API_END
 }
 extern "C" int mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst,
@@ -1702,7 +1747,7 @@ extern "C" int mcb_coclust_reduce(mcb_comm* comm, mcb_coclust* c, int32_t root)
     MCB_CUDA(cudaSetDevice(ctx->device));
     {
         StageTimer t(ctx, "reduce_counts", 0);
-        comm_reduce_sum_u32(comm, c->cnt.p, (size_t)c->N * c->N, root);
+        comm_reduce_sum_u32(comm, c->cnt.p, c->mode == 1 ? (size_t)c->n_edges : (size_t)c->N * c->N, root);
         comm_reduce_sum_u32(comm, c->nsamp.p, (size_t)c->N, root);
     }
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1721,7 +1766,7 @@ extern "C" int mcb_graph_cover(mcb_ctx* ctx, int32_t N, int64_t n_edges, const i
     try {
         MCB_CHECK(ctx && host_cluster && N >= 1, "mcb_graph_cover: bad argument");
         c = coclust_run_impl(ctx, N, n_edges, src, dst, w, 1, N, /*samples = all nodes*/ nullptr, &seed, min_mc_size, cooling, burn_in,
-                             max_sweeps, 0, 0, 1, false);
+                             max_sweeps, 0, 0, 1, 0);
     }
     catch (const mcb::Error& e) { mcb::set_error(e.what()); rc = e.code; }
     catch (const std::bad_alloc&) { mcb::set_error("host out of memory"); rc = 3; }
@@ -1766,6 +1811,7 @@ extern "C" int mcb_coclust_extract(mcb_coclust* c, int64_t* n_pairs)
 {
     MCB_API_BEGIN
     MCB_CHECK(c && n_pairs && c->cnt.p, "null argument");
+    MCB_CHECK(c->mode == 0, "mcb_coclust_extract: a method = \"edges\" run is read with mcb_coclust_edge_counts");
     mcb_ctx* ctx = c->ctx;
     MCB_CUDA(cudaSetDevice(ctx->device));
     const int32_t N = c->N;

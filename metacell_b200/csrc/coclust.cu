@@ -56,13 +56,16 @@ graph_cover_kernel(CoverGraph g, int32_t n_local, const int32_t* __restrict__ re
                    const int32_t* __restrict__ samples, const uint64_t* __restrict__ seeds, int32_t min_size,
                    double cooling, int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap, int32_t* __restrict__ mc_all,
                    int32_t* __restrict__ f_all, int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status,
-                   int32_t knn, const uint16_t* __restrict__ ipos, uint16_t* __restrict__ ocut_all)
+                   int32_t knn, const uint16_t* __restrict__ ipos, uint16_t* __restrict__ ocut_all, uint32_t* __restrict__ acc_ws)
 {
+    // acc_ws != null: the cluster accumulators (size, wout, win: 3 * ncl_cap words per CTA) live in global memory because
+    // they exceed shared memory (10^6-node graphs with small clusters)
     // knn > 0 (`knn` of tgs_graph_cover_resample): a node uses only its first knn out edges, in (weight descending,
     // target ascending) order, among those whose target is sampled.  Out segments are stored in that order, so the
     // usable part of node v's segment is its first ocut[v] positions; the in edge u -> v is usable iff its position in
     // u's out segment, ipos[e], is below ocut[u].
-    extern __shared__ uint32_t dsm[];
+    extern __shared__ uint32_t dsm_[];
+    uint32_t* dsm = acc_ws ? acc_ws + (size_t)blockIdx.x * 3 * ncl_cap : dsm_;
     int32_t* size = (int32_t*)dsm;                  // [ncl_cap]
     uint32_t* wout = dsm + ncl_cap;                 // [ncl_cap]
     uint32_t* win = dsm + 2 * ncl_cap;              // [ncl_cap]
@@ -1260,6 +1263,54 @@ cooccur_kernel(int32_t N, int32_t n_local, const int32_t* __restrict__ mc_all, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// method = "edges": co-occurrence counted only for the pairs that are edges of the graph, one counter per edge in the
+// order of the out-CSR (which is ordered by (source, weight descending, target ascending) for this mode).  Memory is
+// O(edges) instead of O(N^2): this is the variant that reaches cell counts where the N x N matrix of method = "full"
+// cannot exist (10^6 cells: 4 TB).  One warp per (resample, node): edges into the node's own cluster are counted.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+cooccur_edges_kernel(int32_t N, int32_t n_local, const int32_t* __restrict__ mc_all, const int32_t* __restrict__ optr,
+                     const int32_t* __restrict__ odst, uint32_t* __restrict__ cnt_e, int32_t* __restrict__ nsamp)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t items = (int64_t)n_local * N;
+    for (int64_t it = warp0; it < items; it += nwarps) {        // resample-major: one resample's assignment stays in L2
+        const int64_t lr = it / N;
+        const int32_t v = (int32_t)(it - lr * N);
+        const int32_t* mc = mc_all + lr * N;
+        const int32_t k = mc[v];
+        if (k == -2) continue;
+        if (lane == 0) atomicAdd(&nsamp[v], 1);
+        if (k < 0) continue;
+        for (int32_t e = optr[v] + lane; e < optr[v + 1]; e += 32)
+            if (mc[odst[e]] == k) atomicAdd(&cnt_e[e], 1u);
+    }
+}
+__global__ void expand_src_kernel(int32_t N, const int32_t* __restrict__ optr, int32_t* __restrict__ esrc)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t v = warp0; v < N; v += nwarps)
+        for (int32_t e = optr[v] + lane; e < optr[v + 1]; e += 32) esrc[e] = (int32_t)v;
+}
+void launch_cooccur_edges(mcb_ctx* ctx, int32_t N, int32_t n_local, const int32_t* mc, const int32_t* optr32, const int32_t* odst,
+                          uint32_t* cnt_e, int32_t* nsamp)
+{
+    if (n_local == 0 || N == 0) return;
+    const int grid = (int)std::min<int64_t>(ceil_div((int64_t)n_local * N, 8), (int64_t)ctx->num_sms * 8);
+    cooccur_edges_kernel<<<grid, 256, 0, ctx->stream>>>(N, n_local, mc, optr32, odst, cnt_e, nsamp);
+    MCB_LAUNCH_CHECK();
+}
+void launch_expand_src(mcb_ctx* ctx, int32_t N, const int32_t* optr32, int32_t* esrc)
+{
+    if (N == 0) return;
+    const int grid = (int)std::min<int64_t>(ceil_div(N, 8), (int64_t)ctx->num_sms * 8);
+    expand_src_kernel<<<grid, 256, 0, ctx->stream>>>(N, optr32, esrc);
+    MCB_LAUNCH_CHECK();
+}
+
 // row_counts[a] = #{b > a : cnt[a][b] > 0}
 __global__ void count_pairs_kernel(int32_t N, const uint32_t* __restrict__ cnt, int64_t* __restrict__ row_counts)
 {
@@ -1420,13 +1471,19 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
 #undef FAST
         }
     }
-    const size_t smem = (size_t)ncl_cap * 3 * sizeof(uint32_t);
-    MCB_CHECK(smem <= 200 * 1024, "MC-ERR: graph cover: too many potential clusters for shared memory");
+    size_t smem = (size_t)ncl_cap * 3 * sizeof(uint32_t);
+    DevBuf<uint32_t> acc_ws;                   // accumulators of every CTA in global memory when they exceed shared memory
+    int grid = n_local;
+    if (smem > 200 * 1024) {
+        grid = std::min(n_local, ctx->num_sms * 4);
+        acc_ws.alloc(ctx, (size_t)grid * 3 * ncl_cap);
+        smem = 0;
+    }
     static SmemOptIn optin;
     ensure_dyn_smem(optin, ctx, graph_cover_kernel, smem);
-    graph_cover_kernel<<<n_local, CC_THREADS, smem, ctx->stream>>>(g, n_local, resamp_ids, n_s, samples, seeds, min_size,
-                                                                    cooling, burn_in, max_sweeps, ncl_cap, mc, f_ws,
-                                                                    sweeps, status, knn, ipos, ocut_ws);
+    graph_cover_kernel<<<grid, CC_THREADS, smem, ctx->stream>>>(g, n_local, resamp_ids, n_s, samples, seeds, min_size,
+                                                                 cooling, burn_in, max_sweeps, ncl_cap, mc, f_ws,
+                                                                 sweeps, status, knn, ipos, ocut_ws, acc_ws.p);
     MCB_LAUNCH_CHECK();
 }
 

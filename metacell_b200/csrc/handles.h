@@ -51,6 +51,9 @@ struct mcb_coclust {
     mcb::CtxRef ref;
     mcb_ctx* ctx = nullptr;
     int32_t N = 0, n_local = 0, ncl_cap = 0;
+    int mode = 0;                       // 0 = method "full" (cnt is N x N), 1 = method "edges" (cnt is one counter per edge, out-CSR order)
+    int64_t n_edges = 0;
+    mcb::DevBuf<int32_t> e_src, e_dst;  // method "edges": the edge behind every counter
     mcb::DevBuf<uint32_t> cnt; mcb::DevBuf<int32_t> nsamp;
     mcb::DevBuf<int32_t> mc, sweeps;
     int64_t n_pairs = -1;

@@ -275,6 +275,9 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
                         const uint16_t* ipos = nullptr, uint16_t* ocut_ws /* [n_local][N] when knn > 0 */ = nullptr);
 void launch_cooccur(mcb_ctx* ctx, int32_t N, int32_t n_local, const int32_t* mc, int32_t ncl_cap, uint32_t* cnt,
                     int32_t* nsamp, int32_t* ws_order /* [n_local][N] */, int32_t* ws_start /* [n_local][ncl_cap+1] */);
+void launch_cooccur_edges(mcb_ctx* ctx, int32_t N, int32_t n_local, const int32_t* mc, const int32_t* optr32, const int32_t* odst,
+                          uint32_t* cnt_e, int32_t* nsamp);
+void launch_expand_src(mcb_ctx* ctx, int32_t N, const int32_t* optr32, int32_t* esrc);
 void launch_count_pairs(mcb_ctx* ctx, int32_t N, const uint32_t* cnt, int64_t* row_counts);
 void launch_extract_pairs(mcb_ctx* ctx, int32_t N, const uint32_t* cnt, const int64_t* row_offs, int32_t* n1,
                           int32_t* n2, int32_t* c);

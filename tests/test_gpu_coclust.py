@@ -92,6 +92,63 @@ def test_knn_at_or_above_max_out_degree_is_no_limit(ctx, oracle):
     a.destroy(); b.destroy()
 
 
+@pytest.mark.parametrize("knn", [0, 9])
+def test_method_edges_counts_equal_the_full_matrix_on_graph_edges(ctx, oracle, knn):
+    """method = "edges": one counter per graph edge; equals the N x N matrix of method = "full" read at the edges, and the
+    oracle's covers"""
+    from metacell_b200 import _lib, synth
+    ncells, K, min_size, n_resamp = 900, 15, 8, 6
+    src, dst, w = _graph(oracle, ncells, K)
+    sets, seeds = synth.resample_sets(ncells, 0.75, n_resamp, 11)
+    ce = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, min_size, 1.05, 10, knn=knn, method="edges")
+    e1, e2, ec, ens = ce.edge_counts()
+    cf = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, min_size, 1.05, 10, knn=knn)
+    n1, n2, cnt, ns = cf.pairs()
+    dense = np.zeros((ncells, ncells), np.int64)
+    dense[n1, n2] = cnt
+    dense = dense + dense.T
+    assert e1.size == src.size and set(zip(e1.tolist(), e2.tolist())) == set(zip(src.tolist(), dst.tolist()))
+    assert np.array_equal(ec, dense[e1, e2]) and np.array_equal(ens, ns)
+    wmap = {(a, b): x for a, b, x in zip(src.tolist(), dst.tolist(), w.tolist())}
+    wfix = np.maximum(1, np.rint(np.array([wmap[(a, b)] for a, b in zip(e1.tolist(), e2.tolist())]) * 65536.0)).astype(np.int64)
+    assert np.array_equal(np.lexsort((e2, -wfix, e1)), np.arange(e1.size))      # rows ordered by (source, weight descending, target)
+    # against the oracle's own covers (no knn: the whole graph)
+    if knn == 0:
+        csr = oracle.graph_to_csr(ncells, src, dst, w)
+        want = np.zeros(e1.size, np.int64)
+        for r in range(n_resamp):
+            omc, _ = oracle.graph_cover(ncells, csr, sets[r], min_size, 1.05, 10, int(seeds[r]))
+            want += (omc[e1] >= 0) & (omc[e1] == omc[e2])
+        assert np.array_equal(ec, want)
+    ce.destroy(); cf.destroy()
+
+
+def test_method_edges_needs_no_n_squared_memory(ctx):
+    """300,000 nodes: method = "full" is refused (N x N counters), method = "edges" runs"""
+    from metacell_b200 import _lib
+    N = 300000
+    rng = np.random.default_rng(2)
+    base = np.arange(N, dtype=np.int32)
+    src = np.concatenate([base, base, base])
+    dst = np.concatenate([(base + 1) % N, (base + 2) % N, (base // 64 * 64 + rng.integers(0, 64, N)).astype(np.int32) % N]).astype(np.int32)
+    keep = src != dst
+    key = src[keep].astype(np.int64) * N + dst[keep]
+    _, first = np.unique(key, return_index=True)
+    src, dst = src[keep][first], dst[keep][first]
+    w = rng.random(src.size) * 0.9 + 0.1
+    sets = np.sort(np.stack([rng.choice(N, int(0.75 * N), replace=False) for _ in range(2)]), axis=1).astype(np.int32)
+    seeds = np.array([5, 6], np.uint64)
+    with pytest.raises(_lib.McbError, match="N x N"):
+        _lib.CoClust(ctx, N, src, dst, w, sets, seeds, 3, 1.05, 10)
+    cc = _lib.CoClust(ctx, N, src, dst, w, sets, seeds, 3, 1.05, 10, method="edges")
+    e1, e2, ec, ns = cc.edge_counts()
+    mc, _ = cc.assignments()
+    want = sum(((mc[r][e1] >= 0) & (mc[r][e1] == mc[r][e2])).astype(np.int64) for r in range(2))
+    assert np.array_equal(ec, want) and ec.max() <= 2 and ec.sum() > 0
+    assert ns.sum() == 2 * sets.shape[1]
+    cc.destroy()
+
+
 def test_rank_sharding_sums_to_whole(ctx, oracle):
     """resamples strided over 3 emulated ranks: counters add up to the single-rank result"""
     from metacell_b200 import _lib, synth
