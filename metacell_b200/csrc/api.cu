@@ -889,7 +889,7 @@ static void knn_begin(mcb_cgraph* g, int32_t K, int32_t k_expand, int32_t rank, 
         }
         StageTimer t(ctx, "cor_sample_hist");
         launch_sample_thresholds_fused(ctx, 0, g->Zh.p + (size_t)row0 * Gpad, rows, Zs.p, Spad, Gpad * (int32_t)sizeof(__half), (int32_t)S,
-                                       n_tiles1, r_sel, c_hi, c_lo, eps, thr, nullptr);
+                                       n_tiles1, r_sel, c_hi, c_lo, eps, thr, nullptr, g->G * (int32_t)sizeof(__half));
         return;
     }
     DevBuf<__half> Zs(ctx, ctx->gemm_impl != 1 ? (size_t)Spad * Gpad : 0);
@@ -956,8 +956,8 @@ static void knn_filter(mcb_cgraph* g, int exchange)
         CandPool pool{g->pool_records.p, g->pool_ctl.p, g->pool_fill.p, n_chunks, g->pool_ctl.p + 1};
         {
             StageTimer t(ctx, "cor_filter_gemm");
-            if (exchange) launch_tc_filter(ctx, g->Zh.p, g->Zl.p, g->Mpad, 0, M, M, Gpad, g->thr_all.p, pool, g->rank, nranks);
-            else if (rows) launch_tc_filter(ctx, g->Zh.p, g->Zl.p, g->Mpad, row0, rows, M, Gpad, g->thr_all.p + row0, pool);
+            if (exchange) launch_tc_filter(ctx, g->Zh.p, g->Zl.p, g->Mpad, 0, M, M, Gpad, g->thr_all.p, pool, g->rank, nranks, g->G);
+            else if (rows) launch_tc_filter(ctx, g->Zh.p, g->Zl.p, g->Mpad, row0, rows, M, Gpad, g->thr_all.p + row0, pool, 0, 1, g->G);
         }
         if (!exchange) {
             uint32_t hctl[2] = {0, 0};

@@ -77,6 +77,7 @@ struct TcParams {
     int64_t a_rows;      // valid local rows
     int64_t b_rows;      // valid columns
     int32_t num_kb;      // Gpad / BK
+    int32_t last_ksteps; // UMMA k-steps (16 columns each) that hold data in the last k-block: G = 1000 needs 3 of its 4 (columns past G are zero)
     int32_t m_tiles, n_tiles, total_tiles;
     // rank partition of the tile list (symmetric multi-GPU): this launch takes the runs of part_block consecutive
     // tiles whose run index is congruent to `part` modulo `nparts`; local_tiles = how many that is
@@ -515,8 +516,10 @@ tc_cor_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constan
                     const uint64_t b_hi = make_sw128_kmajor_desc(st + Cfg::A_PLANES * Cfg::A_BYTES);
                     const uint64_t a_lo = make_sw128_kmajor_desc(st + Cfg::A_BYTES);
                     const uint64_t b_lo = make_sw128_kmajor_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+                    const int nk = kb == prm.num_kb - 1 ? prm.last_ksteps : BK / UMMA_K;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
+                        if (k >= nk) break;
                         const uint64_t koff = (uint64_t)((k * UMMA_K * ELT) >> 4);   // 32 bytes per k step
                         const uint32_t accum = (kb | k) != 0 ? 1u : 0u;    // first k-step overwrites
                         mma_f16_ss(d_main, a_hi + koff, b_hi + koff, idesc, accum);
@@ -680,8 +683,10 @@ tc_cor2_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant
                     const uint64_t a_lo = make_sw128_kmajor_desc(st + Cfg::A_BYTES);
                     const uint64_t b_hi = make_sw128_kmajor_desc(st + 2 * Cfg::A_BYTES);
                     const uint64_t b_lo = make_sw128_kmajor_desc(st + 2 * Cfg::A_BYTES + Cfg::B_BYTES);
+                    const int nk = kb == prm.num_kb - 1 ? prm.last_ksteps : BK / UMMA_K;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
+                        if (k >= nk) break;
                         const uint64_t koff = (uint64_t)((k * UMMA_K * ELT) >> 4);
                         const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
                         mma_f16_ss_2sm(d_main, a_hi + koff, b_hi + koff, idesc, accum);
@@ -763,6 +768,14 @@ static CUtensorMap make_map(const void* base, int64_t rows, int32_t Gpad, int bo
     return m;
 }
 
+// columns [G, Gpad) of the planes are zero: the k-steps of the last k-block that lie wholly past G contribute nothing and
+// are not issued (G = 1000: 63 k-steps of 16 columns instead of 64)
+static int32_t tc_last_ksteps(int32_t Gpad, int32_t G)
+{
+    if (G <= 0 || G > Gpad || G <= Gpad - BK) return BK / UMMA_K;
+    return std::max(1, (G - (Gpad - BK) + UMMA_K - 1) / UMMA_K);
+}
+
 template <int NPASS, int MODE, int CM>
 static void launch_tc(mcb_ctx* ctx, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh,
                       const CUtensorMap& bl, const TcParams& prm)
@@ -802,7 +815,7 @@ void launch_tc_store16(mcb_ctx* ctx, const void* Ahi, int64_t a_rows_alloc, cons
     const CUtensorMap ah = make_map(Ahi, a_rows_alloc, Gpad, BM);
     const CUtensorMap bh = make_map(Bhi, b_rows_alloc, Gpad, BN);
     TcParams prm{};
-    prm.a_row0 = 0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK;
+    prm.a_row0 = 0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK; prm.last_ksteps = BK / UMMA_K;
     prm.m_tiles = (int32_t)ceil_div(a_rows, BM); prm.n_tiles = (int32_t)ceil_div(b_rows, BN);
     prm.C16 = reinterpret_cast<__half*>(C16); prm.ldc16 = ldc16;
     launch_tc<1, 0, 1>(ctx, ah, ah, bh, bh, prm);
@@ -817,7 +830,7 @@ void launch_tc_store(mcb_ctx* ctx, const void* Ahi, int64_t a_rows_alloc, const 
     const CUtensorMap ah = make_map(Ahi, a_rows_alloc, Gpad, BM);
     const CUtensorMap bh = make_map(Bhi, b_rows_alloc, Gpad, BN);
     TcParams prm{};
-    prm.a_row0 = 0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK;
+    prm.a_row0 = 0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK; prm.last_ksteps = BK / UMMA_K;
     prm.m_tiles = (int32_t)ceil_div(a_rows, BM); prm.n_tiles = (int32_t)ceil_div(b_rows, BN);
     prm.C = C; prm.ldc = ldc;
     launch_tc<1, 0, 1>(ctx, ah, ah, bh, bh, prm);
@@ -844,7 +857,7 @@ uint32_t tc_pool_min_chunks(mcb_ctx* ctx) { return (uint32_t)(EPI_WARPS * ctx->n
 
 void launch_tc_filter(mcb_ctx* ctx, const void* Zhi, const void* Zlo, int64_t rows_alloc, int64_t a_row0,
                       int64_t a_rows, int64_t b_rows, int32_t Gpad, const float* thr, const CandPool& pool, int32_t part,
-                      int32_t nparts)
+                      int32_t nparts, int32_t G)
 {
     if (a_rows == 0 || b_rows == 0) return;
     tc_init();
@@ -855,7 +868,7 @@ void launch_tc_filter(mcb_ctx* ctx, const void* Zhi, const void* Zlo, int64_t ro
     const CUtensorMap bh = make_map(Zhi, rows_alloc, Gpad, BN / FILTER_CM);
     const CUtensorMap bl = make_map(Zlo, rows_alloc, Gpad, BN / FILTER_CM);
     TcParams prm{};
-    prm.a_row0 = a_row0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK;
+    prm.a_row0 = a_row0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK; prm.last_ksteps = tc_last_ksteps(Gpad, G);
     prm.m_tiles = (int32_t)ceil_div(a_rows, BM); prm.n_tiles = (int32_t)ceil_div(b_rows, BN);
     prm.thr = thr;
     prm.pool = reinterpret_cast<uint4*>(pool.records); prm.pool_cursor = pool.cursor; prm.chunk_fill = pool.chunk_fill;
@@ -883,7 +896,7 @@ void launch_tc_store3_ab(mcb_ctx* ctx, const void* Ahi, const void* Alo, int64_t
     const CUtensorMap bh = make_map(Bhi, b_rows_alloc, Gpad, BN);
     const CUtensorMap bl = make_map(Blo, b_rows_alloc, Gpad, BN);
     TcParams prm{};
-    prm.a_row0 = 0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK;
+    prm.a_row0 = 0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK; prm.last_ksteps = BK / UMMA_K;
     prm.m_tiles = (int32_t)ceil_div(a_rows, BM); prm.n_tiles = (int32_t)ceil_div(b_rows, BN);
     prm.C = C; prm.ldc = ldc;
     launch_tc<3, 0, 1>(ctx, ah, al, bh, bl, prm);
@@ -901,7 +914,7 @@ void launch_tc_store3(mcb_ctx* ctx, const void* Zhi, const void* Zlo, int64_t ro
     const CUtensorMap bh = make_map(Zhi, rows_alloc, Gpad, BN);
     const CUtensorMap bl = make_map(Zlo, rows_alloc, Gpad, BN);
     TcParams prm{};
-    prm.a_row0 = 0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK;
+    prm.a_row0 = 0; prm.a_rows = a_rows; prm.b_rows = b_rows; prm.num_kb = Gpad / BK; prm.last_ksteps = BK / UMMA_K;
     prm.m_tiles = (int32_t)ceil_div(a_rows, BM); prm.n_tiles = (int32_t)ceil_div(b_rows, BN);
     prm.C = C; prm.ldc = ldc;
     launch_tc<3, 0, 1>(ctx, ah, al, bh, bl, prm);

@@ -55,7 +55,7 @@ constexpr float ACC16_TO_COR = C_RESCALE;            // fp16 planes hold z * 2^1
 
 struct SampParams {
     int64_t a_rows;
-    int32_t num_kb, n_units, n_tiles, n_tiles1, S, r_sel, c_hi, c_lo;
+    int32_t num_kb, last_ksteps, n_units, n_tiles, n_tiles1, S, r_sel, c_hi, c_lo;
     float eps;
     float* thr;
     uint32_t* n_escaped;        // rows whose quantile left the bracket (statistics)
@@ -169,8 +169,10 @@ tc_sample_hist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                             const uint32_t st = smem_u32(smem + stage * S_STAGE_BYTES);
                             const uint64_t a = make_sw128_kmajor_desc(st);
                             const uint64_t b = make_sw128_kmajor_desc(st + S_A_BYTES);
+                            const int nk = kb == prm.num_kb - 1 ? prm.last_ksteps : SBK / S_UMMA_KB;      // trailing k-steps of zero columns are skipped
 #pragma unroll
                             for (int k = 0; k < SBK / S_UMMA_KB; ++k) {
+                                if (k >= nk) break;
                                 const uint64_t koff = (uint64_t)((k * S_UMMA_KB) >> 4);      // 32 bytes per k step
                                 mma_ss_2sm<F8>(d, a + koff, b + koff, idesc, (kb | k) != 0 ? 1u : 0u);
                             }
@@ -358,7 +360,7 @@ static CUtensorMap make_map_u8(const void* base, int64_t rows, int32_t G8pad)
 // n_tiles1 * 256 sampled columns are the coarse phase; r_sel is the rank to locate among the remaining S - n_tiles1 * 256.
 void launch_sample_thresholds_fused(mcb_ctx* ctx, int f8, const void* A, int64_t a_rows, const void* B, int64_t Spad, int32_t row_bytes,
                                     int32_t S, int32_t n_tiles1, int32_t r_sel, int32_t c_hi, int32_t c_lo, float eps, float* thr,
-                                    uint32_t* n_escaped)
+                                    uint32_t* n_escaped, int32_t valid_bytes)
 {
     if (a_rows == 0) return;
     MCB_CHECK(row_bytes % SBK == 0 && Spad % SBN == 0 && S <= Spad, "sample thresholds: bad padding");
@@ -367,6 +369,8 @@ void launch_sample_thresholds_fused(mcb_ctx* ctx, int f8, const void* A, int64_t
     const CUtensorMap mb = make_map_u8(B, Spad, row_bytes);
     SampParams prm{};
     prm.a_rows = a_rows; prm.num_kb = row_bytes / SBK; prm.n_units = (int32_t)ceil_div(a_rows, 2 * SBM);
+    prm.last_ksteps = SBK / S_UMMA_KB;
+    if (valid_bytes > row_bytes - SBK && valid_bytes <= row_bytes) prm.last_ksteps = std::max(1, (valid_bytes - (row_bytes - SBK) + S_UMMA_KB - 1) / S_UMMA_KB);
     prm.n_tiles = (int32_t)(Spad / SBN); prm.n_tiles1 = n_tiles1; prm.S = S; prm.r_sel = r_sel; prm.c_hi = c_hi; prm.c_lo = c_lo;
     prm.eps = eps; prm.thr = thr; prm.n_escaped = n_escaped;
     const int pairs = std::max(1, std::min(prm.n_units, ctx->num_sms / 2));

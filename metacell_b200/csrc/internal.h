@@ -174,12 +174,12 @@ void launch_tc_store3_ab(mcb_ctx* ctx, const void* Ahi, const void* Alo, int64_t
                          int64_t b_rows_alloc, int64_t a_rows, int64_t b_rows, int32_t Gpad, float* C, int64_t ldc);
 void launch_tc_filter(mcb_ctx* ctx, const void* Zh, const void* Zl, int64_t rows_alloc, int64_t a_row0,
                       int64_t a_rows, int64_t b_rows, int32_t Gpad, const float* thr, const CandPool& pool, int32_t part = 0,
-                      int32_t nparts = 1);
+                      int32_t nparts = 1, int32_t G = 0 /* valid columns (0 = Gpad): trailing all-zero k-steps are skipped */);
 // corsample.cu: fused sampling pass (e4m3 operands, per-row histograms in the epilogue)
 void launch_z8_rows(mcb_ctx* ctx, const void* Zh, int32_t Gpad, const int32_t* rows, int64_t row0, int64_t nrows, int32_t G8pad, void* out);
 void launch_sample_thresholds_fused(mcb_ctx* ctx, int f8, const void* A, int64_t a_rows, const void* B, int64_t Spad, int32_t row_bytes,
                                     int32_t S, int32_t n_tiles1, int32_t r_sel, int32_t c_hi, int32_t c_lo, float eps, float* thr,
-                                    uint32_t* n_escaped);
+                                    uint32_t* n_escaped, int32_t valid_bytes = 0 /* row bytes that hold data (0 = all) */);
 // select.cu: symmetric multi-GPU record exchange helpers
 void launch_count_records_by_dest(mcb_ctx* ctx, const CandPool& pool, int64_t rows_per_rank, int32_t nranks, uint64_t* counts);
 void launch_partition_records(mcb_ctx* ctx, const CandPool& pool, int64_t rows_per_rank, int32_t nranks, const uint64_t* counts,

@@ -82,13 +82,14 @@ mcell_add_cgraph_from_mat_bknn = function(mat_id, gset_id, graph_id, K, dsamp = 
 # the wrapper around it (:13-58) is unchanged.  Seeds and index sets are drawn here, on the host.
 tgs_graph_cover_resample = function(edges, knn, min_mc_size, cooling, burn_in, p_resamp, n_resamp, method = "full")
 {
-	if(method != "full") stop("MC-ERR: only method = \"full\" is supported")
+	if(!(method %in% c("full", "edges"))) stop("MC-ERR: method must be \"full\" or \"edges\"")
 	nodes = levels(edges$col1)
 	N = length(nodes)
 	n_s = round(p_resamp * N)
 	samples = sapply(1:n_resamp, function(i) sort(sample.int(N, n_s)))            # n_s x n_resamp, ascending
 	seeds = floor(runif(n_resamp) * 2^52)
-	r = .Call("mcbr_coclust", N, as.integer(edges$col1), as.integer(edges$col2), as.numeric(edges$weight), as.integer(knn),
+	# "edges": co-occurrence of graph edges only, O(edges) memory -- for cell counts whose N x N matrix cannot exist
+	r = .Call(if(method == "full") "mcbr_coclust" else "mcbr_coclust_edges", N, as.integer(edges$col1), as.integer(edges$col2), as.numeric(edges$weight), as.integer(knn),
 	          samples, seeds, as.integer(min_mc_size), as.numeric(cooling), as.integer(burn_in), PACKAGE = "mcb200")
 	list(co_cluster = data.frame(node1 = factor(nodes[r$node1], levels = nodes),
 	                             node2 = factor(nodes[r$node2], levels = nodes), cnt = r$cnt),

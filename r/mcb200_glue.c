@@ -247,6 +247,43 @@ SEXP mcbr_coclust(SEXP n_nodes, SEXP col1, SEXP col2, SEXP weight, SEXP knn, SEX
     return res;
 }
 
+/* method = "edges" of tgs_graph_cover_resample: co-occurrence of graph edges only, O(edges) memory (for cell counts whose
+ * N x N matrix cannot exist); rows with cnt == 0 are dropped here.  Single device. */
+SEXP mcbr_coclust_edges(SEXP n_nodes, SEXP col1, SEXP col2, SEXP weight, SEXP knn, SEXP samples, SEXP seeds, SEXP min_mc_size,
+                        SEXP cooling, SEXP burn_in)
+{
+    const int32_t N = asInteger(n_nodes);
+    const int64_t ne = XLENGTH(col1);
+    SEXP sdim = getAttrib(samples, R_DimSymbol);
+    const int32_t n_s = INTEGER(sdim)[0], n_resamp = INTEGER(sdim)[1];
+    int32_t* src = (int32_t*)R_alloc((size_t)(ne ? ne : 1), sizeof(int32_t));
+    int32_t* dst = (int32_t*)R_alloc((size_t)(ne ? ne : 1), sizeof(int32_t));
+    for (int64_t e = 0; e < ne; ++e) { src[e] = INTEGER(col1)[e] - 1; dst[e] = INTEGER(col2)[e] - 1; }
+    int32_t* smp = (int32_t*)R_alloc((size_t)n_s * n_resamp, sizeof(int32_t));
+    for (int64_t q = 0; q < (int64_t)n_s * n_resamp; ++q) smp[q] = INTEGER(samples)[q] - 1;
+    uint64_t* sd = (uint64_t*)R_alloc((size_t)n_resamp, sizeof(uint64_t));
+    for (int32_t r = 0; r < n_resamp; ++r) sd[r] = (uint64_t)REAL(seeds)[r];
+    mcb_coclust* c = NULL;
+    CHECK(mcb_coclust_run_edges(ctx(), N, ne, src, dst, REAL(weight), n_resamp, n_s, smp, sd, asInteger(min_mc_size), asReal(cooling),
+                                asInteger(burn_in), 1000, asInteger(knn), 0, 1, &c));
+    int32_t* e1 = (int32_t*)R_alloc((size_t)(ne ? ne : 1), sizeof(int32_t));
+    int32_t* e2 = (int32_t*)R_alloc((size_t)(ne ? ne : 1), sizeof(int32_t));
+    int32_t* ec = (int32_t*)R_alloc((size_t)(ne ? ne : 1), sizeof(int32_t));
+    SEXP ns = PROTECT(allocVector(INTSXP, N));
+    const int rc = mcb_coclust_edge_counts(c, e1, e2, ec, INTEGER(ns));
+    mcb_coclust_destroy(c);
+    if (rc) { UNPROTECT(1); Rf_error("%s", mcb_last_error()); }
+    int64_t np = 0;
+    for (int64_t e = 0; e < ne; ++e) np += ec[e] > 0;
+    SEXP n1 = PROTECT(allocVector(INTSXP, np)), n2 = PROTECT(allocVector(INTSXP, np)), cnt = PROTECT(allocVector(INTSXP, np));
+    for (int64_t e = 0, q = 0; e < ne; ++e)
+        if (ec[e] > 0) { INTEGER(n1)[q] = e1[e] + 1; INTEGER(n2)[q] = e2[e] + 1; INTEGER(cnt)[q] = ec[e]; ++q; }
+    SEXP res = PROTECT(mkNamed(VECSXP, (const char*[]){"node1", "node2", "cnt", "samples", ""}));
+    SET_VECTOR_ELT(res, 0, n1); SET_VECTOR_ELT(res, 1, n2); SET_VECTOR_ELT(res, 2, cnt); SET_VECTOR_ELT(res, 3, ns);
+    UNPROTECT(5);
+    return res;
+}
+
 /* tgs_graph_cover(edges, min_mc_size, cooling, burn_in) (reference R/mc_graphcov.r:27, R/mc_from_coclust.r:247):
  * one cover over all nodes; returns integer cluster per node, 0 = outlier (R/mc_graphcov.r:28) */
 SEXP mcbr_graph_cover(SEXP n_nodes, SEXP col1, SEXP col2, SEXP weight, SEXP min_mc_size, SEXP cooling, SEXP burn_in, SEXP seed)

@@ -167,5 +167,9 @@ def test_coclust_knn_argument(ctx, oracle):
     for knn in (max_out, max_out + 7):                      # no node can exceed it: identical to "no limit"
         got = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, 8, 1.05, 10, knn=knn).pairs()
         assert all(np.array_equal(a, b) for a, b in zip(got, ref))
-    with pytest.raises(_lib.McbError, match="knn"):          # would need truncation: refused, never silently ignored
-        _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, 8, 1.05, 10, knn=3)
+    # below the largest out-degree the limit binds: edges are truncated (parity with the oracle's truncated graphs is in
+    # test_gpu_coclust.py::test_knn_edge_truncation_bit_exact), never silently ignored
+    cut = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, 8, 1.05, 10, knn=3).pairs()
+    assert not all(np.array_equal(a, b) for a, b in zip(cut, ref))
+    with pytest.raises(_lib.McbError, match="knn"):
+        _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, 8, 1.05, 10, knn=-1)
