@@ -1586,9 +1586,9 @@ static void cover_csr_build(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int3
     {
         StageTimer t(ctx, "h2d_graph");
         if (n_edges) {
-            MCB_CUDA(cudaMemcpyAsync(c.src.p, src, (size_t)n_edges * 4, cudaMemcpyHostToDevice, ctx->stream));
-            MCB_CUDA(cudaMemcpyAsync(c.dst.p, dst, (size_t)n_edges * 4, cudaMemcpyHostToDevice, ctx->stream));
-            MCB_CUDA(cudaMemcpyAsync(c.w.p, w, (size_t)n_edges * 8, cudaMemcpyHostToDevice, ctx->stream));
+            staged_copy_h2d(ctx, c.src.p, src, (size_t)n_edges * 4);
+            staged_copy_h2d(ctx, c.dst.p, dst, (size_t)n_edges * 4);
+            staged_copy_h2d(ctx, c.w.p, w, (size_t)n_edges * 8);
         }
     }
     {
@@ -1629,7 +1629,7 @@ static mcb_coclust* coclust_run_impl(mcb_ctx* ctx, int32_t N, int64_t n_edges, c
     DevBuf<int32_t> d_samples(ctx, (size_t)std::max<int64_t>((int64_t)n_resamp * n_s, 1)), d_ids(ctx, (size_t)std::max(nl, 1));
     DevBuf<uint64_t> d_seeds(ctx, (size_t)std::max(n_resamp, 1));
     if (n_resamp) {
-        if (samples) MCB_CUDA(cudaMemcpyAsync(d_samples.p, samples, (size_t)n_resamp * n_s * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (samples) staged_copy_h2d(ctx, d_samples.p, samples, (size_t)n_resamp * n_s * 4);
         else { MCB_CHECK(n_s == N && n_resamp == 1, "mcb_coclust_run: null sample array"); launch_iota_i32(ctx, d_samples.p, N); }   // all nodes
         MCB_CUDA(cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n_resamp * 8, cudaMemcpyHostToDevice, ctx->stream));
         launch_sample_check(ctx, (int64_t)n_resamp * n_s, n_s, d_samples.p, N, csr.scratch.p + 1);
@@ -1721,9 +1721,9 @@ extern "C" int mcb_coclust_edge_counts(mcb_coclust* c, int32_t* host_node1, int3
     MCB_CUDA(cudaSetDevice(ctx->device));
     const size_t ne = (size_t)c->n_edges;
     if (ne) {
-        if (host_node1) MCB_CUDA(cudaMemcpyAsync(host_node1, c->e_src.p, ne * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (host_node2) MCB_CUDA(cudaMemcpyAsync(host_node2, c->e_dst.p, ne * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (host_cnt) MCB_CUDA(cudaMemcpyAsync(host_cnt, c->cnt.p, ne * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (host_node1) staged_copy_d2h(ctx, host_node1, c->e_src.p, ne * 4);
+        if (host_node2) staged_copy_d2h(ctx, host_node2, c->e_dst.p, ne * 4);
+        if (host_cnt) staged_copy_d2h(ctx, host_cnt, c->cnt.p, ne * 4);
     }
     if (host_samples) MCB_CUDA(cudaMemcpyAsync(host_samples, c->nsamp.p, (size_t)c->N * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1840,10 +1840,11 @@ extern "C" int mcb_coclust_pairs(mcb_coclust* c, int32_t* h1, int32_t* h2, int32
     mcb_ctx* ctx = c->ctx;
     MCB_CUDA(cudaSetDevice(ctx->device));
     const size_t np = (size_t)c->n_pairs;
-    if (np) {
-        if (h1) MCB_CUDA(cudaMemcpyAsync(h1, c->p1.p, np * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (h2) MCB_CUDA(cudaMemcpyAsync(h2, c->p2.p, np * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (hc) MCB_CUDA(cudaMemcpyAsync(hc, c->pc.p, np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (np) {           // tens of MB at C3: through the pinned ring with the host threads
+        StageTimer t(ctx, "d2h_pairs", 0);
+        if (h1) staged_copy_d2h(ctx, h1, c->p1.p, np * 4);
+        if (h2) staged_copy_d2h(ctx, h2, c->p2.p, np * 4);
+        if (hc) staged_copy_d2h(ctx, hc, c->pc.p, np * 4);
     }
     if (host_samples) MCB_CUDA(cudaMemcpyAsync(host_samples, c->nsamp.p, (size_t)c->N * 4, cudaMemcpyDeviceToHost, ctx->stream));
     MCB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -125,6 +125,8 @@ void staged_upload_csc(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, const int64
                        int64_t* d_p, int32_t* d_i, uint32_t* d_x);
 void staged_download_edges(mcb_ctx* ctx, int64_t rows, int32_t K, int64_t ne, const int32_t* d_out_deg, const int32_t* d_src_cell,
                            const int32_t* d_e_dst, int32_t* host_src, int32_t* host_dst, double* host_w);
+void staged_copy_h2d(mcb_ctx* ctx, void* dev, const void* host, size_t bytes);      // pageable host bytes -> device, via the pinned ring
+void staged_copy_d2h(mcb_ctx* ctx, void* host, const void* dev, size_t bytes);      // device -> host bytes via the ring; synchronous
 void launch_csc_validate(mcb_ctx* ctx, int32_t ngenes, int64_t ncells, int64_t nnz, const int64_t* p, const int32_t* ridx, int32_t* flags);
 
 // ---- launchers (each enqueues on ctx->stream; no host sync unless stated) -------------------
