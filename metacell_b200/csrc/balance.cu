@@ -25,6 +25,9 @@
 namespace mcb {
 
 constexpr int BAL_THREADS = 256;
+#ifndef MCB_BAL_MIN_BLOCKS
+#define MCB_BAL_MIN_BLOCKS 8          // 32 registers: the cuts are latency bound (barriers, dependent loads), occupancy pays
+#endif
 
 // persistent row-striding kernels launch whole waves only: with a grid of num_sms * 8 and 3 resident CTAs per SM the
 // last 0.67 wave ran at a third of the machine
@@ -372,7 +375,7 @@ probe_blocked_kernel(const uint32_t* __restrict__ blist, const uint16_t* __restr
 
 // mutual scores s(i, r) and the in-degree threshold of every owned row
 template <int IPT>      // 256 * IPT >= Kc keys sorted per row, register resident
-__global__ void __launch_bounds__(BAL_THREADS, IPT <= 4 ? 4 : 1)
+__global__ void __launch_bounds__(BAL_THREADS, IPT <= 4 ? MCB_BAL_MIN_BLOCKS : 1)
 mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ table, int64_t row0, int64_t rows,
               int32_t Kc, int32_t H, int32_t log2H, int32_t rank_bits, long long smax, int strict, int keep_self,
               int32_t kin, uint32_t* __restrict__ sym, uint64_t* __restrict__ thr_in, int have_scores,
@@ -467,7 +470,7 @@ mutual_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ 
 
 // out-degree prune: survivors of the target's in-degree cut, best K by (s, target)
 template <int IPT>
-__global__ void __launch_bounds__(BAL_THREADS, IPT <= 4 ? 4 : 1)
+__global__ void __launch_bounds__(BAL_THREADS, IPT <= 4 ? MCB_BAL_MIN_BLOCKS : 1)
 prune_kernel(const int32_t* __restrict__ knn_col, const uint32_t* __restrict__ sym, const uint64_t* __restrict__ thr_in,
              int64_t row0, int64_t rows, int32_t Kc, int32_t K, long long smax, int32_t* __restrict__ out_deg,
              int32_t* __restrict__ out_dst, int32_t* __restrict__ out_s, const uint64_t* __restrict__ mut,

@@ -390,8 +390,11 @@ void launch_sample_threshold16(mcb_ctx* ctx, const void* C16, int64_t ldc, int64
 // ---------------------------------------------------------------------------------------------
 constexpr int TOPK_BINS = 2048;
 
+#ifndef MCB_TOPK_MIN_BLOCKS
+#define MCB_TOPK_MIN_BLOCKS 6        // 40 registers: six resident CTAs per SM hide the barriers of the per-row select (1.35 -> 1.25 ms at C2)
+#endif
 template <int IPT_IN, int IPT_OUT>
-__global__ void __launch_bounds__(SEL_THREADS)
+__global__ void __launch_bounds__(SEL_THREADS, IPT_IN <= 8 ? MCB_TOPK_MIN_BLOCKS : 1)
 topk_select_rows_kernel(const uint64_t* __restrict__ cand, const uint32_t* __restrict__ cnt, int32_t cap, int64_t row0,
                         int64_t rows, int32_t kc_out, int32_t Kc, int32_t* __restrict__ knn_col, float* __restrict__ knn_cor,
                         int32_t* __restrict__ fail_flag)
