@@ -58,7 +58,7 @@ void* mcb_ctx_stream(mcb_ctx* ctx);                   /* cudaStream_t all kernel
  *          "trim"      release the context's cache of device blocks back to the driver;
  *          "cap_override" n > 0: test hook, caps the per-row candidate capacity so rows take the
  *                      exact-row path;
- *          "host_threads" staging threads of this context (0 = min(16, cores / 2))              */
+ *          "host_threads" staging threads of this context (0 = min(16, cores); cores shared between the processes of a node)              */
 int   mcb_ctx_set_option(mcb_ctx* ctx, const char* key, int64_t value);
 /* stage timings of the calls since the last mcb_ctx_timings_reset (needs option profile=1).
  * Writes up to cap entries; *n receives the number available.  names[i] are static strings.  */
