@@ -10,15 +10,19 @@
 //
 // Data layout: the reverse rank rank(j,i) is found through a per-row open-addressing hash table
 // (H = 2^k >= 2*Kc slots of u32 = (column << rank_bits) | rank0) instead of a binary search or a
-// global sort.  The join is ROUTED (route_* / probe_kernel below): every list entry (i -> j, rank r) becomes an
-// 8-byte record that is bucketed by the block of ~2K rows that holds j; the probe pass then walks the records
-// block by block, so the 16 MB slice of tables it probes -- and the slice of the score array it writes -- stay in
-// L2 and every table atom is read from HBM once (the direct join read one 64-byte DRAM atom per probe: 11.5 GB for
-// 10^8 probes at C2, profiles/r2a_ncu_stages.csv).  The score is symmetric, s(i,j) = s(j,i), so the probe of row j's
-// table by the record of (i -> j) is recorded in ROW j's score array at position rank(j,i): results land at the
-// owner of the probed table and nothing travels back.  Across ranks the same bucketing is the exchange: a rank
-// only ever needs the tables of its own rows, and the records (not the whole kNN lists) cross NVLink once.
-// Selection kernels are one CTA per row with the row's keys in registers; HBM-bound integer work.
+// global sort.  Probing the tables directly costs one 64-byte DRAM atom per probe (11.5 GB for 10^8 probes at C2,
+// profiles/r2a_ncu_stages.csv), so the join is organised by the BLOCK of rows that holds the probed tables:
+//   one rank  -- BLOCKED LISTS (prepare_blocked / probe_blocked): the kernel that builds a row's table also writes the
+//                row's list grouped by target block; the probe pass walks (block, row) segments block-major, so the 32 MB
+//                slice of tables it probes stays in L2, and appends the qualifying pairs to compact per-row lists of
+//                mutual keys that the two cuts then read (no record stream, no count / scatter passes);
+//   N ranks   -- ROUTED RECORDS (route_* / probe_kernel): every list entry (i -> j, rank r) becomes an 8-byte record
+//                bucketed by (owner rank, block) of j; the buckets of other ranks travel in one all-to-all and the probe
+//                pass walks the received records block by block.  The score is symmetric, s(i,j) = s(j,i), so the probe
+//                of row j's table by the record of (i -> j) is recorded in ROW j's score array at position rank(j,i):
+//                results land at the owner of the probed table and nothing travels back; the lists never leave their owner.
+//   direct    -- every entry probes wherever its target's table lies (join_impl = 1; validation, single rank).
+// All three give bit-identical graphs.  Selection kernels are one CTA per row with the row's keys in registers.
 #include "internal.h"
 #include <cstdlib>
 
