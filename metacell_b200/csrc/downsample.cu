@@ -10,7 +10,8 @@
 // to the CPU oracle (oracle/mc_oracle.c orc_downsample).
 //
 // HBM-bound integer work: one CTA per cell, the counts are read twice (sum, final count) and
-// written once; the keys are regenerated in registers per radix pass instead of being stored.
+// written once.  The keys never touch HBM: a cell's Philox words are drawn once and kept in shared memory for
+// the later radix passes and the final pass (cells above DS_KEYCAP UMIs redraw them per pass).
 #include "internal.h"
 
 namespace mcb {
@@ -77,7 +78,9 @@ __device__ __forceinline__ void ds_pass(int pass, int& shift, int& width)
     else if (pass <= 6) { shift = 53 - 8 * pass; width = 8; }
     else { shift = 0; width = 5; }
 }
-constexpr int DS_BITMAP_WORDS = 8192;      // kept-UMI bitmap in shared memory: cells up to 262,144 UMIs take the fast final pass
+constexpr int DS_BITMAP_WORDS = 4096;      // kept-UMI bitmap in shared memory: cells up to 131,072 UMIs take the fast final pass
+constexpr int DS_KEYCAP = 5120;            // Philox words of a cell kept in shared memory after the first pass (typical cells:
+                                           // a few thousand UMIs), so the later radix passes and the final pass do not redraw them
 
 __global__ void __launch_bounds__(DS_THREADS, 4)
 downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t* __restrict__ x, double n,
@@ -86,6 +89,7 @@ downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t*
 {
     __shared__ uint32_t hist[DS_BINS];
     __shared__ uint32_t bitmap[DS_BITMAP_WORDS];
+    __shared__ __align__(16) uint32_t okey[DS_KEYCAP];
     __shared__ long long warp_tot[DS_THREADS / 32 + 1];
     __shared__ unsigned long long s_prefix, s_thr;
     __shared__ long long s_krem;
@@ -94,11 +98,15 @@ downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t*
     const long long d = (long long)floor(n);
     for (int64_t c = blockIdx.x; c < ncells; c += gridDim.x) {
         const int64_t e0 = p[c], e1 = p[c + 1];
-        // 1. column sum
+        // 1. column sum.  Every thread owns a CONTIGUOUS slice of the cell's entries, so this one block scan also gives
+        //    the thread the UMI offset at which its slice starts (used by the final count): one scan per cell, not
+        //    one per 256 entries
+        const int64_t per = (e1 - e0 + DS_THREADS - 1) / DS_THREADS;
+        const int64_t ea0 = min(e1, e0 + (int64_t)threadIdx.x * per), ea1 = min(e1, ea0 + per);
         long long part = 0;
-        for (int64_t e = e0 + threadIdx.x; e < e1; e += DS_THREADS) part += x[e];
+        for (int64_t e = ea0; e < ea1; ++e) part += x[e];
         long long tot;
-        (void)block_excl_scan(part, warp_tot, &tot);
+        const long long my_start = block_excl_scan(part, warp_tot, &tot);
         if ((double)tot < n) {             // dropped cell (R/utils.r:34)
             for (int64_t e = e0 + threadIdx.x; e < e1; e += DS_THREADS) out_x[e] = add_non_dsamp ? x[e] : 0u;
             if (threadIdx.x == 0) kept[c] = 0;
@@ -115,6 +123,7 @@ downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t*
         // the key of a UMI names its cell by the index in the WHOLE matrix, so a cell shard draws the same subset
         const uint32_t c_lo = (uint32_t)(c + cell_base), c_hi = (uint32_t)((uint64_t)(c + cell_base) >> 32);
         const long long ngroups = (tot + 3) >> 2;
+        const bool cached = ngroups * 4 <= DS_KEYCAP;          // block-uniform
         for (int pass = 0; pass < 8; ++pass) {
             int shift, width;
             ds_pass(pass, shift, width);
@@ -125,13 +134,25 @@ downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t*
             __syncthreads();
             for (long long g = threadIdx.x; g < ngroups; g += DS_THREADS) {
                 uint32_t o[4];
-                philox4x32_10((uint32_t)g, c_lo, c_hi, TAG_DOWNSAMP, seed_lo, seed_hi, o);
+                if (cached && pass > 0) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(&okey[g << 2]);
+                    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+                } else {
+                    philox4x32_10((uint32_t)g, c_lo, c_hi, TAG_DOWNSAMP, seed_lo, seed_hi, o);
+                    if (cached) *reinterpret_cast<uint4*>(&okey[g << 2]) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                if (pass == 0) {                 // nothing decided yet: the digit is the top 11 bits of the Philox word
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const long long t = (g << 2) + q;
-                    if (t < tot) {
-                        const uint64_t key = ds_key(o[q], (uint32_t)t);
-                        if ((key & decided) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & bmask], 1u);
+                    for (int q = 0; q < 4; ++q)
+                        if ((g << 2) + q < tot) atomicAdd(&hist[o[q] >> 21], 1u);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const long long t = (g << 2) + q;
+                        if (t < tot) {
+                            const uint64_t key = ds_key(o[q], (uint32_t)t);
+                            if ((key & decided) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & bmask], 1u);
+                        }
                     }
                 }
             }
@@ -163,45 +184,44 @@ downsample_kernel(int64_t ncells, const int64_t* __restrict__ p, const uint32_t*
             // one more uniform pass over the UMIs: thread -> one bitmap word = 8 Philox blocks = 32 UMIs (no atomics),
             // then every entry counts the bits of its own UMI range.  (The per-entry loop below makes a warp wait for
             // its most expressed gene.)
-            const int nwords = (int)((tot + 31) >> 5);
+            const int tot32 = (int)tot;
+            const int nwords = (tot32 + 31) >> 5;
             for (int wq = threadIdx.x; wq < nwords; wq += DS_THREADS) {
                 uint32_t word = 0;
 #pragma unroll
                 for (int b8 = 0; b8 < 8; ++b8) {
-                    const long long g = ((long long)wq << 3) + b8;
-                    if ((g << 2) >= tot) break;
+                    const int g = (wq << 3) + b8;
+                    if ((g << 2) >= tot32) break;
                     uint32_t o[4];
-                    philox4x32_10((uint32_t)g, c_lo, c_hi, TAG_DOWNSAMP, seed_lo, seed_hi, o);
+                    if (cached) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(&okey[g << 2]);
+                        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+                    } else philox4x32_10((uint32_t)g, c_lo, c_hi, TAG_DOWNSAMP, seed_lo, seed_hi, o);
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const long long t = (g << 2) + q;
-                        if (t < tot && ds_key(o[q], (uint32_t)t) <= thr) word |= 1u << (b8 * 4 + q);
+                        const int t = (g << 2) + q;
+                        if (t < tot32 && ds_key(o[q], (uint32_t)t) <= thr) word |= 1u << (b8 * 4 + q);
                     }
                 }
                 bitmap[wq] = word;
             }
             __syncthreads();
-            long long run = 0;
-            for (int64_t base = e0; base < e1; base += DS_THREADS) {
-                const int64_t e = base + threadIdx.x;
-                const long long xe = e < e1 ? (long long)x[e] : 0;
-                long long chunk_tot;
-                const long long start = run + block_excl_scan(xe, warp_tot, &chunk_tot);
-                run += chunk_tot;
-                if (e < e1) {
-                    uint32_t cnt = 0;
-                    if (xe) {
-                        const long long last = start + xe - 1;
-                        const int w0 = (int)(start >> 5), w1 = (int)(last >> 5);
-                        const uint32_t m0 = ~0u << (start & 31), m1 = ~0u >> (31 - (last & 31));
-                        if (w0 == w1) cnt = __popc(bitmap[w0] & m0 & m1);
-                        else {
-                            cnt = __popc(bitmap[w0] & m0) + __popc(bitmap[w1] & m1);
-                            for (int wq = w0 + 1; wq < w1; ++wq) cnt += __popc(bitmap[wq]);
-                        }
+            int start = (int)my_start;                  // tot <= 131,072 here
+            for (int64_t e = ea0; e < ea1; ++e) {
+                const int xe = (int)x[e];
+                uint32_t cnt = 0;
+                if (xe) {
+                    const int last = start + xe - 1;
+                    const int w0 = start >> 5, w1 = last >> 5;
+                    const uint32_t m0 = ~0u << (start & 31), m1 = ~0u >> (31 - (last & 31));
+                    if (w0 == w1) cnt = __popc(bitmap[w0] & m0 & m1);
+                    else {
+                        cnt = __popc(bitmap[w0] & m0) + __popc(bitmap[w1] & m1);
+                        for (int wq = w0 + 1; wq < w1; ++wq) cnt += __popc(bitmap[wq]);
                     }
-                    out_x[e] = cnt;
                 }
+                out_x[e] = cnt;
+                start += xe;
             }
             __syncthreads();
             continue;
