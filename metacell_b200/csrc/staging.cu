@@ -93,7 +93,7 @@ private:
 // ---------------------------------------------------------------------------------------------------------------
 struct Staging {
     static constexpr size_t SLOT = (size_t)4 << 20;        // bytes per pinned slot
-    int nslots = 0, wave = 0;                                 // ring = 2 waves of `wave` slots
+    int nslots = 0, wave = 0, wave_max = 0;                   // two pinned slots per thread; `wave` threads stage uploads, `wave_max` downloads
     std::vector<char*> slot;
     std::vector<cudaEvent_t> ev;
     cudaStream_t copy = nullptr;
@@ -108,11 +108,14 @@ struct Staging {
     }
 };
 
-static int default_host_threads()
+// threads for a phase in which every process of the node stages at the same time (uploads): the cores are shared.
+// `exclusive`: a phase only one process runs (the root's downloads after a gather or a reduce): all cores.
+static int default_host_threads(bool exclusive = false)
 {
     if (const char* e = getenv("MCB_HOST_THREADS")) { const int v = atoi(e); if (v >= 1) return std::min(v, 64); }
     unsigned hw = std::thread::hardware_concurrency();
     if (!hw) hw = 4;
+    if (exclusive) return (int)std::max(2u, std::min(16u, hw));
     // one process per device on the same host (torchrun, mpirun): share the cores, twice oversubscribed -- the ranks do not
     // all stage at the same moment (rank 0 alone downloads the gathered edge table).  Measured on 16 cores and 8 ranks:
     // end to end 18.7 ms with 2 threads per rank, 16.1 with 4, 15.8 with 8
@@ -126,9 +129,11 @@ Staging* ctx_staging(mcb_ctx* ctx)
     if (ctx->staging) return ctx->staging;
     std::unique_ptr<Staging> s(new Staging());
     const int nt = ctx->host_threads > 0 ? ctx->host_threads : default_host_threads();
-    s->workers.reset(new HostWorkers(nt));
+    const int nmax = ctx->host_threads > 0 ? ctx->host_threads : std::max(nt, default_host_threads(true));
+    s->workers.reset(new HostWorkers(nmax));
     s->wave = nt;
-    s->nslots = 2 * nt;
+    s->wave_max = nmax;
+    s->nslots = 2 * nmax;
     s->slot.assign((size_t)s->nslots, nullptr);
     s->ev.assign((size_t)s->nslots, nullptr);
     for (int q = 0; q < s->nslots; ++q) {
@@ -204,7 +209,7 @@ void staged_copy_d2h(mcb_ctx* ctx, void* host, const void* dev, size_t bytes)
     MCB_CUDA(cudaStreamWaitEvent(st->copy, st->done, 0));          // the copy stream starts after the producer kernels
     const int64_t nchunks = (int64_t)ceil_div((int64_t)bytes, (int64_t)Staging::SLOT);
     std::atomic<int64_t> next{0};
-    const int nt = (int)std::min<int64_t>(st->wave, nchunks);
+    const int nt = (int)std::min<int64_t>(st->wave_max, nchunks);
     st->workers->parallel_for(nt, [&](int t) {
         MCB_CUDA(cudaSetDevice(ctx->device));
         int64_t pend[2] = {-1, -1};
@@ -375,7 +380,7 @@ void staged_download_edges(mcb_ctx* ctx, int64_t rows, int32_t K, int64_t ne, co
     MCB_CHECK(offs[rows] == ne, "edge table: degree sum does not match the edge count");
     const int64_t per = (int64_t)(Staging::SLOT / sizeof(int32_t));
     const int64_t nchunks = (host_dst && ne) ? ceil_div(ne, per) : 0;
-    const int nt = st->wave;
+    const int nt = st->wave_max;
     std::atomic<int64_t> next{0};
     st->workers->parallel_for(nt, [&](int t) {
         MCB_CUDA(cudaSetDevice(ctx->device));
