@@ -181,15 +181,25 @@ static void staged_h2d(mcb_ctx* ctx, int64_t nchunks, const std::function<void(i
     MCB_CUDA(cudaStreamWaitEvent(ctx->stream, st->done, 0));
 }
 
+// chunk of a plain copy: small enough that every staging thread gets a few (a 10 MB array cut into 4 MB slots kept
+// three threads busy), at most one slot
+static size_t copy_chunk(int nthreads, size_t bytes)
+{
+    size_t c = bytes / (size_t)(4 * std::max(nthreads, 1));
+    c = std::max<size_t>(c, (size_t)256 << 10);
+    c = std::min<size_t>(c, Staging::SLOT);
+    return (c + 4095) & ~(size_t)4095;
+}
 // plain bytes, host -> device, through the pinned ring (pageable sources: the edge table and the resample index sets
 // of the co-clustering call).  Small copies go straight through cudaMemcpyAsync.
 void staged_copy_h2d(mcb_ctx* ctx, void* dev, const void* host, size_t bytes)
 {
     if (!bytes) return;
     if (bytes < ((size_t)1 << 20)) { MCB_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream)); return; }
-    const int64_t nchunks = (int64_t)ceil_div((int64_t)bytes, (int64_t)Staging::SLOT);
+    const size_t CH = copy_chunk(ctx_staging(ctx)->wave, bytes);
+    const int64_t nchunks = (int64_t)ceil_div((int64_t)bytes, (int64_t)CH);
     staged_h2d(ctx, nchunks, [&](int64_t c, char* slot, cudaStream_t copy) {
-        const size_t a = (size_t)c * Staging::SLOT, n = std::min(Staging::SLOT, bytes - a);
+        const size_t a = (size_t)c * CH, n = std::min(CH, bytes - a);
         memcpy(slot, (const char*)host + a, n);
         MCB_CUDA(cudaMemcpyAsync((char*)dev + a, slot, n, cudaMemcpyHostToDevice, copy));
     });
@@ -207,7 +217,8 @@ void staged_copy_d2h(mcb_ctx* ctx, void* host, const void* dev, size_t bytes)
     Staging* st = ctx_staging(ctx);
     MCB_CUDA(cudaEventRecord(st->done, ctx->stream));
     MCB_CUDA(cudaStreamWaitEvent(st->copy, st->done, 0));          // the copy stream starts after the producer kernels
-    const int64_t nchunks = (int64_t)ceil_div((int64_t)bytes, (int64_t)Staging::SLOT);
+    const size_t CH = copy_chunk(st->wave_max, bytes);
+    const int64_t nchunks = (int64_t)ceil_div((int64_t)bytes, (int64_t)CH);
     std::atomic<int64_t> next{0};
     const int nt = (int)std::min<int64_t>(st->wave_max, nchunks);
     st->workers->parallel_for(nt, [&](int t) {
@@ -216,7 +227,7 @@ void staged_copy_d2h(mcb_ctx* ctx, void* host, const void* dev, size_t bytes)
         auto issue = [&](int sl) {
             const int64_t c = next.fetch_add(1);
             if (c >= nchunks) { pend[sl] = -1; return; }
-            const size_t a = (size_t)c * Staging::SLOT, n = std::min(Staging::SLOT, bytes - a);
+            const size_t a = (size_t)c * CH, n = std::min(CH, bytes - a);
             MCB_CUDA(cudaMemcpyAsync(st->slot[2 * t + sl], (const char*)dev + a, n, cudaMemcpyDeviceToHost, st->copy));
             MCB_CUDA(cudaEventRecord(st->ev[2 * t + sl], st->copy));
             pend[sl] = c;
@@ -225,7 +236,7 @@ void staged_copy_d2h(mcb_ctx* ctx, void* host, const void* dev, size_t bytes)
         issue(1);
         for (int sl = 0; pend[0] >= 0 || pend[1] >= 0; sl ^= 1) {
             if (pend[sl] < 0) continue;
-            const size_t a = (size_t)pend[sl] * Staging::SLOT, n = std::min(Staging::SLOT, bytes - a);
+            const size_t a = (size_t)pend[sl] * CH, n = std::min(CH, bytes - a);
             MCB_CUDA(cudaEventSynchronize(st->ev[2 * t + sl]));
             memcpy((char*)host + a, st->slot[2 * t + sl], n);
             issue(sl);
