@@ -236,3 +236,33 @@ def test_c2_row_sample_vs_fp64_and_invariants(ctx, oracle):
     deg, odst, _ = oracle.balance(col, K, kx, kb)
     osrc, odst2, ow = oracle.edges_from_balance(deg, odst, K)
     assert np.array_equal(src, cells[osrc]) and np.array_equal(dst, cells[odst2]) and np.array_equal(w, ow)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the fused sampling pass (corsample.cu) on a hard shape: low UMI counts, wide size factors, rare types -- rows whose
+# correlation distribution is far from the bulk's must still get thresholds that land in their candidate window
+# ---------------------------------------------------------------------------------------------------------------
+def test_fused_sampling_on_rare_types_and_low_umi(ctx, oracle):
+    from metacell_b200 import _lib, synth
+    from oracle import oracle_np
+    m = synth.make_umi_matrix(45000, 500, n_types=40, median_umis=600.0, size_sigma=0.6, rare_types=8, seed=77)
+    feats = np.arange(500, dtype=np.int32)
+    K, kx = 100, 10
+    csc = _upload(ctx, m)
+    g = _lib.CGraph.from_csc(ctx, csc, feats, 7.0)
+    g.knn(K, kx)
+    col, cor = g.download_knn()
+    stats = g.knn_stats()
+    cells = g.valid_cells()
+    g.destroy()
+    assert stats["sample_cols"] >= 4096                                    # the fused path was taken
+    assert stats["fallback_rows"] <= 45, stats                              # <= 0.1 % of the rows needed the exact path
+    Z, valid = oracle.features(m.indptr, m.indices, m.data, feat_map_of(m.ngenes, feats), feats.size)
+    assert np.array_equal(cells, np.nonzero(valid)[0])
+    Zv = Z[valid]
+    rare = np.flatnonzero(m.cell_type[valid] < 8)                           # every cell of the rare types + a random sample
+    rows = np.unique(np.concatenate([rare[:200], np.random.default_rng(3).choice(Zv.shape[0], 200, replace=False)]))
+    ocol, ocor = oracle_np.cor_knn_blas(Zv, K * kx + 8, rows=rows)
+    agree = knn_parity(col[rows], cor[rows], ocol, ocor, COR_TOL)
+    print(f"rare types / low UMI: {rows.size} rows ({min(200, rare.size)} of rare types), kNN agreement {agree:.6f}, stats {stats}")
+    assert agree > 0.97
