@@ -1641,6 +1641,7 @@ static mcb_coclust* coclust_run_impl(mcb_ctx* ctx, int32_t N, int64_t n_edges, c
     MCB_CHECK(!(hs[1] & 1), "MC-ERR: edge endpoint out of range");
     MCB_CHECK(!(hs[1] & 2), "MC-ERR: sampled node out of range");
     MCB_CHECK(!(hs[1] & 4), "MC-ERR: each resample index set must be strictly ascending");
+    MCB_CHECK(!(hs[1] & 16), "MC-ERR: the edge table lists a (node1, node2) pair more than once");
     MCB_CHECK(!(hs[1] & 8), "MC-ERR: tgs_graph_cover_resample: knn and method = \"edges\" order every node's out edges, which supports out-degrees up to 1024");
     const int32_t max_out = hs[2], max_in = hs[3];
     // `knn` = the most out edges a node may use inside one resample (R/coclust_graph_cov.r:39-41 passes the graph's AVERAGE

@@ -1080,12 +1080,355 @@ graph_cover_warp_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Incremental variant.  The kernels above re-read all ~400 edges of a node at every visit, although in a converged cover
+// almost no visit changes anything (C3: 90,000 visits and 8,700 moves per resample).  Here every node carries two dense
+// rows in global memory, wout[v][k] = summed weight of v's usable out edges into cluster k and win[v][k] = summed weight
+// of its in edges from cluster k (row stride = the number of clusters the seeding made, rounded up to 32).  A visit is ONE
+// WARP reading the node's two rows (coalesced, address known from the visit order alone) and scoring the clusters present
+// in both; a batch is up to B visits evaluated speculatively side by side as in graph_cover_batch_kernel.  A move of
+// node v from cluster a to b edits the rows of v's neighbours, one thread per edge of v and two reductions each at
+// addresses that need no lookup: an out edge v -> u changes win[u][a], win[u][b]; an in edge u -> v changes wout[u][a],
+// wout[u][b].  All sums are integers: the scores, and with them every decision, are the ones orc_graph_cover computes
+// from the edges (tests/cover_incr_model.c is the host model of this structure, checked against the oracle on the CPU;
+// the kernel is checked bit-exact against the oracle on the GPU).  The number of speculative visits adapts to the move
+// rate (2 while most visits move, B when hardly any does).  Resamples are handed to CTAs through an atomic counter, so
+// the row workspace is per resident CTA, not per resample.
+// ---------------------------------------------------------------------------------------------
+struct IncrWs {
+    uint32_t* rows;                   // [slots][2][N * stride_max]: wout rows, then win rows
+    int32_t* next;                    // work counter, zeroed before the launch
+    int64_t slot_words;               // N * stride_max
+};
+
+template <int B, typename VT, bool TRUNC>
+__global__ void __launch_bounds__(32 * B, B >= 16 ? 2 : 4)
+graph_cover_incr_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict__ resamp_ids, int32_t n_s,
+                        const int32_t* __restrict__ samples, const uint64_t* __restrict__ seeds, int32_t min_size,
+                        double cooling, int32_t burn_in, int32_t max_sweeps, int32_t ncl_cap,
+                        int32_t* __restrict__ mc_all, int32_t* __restrict__ f_all, int32_t* __restrict__ sweeps_out,
+                        int32_t* __restrict__ status, int32_t knn, const uint16_t* __restrict__ ipos, uint16_t* __restrict__ ocut_all,
+                        IncrWs ws)
+{
+    constexpr int NT = 32 * B;
+    static_assert(B <= 32, "one lane per node of a batch");
+    extern __shared__ uint32_t dsm[];
+    int32_t* size = (int32_t*)dsm;                               // [ncl_cap]
+    VT* vlist = (VT*)(dsm + ncl_cap);                            // [n_s]
+    int16_t* mc_s = (int16_t*)(vlist + ((n_s + 1) & ~1));        // [N]
+    __shared__ unsigned long long s_part[NT];
+    __shared__ int s_pk[2][B];                // per-node decision (best cluster, or none), double buffered by batch parity
+    __shared__ int4 s_nd[2][B];               // the node's CSR descriptor, fetched beside the rows for the update that may follow
+    __shared__ int s_pick, s_flag, s_lr;
+    __shared__ unsigned long long s_total;
+    constexpr int NONE = 0x7fffffff;
+
+    const int N = g.N;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t* const wout = ws.rows + (size_t)blockIdx.x * 2 * ws.slot_words;
+    uint32_t* const win = wout + ws.slot_words;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_lr = atomicAdd(ws.next, 1);
+        __syncthreads();
+        const int lr = s_lr;
+        if (lr >= n_local) break;
+#ifdef MCB_COVER_PROF
+        long long pc_t0 = clock64(), pc_seed = 0, pc_build = 0, pc_eval = 0, pc_upd = 0, pc_perm = 0, pc_tmp;
+        int pc_batches = 0, pc_moves = 0, pc_visits = 0, pc_exact = 0;
+#endif
+        const int rid = resamp_ids[lr];
+        const int32_t* S = samples + (int64_t)rid * n_s;
+        const uint64_t seed = seeds[rid];
+        const uint32_t seed_lo = (uint32_t)seed, seed_hi = (uint32_t)(seed >> 32);
+        int32_t* f = f_all + (int64_t)lr * N;
+        uint16_t* ocut = TRUNC ? ocut_all + (int64_t)lr * N : nullptr;
+
+        for (int v = tid; v < N; v += NT) { mc_s[v] = -2; f[v] = 0; }
+        for (int k = tid; k < ncl_cap; k += NT) size[k] = 0;
+        if (tid < B) s_pk[0][tid] = s_pk[1][tid] = NONE;
+        __syncthreads();
+        for (int q = tid; q < n_s; q += NT) mc_s[S[q]] = -1;
+        __syncthreads();
+        for (int q = tid; q < n_s; q += NT) {
+            const int v = S[q];
+            int c = 0;
+            int e = g.optr[v];
+            for (; e < g.optr[v + 1]; ++e) {
+                if (mc_s[g.odst[e]] == -1) { if (TRUNC && c == knn) break; ++c; }
+            }
+            f[v] = c;
+            if (TRUNC) ocut[v] = (uint16_t)(e - g.optr[v]);
+        }
+        __syncthreads();
+
+        // ---- seeding (as graph_cover_batch_kernel) ---------------------------------------------------
+        int ncl = 0;
+        int err = 0;
+        const int chunk = (n_s + NT - 1) / NT;
+        const int q0 = min(n_s, tid * chunk), q1 = min(n_s, q0 + chunk);
+        for (uint32_t iter = 0;; ++iter) {
+            unsigned long long part = 0;
+            for (int q = q0; q < q1; ++q) {
+                const int v = S[q];
+                const int fv = f[v];
+                if (mc_s[v] == -1 && fv >= min_size && fv > 0) part += (unsigned long long)fv * fv * fv;
+            }
+            s_part[tid] = part;
+            __syncthreads();
+            if (tid < 32) {
+                unsigned long long tot = 0;
+                for (int q = lane; q < NT; q += 32) tot += s_part[q];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+                if (lane == 0) { s_total = tot; s_pick = -1; }
+            }
+            __syncthreads();
+            const unsigned long long total = s_total;
+            if (total == 0) break;
+            if (ncl >= ncl_cap) { err = 3; break; }
+            const unsigned long long r = cover_rng_u64(seed_lo, seed_hi, STREAM_SEED, iter, 0) % total;
+            unsigned long long excl = 0;
+            for (int q = 0; q < tid; ++q) excl += s_part[q];
+            if (r >= excl && r < excl + part) {
+                unsigned long long cum = excl;
+                for (int q = q0; q < q1; ++q) {
+                    const int v = S[q];
+                    const int fv = f[v];
+                    if (mc_s[v] == -1 && fv >= min_size && fv > 0) {
+                        cum += (unsigned long long)fv * fv * fv;
+                        if (cum > r) { s_pick = v; break; }
+                    }
+                }
+            }
+            __syncthreads();
+            const int pick = s_pick;
+            const int k = ncl++;
+            if (tid == 0) { mc_s[pick] = (int16_t)k; s_flag = 1; }
+            __syncthreads();
+            const int oe0 = g.optr[pick], oe1 = TRUNC ? oe0 + (int)ocut[pick] : g.optr[pick + 1];
+            for (int e = oe0 + tid; e < oe1; e += NT) {
+                const int u = g.odst[e];
+                if (mc_s[u] == -1) { mc_s[u] = (int16_t)k; atomicAdd(&s_flag, 1); }
+            }
+            __syncthreads();
+            if (tid == 0) size[k] = s_flag;
+            for (int e = oe0 - 1 + wid; e < oe1; e += B) {
+                const int u = (e < oe0) ? pick : g.odst[e];
+                if (mc_s[u] != k || (e >= oe0 && u == pick)) continue;
+                for (int e2 = g.iptr[u] + lane; e2 < g.iptr[u + 1]; e2 += 32) {
+                    const int sn = g.isrc[e2];
+                    if (TRUNC && ipos[e2] >= ocut[sn]) continue;
+                    atomicSub(&f[sn], 1);
+                }
+            }
+            __syncthreads();
+        }
+        if (err) {
+            if (tid == 0) { status[lr] = err; sweeps_out[lr] = 0; }
+            for (int v = tid; v < N; v += NT) mc_all[(int64_t)lr * N + v] = mc_s[v];
+            continue;
+        }
+#ifdef MCB_COVER_PROF
+        pc_seed = clock64() - pc_t0; pc_tmp = clock64();
+#endif
+        // ---- rows of every node from the seeded state: zero, then one warp per sampled node walks its usable out edges
+        // (the edge v -> u with both ends sampled feeds wout[v][cluster of u] and win[u][cluster of v])
+        const int stride = max(32, (ncl + 31) & ~31);
+        {
+            uint4* const z = reinterpret_cast<uint4*>(wout);            // slot_words is a multiple of 32: both halves stay 16-byte aligned
+            const size_t nz = (size_t)N * stride / 4;
+            for (size_t i = tid; i < nz; i += NT) z[i] = make_uint4(0u, 0u, 0u, 0u);
+            uint4* const z2 = reinterpret_cast<uint4*>(win);
+            for (size_t i = tid; i < nz; i += NT) z2[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+        for (int q = wid; q < n_s; q += B) {
+            const int v = S[q];
+            const int4 d = __ldg(g.nd + v);
+            const int nout = TRUNC ? (int)ocut[v] : d.y - d.x;
+            const int kv = (int)mc_s[v];
+            for (int i = lane; i < nout; i += 32) {
+                const int2 p = __ldg(g.oe + d.x + i);
+                const int ku = (int)mc_s[p.x];
+                if (ku == -2) continue;
+                if (ku >= 0) atomicAdd(wout + (size_t)v * stride + ku, (uint32_t)p.y);
+                if (kv >= 0) atomicAdd(win + (size_t)p.x * stride + kv, (uint32_t)p.y);
+            }
+        }
+#ifdef MCB_COVER_PROF
+        __syncthreads();
+        pc_build = clock64() - pc_tmp;
+#endif
+        // ---- reassignment sweeps: up to B speculative visits per batch, one warp each ---------------------
+        uint32_t hb = 1;
+        while ((1ull << (2 * hb)) < (unsigned long long)n_s) ++hb;
+        double factor = 1.0;
+        int sweep = 0;
+        uint32_t parity = 0;
+        int nbc = B;                          // visits of the next batch
+        for (; sweep < max_sweeps; ++sweep) {
+            if (sweep > burn_in) factor = factor * cooling;
+            const float factor_f = (float)factor;
+            uint32_t rk[4];
+            {
+                const uint64_t w0 = cover_rng_u64(seed_lo, seed_hi, STREAM_PERM, (uint32_t)sweep, 0u);
+                const uint64_t w1 = cover_rng_u64(seed_lo, seed_hi, STREAM_PERM, (uint32_t)sweep, 1u);
+                rk[0] = (uint32_t)w0; rk[1] = (uint32_t)(w0 >> 32); rk[2] = (uint32_t)w1; rk[3] = (uint32_t)(w1 >> 32);
+            }
+            __syncthreads();
+#ifdef MCB_COVER_PROF
+            pc_tmp = clock64();
+#endif
+            for (int t = tid; t < n_s; t += NT) vlist[t] = (VT)S[perm_index((uint32_t)t, (uint32_t)n_s, hb, rk)];
+            __syncthreads();
+#ifdef MCB_COVER_PROF
+            pc_perm += clock64() - pc_tmp;
+#endif
+            int moved = 0;
+            int t = 0;
+            while (t < n_s) {
+                const int nb = min(nbc, n_s - t);
+                const uint32_t par = parity & 1u;
+#ifdef MCB_COVER_PROF
+                pc_tmp = clock64(); ++pc_batches; pc_visits += nb;
+#endif
+                // current cluster of the batch's nodes, read before anything in this batch can move (lane j <-> node j)
+                int rcur = -3;
+                if (lane < nb) rcur = (int)mc_s[vlist[t + lane]];
+                if (wid < nb) {
+                    const int v = (int)vlist[t + wid];
+                    const int curk = (int)mc_s[v];
+                    const uint32_t* const ro = wout + (size_t)v * stride + lane;
+                    const uint32_t* const ri = win + (size_t)v * stride + lane;
+                    if (lane == 0) s_nd[par][wid] = __ldg(g.nd + v);
+                    // Scores in fp32 first: the arg-max is decided by them whenever the runner-up is more than 1e-5 (relative)
+                    // behind, far above the 1e-6 the fp32 evaluation can be off by -- the exact fp64 scores (one correctly
+                    // rounded division per candidate, the bulk of a visit's instructions) then order the same way and are
+                    // not needed.  Closer calls, ties included, take the exact path below.
+                    float abest = 0.f, asecond = 0.f; int abk = NONE;
+                    for (int k0 = 0; k0 < stride; k0 += 128) {           // four 32-cluster groups per round, eight loads in flight
+                        uint32_t wo[4], wi[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const bool in = k0 + 32 * j < stride;
+                            wo[j] = in ? __ldcg(ro + k0 + 32 * j) : 0u;
+                            wi[j] = in ? __ldcg(ri + k0 + 32 * j) : 0u;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (wo[j] != 0u && wi[j] != 0u) {
+                                const int k = k0 + 32 * j + lane;
+                                const float sz = (float)size[k];
+                                float sc = __fdividef((float)wo[j] * (float)wi[j], sz * sz);
+                                if (k == curk) sc = sc * factor_f;
+                                if (sc > abest) { asecond = abest; abest = sc; abk = k; }
+                                else if (sc > asecond) asecond = sc;
+                            }
+                        }
+                    }
+                    const float mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(abest)));   // scores are >= 0
+                    const float thr = mx * (1.0f - 1e-5f);
+                    const unsigned m1 = __ballot_sync(0xffffffffu, abest >= thr), m2 = __ballot_sync(0xffffffffu, asecond >= thr);
+                    int bk_node = NONE;
+                    if (mx > 0.f) {
+                        if (m2 == 0u && (m1 & (m1 - 1u)) == 0u) bk_node = __shfl_sync(0xffffffffu, abk, __ffs(m1) - 1);
+                        else {
+#ifdef MCB_COVER_PROF
+                            ++pc_exact;
+#endif
+                            unsigned long long bits = 0ull; int bko = NONE;
+                            for (int k = lane; k < stride; k += 32) {
+                                const uint32_t wo = __ldcg(ro + k - lane), wi = __ldcg(ri + k - lane);
+                                if (wo != 0u && wi != 0u) {
+                                    const double sz = (double)size[k];
+                                    double sc = (double)((unsigned long long)wo * (unsigned long long)wi) / (sz * sz);
+                                    if (k == curk) sc = sc * factor;
+                                    const unsigned long long b2 = (unsigned long long)__double_as_longlong(sc);
+                                    if (b2 > bits || (b2 == bits && k < bko)) { bits = b2; bko = k; }
+                                }
+                            }
+                            const uint32_t hi = (uint32_t)(bits >> 32), lo = (uint32_t)bits;
+                            const uint32_t mh = __reduce_max_sync(0xffffffffu, hi);
+                            const uint32_t ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+                            const bool top = bits != 0ull && hi == mh && lo == ml;
+                            bk_node = (int)__reduce_min_sync(0xffffffffu, top ? (uint32_t)bko : (uint32_t)NONE);
+                        }
+                    }
+                    if (lane == 0) s_pk[par][wid] = bk_node;
+                }
+                __syncthreads();
+#ifdef MCB_COVER_PROF
+                pc_eval += clock64() - pc_tmp; pc_tmp = clock64();
+#endif
+                // resolve: every warp finds the first node of the batch that moves
+                int rk_ = NONE;
+                if (lane < nb) rk_ = s_pk[par][lane];
+                const bool mv = lane < nb && rk_ != NONE && rk_ != rcur;
+                const unsigned mvmask = __ballot_sync(0xffffffffu, mv);
+                parity ^= 1u;
+                if (mvmask == 0u) {
+                    t += nb;
+                    nbc = min(B, 2 * nbc);
+                    continue;
+                }
+                const int js = __ffs(mvmask) - 1;              // the first moving node
+                const int bk = __shfl_sync(0xffffffffu, rk_, js);
+                const int ck = __shfl_sync(0xffffffffu, rcur, js);
+                const int v = (int)vlist[t + js];
+                if (tid == 0) {
+                    if (ck >= 0) size[ck]--;
+                    size[bk]++;
+                    mc_s[v] = (int16_t)bk;
+                }
+                {   // v's out edges are in edges of their targets, v's in edges are out edges of their sources
+                    const int4 d = s_nd[par][js];
+                    const int nout = TRUNC ? (int)ocut[v] : d.y - d.x;
+                    const int nin = d.w - d.z;
+                    for (int it = tid; it < nout + nin; it += NT) {
+                        uint32_t* row;
+                        int2 p;
+                        if (it < nout) {
+                            p = __ldg(g.oe + d.x + it);
+                            if (mc_s[p.x] == -2) continue;
+                            row = win + (size_t)p.x * stride;
+                        } else {
+                            const int ei = d.z + it - nout;
+                            p = __ldg(g.ie + ei);
+                            if (mc_s[p.x] == -2 || (TRUNC && ipos[ei] >= ocut[p.x])) continue;
+                            row = wout + (size_t)p.x * stride;
+                        }
+                        if (ck >= 0) atomicSub(row + ck, (uint32_t)p.y);
+                        atomicAdd(row + bk, (uint32_t)p.y);
+                    }
+                }
+                ++moved;
+                t += js + 1;
+                nbc = max(2, min(B, 2 * (js + 1)));
+                __syncthreads();
+#ifdef MCB_COVER_PROF
+                pc_upd += clock64() - pc_tmp; ++pc_moves;
+#endif
+            }
+            if (moved == 0) { ++sweep; break; }
+        }
+        __syncthreads();
+        for (int v = tid; v < N; v += NT) mc_all[(int64_t)lr * N + v] = mc_s[v];
+        if (tid == 0) { sweeps_out[lr] = sweep; status[lr] = 0; }
+#ifdef MCB_COVER_PROF
+        if (tid == 0 && lr == 0)
+            printf("incr<%d> lr 0: total %lld cyc; seed %lld build %lld perm %lld eval %lld upd %lld; batches %d visits %d moves %d sweeps %d stride %d; exact scores in %d of warp 0's visits\n", B,
+                   clock64() - pc_t0, pc_seed, pc_build, pc_perm, pc_eval, pc_upd, pc_batches, pc_visits, pc_moves, sweep, stride, pc_exact);
+#endif
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // CSR (out and in) of the host's edge table, built on the device: degree count, scan, fill.  The order of a node's
 // edges inside its IN segment is arbitrary (atomic cursors); every consumer only sums integer weights or counts over a
 // segment, so the cover does not depend on it.  OUT segments are ordered by (weight descending, target ascending) when
 // per-node edge truncation (`knn`) is requested.  Also validates what the host loops used to validate.
 // err bits: 1 = edge endpoint out of range, 2 = sampled node out of range, 4 = sample set not strictly ascending,
-// 8 = out segment too long to order.
+// 8 = out segment too long to order, 16 = a (source, target) pair listed twice.
 // ---------------------------------------------------------------------------------------------
 __global__ void edge_degree_kernel(int64_t ne, const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int32_t N,
                                    int32_t* __restrict__ odeg, int32_t* __restrict__ ideg, int32_t* __restrict__ err)
@@ -1147,6 +1490,26 @@ finish_csr_kernel(int32_t N, const int32_t* __restrict__ optr, const int32_t* __
         __syncwarp();
     }
 }
+// err bit 16: some node has two out edges to the same target.  Every cover kernel claims a seed's neighbours with one
+// thread per edge and relies on (source, target) pairs being unique, as they are in any cell graph; a table that repeats
+// a pair is refused instead of being covered differently from the sequential statement.  (Segments longer than
+// COVER_DUP_MAX are not checked.)
+constexpr int COVER_DUP_MAX = 4096;
+__global__ void __launch_bounds__(128)
+dup_edge_kernel(int32_t N, const int32_t* __restrict__ optr, const int32_t* __restrict__ odst, int32_t* __restrict__ err)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int v = blockIdx.x * 4 + wid; v < N; v += gridDim.x * 4) {
+        const int o0 = optr[v], d = optr[v + 1] - o0;
+        bool dup = false;
+        if (d <= COVER_DUP_MAX)
+            for (int q = lane; q < d; q += 32) {
+                const int32_t t = odst[o0 + q];
+                for (int r = 0; r < q; ++r) dup |= odst[o0 + r] == t;
+            }
+        if (__any_sync(0xffffffffu, dup) && lane == 0) atomicOr(err, 16);
+    }
+}
 __global__ void node_desc_kernel(int32_t N, const int32_t* __restrict__ optr, const int32_t* __restrict__ iptr, int4* __restrict__ nd)
 {
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < N; v += gridDim.x * blockDim.x)
@@ -1193,6 +1556,10 @@ void launch_build_cover_csr(mcb_ctx* ctx, int32_t N, int64_t ne, const int32_t* 
     }
     node_desc_kernel<<<std::min(ctx->num_sms, (int)ceil_div(N, 256)), 256, 0, ctx->stream>>>(N, optr, iptr, (int4*)nd);
     MCB_LAUNCH_CHECK();
+    if (ne > 0) {
+        dup_edge_kernel<<<(int)std::min<int64_t>(ceil_div(N, 4), (int64_t)ctx->num_sms * 16), 128, 0, ctx->stream>>>(N, optr, odst, scratch4 + 1);
+        MCB_LAUNCH_CHECK();
+    }
 }
 __global__ void iota_i32_kernel(int32_t* __restrict__ v, int32_t n)
 {
@@ -1402,6 +1769,45 @@ static void launch_cover_warp(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local
     MCB_LAUNCH_CHECK();
 }
 
+// rows: 2 x N x stride_max words per resident CTA.  The CTA count is cut (down to one per SM) until the workspace fits
+// `budget` bytes; returns false when even that does not fit (the caller then takes an edge-reading kernel).
+template <int B, typename VT, bool TRUNC>
+static bool launch_cover_incr_t(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
+                                const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling, int32_t burn_in,
+                                int32_t max_sweeps, int32_t ncl_cap, size_t smem, int32_t* mc, int32_t* f_ws, int32_t* sweeps,
+                                int32_t* status, int32_t knn, const uint16_t* ipos, uint16_t* ocut, size_t budget)
+{
+    static SmemOptIn optin;
+    auto* kern = graph_cover_incr_kernel<B, VT, TRUNC>;
+    ensure_dyn_smem(optin, ctx, kern, smem);
+    int occ = 0;
+    MCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * B, smem));
+    const size_t slot_words = (size_t)fg.N * (size_t)round_up((int64_t)std::max(ncl_cap, 1), 32);
+    int slots = std::max(1, std::min(n_local, std::max(occ, 1) * ctx->num_sms));
+    const size_t fit = budget / (slot_words * 2 * sizeof(uint32_t));
+    if (fit < (size_t)std::min(n_local, ctx->num_sms)) return false;
+    slots = (int)std::min<size_t>((size_t)slots, fit);
+    DevBuf<uint32_t> rows(ctx, (size_t)slots * 2 * slot_words);
+    DevBuf<int32_t> next(ctx, 1);
+    next.zero();
+    const IncrWs ws{rows.p, next.p, (int64_t)slot_words};
+    kern<<<slots, 32 * B, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in, max_sweeps,
+                                                 ncl_cap, mc, f_ws, sweeps, status, knn, ipos, ocut, ws);
+    MCB_LAUNCH_CHECK();
+    return true;
+}
+template <int B, typename VT>
+static bool launch_cover_incr(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
+                              const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling, int32_t burn_in,
+                              int32_t max_sweeps, int32_t ncl_cap, size_t smem, int32_t* mc, int32_t* f_ws, int32_t* sweeps,
+                              int32_t* status, int32_t knn, const uint16_t* ipos, uint16_t* ocut, size_t budget)
+{
+    if (knn > 0) return launch_cover_incr_t<B, VT, true>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,
+                                                         max_sweeps, ncl_cap, smem, mc, f_ws, sweeps, status, knn, ipos, ocut, budget);
+    return launch_cover_incr_t<B, VT, false>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,
+                                             max_sweeps, ncl_cap, smem, mc, f_ws, sweeps, status, 0, nullptr, nullptr, budget);
+}
+
 void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32, const int32_t* iptr32, const void* nd,
                         const void* oe, const void* ie, int32_t max_out, int32_t max_in, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
                         const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling,
@@ -1411,7 +1817,9 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
     // knn > 0: per-node edge truncation is active (the caller passes 0 when knn >= the largest out-degree, where it can never
     // bind).  Only the speculative batch kernels and the general kernel implement it.
     if (n_local == 0) return;
-    // Kernel choice (MCB_COVER_KERNEL overrides for tests/diagnostics: batch2|batch4|batch8|warp8|warp16|warp32|fast|slow):
+    // Kernel choice (MCB_COVER_KERNEL overrides for tests/diagnostics: incr8|incr16|batch2|batch4|batch8|warp8|warp16|warp32|fast|slow):
+    //   incr16  per-node cluster rows edited on moves, 16 speculative visits of one warp each (any degree; needs
+    //           2 x N x clusters words of workspace per resident CTA); incr8 once more resamples are queued than two per SM
     //   batch4  speculative batches of 4 visits, 4 warps per node  (out-degree <= 128, in-degree <= 384)
     //   warp16  speculative batches of 16 visits, 1 warp per node  (out-degree <= 256, any in-degree)
     //   fast    sequential visits, state in shared memory
@@ -1426,6 +1834,24 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
         // resamples are queued than those 2 x num_sms slots the machine is issue-bound and batches of 2 (less
         // speculative waste, four 256-thread CTAs per SM) give more throughput: 500 resamples 99 ms vs 112 ms
         const int auto_b = n_local > 2 * ctx->num_sms ? 2 : 4;
+        {
+            // the row workspace may take a quarter of the device's free memory
+            size_t free_b = 0, total_b = 0;
+            MCB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            const size_t budget = free_b / 4;
+            const bool many = n_local > 2 * ctx->num_sms;
+#define INCR(BB, VT, AUTO)                                                                                                \
+    if ((auto_ && (AUTO)) || want == "incr" #BB) {                                                                        \
+        const size_t ismem = (size_t)ncl_cap * sizeof(uint32_t) + (size_t)((n_s + 1) & ~1) * sizeof(VT) +                 \
+                             (size_t)g.N * sizeof(int16_t) + 16;                                                          \
+        if (ismem <= 200 * 1024 && (sizeof(VT) == 4 || g.N < 65536) &&                                                    \
+            launch_cover_incr<BB, VT>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,      \
+                                      max_sweeps, ncl_cap, ismem, mc, f_ws, sweeps, status, knn, ipos, ocut_ws, budget))  \
+            return;                                                                                                       \
+    }
+            INCR(16, uint16_t, !many) INCR(8, uint16_t, true) INCR(16, int32_t, !many) INCR(8, int32_t, true)
+#undef INCR
+        }
 #define BATCH(BB, OS, IS, VT, AUTO)                                                                                       \
     if ((auto_ && (AUTO)) || want == "batch" #BB) {                                                                      \
         const size_t bsmem = (size_t)(1 + 4 * BB) * ncl_cap * sizeof(uint32_t) + (size_t)((n_s + 1) & ~1) * sizeof(VT) +  \

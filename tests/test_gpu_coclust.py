@@ -45,7 +45,7 @@ def test_cover_assignments_and_counts_bit_exact(ctx, oracle, ncells, K, min_size
     cc.destroy()
 
 
-@pytest.mark.parametrize("kernel", ["auto", "batch2", "batch4", "slow"])
+@pytest.mark.parametrize("kernel", ["auto", "incr8", "incr16", "batch2", "batch4", "slow"])
 @pytest.mark.parametrize("ncells,K,knn,min_size", [(900, 15, 9, 8), (1400, 30, 20, 15)])
 def test_knn_edge_truncation_bit_exact(ctx, oracle, monkeypatch, ncells, K, knn, min_size, kernel):
     """`knn` of tgs_graph_cover_resample (R/coclust_graph_cov.r:39-41): every resample's cover must equal the oracle's cover
@@ -213,10 +213,10 @@ def test_single_graph_cover_and_mc_from_coclust(ctx, oracle, tmp_path):
         api.mcell_mc_from_coclust_balanced("mc3", "nope", "m", 10, 8, ctx=ctx)
 
 
-@pytest.mark.parametrize("kernel", ["batch2", "batch4", "batch8", "warp8", "warp16", "warp32", "fast", "slow"])
+@pytest.mark.parametrize("kernel", ["incr8", "incr16", "batch2", "batch4", "batch8", "warp8", "warp16", "warp32", "fast", "slow"])
 def test_graph_cover_kernel_variants_bit_exact(ctx, oracle, kernel, monkeypatch):
-    """Every cover kernel (speculative 4-warp batches, speculative warp-per-node, sequential shared-memory,
-    sequential global-memory) evaluates the same Gauss-Seidel pass: assignments and sweep counts must equal the
+    """Every cover kernel (incremental per-node cluster tables, speculative 4-warp batches, speculative warp-per-node,
+    sequential shared-memory, sequential global-memory) evaluates the same Gauss-Seidel pass: assignments and sweep counts must equal the
     oracle's for each of them (MCB_COVER_KERNEL forces the choice inside launch_graph_cover)."""
     from metacell_b200 import _lib, synth
     ncells, min_size = 1100, 10
@@ -233,7 +233,7 @@ def test_graph_cover_kernel_variants_bit_exact(ctx, oracle, kernel, monkeypatch)
         assert np.array_equal(mc[r], omc), (kernel, r)
 
 
-@pytest.mark.parametrize("kernel", ["auto", "batch2", "batch4", "warp16", "warp8", "fast", "slow"])
+@pytest.mark.parametrize("kernel", ["auto", "incr8", "incr16", "batch2", "batch4", "warp16", "warp8", "fast", "slow"])
 def test_graph_cover_high_degree_graph(ctx, oracle, kernel, monkeypatch):
     """K = 140 graph (out-degree > 128, in-degree up to 3K as at K = 150 in C4/C5): the wider-slot instantiations
     of the speculative kernels and the 256-thread sequential kernel against the oracle"""
@@ -251,3 +251,17 @@ def test_graph_cover_high_degree_graph(ctx, oracle, kernel, monkeypatch):
         omc, osw = oracle.graph_cover(ncells, csr, sets[r], min_size, 1.05, 10, int(seeds[r]))
         assert sweeps[r] == osw, (kernel, r, sweeps[r], osw)
         assert np.array_equal(mc[r], omc), (kernel, r)
+
+
+def test_duplicate_edges_are_refused(ctx, oracle):
+    """(source, target) pairs are unique in every cell graph and the cover kernels rely on it (one thread per edge claims a
+    seed's neighbours): an edge table that repeats a pair is an MC-ERR, not a silently different cover"""
+    from metacell_b200 import _lib, synth
+    ncells = 800
+    src, dst, w = _graph(oracle, ncells, 14, seed=21)
+    extra = np.random.default_rng(3).choice(src.size, 5, replace=False)
+    src2, dst2, w2 = np.concatenate([src, src[extra]]), np.concatenate([dst, dst[extra]]), np.concatenate([w, w[extra] * 0.5])
+    sets, seeds = synth.resample_sets(ncells, 0.75, 2, 77)
+    with pytest.raises(_lib.McbError, match="MC-ERR.*more than once"):
+        _lib.CoClust(ctx, ncells, src2, dst2, w2, sets, seeds, 8, 1.05, 10)
+    _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, 8, 1.05, 10).destroy()

@@ -252,6 +252,39 @@ def test_coclust_invariants(oracle):
     assert np.array_equal(acc, cnt)
 
 
+def test_incremental_cover_structure_equals_the_oracle(oracle, tmp_path):
+    """tests/cover_incr_model.c is the host model of what graph_cover_incr_kernel keeps (per-node cluster rows edited on
+    moves instead of re-read edges): same assignments and sweep counts as orc_graph_cover, and most visits are not moves
+    (the premise of the kernel)"""
+    import ctypes as C
+    import subprocess
+    from metacell_b200 import synth
+    so = str(tmp_path / "libcover_incr_model.so")
+    here = os.path.dirname(os.path.abspath(__file__))
+    subprocess.check_call(["gcc", "-O2", "-mavx2", "-fopenmp", "-ffp-contract=off", "-fPIC", "-shared", "-o", so,
+                           os.path.join(here, "cover_incr_model.c"), "-lm"])
+    L = C.CDLL(so)
+
+    def p(a, t):
+        return a.ctypes.data_as(C.POINTER(t))
+
+    for ncells, K, min_size in ((240, 8, 5), (700, 20, 10)):
+        N, (src, dst, w) = _graph(oracle, ncells, K)
+        optr, odst, ow, iptr, isrc, iw = csr = oracle.graph_to_csr(N, src, dst, w)
+        sets, seeds = synth.resample_sets(N, 0.75, 3, 5)
+        for r in range(3):
+            mc, sweeps = oracle.graph_cover(N, csr, sets[r], min_size, 1.05, 10, int(seeds[r]))
+            mc2 = np.zeros(N, np.int32); nsw = C.c_int32(0); moves = np.zeros(1000, np.int64)
+            smp = np.ascontiguousarray(sets[r], dtype=np.int32)
+            rc = L.model_graph_cover_incr(C.c_int32(N), p(optr, C.c_int64), p(odst, C.c_int32), p(ow, C.c_uint32), p(iptr, C.c_int64),
+                                          p(isrc, C.c_int32), p(iw, C.c_uint32), C.c_int32(smp.size), p(smp, C.c_int32),
+                                          C.c_int32(min_size), C.c_double(1.05), C.c_int32(10), C.c_uint64(int(seeds[r])),
+                                          C.c_int32(1000), p(mc2, C.c_int32), C.byref(nsw), p(moves, C.c_int64))
+            assert rc == 0
+            assert nsw.value == sweeps and np.array_equal(mc, mc2)
+            assert moves[:sweeps].sum() < 0.5 * sweeps * smp.size and moves[sweeps - 1] == 0
+
+
 # ---- golden vectors -------------------------------------------------------------------------------------
 def test_golden_vectors(oracle):
     g = np.load(GOLDEN)
