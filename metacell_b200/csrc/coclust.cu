@@ -1118,6 +1118,7 @@ graph_cover_incr_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict_
     __shared__ unsigned long long s_part[NT];
     __shared__ int s_pk[2][B];                // per-node decision (best cluster, or none), double buffered by batch parity
     __shared__ int4 s_nd[2][B];               // the node's CSR descriptor, fetched beside the rows for the update that may follow
+    __shared__ int4 s_cand[B][32];            // per warp: {cluster, wout, win} of the clusters present in both rows of its node
     __shared__ int s_pick, s_flag, s_lr;
     __shared__ unsigned long long s_total;
     constexpr int NONE = 0x7fffffff;
@@ -1126,6 +1127,7 @@ graph_cover_incr_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict_
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     uint32_t* const wout = ws.rows + (size_t)blockIdx.x * 2 * ws.slot_words;
     uint32_t* const win = wout + ws.slot_words;
+    const unsigned lt_mask = (1u << lane) - 1u;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_lr = atomicAdd(ws.next, 1);
@@ -1303,9 +1305,11 @@ graph_cover_incr_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict_
                     if (lane == 0) s_nd[par][wid] = __ldg(g.nd + v);
                     // Scores in fp32 first: the arg-max is decided by them whenever the runner-up is more than 1e-5 (relative)
                     // behind, far above the 1e-6 the fp32 evaluation can be off by -- the exact fp64 scores (one correctly
-                    // rounded division per candidate, the bulk of a visit's instructions) then order the same way and are
-                    // not needed.  Closer calls, ties included, take the exact path below.
-                    float abest = 0.f, asecond = 0.f; int abk = NONE;
+                    // rounded division per candidate) then order the same way and are not needed.  Closer calls, ties
+                    // included, take the exact path below.
+                    // the handful of clusters present in both rows are first packed into the warp's candidate list, one
+                    // per lane, so the score arithmetic runs once per visit instead of once per 32-cluster group
+                    int ncand = 0;
                     for (int k0 = 0; k0 < stride; k0 += 128) {           // four 32-cluster groups per round, eight loads in flight
                         uint32_t wo[4], wi[4];
 #pragma unroll
@@ -1316,22 +1320,28 @@ graph_cover_incr_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict_
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
-                            if (wo[j] != 0u && wi[j] != 0u) {
-                                const int k = k0 + 32 * j + lane;
-                                const float sz = (float)size[k];
-                                float sc = __fdividef((float)wo[j] * (float)wi[j], sz * sz);
-                                if (k == curk) sc = sc * factor_f;
-                                if (sc > abest) { asecond = abest; abest = sc; abk = k; }
-                                else if (sc > asecond) asecond = sc;
-                            }
+                            const bool c = wo[j] != 0u && wi[j] != 0u;
+                            const unsigned m = __ballot_sync(0xffffffffu, c);
+                            const int slot = ncand + __popc(m & lt_mask);
+                            if (c && slot < 32) s_cand[wid][slot] = make_int4(k0 + 32 * j + lane, (int)wo[j], (int)wi[j], 0);
+                            ncand += __popc(m);
                         }
                     }
-                    const float mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(abest)));   // scores are >= 0
+                    __syncwarp();
+                    float sc = 0.f; int kc = NONE;
+                    if (lane < ncand) {                                  // (more than 32 candidates: the exact path below)
+                        const int4 c = s_cand[wid][lane];
+                        const float sz = (float)size[c.x];
+                        sc = __fdividef((float)(uint32_t)c.y * (float)(uint32_t)c.z, sz * sz);
+                        if (c.x == curk) sc = sc * factor_f;
+                        kc = c.x;
+                    }
+                    const float mx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(sc)));   // scores are >= 0
                     const float thr = mx * (1.0f - 1e-5f);
-                    const unsigned m1 = __ballot_sync(0xffffffffu, abest >= thr), m2 = __ballot_sync(0xffffffffu, asecond >= thr);
+                    const unsigned m1 = __ballot_sync(0xffffffffu, sc >= thr);
                     int bk_node = NONE;
                     if (mx > 0.f) {
-                        if (m2 == 0u && (m1 & (m1 - 1u)) == 0u) bk_node = __shfl_sync(0xffffffffu, abk, __ffs(m1) - 1);
+                        if (ncand <= 32 && (m1 & (m1 - 1u)) == 0u) bk_node = __shfl_sync(0xffffffffu, kc, __ffs(m1) - 1);
                         else {
 #ifdef MCB_COVER_PROF
                             ++pc_exact;
@@ -1341,9 +1351,9 @@ graph_cover_incr_kernel(FastGraph g, int32_t n_local, const int32_t* __restrict_
                                 const uint32_t wo = __ldcg(ro + k - lane), wi = __ldcg(ri + k - lane);
                                 if (wo != 0u && wi != 0u) {
                                     const double sz = (double)size[k];
-                                    double sc = (double)((unsigned long long)wo * (unsigned long long)wi) / (sz * sz);
-                                    if (k == curk) sc = sc * factor;
-                                    const unsigned long long b2 = (unsigned long long)__double_as_longlong(sc);
+                                    double dsc = (double)((unsigned long long)wo * (unsigned long long)wi) / (sz * sz);
+                                    if (k == curk) dsc = dsc * factor;
+                                    const unsigned long long b2 = (unsigned long long)__double_as_longlong(dsc);
                                     if (b2 > bits || (b2 == bits && k < bko)) { bits = b2; bko = k; }
                                 }
                             }
