@@ -508,7 +508,11 @@ def bench_sub_records(ctx, comm, a, rank, world, peaks):
                    "roofline": {"bound": "latency (neither HBM nor tensor roofline binds: sequential Gauss-Seidel sweeps, SURVEY 8d)",
                                 "node_visits_per_s": visits / (ms * 1e-3), "achieved": edge_bytes / (cover_ms * 1e-3) / 1e9, "peak": hbm,
                                 "unit": "GB/s", "frac": edge_bytes / (cover_ms * 1e-3) / 1e9 / hbm,
-                                "note": "achieved = edge bytes touched by this rank's node visits / graph_cover kernel time (served from L2, not HBM)"},
+                                "kernel": "graph_cover_incr_kernel (per-node cluster rows edited on moves, one warp per speculative visit)",
+                                "ms_per_launch": cover_ms,
+                                "note": "achieved = ALGORITHMIC bytes / graph_cover kernel time: the (K + 3K) packed 8-byte edges the sequential statement "
+                                        "reads at every node visit (SURVEY 8d), this rank's visits.  The kernel itself reads two cluster rows per visit and "
+                                        "edits two entries per edge of a MOVING node; with many resamples resident it is bound by random 32-byte HBM sectors"},
                    "note": "host edge table in, host (node1, node2, cnt) out on rank 0; counters reduced with NCCL inside the library"}
         cc.destroy()
         return rec

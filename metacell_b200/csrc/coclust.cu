@@ -1782,18 +1782,24 @@ static void launch_cover_warp(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local
 // rows: 2 x N x stride_max words per resident CTA.  The CTA count is cut (down to one per SM) until the workspace fits
 // `budget` bytes; returns false when even that does not fit (the caller then takes an edge-reading kernel).
 template <int B, typename VT, bool TRUNC>
-static bool launch_cover_incr_t(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
-                                const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling, int32_t burn_in,
-                                int32_t max_sweeps, int32_t ncl_cap, size_t smem, int32_t* mc, int32_t* f_ws, int32_t* sweeps,
-                                int32_t* status, int32_t knn, const uint16_t* ipos, uint16_t* ocut, size_t budget)
+static int cover_incr_occupancy(mcb_ctx* ctx, size_t smem)
 {
     static SmemOptIn optin;
     auto* kern = graph_cover_incr_kernel<B, VT, TRUNC>;
     ensure_dyn_smem(optin, ctx, kern, smem);
     int occ = 0;
     MCB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * B, smem));
+    return std::max(occ, 1);
+}
+template <int B, typename VT, bool TRUNC>
+static bool launch_cover_incr_t(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
+                                const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling, int32_t burn_in,
+                                int32_t max_sweeps, int32_t ncl_cap, size_t smem, int32_t* mc, int32_t* f_ws, int32_t* sweeps,
+                                int32_t* status, int32_t knn, const uint16_t* ipos, uint16_t* ocut, size_t budget)
+{
+    const int occ = cover_incr_occupancy<B, VT, TRUNC>(ctx, smem);
     const size_t slot_words = (size_t)fg.N * (size_t)round_up((int64_t)std::max(ncl_cap, 1), 32);
-    int slots = std::max(1, std::min(n_local, std::max(occ, 1) * ctx->num_sms));
+    int slots = std::max(1, std::min(n_local, occ * ctx->num_sms));
     const size_t fit = budget / (slot_words * 2 * sizeof(uint32_t));
     if (fit < (size_t)std::min(n_local, ctx->num_sms)) return false;
     slots = (int)std::min<size_t>((size_t)slots, fit);
@@ -1801,21 +1807,41 @@ static bool launch_cover_incr_t(mcb_ctx* ctx, const FastGraph& fg, int32_t n_loc
     DevBuf<int32_t> next(ctx, 1);
     next.zero();
     const IncrWs ws{rows.p, next.p, (int64_t)slot_words};
-    kern<<<slots, 32 * B, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in, max_sweeps,
-                                                 ncl_cap, mc, f_ws, sweeps, status, knn, ipos, ocut, ws);
+    graph_cover_incr_kernel<B, VT, TRUNC><<<slots, 32 * B, smem, ctx->stream>>>(fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling,
+                                                                                 burn_in, max_sweeps, ncl_cap, mc, f_ws, sweeps, status, knn,
+                                                                                 ipos, ocut, ws);
     MCB_LAUNCH_CHECK();
     return true;
 }
-template <int B, typename VT>
-static bool launch_cover_incr(mcb_ctx* ctx, const FastGraph& fg, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
+// want_b: 16 or 8 forced, 0 = by occupancy: 16 warps per CTA unless the resamples need more CTA slots than that gives AND
+// the 8-warp instantiation doubles the CTAs per SM (C3: 500 resamples over 296 slots would run in two waves; C5: both
+// instantiations fit two CTAs per SM, so the larger one keeps twice the warps busy)
+template <typename VT, bool TRUNC>
+static bool launch_cover_incr_v(mcb_ctx* ctx, int want_b, const FastGraph& fg, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
+                                const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling, int32_t burn_in,
+                                int32_t max_sweeps, int32_t ncl_cap, size_t smem, int32_t* mc, int32_t* f_ws, int32_t* sweeps,
+                                int32_t* status, int32_t knn, const uint16_t* ipos, uint16_t* ocut, size_t budget)
+{
+    int b = want_b;
+    if (b == 0) {
+        const int occ16 = cover_incr_occupancy<16, VT, TRUNC>(ctx, smem), occ8 = cover_incr_occupancy<8, VT, TRUNC>(ctx, smem);
+        b = (n_local > occ16 * ctx->num_sms && occ8 >= 2 * occ16) ? 8 : 16;
+    }
+    if (b == 8) return launch_cover_incr_t<8, VT, TRUNC>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in, max_sweeps,
+                                                         ncl_cap, smem, mc, f_ws, sweeps, status, knn, ipos, ocut, budget);
+    return launch_cover_incr_t<16, VT, TRUNC>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in, max_sweeps,
+                                              ncl_cap, smem, mc, f_ws, sweeps, status, knn, ipos, ocut, budget);
+}
+template <typename VT>
+static bool launch_cover_incr(mcb_ctx* ctx, int want_b, const FastGraph& fg, int32_t n_local, const int32_t* resamp_ids, int32_t n_s,
                               const int32_t* samples, const uint64_t* seeds, int32_t min_size, double cooling, int32_t burn_in,
                               int32_t max_sweeps, int32_t ncl_cap, size_t smem, int32_t* mc, int32_t* f_ws, int32_t* sweeps,
                               int32_t* status, int32_t knn, const uint16_t* ipos, uint16_t* ocut, size_t budget)
 {
-    if (knn > 0) return launch_cover_incr_t<B, VT, true>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,
-                                                         max_sweeps, ncl_cap, smem, mc, f_ws, sweeps, status, knn, ipos, ocut, budget);
-    return launch_cover_incr_t<B, VT, false>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,
-                                             max_sweeps, ncl_cap, smem, mc, f_ws, sweeps, status, 0, nullptr, nullptr, budget);
+    if (knn > 0) return launch_cover_incr_v<VT, true>(ctx, want_b, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,
+                                                      max_sweeps, ncl_cap, smem, mc, f_ws, sweeps, status, knn, ipos, ocut, budget);
+    return launch_cover_incr_v<VT, false>(ctx, want_b, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,
+                                          max_sweeps, ncl_cap, smem, mc, f_ws, sweeps, status, 0, nullptr, nullptr, budget);
 }
 
 void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32, const int32_t* iptr32, const void* nd,
@@ -1829,7 +1855,8 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
     if (n_local == 0) return;
     // Kernel choice (MCB_COVER_KERNEL overrides for tests/diagnostics: incr8|incr16|batch2|batch4|batch8|warp8|warp16|warp32|fast|slow):
     //   incr16  per-node cluster rows edited on moves, 16 speculative visits of one warp each (any degree; needs
-    //           2 x N x clusters words of workspace per resident CTA); incr8 once more resamples are queued than two per SM
+    //           2 x N x clusters words of workspace per resident CTA); incr8 when that doubles the CTAs per SM and the
+    //           resamples need the slots
     //   batch4  speculative batches of 4 visits, 4 warps per node  (out-degree <= 128, in-degree <= 384)
     //   warp16  speculative batches of 16 visits, 1 warp per node  (out-degree <= 256, any in-degree)
     //   fast    sequential visits, state in shared memory
@@ -1845,22 +1872,25 @@ void launch_graph_cover(mcb_ctx* ctx, const CoverGraph& g, const int32_t* optr32
         // speculative waste, four 256-thread CTAs per SM) give more throughput: 500 resamples 99 ms vs 112 ms
         const int auto_b = n_local > 2 * ctx->num_sms ? 2 : 4;
         {
-            // the row workspace may take a quarter of the device's free memory
+            // the row workspace may take a quarter of the memory that is free or held by the context's own block cache (so a
+            // repeated call sizes it the same way and finds its block again)
             size_t free_b = 0, total_b = 0;
             MCB_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            const size_t budget = free_b / 4;
-            const bool many = n_local > 2 * ctx->num_sms;
-#define INCR(BB, VT, AUTO)                                                                                                \
-    if ((auto_ && (AUTO)) || want == "incr" #BB) {                                                                        \
-        const size_t ismem = (size_t)ncl_cap * sizeof(uint32_t) + (size_t)((n_s + 1) & ~1) * sizeof(VT) +                 \
-                             (size_t)g.N * sizeof(int16_t) + 16;                                                          \
-        if (ismem <= 200 * 1024 && (sizeof(VT) == 4 || g.N < 65536) &&                                                    \
-            launch_cover_incr<BB, VT>(ctx, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,      \
-                                      max_sweeps, ncl_cap, ismem, mc, f_ws, sweeps, status, knn, ipos, ocut_ws, budget))  \
-            return;                                                                                                       \
-    }
-            INCR(16, uint16_t, !many) INCR(8, uint16_t, true) INCR(16, int32_t, !many) INCR(8, int32_t, true)
-#undef INCR
+            const size_t budget = (free_b + ctx->cached_bytes) / 4;
+            const int want_b = want == "incr16" ? 16 : want == "incr8" ? 8 : auto_ ? 0 : -1;
+            if (want_b >= 0) {
+                const bool small_ids = g.N < 65536;          // 16-bit visit order
+                const size_t ismem = (size_t)ncl_cap * sizeof(uint32_t) + (size_t)((n_s + 1) & ~1) * (small_ids ? 2 : 4) +
+                                     (size_t)g.N * sizeof(int16_t) + 16;
+                if (ismem <= 200 * 1024) {
+                    const bool ok = small_ids
+                        ? launch_cover_incr<uint16_t>(ctx, want_b, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,
+                                                      max_sweeps, ncl_cap, ismem, mc, f_ws, sweeps, status, knn, ipos, ocut_ws, budget)
+                        : launch_cover_incr<int32_t>(ctx, want_b, fg, n_local, resamp_ids, n_s, samples, seeds, min_size, cooling, burn_in,
+                                                     max_sweeps, ncl_cap, ismem, mc, f_ws, sweeps, status, knn, ipos, ocut_ws, budget);
+                    if (ok) return;
+                }
+            }
         }
 #define BATCH(BB, OS, IS, VT, AUTO)                                                                                       \
     if ((auto_ && (AUTO)) || want == "batch" #BB) {                                                                      \
