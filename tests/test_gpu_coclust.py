@@ -265,3 +265,32 @@ def test_duplicate_edges_are_refused(ctx, oracle):
     with pytest.raises(_lib.McbError, match="MC-ERR.*more than once"):
         _lib.CoClust(ctx, ncells, src2, dst2, w2, sets, seeds, 8, 1.05, 10)
     _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, 8, 1.05, 10).destroy()
+
+
+def test_cover_of_a_graph_beyond_shared_memory(ctx, oracle):
+    """100,000 nodes, thousands of clusters: the per-resample state no longer fits shared memory; the resampled cover and
+    tgs_graph_cover (general kernel: assignment in global memory) equal the oracle's"""
+    from metacell_b200 import _lib
+    N, min_size = 100000, 8
+    rng = np.random.default_rng(8)
+    base = np.arange(N, dtype=np.int64)
+    blk = base // 64 * 64
+    src = np.concatenate([base] * 12)
+    dst = np.concatenate([(base + 1) % N, (base + 2) % N] + [blk + rng.integers(0, 64, N) for _ in range(10)]) % N
+    keep = src != dst
+    _, first = np.unique(src[keep] * N + dst[keep], return_index=True)
+    src, dst = src[keep][first].astype(np.int32), dst[keep][first].astype(np.int32)
+    w = rng.random(src.size) * 0.9 + 0.1
+    sets = np.sort(np.stack([rng.choice(N, int(0.75 * N), replace=False) for _ in range(2)]), axis=1).astype(np.int32)
+    seeds = np.array([15, 16], np.uint64)
+    cc = _lib.CoClust(ctx, N, src, dst, w, sets, seeds, min_size, 1.05, 10, method="edges")
+    mc, sweeps = cc.assignments()
+    cc.destroy()
+    csr = oracle.graph_to_csr(N, src, dst, w)
+    for r in range(2):
+        omc, osw = oracle.graph_cover(N, csr, sets[r], min_size, 1.05, 10, int(seeds[r]))
+        assert sweeps[r] == osw and np.array_equal(mc[r], omc), r
+        assert omc.max() > 1000                                    # thousands of clusters
+    cluster, nsw = _lib.graph_cover(ctx, N, src, dst, w, min_size, 1.05, 10, 99)
+    omc, osw = oracle.graph_cover(N, csr, np.arange(N, dtype=np.int32), min_size, 1.05, 10, 99)
+    assert nsw == osw and np.array_equal(cluster, np.where(omc < 0, 0, omc + 1))
