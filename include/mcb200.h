@@ -205,7 +205,8 @@ int  mcb_cgraph_gather_edges(mcb_comm* comm, mcb_cgraph* g, int32_t root, int64_
 int  mcb_coclust_reduce(mcb_comm* comm, mcb_coclust* c, int32_t root);
 
 /* ---- A8: tgs_graph_cover_resample(..., method = "full") ------------------------------------ */
-/* Graph = directed weighted edges (0-based).  samples: [n_resamp][n_s] node ids and one uint64
+/* Graph = directed weighted edges (0-based), every (src, dst) pair listed once as in a tgCellGraph
+ * (MC-ERR otherwise).  samples: [n_resamp][n_s] node ids and one uint64
  * seed per resample, both host-supplied.  Runs the resamples r with r % nranks == rank and
  * accumulates cnt[a][b] (a < b) and nsamp[a] on the device.                                     */
 int  mcb_coclust_run(mcb_ctx* ctx, int32_t N, int64_t n_edges, const int32_t* src, const int32_t* dst,
