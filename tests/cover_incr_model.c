@@ -4,7 +4,9 @@
  * a move of node v from cluster a to cluster b edits two entries in the row of each of v's neighbours.  All sums are
  * integers, so the scores -- and with them every decision -- are the ones orc_graph_cover computes from the edges:
  * tests/test_oracle.py asserts identical assignments and sweep counts, and reads the statistic the kernel rests on
- * (moves per sweep: most visits move nothing).
+ * (moves per sweep: most visits move nothing).  It also replays the kernel's fp32 pre-decision beside every exact
+ * decision: whenever the best fp32 score leads the runner-up by more than 1e-5 (relative) the fp32 arg-max must be the
+ * exact one; the visits that do not clear that margin are the ones the kernel scores in fp64.
  *
  * Includes the oracle's translation unit for its static helpers (Philox stream, keyed permutation).  Seeding is the
  * oracle's own code path restated; only the sweeps differ.
@@ -15,7 +17,9 @@ int model_graph_cover_incr(int32_t N, const int64_t* optr, const int32_t* odst, 
                            const int64_t* iptr, const int32_t* isrc, const uint32_t* iw,
                            int32_t n_s, const int32_t* sample, int32_t min_size, double cooling, int32_t burn_in,
                            uint64_t seed, int32_t max_sweeps, int32_t* mc, int32_t* n_sweeps_out,
-                           int64_t* moves_per_sweep /* [max_sweeps] or NULL */)
+                           int64_t* moves_per_sweep /* [max_sweeps] or NULL */,
+                           int64_t* fp32_stats /* [3] or NULL: visits with a candidate, visits inside the 1e-5 margin (exact
+                                                  path), visits where a clear fp32 decision differs from the exact one */)
 {
     int32_t* f = (int32_t*)calloc((size_t)N, sizeof(int32_t));
     int32_t ncl_cap = n_s / (min_size > 0 ? min_size + 1 : 1) + 2;
@@ -81,6 +85,7 @@ int model_graph_cover_incr(int32_t N, const int64_t* optr, const int32_t* odst, 
         for (int32_t t = 0; t < n_s; ++t) {
             int32_t v = sample[perm_index((uint32_t)t, (uint32_t)n_s, hb, rk)];
             int32_t best = -1; double best_score = 0.0;
+            float fbest = 0.f, fsecond = 0.f; int32_t fk = -1;                       /* the kernel's fp32 pre-decision */
             for (int32_t k = 0; k < ncl; ++k) {
                 const uint32_t wo = wout[(size_t)v * stride + k], wi = win[(size_t)v * stride + k];
                 if (wo == 0 || wi == 0) continue;
@@ -88,6 +93,15 @@ int model_graph_cover_incr(int32_t N, const int64_t* optr, const int32_t* odst, 
                 double sc = (double)((int64_t)wo * (int64_t)wi) / (sz * sz);
                 if (k == mc[v]) sc = sc * factor;
                 if (best < 0 || sc > best_score) { best = k; best_score = sc; }      /* ascending k: ties keep the lower cluster */
+                float szf = (float)size[k];
+                float fs = ((float)wo * (float)wi) / (szf * szf);
+                if (k == mc[v]) fs = fs * (float)factor;
+                if (fs > fbest) { fsecond = fbest; fbest = fs; fk = k; } else if (fs > fsecond) fsecond = fs;
+            }
+            if (fp32_stats && best >= 0) {
+                fp32_stats[0]++;
+                if (fsecond >= fbest * (1.0f - 1e-5f)) fp32_stats[1]++;
+                else if (fk != best) fp32_stats[2]++;
             }
             if (best >= 0 && best != mc[v]) {
                 const int32_t a = mc[v], b = best;

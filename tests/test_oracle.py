@@ -254,8 +254,9 @@ def test_coclust_invariants(oracle):
 
 def test_incremental_cover_structure_equals_the_oracle(oracle, tmp_path):
     """tests/cover_incr_model.c is the host model of what graph_cover_incr_kernel keeps (per-node cluster rows edited on
-    moves instead of re-read edges): same assignments and sweep counts as orc_graph_cover, and most visits are not moves
-    (the premise of the kernel)"""
+    moves instead of re-read edges): same assignments and sweep counts as orc_graph_cover, most visits are not moves
+    (the premise of the kernel), and an fp32 evaluation of the scores decides the arg-max correctly whenever the runner-up
+    is more than 1e-5 behind (the kernel's shortcut; closer calls are scored in fp64)"""
     import ctypes as C
     import subprocess
     from metacell_b200 import synth
@@ -274,13 +275,15 @@ def test_incremental_cover_structure_equals_the_oracle(oracle, tmp_path):
         sets, seeds = synth.resample_sets(N, 0.75, 3, 5)
         for r in range(3):
             mc, sweeps = oracle.graph_cover(N, csr, sets[r], min_size, 1.05, 10, int(seeds[r]))
-            mc2 = np.zeros(N, np.int32); nsw = C.c_int32(0); moves = np.zeros(1000, np.int64)
+            mc2 = np.zeros(N, np.int32); nsw = C.c_int32(0); moves = np.zeros(1000, np.int64); f32 = np.zeros(3, np.int64)
             smp = np.ascontiguousarray(sets[r], dtype=np.int32)
             rc = L.model_graph_cover_incr(C.c_int32(N), p(optr, C.c_int64), p(odst, C.c_int32), p(ow, C.c_uint32), p(iptr, C.c_int64),
                                           p(isrc, C.c_int32), p(iw, C.c_uint32), C.c_int32(smp.size), p(smp, C.c_int32),
                                           C.c_int32(min_size), C.c_double(1.05), C.c_int32(10), C.c_uint64(int(seeds[r])),
-                                          C.c_int32(1000), p(mc2, C.c_int32), C.byref(nsw), p(moves, C.c_int64))
+                                          C.c_int32(1000), p(mc2, C.c_int32), C.byref(nsw), p(moves, C.c_int64), p(f32, C.c_int64))
             assert rc == 0
+            # the kernel's fp32 pre-decision: never wrong when it clears its 1e-5 margin, and it clears it almost always
+            assert f32[0] > 0 and f32[2] == 0 and f32[1] < 0.02 * f32[0], f32
             assert nsw.value == sweeps and np.array_equal(mc, mc2)
             assert moves[:sweeps].sum() < 0.5 * sweeps * smp.size and moves[sweeps - 1] == 0
 
