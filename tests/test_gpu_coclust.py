@@ -294,3 +294,23 @@ def test_cover_of_a_graph_beyond_shared_memory(ctx, oracle):
     cluster, nsw = _lib.graph_cover(ctx, N, src, dst, w, min_size, 1.05, 10, 99)
     omc, osw = oracle.graph_cover(N, csr, np.arange(N, dtype=np.int32), min_size, 1.05, 10, 99)
     assert nsw == osw and np.array_equal(cluster, np.where(omc < 0, 0, omc + 1))
+
+
+@pytest.mark.parametrize("kernel", ["auto", "incr8", "incr16"])
+def test_incremental_cover_with_more_clusters_than_one_load_round(ctx, oracle, kernel, monkeypatch):
+    """more than 128 clusters: the incremental kernel reads a node's cluster rows in several rounds of 128 (the C1 / C3-sized
+    cases stay inside one); assignments, sweep counts and counts against the oracle"""
+    from metacell_b200 import _lib, synth
+    ncells, K, min_size = 3600, 12, 6
+    src, dst, w = _graph(oracle, ncells, K, seed=31)
+    monkeypatch.setenv("MCB_COVER_KERNEL", kernel)
+    sets, seeds = synth.resample_sets(ncells, 0.75, 3, 5)
+    cc = _lib.CoClust(ctx, ncells, src, dst, w, sets, seeds, min_size, 1.05, 10)
+    mc, sweeps = cc.assignments()
+    cc.destroy()
+    csr = oracle.graph_to_csr(ncells, src, dst, w)
+    for r in range(sets.shape[0]):
+        omc, osw = oracle.graph_cover(ncells, csr, sets[r], min_size, 1.05, 10, int(seeds[r]))
+        assert omc.max() + 1 > 128, "the case must need a second round of row loads"
+        assert sweeps[r] == osw, (kernel, r, sweeps[r], osw)
+        assert np.array_equal(mc[r], omc), (kernel, r)
