@@ -335,3 +335,39 @@ def test_truncate_edges_keeps_the_knn_heaviest_sampled_out_edges():
     assert set(zip(ts.tolist(), td.tolist())) == want
     a, b, c = O.truncate_edges(N, src, dst, w, sample, 0)
     assert a.size == sum(1 for s_, d_ in zip(src.tolist(), dst.tolist()) if s_ in inside and d_ in inside)
+
+
+def test_device_form_of_the_knn_rule_equals_truncate_edges():
+    """The cover kernels never build a resample's truncated edge table: out segments are stored by (weight descending,
+    target ascending), a resample keeps ocut[v] = the leading positions of v's segment up to (not including) its
+    (knn+1)-th sampled target, and the edge u -> v is usable iff its position in u's segment is below ocut[u]
+    (coclust.cu: the `ocut` loop of every kernel's set-up, `ipos[e] < ocut[source]`).  Restated here literally and compared
+    with oracle.truncate_edges, the form the oracle's covers are run on."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(11)
+    for N, dens, knn in ((80, 0.25, 5), (120, 0.15, 3), (50, 0.5, 40)):
+        src, dst = np.nonzero(rng.random((N, N)) < dens)
+        keep = src != dst
+        src, dst = src[keep].astype(np.int32), dst[keep].astype(np.int32)
+        w = np.round(rng.random(src.size) * 6) / 6 + 1.0 / 65536               # many tied weights
+        sample = np.sort(rng.choice(N, int(0.75 * N), replace=False)).astype(np.int32)
+        sampled = np.zeros(N, bool); sampled[sample] = True
+        wf = np.maximum(1, np.rint(w * 65536.0)).astype(np.int64)
+        usable = set()
+        for v in range(N):
+            e = np.flatnonzero(src == v)
+            e = e[np.lexsort((dst[e], -wf[e]))]                                # the stored order of v's out segment
+            c, ocut = 0, e.size
+            for pos, ee in enumerate(e):                                      # the kernels' ocut loop
+                if sampled[dst[ee]]:
+                    if c == knn:
+                        ocut = pos
+                        break
+                    c += 1
+            if not sampled[v]:
+                continue                                                      # unsampled nodes have no ocut: none of their edges is ever read
+            for pos, ee in enumerate(e):
+                if pos < ocut and sampled[dst[ee]]:                           # targets outside the sample are skipped at use
+                    usable.add((int(v), int(dst[ee])))
+        ts, td, _ = O.truncate_edges(N, src, dst, w, sample, knn)
+        assert usable == set(zip(ts.tolist(), td.tolist())), (N, knn)
